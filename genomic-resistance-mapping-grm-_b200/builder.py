@@ -1,0 +1,157 @@
+"""KmerMatrixBuilder -- numpy-facing wrapper over the C ABI (one context = one GPU).
+
+Stands where the reference shells out to ``multidsk`` + ``dsk2kover``
+(bin/kover/core/kover/dataset/tools/kmer_count.py:23-53, kmer_pack.py:23-39) and to
+``Ray`` (src/app.py:1310): same parameters, result as arrays instead of temp files.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import native
+from .native import FASTA, FASTQ, GrmkmError  # noqa: F401
+
+
+class KmerMatrixBuilder:
+    def __init__(self, k: int = 31, min_abundance: int = 1, keep_singletons: bool = False,
+                 input_kind: int = FASTA, device: int = -1, bucket_bits: int = 0, flags: int = 0,
+                 stream: int | None = None):
+        self._lib = native.load()
+        self._ctx = C.c_void_p()
+        self._keep = []          # borrowed host buffers must outlive build()
+        self.k = int(k)
+        cfg = native.Config(C.sizeof(native.Config), int(k), int(min_abundance), int(bool(keep_singletons)),
+                            int(input_kind), int(device), int(bucket_bits), int(flags),
+                            C.c_void_p(stream) if stream else None)
+        rc = self._lib.grmkm_create(C.byref(cfg), C.byref(self._ctx))
+        if rc != native.OK:
+            msg = self._lib.grmkm_last_error(None)
+            raise GrmkmError(rc, msg.decode() if msg else "grmkm_create failed")
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self._lib.grmkm_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+        self._keep = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != native.OK:
+            msg = self._lib.grmkm_last_error(self._ctx)
+            raise GrmkmError(rc, msg.decode() if msg else "")
+
+    # -- inputs -----------------------------------------------------------------------------
+    def reset(self):
+        self._check(self._lib.grmkm_reset(self._ctx))
+        self._keep = []
+
+    def add_genome_bytes(self, row: int, data) -> None:
+        """data: bytes / bytearray / memoryview / uint8 ndarray (borrowed until build returns)."""
+        if isinstance(data, np.ndarray):
+            arr = np.ascontiguousarray(data, dtype=np.uint8)
+        else:
+            arr = np.frombuffer(data, dtype=np.uint8)
+        self._keep.append(arr)
+        self._check(self._lib.grmkm_add_genome_bytes(self._ctx, int(row), C.c_void_p(arr.ctypes.data), arr.size))
+
+    def add_genome_device(self, row: int, dev_ptr: int, n_bytes: int) -> None:
+        self._check(self._lib.grmkm_add_genome_device(self._ctx, int(row), C.c_void_p(int(dev_ptr)), int(n_bytes)))
+
+    def add_genome_files(self, row: int, paths: Sequence[str]) -> None:
+        paths = [paths] if isinstance(paths, (str, bytes)) else list(paths)
+        arr = (C.c_char_p * max(len(paths), 1))(*[p.encode() if isinstance(p, str) else p for p in paths])
+        self._check(self._lib.grmkm_add_genome_files(self._ctx, int(row), arr, len(paths)))
+
+    def set_genome_count(self, n: int) -> None:
+        self._check(self._lib.grmkm_set_genome_count(self._ctx, int(n)))
+
+    # -- build + results ----------------------------------------------------------------------
+    def build(self) -> "KmerMatrixBuilder":
+        self._check(self._lib.grmkm_build(self._ctx))
+        return self
+
+    @property
+    def dims(self) -> tuple[int, int, int]:
+        u, w, g = C.c_uint64(), C.c_uint32(), C.c_uint32()
+        self._check(self._lib.grmkm_dims(self._ctx, C.byref(u), C.byref(w), C.byref(g)))
+        return int(u.value), int(w.value), int(g.value)
+
+    @property
+    def stats(self) -> dict:
+        s = native.Stats()
+        self._check(self._lib.grmkm_get_stats(self._ctx, C.byref(s)))
+        return s.asdict()
+
+    @property
+    def times(self) -> dict:
+        t = native.Times()
+        self._check(self._lib.grmkm_stage_times(self._ctx, C.byref(t)))
+        return t.asdict()
+
+    def kmers(self) -> np.ndarray:
+        U, _, _ = self.dims
+        out = np.empty(U, dtype=np.uint64)
+        self._check(self._lib.grmkm_copy_kmers_packed(self._ctx, C.c_void_p(out.ctypes.data), U))
+        return out
+
+    def matrix(self) -> np.ndarray:
+        U, W, _ = self.dims
+        out = np.empty((W, U), dtype=np.uint64)
+        self._check(self._lib.grmkm_copy_matrix(self._ctx, C.c_void_p(out.ctypes.data), U * W))
+        return out
+
+    def kmer_strings(self) -> np.ndarray:
+        U, _, _ = self.dims
+        out = np.empty(U, dtype=f"S{self.k}")
+        self._check(self._lib.grmkm_copy_kmer_strings(self._ctx, C.c_void_p(out.ctypes.data), U * self.k))
+        return out
+
+    def tsv(self, names: Iterable[str]) -> np.ndarray:
+        """Ray Surveyor style KmerMatrix.tsv as a uint8 array (write with .tofile)."""
+        names = [n.encode() if isinstance(n, str) else n for n in names]
+        U, _, G = self.dims
+        if len(names) != G:
+            raise ValueError(f"{len(names)} names for {G} genomes")
+        arr = (C.c_char_p * max(G, 1))(*names)
+        need = C.c_uint64()
+        rc = self._lib.grmkm_format_tsv(self._ctx, arr, None, 0, C.byref(need))
+        if rc not in (native.OK, native.E_CAPACITY):
+            self._check(rc)
+        out = np.empty(int(need.value), dtype=np.uint8)
+        self._check(self._lib.grmkm_format_tsv(self._ctx, arr, C.c_void_p(out.ctypes.data), out.size, C.byref(need)))
+        return out
+
+    def device_result(self) -> tuple[int, int]:
+        a, b = C.c_void_p(), C.c_void_p()
+        self._check(self._lib.grmkm_device_result(self._ctx, C.byref(a), C.byref(b)))
+        return int(a.value or 0), int(b.value or 0)
+
+
+def build_matrix(genomes: Sequence, k: int = 31, min_abundance: int = 1, keep_singletons: bool = False,
+                 input_kind: int = FASTA, **kw):
+    """One-shot helper: genomes = list (row order) of bytes or lists of bytes.  Returns (kmers, matrix, stats)."""
+    with KmerMatrixBuilder(k=k, min_abundance=min_abundance, keep_singletons=keep_singletons,
+                           input_kind=input_kind, **kw) as b:
+        b.set_genome_count(len(genomes))
+        for row, files in enumerate(genomes):
+            if isinstance(files, (bytes, bytearray, memoryview, np.ndarray)):
+                files = [files]
+            for f in files:
+                b.add_genome_bytes(row, f)
+        b.build()
+        return b.kmers(), b.matrix(), b.stats

@@ -1,0 +1,742 @@
+// grmkm_api.cu -- C ABI (include/grmkm.h) and host orchestration of the sm_100a kernels.
+// One context = one GPU.  No CPU fallback: without a device grmkm_create fails.
+#include "../../include/grmkm.h"
+#include "grmkm_kernels.cuh"
+#include "grmkm_synth.cuh"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace grmkm;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct Input {
+    uint32_t row = 0;
+    uint32_t kind = 0;
+    const uint8_t* host = nullptr;
+    const uint8_t* dev = nullptr;
+    uint64_t len = 0;
+    std::vector<uint8_t> owned;
+};
+
+enum Stage { T_START = 0, T_H2D, T_PARSE, T_PACK, T_COUNT, T_SCATTER, T_ABUND, T_AGG, T_SORT, T_N };
+
+}  // namespace
+
+struct grmkm_ctx {
+    grmkm_config cfg{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    std::vector<Input> inputs;
+    uint32_t n_genomes_decl = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+
+    // device buffers (grow-only, reused across builds)
+    DevBuf in, files, hdr0, tsum, tile_file, tile_state, tile_pos, bsum, bstate, bpos, fss, codes, valid, hist,
+        offsets, offsets2, bcounts, records, records2, ukeys, uwords, skeys, sidx_a, sidx_b, shist, kmers, matrix,
+        scalars, fmt, synth;
+    size_t device_bytes = 0;
+
+    cudaEvent_t ev[T_N]{};
+    bool ev_ok = false;
+
+    // result
+    bool built = false;
+    uint64_t U = 0;
+    uint32_t W = 0, G = 0;
+    grmkm_stats stats{};
+    grmkm_times times{};
+
+    // multi-GPU partial state
+    uint32_t part_ranks = 0;
+    std::vector<uint64_t> part_counts;
+    uint32_t cur_bucket_bits = 0;
+};
+
+namespace {
+
+int fail(grmkm_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CU_TRY(c, call)                                                                                   \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail((c), GRMKM_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));           \
+    } while (0)
+
+int ensure(grmkm_ctx* c, DevBuf& b, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return GRMKM_OK;
+    if (b.p) { cudaFree(b.p); c->device_bytes -= b.cap; b.p = nullptr; b.cap = 0; }
+    size_t want = (bytes + 255) & ~size_t(255);
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        return fail(c, GRMKM_E_NOMEM, "cudaMalloc of " + std::to_string(want) + " bytes failed: " + cudaGetErrorString(e));
+    }
+    b.cap = want;
+    c->device_bytes += want;
+    return GRMKM_OK;
+}
+#define ENSURE(c, buf, bytes) do { int r_ = ensure((c), (buf), (bytes)); if (r_) return r_; } while (0)
+
+void release(grmkm_ctx* c, DevBuf& b) {
+    if (b.p) { cudaFree(b.p); c->device_bytes -= b.cap; }
+    b.p = nullptr; b.cap = 0;
+}
+
+uint32_t ceil_log2(uint64_t x) {
+    uint32_t b = 0;
+    while ((1ULL << b) < x) ++b;
+    return b;
+}
+
+struct Launches { uint32_t n = 0; };
+
+int read_file(grmkm_ctx* c, const char* path, std::vector<uint8_t>& out) {
+    const size_t L = strlen(path);
+    const bool gz = L > 3 && strcmp(path + L - 3, ".gz") == 0;
+    if (gz) {
+        gzFile f = gzopen(path, "rb");
+        if (!f) return fail(c, GRMKM_E_IO, std::string("cannot open ") + path);
+        gzbuffer(f, 1 << 20);
+        std::vector<uint8_t> buf(1 << 22);
+        int n;
+        while ((n = gzread(f, buf.data(), (unsigned)buf.size())) > 0) out.insert(out.end(), buf.begin(), buf.begin() + n);
+        const bool bad = n < 0;
+        gzclose(f);
+        if (bad) return fail(c, GRMKM_E_IO, std::string("cannot inflate ") + path);
+        return GRMKM_OK;
+    }
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(c, GRMKM_E_IO, std::string("cannot open ") + path);
+    fseek(f, 0, SEEK_END);
+    long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    if (sz < 0) { fclose(f); return fail(c, GRMKM_E_IO, std::string("cannot size ") + path); }
+    out.resize((size_t)sz);
+    size_t got = sz ? fread(out.data(), 1, (size_t)sz, f) : 0;
+    fclose(f);
+    if (got != (size_t)sz) return fail(c, GRMKM_E_IO, std::string("short read on ") + path);
+    return GRMKM_OK;
+}
+
+struct Plan {
+    uint32_t F = 0, G = 0, W = 0;
+    uint64_t n_tiles = 0, n_sblk = 0, max_stream = 0, n_groups_max = 0, in_bytes = 0;
+    uint32_t bucket_bits = 0, row_bits = 0, slots = 0;
+    size_t agg_smem = 0;
+};
+
+size_t agg_smem_budget(const grmkm_ctx* c) {
+    // leave room for the kernel's static shared memory
+    size_t lim = c->smem_optin ? c->smem_optin : 227 * 1024;
+    return lim - 4096;
+}
+
+// sort columns (ukeys/uwords, n items, stride ucap) by key into kmers/matrix
+int sort_and_gather(grmkm_ctx* c, uint64_t U, uint32_t W, uint64_t ucap, uint32_t key_bits_total, bool keep_order,
+                    Launches& L) {
+    cudaStream_t st = c->stream;
+    ENSURE(c, c->kmers, U * 8);
+    ENSURE(c, c->matrix, (size_t)U * W * 8);
+    if (U == 0) return GRMKM_OK;
+    const uint32_t gblocks = (uint32_t)((U + 255) / 256);
+    if (keep_order) {
+        // identity order: reuse gather with idx = iota produced by a zero-pass "sort"
+        ENSURE(c, c->sidx_a, U * 4);
+        std::vector<uint32_t> iota;  // small helper path, only used with GRMKM_FLAG_HASH_ORDER
+        iota.resize(U);
+        for (uint64_t i = 0; i < U; ++i) iota[i] = (uint32_t)i;
+        CU_TRY(c, cudaMemcpyAsync(c->sidx_a.p, iota.data(), U * 4, cudaMemcpyHostToDevice, st));
+        CU_TRY(c, cudaStreamSynchronize(st));
+        k_gather<<<gblocks, 256, 0, st>>>((const unsigned long long*)c->ukeys.p, (const uint32_t*)c->sidx_a.p, U, W,
+                                          (const unsigned long long*)c->uwords.p, ucap,
+                                          (unsigned long long*)c->kmers.p, (unsigned long long*)c->matrix.p);
+        L.n++;
+        CU_TRY(c, cudaGetLastError());
+        return GRMKM_OK;
+    }
+    const uint32_t n_seg = (uint32_t)((U + kSortSeg - 1) / kSortSeg);
+    const uint32_t sblocks = (n_seg + kSortWarps - 1) / kSortWarps;
+    ENSURE(c, c->skeys, U * 8);
+    ENSURE(c, c->sidx_a, U * 4);
+    ENSURE(c, c->sidx_b, U * 4);
+    ENSURE(c, c->shist, (size_t)256 * n_seg * 4);
+    const uint32_t passes = (key_bits_total + 7) / 8;
+    unsigned long long* ka = (unsigned long long*)c->ukeys.p;
+    unsigned long long* kb = (unsigned long long*)c->skeys.p;
+    uint32_t* ia = nullptr;
+    uint32_t* ib = (uint32_t*)c->sidx_a.p;
+    uint32_t* ispare = (uint32_t*)c->sidx_b.p;
+    for (uint32_t pass = 0; pass < passes; ++pass) {
+        const uint32_t shift = pass * 8;
+        k_sort_hist<<<sblocks, kSortWarps * 32, 0, st>>>(ka, U, shift, n_seg, (uint32_t*)c->shist.p);
+        k_scan_u32<<<1, 1024, 0, st>>>((uint32_t*)c->shist.p, (uint64_t)256 * n_seg);
+        k_sort_scatter<<<sblocks, kSortWarps * 32, 0, st>>>(ka, ia, U, shift, n_seg, (const uint32_t*)c->shist.p, kb, ib);
+        L.n += 3;
+        std::swap(ka, kb);
+        uint32_t* t = ia ? ia : ispare;
+        ia = ib; ib = t;
+    }
+    CU_TRY(c, cudaGetLastError());
+    k_gather<<<gblocks, 256, 0, st>>>(ka, ia, U, W, (const unsigned long long*)c->uwords.p, ucap,
+                                      (unsigned long long*)c->kmers.p, (unsigned long long*)c->matrix.p);
+    L.n++;
+    CU_TRY(c, cudaGetLastError());
+    return GRMKM_OK;
+}
+
+int check_ctx(const grmkm_ctx* c) { return c ? GRMKM_OK : GRMKM_E_INVALID; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int grmkm_abi_version(void) { return GRMKM_ABI_VERSION; }
+
+int grmkm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int grmkm_create(const grmkm_config* cfg, grmkm_ctx** out) {
+    if (!cfg || !out) return fail(nullptr, GRMKM_E_INVALID, "null argument");
+    *out = nullptr;
+    grmkm_config c{};
+    memcpy(&c, cfg, std::min<size_t>(sizeof c, cfg->struct_size ? cfg->struct_size : sizeof c));
+    if (c.k < 1 || c.k > 32)
+        return fail(nullptr, GRMKM_E_UNSUPPORTED_K, "k must be in 1..32 (got " + std::to_string(c.k) + ")");
+    if (c.min_abundance == 0) c.min_abundance = 1;
+    if (c.input_kind > GRMKM_FASTQ) return fail(nullptr, GRMKM_E_INVALID, "input_kind must be GRMKM_FASTA or GRMKM_FASTQ");
+    if (c.bucket_bits && (c.bucket_bits < 4 || c.bucket_bits > 15))
+        return fail(nullptr, GRMKM_E_INVALID, "bucket_bits must be 0 (auto) or 4..15");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, GRMKM_E_NO_DEVICE,
+                    std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "0 devices") +
+                        "); libgrmkm has no CPU fallback");
+    }
+    int dev = c.device;
+    if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+    if (dev >= ndev) return fail(nullptr, GRMKM_E_INVALID, "device ordinal out of range");
+    if ((e = cudaSetDevice(dev)) != cudaSuccess)
+        return fail(nullptr, GRMKM_E_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    grmkm_ctx* x = new (std::nothrow) grmkm_ctx();
+    if (!x) return fail(nullptr, GRMKM_E_NOMEM, "out of host memory");
+    x->cfg = c;
+    x->device = dev;
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) {
+        x->sm_count = prop.multiProcessorCount;
+        x->smem_optin = prop.sharedMemPerBlockOptin;
+    }
+    if (c.stream) x->stream = (cudaStream_t)c.stream;
+    else {
+        if ((e = cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+            delete x;
+            return fail(nullptr, GRMKM_E_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+        }
+        x->own_stream = true;
+    }
+    for (int i = 0; i < T_N; ++i) {
+        if (cudaEventCreate(&x->ev[i]) != cudaSuccess) { x->ev_ok = false; break; }
+        x->ev_ok = true;
+    }
+    *out = x;
+    return GRMKM_OK;
+}
+
+void grmkm_destroy(grmkm_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    DevBuf* all[] = {&c->in, &c->files, &c->hdr0, &c->tsum, &c->tile_file, &c->tile_state, &c->tile_pos, &c->bsum,
+                     &c->bstate, &c->bpos, &c->fss, &c->codes, &c->valid, &c->hist, &c->offsets, &c->offsets2,
+                     &c->bcounts, &c->records, &c->records2, &c->ukeys, &c->uwords, &c->skeys, &c->sidx_a, &c->sidx_b,
+                     &c->shist, &c->kmers, &c->matrix, &c->scalars, &c->fmt, &c->synth};
+    for (DevBuf* b : all) release(c, *b);
+    if (c->ev_ok) for (int i = 0; i < T_N; ++i) cudaEventDestroy(c->ev[i]);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* grmkm_last_error(const grmkm_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int grmkm_reset(grmkm_ctx* c) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    c->inputs.clear();
+    c->n_genomes_decl = 0;
+    c->built = false;
+    c->U = 0; c->W = 0; c->G = 0;
+    c->part_ranks = 0;
+    return GRMKM_OK;
+}
+
+int grmkm_add_genome_bytes(grmkm_ctx* c, uint32_t row, const uint8_t* data, uint64_t n) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    if (!data && n) return fail(c, GRMKM_E_INVALID, "null data");
+    Input in; in.row = row; in.kind = c->cfg.input_kind; in.host = data; in.len = n;
+    c->inputs.push_back(std::move(in));
+    c->built = false;
+    return GRMKM_OK;
+}
+
+int grmkm_add_genome_device(grmkm_ctx* c, uint32_t row, const void* dev_data, uint64_t n) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    if (!dev_data && n) return fail(c, GRMKM_E_INVALID, "null data");
+    if ((uintptr_t)dev_data & 15) return fail(c, GRMKM_E_INVALID, "device input must be 16-byte aligned");
+    Input in; in.row = row; in.kind = c->cfg.input_kind; in.dev = (const uint8_t*)dev_data; in.len = n;
+    c->inputs.push_back(std::move(in));
+    c->built = false;
+    return GRMKM_OK;
+}
+
+int grmkm_add_genome_files(grmkm_ctx* c, uint32_t row, const char* const* paths, int n_paths) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    if (n_paths < 0 || (!paths && n_paths)) return fail(c, GRMKM_E_INVALID, "bad path list");
+    for (int i = 0; i < n_paths; ++i) {
+        Input in; in.row = row; in.kind = c->cfg.input_kind;
+        int r = read_file(c, paths[i], in.owned);
+        if (r) return r;
+        in.len = in.owned.size();
+        c->inputs.push_back(std::move(in));
+        c->inputs.back().host = c->inputs.back().owned.data();
+    }
+    c->built = false;
+    return GRMKM_OK;
+}
+
+int grmkm_set_genome_count(grmkm_ctx* c, uint32_t n) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    c->n_genomes_decl = n;
+    return GRMKM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the build
+// ------------------------------------------------------------------------------------------------
+static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/) {
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    Launches L;
+    c->built = false;
+    c->stats = grmkm_stats{};
+    c->times = grmkm_times{};
+
+    Plan P;
+    P.F = (uint32_t)c->inputs.size();
+    uint32_t maxrow = 0;
+    for (const Input& in : c->inputs) maxrow = std::max(maxrow, in.row + 1);
+    P.G = std::max(maxrow, c->n_genomes_decl);
+    P.W = (P.G + 63) / 64;
+    c->G = P.G; c->W = P.W; c->U = 0;
+    if (P.G == 0 || P.F == 0) {
+        c->built = true;
+        c->stats.n_genomes = P.G; c->stats.n_words = P.W;
+        return GRMKM_OK;
+    }
+    P.row_bits = std::max(1u, ceil_log2(P.G));
+    if (P.row_bits > 15) return fail(c, GRMKM_E_UNSUPPORTED, "more than 32768 genomes in one context");
+
+    // ---- file table, staging offsets, tiles
+    std::vector<FileDesc> fds(P.F);
+    std::vector<uint64_t> stage_off(P.F, 0);
+    std::vector<uint64_t> row_bytes(P.G, 0);
+    uint64_t stage_total = 0, tiles = 0;
+    for (uint32_t f = 0; f < P.F; ++f) {
+        const Input& in = c->inputs[f];
+        if (!in.dev) { stage_off[f] = stage_total; stage_total += (in.len + 15) & ~15ULL; }
+        fds[f].len = in.len; fds[f].row = in.row; fds[f].kind = in.kind; fds[f].tile_begin = tiles;
+        tiles += std::max<uint64_t>(1, (in.len + kTileBytes - 1) / kTileBytes);
+        P.max_stream += in.len;
+        row_bytes[in.row] += in.len;
+    }
+    P.in_bytes = P.max_stream;
+    P.n_tiles = tiles;
+    P.n_sblk = (tiles + kScanTilesPerBlock - 1) / kScanTilesPerBlock;
+    P.n_groups_max = P.max_stream / 32 + 2;
+    if (P.n_tiles > 0x7fffffffULL) return fail(c, GRMKM_E_UNSUPPORTED, "input too large for one build (tile count)");
+
+    // ---- aggregate table geometry and bucket count
+    const uint32_t Wtab = P.W;
+    const size_t budget = agg_smem_budget(c);
+    P.slots = (uint32_t)(budget / (8 * (1 + (size_t)Wtab)));
+    if (P.slots < 256) return fail(c, GRMKM_E_UNSUPPORTED, "too many genomes for the shared-memory column table");
+    P.slots = std::min(P.slots, 16384u);
+    P.agg_smem = (size_t)P.slots * 8 * (1 + Wtab);
+    if (c->cfg.bucket_bits) P.bucket_bits = c->cfg.bucket_bits;
+    else {
+        const uint64_t max_row = *std::max_element(row_bytes.begin(), row_bytes.end());
+        const uint64_t u_est = 3 * max_row + 1024;
+        const uint64_t per = std::max<uint64_t>(1, P.slots / 2);
+        P.bucket_bits = std::min(15u, std::max(6u, ceil_log2((u_est + per - 1) / per)));
+    }
+    P.bucket_bits = std::max(P.bucket_bits, P.row_bits);
+    if (P.bucket_bits > 15) return fail(c, GRMKM_E_UNSUPPORTED, "bucket_bits > 15");
+    c->cur_bucket_bits = P.bucket_bits;
+    const uint32_t B = 1u << P.bucket_bits;
+
+    // ---- device buffers
+    ENSURE(c, c->scalars, S_COUNT * 8);
+    ENSURE(c, c->in, stage_total);
+    ENSURE(c, c->files, P.F * sizeof(FileDesc));
+    ENSURE(c, c->hdr0, P.F * 8);
+    ENSURE(c, c->fss, (P.F + 1) * 8);
+    ENSURE(c, c->tsum, P.n_tiles * sizeof(Sum));
+    ENSURE(c, c->tile_file, P.n_tiles * 4);
+    ENSURE(c, c->tile_state, P.n_tiles);
+    ENSURE(c, c->tile_pos, P.n_tiles * 8);
+    ENSURE(c, c->bsum, P.n_sblk * sizeof(Sum));
+    ENSURE(c, c->bstate, P.n_sblk * 4);
+    ENSURE(c, c->bpos, P.n_sblk * 8);
+    ENSURE(c, c->codes, P.n_groups_max * 8);
+    ENSURE(c, c->valid, P.n_groups_max * 4);
+    ENSURE(c, c->hist, (size_t)B * 8);
+    ENSURE(c, c->offsets, (size_t)(B + 1) * 8);
+    ENSURE(c, c->records, P.max_stream * 8);
+
+    if (c->ev_ok) cudaEventRecord(c->ev[T_START], st);
+    // ---- stage host inputs
+    uint64_t h2d = 0;
+    for (uint32_t f = 0; f < P.F; ++f) {
+        const Input& in = c->inputs[f];
+        if (in.dev) fds[f].ptr = in.dev;
+        else {
+            fds[f].ptr = (const uint8_t*)c->in.p + stage_off[f];
+            if (in.len) {
+                CU_TRY(c, cudaMemcpyAsync((void*)fds[f].ptr, in.host, in.len, cudaMemcpyHostToDevice, st));
+                h2d += in.len;
+            }
+        }
+    }
+    CU_TRY(c, cudaMemcpyAsync(c->files.p, fds.data(), P.F * sizeof(FileDesc), cudaMemcpyHostToDevice, st));
+    CU_TRY(c, cudaMemsetAsync(c->scalars.p, 0, S_COUNT * 8, st));
+    CU_TRY(c, cudaMemsetAsync(c->codes.p, 0, P.n_groups_max * 8, st));
+    CU_TRY(c, cudaMemsetAsync(c->valid.p, 0, P.n_groups_max * 4, st));
+    CU_TRY(c, cudaMemsetAsync(c->hist.p, 0, (size_t)B * 8, st));
+    if (c->ev_ok) cudaEventRecord(c->ev[T_H2D], st);
+
+    const FileDesc* d_files = (const FileDesc*)c->files.p;
+    uint64_t* d_scalars = (uint64_t*)c->scalars.p;
+
+    // ---- parse
+    k_first_header<<<(P.F * 32 + 255) / 256, 256, 0, st>>>(d_files, P.F, (uint64_t*)c->hdr0.p);
+    k_tile_summary<<<(uint32_t)P.n_tiles, kParseThreads, 0, st>>>(d_files, P.F, (const uint64_t*)c->hdr0.p, P.n_tiles,
+                                                                  (Sum*)c->tsum.p, (uint32_t*)c->tile_file.p);
+    k_scan_reduce<<<(uint32_t)P.n_sblk, kParseThreads, 0, st>>>((const Sum*)c->tsum.p, P.n_tiles, (Sum*)c->bsum.p);
+    k_scan_blocks<<<1, 1024, 0, st>>>((const Sum*)c->bsum.p, (uint32_t)P.n_sblk, (uint32_t*)c->bstate.p,
+                                      (uint64_t*)c->bpos.p, d_scalars, (uint64_t*)c->fss.p, P.F);
+    k_scan_apply<<<(uint32_t)P.n_sblk, kParseThreads, 0, st>>>((const Sum*)c->tsum.p, P.n_tiles,
+                                                               (const uint32_t*)c->bstate.p, (const uint64_t*)c->bpos.p,
+                                                               (const uint32_t*)c->tile_file.p, d_files,
+                                                               (uint8_t*)c->tile_state.p, (uint64_t*)c->tile_pos.p,
+                                                               (uint64_t*)c->fss.p);
+    L.n += 5;
+    CU_TRY(c, cudaGetLastError());
+    if (c->ev_ok) cudaEventRecord(c->ev[T_PARSE], st);
+    k_pack<<<(uint32_t)P.n_tiles, kParseThreads, 0, st>>>(d_files, P.F, (const uint64_t*)c->hdr0.p, P.n_tiles,
+                                                          (const uint8_t*)c->tile_state.p, (const uint64_t*)c->tile_pos.p,
+                                                          (unsigned long long*)c->codes.p, (uint32_t*)c->valid.p, d_scalars);
+    L.n++;
+    CU_TRY(c, cudaGetLastError());
+    if (c->ev_ok) cudaEventRecord(c->ev[T_PACK], st);
+
+    // ---- extract: count, offsets, scatter
+    ExtractParams ep{};
+    ep.codes = (const unsigned long long*)c->codes.p;
+    ep.valid = (const uint32_t*)c->valid.p;
+    ep.scalars = d_scalars;
+    ep.file_stream_start = (const uint64_t*)c->fss.p;
+    ep.files = d_files;
+    ep.n_files = P.F;
+    ep.k = c->cfg.k;
+    ep.bucket_bits = P.bucket_bits;
+    ep.row_bits = P.row_bits;
+    ep.hist = (unsigned long long*)c->hist.p;
+    ep.records = (unsigned long long*)c->records.p;
+    const uint64_t n_etiles_max = (P.n_groups_max + kExtractThreads - 1) / kExtractThreads;
+    const uint32_t egrid = (uint32_t)std::min<uint64_t>(n_etiles_max, (uint64_t)c->sm_count * 8);
+    const size_t hist_smem = (size_t)B * 4;
+    CU_TRY(c, cudaFuncSetAttribute(k_extract<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
+    k_extract<0><<<egrid, kExtractThreads, hist_smem, st>>>(ep);
+    k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->hist.p, (unsigned long long*)c->offsets.p, B, d_scalars,
+                                         S_N_WINDOWS);
+    L.n += 2;
+    CU_TRY(c, cudaGetLastError());
+    if (c->ev_ok) cudaEventRecord(c->ev[T_COUNT], st);
+    k_extract<1><<<egrid, kExtractThreads, 0, st>>>(ep);
+    L.n++;
+    CU_TRY(c, cudaGetLastError());
+    if (c->ev_ok) cudaEventRecord(c->ev[T_SCATTER], st);
+
+    // ---- optional abundance filter (reads: -abundance-min, kmer_count.py:48)
+    const unsigned long long* agg_records = (const unsigned long long*)c->records.p;
+    const unsigned long long* agg_offsets = (const unsigned long long*)c->offsets.p;
+    const uint32_t agrid = std::min<uint32_t>(B, (uint32_t)c->sm_count);
+    if (c->cfg.min_abundance > 1) {
+        ENSURE(c, c->records2, P.max_stream * 8);
+        ENSURE(c, c->bcounts, (size_t)B * 8);
+        ENSURE(c, c->offsets2, (size_t)(B + 1) * 8);
+        AggParams ap{};
+        ap.records = agg_records; ap.offsets = agg_offsets; ap.B = B; ap.bucket_bits = P.bucket_bits;
+        ap.row_bits = P.row_bits; ap.n_words = 1;
+        ap.slots = (uint32_t)std::min<size_t>(16384, budget / 16);
+        ap.mode = 2; ap.min_abundance = c->cfg.min_abundance;
+        ap.scalars = (unsigned long long*)d_scalars;
+        ap.bucket_out_counts = (unsigned long long*)c->bcounts.p;
+        ap.out_records = (unsigned long long*)c->records2.p;
+        const size_t sm = (size_t)ap.slots * 16;
+        CU_TRY(c, cudaFuncSetAttribute(k_aggregate<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        k_aggregate<2><<<agrid, kAggThreads, sm, st>>>(ap);
+        k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->bcounts.p, (unsigned long long*)c->offsets2.p, B,
+                                             d_scalars, S_N_SOLID);
+        k_compact_records<<<agrid * 4, 256, 0, st>>>((const unsigned long long*)c->records2.p, agg_offsets,
+                                                     (const unsigned long long*)c->offsets2.p, B,
+                                                     (unsigned long long*)c->records.p);
+        L.n += 3;
+        CU_TRY(c, cudaGetLastError());
+        agg_offsets = (const unsigned long long*)c->offsets2.p;
+    }
+    if (c->ev_ok) cudaEventRecord(c->ev[T_ABUND], st);
+
+    // ---- aggregate (dsk2kover): retry with a larger output if the first guess was too small
+    uint64_t ucap = std::min<uint64_t>(P.max_stream, std::max<uint64_t>(1 << 16, P.max_stream / 4));
+    ucap = std::min<uint64_t>(ucap, 0xFFFFFFFFULL);
+    uint64_t sc[S_COUNT];
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        ENSURE(c, c->ukeys, ucap * 8);
+        ENSURE(c, c->uwords, (size_t)ucap * P.W * 8);
+        if (mode == 1) { ENSURE(c, c->bcounts, (size_t)B * 8); CU_TRY(c, cudaMemsetAsync(c->bcounts.p, 0, (size_t)B * 8, st)); }
+        AggParams ap{};
+        ap.records = agg_records; ap.offsets = agg_offsets; ap.B = B; ap.bucket_bits = P.bucket_bits;
+        ap.row_bits = P.row_bits; ap.n_words = P.W; ap.slots = P.slots;
+        ap.keep_singletons = c->cfg.keep_singletons; ap.mode = mode;
+        ap.out_keys = (unsigned long long*)c->ukeys.p; ap.out_words = (unsigned long long*)c->uwords.p;
+        ap.cap = ucap; ap.scalars = (unsigned long long*)d_scalars;
+        ap.bucket_out_counts = (unsigned long long*)c->bcounts.p;
+        if (mode == 0) {
+            CU_TRY(c, cudaFuncSetAttribute(k_aggregate<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.agg_smem));
+            k_aggregate<0><<<agrid, kAggThreads, P.agg_smem, st>>>(ap);
+        } else {
+            CU_TRY(c, cudaFuncSetAttribute(k_aggregate<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.agg_smem));
+            k_aggregate<1><<<agrid, kAggThreads, P.agg_smem, st>>>(ap);
+        }
+        L.n++;
+        CU_TRY(c, cudaGetLastError());
+        CU_TRY(c, cudaMemcpyAsync(sc, d_scalars, sizeof sc, cudaMemcpyDeviceToHost, st));
+        CU_TRY(c, cudaStreamSynchronize(st));
+        if (sc[S_U_NEEDED] <= ucap) break;
+        if (attempt == 1 || sc[S_U_NEEDED] > 0xFFFFFFFFULL)
+            return fail(c, GRMKM_E_UNSUPPORTED, "more than 2^32 columns in one context");
+        ucap = sc[S_U_NEEDED];
+        const uint64_t zero3[3] = {0, 0, 0};
+        CU_TRY(c, cudaMemcpyAsync(d_scalars + S_U_NEEDED, zero3, 3 * 8, cudaMemcpyHostToDevice, st));
+    }
+    if (c->ev_ok) cudaEventRecord(c->ev[T_AGG], st);
+    const uint64_t U = sc[S_U_NEEDED];
+
+    // ---- final order + gather
+    if (mode == 0) {
+        int r = sort_and_gather(c, U, P.W, ucap, 2 * c->cfg.k, (c->cfg.flags & GRMKM_FLAG_HASH_ORDER) != 0, L);
+        if (r) return r;
+    }
+    if (c->ev_ok) cudaEventRecord(c->ev[T_SORT], st);
+    CU_TRY(c, cudaStreamSynchronize(st));
+
+    c->U = U;
+    c->built = (mode == 0);
+    grmkm_stats& s = c->stats;
+    s.n_input_bytes = P.in_bytes;
+    s.n_records = sc[S_N_RECORDS];
+    s.n_bases = sc[S_STREAM_LEN] - sc[S_N_RECORDS];
+    s.n_windows = sc[S_N_WINDOWS];
+    s.n_kmers = U;
+    s.n_distinct = sc[S_N_DISTINCT];
+    s.n_words = P.W; s.n_genomes = P.G; s.n_buckets = B;
+    s.n_launches = L.n;
+    s.h2d_bytes = h2d;
+    s.device_bytes = c->device_bytes;
+    s.n_splits = sc[S_N_SPLITS];
+    if (c->ev_ok) {
+        float* t[] = {&c->times.h2d, &c->times.parse, &c->times.pack, &c->times.count, &c->times.scatter,
+                      &c->times.abundance, &c->times.aggregate, &c->times.sort};
+        for (int i = 1; i < T_N; ++i) cudaEventElapsedTime(t[i - 1], c->ev[i - 1], c->ev[i]);
+        cudaEventElapsedTime(&c->times.total, c->ev[T_START], c->ev[T_SORT]);
+    }
+    return GRMKM_OK;
+}
+
+int grmkm_build(grmkm_ctx* c) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    return build_impl(c, 0);
+}
+
+int grmkm_dims(const grmkm_ctx* c, uint64_t* n_kmers, uint32_t* n_words, uint32_t* n_genomes) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    if (!c->built) return fail(const_cast<grmkm_ctx*>(c), GRMKM_E_INVALID, "no result: call grmkm_build first");
+    if (n_kmers) *n_kmers = c->U;
+    if (n_words) *n_words = c->W;
+    if (n_genomes) *n_genomes = c->G;
+    return GRMKM_OK;
+}
+
+int grmkm_get_stats(const grmkm_ctx* c, grmkm_stats* out) {
+    if (check_ctx(c) || !out) return GRMKM_E_INVALID;
+    *out = c->stats;
+    out->device_bytes = c->device_bytes;
+    return GRMKM_OK;
+}
+
+int grmkm_stage_times(const grmkm_ctx* c, grmkm_times* out) {
+    if (check_ctx(c) || !out) return GRMKM_E_INVALID;
+    *out = c->times;
+    return GRMKM_OK;
+}
+
+int grmkm_copy_kmers_packed(grmkm_ctx* c, uint64_t* dst, uint64_t cap) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    if (!c->built) return fail(c, GRMKM_E_INVALID, "no result: call grmkm_build first");
+    if (cap < c->U) return fail(c, GRMKM_E_CAPACITY, "kmers buffer too small");
+    if (!c->U) return GRMKM_OK;
+    if (!dst) return fail(c, GRMKM_E_INVALID, "null dst");
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaMemcpyAsync(dst, c->kmers.p, c->U * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return GRMKM_OK;
+}
+
+int grmkm_copy_matrix(grmkm_ctx* c, uint64_t* dst, uint64_t cap) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    if (!c->built) return fail(c, GRMKM_E_INVALID, "no result: call grmkm_build first");
+    const uint64_t n = c->U * c->W;
+    if (cap < n) return fail(c, GRMKM_E_CAPACITY, "matrix buffer too small");
+    if (!n) return GRMKM_OK;
+    if (!dst) return fail(c, GRMKM_E_INVALID, "null dst");
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaMemcpyAsync(dst, c->matrix.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return GRMKM_OK;
+}
+
+int grmkm_copy_kmer_strings(grmkm_ctx* c, char* dst, uint64_t cap) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    if (!c->built) return fail(c, GRMKM_E_INVALID, "no result: call grmkm_build first");
+    const uint32_t k = c->cfg.k;
+    const uint64_t n = c->U * k;
+    if (cap < n) return fail(c, GRMKM_E_CAPACITY, "kmer string buffer too small");
+    if (!n) return GRMKM_OK;
+    if (!dst) return fail(c, GRMKM_E_INVALID, "null dst");
+    CU_TRY(c, cudaSetDevice(c->device));
+    const uint64_t rows_per = std::max<uint64_t>(1, (256ULL << 20) / k);
+    ENSURE(c, c->fmt, std::min<uint64_t>(n, rows_per * k));
+    for (uint64_t j0 = 0; j0 < c->U; j0 += rows_per) {
+        const uint64_t rows = std::min(rows_per, c->U - j0), nb = rows * k;
+        k_kmer_strings<<<(uint32_t)((nb + 255) / 256), 256, 0, c->stream>>>((const unsigned long long*)c->kmers.p, j0, nb,
+                                                                            k, (char*)c->fmt.p);
+        CU_TRY(c, cudaGetLastError());
+        CU_TRY(c, cudaMemcpyAsync(dst + j0 * k, c->fmt.p, nb, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    return GRMKM_OK;
+}
+
+int grmkm_format_tsv(grmkm_ctx* c, const char* const* names, char* dst, uint64_t cap, uint64_t* written) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    if (!c->built) return fail(c, GRMKM_E_INVALID, "no result: call grmkm_build first");
+    if (!names && c->G) return fail(c, GRMKM_E_INVALID, "null names");
+    const uint32_t k = c->cfg.k, G = c->G;
+    uint64_t hdr = 5;
+    for (uint32_t g = 0; g < G; ++g) {
+        if (!names[g]) return fail(c, GRMKM_E_INVALID, "null name");
+        hdr += 1 + strlen(names[g]);
+    }
+    hdr += 1;
+    const uint64_t roww = (uint64_t)k + 2ULL * G + 1;
+    const uint64_t need = hdr + roww * c->U;
+    if (written) *written = need;
+    if (!dst || cap < need) return fail(c, GRMKM_E_CAPACITY, "tsv buffer too small");
+    char* p = dst;
+    memcpy(p, "kmers", 5); p += 5;
+    for (uint32_t g = 0; g < G; ++g) { *p++ = '\t'; size_t l = strlen(names[g]); memcpy(p, names[g], l); p += l; }
+    *p++ = '\n';
+    if (!c->U) return GRMKM_OK;
+    CU_TRY(c, cudaSetDevice(c->device));
+    const uint64_t rows_per = std::max<uint64_t>(1, (256ULL << 20) / roww);
+    ENSURE(c, c->fmt, std::min<uint64_t>(roww * c->U, rows_per * roww));
+    for (uint64_t j0 = 0; j0 < c->U; j0 += rows_per) {
+        const uint64_t rows = std::min(rows_per, c->U - j0), nb = rows * roww;
+        k_format_tsv<<<(uint32_t)((nb + 255) / 256), 256, 0, c->stream>>>((const unsigned long long*)c->kmers.p,
+                                                                          (const unsigned long long*)c->matrix.p, c->U, G,
+                                                                          k, j0, nb, (char*)c->fmt.p);
+        CU_TRY(c, cudaGetLastError());
+        CU_TRY(c, cudaMemcpyAsync(p + j0 * roww, c->fmt.p, nb, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    return GRMKM_OK;
+}
+
+int grmkm_device_result(const grmkm_ctx* c, const uint64_t** d_kmers, const uint64_t** d_matrix) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    if (!c->built) return fail(const_cast<grmkm_ctx*>(c), GRMKM_E_INVALID, "no result: call grmkm_build first");
+    if (d_kmers) *d_kmers = (const uint64_t*)c->kmers.p;
+    if (d_matrix) *d_matrix = (const uint64_t*)c->matrix.p;
+    return GRMKM_OK;
+}
+
+int grmkm_synth_fasta_device(grmkm_ctx* c, const void* layout, uint64_t layout_bytes, void* dev_dst, uint64_t dst_bytes) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    if (!layout || !dev_dst) return fail(c, GRMKM_E_INVALID, "null argument");
+    CU_TRY(c, cudaSetDevice(c->device));
+    ENSURE(c, c->synth, layout_bytes);
+    CU_TRY(c, cudaMemcpyAsync(c->synth.p, layout, layout_bytes, cudaMemcpyHostToDevice, c->stream));
+    std::string msg;
+    if (!synth_launch((const uint8_t*)layout, layout_bytes, (const uint8_t*)c->synth.p, (uint8_t*)dev_dst, dst_bytes,
+                      c->stream, msg))
+        return fail(c, GRMKM_E_INVALID, msg);
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return GRMKM_OK;
+}
+
+int grmkm_build_partial(grmkm_ctx* c, uint32_t n_ranks, uint64_t* counts) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    (void)n_ranks; (void)counts;
+    return fail(c, GRMKM_E_UNSUPPORTED, "grmkm_build_partial: not implemented yet");
+}
+int grmkm_export_partials(grmkm_ctx* c, void* dev_dst, uint64_t dst_bytes) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    (void)dev_dst; (void)dst_bytes;
+    return fail(c, GRMKM_E_UNSUPPORTED, "grmkm_export_partials: not implemented yet");
+}
+int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, uint32_t rank, const uint64_t* src_counts,
+                         const uint32_t* src_words, uint32_t total_genomes) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    (void)dev_parts; (void)n_ranks; (void)rank; (void)src_counts; (void)src_words; (void)total_genomes;
+    return fail(c, GRMKM_E_UNSUPPORTED, "grmkm_merge_partials: not implemented yet");
+}
+
+}  // extern "C"

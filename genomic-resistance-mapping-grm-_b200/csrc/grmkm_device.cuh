@@ -1,0 +1,207 @@
+// grmkm_device.cuh -- device-side building blocks shared by the kernels.
+// Semantics implemented here are SURVEY.md Appendix E (E2-E8); the reference
+// call sites they stand in for are cited in include/grmkm.h.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace grmkm {
+
+constexpr int kTileBytes = 4096;      // input bytes per parse tile (256 threads x 16 B)
+constexpr int kParseThreads = 256;
+constexpr int kScanTilesPerThread = 4;
+constexpr int kScanTilesPerBlock = kParseThreads * kScanTilesPerThread;  // 1024
+constexpr int kExtractThreads = 256;
+constexpr int kAggThreads = 1024;
+constexpr int kMaxProbe = 96;
+constexpr uint64_t kEmptyKey = ~0ULL;
+
+// device scalars (u64 each)
+enum Scalar : int {
+    S_STREAM_LEN = 0,   // entries in the packed base stream
+    S_N_RECORDS,        // FASTA/FASTQ records seen
+    S_N_WINDOWS,        // k-mer windows partitioned (N)
+    S_U_NEEDED,         // columns the aggregate kernel wanted to emit
+    S_N_DISTINCT,       // distinct k-mers before the singleton filter
+    S_N_SPLITS,         // sub-range splits
+    S_N_SOLID,          // records surviving the abundance filter
+    S_WORK,             // persistent-kernel work counter
+    S_COUNT
+};
+
+struct FileDesc {
+    const uint8_t* ptr;   // device pointer to the file's bytes
+    uint64_t len;
+    uint64_t tile_begin;  // first tile index of this file
+    uint32_t row;         // genome row
+    uint32_t kind;        // GRMKM_FASTA / GRMKM_FASTQ
+};
+
+// ---- invertible 64-bit mixer (murmur3 fmix64 and its inverse) ---------------
+__host__ __device__ __forceinline__ uint64_t fmix64(uint64_t h) {
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdULL;
+    h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ULL;
+    h ^= h >> 33; return h;
+}
+__host__ __device__ __forceinline__ uint64_t unfmix64(uint64_t h) {
+    h ^= h >> 33; h *= 0x9cb4b2f8129337dbULL;
+    h ^= h >> 33; h *= 0x4f74430c22a54005ULL;
+    h ^= h >> 33; return h;
+}
+
+// ---- parse transducer summaries ---------------------------------------------
+// A tile (or 16-byte chunk) of text is summarised as a function of the parser
+// state s in {0..3} at its first byte: end state e[s] and number of stream
+// entries c[s] it emits.  FASTA uses states 0 = header line, 1 = sequence line;
+// FASTQ uses the line number mod 4.  Composition is associative, so the state
+// and stream position of every tile come out of one scan.
+struct Sum {
+    uint32_t e;           // 4 x 2 bits: e[s] at bits 2s
+    uint32_t c0, c1, c2, c3;
+};
+__device__ __forceinline__ uint32_t sum_end(const Sum& a, uint32_t s) { return (a.e >> (2 * s)) & 3u; }
+__device__ __forceinline__ uint32_t sum_cnt(const Sum& a, uint32_t s) {
+    return s == 0 ? a.c0 : (s == 1 ? a.c1 : (s == 2 ? a.c2 : a.c3));
+}
+__device__ __forceinline__ Sum sum_identity() { Sum r; r.e = 0xE4u; r.c0 = r.c1 = r.c2 = r.c3 = 0; return r; }
+// A happens first, then B
+__device__ __forceinline__ Sum sum_combine(const Sum& A, const Sum& B) {
+    uint32_t e0 = sum_end(A, 0), e1 = sum_end(A, 1), e2 = sum_end(A, 2), e3 = sum_end(A, 3);
+    Sum r;
+    r.e = sum_end(B, e0) | (sum_end(B, e1) << 2) | (sum_end(B, e2) << 4) | (sum_end(B, e3) << 6);
+    r.c0 = A.c0 + sum_cnt(B, e0);
+    r.c1 = A.c1 + sum_cnt(B, e1);
+    r.c2 = A.c2 + sum_cnt(B, e2);
+    r.c3 = A.c3 + sum_cnt(B, e3);
+    return r;
+}
+// force "the state at the first byte is s0" (first tile of a file)
+__device__ __forceinline__ Sum sum_fix_start(const Sum& a, uint32_t s0) {
+    Sum r; uint32_t e = sum_end(a, s0), c = sum_cnt(a, s0);
+    r.e = e * 0x55u; r.c0 = r.c1 = r.c2 = r.c3 = c; return r;
+}
+__device__ __forceinline__ Sum sum_shfl_up(const Sum& a, int d) {
+    Sum r;
+    r.e = __shfl_up_sync(0xffffffffu, a.e, d);
+    r.c0 = __shfl_up_sync(0xffffffffu, a.c0, d);
+    r.c1 = __shfl_up_sync(0xffffffffu, a.c1, d);
+    r.c2 = __shfl_up_sync(0xffffffffu, a.c2, d);
+    r.c3 = __shfl_up_sync(0xffffffffu, a.c3, d);
+    return r;
+}
+
+// Ordered block scan over kParseThreads threads.  excl = fold of all earlier
+// threads, total = fold of the whole block.  smem must hold (blockDim/32) Sums.
+__device__ __forceinline__ void block_scan_sum(const Sum& mine, Sum& excl, Sum& total, Sum* smem) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    Sum inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        Sum o = sum_shfl_up(inc, d);
+        if (lane >= d) inc = sum_combine(o, inc);
+    }
+    Sum prev = sum_shfl_up(inc, 1);
+    if (lane == 0) prev = sum_identity();
+    if (lane == 31) smem[warp] = inc;
+    __syncthreads();
+    Sum wpre = sum_identity(), tot = sum_identity();
+    for (int w = 0; w < nwarp; ++w) {
+        if (w == warp) wpre = tot;
+        tot = sum_combine(tot, smem[w]);
+    }
+    excl = sum_combine(wpre, prev);
+    total = tot;
+    __syncthreads();
+}
+
+// ---- byte classes -------------------------------------------------------------
+__device__ __forceinline__ bool is_acgt(uint32_t c) {
+    uint32_t u = c & 0xDFu;  // upper-case
+    return u == 'A' || u == 'C' || u == 'G' || u == 'T';
+}
+
+struct Chunk16 {
+    uint32_t w[4];
+    __device__ __forceinline__ uint32_t byte(int i) const { return (w[i >> 2] >> (8 * (i & 3))) & 0xFFu; }
+};
+
+// 16 bytes of a file at offset off (off is a multiple of 16 relative to a
+// 16-byte aligned base); bytes beyond len read as 0.
+__device__ __forceinline__ Chunk16 load_chunk(const uint8_t* base, uint64_t off, uint64_t len) {
+    Chunk16 c;
+    if (off + 16 <= len) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + off));
+        c.w[0] = v.x; c.w[1] = v.y; c.w[2] = v.z; c.w[3] = v.w;
+    } else {
+        c.w[0] = c.w[1] = c.w[2] = c.w[3] = 0;
+        for (int i = 0; i < 16; ++i)
+            if (off + i < len) c.w[i >> 2] |= (uint32_t)base[off + i] << (8 * (i & 3));
+    }
+    return c;
+}
+
+// FASTA states
+constexpr uint32_t ST_HDR = 0, ST_SEQ = 1;
+
+// summary of one 16-byte chunk (E2 / E3).  prev = byte before the chunk.
+template <int KIND>
+__device__ __forceinline__ Sum chunk_summary(const Chunk16& ch, uint32_t prev, uint64_t pos0, uint64_t len,
+                                             uint64_t hdr0) {
+    Sum r;
+    if (KIND == 0) {
+        uint32_t t = 0, c_head = 0, c_rest = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint64_t pos = pos0 + i;
+            const uint32_t c = ch.byte(i);
+            if (pos < len && pos >= hdr0) {
+                const bool ls = (pos == hdr0) || (prev == '\n');
+                const bool emits = (c != '\n' && c != '\r');
+                if (ls) {
+                    if (c == '>') { t = 1; c_rest++; }
+                    else { t = 2; c_rest += emits; }
+                } else if (t == 0) c_head += emits;
+                else if (t == 2) c_rest += emits;
+            }
+            prev = c;
+        }
+        r.e = t ? (t - 1) * 0x55u : 0xE4u;
+        r.c0 = c_rest; r.c1 = c_rest + c_head; r.c2 = 0; r.c3 = 0;
+    } else {
+        uint32_t nl = 0, a = 0, b = 0;  // a/b: four byte counters indexed by (relative line & 3)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint64_t pos = pos0 + i;
+            const uint32_t c = ch.byte(i);
+            if (pos < len && pos >= hdr0) {
+                const bool ls = (pos == hdr0) || (prev == '\n');
+                if (c == '\n') nl++;
+                else {
+                    const uint32_t sh = 8 * (nl & 3);
+                    if (c != '\r') a += 1u << sh;
+                    if (ls) b += 1u << sh;
+                }
+            }
+            prev = c;
+        }
+        // incoming line m: sequence bytes are those with (m + r) & 3 == 1, header starts (m + r) & 3 == 0
+        r.e = ((0 + nl) & 3) | (((1 + nl) & 3) << 2) | (((2 + nl) & 3) << 4) | (((3 + nl) & 3) << 6);
+        r.c0 = ((a >> 8) & 0xFF) + (b & 0xFF);
+        r.c1 = (a & 0xFF) + ((b >> 24) & 0xFF);
+        r.c2 = ((a >> 24) & 0xFF) + ((b >> 16) & 0xFF);
+        r.c3 = ((a >> 16) & 0xFF) + ((b >> 8) & 0xFF);
+    }
+    return r;
+}
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m;
+}
+
+// reverse the order of the 32 2-bit groups of x
+__device__ __forceinline__ uint64_t rev2(uint64_t x) {
+    x = __brevll(x);
+    return ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
+}
+
+}  // namespace grmkm

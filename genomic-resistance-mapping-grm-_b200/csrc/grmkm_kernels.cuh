@@ -1,0 +1,697 @@
+// grmkm_kernels.cuh -- the sm_100a kernels of the k-mer matrix path.
+//
+//   parse   : k_first_header, k_tile_summary, k_scan_reduce/blocks/apply, k_pack
+//             FASTA/FASTQ text -> dense 2-bit base stream + validity mask   (multidsk's bank reader)
+//   extract : k_extract<COUNT|SCATTER>
+//             canonical k-mers -> hash buckets                              (multidsk's partitioning)
+//   count   : k_abundance        per-(k-mer, genome) abundance filter       (multidsk -abundance-min)
+//   merge   : k_aggregate        per-bucket shared-memory hash aggregation: presence bits of all
+//             genomes ORed into 64-genome words + singleton filter         (dsk2kover)
+//   order   : k_sort_*           LSD radix sort of the columns by canonical k-mer, k_gather
+//   emit    : k_kmer_strings, k_format_tsv                                  (kmer_sequences / Ray TSV)
+#pragma once
+#include "grmkm_device.cuh"
+
+namespace grmkm {
+
+// ------------------------------------------------------------------------------------------
+// parse
+// ------------------------------------------------------------------------------------------
+
+// One warp per file: offset of the first header marker ('>' / '@') at a line start, or len.
+__global__ void k_first_header(const FileDesc* __restrict__ files, uint32_t n_files, uint64_t* __restrict__ hdr0) {
+    const uint32_t f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (f >= n_files) return;
+    const FileDesc fd = files[f];
+    const uint32_t marker = fd.kind == 0 ? '>' : '@';
+    uint64_t found = fd.len;
+    for (uint64_t base = 0; base < fd.len; base += 32) {
+        const uint64_t pos = base + lane;
+        bool hit = false;
+        if (pos < fd.len) {
+            const uint32_t c = fd.ptr[pos];
+            const bool ls = pos == 0 || fd.ptr[pos - 1] == '\n';
+            hit = ls && c == marker;
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, hit);
+        if (m) { found = base + (__ffs(m) - 1); break; }
+    }
+    if (lane == 0) hdr0[f] = found;
+}
+
+__device__ __forceinline__ uint32_t find_file(const FileDesc* __restrict__ files, uint32_t n_files, uint64_t tile) {
+    uint32_t lo = 0, hi = n_files - 1;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (files[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+struct TileCtx {
+    FileDesc fd;
+    uint64_t hdr0;
+    uint64_t off;   // byte offset of this thread's chunk in the file
+    uint32_t f;
+    bool first_tile;
+};
+
+__device__ __forceinline__ TileCtx tile_context(const FileDesc* __restrict__ files, uint32_t n_files,
+                                                const uint64_t* __restrict__ hdr0, uint64_t tile, uint32_t* s_f) {
+    if (threadIdx.x == 0) *s_f = find_file(files, n_files, tile);
+    __syncthreads();
+    TileCtx t;
+    t.f = *s_f;
+    t.fd = files[t.f];
+    t.hdr0 = hdr0[t.f];
+    t.first_tile = (tile == t.fd.tile_begin);
+    t.off = (tile - t.fd.tile_begin) * (uint64_t)kTileBytes + (uint64_t)threadIdx.x * 16;
+    return t;
+}
+
+__device__ __forceinline__ uint32_t prev_byte(const TileCtx& t, const Chunk16& ch) {
+    // last byte of the previous thread's chunk; lane 0 reads it from memory
+    uint32_t last = ch.byte(15);
+    uint32_t p = __shfl_up_sync(0xffffffffu, last, 1);
+    if ((threadIdx.x & 31) == 0) p = (t.off > 0 && t.off - 1 < t.fd.len) ? t.fd.ptr[t.off - 1] : (uint32_t)'\n';
+    return p;
+}
+
+// per-tile transducer summary
+__global__ void __launch_bounds__(kParseThreads)
+k_tile_summary(const FileDesc* __restrict__ files, uint32_t n_files, const uint64_t* __restrict__ hdr0,
+               uint64_t n_tiles, Sum* __restrict__ tsum, uint32_t* __restrict__ tile_file) {
+    __shared__ Sum s_w[kParseThreads / 32];
+    __shared__ uint32_t s_f;
+    const uint64_t tile = blockIdx.x;
+    if (tile >= n_tiles) return;
+    const TileCtx t = tile_context(files, n_files, hdr0, tile, &s_f);
+    const Chunk16 ch = load_chunk(t.fd.ptr, t.off, t.fd.len);
+    const uint32_t prev = prev_byte(t, ch);
+    Sum mine = t.fd.kind == 0 ? chunk_summary<0>(ch, prev, t.off, t.fd.len, t.hdr0)
+                              : chunk_summary<1>(ch, prev, t.off, t.fd.len, t.hdr0);
+    Sum excl, total;
+    block_scan_sum(mine, excl, total, s_w);
+    if (threadIdx.x == 0) {
+        if (t.first_tile) total = sum_fix_start(total, 0);
+        tsum[tile] = total;
+        tile_file[tile] = t.f;
+    }
+}
+
+// fold of kScanTilesPerBlock consecutive tile summaries
+__global__ void __launch_bounds__(kParseThreads)
+k_scan_reduce(const Sum* __restrict__ tsum, uint64_t n_tiles, Sum* __restrict__ bsum) {
+    __shared__ Sum s_w[kParseThreads / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * kScanTilesPerBlock + (uint64_t)threadIdx.x * kScanTilesPerThread;
+    Sum mine = sum_identity();
+#pragma unroll
+    for (int i = 0; i < kScanTilesPerThread; ++i)
+        if (base + i < n_tiles) mine = sum_combine(mine, tsum[base + i]);
+    Sum excl, total;
+    block_scan_sum(mine, excl, total, s_w);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = total;
+}
+
+// serial resolution of the block aggregates (tile 0 is a file's first tile, so the start state is moot)
+__global__ void k_scan_blocks(const Sum* __restrict__ bsum, uint32_t n_blocks, uint32_t* __restrict__ bstate,
+                              uint64_t* __restrict__ bpos, uint64_t* __restrict__ scalars,
+                              uint64_t* __restrict__ file_stream_start, uint32_t n_files) {
+    __shared__ Sum s[1024];
+    __shared__ uint32_t s_state;
+    __shared__ uint64_t s_pos;
+    if (threadIdx.x == 0) { s_state = 0; s_pos = 0; }
+    for (uint32_t base = 0; base < n_blocks; base += 1024) {
+        const uint32_t n = min(1024u, n_blocks - base);
+        __syncthreads();
+        if (threadIdx.x < n) s[threadIdx.x] = bsum[base + threadIdx.x];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t st = s_state; uint64_t pos = s_pos;
+            for (uint32_t i = 0; i < n; ++i) {
+                bstate[base + i] = st; bpos[base + i] = pos;
+                pos += sum_cnt(s[i], st); st = sum_end(s[i], st);
+            }
+            s_state = st; s_pos = pos;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { scalars[S_STREAM_LEN] = s_pos; file_stream_start[n_files] = s_pos; }
+}
+
+// per-tile incoming state and stream position
+__global__ void __launch_bounds__(kParseThreads)
+k_scan_apply(const Sum* __restrict__ tsum, uint64_t n_tiles, const uint32_t* __restrict__ bstate,
+             const uint64_t* __restrict__ bpos, const uint32_t* __restrict__ tile_file,
+             const FileDesc* __restrict__ files, uint8_t* __restrict__ tile_state, uint64_t* __restrict__ tile_pos,
+             uint64_t* __restrict__ file_stream_start) {
+    __shared__ Sum s_w[kParseThreads / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * kScanTilesPerBlock + (uint64_t)threadIdx.x * kScanTilesPerThread;
+    Sum t[kScanTilesPerThread];
+    Sum mine = sum_identity();
+#pragma unroll
+    for (int i = 0; i < kScanTilesPerThread; ++i) {
+        t[i] = (base + i < n_tiles) ? tsum[base + i] : sum_identity();
+        mine = sum_combine(mine, t[i]);
+    }
+    Sum excl, total;
+    block_scan_sum(mine, excl, total, s_w);
+    const uint32_t st_in = bstate[blockIdx.x];
+    uint32_t st = sum_end(excl, st_in);
+    uint64_t pos = bpos[blockIdx.x] + sum_cnt(excl, st_in);
+#pragma unroll
+    for (int i = 0; i < kScanTilesPerThread; ++i) {
+        if (base + i < n_tiles) {
+            tile_state[base + i] = (uint8_t)st;
+            tile_pos[base + i] = pos;
+            const uint32_t f = tile_file[base + i];
+            if (files[f].tile_begin == base + i) file_stream_start[f] = pos;
+            pos += sum_cnt(t[i], st); st = sum_end(t[i], st);
+        }
+    }
+}
+
+// text tile -> packed stream: codes64[g] holds entries 32g..32g+31 (entry j at bits 2j), valid32[g] bit j.
+__global__ void __launch_bounds__(kParseThreads)
+k_pack(const FileDesc* __restrict__ files, uint32_t n_files, const uint64_t* __restrict__ hdr0, uint64_t n_tiles,
+       const uint8_t* __restrict__ tile_state, const uint64_t* __restrict__ tile_pos,
+       unsigned long long* __restrict__ codes, uint32_t* __restrict__ valid, uint64_t* __restrict__ scalars) {
+    constexpr int kGroups = kTileBytes / 32 + 2;
+    __shared__ Sum s_w[kParseThreads / 32];
+    __shared__ uint32_t s_f;
+    __shared__ uint32_t s_codes[kGroups * 2];
+    __shared__ uint32_t s_valid[kGroups];
+    __shared__ uint32_t s_nrec;
+    const uint64_t tile = blockIdx.x;
+    if (tile >= n_tiles) return;
+    for (int i = threadIdx.x; i < kGroups * 2; i += blockDim.x) s_codes[i] = 0;
+    for (int i = threadIdx.x; i < kGroups; i += blockDim.x) s_valid[i] = 0;
+    if (threadIdx.x == 0) s_nrec = 0;
+    const TileCtx t = tile_context(files, n_files, hdr0, tile, &s_f);
+    const Chunk16 ch = load_chunk(t.fd.ptr, t.off, t.fd.len);
+    uint32_t prev = prev_byte(t, ch);
+    const Sum mine = t.fd.kind == 0 ? chunk_summary<0>(ch, prev, t.off, t.fd.len, t.hdr0)
+                                    : chunk_summary<1>(ch, prev, t.off, t.fd.len, t.hdr0);
+    Sum excl, total;
+    block_scan_sum(mine, excl, total, s_w);
+    const uint32_t st_in = tile_state[tile];
+    const uint64_t tpos = tile_pos[tile];
+    uint32_t st = sum_end(excl, st_in);
+    const uint32_t local = sum_cnt(excl, st_in);
+    const uint32_t e_total = sum_cnt(total, st_in);
+
+    // walk the 16 bytes with the now-known state
+    uint32_t cbits = 0, vbits = 0, n = 0, nrec = 0;
+    if (t.fd.kind == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint64_t pos = t.off + i;
+            const uint32_t c = ch.byte(i);
+            if (pos < t.fd.len && pos >= t.hdr0) {
+                const bool ls = (pos == t.hdr0) || (prev == '\n');
+                if (ls) st = (c == '>') ? ST_HDR : ST_SEQ;
+                if (ls && c == '>') { n++; nrec++; }                       // record break entry (invalid)
+                else if (st == ST_SEQ && c != '\n' && c != '\r') {
+                    if (is_acgt(c)) { cbits |= ((c >> 1) & 3u) << (2 * n); vbits |= 1u << n; }
+                    n++;
+                }
+            }
+            prev = c;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint64_t pos = t.off + i;
+            const uint32_t c = ch.byte(i);
+            if (pos < t.fd.len && pos >= t.hdr0) {
+                const bool ls = (pos == t.hdr0) || (prev == '\n');
+                if (c == '\n') st = (st + 1) & 3;
+                else if (st == 0) { if (ls) { n++; nrec++; } }
+                else if (st == 1 && c != '\r') {
+                    if (is_acgt(c)) { cbits |= ((c >> 1) & 3u) << (2 * n); vbits |= 1u << n; }
+                    n++;
+                }
+            }
+            prev = c;
+        }
+    }
+    const uint32_t rel = (uint32_t)(tpos & 31) + local;   // entry offset from the tile's first group
+    if (n) {
+        const uint32_t cb = rel * 2, cw = cb >> 5, cs = cb & 31;
+        atomicOr(&s_codes[cw], cbits << cs);
+        if (cs && (cbits >> (32 - cs))) atomicOr(&s_codes[cw + 1], cbits >> (32 - cs));
+        const uint32_t vw = rel >> 5, vs = rel & 31;
+        atomicOr(&s_valid[vw], vbits << vs);
+        if (vs && (vbits >> (32 - vs))) atomicOr(&s_valid[vw + 1], vbits >> (32 - vs));
+    }
+    if (nrec) atomicAdd(&s_nrec, nrec);
+    __syncthreads();
+    if (e_total) {
+        const uint64_t g0 = tpos >> 5;
+        const uint32_t first_off = (uint32_t)(tpos & 31);
+        const uint32_t ngroups = (first_off + e_total + 31) >> 5;
+        for (uint32_t gi = threadIdx.x; gi < ngroups; gi += blockDim.x) {
+            const unsigned long long cw = (unsigned long long)s_codes[2 * gi] | ((unsigned long long)s_codes[2 * gi + 1] << 32);
+            const uint32_t vw = s_valid[gi];
+            const bool partial = (gi == 0 && first_off) || (gi == ngroups - 1 && ((first_off + e_total) & 31));
+            if (partial) {
+                if (cw) atomicOr(&codes[g0 + gi], cw);
+                if (vw) atomicOr(&valid[g0 + gi], vw);
+            } else {
+                codes[g0 + gi] = cw;
+                valid[g0 + gi] = vw;
+            }
+        }
+    }
+    if (threadIdx.x == 0 && s_nrec) atomicAdd((unsigned long long*)&scalars[S_N_RECORDS], (unsigned long long)s_nrec);
+}
+
+// ------------------------------------------------------------------------------------------
+// extract: canonical k-mers -> hash buckets
+// ------------------------------------------------------------------------------------------
+struct ExtractParams {
+    const unsigned long long* codes;
+    const uint32_t* valid;
+    const uint64_t* scalars;            // S_STREAM_LEN
+    const uint64_t* file_stream_start;  // [n_files + 1]
+    const FileDesc* files;
+    uint32_t n_files;
+    uint32_t k;
+    uint32_t bucket_bits;
+    uint32_t row_bits;
+    unsigned long long* hist;     // [B] (COUNT) / cursors [B] (SCATTER)
+    unsigned long long* records;  // SCATTER
+};
+
+template <int MODE>  // 0 = count per bucket, 1 = scatter records
+__global__ void __launch_bounds__(kExtractThreads)
+k_extract(const ExtractParams p) {
+    extern __shared__ uint32_t s_hist[];   // COUNT: B counters
+    __shared__ uint32_t s_f0;
+    const uint32_t B = 1u << p.bucket_bits;
+    const uint64_t stream_len = p.scalars[S_STREAM_LEN];
+    const uint64_t n_groups = (stream_len + 31) >> 5;
+    const uint64_t n_etiles = (n_groups + kExtractThreads - 1) / kExtractThreads;
+    const uint32_t k = p.k;
+    const uint64_t kmask = k == 32 ? ~0ULL : ((1ULL << (2 * k)) - 1);
+    const uint32_t key_bits = 64 - p.bucket_bits;
+    const uint64_t key_mask = (1ULL << key_bits) - 1;
+    const int lane = threadIdx.x & 31;
+    if (MODE == 0) {
+        for (uint32_t i = threadIdx.x; i < B; i += blockDim.x) s_hist[i] = 0;
+        __syncthreads();
+    }
+    for (uint64_t et = blockIdx.x; et < n_etiles; et += gridDim.x) {
+        const uint64_t g = et * kExtractThreads + threadIdx.x;
+        // file of the tile's first position
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint64_t p0 = et * kExtractThreads * 32ULL;
+            uint32_t lo = 0, hi = p.n_files - 1;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi + 1) >> 1;
+                if (p.file_stream_start[mid] <= p0) lo = mid; else hi = mid - 1;
+            }
+            s_f0 = lo;
+        }
+        __syncthreads();
+        unsigned long long cur_c = 0; uint32_t cur_v = 0;
+        if (g < n_groups) { cur_c = p.codes[g]; cur_v = p.valid[g]; }
+        unsigned long long prev_c = __shfl_up_sync(0xffffffffu, cur_c, 1);
+        uint32_t prev_v = __shfl_up_sync(0xffffffffu, cur_v, 1);
+        if (lane == 0) {
+            if (g > 0 && g - 1 < n_groups) { prev_c = p.codes[g - 1]; prev_v = p.valid[g - 1]; }
+            else { prev_c = 0; prev_v = 0; }
+        }
+        if (g >= n_groups || cur_v == 0) continue;
+        const uint64_t pos0 = g * 32ULL;
+        uint32_t f = s_f0;
+        while (f + 1 < p.n_files && p.file_stream_start[f + 1] <= pos0) ++f;
+        uint64_t next_start = (f + 1 < p.n_files) ? p.file_stream_start[f + 1] : ~0ULL;
+        uint32_t row = p.files[f].row;
+        // state after the last entry of the previous group
+        const uint64_t le = k == 32 ? prev_c : ((prev_c >> (2 * (32 - k))) & kmask);
+        uint64_t rc = le ^ (0xAAAAAAAAAAAAAAAAULL & kmask);
+        uint64_t fw = rev2(le) >> (64 - 2 * k);
+        uint32_t run = min((uint32_t)__clz(~prev_v), k);
+#pragma unroll 4
+        for (int e = 0; e < 32; ++e) {
+            const uint32_t c = (uint32_t)(cur_c >> (2 * e)) & 3u;
+            fw = ((fw << 2) | c) & kmask;
+            rc = (rc >> 2) | ((uint64_t)(c ^ 2u) << (2 * (k - 1)));
+            if ((cur_v >> e) & 1u) run = min(run + 1, k); else run = 0;
+            if (run == k) {
+                const uint64_t pos = pos0 + e;
+                if (pos >= next_start) {
+                    while (f + 1 < p.n_files && p.file_stream_start[f + 1] <= pos) ++f;
+                    next_start = (f + 1 < p.n_files) ? p.file_stream_start[f + 1] : ~0ULL;
+                    row = p.files[f].row;
+                }
+                const uint64_t canon = fw < rc ? fw : rc;
+                const uint64_t h = fmix64(canon);
+                const uint32_t b = (uint32_t)(h >> key_bits);
+                if (MODE == 0) {
+                    atomicAdd(&s_hist[b], 1u);
+                } else {
+                    const unsigned long long slot = atomicAdd(&p.hist[b], 1ULL);
+                    p.records[slot] = ((h & key_mask) << p.row_bits) | row;
+                }
+            }
+        }
+    }
+    if (MODE == 0) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < B; i += blockDim.x) {
+            const uint32_t v = s_hist[i];
+            if (v) atomicAdd(&p.hist[i], (unsigned long long)v);
+        }
+    }
+}
+
+// exclusive scan of the bucket histogram -> offsets[B+1]; cursors[b] = offsets[b]
+__global__ void __launch_bounds__(1024)
+k_bucket_offsets(unsigned long long* __restrict__ hist_cursor, unsigned long long* __restrict__ offsets, uint32_t B,
+                 uint64_t* __restrict__ scalars, int total_scalar) {
+    __shared__ unsigned long long s_part[1024];
+    const uint32_t per = (B + 1023) / 1024;
+    const uint32_t b0 = threadIdx.x * per;
+    unsigned long long sum = 0;
+    for (uint32_t i = 0; i < per; ++i) if (b0 + i < B) sum += hist_cursor[b0 + i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    // simple Hillis-Steele inclusive scan
+    for (int d = 1; d < 1024; d <<= 1) {
+        unsigned long long v = threadIdx.x >= d ? s_part[threadIdx.x - d] : 0;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned long long run = s_part[threadIdx.x] - sum;
+    for (uint32_t i = 0; i < per; ++i) {
+        if (b0 + i < B) {
+            const unsigned long long c = hist_cursor[b0 + i];
+            offsets[b0 + i] = run;
+            hist_cursor[b0 + i] = run;
+            run += c;
+        }
+    }
+    if (threadIdx.x == 1023) { offsets[B] = s_part[1023]; scalars[total_scalar] = s_part[1023]; }
+}
+
+// ------------------------------------------------------------------------------------------
+// aggregate: per-bucket shared-memory hash table
+// ------------------------------------------------------------------------------------------
+struct AggParams {
+    const unsigned long long* records;   // (key << row_bits) | row
+    const unsigned long long* offsets;   // [B+1]
+    uint32_t B;
+    uint32_t bucket_bits;
+    uint32_t row_bits;
+    uint32_t n_words;        // words per column handled here
+    uint32_t slots;          // table capacity
+    uint32_t keep_singletons;
+    uint32_t mode;           // 0: final columns (k-mers), 1: partial columns (hash keys), 2: abundance filter
+    uint32_t min_abundance;  // mode 2
+    unsigned long long* out_keys;    // [cap]
+    unsigned long long* out_words;   // [n_words][cap]  (mode 0/1)
+    unsigned long long cap;
+    unsigned long long* scalars;
+    unsigned long long* bucket_out_counts;  // mode 1/2: entries emitted per bucket (atomic)
+    unsigned long long* out_records;        // mode 2: filtered records, written at the bucket's own offset
+};
+
+__device__ __forceinline__ uint32_t slot_of(uint64_t key, uint32_t slots) {
+    uint32_t hh = (uint32_t)key ^ (uint32_t)(key >> 32);
+    hh *= 0x9E3779B1u;
+    return __umulhi(hh, slots);
+}
+
+// Table key for MODE 0/1 is the hash key; for MODE 2 it is the whole record (key, row) and the
+// single word per slot is an abundance counter.
+template <int MODE>
+__global__ void __launch_bounds__(kAggThreads, 1)
+k_aggregate(const AggParams p) {
+    extern __shared__ unsigned long long s_tab[];   // keys[slots] then words[n_words][slots]
+    __shared__ uint32_t s_overflow, s_sp, s_cnt, s_kept, s_wr;
+    __shared__ uint32_t s_depth[72];
+    __shared__ unsigned long long s_idx[72];
+    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_red[kAggThreads / 32];
+    const uint32_t slots = p.slots;
+    const uint32_t W = (MODE == 2) ? 1u : p.n_words;
+    unsigned long long* keys = s_tab;
+    unsigned long long* words = s_tab + slots;
+    const uint32_t key_bits = (MODE == 2) ? (64 - p.bucket_bits + p.row_bits) : (64 - p.bucket_bits);
+    const uint64_t row_mask = (1ULL << p.row_bits) - 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    for (uint32_t b = blockIdx.x; b < p.B; b += gridDim.x) {
+        const unsigned long long rbeg = p.offsets[b], rend = p.offsets[b + 1];
+        if (rbeg == rend) continue;
+        __syncthreads();
+        if (threadIdx.x == 0) { s_sp = 1; s_depth[0] = 0; s_idx[0] = 0; s_wr = 0; }
+        __syncthreads();
+        while (true) {
+            __syncthreads();
+            if (s_sp == 0) break;
+            const uint32_t depth = s_depth[s_sp - 1];
+            const unsigned long long ridx = s_idx[s_sp - 1];
+            __syncthreads();
+            if (threadIdx.x == 0) { s_sp--; s_overflow = 0; s_cnt = 0; s_kept = 0; }
+            for (uint32_t i = threadIdx.x; i < slots; i += blockDim.x) keys[i] = kEmptyKey;
+            for (uint32_t i = threadIdx.x; i < slots * W; i += blockDim.x) words[i] = 0;
+            __syncthreads();
+            // ---- stream the bucket's records through the table
+            for (unsigned long long r = rbeg + threadIdx.x; r < rend; r += blockDim.x) {
+                if (*(volatile uint32_t*)&s_overflow) break;
+                const unsigned long long rec = p.records[r];
+                unsigned long long key; uint32_t row = 0;
+                if (MODE == 2) key = rec;
+                else { key = rec >> p.row_bits; row = (uint32_t)(rec & row_mask); }
+                if (depth && (key >> (key_bits - depth)) != ridx) continue;
+                uint32_t slot = slot_of(key, slots);
+                bool hit = false;
+                for (int probe = 0; probe < kMaxProbe; ++probe) {
+                    unsigned long long k0 = *(volatile unsigned long long*)&keys[slot];
+                    if (k0 == kEmptyKey) k0 = atomicCAS(&keys[slot], kEmptyKey, key);
+                    if (k0 == kEmptyKey || k0 == key) { hit = true; break; }
+                    slot = slot + 1 == slots ? 0 : slot + 1;
+                }
+                if (!hit) { s_overflow = 1; break; }
+                if (MODE == 2) {
+                    atomicAdd((uint32_t*)&words[slot], 1u);
+                } else {
+                    const uint32_t bit = 63u - (row & 63u);      // utils.py:144-154
+                    uint32_t* w32 = (uint32_t*)&words[(row >> 6) * slots + slot];
+                    atomicOr(&w32[bit >> 5], 1u << (bit & 31u));
+                }
+            }
+            __syncthreads();
+            if (s_overflow) {
+                // split this key range in two and retry (terminates: a range of one key needs one slot)
+                if (threadIdx.x == 0) {
+                    s_depth[s_sp] = depth + 1; s_idx[s_sp] = ridx * 2 + 1; s_sp++;
+                    s_depth[s_sp] = depth + 1; s_idx[s_sp] = ridx * 2; s_sp++;
+                    atomicAdd(&p.scalars[S_N_SPLITS], 1ULL);
+                }
+                continue;
+            }
+            // ---- count what this range emits
+            uint32_t occ = 0, kept = 0;
+            for (uint32_t i = threadIdx.x; i < slots; i += blockDim.x) {
+                if (keys[i] != kEmptyKey) {
+                    occ++;
+                    if (MODE == 2) kept += ((uint32_t)words[i] >= p.min_abundance);
+                    else if (MODE == 1) kept++;
+                    else {
+                        uint32_t pc = 0;
+                        for (uint32_t w = 0; w < W; ++w) pc += __popcll(words[w * slots + i]);
+                        kept += (pc >= 2 || p.keep_singletons);
+                    }
+                }
+            }
+            occ = __reduce_add_sync(0xffffffffu, occ);
+            kept = __reduce_add_sync(0xffffffffu, kept);
+            if (lane == 0) { atomicAdd(&s_cnt, occ); atomicAdd(&s_kept, kept); }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                if (MODE == 2) {
+                    s_base = rbeg + s_wr;           // filtered records stay inside the bucket's own range
+                    s_wr += s_kept;
+                } else {
+                    s_base = atomicAdd(&p.scalars[S_U_NEEDED], (unsigned long long)s_kept);
+                    atomicAdd(&p.scalars[S_N_DISTINCT], (unsigned long long)s_cnt);
+                    if (MODE == 1) atomicAdd(&p.bucket_out_counts[b], (unsigned long long)s_kept);
+                }
+                s_cnt = 0;
+            }
+            __syncthreads();
+            // ---- emit
+            const unsigned long long base = s_base;
+            for (uint32_t i0 = 0; i0 < slots; i0 += blockDim.x) {
+                const uint32_t i = i0 + threadIdx.x;
+                bool keep = false;
+                unsigned long long key = 0;
+                if (i < slots) {
+                    key = keys[i];
+                    if (key != kEmptyKey) {
+                        if (MODE == 2) keep = ((uint32_t)words[i] >= p.min_abundance);
+                        else if (MODE == 1) keep = true;
+                        else {
+                            uint32_t pc = 0;
+                            for (uint32_t w = 0; w < W; ++w) pc += __popcll(words[w * slots + i]);
+                            keep = (pc >= 2 || p.keep_singletons);
+                        }
+                    }
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, keep);
+                uint32_t wbase = 0;
+                if (lane == 0 && m) wbase = atomicAdd(&s_cnt, __popc(m));
+                wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                if (keep) {
+                    const unsigned long long o = base + wbase + __popc(m & lanemask_lt());
+                    if (MODE == 2) {
+                        p.out_records[o] = key;
+                    } else if (o < p.cap) {
+                        const unsigned long long h = ((unsigned long long)b << key_bits) | key;
+                        p.out_keys[o] = (MODE == 0) ? unfmix64(h) : h;
+                        for (uint32_t w = 0; w < W; ++w) p.out_words[w * p.cap + o] = words[w * slots + i];
+                    }
+                }
+            }
+        }
+        if (MODE == 2 && threadIdx.x == 0) {
+            p.bucket_out_counts[b] = s_wr;
+            atomicAdd(&p.scalars[S_N_SOLID], (unsigned long long)s_wr);
+        }
+    }
+    (void)warp; (void)s_red;
+}
+
+// compact per-bucket filtered records (mode 2 leaves them at the bucket's old offset) into new offsets
+__global__ void k_compact_records(const unsigned long long* __restrict__ src, const unsigned long long* __restrict__ old_off,
+                                  const unsigned long long* __restrict__ new_off, uint32_t B,
+                                  unsigned long long* __restrict__ dst) {
+    for (uint32_t b = blockIdx.x; b < B; b += gridDim.x) {
+        const unsigned long long s = old_off[b], d = new_off[b], n = new_off[b + 1] - d;
+        for (unsigned long long i = threadIdx.x; i < n; i += blockDim.x) dst[d + i] = src[s + i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// order: LSD radix sort of (k-mer, column index), one warp per contiguous segment
+// ------------------------------------------------------------------------------------------
+constexpr int kSortSeg = 4096;        // items per warp segment
+constexpr int kSortWarps = 8;
+
+__global__ void __launch_bounds__(kSortWarps * 32)
+k_sort_hist(const unsigned long long* __restrict__ keys, uint64_t n, uint32_t shift, uint32_t n_seg,
+            uint32_t* __restrict__ hist /* [256][n_seg] */) {
+    __shared__ uint32_t s_h[kSortWarps][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t seg = blockIdx.x * kSortWarps + warp;
+    for (int i = lane; i < 256; i += 32) s_h[warp][i] = 0;
+    __syncwarp();
+    if (seg < n_seg) {
+        const uint64_t beg = (uint64_t)seg * kSortSeg, end = min(n, beg + kSortSeg);
+        for (uint64_t i = beg + lane; i < end; i += 32) atomicAdd(&s_h[warp][(keys[i] >> shift) & 255u], 1u);
+        __syncwarp();
+        for (int i = lane; i < 256; i += 32) hist[(uint64_t)i * n_seg + seg] = s_h[warp][i];
+    }
+}
+
+// exclusive scan of a u32 array of length n in place (single block)
+__global__ void __launch_bounds__(1024)
+k_scan_u32(uint32_t* __restrict__ a, uint64_t n) {
+    __shared__ uint32_t s_part[1024];
+    const uint64_t per = (n + 1023) / 1024;
+    const uint64_t b0 = threadIdx.x * per;
+    uint32_t sum = 0;
+    for (uint64_t i = 0; i < per; ++i) if (b0 + i < n) sum += a[b0 + i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        uint32_t v = threadIdx.x >= d ? s_part[threadIdx.x - d] : 0;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = s_part[threadIdx.x] - sum;
+    for (uint64_t i = 0; i < per; ++i)
+        if (b0 + i < n) { const uint32_t c = a[b0 + i]; a[b0 + i] = run; run += c; }
+}
+
+__global__ void __launch_bounds__(kSortWarps * 32)
+k_sort_scatter(const unsigned long long* __restrict__ keys_in, const uint32_t* __restrict__ idx_in, uint64_t n,
+               uint32_t shift, uint32_t n_seg, const uint32_t* __restrict__ hist,
+               unsigned long long* __restrict__ keys_out, uint32_t* __restrict__ idx_out) {
+    __shared__ uint32_t s_b[kSortWarps][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t seg = blockIdx.x * kSortWarps + warp;
+    if (seg >= n_seg) return;
+    for (int i = lane; i < 256; i += 32) s_b[warp][i] = hist[(uint64_t)i * n_seg + seg];
+    __syncwarp();
+    const uint64_t beg = (uint64_t)seg * kSortSeg, end = min(n, beg + kSortSeg);
+    for (uint64_t i0 = beg; i0 < end; i0 += 32) {
+        const uint64_t i = i0 + lane;
+        const bool act = i < end;
+        const uint32_t amask = __ballot_sync(0xffffffffu, act);
+        if (act) {
+            const unsigned long long key = keys_in[i];
+            const uint32_t idx = idx_in ? idx_in[i] : (uint32_t)i;
+            const uint32_t d = (uint32_t)(key >> shift) & 255u;
+            const uint32_t peers = __match_any_sync(amask, d);
+            const uint32_t rank = __popc(peers & lanemask_lt());
+            const uint32_t pos = s_b[warp][d] + rank;
+            __syncwarp(amask);
+            if (rank == 0) s_b[warp][d] += __popc(peers);
+            __syncwarp(amask);
+            keys_out[pos] = key;
+            idx_out[pos] = idx;
+        }
+    }
+}
+
+// columns in final order: kmers[j], matrix[w][j] = uwords[w][idx[j]]
+__global__ void k_gather(const unsigned long long* __restrict__ sorted_keys, const uint32_t* __restrict__ idx,
+                         uint64_t U, uint32_t W, const unsigned long long* __restrict__ uwords, uint64_t ucap,
+                         unsigned long long* __restrict__ kmers, unsigned long long* __restrict__ matrix) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= U) return;
+    kmers[j] = sorted_keys[j];
+    const uint32_t src = idx[j];
+    for (uint32_t w = 0; w < W; ++w) matrix[(uint64_t)w * U + j] = uwords[(uint64_t)w * ucap + src];
+}
+
+// ------------------------------------------------------------------------------------------
+// emit
+// ------------------------------------------------------------------------------------------
+__global__ void k_kmer_strings(const unsigned long long* __restrict__ kmers, uint64_t j0, uint64_t n_bytes,
+                               uint32_t k, char* __restrict__ dst) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_bytes) return;
+    const uint64_t j = i / k; const uint32_t c = (uint32_t)(i % k);
+    const uint32_t code = (uint32_t)(kmers[j0 + j] >> (2 * (k - 1 - c))) & 3u;
+    dst[i] = "ACTG"[code];
+}
+
+// rows [j0, j0 + n_rows) of the TSV body; row width = k + 2G + 1
+__global__ void k_format_tsv(const unsigned long long* __restrict__ kmers, const unsigned long long* __restrict__ matrix,
+                             uint64_t U, uint32_t G, uint32_t k, uint64_t j0, uint64_t n_bytes, char* __restrict__ dst) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_bytes) return;
+    const uint32_t roww = k + 2 * G + 1;
+    const uint64_t j = j0 + i / roww; const uint32_t c = (uint32_t)(i % roww);
+    char out;
+    if (c < k) out = "ACTG"[(uint32_t)(kmers[j] >> (2 * (k - 1 - c))) & 3u];
+    else if (c == roww - 1) out = '\n';
+    else if (((c - k) & 1u) == 0) out = '\t';
+    else {
+        const uint32_t g = (c - k) >> 1;
+        out = ((matrix[(uint64_t)(g >> 6) * U + j] >> (63 - (g & 63))) & 1ULL) ? '1' : '0';
+    }
+    dst[i] = out;
+}
+
+}  // namespace grmkm

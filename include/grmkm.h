@@ -1,0 +1,179 @@
+/*
+ * grmkm.h -- C ABI of libgrmkm.so: the B200-native k-mer matrix builder that
+ * replaces the native half of GRM's "genomes -> genome x k-mer matrix" path.
+ *
+ * The reference has no in-process FFI for this path: it reaches the native
+ * code through argv of child processes.  Each entry point
+ * below names the reference interface it stands in for; paths are under
+ * /root/reference.
+ *
+ *   multidsk  argv   bin/kover/core/kover/dataset/tools/kmer_count.py:28-37, 44-53
+ *   dsk2kover argv   bin/kover/core/kover/dataset/tools/kmer_pack.py:28-36
+ *   Ray       argv   src/app.py:1310 + survey.conf grammar src/app.py:3820-3833
+ *   dsk       argv   src/app.py:1371-1372
+ *
+ * Conventions: extern "C", plain pointers and sizes, no exceptions cross the
+ * boundary.  Every call returns GRMKM_OK (0) or a negative GRMKM_E_* code; the
+ * message is available from grmkm_last_error().  The caller allocates every
+ * output buffer and passes its capacity.  A context owns all device memory and
+ * is single-owner (not thread safe); several contexts may coexist.  There is
+ * NO CPU fallback: without a CUDA device grmkm_create fails with
+ * GRMKM_E_NO_DEVICE.
+ */
+#ifndef GRMKM_H
+#define GRMKM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRMKM_ABI_VERSION 2
+
+enum {
+    GRMKM_OK = 0,
+    GRMKM_E_INVALID = -1,       /* bad argument / bad state                          */
+    GRMKM_E_UNSUPPORTED_K = -2, /* k outside 1..32 (reference allows <=128, kover:114) */
+    GRMKM_E_NOMEM = -3,         /* host or device allocation failed                  */
+    GRMKM_E_CUDA = -4,          /* CUDA runtime error (message has the detail)       */
+    GRMKM_E_IO = -5,            /* file could not be read / inflated                 */
+    GRMKM_E_CAPACITY = -6,      /* caller buffer too small                           */
+    GRMKM_E_NO_DEVICE = -7,     /* no usable CUDA device: there is no CPU fallback   */
+    GRMKM_E_UNSUPPORTED = -8    /* e.g. more genomes than one context can hold       */
+};
+
+enum { GRMKM_FASTA = 0, GRMKM_FASTQ = 1 };
+
+/* cfg.flags */
+#define GRMKM_FLAG_HASH_ORDER 1u /* keep columns in internal hash order (skip the final sort) */
+
+typedef struct grmkm_ctx grmkm_ctx;
+
+/*
+ * Parameters = the knobs the reference forwards to the native tools:
+ *   k               -kmer-size / -kmer-length / "-k"      (kmer_count.py:31, kmer_pack.py:32, app.py:3821)
+ *   min_abundance   -abundance-min  (contigs: 1, kmer_count.py:32; reads: user value, :48)
+ *   keep_singletons -filter nothing|singleton  (kover:144-147 -> kmer_pack.py:31); Ray mode: 1
+ *   input_kind      contigs (.fna, FASTA) or reads (.fastq, FASTQ)  (create.py:278, 399-402)
+ */
+typedef struct grmkm_config {
+    uint32_t struct_size;     /* = sizeof(grmkm_config), for forward compatibility */
+    uint32_t k;               /* 1..32 */
+    uint32_t min_abundance;   /* >= 1 */
+    uint32_t keep_singletons; /* 0: drop k-mers present in exactly one genome */
+    uint32_t input_kind;      /* default kind for grmkm_add_genome_* */
+    int32_t device;           /* CUDA ordinal; -1 = current device */
+    uint32_t bucket_bits;     /* 0 = auto; log2 of the number of hash buckets */
+    uint32_t flags;
+    void* stream;             /* cudaStream_t to run on; NULL = context-owned stream */
+} grmkm_config;
+
+typedef struct grmkm_stats {
+    uint64_t n_bases;       /* nucleotide characters in sequence lines             */
+    uint64_t n_windows;     /* valid k-mer windows (= records partitioned)         */
+    uint64_t n_input_bytes; /* bytes of FASTA/FASTQ text                           */
+    uint64_t n_records;     /* FASTA/FASTQ records                                 */
+    uint64_t n_kmers;       /* U: columns kept                                     */
+    uint64_t n_distinct;    /* distinct canonical k-mers before the singleton filter */
+    uint32_t n_words;       /* ceil(G/64)                                          */
+    uint32_t n_genomes;     /* G                                                   */
+    uint32_t n_buckets;     /* hash buckets used                                   */
+    uint32_t n_launches;    /* kernels launched by the last build                  */
+    uint64_t h2d_bytes;     /* host->device bytes moved by the last build          */
+    uint64_t device_bytes;  /* device memory held by the context                   */
+    uint64_t n_splits;      /* bucket sub-range splits (table overflows handled)   */
+} grmkm_stats;
+
+/* per-stage device time of the last build, milliseconds (CUDA events on the build stream) */
+typedef struct grmkm_times {
+    float h2d, parse, pack, count, scatter, abundance, aggregate, sort, total;
+} grmkm_times;
+
+int grmkm_abi_version(void);
+int grmkm_device_count(void);
+
+int grmkm_create(const grmkm_config* cfg, grmkm_ctx** out);
+void grmkm_destroy(grmkm_ctx* ctx);
+/* ctx may be NULL: message of the last failed grmkm_create on this thread */
+const char* grmkm_last_error(const grmkm_ctx* ctx);
+
+/* Forget the inputs (and result) of the previous build; device buffers are kept for reuse. */
+int grmkm_reset(grmkm_ctx* ctx);
+
+/*
+ * One line of multidsk's "-file" list (create.py:361-362, 482-489): the file(s)
+ * of genome `genome_row` (row order = order of genome_identifiers, create.py:334-347).
+ * All inputs of one row are pooled.  *_bytes: host memory, borrowed until the
+ * build returns.  *_device: device memory on cfg.device, borrowed likewise.
+ * *_files: read (and gunzip'ed when the name ends in .gz) by the library.
+ */
+int grmkm_add_genome_bytes(grmkm_ctx* ctx, uint32_t genome_row, const uint8_t* data, uint64_t n);
+int grmkm_add_genome_device(grmkm_ctx* ctx, uint32_t genome_row, const void* dev_data, uint64_t n);
+int grmkm_add_genome_files(grmkm_ctx* ctx, uint32_t genome_row, const char* const* paths, int n_paths);
+/* Declare rows without input (trailing empty genomes still get a matrix row). */
+int grmkm_set_genome_count(grmkm_ctx* ctx, uint32_t n_genomes);
+
+/*
+ * multidsk + dsk2kover in one call: count canonical k-mers per genome, apply
+ * min_abundance per genome, merge across genomes, apply the singleton filter,
+ * pack 64 genomes per word (bit 63-(g%64) of word g/64, utils.py:144-154).
+ * The result stays device-resident until the next reset/build/destroy.
+ */
+int grmkm_build(grmkm_ctx* ctx);
+
+int grmkm_dims(const grmkm_ctx* ctx, uint64_t* n_kmers, uint32_t* n_words, uint32_t* n_genomes);
+int grmkm_get_stats(const grmkm_ctx* ctx, grmkm_stats* out);
+int grmkm_stage_times(const grmkm_ctx* ctx, grmkm_times* out);
+
+/* canonical k-mers as integers (A0 C1 T2 G3, first base most significant), ascending; cap in elements */
+int grmkm_copy_kmers_packed(grmkm_ctx* ctx, uint64_t* dst, uint64_t cap);
+/* kmer_sequences: U x k bytes, upper-case, no terminator (create.py:216-220, ds.py:84); cap in bytes */
+int grmkm_copy_kmer_strings(grmkm_ctx* ctx, char* dst, uint64_t cap);
+/* kmer_matrix: row-major n_words x U (create.py:224-230); cap in elements */
+int grmkm_copy_matrix(grmkm_ctx* ctx, uint64_t* dst, uint64_t cap);
+/*
+ * Ray Surveyor KmerMatrix.tsv (consumer grammar create.py:121-137,241-264):
+ * "kmers\t<name_1>...\n" then fixed-width rows "<kmer>\t<0|1>...\n".
+ * dst may be NULL to query the size (returned in *written with GRMKM_E_CAPACITY).
+ */
+int grmkm_format_tsv(grmkm_ctx* ctx, const char* const* names, char* dst, uint64_t cap, uint64_t* written);
+
+/* Device pointers of the result (kmers[U], matrix[n_words][U]) for callers that stay on the GPU. */
+int grmkm_device_result(const grmkm_ctx* ctx, const uint64_t** d_kmers, const uint64_t** d_matrix);
+
+/*
+ * Bench/test utility: materialise the synthetic FASTA of BASELINE.md section 4 /
+ * SURVEY.md section 8d on the device.  layout = host table produced by
+ * genomic-resistance-mapping-grm-_b200/synth.py (see grmkm_synth_genome there).
+ */
+int grmkm_synth_fasta_device(grmkm_ctx* ctx, const void* layout, uint64_t layout_bytes, void* dev_dst,
+                             uint64_t dst_bytes);
+
+/*
+ * Multi-GPU (one context per process/GPU; the exchange itself is done by the
+ * host layer with torch.distributed all_to_all over NCCL).
+ *
+ * grmkm_build_partial: local stages only.  Produces partial columns
+ * (hashed k-mer, n_local_words words) grouped by owner rank = hash range,
+ * owner r holding buckets [r*B/P, (r+1)*B/P).  counts[P] receives the number of
+ * partial columns per owner.  Export copies them, owner-major, as
+ * u64 records of (1 + n_local_words) words into caller device memory.
+ *
+ * grmkm_merge_partials: owner side.  parts = device buffer with the received
+ * partial columns of all P sources back to back (source-major), src_counts[P]
+ * their lengths, src_words[P] the words per source; source s contributes matrix
+ * word rows [word_offset_s, word_offset_s + src_words[s]).  Applies the
+ * singleton filter on the full popcount and leaves this owner's slice of the
+ * result in the context (dims/copy_* as after grmkm_build).
+ */
+int grmkm_build_partial(grmkm_ctx* ctx, uint32_t n_ranks, uint64_t* counts);
+int grmkm_export_partials(grmkm_ctx* ctx, void* dev_dst, uint64_t dst_bytes);
+int grmkm_merge_partials(grmkm_ctx* ctx, const void* dev_parts, uint32_t n_ranks, uint32_t rank,
+                         const uint64_t* src_counts, const uint32_t* src_words, uint32_t total_genomes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRMKM_H */

@@ -1,0 +1,193 @@
+"""GPU parity: the CUDA path through the C ABI versus the CPU oracle, bit-exact (-m gpu)."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests import inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_build(genomes, k, min_abundance=1, keep_singletons=False, kind=0, **kw):
+    from grm_b200.builder import KmerMatrixBuilder
+    with KmerMatrixBuilder(k=k, min_abundance=min_abundance, keep_singletons=keep_singletons, input_kind=kind, **kw) as b:
+        b.set_genome_count(len(genomes))
+        for row, files in enumerate(genomes):
+            for f in files:
+                b.add_genome_bytes(row, f)
+        b.build()
+        return b.kmers(), b.matrix(), b.stats
+
+
+def check(genomes, k, min_abundance=1, keep_singletons=False, kind=0, **kw):
+    ref = oracle.build([[(f, kind) for f in files] for files in genomes], k, min_abundance, keep_singletons)
+    kmers, mat, stats = gpu_build(genomes, k, min_abundance, keep_singletons, kind, **kw)
+    assert stats["n_bases"] == ref.n_bases, (stats, ref.n_bases)
+    assert stats["n_windows"] == ref.n_windows, (stats, ref.n_windows)
+    assert kmers.shape == ref.kmers.shape, (kmers.shape, ref.kmers.shape, stats)
+    assert np.array_equal(kmers, ref.kmers)
+    assert mat.shape == ref.matrix.shape
+    assert np.array_equal(mat, ref.matrix)
+    return stats
+
+
+def test_known_answer_k4(gpu):
+    fa = b">r1\nGATTACAGGTNACCTGTAATC\n"
+    kmers, mat, stats = gpu_build([[fa]], 5, keep_singletons=True)
+    assert [hex(int(x)) for x in kmers] == ["0x4f", "0x5b", "0xa1", "0x1b8", "0x209", "0x284"]
+    assert stats["n_windows"] == 12 and stats["n_bases"] == 21 and stats["n_records"] == 1
+    assert (mat == np.uint64(1) << np.uint64(63)).all()
+
+
+@pytest.mark.parametrize("k", [1, 5, 15, 21, 31, 32])
+@pytest.mark.parametrize("keep", [False, True])
+def test_random_small(gpu, k, keep):
+    rng = np.random.default_rng(1000 + k)
+    shared = [inputs.rand_seq(rng, 700), inputs.rand_seq(rng, 300)]
+    genomes = [[inputs.fasta(rng, n_records=int(rng.integers(1, 6)), shared=shared, blank=True)] for _ in range(7)]
+    check(genomes, k, keep_singletons=keep)
+
+
+@pytest.mark.parametrize("G", [1, 2, 63, 64, 65, 130])
+def test_genome_counts_cross_word(gpu, G):
+    rng = np.random.default_rng(G)
+    shared = [inputs.rand_seq(rng, 400)]
+    genomes = [[inputs.fasta(rng, n_records=2, max_len=150, shared=shared)] for _ in range(G)]
+    check(genomes, 11, keep_singletons=(G % 2 == 0))
+
+
+def test_text_quirks(gpu):
+    rng = np.random.default_rng(7)
+    shared = [inputs.rand_seq(rng, 500)]
+    variants = [
+        dict(crlf=True), dict(final_nl=False), dict(junk_prefix=True), dict(width=7), dict(width=0),
+        dict(width=4096 + 37, max_len=20000), dict(p_n=0.2), dict(p_lower=1.0), dict(blank=True, crlf=True),
+        dict(min_len=0, max_len=12), dict(p_iupac=0.1),
+    ]
+    genomes = [[inputs.fasta(rng, n_records=4, shared=shared, **v)] for v in variants]
+    check(genomes, 9, keep_singletons=True)
+    check(genomes, 31, keep_singletons=False)
+
+
+def test_degenerate_inputs(gpu):
+    long_header = b">" + b"x" * 10000 + b"\nACGTACGTACGTACGTTTGACCA\n"
+    genomes = [
+        [b""],                                  # empty file
+        [b"no header at all\nACGTACGT\n"],      # never starts a record
+        [b">only header"],
+        [b">h\n"],
+        [long_header],
+        [b">a\nACGT\n>b\nACGTACGTACGTACGTTTGACCA"],  # no trailing newline
+        [b"\n\n\n>x\n\nACGTACG\n\nTACGTACGTTTGACCA\n\n"],
+        [b">e1\n>e2\n>e3\nACGTACGTACGTACGTTTGACCA\n>e4\n"],
+    ]
+    check(genomes, 8, keep_singletons=True)
+    check(genomes, 8, keep_singletons=False)
+
+
+def test_multiple_files_and_empty_rows(gpu):
+    rng = np.random.default_rng(3)
+    shared = [inputs.rand_seq(rng, 600)]
+    genomes = [
+        [inputs.fasta(rng, shared=shared), inputs.fasta(rng, shared=shared), inputs.fasta(rng, shared=shared)],
+        [],
+        [inputs.fasta(rng, shared=shared)],
+        [],
+    ]
+    check(genomes, 13, keep_singletons=True)
+
+
+def test_large_tiles_and_overflow_splits(gpu):
+    # several tiles / scan blocks per file, and a bucket count too small for the table -> sub-range splits
+    rng = np.random.default_rng(11)
+    shared = [inputs.rand_seq(rng, 300_000)]
+    genomes = [[inputs.fasta(rng, n_records=3, min_len=100_000, max_len=200_000, shared=shared, p_shared=0.5)]
+               for _ in range(5)]
+    stats = check(genomes, 31, keep_singletons=True, bucket_bits=4)
+    assert stats["n_splits"] > 0
+    check(genomes, 31, keep_singletons=False)
+
+
+@pytest.mark.parametrize("min_ab", [1, 2, 3])
+def test_fastq_reads(gpu, min_ab):
+    rng = np.random.default_rng(50 + min_ab)
+    src = [inputs.rand_seq(rng, 3000) for _ in range(3)]
+    genomes = []
+    for g in range(6):
+        s = src[g % 3]
+        genomes.append([inputs.fastq(rng, s, n_reads=400, read_len=60, crlf=(g == 1), final_nl=(g != 2)),
+                        inputs.fastq(rng, s, n_reads=100, read_len=45)])
+    check(genomes, 21, min_abundance=min_ab, keep_singletons=False, kind=1)
+    check(genomes, 21, min_abundance=min_ab, keep_singletons=True, kind=1)
+
+
+def test_tsv_and_strings(gpu):
+    from grm_b200.builder import KmerMatrixBuilder
+    rng = np.random.default_rng(5)
+    shared = [inputs.rand_seq(rng, 800)]
+    genomes = [[inputs.fasta(rng, shared=shared)] for _ in range(5)]
+    names = ["562.1", "my genome", "b", "c", "d"]
+    ref = oracle.build([[(f, 0) for f in files] for files in genomes], 17, 1, True, want_tsv_names=names)
+    with KmerMatrixBuilder(k=17, keep_singletons=True) as b:
+        for row, files in enumerate(genomes):
+            b.add_genome_bytes(row, files[0])
+        b.build()
+        assert b.tsv(names).tobytes() == ref.tsv
+        strs = b.kmer_strings()
+        assert [s.decode() for s in strs] == [oracle.py_kmer_string(int(x), 17) for x in ref.kmers]
+
+
+def test_synth_device_matches_numpy_and_oracle(gpu):
+    import ctypes as C
+    import torch
+    from grm_b200 import synth
+    from grm_b200.builder import KmerMatrixBuilder
+    cfg = synth.SynthConfig(seed=synth.MASTER_SEED + 1, core_len=30_000, island_len=500, n_islands=40, n_contigs=7)
+    ids = list(range(6))
+    lay, total, spans = synth.build_layout(cfg, ids)
+    buf = torch.empty(total, dtype=torch.uint8, device="cuda")
+    with KmerMatrixBuilder(k=31, keep_singletons=False) as b:
+        b._check(b._lib.grmkm_synth_fasta_device(b._ctx, C.c_void_p(lay.ctypes.data), lay.nbytes,
+                                                 C.c_void_p(buf.data_ptr()), total))
+        host = buf.cpu().numpy()
+        texts = []
+        for g, (off, ln) in zip(ids, spans):
+            ref = synth.genome_fasta(cfg, g)
+            assert host[off:off + ln].tobytes() == ref, f"genome {g} differs"
+            texts.append(ref)
+        # device-resident inputs, no host copy
+        for row, (off, ln) in enumerate(spans):
+            b.add_genome_device(row, buf.data_ptr() + off, ln)
+        b.build()
+        assert b.stats["h2d_bytes"] == 0
+        ref = oracle.build([[(t, 0)] for t in texts], 31, 1, False)
+        assert np.array_equal(b.kmers(), ref.kmers)
+        assert np.array_equal(b.matrix(), ref.matrix)
+        assert b.stats["n_bases"] == synth.n_bases_of(cfg, ids)
+
+
+def test_rebuild_reuses_context(gpu):
+    from grm_b200.builder import KmerMatrixBuilder
+    rng = np.random.default_rng(9)
+    with KmerMatrixBuilder(k=15, keep_singletons=True) as b:
+        for it in range(3):
+            genomes = [[inputs.fasta(rng, max_len=2000 * (it + 1))] for _ in range(3)]
+            b.reset()
+            for row, files in enumerate(genomes):
+                b.add_genome_bytes(row, files[0])
+            b.build()
+            ref = oracle.build([[(f, 0) for f in files] for files in genomes], 15, 1, True)
+            assert np.array_equal(b.kmers(), ref.kmers) and np.array_equal(b.matrix(), ref.matrix)
+
+
+def test_errors(gpu):
+    from grm_b200.builder import KmerMatrixBuilder, GrmkmError
+    with pytest.raises(GrmkmError) as e:
+        KmerMatrixBuilder(k=33)
+    assert e.value.code == -2
+    with KmerMatrixBuilder(k=5) as b:
+        with pytest.raises(GrmkmError):
+            b.dims
+        with pytest.raises(GrmkmError) as e2:
+            b.add_genome_files(0, ["/nonexistent/file.fna"])
+        assert e2.value.code == -5
