@@ -163,10 +163,11 @@ k_scan_apply(const Sum* __restrict__ tsum, uint64_t n_tiles, const uint32_t* __r
 #pragma unroll
     for (int i = 0; i < kScanTilesPerThread; ++i) {
         if (base + i < n_tiles) {
+            const uint32_t f = tile_file[base + i];
+            // a file always starts in state 0, whatever state the previous file ended in
+            if (files[f].tile_begin == base + i) { file_stream_start[f] = pos; st = 0; }
             tile_state[base + i] = (uint8_t)st;
             tile_pos[base + i] = pos;
-            const uint32_t f = tile_file[base + i];
-            if (files[f].tile_begin == base + i) file_stream_start[f] = pos;
             pos += sum_cnt(t[i], st); st = sum_end(t[i], st);
         }
     }
