@@ -51,7 +51,7 @@ struct grmkm_ctx {
     // device buffers (grow-only, reused across builds)
     DevBuf in, files, hdr0, tsum, tile_file, tile_state, tile_pos, bsum, bstate, bpos, fss, codes, valid, hist,
         offsets, offsets2, bcounts, records, records2, ukeys, uwords, skeys, sidx_a, sidx_b, shist, kmers, matrix,
-        scalars, fmt, synth;
+        scalars, fmt, synth, owner_start, refs;
     size_t device_bytes = 0;
 
     cudaEvent_t ev[T_N]{};
@@ -67,6 +67,8 @@ struct grmkm_ctx {
     // multi-GPU partial state
     uint32_t part_ranks = 0;
     std::vector<uint64_t> part_counts;
+    uint64_t part_total = 0, part_cap = 0;
+    uint32_t part_words = 0;
     uint32_t cur_bucket_bits = 0;
 };
 
@@ -152,6 +154,23 @@ size_t agg_smem_budget(const grmkm_ctx* c) {
     // leave room for the kernel's static shared memory
     size_t lim = c->smem_optin ? c->smem_optin : 227 * 1024;
     return lim - 4096;
+}
+
+// table capacity for W words per column and the bucket count that keeps a bucket's distinct k-mers
+// (estimated as 3x the largest genome) at about half of it
+uint32_t table_slots(const grmkm_ctx* c, uint32_t W) {
+    const size_t budget = agg_smem_budget(c);
+    return (uint32_t)std::min<size_t>(16384, budget / (8 * (1 + (size_t)W)));
+}
+uint32_t auto_bucket_bits(const grmkm_ctx* c, uint32_t G) {
+    std::vector<uint64_t> row_bytes(std::max(G, 1u), 0);
+    for (const Input& in : c->inputs) if (in.row < G) row_bytes[in.row] += in.len;
+    const uint64_t max_row = *std::max_element(row_bytes.begin(), row_bytes.end());
+    const uint32_t slots = table_slots(c, (G + 63) / 64);
+    const uint64_t u_est = 3 * max_row + 1024;
+    const uint64_t per = std::max<uint64_t>(1, slots / 2);
+    const uint32_t row_bits = std::max(1u, ceil_log2(G));
+    return std::max(row_bits, std::min(15u, std::max(6u, ceil_log2((u_est + per - 1) / per))));
 }
 
 // sort columns (ukeys/uwords, n items, stride ucap) by key into kmers/matrix
@@ -277,7 +296,7 @@ void grmkm_destroy(grmkm_ctx* c) {
     DevBuf* all[] = {&c->in, &c->files, &c->hdr0, &c->tsum, &c->tile_file, &c->tile_state, &c->tile_pos, &c->bsum,
                      &c->bstate, &c->bpos, &c->fss, &c->codes, &c->valid, &c->hist, &c->offsets, &c->offsets2,
                      &c->bcounts, &c->records, &c->records2, &c->ukeys, &c->uwords, &c->skeys, &c->sidx_a, &c->sidx_b,
-                     &c->shist, &c->kmers, &c->matrix, &c->scalars, &c->fmt, &c->synth};
+                     &c->shist, &c->kmers, &c->matrix, &c->scalars, &c->fmt, &c->synth, &c->owner_start, &c->refs};
     for (DevBuf* b : all) release(c, *b);
     if (c->ev_ok) for (int i = 0; i < T_N; ++i) cudaEventDestroy(c->ev[i]);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -339,7 +358,7 @@ int grmkm_set_genome_count(grmkm_ctx* c, uint32_t n) {
 // ------------------------------------------------------------------------------------------------
 // the build
 // ------------------------------------------------------------------------------------------------
-static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/) {
+static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32_t n_ranges) {
     CU_TRY(c, cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     Launches L;
@@ -354,9 +373,11 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/) {
     P.G = std::max(maxrow, c->n_genomes_decl);
     P.W = (P.G + 63) / 64;
     c->G = P.G; c->W = P.W; c->U = 0;
+    c->part_ranks = 0; c->part_total = 0; c->part_words = P.W;
     if (P.G == 0 || P.F == 0) {
-        c->built = true;
+        c->built = (mode == 0);
         c->stats.n_genomes = P.G; c->stats.n_words = P.W;
+        if (mode == 1) { c->part_ranks = n_ranges; c->part_counts.assign(n_ranges, 0); }
         return GRMKM_OK;
     }
     P.row_bits = std::max(1u, ceil_log2(P.G));
@@ -365,7 +386,6 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/) {
     // ---- file table, staging offsets, tiles
     std::vector<FileDesc> fds(P.F);
     std::vector<uint64_t> stage_off(P.F, 0);
-    std::vector<uint64_t> row_bytes(P.G, 0);
     uint64_t stage_total = 0, tiles = 0;
     for (uint32_t f = 0; f < P.F; ++f) {
         const Input& in = c->inputs[f];
@@ -373,7 +393,6 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/) {
         fds[f].len = in.len; fds[f].row = in.row; fds[f].kind = in.kind; fds[f].tile_begin = tiles;
         tiles += std::max<uint64_t>(1, (in.len + kTileBytes - 1) / kTileBytes);
         P.max_stream += in.len;
-        row_bytes[in.row] += in.len;
     }
     P.in_bytes = P.max_stream;
     P.n_tiles = tiles;
@@ -388,13 +407,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/) {
     if (P.slots < 256) return fail(c, GRMKM_E_UNSUPPORTED, "too many genomes for the shared-memory column table");
     P.slots = std::min(P.slots, 16384u);
     P.agg_smem = (size_t)P.slots * 8 * (1 + Wtab);
-    if (c->cfg.bucket_bits) P.bucket_bits = c->cfg.bucket_bits;
-    else {
-        const uint64_t max_row = *std::max_element(row_bytes.begin(), row_bytes.end());
-        const uint64_t u_est = 3 * max_row + 1024;
-        const uint64_t per = std::max<uint64_t>(1, P.slots / 2);
-        P.bucket_bits = std::min(15u, std::max(6u, ceil_log2((u_est + per - 1) / per)));
-    }
+    P.bucket_bits = c->cfg.bucket_bits ? c->cfg.bucket_bits : auto_bucket_bits(c, P.G);
     P.bucket_bits = std::max(P.bucket_bits, P.row_bits);
     if (P.bucket_bits > 15) return fail(c, GRMKM_E_UNSUPPORTED, "bucket_bits > 15");
     c->cur_bucket_bits = P.bucket_bits;
@@ -505,7 +518,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/) {
         ap.records = agg_records; ap.offsets = agg_offsets; ap.B = B; ap.bucket_bits = P.bucket_bits;
         ap.row_bits = P.row_bits; ap.n_words = 1;
         ap.slots = (uint32_t)std::min<size_t>(16384, budget / 16);
-        ap.mode = 2; ap.min_abundance = c->cfg.min_abundance;
+        ap.mode = 2; ap.min_abundance = c->cfg.min_abundance; ap.b_begin = 0; ap.b_end = B;
         ap.scalars = (unsigned long long*)d_scalars;
         ap.bucket_out_counts = (unsigned long long*)c->bcounts.p;
         ap.out_records = (unsigned long long*)c->records2.p;
@@ -538,14 +551,23 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/) {
         ap.out_keys = (unsigned long long*)c->ukeys.p; ap.out_words = (unsigned long long*)c->uwords.p;
         ap.cap = ucap; ap.scalars = (unsigned long long*)d_scalars;
         ap.bucket_out_counts = (unsigned long long*)c->bcounts.p;
-        if (mode == 0) {
-            CU_TRY(c, cudaFuncSetAttribute(k_aggregate<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.agg_smem));
-            k_aggregate<0><<<agrid, kAggThreads, P.agg_smem, st>>>(ap);
-        } else {
-            CU_TRY(c, cudaFuncSetAttribute(k_aggregate<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.agg_smem));
-            k_aggregate<1><<<agrid, kAggThreads, P.agg_smem, st>>>(ap);
+        ENSURE(c, c->owner_start, (size_t)(n_ranges + 1) * 8);
+        uint64_t* d_owner = (uint64_t*)c->owner_start.p;
+        for (uint32_t r = 0; r < n_ranges; ++r) {
+            ap.b_begin = (uint32_t)((uint64_t)B * r / n_ranges);
+            ap.b_end = (uint32_t)((uint64_t)B * (r + 1) / n_ranges);
+            CU_TRY(c, cudaMemcpyAsync(d_owner + r, d_scalars + S_U_NEEDED, 8, cudaMemcpyDeviceToDevice, st));
+            const uint32_t grid = std::max(1u, std::min<uint32_t>(ap.b_end - ap.b_begin, (uint32_t)c->sm_count));
+            if (mode == 0) {
+                CU_TRY(c, cudaFuncSetAttribute(k_aggregate<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.agg_smem));
+                k_aggregate<0><<<grid, kAggThreads, P.agg_smem, st>>>(ap);
+            } else {
+                CU_TRY(c, cudaFuncSetAttribute(k_aggregate<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.agg_smem));
+                k_aggregate<1><<<grid, kAggThreads, P.agg_smem, st>>>(ap);
+            }
+            L.n++;
         }
-        L.n++;
+        CU_TRY(c, cudaMemcpyAsync(d_owner + n_ranges, d_scalars + S_U_NEEDED, 8, cudaMemcpyDeviceToDevice, st));
         CU_TRY(c, cudaGetLastError());
         CU_TRY(c, cudaMemcpyAsync(sc, d_scalars, sizeof sc, cudaMemcpyDeviceToHost, st));
         CU_TRY(c, cudaStreamSynchronize(st));
@@ -569,6 +591,14 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/) {
 
     c->U = U;
     c->built = (mode == 0);
+    if (mode == 1) {
+        std::vector<uint64_t> own(n_ranges + 1);
+        CU_TRY(c, cudaMemcpy(own.data(), c->owner_start.p, (n_ranges + 1) * 8, cudaMemcpyDeviceToHost));
+        c->part_ranks = n_ranges;
+        c->part_counts.resize(n_ranges);
+        for (uint32_t r = 0; r < n_ranges; ++r) c->part_counts[r] = own[r + 1] - own[r];
+        c->part_total = U; c->part_cap = ucap; c->part_words = P.W;
+    }
     grmkm_stats& s = c->stats;
     s.n_input_bytes = P.in_bytes;
     s.n_records = sc[S_N_RECORDS];
@@ -592,7 +622,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/) {
 
 int grmkm_build(grmkm_ctx* c) {
     if (check_ctx(c)) return GRMKM_E_INVALID;
-    return build_impl(c, 0);
+    return build_impl(c, 0, 1);
 }
 
 int grmkm_dims(const grmkm_ctx* c, uint64_t* n_kmers, uint32_t* n_words, uint32_t* n_genomes) {
@@ -722,21 +752,130 @@ int grmkm_synth_fasta_device(grmkm_ctx* c, const void* layout, uint64_t layout_b
     return GRMKM_OK;
 }
 
+int grmkm_set_bucket_bits(grmkm_ctx* c, uint32_t bits) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    if (bits && (bits < 4 || bits > 15)) return fail(c, GRMKM_E_INVALID, "bucket_bits must be 0 (auto) or 4..15");
+    c->cfg.bucket_bits = bits;
+    return GRMKM_OK;
+}
+
+int grmkm_plan_bucket_bits(grmkm_ctx* c, uint32_t* bits) {
+    if (check_ctx(c) || !bits) return GRMKM_E_INVALID;
+    uint32_t maxrow = 0;
+    for (const Input& in : c->inputs) maxrow = std::max(maxrow, in.row + 1);
+    *bits = auto_bucket_bits(c, std::max(1u, std::max(maxrow, c->n_genomes_decl)));
+    return GRMKM_OK;
+}
+
 int grmkm_build_partial(grmkm_ctx* c, uint32_t n_ranks, uint64_t* counts) {
     if (check_ctx(c)) return GRMKM_E_INVALID;
-    (void)n_ranks; (void)counts;
-    return fail(c, GRMKM_E_UNSUPPORTED, "grmkm_build_partial: not implemented yet");
+    if (n_ranks < 1 || n_ranks > 16 || !counts) return fail(c, GRMKM_E_INVALID, "n_ranks must be 1..16");
+    int r = build_impl(c, 1, n_ranks);
+    if (r) return r;
+    for (uint32_t i = 0; i < n_ranks; ++i) counts[i] = c->part_counts[i];
+    return GRMKM_OK;
 }
+
 int grmkm_export_partials(grmkm_ctx* c, void* dev_dst, uint64_t dst_bytes) {
     if (check_ctx(c)) return GRMKM_E_INVALID;
-    (void)dev_dst; (void)dst_bytes;
-    return fail(c, GRMKM_E_UNSUPPORTED, "grmkm_export_partials: not implemented yet");
+    if (!c->part_ranks) return fail(c, GRMKM_E_INVALID, "no partial result: call grmkm_build_partial first");
+    const uint64_t need = c->part_total * (1 + (uint64_t)c->part_words) * 8;
+    if (dst_bytes < need) return fail(c, GRMKM_E_CAPACITY, "partial export buffer too small");
+    if (!c->part_total) return GRMKM_OK;
+    if (!dev_dst) return fail(c, GRMKM_E_INVALID, "null dst");
+    CU_TRY(c, cudaSetDevice(c->device));
+    k_export_aos<<<(uint32_t)((c->part_total + 255) / 256), 256, 0, c->stream>>>(
+        (const unsigned long long*)c->ukeys.p, (const unsigned long long*)c->uwords.p, c->part_total, c->part_words,
+        c->part_cap, (unsigned long long*)dev_dst);
+    CU_TRY(c, cudaGetLastError());
+    c->stats.n_launches++;
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return GRMKM_OK;
 }
+
 int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, uint32_t rank, const uint64_t* src_counts,
                          const uint32_t* src_words, uint32_t total_genomes) {
     if (check_ctx(c)) return GRMKM_E_INVALID;
-    (void)dev_parts; (void)n_ranks; (void)rank; (void)src_counts; (void)src_words; (void)total_genomes;
-    return fail(c, GRMKM_E_UNSUPPORTED, "grmkm_merge_partials: not implemented yet");
+    if (n_ranks < 1 || n_ranks > 16 || rank >= n_ranks || !src_counts || !src_words)
+        return fail(c, GRMKM_E_INVALID, "bad merge arguments");
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    Launches L;
+    MergeSrc ms{};
+    ms.n_src = n_ranks;
+    uint64_t n_total = 0, words = 0;
+    uint32_t W_total = 0;
+    AggParams ap{};
+    for (uint32_t s = 0; s < n_ranks; ++s) {
+        ms.ent_off[s] = n_total; ms.word_off[s] = words; ms.width[s] = 1 + src_words[s];
+        ap.src_words[s] = src_words[s]; ap.src_woff[s] = W_total;
+        n_total += src_counts[s]; words += src_counts[s] * (1 + (uint64_t)src_words[s]); W_total += src_words[s];
+    }
+    ms.ent_off[n_ranks] = n_total; ms.word_off[n_ranks] = words;
+    if (W_total != (total_genomes + 63) / 64) return fail(c, GRMKM_E_INVALID, "source words do not add up to the genome count");
+    if (n_total && !dev_parts) return fail(c, GRMKM_E_INVALID, "null parts");
+    c->built = false; c->U = 0; c->W = W_total; c->G = total_genomes;
+    c->times = grmkm_times{};
+    const uint32_t launches_before = c->stats.n_launches;
+    if (n_total == 0) { c->built = true; c->stats.n_kmers = 0; return GRMKM_OK; }
+    const uint32_t slots = table_slots(c, W_total);
+    if (slots < 256) return fail(c, GRMKM_E_UNSUPPORTED, "too many genomes for the shared-memory column table");
+    const size_t smem = (size_t)slots * 8 * (1 + W_total);
+    // every rank sees 1/P of the hash space: size the buckets for n_total * P entries over the full range
+    const uint64_t per = std::max<uint64_t>(1, slots / 2);
+    uint32_t mb = std::min(20u, std::max(6u, ceil_log2((n_total * n_ranks + per - 1) / per)));
+    const uint32_t B = 1u << mb;
+    ENSURE(c, c->scalars, S_COUNT * 8);
+    ENSURE(c, c->hist, (size_t)B * 8);
+    ENSURE(c, c->offsets, (size_t)(B + 1) * 8);
+    ENSURE(c, c->refs, n_total * 8);
+    uint64_t ucap = std::min<uint64_t>(n_total, 0xFFFFFFFFULL);
+    ENSURE(c, c->ukeys, ucap * 8);
+    ENSURE(c, c->uwords, (size_t)ucap * W_total * 8);
+    uint64_t* d_scalars = (uint64_t*)c->scalars.p;
+    if (c->ev_ok) cudaEventRecord(c->ev[T_START], st);
+    CU_TRY(c, cudaMemsetAsync(c->scalars.p, 0, S_COUNT * 8, st));
+    CU_TRY(c, cudaMemsetAsync(c->hist.p, 0, (size_t)B * 8, st));
+    const uint32_t pgrid = (uint32_t)((n_total + 255) / 256);
+    const unsigned long long* parts = (const unsigned long long*)dev_parts;
+    k_merge_partition<0><<<pgrid, 256, 0, st>>>(parts, ms, n_total, mb, (unsigned long long*)c->hist.p, nullptr);
+    k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->hist.p, (unsigned long long*)c->offsets.p, B, d_scalars,
+                                         S_N_WINDOWS);
+    k_merge_partition<1><<<pgrid, 256, 0, st>>>(parts, ms, n_total, mb, (unsigned long long*)c->hist.p,
+                                                (unsigned long long*)c->refs.p);
+    L.n += 3;
+    CU_TRY(c, cudaGetLastError());
+    if (c->ev_ok) cudaEventRecord(c->ev[T_SCATTER], st);
+    ap.records = (const unsigned long long*)c->refs.p; ap.offsets = (const unsigned long long*)c->offsets.p;
+    ap.B = B; ap.bucket_bits = mb; ap.row_bits = 0; ap.n_words = W_total; ap.slots = slots;
+    ap.keep_singletons = c->cfg.keep_singletons; ap.mode = 3;
+    ap.out_keys = (unsigned long long*)c->ukeys.p; ap.out_words = (unsigned long long*)c->uwords.p;
+    ap.cap = ucap; ap.scalars = (unsigned long long*)d_scalars; ap.parts = parts;
+    ap.b_begin = 0; ap.b_end = B;
+    CU_TRY(c, cudaFuncSetAttribute(k_aggregate<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_aggregate<3><<<std::min<uint32_t>(B, (uint32_t)c->sm_count * 2), kAggThreads, smem, st>>>(ap);
+    L.n++;
+    CU_TRY(c, cudaGetLastError());
+    uint64_t sc[S_COUNT];
+    CU_TRY(c, cudaMemcpyAsync(sc, d_scalars, sizeof sc, cudaMemcpyDeviceToHost, st));
+    CU_TRY(c, cudaStreamSynchronize(st));
+    if (c->ev_ok) cudaEventRecord(c->ev[T_AGG], st);
+    const uint64_t U = sc[S_U_NEEDED];
+    int r = sort_and_gather(c, U, W_total, ucap, 2 * c->cfg.k, (c->cfg.flags & GRMKM_FLAG_HASH_ORDER) != 0, L);
+    if (r) return r;
+    if (c->ev_ok) cudaEventRecord(c->ev[T_SORT], st);
+    CU_TRY(c, cudaStreamSynchronize(st));
+    c->U = U; c->built = true;
+    c->stats.n_kmers = U; c->stats.n_distinct = sc[S_N_DISTINCT]; c->stats.n_words = W_total;
+    c->stats.n_genomes = total_genomes; c->stats.n_splits += sc[S_N_SPLITS];
+    c->stats.n_launches = launches_before + L.n;
+    if (c->ev_ok) {
+        cudaEventElapsedTime(&c->times.scatter, c->ev[T_START], c->ev[T_SCATTER]);
+        cudaEventElapsedTime(&c->times.aggregate, c->ev[T_SCATTER], c->ev[T_AGG]);
+        cudaEventElapsedTime(&c->times.sort, c->ev[T_AGG], c->ev[T_SORT]);
+        cudaEventElapsedTime(&c->times.total, c->ev[T_START], c->ev[T_SORT]);
+    }
+    return GRMKM_OK;
 }
 
 }  // extern "C"

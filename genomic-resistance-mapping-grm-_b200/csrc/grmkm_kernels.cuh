@@ -420,6 +420,11 @@ struct AggParams {
     unsigned long long* scalars;
     unsigned long long* bucket_out_counts;  // mode 1/2: entries emitted per bucket (atomic)
     unsigned long long* out_records;        // mode 2: filtered records, written at the bucket's own offset
+    uint32_t b_begin, b_end;                // bucket range handled by this launch
+    // mode 3 (owner-side merge of partial columns): records are refs (word offset << 8 | source)
+    const unsigned long long* parts;
+    uint32_t src_words[16];
+    uint32_t src_woff[16];
 };
 
 __device__ __forceinline__ uint32_t slot_of(uint64_t key, uint32_t slots) {
@@ -441,13 +446,14 @@ k_aggregate(const AggParams p) {
     __shared__ uint32_t s_red[kAggThreads / 32];
     const uint32_t slots = p.slots;
     const uint32_t W = (MODE == 2) ? 1u : p.n_words;
+    constexpr bool kFinal = (MODE == 0 || MODE == 3);   // emits filtered k-mer columns
     unsigned long long* keys = s_tab;
     unsigned long long* words = s_tab + slots;
     const uint32_t key_bits = (MODE == 2) ? (64 - p.bucket_bits + p.row_bits) : (64 - p.bucket_bits);
     const uint64_t row_mask = (1ULL << p.row_bits) - 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    for (uint32_t b = blockIdx.x; b < p.B; b += gridDim.x) {
+    for (uint32_t b = p.b_begin + blockIdx.x; b < p.b_end; b += gridDim.x) {
         const unsigned long long rbeg = p.offsets[b], rend = p.offsets[b + 1];
         if (rbeg == rend) continue;
         __syncthreads();
@@ -468,7 +474,9 @@ k_aggregate(const AggParams p) {
                 if (*(volatile uint32_t*)&s_overflow) break;
                 const unsigned long long rec = p.records[r];
                 unsigned long long key; uint32_t row = 0;
+                const unsigned long long* ent = nullptr;
                 if (MODE == 2) key = rec;
+                else if (MODE == 3) { ent = p.parts + (rec >> 8); key = ent[0] & ((1ULL << key_bits) - 1); }
                 else { key = rec >> p.row_bits; row = (uint32_t)(rec & row_mask); }
                 if (depth && (key >> (key_bits - depth)) != ridx) continue;
                 uint32_t slot = slot_of(key, slots);
@@ -482,6 +490,12 @@ k_aggregate(const AggParams p) {
                 if (!hit) { s_overflow = 1; break; }
                 if (MODE == 2) {
                     atomicAdd((uint32_t*)&words[slot], 1u);
+                } else if (MODE == 3) {
+                    const uint32_t src = (uint32_t)(rec & 255u), nw = p.src_words[src], wo = p.src_woff[src];
+                    for (uint32_t w = 0; w < nw; ++w) {
+                        const unsigned long long v = ent[1 + w];
+                        if (v) atomicOr(&words[(wo + w) * slots + slot], v);
+                    }
                 } else {
                     const uint32_t bit = 63u - (row & 63u);      // utils.py:144-154
                     uint32_t* w32 = (uint32_t*)&words[(row >> 6) * slots + slot];
@@ -556,7 +570,7 @@ k_aggregate(const AggParams p) {
                         p.out_records[o] = key;
                     } else if (o < p.cap) {
                         const unsigned long long h = ((unsigned long long)b << key_bits) | key;
-                        p.out_keys[o] = (MODE == 0) ? unfmix64(h) : h;
+                        p.out_keys[o] = kFinal ? unfmix64(h) : h;
                         for (uint32_t w = 0; w < W; ++w) p.out_words[w * p.cap + o] = words[w * slots + i];
                     }
                 }
@@ -568,6 +582,42 @@ k_aggregate(const AggParams p) {
         }
     }
     (void)warp; (void)s_red;
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-GPU: partial columns out (AoS records for the all-to-all) and owner-side partition
+// ------------------------------------------------------------------------------------------
+// record i = [hash, word_0 .. word_{W-1}]
+__global__ void k_export_aos(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ words,
+                             uint64_t n, uint32_t W, uint64_t cap, unsigned long long* __restrict__ dst) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long* d = dst + i * (1 + W);
+    d[0] = keys[i];
+    for (uint32_t w = 0; w < W; ++w) d[1 + w] = words[(uint64_t)w * cap + i];
+}
+
+struct MergeSrc {
+    unsigned long long ent_off[17];    // first entry index of each source (prefix sum of counts)
+    unsigned long long word_off[17];   // first u64 word of each source in the receive buffer
+    uint32_t width[16];                // 1 + words of the source
+    uint32_t n_src;
+};
+
+// count (SCATTER=0) or scatter refs (SCATTER=1) of received partial columns by hash bucket
+template <int SCATTER>
+__global__ void k_merge_partition(const unsigned long long* __restrict__ parts, const MergeSrc ms, uint64_t n_total,
+                                  uint32_t bucket_bits, unsigned long long* __restrict__ hist_cursor,
+                                  unsigned long long* __restrict__ refs) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_total) return;
+    uint32_t s = 0;
+    while (s + 1 < ms.n_src && ms.ent_off[s + 1] <= i) ++s;
+    const unsigned long long woff = ms.word_off[s] + (i - ms.ent_off[s]) * ms.width[s];
+    const unsigned long long h = parts[woff];
+    const uint32_t b = (uint32_t)(h >> (64 - bucket_bits));
+    if (SCATTER == 0) atomicAdd(&hist_cursor[b], 1ULL);
+    else refs[atomicAdd(&hist_cursor[b], 1ULL)] = (woff << 8) | s;
 }
 
 // compact per-bucket filtered records (mode 2 leaves them at the bucket's old offset) into new offsets

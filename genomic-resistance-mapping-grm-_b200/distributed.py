@@ -1,0 +1,199 @@
+"""Multi-GPU k-mer matrix build: one process per GPU, torch.distributed for the plumbing.
+
+Sharding: genome ROWS are split across ranks in 64-aligned blocks of the
+final row order, so a rank's contribution to a column is whole uint64 words.  Each rank runs the
+local stages (parse -> extract -> partition -> per-bucket aggregation) and ends with *partial
+columns* (hashed k-mer, its local words).  Partial columns are routed to the rank that owns
+their hash range with ONE all-to-all (NCCL over NVLink on GPUs; gloo in the CPU tests), and the
+owner merges them, applies the singleton filter on the full popcount and orders its slice.
+This replaces the hash-routed actor messages of ``mpiexec -n 4 Ray`` (src/app.py:1310).
+
+The compute engine is injectable so the host-side logic can be tested without a GPU
+(tests/test_distributed_cpu.py drives it with an oracle-backed engine over gloo).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Sequence
+
+import numpy as np
+
+from . import native
+from .native import FASTA
+
+
+def row_partition(n_genomes: int, world: int) -> list[range]:
+    """64-aligned blocks of rows per rank (whole words per rank)."""
+    words = (n_genomes + 63) // 64
+    out, w0 = [], 0
+    for r in range(world):
+        nw = words // world + (1 if r < words % world else 0)
+        lo, hi = min(64 * w0, n_genomes), min(64 * (w0 + nw), n_genomes)
+        out.append(range(lo, hi))
+        w0 += nw
+    return out
+
+
+def words_per_rank(n_genomes: int, world: int) -> list[int]:
+    words = (n_genomes + 63) // 64
+    return [words // world + (1 if r < words % world else 0) for r in range(world)]
+
+
+def init_process_group_from_env(backend: str | None = None):
+    import torch
+    import torch.distributed as dist
+    if dist.is_initialized():
+        return dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29511")
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    kw = {}
+    if backend == "nccl":
+        kw["device_id"] = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group(backend=backend, rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]), **kw)
+    return dist
+
+
+class CudaEngine:
+    """Local stages on one GPU through the C ABI (grmkm_build_partial / export / merge)."""
+
+    def __init__(self, builder):
+        self.b = builder
+
+    def plan_bucket_bits(self) -> int:
+        v = C.c_uint32()
+        self.b._check(self.b._lib.grmkm_plan_bucket_bits(self.b._ctx, C.byref(v)))
+        return int(v.value)
+
+    def set_bucket_bits(self, bits: int):
+        self.b._check(self.b._lib.grmkm_set_bucket_bits(self.b._ctx, int(bits)))
+
+    def build_partial(self, world: int, n_local_words: int):
+        """-> (counts per owner [world], send tensor int64 on the GPU, AoS records of 1+n_local_words)."""
+        import torch
+        counts = (C.c_uint64 * world)()
+        self.b._check(self.b._lib.grmkm_build_partial(self.b._ctx, world, counts))
+        counts = [int(x) for x in counts]
+        self.launches = self.b.stats["n_launches"]
+        n = sum(counts) * (1 + n_local_words)
+        send = torch.empty(max(n, 1), dtype=torch.int64, device="cuda")
+        self.b._check(self.b._lib.grmkm_export_partials(self.b._ctx, C.c_void_p(send.data_ptr()), send.numel() * 8))
+        self.launches += 1
+        return counts, send[:n]
+
+    def merge(self, recv, world: int, rank: int, src_counts: Sequence[int], src_words: Sequence[int], n_genomes: int):
+        sc = (C.c_uint64 * world)(*src_counts)
+        sw = (C.c_uint32 * world)(*src_words)
+        before = self.b.stats["n_launches"]
+        self.b._check(self.b._lib.grmkm_merge_partials(self.b._ctx, C.c_void_p(recv.data_ptr() if recv.numel() else 0),
+                                                       world, rank, sc, sw, n_genomes))
+        self.launches += self.b.stats["n_launches"] - before
+
+    def result(self):
+        return self.b.kmers(), self.b.matrix()
+
+
+class DistributedBuilder:
+    """Same surface as KmerMatrixBuilder, for rank `rank` of `world` processes.
+
+    Rows are LOCAL indices into ``local_rows`` (the global genome rows this rank holds).
+    After build(), kmers()/matrix() return this rank's slice of the columns (all word rows);
+    gather() assembles the global matrix in ascending k-mer order on rank 0.
+    """
+
+    def __init__(self, k=31, min_abundance=1, keep_singletons=False, n_genomes=0, rank=0, world=1,
+                 input_kind=FASTA, stream=None, device=-1, engine=None, builder=None):
+        self.k, self.rank, self.world, self.n_genomes = int(k), int(rank), int(world), int(n_genomes)
+        self.local_rows = row_partition(self.n_genomes, self.world)[self.rank]
+        self.src_words = words_per_rank(self.n_genomes, self.world)
+        self.launches = 0
+        self.builder = builder
+        if engine is None:
+            from .builder import KmerMatrixBuilder
+            self.builder = KmerMatrixBuilder(k=k, min_abundance=min_abundance, keep_singletons=keep_singletons,
+                                             input_kind=input_kind, device=device, stream=stream)
+            engine = CudaEngine(self.builder)
+        self.engine = engine
+        self._n_kmers = 0
+
+    # -- inputs (local row index) ----------------------------------------------------------------
+    def reset(self):
+        self.builder.reset()
+        self.builder.set_genome_count(len(self.local_rows) if self.world > 1 else self.n_genomes)
+
+    def add_genome_bytes(self, local_row: int, data):
+        self.builder.add_genome_bytes(local_row, data)
+
+    def add_genome_device(self, local_row: int, ptr: int, n: int):
+        self.builder.add_genome_device(local_row, ptr, n)
+
+    def add_genome_files(self, local_row: int, paths):
+        self.builder.add_genome_files(local_row, paths)
+
+    # -- build -------------------------------------------------------------------------------------
+    def build(self):
+        if self.world == 1:
+            self.builder.build()
+            self.launches = self.builder.stats["n_launches"]
+            self._n_kmers = self.builder.dims[0]
+            return self
+        import torch
+        import torch.distributed as dist
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        # 1. identical hash partition on every rank
+        bits = torch.tensor([self.engine.plan_bucket_bits()], dtype=torch.int64, device=dev)
+        dist.all_reduce(bits, op=dist.ReduceOp.MAX)
+        self.engine.set_bucket_bits(int(bits.item()))
+        # 2. local stages -> partial columns grouped by owner
+        wl = self.src_words[self.rank]
+        counts, send = self.engine.build_partial(self.world, wl)
+        # 3. one all-to-all: counts first, then the records
+        c_out = torch.tensor(counts, dtype=torch.int64, device=dev)
+        c_in = torch.empty_like(c_out)
+        dist.all_to_all_single(c_in, c_out)
+        src_counts = [int(x) for x in c_in.tolist()]
+        in_split = [c * (1 + wl) for c in counts]
+        out_split = [src_counts[s] * (1 + self.src_words[s]) for s in range(self.world)]
+        recv = torch.empty(sum(out_split), dtype=torch.int64, device=send.device)
+        dist.all_to_all_single(recv, send, output_split_sizes=out_split, input_split_sizes=in_split)
+        self.exchange_bytes = int(send.numel() * 8)
+        # 4. owner-side merge
+        self.engine.merge(recv, self.world, self.rank, src_counts, self.src_words, self.n_genomes)
+        self.launches = getattr(self.engine, "launches", 0)
+        self._recv = recv  # keep alive until the next build
+        self._kmers_cache = None
+        self._n_kmers = None
+        return self
+
+    @property
+    def n_kmers(self) -> int:
+        if self._n_kmers is None:
+            self._n_kmers = int(self.builder.dims[0]) if self.builder is not None else len(self.engine.result()[0])
+        return self._n_kmers
+
+    def kmers(self):
+        return self.engine.result()[0] if self.world > 1 else self.builder.kmers()
+
+    def matrix(self):
+        return self.engine.result()[1] if self.world > 1 else self.builder.matrix()
+
+    def gather(self):
+        """Global (kmers ascending, matrix [W][U]) on rank 0, None elsewhere.  Host-side P-way merge."""
+        km, mat = self.kmers(), self.matrix()
+        if self.world == 1:
+            return km, mat
+        import torch.distributed as dist
+        objs = [None] * self.world if self.rank == 0 else None
+        dist.gather_object((km, mat), objs, dst=0)
+        if self.rank != 0:
+            return None
+        allk = np.concatenate([o[0] for o in objs])
+        allm = np.concatenate([o[1] for o in objs], axis=1)
+        order = np.argsort(allk, kind="stable")
+        return allk[order], np.ascontiguousarray(allm[:, order])
+
+    def close(self):
+        if self.builder is not None:
+            self.builder.close()

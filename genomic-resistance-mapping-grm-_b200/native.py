@@ -20,6 +20,7 @@ SYMBOLS = [
     "grmkm_build", "grmkm_dims", "grmkm_get_stats", "grmkm_stage_times", "grmkm_copy_kmers_packed",
     "grmkm_copy_kmer_strings", "grmkm_copy_matrix", "grmkm_format_tsv", "grmkm_device_result",
     "grmkm_synth_fasta_device", "grmkm_build_partial", "grmkm_export_partials", "grmkm_merge_partials",
+    "grmkm_plan_bucket_bits", "grmkm_set_bucket_bits",
 ]
 
 
@@ -91,6 +92,8 @@ def load() -> C.CDLL:
         "grmkm_build_partial": (i32, [vp, u32, C.POINTER(u64)]),
         "grmkm_export_partials": (i32, [vp, vp, u64]),
         "grmkm_merge_partials": (i32, [vp, vp, u32, u32, C.POINTER(u64), C.POINTER(u32), u32]),
+        "grmkm_plan_bucket_bits": (i32, [vp, C.POINTER(u32)]),
+        "grmkm_set_bucket_bits": (i32, [vp, u32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

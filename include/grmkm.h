@@ -169,6 +169,10 @@ int grmkm_synth_fasta_device(grmkm_ctx* ctx, const void* layout, uint64_t layout
  * result in the context (dims/copy_* as after grmkm_build).
  */
 int grmkm_build_partial(grmkm_ctx* ctx, uint32_t n_ranks, uint64_t* counts);
+/* All ranks must partition the hash space identically: read this rank's automatic choice for
+ * the inputs added so far, agree on the maximum over ranks, set it before grmkm_build_partial. */
+int grmkm_plan_bucket_bits(grmkm_ctx* ctx, uint32_t* bits);
+int grmkm_set_bucket_bits(grmkm_ctx* ctx, uint32_t bits);
 int grmkm_export_partials(grmkm_ctx* ctx, void* dev_dst, uint64_t dst_bytes);
 int grmkm_merge_partials(grmkm_ctx* ctx, const void* dev_parts, uint32_t n_ranks, uint32_t rank,
                          const uint64_t* src_counts, const uint32_t* src_words, uint32_t total_genomes);

@@ -191,3 +191,49 @@ def test_errors(gpu):
         with pytest.raises(GrmkmError) as e2:
             b.add_genome_files(0, ["/nonexistent/file.fna"])
         assert e2.value.code == -5
+
+
+@pytest.mark.parametrize("world,G,keep", [(2, 130, False), (4, 300, True), (3, 70, False), (8, 1000, False)])
+def test_partial_merge_emulated_ranks(gpu, world, G, keep):
+    """The CUDA partial/export/merge entry points, with the all-to-all emulated by tensor slicing:
+    P contexts on one GPU, one after the other (never concurrently)."""
+    import torch
+    from grm_b200.builder import KmerMatrixBuilder
+    from grm_b200.distributed import CudaEngine, row_partition, words_per_rank
+    rng = np.random.default_rng(G)
+    shared = [inputs.rand_seq(rng, 2000), inputs.rand_seq(rng, 500)]
+    genomes = [inputs.fasta(rng, n_records=2, max_len=300, shared=shared) for _ in range(G)]
+    parts, sw = row_partition(G, world), words_per_rank(G, world)
+    engines, sends, counts = [], [], []
+    for r in range(world):
+        b = KmerMatrixBuilder(k=19, keep_singletons=keep)
+        b.set_genome_count(len(parts[r]))
+        for i, g in enumerate(parts[r]):
+            b.add_genome_bytes(i, genomes[g])
+        e = CudaEngine(b)
+        engines.append(e)
+    bits = max(e.plan_bucket_bits() for e in engines)
+    for r, e in enumerate(engines):
+        e.set_bucket_bits(bits)
+        c, s = e.build_partial(world, sw[r])
+        counts.append(c); sends.append(s)
+    slices_k, slices_m = [], []
+    for dst in range(world):
+        chunks, src_counts = [], []
+        for src in range(world):
+            width = 1 + sw[src]
+            off = sum(counts[src][:dst]) * width
+            chunks.append(sends[src][off: off + counts[src][dst] * width])
+            src_counts.append(counts[src][dst])
+        recv = torch.cat(chunks) if chunks else torch.empty(0, dtype=torch.int64, device="cuda")
+        engines[dst].merge(recv, world, dst, src_counts, sw, G)
+        k_, m_ = engines[dst].result()
+        assert np.all(k_[1:] > k_[:-1])
+        slices_k.append(k_); slices_m.append(m_)
+    allk = np.concatenate(slices_k); allm = np.concatenate(slices_m, axis=1)
+    order = np.argsort(allk, kind="stable")
+    ref = oracle.build([[(g, 0)] for g in genomes], 19, 1, keep)
+    assert np.array_equal(allk[order], ref.kmers)
+    assert np.array_equal(allm[:, order], ref.matrix)
+    for e in engines:
+        e.b.close()
