@@ -51,7 +51,7 @@ struct grmkm_ctx {
     // device buffers (grow-only, reused across builds)
     DevBuf in, files, hdr0, tsum, tile_file, tile_state, tile_pos, bsum, bstate, bpos, fss, codes, valid, hist,
         offsets, offsets2, bcounts, records, records2, ukeys, uwords, skeys, sidx_a, sidx_b, shist, kmers, matrix,
-        scalars, fmt, synth, owner_start, refs;
+        scalars, fmt, synth, owner_start, refs, spart;
     size_t device_bytes = 0;
 
     cudaEvent_t ev[T_N]{};
@@ -202,6 +202,9 @@ int sort_and_gather(grmkm_ctx* c, uint64_t U, uint32_t W, uint64_t ucap, uint32_
     ENSURE(c, c->sidx_a, U * 4);
     ENSURE(c, c->sidx_b, U * 4);
     ENSURE(c, c->shist, (size_t)256 * n_seg * 4);
+    const uint64_t hist_n = (uint64_t)256 * n_seg;
+    const uint32_t n_chunks = (uint32_t)((hist_n + kScanChunk - 1) / kScanChunk);
+    ENSURE(c, c->spart, (size_t)n_chunks * 4);
     const uint32_t passes = (key_bits_total + 7) / 8;
     unsigned long long* ka = (unsigned long long*)c->ukeys.p;
     unsigned long long* kb = (unsigned long long*)c->skeys.p;
@@ -211,9 +214,11 @@ int sort_and_gather(grmkm_ctx* c, uint64_t U, uint32_t W, uint64_t ucap, uint32_
     for (uint32_t pass = 0; pass < passes; ++pass) {
         const uint32_t shift = pass * 8;
         k_sort_hist<<<sblocks, kSortWarps * 32, 0, st>>>(ka, U, shift, n_seg, (uint32_t*)c->shist.p);
-        k_scan_u32<<<1, 1024, 0, st>>>((uint32_t*)c->shist.p, (uint64_t)256 * n_seg);
+        k_scan_u32_partial<<<n_chunks, 1024, 0, st>>>((const uint32_t*)c->shist.p, hist_n, (uint32_t*)c->spart.p);
+        k_scan_u32_mid<<<1, 1024, 0, st>>>((uint32_t*)c->spart.p, n_chunks);
+        k_scan_u32_final<<<n_chunks, 1024, 0, st>>>((uint32_t*)c->shist.p, hist_n, (const uint32_t*)c->spart.p);
         k_sort_scatter<<<sblocks, kSortWarps * 32, 0, st>>>(ka, ia, U, shift, n_seg, (const uint32_t*)c->shist.p, kb, ib);
-        L.n += 3;
+        L.n += 5;
         std::swap(ka, kb);
         uint32_t* t = ia ? ia : ispare;
         ia = ib; ib = t;
@@ -296,7 +301,7 @@ void grmkm_destroy(grmkm_ctx* c) {
     DevBuf* all[] = {&c->in, &c->files, &c->hdr0, &c->tsum, &c->tile_file, &c->tile_state, &c->tile_pos, &c->bsum,
                      &c->bstate, &c->bpos, &c->fss, &c->codes, &c->valid, &c->hist, &c->offsets, &c->offsets2,
                      &c->bcounts, &c->records, &c->records2, &c->ukeys, &c->uwords, &c->skeys, &c->sidx_a, &c->sidx_b,
-                     &c->shist, &c->kmers, &c->matrix, &c->scalars, &c->fmt, &c->synth, &c->owner_start, &c->refs};
+                     &c->shist, &c->kmers, &c->matrix, &c->scalars, &c->fmt, &c->synth, &c->owner_start, &c->refs, &c->spart};
     for (DevBuf* b : all) release(c, *b);
     if (c->ev_ok) for (int i = 0; i < T_N; ++i) cudaEventDestroy(c->ev[i]);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -428,7 +433,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
     ENSURE(c, c->bpos, P.n_sblk * 8);
     ENSURE(c, c->codes, P.n_groups_max * 8);
     ENSURE(c, c->valid, P.n_groups_max * 4);
-    ENSURE(c, c->hist, (size_t)B * 8);
+    ENSURE(c, c->hist, (size_t)B * 8 * kCursorStride);
     ENSURE(c, c->offsets, (size_t)(B + 1) * 8);
     ENSURE(c, c->records, P.max_stream * 8);
 
@@ -450,7 +455,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
     CU_TRY(c, cudaMemsetAsync(c->scalars.p, 0, S_COUNT * 8, st));
     CU_TRY(c, cudaMemsetAsync(c->codes.p, 0, P.n_groups_max * 8, st));
     CU_TRY(c, cudaMemsetAsync(c->valid.p, 0, P.n_groups_max * 4, st));
-    CU_TRY(c, cudaMemsetAsync(c->hist.p, 0, (size_t)B * 8, st));
+    CU_TRY(c, cudaMemsetAsync(c->hist.p, 0, (size_t)B * 8 * kCursorStride, st));
     if (c->ev_ok) cudaEventRecord(c->ev[T_H2D], st);
 
     const FileDesc* d_files = (const FileDesc*)c->files.p;
@@ -491,17 +496,26 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
     ep.row_bits = P.row_bits;
     ep.hist = (unsigned long long*)c->hist.p;
     ep.records = (unsigned long long*)c->records.p;
+    ep.dbg = (c->cfg.flags >> 8) & 3;
+    ep.offsets = (const unsigned long long*)c->offsets.p;
     const uint64_t n_etiles_max = (P.n_groups_max + kExtractThreads - 1) / kExtractThreads;
     const uint32_t egrid = (uint32_t)std::min<uint64_t>(n_etiles_max, (uint64_t)c->sm_count * 8);
     const size_t hist_smem = (size_t)B * 4;
     CU_TRY(c, cudaFuncSetAttribute(k_extract<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
     k_extract<0><<<egrid, kExtractThreads, hist_smem, st>>>(ep);
     k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->hist.p, (unsigned long long*)c->offsets.p, B, d_scalars,
-                                         S_N_WINDOWS);
+                                         S_N_WINDOWS, kCursorStride);
     L.n += 2;
     CU_TRY(c, cudaGetLastError());
     if (c->ev_ok) cudaEventRecord(c->ev[T_COUNT], st);
-    k_extract<1><<<egrid, kExtractThreads, 0, st>>>(ep);
+    if (B <= (uint32_t)kStMaxBuckets && !(c->cfg.flags & GRMKM_FLAG_SIMPLE_SCATTER)) {
+        const size_t ssm = staged_smem_bytes(B);
+        const uint64_t n_stiles = (P.n_groups_max + (kStTile / 32) - 1) / (kStTile / 32);
+        CU_TRY(c, cudaFuncSetAttribute(k_extract_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+        k_extract_staged<<<(uint32_t)std::min<uint64_t>(n_stiles, (uint64_t)c->sm_count), kStThreads, ssm, st>>>(ep);
+    } else {
+        k_extract<1><<<egrid, kExtractThreads, 0, st>>>(ep);
+    }
     L.n++;
     CU_TRY(c, cudaGetLastError());
     if (c->ev_ok) cudaEventRecord(c->ev[T_SCATTER], st);
@@ -526,7 +540,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         CU_TRY(c, cudaFuncSetAttribute(k_aggregate<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         k_aggregate<2><<<agrid, kAggThreads, sm, st>>>(ap);
         k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->bcounts.p, (unsigned long long*)c->offsets2.p, B,
-                                             d_scalars, S_N_SOLID);
+                                             d_scalars, S_N_SOLID, 1);
         k_compact_records<<<agrid * 4, 256, 0, st>>>((const unsigned long long*)c->records2.p, agg_offsets,
                                                      (const unsigned long long*)c->offsets2.p, B,
                                                      (unsigned long long*)c->records.p);
@@ -840,7 +854,7 @@ int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
     const unsigned long long* parts = (const unsigned long long*)dev_parts;
     k_merge_partition<0><<<pgrid, 256, 0, st>>>(parts, ms, n_total, mb, (unsigned long long*)c->hist.p, nullptr);
     k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->hist.p, (unsigned long long*)c->offsets.p, B, d_scalars,
-                                         S_N_WINDOWS);
+                                         S_N_WINDOWS, 1);
     k_merge_partition<1><<<pgrid, 256, 0, st>>>(parts, ms, n_total, mb, (unsigned long long*)c->hist.p,
                                                 (unsigned long long*)c->refs.p);
     L.n += 3;

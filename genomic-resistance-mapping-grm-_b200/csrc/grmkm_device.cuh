@@ -15,6 +15,7 @@ constexpr int kExtractThreads = 256;
 constexpr int kAggThreads = 1024;
 constexpr int kMaxProbe = 96;
 constexpr uint64_t kEmptyKey = ~0ULL;
+constexpr int kCursorStride = 1;       // spacing of the bucket cursors (32 = 256 B apart was measured: no gain)
 
 // device scalars (u64 each)
 enum Scalar : int {
@@ -191,6 +192,34 @@ __device__ __forceinline__ Sum chunk_summary(const Chunk16& ch, uint32_t prev, u
         r.c2 = ((a >> 24) & 0xFF) + ((b >> 16) & 0xFF);
         r.c3 = ((a >> 16) & 0xFF) + ((b >> 8) & 0xFF);
     }
+    return r;
+}
+
+// exclusive scan of one u32 per thread over a 1024-thread block; s_warp must hold 33 words
+__device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t* s_warp, uint32_t& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_warp[lane], wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += o;
+        }
+        s_warp[lane] = wi - w;          // exclusive warp offsets
+        if (lane == 31) s_warp[32] = wi;
+    }
+    __syncthreads();
+    total = s_warp[32];
+    const uint32_t r = s_warp[warp] + inc - v;
+    __syncthreads();
     return r;
 }
 

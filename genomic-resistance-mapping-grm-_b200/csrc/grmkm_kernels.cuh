@@ -283,6 +283,8 @@ struct ExtractParams {
     uint32_t row_bits;
     unsigned long long* hist;     // [B] (COUNT) / cursors [B] (SCATTER)
     unsigned long long* records;  // SCATTER
+    uint32_t dbg;                 // timing experiments only: 1 = no atomics, 2 = no stores
+    const unsigned long long* offsets;
 };
 
 template <int MODE>  // 0 = count per bucket, 1 = scatter records
@@ -355,8 +357,12 @@ k_extract(const ExtractParams p) {
                 if (MODE == 0) {
                     atomicAdd(&s_hist[b], 1u);
                 } else {
-                    const unsigned long long slot = atomicAdd(&p.hist[b], 1ULL);
-                    p.records[slot] = ((h & key_mask) << p.row_bits) | row;
+                    unsigned long long slot;
+                    if (p.dbg & 1) {
+                        const unsigned long long o0 = p.offsets[b], o1 = p.offsets[b + 1];
+                        slot = o0 + (o1 > o0 ? (h & key_mask) % (o1 - o0) : 0);
+                    } else slot = atomicAdd(&p.hist[(size_t)b * kCursorStride], 1ULL);
+                    if (!(p.dbg & 2)) p.records[slot] = ((h & key_mask) << p.row_bits) | row;
                 }
             }
         }
@@ -365,20 +371,159 @@ k_extract(const ExtractParams p) {
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < B; i += blockDim.x) {
             const uint32_t v = s_hist[i];
-            if (v) atomicAdd(&p.hist[i], (unsigned long long)v);
+            if (v) atomicAdd(&p.hist[(size_t)i * kCursorStride], (unsigned long long)v);
         }
+    }
+}
+
+// ---- staged scatter: one tile of 16384 stream positions per CTA iteration -------------------------
+// Records are ranked per bucket with shared-memory atomics, space is reserved with ONE global atomic
+// per (tile, non-empty bucket), the tile is counting-sorted in shared memory and copied out so that
+// records of one bucket leave the SM as contiguous runs (full-sector writes instead of 8-byte ones).
+constexpr int kStThreads = 1024;
+constexpr int kStPerThread = 16;                       // half a 32-entry stream group
+constexpr int kStTile = kStThreads * kStPerThread;     // 16384 positions = 512 groups
+constexpr int kStMaxBuckets = 4096;
+
+__host__ __device__ inline size_t staged_smem_bytes(uint32_t B) {
+    return (size_t)B * (8 + 4 + 4) + (size_t)kStTile * (8 + 2);
+}
+
+__global__ void __launch_bounds__(kStThreads, 1)
+k_extract_staged(const ExtractParams p) {
+    extern __shared__ unsigned long long s_dyn[];
+    __shared__ uint32_t s_f0, s_total;
+    __shared__ uint32_t s_warp[33];
+    const uint32_t B = 1u << p.bucket_bits;
+    unsigned long long* s_delta = s_dyn;                         // [B]   global base - tile offset
+    unsigned long long* s_rec = s_delta + B;                     // [kStTile]
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_rec + kStTile);   // [B]
+    uint32_t* s_off = s_cnt + B;                                 // [B]
+    uint16_t* s_bin = reinterpret_cast<uint16_t*>(s_off + B);    // [kStTile]
+    const uint64_t stream_len = p.scalars[S_STREAM_LEN];
+    const uint64_t n_groups = (stream_len + 31) >> 5;
+    const uint64_t n_tiles = (n_groups + (kStTile / 32) - 1) / (kStTile / 32);
+    const uint32_t k = p.k;
+    const uint64_t kmask = k == 32 ? ~0ULL : ((1ULL << (2 * k)) - 1);
+    const uint32_t key_bits = 64 - p.bucket_bits;
+    const uint64_t key_mask = (1ULL << key_bits) - 1;
+    const int lane = threadIdx.x & 31;
+    const uint32_t half = threadIdx.x & 1;
+    const uint32_t bins_per_thread = (B + kStThreads - 1) / kStThreads;
+    for (uint32_t i = threadIdx.x; i < B; i += kStThreads) s_cnt[i] = 0;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t g = tile * (kStTile / 32) + (threadIdx.x >> 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint64_t p0 = tile * (uint64_t)kStTile;
+            uint32_t lo = 0, hi = p.n_files - 1;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi + 1) >> 1;
+                if (p.file_stream_start[mid] <= p0) lo = mid; else hi = mid - 1;
+            }
+            s_f0 = lo;
+        }
+        __syncthreads();
+        // ---- phase 1: records into registers, rank per bucket
+        unsigned long long cur_c = 0; uint32_t cur_v = 0;
+        if (g < n_groups) { cur_c = p.codes[g]; cur_v = p.valid[g]; }
+        unsigned long long prev_c = __shfl_up_sync(0xffffffffu, cur_c, 2);
+        uint32_t prev_v = __shfl_up_sync(0xffffffffu, cur_v, 2);
+        if (lane < 2) {
+            if (g > 0 && g - 1 < n_groups) { prev_c = p.codes[g - 1]; prev_v = p.valid[g - 1]; }
+            else { prev_c = 0; prev_v = 0; }
+        }
+        unsigned long long rec[kStPerThread];
+        uint32_t meta[kStPerThread];
+        uint32_t have = 0;
+        const uint32_t my_v = (cur_v >> (16 * half)) & 0xFFFFu;
+        if (g < n_groups && my_v) {
+            const uint32_t my_c = (uint32_t)(cur_c >> (32 * half));
+            const unsigned long long win_c = half ? ((prev_c >> 32) | (cur_c << 32)) : prev_c;
+            const uint32_t win_v = half ? ((prev_v >> 16) | (cur_v << 16)) : prev_v;
+            const uint64_t pos0 = g * 32ULL + 16 * half;
+            uint32_t f = s_f0;
+            while (f + 1 < p.n_files && p.file_stream_start[f + 1] <= pos0) ++f;
+            uint64_t next_start = (f + 1 < p.n_files) ? p.file_stream_start[f + 1] : ~0ULL;
+            uint32_t row = p.files[f].row;
+            const uint64_t le = k == 32 ? win_c : ((win_c >> (2 * (32 - k))) & kmask);
+            uint64_t rc = le ^ (0xAAAAAAAAAAAAAAAAULL & kmask);
+            uint64_t fw = rev2(le) >> (64 - 2 * k);
+            uint32_t run = min((uint32_t)__clz(~win_v), k);
+#pragma unroll
+            for (int e = 0; e < kStPerThread; ++e) {
+                const uint32_t c = (my_c >> (2 * e)) & 3u;
+                fw = ((fw << 2) | c) & kmask;
+                rc = (rc >> 2) | ((uint64_t)(c ^ 2u) << (2 * (k - 1)));
+                if ((my_v >> e) & 1u) run = min(run + 1, k); else run = 0;
+                if (run == k) {
+                    const uint64_t pos = pos0 + e;
+                    if (pos >= next_start) {
+                        while (f + 1 < p.n_files && p.file_stream_start[f + 1] <= pos) ++f;
+                        next_start = (f + 1 < p.n_files) ? p.file_stream_start[f + 1] : ~0ULL;
+                        row = p.files[f].row;
+                    }
+                    const uint64_t canon = fw < rc ? fw : rc;
+                    const uint64_t h = fmix64(canon);
+                    const uint32_t b = (uint32_t)(h >> key_bits);
+                    const uint32_t rank = atomicAdd(&s_cnt[b], 1u);
+                    rec[e] = ((h & key_mask) << p.row_bits) | row;
+                    meta[e] = b | (rank << 12);
+                    have |= 1u << e;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: scan the tile histogram, reserve global space, clear the histogram
+        {
+            const uint32_t b0 = threadIdx.x * bins_per_thread;
+            uint32_t cnt[4] = {0, 0, 0, 0};
+            uint32_t sum = 0;
+            for (uint32_t i = 0; i < bins_per_thread; ++i)
+                if (b0 + i < B) { cnt[i] = s_cnt[b0 + i]; s_cnt[b0 + i] = 0; sum += cnt[i]; }
+            uint32_t total;
+            uint32_t off = block_excl_scan_1024(sum, s_warp, total);
+            if (threadIdx.x == 0) s_total = total;
+            for (uint32_t i = 0; i < bins_per_thread; ++i) {
+                if (b0 + i < B) {
+                    s_off[b0 + i] = off;
+                    if (cnt[i]) {
+                        const unsigned long long gb = atomicAdd(&p.hist[(size_t)(b0 + i) * kCursorStride],
+                                                                (unsigned long long)cnt[i]);
+                        s_delta[b0 + i] = gb - off;
+                    }
+                    off += cnt[i];
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase 3: counting sort into shared memory
+#pragma unroll
+        for (int e = 0; e < kStPerThread; ++e) {
+            if ((have >> e) & 1u) {
+                const uint32_t b = meta[e] & 4095u;
+                const uint32_t dst = s_off[b] + (meta[e] >> 12);
+                s_rec[dst] = rec[e];
+                s_bin[dst] = (uint16_t)b;
+            }
+        }
+        __syncthreads();
+        // ---- phase 4: copy out; consecutive threads write consecutive records of a bucket
+        const uint32_t total = s_total;
+        for (uint32_t i = threadIdx.x; i < total; i += kStThreads)
+            p.records[s_delta[s_bin[i]] + i] = s_rec[i];
     }
 }
 
 // exclusive scan of the bucket histogram -> offsets[B+1]; cursors[b] = offsets[b]
 __global__ void __launch_bounds__(1024)
 k_bucket_offsets(unsigned long long* __restrict__ hist_cursor, unsigned long long* __restrict__ offsets, uint32_t B,
-                 uint64_t* __restrict__ scalars, int total_scalar) {
+                 uint64_t* __restrict__ scalars, int total_scalar, uint32_t stride) {
     __shared__ unsigned long long s_part[1024];
     const uint32_t per = (B + 1023) / 1024;
     const uint32_t b0 = threadIdx.x * per;
     unsigned long long sum = 0;
-    for (uint32_t i = 0; i < per; ++i) if (b0 + i < B) sum += hist_cursor[b0 + i];
+    for (uint32_t i = 0; i < per; ++i) if (b0 + i < B) sum += hist_cursor[(size_t)(b0 + i) * stride];
     s_part[threadIdx.x] = sum;
     __syncthreads();
     // simple Hillis-Steele inclusive scan
@@ -391,9 +536,9 @@ k_bucket_offsets(unsigned long long* __restrict__ hist_cursor, unsigned long lon
     unsigned long long run = s_part[threadIdx.x] - sum;
     for (uint32_t i = 0; i < per; ++i) {
         if (b0 + i < B) {
-            const unsigned long long c = hist_cursor[b0 + i];
+            const unsigned long long c = hist_cursor[(size_t)(b0 + i) * stride];
             offsets[b0 + i] = run;
-            hist_cursor[b0 + i] = run;
+            hist_cursor[(size_t)(b0 + i) * stride] = run;
             run += c;
         }
     }
@@ -652,25 +797,54 @@ k_sort_hist(const unsigned long long* __restrict__ keys, uint64_t n, uint32_t sh
     }
 }
 
-// exclusive scan of a u32 array of length n in place (single block)
+// exclusive scan of a u32 array (length n, multiple of 4) in place, three launches:
+//   k_scan_u32_partial: per-4096-chunk totals; k_scan_u32_mid: scan of the totals (one block);
+//   k_scan_u32_final: chunk-local scan + chunk offset.  All accesses are 16-byte coalesced.
+constexpr int kScanChunk = 4096;
+
 __global__ void __launch_bounds__(1024)
-k_scan_u32(uint32_t* __restrict__ a, uint64_t n) {
-    __shared__ uint32_t s_part[1024];
-    const uint64_t per = (n + 1023) / 1024;
-    const uint64_t b0 = threadIdx.x * per;
-    uint32_t sum = 0;
-    for (uint64_t i = 0; i < per; ++i) if (b0 + i < n) sum += a[b0 + i];
-    s_part[threadIdx.x] = sum;
+k_scan_u32_partial(const uint32_t* __restrict__ a, uint64_t n, uint32_t* __restrict__ partial) {
+    __shared__ uint32_t s_warp[33];
+    const uint64_t i = (uint64_t)blockIdx.x * kScanChunk + (uint64_t)threadIdx.x * 4;
+    uint32_t v = 0;
+    if (i < n) { const uint4 q = *reinterpret_cast<const uint4*>(a + i); v = q.x + q.y + q.z + q.w; }
+    uint32_t total;
+    block_excl_scan_1024(v, s_warp, total);
+    if (threadIdx.x == 0) partial[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024)
+k_scan_u32_mid(uint32_t* __restrict__ partial, uint32_t nb) {
+    __shared__ uint32_t s_warp[33];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {
-        uint32_t v = threadIdx.x >= d ? s_part[threadIdx.x - d] : 0;
+    for (uint32_t base = 0; base < nb; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < nb ? partial[i] : 0;
+        uint32_t total;
+        const uint32_t ex = block_excl_scan_1024(v, s_warp, total);
+        const uint32_t carry = s_carry;
+        if (i < nb) partial[i] = carry + ex;
         __syncthreads();
-        s_part[threadIdx.x] += v;
+        if (threadIdx.x == 0) s_carry = carry + total;
         __syncthreads();
     }
-    uint32_t run = s_part[threadIdx.x] - sum;
-    for (uint64_t i = 0; i < per; ++i)
-        if (b0 + i < n) { const uint32_t c = a[b0 + i]; a[b0 + i] = run; run += c; }
+}
+
+__global__ void __launch_bounds__(1024)
+k_scan_u32_final(uint32_t* __restrict__ a, uint64_t n, const uint32_t* __restrict__ partial) {
+    __shared__ uint32_t s_warp[33];
+    const uint64_t i = (uint64_t)blockIdx.x * kScanChunk + (uint64_t)threadIdx.x * 4;
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (i < n) q = *reinterpret_cast<const uint4*>(a + i);
+    uint32_t total;
+    uint32_t ex = block_excl_scan_1024(q.x + q.y + q.z + q.w, s_warp, total) + partial[blockIdx.x];
+    if (i < n) {
+        uint4 o;
+        o.x = ex; o.y = ex + q.x; o.z = o.y + q.y; o.w = o.z + q.z;
+        *reinterpret_cast<uint4*>(a + i) = o;
+    }
 }
 
 __global__ void __launch_bounds__(kSortWarps * 32)

@@ -13,6 +13,7 @@ G = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 bbits = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+flags = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 cfg = synth.SynthConfig(seed=synth.MASTER_SEED + 1)
 if scale != 1.0:
     cfg = cfg.scaled(scale)
@@ -20,7 +21,7 @@ t0 = time.time()
 lay, total, spans = synth.build_layout(cfg, range(G))
 print(f"layout {time.time()-t0:.2f}s total_bytes={total}")
 buf = torch.empty(total, dtype=torch.uint8, device="cuda")
-with KmerMatrixBuilder(k=31, keep_singletons=True, bucket_bits=bbits) as b:
+with KmerMatrixBuilder(k=31, keep_singletons=True, bucket_bits=bbits, flags=flags) as b:
     b._check(b._lib.grmkm_synth_fasta_device(b._ctx, C.c_void_p(lay.ctypes.data), lay.nbytes, C.c_void_p(buf.data_ptr()), total))
     for r in range(reps):
         b.reset()
