@@ -312,7 +312,7 @@ def main():
         n_windows, n_in, U0 = stats["n_windows"], stats["n_input_bytes"], stats["n_kmers"]
         stream_bytes = (stats["n_bases"] + stats["n_records"]) * 12 / 32
         kernels = {
-            "k_extract<1> (scatter)": (stage_ms.get("scatter", 0.0), 8.0 * n_windows + stream_bytes),
+            "k_extract_staged (scatter)": (stage_ms.get("scatter", 0.0), 8.0 * n_windows + stream_bytes),
             "k_aggregate<0>": (stage_ms.get("aggregate", 0.0), 8.0 * n_windows + U0 * 8.0 * (1 + W)),
             "k_pack": (stage_ms.get("pack", 0.0), n_in + stream_bytes),
             "k_extract<0> (count)": (stage_ms.get("count", 0.0), stream_bytes),

@@ -196,10 +196,48 @@ int sort_and_gather(grmkm_ctx* c, uint64_t U, uint32_t W, uint64_t ucap, uint32_
         CU_TRY(c, cudaGetLastError());
         return GRMKM_OK;
     }
-    const uint32_t n_seg = (uint32_t)((U + kSortSeg - 1) / kSortSeg);
-    const uint32_t sblocks = (n_seg + kSortWarps - 1) / kSortWarps;
+    // ---- fast path: MSD partition + shared-memory sort fused with the gather
     ENSURE(c, c->skeys, U * 8);
     ENSURE(c, c->sidx_a, U * 4);
+    if (U <= 0xFFFFFFFFULL && !(c->cfg.flags & GRMKM_FLAG_RADIX_ORDER)) {
+        uint32_t pbits = std::min(key_bits_total, std::min(15u, ceil_log2((U + 4095) / 4096)));
+        const uint32_t Pn = 1u << pbits;
+        const uint32_t shift = key_bits_total - pbits;
+        ENSURE(c, c->hist, (size_t)std::max<uint32_t>(Pn, 1) * 8 * kCursorStride);
+        ENSURE(c, c->offsets2, (size_t)(Pn + 1) * 8);
+        uint64_t* d_scalars = (uint64_t*)c->scalars.p;
+        CU_TRY(c, cudaMemsetAsync(c->hist.p, 0, (size_t)Pn * 8, st));
+        CU_TRY(c, cudaMemsetAsync(d_scalars + S_WORK, 0, 8, st));
+        const uint32_t cgrid = (uint32_t)std::min<uint64_t>((U + 255) / 256, (uint64_t)c->sm_count * 8);
+        if (pbits == 0) {
+            const unsigned long long uu = U;   // one partition holds everything
+            CU_TRY(c, cudaMemcpyAsync(c->hist.p, &uu, 8, cudaMemcpyHostToDevice, st));
+        } else {
+            CU_TRY(c, cudaFuncSetAttribute(k_msd_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Pn * 4)));
+            k_msd_count<<<cgrid, 256, (size_t)Pn * 4, st>>>((const unsigned long long*)c->ukeys.p, U, shift, Pn,
+                                                           (unsigned long long*)c->hist.p);
+        }
+        k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->hist.p, (unsigned long long*)c->offsets2.p, Pn,
+                                             d_scalars, S_N_SOLID, 1);
+        k_msd_scatter<<<gblocks, 256, 0, st>>>((const unsigned long long*)c->ukeys.p, U, pbits ? shift : 64,
+                                               (unsigned long long*)c->hist.p, (unsigned long long*)c->skeys.p,
+                                               (uint32_t*)c->sidx_a.p);
+        const size_t lsm = (size_t)kLocalSortCap * 12;
+        CU_TRY(c, cudaFuncSetAttribute(k_local_sort_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
+        k_local_sort_gather<<<std::min<uint32_t>(Pn, (uint32_t)c->sm_count), kLocalSortThreads, lsm, st>>>(
+            (const unsigned long long*)c->skeys.p, (const uint32_t*)c->sidx_a.p, (const unsigned long long*)c->offsets2.p,
+            Pn, U, W, (const unsigned long long*)c->uwords.p, ucap, (unsigned long long*)c->kmers.p,
+            (unsigned long long*)c->matrix.p, (unsigned long long*)d_scalars);
+        L.n += 4;
+        CU_TRY(c, cudaGetLastError());
+        uint64_t overflow = 0;
+        CU_TRY(c, cudaMemcpyAsync(&overflow, d_scalars + S_WORK, 8, cudaMemcpyDeviceToHost, st));
+        CU_TRY(c, cudaStreamSynchronize(st));
+        if (!overflow) return GRMKM_OK;
+        // a partition did not fit shared memory (heavily skewed k-mer prefixes): radix sort below
+    }
+    const uint32_t n_seg = (uint32_t)((U + kSortSeg - 1) / kSortSeg);
+    const uint32_t sblocks = (n_seg + kSortWarps - 1) / kSortWarps;
     ENSURE(c, c->sidx_b, U * 4);
     ENSURE(c, c->shist, (size_t)256 * n_seg * 4);
     const uint64_t hist_n = (uint64_t)256 * n_seg;

@@ -195,6 +195,86 @@ __device__ __forceinline__ Sum chunk_summary(const Chunk16& ch, uint32_t prev, u
     return r;
 }
 
+// ---- compact FASTA path ------------------------------------------------------------------------
+// Inside a 4 KiB tile the FASTA transducer fits one u32: bits 0-13 entries emitted after the first
+// line start (c_rest), bits 14-27 sequence bytes before it (c_head, emitted only when the chunk
+// starts inside a sequence line), bits 28-29 type of the last line start (0 none, 1 header, 2 seq).
+__device__ __forceinline__ uint32_t fa_combine(uint32_t A, uint32_t B) {
+    const uint32_t ta = A >> 28, tb = B >> 28, hb = (B >> 14) & 0x3FFFu;
+    uint32_t r = (A & 0x0FFFFFFFu) + (B & 0x3FFFu);
+    r += (ta == 0) ? (hb << 14) : 0u;
+    r += (ta == 2) ? hb : 0u;
+    return r | ((tb ? tb : ta) << 28);
+}
+__device__ __forceinline__ Sum fa_to_sum(uint32_t a) {
+    const uint32_t t = a >> 28, c_rest = a & 0x3FFFu, c_head = (a >> 14) & 0x3FFFu;
+    Sum r; r.e = t ? (t - 1) * 0x55u : 0xE4u; r.c0 = c_rest; r.c1 = c_rest + c_head; r.c2 = 0; r.c3 = 0;
+    return r;
+}
+// ordered scan of compact FASTA summaries over a 256-thread block; s_w holds 8 words
+__device__ __forceinline__ void block_scan_fa(uint32_t mine, uint32_t& excl, uint32_t& total, uint32_t* s_w) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    uint32_t inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc = fa_combine(o, inc);
+    }
+    uint32_t prev = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) prev = 0;
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    uint32_t wpre = 0, tot = 0;
+    for (int w = 0; w < nwarp; ++w) {
+        if (w == warp) wpre = tot;
+        tot = fa_combine(tot, s_w[w]);
+    }
+    excl = fa_combine(wpre, prev);
+    total = tot;
+    __syncthreads();
+}
+
+// One pass over a 16-byte FASTA chunk: compact summary and (EMIT) the packed entries, kept apart
+// for the bytes before the chunk's first line start (head) and after it (rest).
+struct FaChunk {
+    uint32_t sum;
+    uint32_t head_c, head_v, rest_c, rest_v, nrec;   // 2-bit codes / validity bits, entry j at bit 2j / j
+};
+template <bool EMIT>
+__device__ __forceinline__ FaChunk fa_chunk(const Chunk16& ch, uint32_t prev, uint64_t pos0, uint64_t len, uint64_t hdr0) {
+    // live bytes: [max(hdr0, pos0), min(len, pos0 + 16))
+    const uint32_t lo = hdr0 > pos0 ? (uint32_t)min((uint64_t)16, hdr0 - pos0) : 0u;
+    const uint32_t hi = len > pos0 ? (uint32_t)min((uint64_t)16, len - pos0) : 0u;
+    const uint32_t live = hi > lo ? (((1u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
+    const uint32_t force_ls = (hdr0 >= pos0 && hdr0 < pos0 + 16) ? (1u << (uint32_t)(hdr0 - pos0)) : 0u;
+    uint32_t t = 0, hn = 0, rn = 0;
+    FaChunk r; r.head_c = r.head_v = r.rest_c = r.rest_v = r.nrec = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t c = ch.byte(i);
+        if ((live >> i) & 1u) {
+            const bool ls = ((force_ls >> i) & 1u) || (prev == '\n');
+            const bool emits = (c != '\n' && c != '\r');
+            const bool ok = is_acgt(c);
+            const uint32_t code = ok ? ((c >> 1) & 3u) : 0u;
+            if (ls) t = (c == '>') ? 1u : 2u;
+            if (ls && c == '>') { rn++; if (EMIT) r.nrec++; }            // record break: one invalid entry
+            else if (emits && t != 1u) {
+                if (t == 0) {
+                    if (EMIT) { r.head_c |= code << (2 * hn); r.head_v |= (uint32_t)ok << hn; }
+                    hn++;
+                } else {
+                    if (EMIT) { r.rest_c |= code << (2 * rn); r.rest_v |= (uint32_t)ok << rn; }
+                    rn++;
+                }
+            }
+        }
+        prev = c;
+    }
+    r.sum = rn | (hn << 14) | (t << 28);
+    return r;
+}
+
 // exclusive scan of one u32 per thread over a 1024-thread block; s_warp must hold 33 words
 __device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t* s_warp, uint32_t& total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -89,10 +89,16 @@ k_tile_summary(const FileDesc* __restrict__ files, uint32_t n_files, const uint6
     const TileCtx t = tile_context(files, n_files, hdr0, tile, &s_f);
     const Chunk16 ch = load_chunk(t.fd.ptr, t.off, t.fd.len);
     const uint32_t prev = prev_byte(t, ch);
-    Sum mine = t.fd.kind == 0 ? chunk_summary<0>(ch, prev, t.off, t.fd.len, t.hdr0)
-                              : chunk_summary<1>(ch, prev, t.off, t.fd.len, t.hdr0);
-    Sum excl, total;
-    block_scan_sum(mine, excl, total, s_w);
+    Sum total;
+    if (t.fd.kind == 0) {
+        const FaChunk fc = fa_chunk<false>(ch, prev, t.off, t.fd.len, t.hdr0);
+        uint32_t ex, tot;
+        block_scan_fa(fc.sum, ex, tot, reinterpret_cast<uint32_t*>(s_w));
+        total = fa_to_sum(tot);
+    } else {
+        Sum excl;
+        block_scan_sum(chunk_summary<1>(ch, prev, t.off, t.fd.len, t.hdr0), excl, total, s_w);
+    }
     if (threadIdx.x == 0) {
         if (t.first_tile) total = sum_fix_start(total, 0);
         tsum[tile] = total;
@@ -192,35 +198,31 @@ k_pack(const FileDesc* __restrict__ files, uint32_t n_files, const uint64_t* __r
     const TileCtx t = tile_context(files, n_files, hdr0, tile, &s_f);
     const Chunk16 ch = load_chunk(t.fd.ptr, t.off, t.fd.len);
     uint32_t prev = prev_byte(t, ch);
-    const Sum mine = t.fd.kind == 0 ? chunk_summary<0>(ch, prev, t.off, t.fd.len, t.hdr0)
-                                    : chunk_summary<1>(ch, prev, t.off, t.fd.len, t.hdr0);
-    Sum excl, total;
-    block_scan_sum(mine, excl, total, s_w);
     const uint32_t st_in = tile_state[tile];
     const uint64_t tpos = tile_pos[tile];
-    uint32_t st = sum_end(excl, st_in);
-    const uint32_t local = sum_cnt(excl, st_in);
-    const uint32_t e_total = sum_cnt(total, st_in);
-
-    // walk the 16 bytes with the now-known state
-    uint32_t cbits = 0, vbits = 0, n = 0, nrec = 0;
+    uint32_t cbits = 0, vbits = 0, n = 0, nrec = 0, local, e_total;
     if (t.fd.kind == 0) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const uint64_t pos = t.off + i;
-            const uint32_t c = ch.byte(i);
-            if (pos < t.fd.len && pos >= t.hdr0) {
-                const bool ls = (pos == t.hdr0) || (prev == '\n');
-                if (ls) st = (c == '>') ? ST_HDR : ST_SEQ;
-                if (ls && c == '>') { n++; nrec++; }                       // record break entry (invalid)
-                else if (st == ST_SEQ && c != '\n' && c != '\r') {
-                    if (is_acgt(c)) { cbits |= ((c >> 1) & 3u) << (2 * n); vbits |= 1u << n; }
-                    n++;
-                }
-            }
-            prev = c;
-        }
+        const FaChunk fc = fa_chunk<true>(ch, prev, t.off, t.fd.len, t.hdr0);
+        uint32_t ex, tot;
+        block_scan_fa(fc.sum, ex, tot, reinterpret_cast<uint32_t*>(s_w));
+        const bool tile_seq = (st_in == ST_SEQ);
+        const uint32_t ex_t = ex >> 28;
+        const bool in_seq = ex_t ? (ex_t == 2) : tile_seq;          // line type at this chunk's first byte
+        local = (ex & 0x3FFFu) + (tile_seq ? ((ex >> 14) & 0x3FFFu) : 0u);
+        e_total = (tot & 0x3FFFu) + (tile_seq ? ((tot >> 14) & 0x3FFFu) : 0u);
+        const uint32_t hn = in_seq ? ((fc.sum >> 14) & 0x3FFFu) : 0u, rn = fc.sum & 0x3FFFu;
+        n = hn + rn;
+        // head entries (if any) come first; hn + rn <= 16 so the shifts stay below 32 unless hn == 16
+        cbits = (in_seq ? fc.head_c : 0u) | (hn < 16 ? fc.rest_c << (2 * hn) : 0u);
+        vbits = (in_seq ? fc.head_v : 0u) | (fc.rest_v << hn);
+        nrec = fc.nrec;
     } else {
+        const Sum mine = chunk_summary<1>(ch, prev, t.off, t.fd.len, t.hdr0);
+        Sum excl, total;
+        block_scan_sum(mine, excl, total, s_w);
+        uint32_t st = sum_end(excl, st_in);
+        local = sum_cnt(excl, st_in);
+        e_total = sum_cnt(total, st_in);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const uint64_t pos = t.off + i;
@@ -874,6 +876,82 @@ k_sort_scatter(const unsigned long long* __restrict__ keys_in, const uint32_t* _
             __syncwarp(amask);
             keys_out[pos] = key;
             idx_out[pos] = idx;
+        }
+    }
+}
+
+// ---- order, fast path: one MSD partition on the top bits of the k-mer, then a per-partition bitonic
+// sort in shared memory fused with the column gather (2 passes over U instead of 8 radix passes).
+// Canonical k-mers are denser near 0 (density 2(1-x)), so partitions hold up to ~2x the average;
+// the host sizes the partition count for a 4x margin and falls back to the radix sort on overflow.
+constexpr int kLocalSortCap = 16384;
+constexpr int kLocalSortThreads = 1024;
+
+__global__ void __launch_bounds__(256)
+k_msd_count(const unsigned long long* __restrict__ keys, uint64_t U, uint32_t shift, uint32_t P,
+            unsigned long long* __restrict__ hist) {
+    extern __shared__ uint32_t s_h[];
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) s_h[i] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < U; i += (uint64_t)gridDim.x * blockDim.x)
+        atomicAdd(&s_h[(uint32_t)(keys[i] >> shift)], 1u);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x)
+        if (s_h[i]) atomicAdd(&hist[i], (unsigned long long)s_h[i]);
+}
+
+__global__ void __launch_bounds__(256)
+k_msd_scatter(const unsigned long long* __restrict__ keys, uint64_t U, uint32_t shift,
+              unsigned long long* __restrict__ cursors, unsigned long long* __restrict__ out_keys,
+              uint32_t* __restrict__ out_idx) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= U) return;
+    const unsigned long long key = keys[i];
+    const unsigned long long o = atomicAdd(&cursors[shift >= 64 ? 0u : (uint32_t)(key >> shift)], 1ULL);
+    out_keys[o] = key;
+    out_idx[o] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(kLocalSortThreads, 1)
+k_local_sort_gather(const unsigned long long* __restrict__ pkeys, const uint32_t* __restrict__ pidx,
+                    const unsigned long long* __restrict__ offsets, uint32_t P, uint64_t U, uint32_t W,
+                    const unsigned long long* __restrict__ uwords, uint64_t ucap,
+                    unsigned long long* __restrict__ kmers, unsigned long long* __restrict__ matrix,
+                    unsigned long long* __restrict__ scalars) {
+    extern __shared__ unsigned long long s_key[];          // [cap] keys, then [cap] u32 indices
+    for (uint32_t part = blockIdx.x; part < P; part += gridDim.x) {
+        const unsigned long long beg = offsets[part], end = offsets[part + 1];
+        const uint32_t n = (uint32_t)(end - beg);
+        if (n == 0) continue;
+        if (n > (uint32_t)kLocalSortCap) { if (threadIdx.x == 0) scalars[S_WORK] = 1; continue; }
+        uint32_t npad = 1;
+        while (npad < n) npad <<= 1;
+        uint32_t* s_idx = reinterpret_cast<uint32_t*>(s_key + npad);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) {
+            s_key[i] = i < n ? pkeys[beg + i] : ~0ULL;
+            s_idx[i] = i < n ? pidx[beg + i] : 0u;
+        }
+        for (uint32_t size = 2; size <= npad; size <<= 1) {
+            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                __syncthreads();
+                for (uint32_t t = threadIdx.x; t < (npad >> 1); t += blockDim.x) {
+                    const uint32_t i = 2 * t - (t & (stride - 1));
+                    const uint32_t j = i + stride;
+                    const unsigned long long a = s_key[i], b = s_key[j];
+                    const bool asc = (i & size) == 0;
+                    if ((a > b) == asc) {
+                        s_key[i] = b; s_key[j] = a;
+                        const uint32_t x = s_idx[i]; s_idx[i] = s_idx[j]; s_idx[j] = x;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            kmers[beg + i] = s_key[i];
+            const uint32_t src = s_idx[i];
+            for (uint32_t w = 0; w < W; ++w) matrix[(uint64_t)w * U + beg + i] = uwords[(uint64_t)w * ucap + src];
         }
     }
 }

@@ -13,6 +13,7 @@ E_INVALID, E_UNSUPPORTED_K, E_NOMEM, E_CUDA, E_IO, E_CAPACITY, E_NO_DEVICE, E_UN
 FASTA, FASTQ = 0, 1
 FLAG_HASH_ORDER = 1
 FLAG_SIMPLE_SCATTER = 2
+FLAG_RADIX_ORDER = 4
 
 # every symbol include/grmkm.h declares (checked by tests/test_abi.py)
 SYMBOLS = [

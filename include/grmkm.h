@@ -48,6 +48,7 @@ enum { GRMKM_FASTA = 0, GRMKM_FASTQ = 1 };
 
 /* cfg.flags */
 #define GRMKM_FLAG_HASH_ORDER 1u /* keep columns in internal hash order (skip the final sort) */
+#define GRMKM_FLAG_RADIX_ORDER 4u /* order the columns with the LSD radix sort only (A/B timing, fallback test) */
 #define GRMKM_FLAG_SIMPLE_SCATTER 2u /* per-record global-atomic scatter instead of the staged one (A/B timing) */
 
 typedef struct grmkm_ctx grmkm_ctx;

@@ -237,3 +237,14 @@ def test_partial_merge_emulated_ranks(gpu, world, G, keep):
     assert np.array_equal(allm[:, order], ref.matrix)
     for e in engines:
         e.b.close()
+
+
+def test_radix_order_fallback_and_simple_scatter(gpu):
+    """The A/B flags select the older code paths; results must not change."""
+    from grm_b200 import native
+    rng = np.random.default_rng(21)
+    shared = [inputs.rand_seq(rng, 50_000)]
+    genomes = [[inputs.fasta(rng, n_records=3, min_len=20_000, max_len=40_000, shared=shared)] for _ in range(4)]
+    for flags in (native.FLAG_RADIX_ORDER, native.FLAG_SIMPLE_SCATTER, native.FLAG_RADIX_ORDER | native.FLAG_SIMPLE_SCATTER):
+        check(genomes, 31, keep_singletons=True, flags=flags)
+        check(genomes, 32, keep_singletons=False, flags=flags)
