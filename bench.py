@@ -246,7 +246,7 @@ def main():
         e0.record(stream)
         for _ in range(args.steps):
             step_resident()
-            for kname, v in db.builder.times.items():
+            for kname, v in db.stage_times.items():
                 stage_acc[kname] = stage_acc.get(kname, 0.0) + v
             launches += db.launches
         e1.record(stream)
@@ -256,6 +256,7 @@ def main():
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop() if rank == 0 else None
         stats = dict(db.builder.stats)
+        stats.update({k2: v for k2, v in db.local_stats.items() if k2 in ("n_windows", "n_input_bytes", "n_bases", "n_records", "n_buckets")})
         U_local = db.n_kmers
 
         # ---- e2e: host (pinned) buffers in, kmers + matrix out, every step

@@ -77,6 +77,8 @@ class CudaEngine:
         self.b._check(self.b._lib.grmkm_build_partial(self.b._ctx, world, counts))
         counts = [int(x) for x in counts]
         self.launches = self.b.stats["n_launches"]
+        self.local_times = self.b.times
+        self.local_stats = self.b.stats
         n = sum(counts) * (1 + n_local_words)
         send = torch.empty(max(n, 1), dtype=torch.int64, device="cuda")
         self.b._check(self.b._lib.grmkm_export_partials(self.b._ctx, C.c_void_p(send.data_ptr()), send.numel() * 8))
@@ -90,6 +92,7 @@ class CudaEngine:
         self.b._check(self.b._lib.grmkm_merge_partials(self.b._ctx, C.c_void_p(recv.data_ptr() if recv.numel() else 0),
                                                        world, rank, sc, sw, n_genomes))
         self.launches += self.b.stats["n_launches"] - before
+        self.merge_times = self.b.times
 
     def result(self):
         return self.b.kmers(), self.b.matrix()
@@ -138,6 +141,8 @@ class DistributedBuilder:
             self.builder.build()
             self.launches = self.builder.stats["n_launches"]
             self._n_kmers = self.builder.dims[0]
+            self.stage_times = dict(self.builder.times)
+            self.local_stats = self.builder.stats
             return self
         import torch
         import torch.distributed as dist
@@ -148,7 +153,12 @@ class DistributedBuilder:
         self.engine.set_bucket_bits(int(bits.item()))
         # 2. local stages -> partial columns grouped by owner
         wl = self.src_words[self.rank]
+        ev = None
+        if dev == "cuda":
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         counts, send = self.engine.build_partial(self.world, wl)
+        if ev:
+            ev[0].record()
         # 3. one all-to-all: counts first, then the records
         c_out = torch.tensor(counts, dtype=torch.int64, device=dev)
         c_in = torch.empty_like(c_out)
@@ -159,8 +169,22 @@ class DistributedBuilder:
         recv = torch.empty(sum(out_split), dtype=torch.int64, device=send.device)
         dist.all_to_all_single(recv, send, output_split_sizes=out_split, input_split_sizes=in_split)
         self.exchange_bytes = int(send.numel() * 8)
+        if ev:
+            ev[1].record()
         # 4. owner-side merge
         self.engine.merge(recv, self.world, self.rank, src_counts, self.src_words, self.n_genomes)
+        lt = dict(getattr(self.engine, "local_times", {}))
+        mt = getattr(self.engine, "merge_times", {})
+        lt.pop("total", None)
+        lt.pop("sort", None)
+        if ev:
+            ev[1].synchronize()
+            lt["exchange"] = ev[0].elapsed_time(ev[1])
+        lt.update({"merge_partition": mt.get("scatter", 0.0), "merge_aggregate": mt.get("aggregate", 0.0),
+                   "merge_sort": mt.get("sort", 0.0)})
+        lt["total"] = sum(lt.values())
+        self.stage_times = lt
+        self.local_stats = getattr(self.engine, "local_stats", {})
         self.launches = getattr(self.engine, "launches", 0)
         self._recv = recv  # keep alive until the next build
         self._kmers_cache = None
