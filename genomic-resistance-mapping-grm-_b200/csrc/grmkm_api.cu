@@ -51,7 +51,7 @@ struct grmkm_ctx {
     // device buffers (grow-only, reused across builds)
     DevBuf in, files, hdr0, tsum, tile_file, tile_state, tile_pos, bsum, bstate, bpos, fss, codes, valid, hist,
         offsets, offsets2, bcounts, records, records2, ukeys, uwords, skeys, sidx_a, sidx_b, shist, kmers, matrix,
-        scalars, fmt, synth, owner_start, refs, spart;
+        scalars, fmt, synth, owner_start, refs, spart, stile_file;
     size_t device_bytes = 0;
 
     cudaEvent_t ev[T_N]{};
@@ -339,7 +339,7 @@ void grmkm_destroy(grmkm_ctx* c) {
     DevBuf* all[] = {&c->in, &c->files, &c->hdr0, &c->tsum, &c->tile_file, &c->tile_state, &c->tile_pos, &c->bsum,
                      &c->bstate, &c->bpos, &c->fss, &c->codes, &c->valid, &c->hist, &c->offsets, &c->offsets2,
                      &c->bcounts, &c->records, &c->records2, &c->ukeys, &c->uwords, &c->skeys, &c->sidx_a, &c->sidx_b,
-                     &c->shist, &c->kmers, &c->matrix, &c->scalars, &c->fmt, &c->synth, &c->owner_start, &c->refs, &c->spart};
+                     &c->shist, &c->kmers, &c->matrix, &c->scalars, &c->fmt, &c->synth, &c->owner_start, &c->refs, &c->spart, &c->stile_file};
     for (DevBuf* b : all) release(c, *b);
     if (c->ev_ok) for (int i = 0; i < T_N; ++i) cudaEventDestroy(c->ev[i]);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -473,7 +473,6 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
     ENSURE(c, c->valid, P.n_groups_max * 4);
     ENSURE(c, c->hist, (size_t)B * 8 * kCursorStride);
     ENSURE(c, c->offsets, (size_t)(B + 1) * 8);
-    ENSURE(c, c->records, P.max_stream * 8);
 
     if (c->ev_ok) cudaEventRecord(c->ev[T_START], st);
     // ---- stage host inputs
@@ -521,114 +520,172 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
     CU_TRY(c, cudaGetLastError());
     if (c->ev_ok) cudaEventRecord(c->ev[T_PACK], st);
 
-    // ---- extract: count, offsets, scatter
-    ExtractParams ep{};
-    ep.codes = (const unsigned long long*)c->codes.p;
-    ep.valid = (const uint32_t*)c->valid.p;
-    ep.scalars = d_scalars;
-    ep.file_stream_start = (const uint64_t*)c->fss.p;
-    ep.files = d_files;
-    ep.n_files = P.F;
-    ep.k = c->cfg.k;
-    ep.bucket_bits = P.bucket_bits;
-    ep.row_bits = P.row_bits;
-    ep.hist = (unsigned long long*)c->hist.p;
-    ep.records = (unsigned long long*)c->records.p;
-    ep.dbg = (c->cfg.flags >> 8) & 3;
-    ep.offsets = (const unsigned long long*)c->offsets.p;
-    const uint64_t n_etiles_max = (P.n_groups_max + kExtractThreads - 1) / kExtractThreads;
-    const uint32_t egrid = (uint32_t)std::min<uint64_t>(n_etiles_max, (uint64_t)c->sm_count * 8);
-    const size_t hist_smem = (size_t)B * 4;
-    CU_TRY(c, cudaFuncSetAttribute(k_extract<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
-    k_extract<0><<<egrid, kExtractThreads, hist_smem, st>>>(ep);
-    k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->hist.p, (unsigned long long*)c->offsets.p, B, d_scalars,
-                                         S_N_WINDOWS, kCursorStride);
-    L.n += 2;
-    CU_TRY(c, cudaGetLastError());
-    if (c->ev_ok) cudaEventRecord(c->ev[T_COUNT], st);
-    if (B <= (uint32_t)kStMaxBuckets && !(c->cfg.flags & GRMKM_FLAG_SIMPLE_SCATTER)) {
-        const size_t ssm = staged_smem_bytes(B);
-        const uint64_t n_stiles = (P.n_groups_max + (kStTile / 32) - 1) / (kStTile / 32);
-        CU_TRY(c, cudaFuncSetAttribute(k_extract_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
-        k_extract_staged<<<(uint32_t)std::min<uint64_t>(n_stiles, (uint64_t)c->sm_count), kStThreads, ssm, st>>>(ep);
-    } else {
-        k_extract<1><<<egrid, kExtractThreads, 0, st>>>(ep);
-    }
-    L.n++;
-    CU_TRY(c, cudaGetLastError());
-    if (c->ev_ok) cudaEventRecord(c->ev[T_SCATTER], st);
-
-    // ---- optional abundance filter (reads: -abundance-min, kmer_count.py:48)
-    const unsigned long long* agg_records = (const unsigned long long*)c->records.p;
-    const unsigned long long* agg_offsets = (const unsigned long long*)c->offsets.p;
+    // ---- extract + scatter, (abundance), aggregate.  Pass 0 scatters into over-provisioned bucket regions
+    // without a count pass; if a region overflows (heavily skewed k-mer spectrum) pass 1 redoes the
+    // scatter with exact offsets from a count pass.
+    const bool staged = B <= (uint32_t)kStMaxBuckets && !(c->cfg.flags & GRMKM_FLAG_SIMPLE_SCATTER);
+    const bool try_regions = staged && !(c->cfg.flags & GRMKM_FLAG_EXACT_OFFSETS);
+    const uint64_t n_stiles = (P.n_groups_max + (kStTile / 32) - 1) / (kStTile / 32);
     const uint32_t agrid = std::min<uint32_t>(B, (uint32_t)c->sm_count);
-    if (c->cfg.min_abundance > 1) {
-        ENSURE(c, c->records2, P.max_stream * 8);
-        ENSURE(c, c->bcounts, (size_t)B * 8);
-        ENSURE(c, c->offsets2, (size_t)(B + 1) * 8);
-        AggParams ap{};
-        ap.records = agg_records; ap.offsets = agg_offsets; ap.B = B; ap.bucket_bits = P.bucket_bits;
-        ap.row_bits = P.row_bits; ap.n_words = 1;
-        ap.slots = (uint32_t)std::min<size_t>(16384, budget / 16);
-        ap.mode = 2; ap.min_abundance = c->cfg.min_abundance; ap.b_begin = 0; ap.b_end = B;
-        ap.scalars = (unsigned long long*)d_scalars;
-        ap.bucket_out_counts = (unsigned long long*)c->bcounts.p;
-        ap.out_records = (unsigned long long*)c->records2.p;
-        const size_t sm = (size_t)ap.slots * 16;
-        CU_TRY(c, cudaFuncSetAttribute(k_aggregate<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        k_aggregate<2><<<agrid, kAggThreads, sm, st>>>(ap);
-        k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->bcounts.p, (unsigned long long*)c->offsets2.p, B,
-                                             d_scalars, S_N_SOLID, 1);
-        k_compact_records<<<agrid * 4, 256, 0, st>>>((const unsigned long long*)c->records2.p, agg_offsets,
-                                                     (const unsigned long long*)c->offsets2.p, B,
-                                                     (unsigned long long*)c->records.p);
-        L.n += 3;
-        CU_TRY(c, cudaGetLastError());
-        agg_offsets = (const unsigned long long*)c->offsets2.p;
-    }
-    if (c->ev_ok) cudaEventRecord(c->ev[T_ABUND], st);
-
-    // ---- aggregate (dsk2kover): retry with a larger output if the first guess was too small
-    uint64_t ucap = std::min<uint64_t>(P.max_stream, std::max<uint64_t>(1 << 16, P.max_stream / 4));
-    ucap = std::min<uint64_t>(ucap, 0xFFFFFFFFULL);
     uint64_t sc[S_COUNT];
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        ENSURE(c, c->ukeys, ucap * 8);
-        ENSURE(c, c->uwords, (size_t)ucap * P.W * 8);
-        if (mode == 1) { ENSURE(c, c->bcounts, (size_t)B * 8); CU_TRY(c, cudaMemsetAsync(c->bcounts.p, 0, (size_t)B * 8, st)); }
-        AggParams ap{};
-        ap.records = agg_records; ap.offsets = agg_offsets; ap.B = B; ap.bucket_bits = P.bucket_bits;
-        ap.row_bits = P.row_bits; ap.n_words = P.W; ap.slots = P.slots;
-        ap.keep_singletons = c->cfg.keep_singletons; ap.mode = mode;
-        ap.out_keys = (unsigned long long*)c->ukeys.p; ap.out_words = (unsigned long long*)c->uwords.p;
-        ap.cap = ucap; ap.scalars = (unsigned long long*)d_scalars;
-        ap.bucket_out_counts = (unsigned long long*)c->bcounts.p;
-        ENSURE(c, c->owner_start, (size_t)(n_ranges + 1) * 8);
-        uint64_t* d_owner = (uint64_t*)c->owner_start.p;
-        for (uint32_t r = 0; r < n_ranges; ++r) {
-            ap.b_begin = (uint32_t)((uint64_t)B * r / n_ranges);
-            ap.b_end = (uint32_t)((uint64_t)B * (r + 1) / n_ranges);
-            CU_TRY(c, cudaMemcpyAsync(d_owner + r, d_scalars + S_U_NEEDED, 8, cudaMemcpyDeviceToDevice, st));
-            const uint32_t grid = std::max(1u, std::min<uint32_t>(ap.b_end - ap.b_begin, (uint32_t)c->sm_count));
-            if (mode == 0) {
-                CU_TRY(c, cudaFuncSetAttribute(k_aggregate<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.agg_smem));
-                k_aggregate<0><<<grid, kAggThreads, P.agg_smem, st>>>(ap);
-            } else {
-                CU_TRY(c, cudaFuncSetAttribute(k_aggregate<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.agg_smem));
-                k_aggregate<1><<<grid, kAggThreads, P.agg_smem, st>>>(ap);
+    uint64_t ucap = 0;
+    for (int pass = try_regions ? 0 : 1; pass < 2; ++pass) {
+        const bool regions = (pass == 0);
+        uint64_t cap = 0;
+        if (regions) {
+            cap = (uint64_t)((double)P.max_stream / B * 1.25) + 2048;
+            cap = (cap + 15) & ~15ULL;
+            ENSURE(c, c->records, ((uint64_t)B * cap + kStTile) * 8);
+        } else {
+            ENSURE(c, c->records, P.max_stream * 8);
+        }
+        {
+            const uint64_t zeros[S_COUNT] = {0};
+            // keep S_STREAM_LEN and S_N_RECORDS (parse results), clear the rest
+            CU_TRY(c, cudaMemcpyAsync(d_scalars + S_N_WINDOWS, zeros, (S_COUNT - S_N_WINDOWS) * 8, cudaMemcpyHostToDevice, st));
+        }
+        ExtractParams ep{};
+        ep.codes = (const unsigned long long*)c->codes.p;
+        ep.valid = (const uint32_t*)c->valid.p;
+        ep.scalars = d_scalars;
+        ep.file_stream_start = (const uint64_t*)c->fss.p;
+        ep.files = d_files;
+        ep.n_files = P.F;
+        ep.k = c->cfg.k;
+        ep.bucket_bits = P.bucket_bits;
+        ep.row_bits = P.row_bits;
+        ep.hist = (unsigned long long*)c->hist.p;
+        ep.records = (unsigned long long*)c->records.p;
+        ep.dbg = 0;
+        ep.offsets = (const unsigned long long*)c->offsets.p;
+        const uint64_t n_etiles_max = (P.n_groups_max + kExtractThreads - 1) / kExtractThreads;
+        const uint32_t egrid = (uint32_t)std::min<uint64_t>(n_etiles_max, (uint64_t)c->sm_count * 8);
+        if (regions) {
+            k_init_regions<<<(B + 1 + 255) / 256, 256, 0, st>>>((unsigned long long*)c->offsets.p,
+                                                                (unsigned long long*)c->hist.p, B, cap);
+            L.n++;
+        } else {
+            CU_TRY(c, cudaMemsetAsync(c->hist.p, 0, (size_t)B * 8, st));
+            const size_t hist_smem = (size_t)B * 4;
+            CU_TRY(c, cudaFuncSetAttribute(k_extract<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
+            k_extract<0><<<egrid, kExtractThreads, hist_smem, st>>>(ep);
+            k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->hist.p, (unsigned long long*)c->offsets.p, B,
+                                                 d_scalars, S_N_WINDOWS, kCursorStride);
+            L.n += 2;
+        }
+        CU_TRY(c, cudaGetLastError());
+        if (c->ev_ok) cudaEventRecord(c->ev[T_COUNT], st);
+        if (staged) {
+            ENSURE(c, c->stile_file, n_stiles * 4);
+            ScatterParams sp{};
+            sp.codes = ep.codes; sp.valid = ep.valid; sp.scalars = d_scalars; sp.file_stream_start = ep.file_stream_start;
+            sp.files = d_files; sp.tile_file = (const uint32_t*)c->stile_file.p; sp.n_files = P.F; sp.k = c->cfg.k;
+            sp.bucket_bits = P.bucket_bits; sp.row_bits = P.row_bits; sp.cursors = (unsigned long long*)c->hist.p;
+            sp.records = (unsigned long long*)c->records.p; sp.cap = cap; sp.dump = (uint64_t)B * cap;
+            sp.overflow = (unsigned long long*)(d_scalars + S_OVERFLOW);
+            k_scatter_tile_files<<<(uint32_t)((n_stiles + 255) / 256), 256, 0, st>>>(d_scalars, sp.file_stream_start, P.F,
+                                                                                  (uint32_t*)c->stile_file.p, n_stiles);
+            const size_t ssm = staged_smem_bytes(B);
+            const uint32_t sgrid = (uint32_t)std::min<uint64_t>(n_stiles, (uint64_t)c->sm_count);
+#define GRMKM_SCATTER(KT)                                                                                       \
+    do {                                                                                                        \
+        CU_TRY(c, cudaFuncSetAttribute(k_scatter<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));  \
+        k_scatter<KT><<<sgrid, kStThreads, ssm, st>>>(sp);                                                      \
+    } while (0)
+            switch (c->cfg.k) {
+                case 31: GRMKM_SCATTER(31); break;
+                case 21: GRMKM_SCATTER(21); break;
+                case 15: GRMKM_SCATTER(15); break;
+                default: GRMKM_SCATTER(0); break;
             }
+#undef GRMKM_SCATTER
+            L.n += 2;
+        } else {
+            k_extract<1><<<egrid, kExtractThreads, 0, st>>>(ep);
             L.n++;
         }
-        CU_TRY(c, cudaMemcpyAsync(d_owner + n_ranges, d_scalars + S_U_NEEDED, 8, cudaMemcpyDeviceToDevice, st));
+        // bucket b = records[begin[b], end[b]): begin = offsets, end = the cursors (clamped to the region)
+        k_finish_regions<<<1, 1024, 0, st>>>((const unsigned long long*)c->offsets.p, (unsigned long long*)c->hist.p, B, cap,
+                                             (unsigned long long*)d_scalars, S_N_WINDOWS);
+        L.n++;
         CU_TRY(c, cudaGetLastError());
-        CU_TRY(c, cudaMemcpyAsync(sc, d_scalars, sizeof sc, cudaMemcpyDeviceToHost, st));
-        CU_TRY(c, cudaStreamSynchronize(st));
-        if (sc[S_U_NEEDED] <= ucap) break;
-        if (attempt == 1 || sc[S_U_NEEDED] > 0xFFFFFFFFULL)
-            return fail(c, GRMKM_E_UNSUPPORTED, "more than 2^32 columns in one context");
-        ucap = sc[S_U_NEEDED];
-        const uint64_t zero3[3] = {0, 0, 0};
-        CU_TRY(c, cudaMemcpyAsync(d_scalars + S_U_NEEDED, zero3, 3 * 8, cudaMemcpyHostToDevice, st));
+        if (c->ev_ok) cudaEventRecord(c->ev[T_SCATTER], st);
+
+        // ---- optional abundance filter (reads: -abundance-min, kmer_count.py:48)
+        const unsigned long long* agg_records = (const unsigned long long*)c->records.p;
+        const unsigned long long* agg_begin = (const unsigned long long*)c->offsets.p;
+        const unsigned long long* agg_end = (const unsigned long long*)c->hist.p;
+        if (c->cfg.min_abundance > 1) {
+            ENSURE(c, c->records2, c->records.cap);
+            ENSURE(c, c->bcounts, (size_t)B * 8);
+            ENSURE(c, c->offsets2, (size_t)(B + 1) * 8);
+            AggParams ap{};
+            ap.records = agg_records; ap.begin = agg_begin; ap.end = agg_end; ap.B = B; ap.bucket_bits = P.bucket_bits;
+            ap.row_bits = P.row_bits; ap.n_words = 1;
+            ap.slots = (uint32_t)std::min<size_t>(16384, budget / 16);
+            ap.mode = 2; ap.min_abundance = c->cfg.min_abundance; ap.b_begin = 0; ap.b_end = B;
+            ap.scalars = (unsigned long long*)d_scalars;
+            ap.bucket_out_counts = (unsigned long long*)c->bcounts.p;
+            ap.out_records = (unsigned long long*)c->records2.p;
+            const size_t sm = (size_t)ap.slots * 16;
+            CU_TRY(c, cudaFuncSetAttribute(k_aggregate<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            k_aggregate<2><<<agrid, kAggThreads, sm, st>>>(ap);
+            k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->bcounts.p, (unsigned long long*)c->offsets2.p, B,
+                                                 d_scalars, S_N_SOLID, 1);
+            k_compact_records<<<agrid * 4, 256, 0, st>>>((const unsigned long long*)c->records2.p, agg_begin,
+                                                         (const unsigned long long*)c->offsets2.p, B,
+                                                         (unsigned long long*)c->records.p);
+            L.n += 3;
+            CU_TRY(c, cudaGetLastError());
+            agg_begin = (const unsigned long long*)c->offsets2.p;
+            agg_end = agg_begin + 1;
+        }
+        if (c->ev_ok) cudaEventRecord(c->ev[T_ABUND], st);
+
+        // ---- aggregate (dsk2kover): retry with a larger output if the first guess was too small
+        ucap = std::min<uint64_t>(P.max_stream, std::max<uint64_t>(1 << 16, P.max_stream / 4));
+        ucap = std::min<uint64_t>(ucap, 0xFFFFFFFFULL);
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            ENSURE(c, c->ukeys, ucap * 8);
+            ENSURE(c, c->uwords, (size_t)ucap * P.W * 8);
+            if (mode == 1) { ENSURE(c, c->bcounts, (size_t)B * 8); CU_TRY(c, cudaMemsetAsync(c->bcounts.p, 0, (size_t)B * 8, st)); }
+            AggParams ap{};
+            ap.records = agg_records; ap.begin = agg_begin; ap.end = agg_end; ap.B = B; ap.bucket_bits = P.bucket_bits;
+            ap.row_bits = P.row_bits; ap.n_words = P.W; ap.slots = P.slots;
+            ap.keep_singletons = c->cfg.keep_singletons; ap.mode = mode;
+            ap.out_keys = (unsigned long long*)c->ukeys.p; ap.out_words = (unsigned long long*)c->uwords.p;
+            ap.cap = ucap; ap.scalars = (unsigned long long*)d_scalars;
+            ap.bucket_out_counts = (unsigned long long*)c->bcounts.p;
+            ENSURE(c, c->owner_start, (size_t)(n_ranges + 1) * 8);
+            uint64_t* d_owner = (uint64_t*)c->owner_start.p;
+            for (uint32_t r = 0; r < n_ranges; ++r) {
+                ap.b_begin = (uint32_t)((uint64_t)B * r / n_ranges);
+                ap.b_end = (uint32_t)((uint64_t)B * (r + 1) / n_ranges);
+                CU_TRY(c, cudaMemcpyAsync(d_owner + r, d_scalars + S_U_NEEDED, 8, cudaMemcpyDeviceToDevice, st));
+                const uint32_t grid = std::max(1u, std::min<uint32_t>(ap.b_end - ap.b_begin, (uint32_t)c->sm_count));
+                if (mode == 0) {
+                    CU_TRY(c, cudaFuncSetAttribute(k_aggregate_cols<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.agg_smem));
+                    k_aggregate_cols<0><<<grid, kAggThreads, P.agg_smem, st>>>(ap);
+                } else {
+                    CU_TRY(c, cudaFuncSetAttribute(k_aggregate_cols<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.agg_smem));
+                    k_aggregate_cols<1><<<grid, kAggThreads, P.agg_smem, st>>>(ap);
+                }
+                L.n++;
+            }
+            CU_TRY(c, cudaMemcpyAsync(d_owner + n_ranges, d_scalars + S_U_NEEDED, 8, cudaMemcpyDeviceToDevice, st));
+            CU_TRY(c, cudaGetLastError());
+            CU_TRY(c, cudaMemcpyAsync(sc, d_scalars, sizeof sc, cudaMemcpyDeviceToHost, st));
+            CU_TRY(c, cudaStreamSynchronize(st));
+            if (regions && sc[S_OVERFLOW]) break;
+            if (sc[S_U_NEEDED] <= ucap) break;
+            if (attempt == 1 || sc[S_U_NEEDED] > 0xFFFFFFFFULL)
+                return fail(c, GRMKM_E_UNSUPPORTED, "more than 2^32 columns in one context");
+            ucap = sc[S_U_NEEDED];
+            const uint64_t zero3[3] = {0, 0, 0};
+            CU_TRY(c, cudaMemcpyAsync(d_scalars + S_U_NEEDED, zero3, 3 * 8, cudaMemcpyHostToDevice, st));
+        }
+        if (!(regions && sc[S_OVERFLOW])) break;
+        c->stats.n_region_overflows++;
     }
     if (c->ev_ok) cudaEventRecord(c->ev[T_AGG], st);
     const uint64_t U = sc[S_U_NEEDED];
@@ -898,7 +955,7 @@ int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
     L.n += 3;
     CU_TRY(c, cudaGetLastError());
     if (c->ev_ok) cudaEventRecord(c->ev[T_SCATTER], st);
-    ap.records = (const unsigned long long*)c->refs.p; ap.offsets = (const unsigned long long*)c->offsets.p;
+    ap.records = (const unsigned long long*)c->refs.p; ap.begin = (const unsigned long long*)c->offsets.p; ap.end = ap.begin + 1;
     ap.B = B; ap.bucket_bits = mb; ap.row_bits = 0; ap.n_words = W_total; ap.slots = slots;
     ap.keep_singletons = c->cfg.keep_singletons; ap.mode = 3;
     ap.out_keys = (unsigned long long*)c->ukeys.p; ap.out_words = (unsigned long long*)c->uwords.p;

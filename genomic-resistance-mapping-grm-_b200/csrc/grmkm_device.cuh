@@ -26,7 +26,8 @@ enum Scalar : int {
     S_N_DISTINCT,       // distinct k-mers before the singleton filter
     S_N_SPLITS,         // sub-range splits
     S_N_SOLID,          // records surviving the abundance filter
-    S_WORK,             // persistent-kernel work counter
+    S_WORK,             // local-sort overflow flag
+    S_OVERFLOW,         // a bucket region of the over-provisioned scatter was too small
     S_COUNT
 };
 
@@ -49,6 +50,19 @@ __host__ __device__ __forceinline__ uint64_t unfmix64(uint64_t h) {
     h ^= h >> 33; h *= 0x4f74430c22a54005ULL;
     h ^= h >> 33; return h;
 }
+
+// ---- multiplicative hash: a bijection on u64 that costs one 64-bit multiply ----------------
+// bucket = top bits of the product, table key = the rest; the k-mer comes back with the inverse.
+constexpr uint64_t kHashMul = 0x9E3779B97F4A7C15ULL;
+constexpr uint64_t inv_odd64(uint64_t a) {
+    uint64_t x = a;                      // Newton: doubles the number of correct low bits per step
+    for (int i = 0; i < 6; ++i) x *= 2 - a * x;
+    return x;
+}
+constexpr uint64_t kHashInv = inv_odd64(kHashMul);
+static_assert(kHashMul * kHashInv == 1ULL, "kHashInv is not the inverse of kHashMul");
+__host__ __device__ __forceinline__ uint64_t khash(uint64_t x) { return x * kHashMul; }
+__host__ __device__ __forceinline__ uint64_t kunhash(uint64_t h) { return h * kHashInv; }
 
 // ---- parse transducer summaries ---------------------------------------------
 // A tile (or 16-byte chunk) of text is summarised as a function of the parser

@@ -354,7 +354,7 @@ k_extract(const ExtractParams p) {
                     row = p.files[f].row;
                 }
                 const uint64_t canon = fw < rc ? fw : rc;
-                const uint64_t h = fmix64(canon);
+                const uint64_t h = khash(canon);
                 const uint32_t b = (uint32_t)(h >> key_bits);
                 if (MODE == 0) {
                     atomicAdd(&s_hist[b], 1u);
@@ -379,22 +379,148 @@ k_extract(const ExtractParams p) {
 }
 
 // ---- staged scatter: one tile of 16384 stream positions per CTA iteration -------------------------
-// Records are ranked per bucket with shared-memory atomics, space is reserved with ONE global atomic
-// per (tile, non-empty bucket), the tile is counting-sorted in shared memory and copied out so that
-// records of one bucket leave the SM as contiguous runs (full-sector writes instead of 8-byte ones).
-constexpr int kStThreads = 1024;
-constexpr int kStPerThread = 16;                       // half a 32-entry stream group
+// Phase 1: every thread turns one 32-entry stream group into up to 32 hashed k-mers held in registers.
+//   Forward and reverse-complement values are funnel-shift extractions from a 128-bit window of the
+//   packed stream (and of its 2-bit-reversed copy), so there is no serial rolling dependency.
+//   The tile histogram is built with non-returning shared-memory atomics.
+// Phase 2: scan of the tile histogram; ONE global atomic per (tile, non-empty bucket) reserves space.
+// Phase 3: counting sort of the tile into shared memory (slot = atomic walk of the bucket's run).
+// Phase 4: copy out; records of one bucket leave the SM as contiguous runs.
+// Bucket regions are either exact (cursors = prefix sums from a count pass, cap == 0) or
+// over-provisioned (region b = [b*cap, (b+1)*cap)); an overflowing bucket raises S_OVERFLOW and its
+// records are diverted to a dump area so nothing is corrupted; the host then re-runs the exact path.
+constexpr int kStThreads = 512;
+constexpr int kStPerThread = 32;                       // one 32-entry stream group per thread
 constexpr int kStTile = kStThreads * kStPerThread;     // 16384 positions = 512 groups
 constexpr int kStMaxBuckets = 4096;
+constexpr int kStMaxBins = kStMaxBuckets / kStThreads; // bins per thread in phase 2
 
 __host__ __device__ inline size_t staged_smem_bytes(uint32_t B) {
     return (size_t)B * (8 + 4 + 4) + (size_t)kStTile * (8 + 2);
 }
 
+struct ScatterParams {
+    const unsigned long long* codes;
+    const uint32_t* valid;
+    const uint64_t* scalars;            // S_STREAM_LEN
+    const uint64_t* file_stream_start;  // [n_files + 1]
+    const FileDesc* files;
+    const uint32_t* tile_file;          // file of the first position of every scatter tile
+    uint32_t n_files;
+    uint32_t k;
+    uint32_t bucket_bits;
+    uint32_t row_bits;
+    unsigned long long* cursors;        // [B]
+    unsigned long long* records;
+    unsigned long long cap;             // records per bucket region, 0 = exact offsets
+    unsigned long long dump;            // index of the dump area (kStTile records)
+    unsigned long long* overflow;       // scalar raised when a region is too small
+};
+
+// file of the first position of every scatter tile (one thread per tile)
+__global__ void k_scatter_tile_files(const uint64_t* __restrict__ scalars, const uint64_t* __restrict__ fss,
+                                     uint32_t n_files, uint32_t* __restrict__ tile_file, uint64_t max_tiles) {
+    const uint64_t tile = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= max_tiles) return;
+    const uint64_t p0 = tile * (uint64_t)kStTile;
+    if (p0 >= scalars[S_STREAM_LEN]) return;
+    uint32_t lo = 0, hi = n_files - 1;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (fss[mid] <= p0) lo = mid; else hi = mid - 1;
+    }
+    tile_file[tile] = lo;
+}
+
+__device__ __noinline__ uint32_t row_of_position(const uint64_t* __restrict__ fss, const FileDesc* __restrict__ files,
+                                                 uint32_t n_files, uint32_t f, uint64_t pos) {
+    while (f + 1 < n_files && fss[f + 1] <= pos) ++f;
+    return files[f].row;
+}
+
+__device__ __forceinline__ uint32_t rev2_32(uint32_t x) {
+    x = __brev(x);
+    return ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+}
+
+// exclusive scan of one u32 per thread over an NT-thread block; s_warp must hold 33 words
+template <int NT>
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp, uint32_t& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = lane < NT / 32 ? s_warp[lane] : 0u;
+        uint32_t wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += o;
+        }
+        s_warp[lane] = wi - w;          // exclusive warp offsets
+        if (lane == 31) s_warp[32] = wi;
+    }
+    __syncthreads();
+    total = s_warp[32];
+    const uint32_t r = s_warp[warp] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+// phase 1 body: ALL = every window of this group is valid (no per-entry test)
+template <bool ALL>
+__device__ __forceinline__ uint32_t scatter_hash_group(const uint32_t (&r)[4], const uint32_t (&y)[4], uint32_t n0, uint32_t n1,
+                                                       uint32_t kbits, uint32_t kmask_lo, uint32_t kmask_hi, uint32_t key_bits,
+                                                       uint32_t* s_cnt, unsigned long long (&hsh)[kStPerThread]) {
+    uint32_t have = 0;
+#pragma unroll
+    for (int e = 0; e < kStPerThread; ++e) {
+        if (ALL || (__funnelshift_r(n0, n1, e) & kbits) == 0) {
+            const int fs = 2 * (31 - e), fw_w = fs >> 5, fw_s = fs & 31;
+            const int rs = 2 * e, rc_w = rs >> 5, rc_s = rs & 31;
+            const uint32_t fw_lo = __funnelshift_r(r[fw_w], r[fw_w + 1], fw_s) & kmask_lo;
+            const uint32_t fw_hi = __funnelshift_r(r[fw_w + 1], r[fw_w + 2], fw_s) & kmask_hi;
+            const uint32_t rc_lo = __funnelshift_r(y[rc_w], y[rc_w + 1], rc_s) & kmask_lo;
+            const uint32_t rc_hi = __funnelshift_r(y[rc_w + 1], y[rc_w + 2], rc_s) & kmask_hi;
+            const uint64_t fw = ((uint64_t)fw_hi << 32) | fw_lo, rc = ((uint64_t)rc_hi << 32) | rc_lo;
+            const uint64_t h = khash(fw < rc ? fw : rc);
+            atomicAdd(&s_cnt[(uint32_t)(h >> key_bits)], 1u);
+            hsh[e] = h;
+            if (!ALL) have |= 1u << e;
+        }
+    }
+    return ALL ? 0xFFFFFFFFu : have;
+}
+
+// phase 3 body: record = (hash << row_bits) | row (the top row_bits bits of the hash are bucket bits and fall off)
+template <bool ALL>
+__device__ __forceinline__ void scatter_place_group(const unsigned long long (&hsh)[kStPerThread], uint32_t have, uint32_t key_bits,
+                                                    uint32_t row_bits, uint32_t row0, bool one_row, uint32_t f, uint64_t pos0,
+                                                    const ScatterParams& p, uint32_t* s_off, unsigned long long* s_rec,
+                                                    uint16_t* s_bin) {
+#pragma unroll
+    for (int e = 0; e < kStPerThread; ++e) {
+        if (ALL || ((have >> e) & 1u)) {
+            const uint32_t b = (uint32_t)(hsh[e] >> key_bits);
+            const uint32_t dst = atomicAdd(&s_off[b], 1u);      // s_off[b] walks through the bucket's run
+            const uint32_t row = (ALL || one_row) ? row0 : row_of_position(p.file_stream_start, p.files, p.n_files, f, pos0 + e);
+            s_rec[dst] = (hsh[e] << row_bits) | row;
+            s_bin[dst] = (uint16_t)b;
+        }
+    }
+}
+
+template <int KT>   // compile-time k, or 0 = p.k
 __global__ void __launch_bounds__(kStThreads, 1)
-k_extract_staged(const ExtractParams p) {
+k_scatter(const ScatterParams p) {
     extern __shared__ unsigned long long s_dyn[];
-    __shared__ uint32_t s_f0, s_total;
+    __shared__ uint32_t s_total;
     __shared__ uint32_t s_warp[33];
     const uint32_t B = 1u << p.bucket_bits;
     unsigned long long* s_delta = s_dyn;                         // [B]   global base - tile offset
@@ -404,95 +530,78 @@ k_extract_staged(const ExtractParams p) {
     uint16_t* s_bin = reinterpret_cast<uint16_t*>(s_off + B);    // [kStTile]
     const uint64_t stream_len = p.scalars[S_STREAM_LEN];
     const uint64_t n_groups = (stream_len + 31) >> 5;
-    const uint64_t n_tiles = (n_groups + (kStTile / 32) - 1) / (kStTile / 32);
-    const uint32_t k = p.k;
-    const uint64_t kmask = k == 32 ? ~0ULL : ((1ULL << (2 * k)) - 1);
+    const uint64_t n_tiles = (n_groups + kStThreads - 1) / kStThreads;
+    const uint32_t k = KT ? (uint32_t)KT : p.k;
+    const uint32_t kmask_lo = k >= 16 ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
+    const uint32_t kmask_hi = k <= 16 ? 0u : (k == 32 ? 0xFFFFFFFFu : ((1u << (2 * k - 32)) - 1u));
+    const uint32_t kbits = k == 32 ? 0xFFFFFFFFu : ((1u << k) - 1u);
     const uint32_t key_bits = 64 - p.bucket_bits;
-    const uint64_t key_mask = (1ULL << key_bits) - 1;
-    const int lane = threadIdx.x & 31;
-    const uint32_t half = threadIdx.x & 1;
-    const uint32_t bins_per_thread = (B + kStThreads - 1) / kStThreads;
+    const uint32_t row_bits = p.row_bits;
+    const uint32_t per = B >= (uint32_t)kStThreads ? B / kStThreads : 1u;   // bins per thread in phase 2
     for (uint32_t i = threadIdx.x; i < B; i += kStThreads) s_cnt[i] = 0;
+    __syncthreads();
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint64_t g = tile * (kStTile / 32) + (threadIdx.x >> 1);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const uint64_t p0 = tile * (uint64_t)kStTile;
-            uint32_t lo = 0, hi = p.n_files - 1;
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi + 1) >> 1;
-                if (p.file_stream_start[mid] <= p0) lo = mid; else hi = mid - 1;
-            }
-            s_f0 = lo;
+        // ---- phase 1: 32 hashed k-mers per thread into registers + tile histogram
+        const uint64_t g = tile * kStThreads + threadIdx.x;
+        unsigned long long cur_c = 0, prev_c = 0; uint32_t cur_v = 0, prev_v = 0;
+        if (g < n_groups) {
+            cur_c = p.codes[g]; cur_v = p.valid[g];
+            if (g > 0) { prev_c = p.codes[g - 1]; prev_v = p.valid[g - 1]; }
         }
-        __syncthreads();
-        // ---- phase 1: records into registers, rank per bucket
-        unsigned long long cur_c = 0; uint32_t cur_v = 0;
-        if (g < n_groups) { cur_c = p.codes[g]; cur_v = p.valid[g]; }
-        unsigned long long prev_c = __shfl_up_sync(0xffffffffu, cur_c, 2);
-        uint32_t prev_v = __shfl_up_sync(0xffffffffu, cur_v, 2);
-        if (lane < 2) {
-            if (g > 0 && g - 1 < n_groups) { prev_c = p.codes[g - 1]; prev_v = p.valid[g - 1]; }
-            else { prev_c = 0; prev_v = 0; }
-        }
-        unsigned long long rec[kStPerThread];
-        uint32_t meta[kStPerThread];
-        uint32_t have = 0;
-        const uint32_t my_v = (cur_v >> (16 * half)) & 0xFFFFu;
-        if (g < n_groups && my_v) {
-            const uint32_t my_c = (uint32_t)(cur_c >> (32 * half));
-            const unsigned long long win_c = half ? ((prev_c >> 32) | (cur_c << 32)) : prev_c;
-            const uint32_t win_v = half ? ((prev_v >> 16) | (cur_v << 16)) : prev_v;
-            const uint64_t pos0 = g * 32ULL + 16 * half;
-            uint32_t f = s_f0;
+        unsigned long long hsh[kStPerThread];     // kept across the barriers
+        uint32_t have = 0, row0 = 0, f = 0;
+        bool one_row = true;
+        const uint64_t pos0 = g * 32ULL;
+        if (cur_v) {
+            // 128-bit window: the 32 entries before mine (x[0], x[1]) and my 32 entries (x[2], x[3]); entry j at bits 2j
+            const uint32_t x[4] = {(uint32_t)prev_c, (uint32_t)(prev_c >> 32), (uint32_t)cur_c, (uint32_t)(cur_c >> 32)};
+            // invalid-entry bits, shifted so that bit e is the first entry of the window of my entry e
+            const unsigned long long nvs = (~((unsigned long long)prev_v | ((unsigned long long)cur_v << 32))) >> (33 - k);
+            const uint32_t n0 = (uint32_t)nvs, n1 = (uint32_t)(nvs >> 32);
+            // reverse-complement source: window >> 2(33-k), complemented (code ^ 2); forward source: 2-bit reversed window
+            const uint32_t S0 = 2 * (33 - k);
+            unsigned long long Yl, Yh;
+            if (S0 == 64) { Yl = cur_c; Yh = 0; }
+            else { Yl = (prev_c >> S0) | (cur_c << (64 - S0)); Yh = cur_c >> S0; }
+            const uint32_t y[4] = {(uint32_t)Yl ^ 0xAAAAAAAAu, (uint32_t)(Yl >> 32) ^ 0xAAAAAAAAu,
+                                   (uint32_t)Yh ^ 0xAAAAAAAAu, (uint32_t)(Yh >> 32) ^ 0xAAAAAAAAu};
+            const uint32_t r[4] = {rev2_32(x[3]), rev2_32(x[2]), rev2_32(x[1]), rev2_32(x[0])};
+            f = p.tile_file[tile];
             while (f + 1 < p.n_files && p.file_stream_start[f + 1] <= pos0) ++f;
-            uint64_t next_start = (f + 1 < p.n_files) ? p.file_stream_start[f + 1] : ~0ULL;
-            uint32_t row = p.files[f].row;
-            const uint64_t le = k == 32 ? win_c : ((win_c >> (2 * (32 - k))) & kmask);
-            uint64_t rc = le ^ (0xAAAAAAAAAAAAAAAAULL & kmask);
-            uint64_t fw = rev2(le) >> (64 - 2 * k);
-            uint32_t run = min((uint32_t)__clz(~win_v), k);
-#pragma unroll
-            for (int e = 0; e < kStPerThread; ++e) {
-                const uint32_t c = (my_c >> (2 * e)) & 3u;
-                fw = ((fw << 2) | c) & kmask;
-                rc = (rc >> 2) | ((uint64_t)(c ^ 2u) << (2 * (k - 1)));
-                if ((my_v >> e) & 1u) run = min(run + 1, k); else run = 0;
-                if (run == k) {
-                    const uint64_t pos = pos0 + e;
-                    if (pos >= next_start) {
-                        while (f + 1 < p.n_files && p.file_stream_start[f + 1] <= pos) ++f;
-                        next_start = (f + 1 < p.n_files) ? p.file_stream_start[f + 1] : ~0ULL;
-                        row = p.files[f].row;
-                    }
-                    const uint64_t canon = fw < rc ? fw : rc;
-                    const uint64_t h = fmix64(canon);
-                    const uint32_t b = (uint32_t)(h >> key_bits);
-                    const uint32_t rank = atomicAdd(&s_cnt[b], 1u);
-                    rec[e] = ((h & key_mask) << p.row_bits) | row;
-                    meta[e] = b | (rank << 12);
-                    have |= 1u << e;
-                }
-            }
+            const uint64_t next_start = (f + 1 < p.n_files) ? p.file_stream_start[f + 1] : ~0ULL;
+            row0 = p.files[f].row;
+            one_row = pos0 + kStPerThread <= next_start;
+            // windows of my entries cover bits [0, 31 + k) of nvs
+            const bool all_valid = (n0 | (n1 & ((1u << (k - 1)) - 1u))) == 0;
+            if (all_valid) have = scatter_hash_group<true>(r, y, n0, n1, kbits, kmask_lo, kmask_hi, key_bits, s_cnt, hsh);
+            else have = scatter_hash_group<false>(r, y, n0, n1, kbits, kmask_lo, kmask_hi, key_bits, s_cnt, hsh);
         }
         __syncthreads();
         // ---- phase 2: scan the tile histogram, reserve global space, clear the histogram
         {
-            const uint32_t b0 = threadIdx.x * bins_per_thread;
-            uint32_t cnt[4] = {0, 0, 0, 0};
+            const uint32_t b0 = threadIdx.x * per;
+            uint32_t cnt[kStMaxBins];
             uint32_t sum = 0;
-            for (uint32_t i = 0; i < bins_per_thread; ++i)
-                if (b0 + i < B) { cnt[i] = s_cnt[b0 + i]; s_cnt[b0 + i] = 0; sum += cnt[i]; }
+#pragma unroll
+            for (uint32_t i = 0; i < (uint32_t)kStMaxBins; ++i) {
+                cnt[i] = 0;
+                if (i < per && b0 < B) { cnt[i] = s_cnt[b0 + i]; s_cnt[b0 + i] = 0; sum += cnt[i]; }
+            }
             uint32_t total;
-            uint32_t off = block_excl_scan_1024(sum, s_warp, total);
+            uint32_t off = block_excl_scan<kStThreads>(sum, s_warp, total);
             if (threadIdx.x == 0) s_total = total;
-            for (uint32_t i = 0; i < bins_per_thread; ++i) {
-                if (b0 + i < B) {
+#pragma unroll
+            for (uint32_t i = 0; i < (uint32_t)kStMaxBins; ++i) {
+                if (i < per && b0 < B) {
                     s_off[b0 + i] = off;
                     if (cnt[i]) {
-                        const unsigned long long gb = atomicAdd(&p.hist[(size_t)(b0 + i) * kCursorStride],
-                                                                (unsigned long long)cnt[i]);
-                        s_delta[b0 + i] = gb - off;
+                        const unsigned long long gb = atomicAdd(&p.cursors[b0 + i], (unsigned long long)cnt[i]);
+                        if (p.cap && gb + cnt[i] > (unsigned long long)(b0 + i + 1) * p.cap) {
+                            *p.overflow = 1ULL;           // region too small: divert, the host re-runs the exact path
+                            s_delta[b0 + i] = p.dump;
+                        } else {
+                            s_delta[b0 + i] = gb - off;
+                        }
                     }
                     off += cnt[i];
                 }
@@ -500,21 +609,44 @@ k_extract_staged(const ExtractParams p) {
         }
         __syncthreads();
         // ---- phase 3: counting sort into shared memory
-#pragma unroll
-        for (int e = 0; e < kStPerThread; ++e) {
-            if ((have >> e) & 1u) {
-                const uint32_t b = meta[e] & 4095u;
-                const uint32_t dst = s_off[b] + (meta[e] >> 12);
-                s_rec[dst] = rec[e];
-                s_bin[dst] = (uint16_t)b;
-            }
-        }
+        if (have == 0xFFFFFFFFu && one_row) scatter_place_group<true>(hsh, have, key_bits, row_bits, row0, one_row, f, pos0, p, s_off, s_rec, s_bin);
+        else if (have) scatter_place_group<false>(hsh, have, key_bits, row_bits, row0, one_row, f, pos0, p, s_off, s_rec, s_bin);
         __syncthreads();
-        // ---- phase 4: copy out; consecutive threads write consecutive records of a bucket
+        // ---- phase 4: copy out; consecutive threads write consecutive records of a bucket.  No barrier after
+        // it: phase 1 of the next tile touches only s_cnt (already cleared) and registers.
         const uint32_t total = s_total;
+#pragma unroll 4
         for (uint32_t i = threadIdx.x; i < total; i += kStThreads)
             p.records[s_delta[s_bin[i]] + i] = s_rec[i];
     }
+}
+
+// After the scatter: end[b] = cursor[b], clamped to the region when regions are over-provisioned (an
+// overflowing bucket is re-done by the exact path, but nothing may read past its region meanwhile);
+// scalars[which] = number of records = n_windows.  One block.
+__global__ void __launch_bounds__(1024)
+k_finish_regions(const unsigned long long* __restrict__ begin, unsigned long long* __restrict__ end, uint32_t B,
+                 unsigned long long cap, unsigned long long* __restrict__ scalars, int which) {
+    __shared__ unsigned long long s_sum;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    unsigned long long v = 0;
+    for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) {
+        unsigned long long e = end[b];
+        if (cap && e > (unsigned long long)(b + 1) * cap) { e = (unsigned long long)(b + 1) * cap; end[b] = e; }
+        v += e - begin[b];
+    }
+    atomicAdd(&s_sum, v);
+    __syncthreads();
+    if (threadIdx.x == 0) scalars[which] = s_sum;
+}
+
+// region starts for the over-provisioned layout: begin[b] = cursors[b] = b * cap
+__global__ void k_init_regions(unsigned long long* __restrict__ begin, unsigned long long* __restrict__ cursors,
+                               uint32_t B, unsigned long long cap) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) { begin[b] = (unsigned long long)b * cap; cursors[b] = (unsigned long long)b * cap; }
+    if (b == B) begin[b] = (unsigned long long)B * cap;
 }
 
 // exclusive scan of the bucket histogram -> offsets[B+1]; cursors[b] = offsets[b]
@@ -552,7 +684,8 @@ k_bucket_offsets(unsigned long long* __restrict__ hist_cursor, unsigned long lon
 // ------------------------------------------------------------------------------------------
 struct AggParams {
     const unsigned long long* records;   // (key << row_bits) | row
-    const unsigned long long* offsets;   // [B+1]
+    const unsigned long long* begin;     // [B] first record of every bucket
+    const unsigned long long* end;       // [B] one past its last record
     uint32_t B;
     uint32_t bucket_bits;
     uint32_t row_bits;
@@ -601,7 +734,7 @@ k_aggregate(const AggParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     for (uint32_t b = p.b_begin + blockIdx.x; b < p.b_end; b += gridDim.x) {
-        const unsigned long long rbeg = p.offsets[b], rend = p.offsets[b + 1];
+        const unsigned long long rbeg = p.begin[b], rend = p.end[b];
         if (rbeg == rend) continue;
         __syncthreads();
         if (threadIdx.x == 0) { s_sp = 1; s_depth[0] = 0; s_idx[0] = 0; s_wr = 0; }
@@ -625,7 +758,8 @@ k_aggregate(const AggParams p) {
                 if (MODE == 2) key = rec;
                 else if (MODE == 3) { ent = p.parts + (rec >> 8); key = ent[0] & ((1ULL << key_bits) - 1); }
                 else { key = rec >> p.row_bits; row = (uint32_t)(rec & row_mask); }
-                if (depth && (key >> (key_bits - depth)) != ridx) continue;
+                // records carry (bucket_bits - row_bits) redundant bucket bits above the key: mask them for the range test
+                if (depth && ((key & (key_bits >= 64 ? ~0ULL : ((1ULL << key_bits) - 1))) >> (key_bits - depth)) != ridx) continue;
                 uint32_t slot = slot_of(key, slots);
                 bool hit = false;
                 for (int probe = 0; probe < kMaxProbe; ++probe) {
@@ -717,7 +851,7 @@ k_aggregate(const AggParams p) {
                         p.out_records[o] = key;
                     } else if (o < p.cap) {
                         const unsigned long long h = ((unsigned long long)b << key_bits) | key;
-                        p.out_keys[o] = kFinal ? unfmix64(h) : h;
+                        p.out_keys[o] = kFinal ? kunhash(h) : h;
                         for (uint32_t w = 0; w < W; ++w) p.out_words[w * p.cap + o] = words[w * slots + i];
                     }
                 }
@@ -729,6 +863,153 @@ k_aggregate(const AggParams p) {
         }
     }
     (void)warp; (void)s_red;
+}
+
+// ---- column aggregation, tight version (modes 0 = final columns, 1 = partial columns) -------------------
+// Same algorithm as k_aggregate<0/1>; differences that matter for the instruction count and for latency:
+// eight coalesced record loads in flight per thread, the key-range filter only exists on the (rare) split
+// path, presence bits live in 32-bit half-word planes w32[h][slot] (h = (row >> 5) ^ 1, so that
+// word = w32[2w+1] : w32[2w] has genome row g at bit 63 - (g & 63), kover/utils.py:144-154), and the
+// overflow flag is polled once per batch.
+constexpr int kAggBatch = 8;
+
+template <bool FILTER>
+__device__ __forceinline__ void agg_stream(const unsigned long long* __restrict__ recs, uint32_t n, unsigned long long* keys,
+                                           uint32_t* w32, uint32_t slots, uint32_t row_bits, uint32_t row_mask,
+                                           uint32_t key_bits, uint32_t depth, unsigned long long ridx,
+                                           volatile uint32_t* overflow) {
+    for (uint32_t base = threadIdx.x; base < n; base += kAggThreads * kAggBatch) {
+        unsigned long long r[kAggBatch];
+#pragma unroll
+        for (int j = 0; j < kAggBatch; ++j) {
+            const uint32_t idx = base + j * kAggThreads;
+            r[j] = idx < n ? __ldcs(recs + idx) : 0ULL;
+        }
+        if (*overflow) break;
+#pragma unroll
+        for (int j = 0; j < kAggBatch; ++j) {
+            if (base + j * kAggThreads >= n) break;
+            const unsigned long long key = r[j] >> row_bits;
+            const uint32_t row = (uint32_t)r[j] & row_mask;
+            if (FILTER && ((key & ((1ULL << key_bits) - 1)) >> (key_bits - depth)) != ridx) continue;
+            uint32_t slot = slot_of(key, slots);
+            int probe = 0;
+            while (true) {
+                unsigned long long k0 = *(volatile unsigned long long*)&keys[slot];
+                if (k0 == key) break;
+                if (k0 == kEmptyKey) {
+                    k0 = atomicCAS(&keys[slot], kEmptyKey, key);
+                    if (k0 == kEmptyKey || k0 == key) break;
+                }
+                slot = slot + 1 == slots ? 0 : slot + 1;
+                if (++probe >= kMaxProbe) { *overflow = 1; break; }
+            }
+            if (probe < kMaxProbe) atomicOr(&w32[((row >> 5) ^ 1u) * slots + slot], 0x80000000u >> (row & 31u));
+        }
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kAggThreads, 1)
+k_aggregate_cols(const AggParams p) {
+    extern __shared__ unsigned long long s_tab[];   // keys[slots] then w32[2W][slots]
+    __shared__ uint32_t s_overflow, s_sp, s_cnt, s_kept;
+    __shared__ uint32_t s_depth[72];
+    __shared__ unsigned long long s_idx[72];
+    __shared__ unsigned long long s_base;
+    const uint32_t slots = p.slots;
+    const uint32_t W = p.n_words;
+    unsigned long long* keys = s_tab;
+    uint32_t* w32 = reinterpret_cast<uint32_t*>(s_tab + slots);
+    const uint32_t key_bits = 64 - p.bucket_bits;
+    const uint32_t row_mask = (1u << p.row_bits) - 1u;
+    const int lane = threadIdx.x & 31;
+
+    for (uint32_t b = p.b_begin + blockIdx.x; b < p.b_end; b += gridDim.x) {
+        const unsigned long long rbeg = p.begin[b], rend = p.end[b];
+        if (rbeg >= rend) continue;
+        const uint32_t n = (uint32_t)(rend - rbeg);
+        __syncthreads();
+        if (threadIdx.x == 0) { s_sp = 1; s_depth[0] = 0; s_idx[0] = 0; }
+        while (true) {
+            __syncthreads();
+            if (s_sp == 0) break;
+            const uint32_t depth = s_depth[s_sp - 1];
+            const unsigned long long ridx = s_idx[s_sp - 1];
+            __syncthreads();
+            if (threadIdx.x == 0) { s_sp--; s_overflow = 0; s_cnt = 0; s_kept = 0; }
+            for (uint32_t i = threadIdx.x; i < slots; i += kAggThreads) keys[i] = kEmptyKey;
+            for (uint32_t i = threadIdx.x; i < slots * W; i += kAggThreads) reinterpret_cast<unsigned long long*>(w32)[i] = 0;
+            __syncthreads();
+            if (depth == 0) agg_stream<false>(p.records + rbeg, n, keys, w32, slots, p.row_bits, row_mask, key_bits, 0, 0, &s_overflow);
+            else agg_stream<true>(p.records + rbeg, n, keys, w32, slots, p.row_bits, row_mask, key_bits, depth, ridx, &s_overflow);
+            __syncthreads();
+            if (s_overflow) {
+                // split this key range in two and retry (terminates: a range of one key needs one slot)
+                if (threadIdx.x == 0) {
+                    s_depth[s_sp] = depth + 1; s_idx[s_sp] = ridx * 2 + 1; s_sp++;
+                    s_depth[s_sp] = depth + 1; s_idx[s_sp] = ridx * 2; s_sp++;
+                    atomicAdd(&p.scalars[S_N_SPLITS], 1ULL);
+                }
+                continue;
+            }
+            // ---- count what this range emits
+            uint32_t occ = 0, kept = 0;
+            for (uint32_t i = threadIdx.x; i < slots; i += kAggThreads) {
+                if (keys[i] != kEmptyKey) {
+                    occ++;
+                    if (MODE == 1 || p.keep_singletons) kept++;
+                    else {
+                        uint32_t pc = 0;
+                        for (uint32_t h = 0; h < 2 * W; ++h) pc += __popc(w32[h * slots + i]);
+                        kept += (pc >= 2);
+                    }
+                }
+            }
+            occ = __reduce_add_sync(0xffffffffu, occ);
+            kept = __reduce_add_sync(0xffffffffu, kept);
+            if (lane == 0) { atomicAdd(&s_cnt, occ); atomicAdd(&s_kept, kept); }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                s_base = atomicAdd(&p.scalars[S_U_NEEDED], (unsigned long long)s_kept);
+                atomicAdd(&p.scalars[S_N_DISTINCT], (unsigned long long)s_cnt);
+                if (MODE == 1) atomicAdd(&p.bucket_out_counts[b], (unsigned long long)s_kept);
+                s_cnt = 0;
+            }
+            __syncthreads();
+            // ---- emit
+            const unsigned long long base = s_base;
+            for (uint32_t i0 = 0; i0 < slots; i0 += kAggThreads) {
+                const uint32_t i = i0 + threadIdx.x;
+                bool keep = false;
+                unsigned long long key = 0;
+                if (i < slots) {
+                    key = keys[i];
+                    if (key != kEmptyKey) {
+                        if (MODE == 1 || p.keep_singletons) keep = true;
+                        else {
+                            uint32_t pc = 0;
+                            for (uint32_t h = 0; h < 2 * W; ++h) pc += __popc(w32[h * slots + i]);
+                            keep = (pc >= 2);
+                        }
+                    }
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, keep);
+                uint32_t wbase = 0;
+                if (lane == 0 && m) wbase = atomicAdd(&s_cnt, __popc(m));
+                wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                if (keep) {
+                    const unsigned long long o = base + wbase + __popc(m & lanemask_lt());
+                    if (o < p.cap) {
+                        const unsigned long long h = ((unsigned long long)b << key_bits) | (key & ((1ULL << key_bits) - 1));
+                        p.out_keys[o] = MODE == 0 ? kunhash(h) : h;
+                        for (uint32_t w = 0; w < W; ++w)
+                            p.out_words[w * p.cap + o] = ((unsigned long long)w32[(2 * w + 1) * slots + i] << 32) | w32[2 * w * slots + i];
+                    }
+                }
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------

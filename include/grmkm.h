@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GRMKM_ABI_VERSION 2
+#define GRMKM_ABI_VERSION 3
 
 enum {
     GRMKM_OK = 0,
@@ -50,6 +50,7 @@ enum { GRMKM_FASTA = 0, GRMKM_FASTQ = 1 };
 #define GRMKM_FLAG_HASH_ORDER 1u /* keep columns in internal hash order (skip the final sort) */
 #define GRMKM_FLAG_RADIX_ORDER 4u /* order the columns with the LSD radix sort only (A/B timing, fallback test) */
 #define GRMKM_FLAG_SIMPLE_SCATTER 2u /* per-record global-atomic scatter instead of the staged one (A/B timing) */
+#define GRMKM_FLAG_EXACT_OFFSETS 8u /* count pass + exact bucket offsets instead of over-provisioned regions (fallback test) */
 
 typedef struct grmkm_ctx grmkm_ctx;
 
@@ -86,6 +87,7 @@ typedef struct grmkm_stats {
     uint64_t h2d_bytes;     /* host->device bytes moved by the last build          */
     uint64_t device_bytes;  /* device memory held by the context                   */
     uint64_t n_splits;      /* bucket sub-range splits (table overflows handled)   */
+    uint64_t n_region_overflows; /* builds redone with exact offsets (a bucket region was too small) */
 } grmkm_stats;
 
 /* per-stage device time of the last build, milliseconds (CUDA events on the build stream) */
