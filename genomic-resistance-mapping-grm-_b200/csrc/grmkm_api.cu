@@ -51,7 +51,7 @@ struct grmkm_ctx {
     // device buffers (grow-only, reused across builds)
     DevBuf in, files, hdr0, tsum, tile_file, tile_state, tile_pos, bsum, bstate, bpos, fss, codes, valid, hist,
         offsets, offsets2, bcounts, records, records2, ukeys, uwords, skeys, sidx_a, sidx_b, shist, kmers, matrix,
-        scalars, fmt, synth, owner_start, refs, spart, stile_file;
+        scalars, fmt, synth, owner_start, refs, spart, stile_file, bbase;
     size_t device_bytes = 0;
 
     cudaEvent_t ev[T_N]{};
@@ -158,17 +158,27 @@ size_t agg_smem_budget(const grmkm_ctx* c) {
 
 // table capacity for W words per column and the bucket count that keeps a bucket's distinct k-mers
 // (estimated as 3x the largest genome) at about half of it
+// table = (slots + kMaxProbe) x (u64 key + 2W u32 half-words + u8 kept flag); slots = home positions
 uint32_t table_slots(const grmkm_ctx* c, uint32_t W) {
     const size_t budget = agg_smem_budget(c);
-    return (uint32_t)std::min<size_t>(16384, budget / (8 * (1 + (size_t)W)));
+    const size_t total = budget / (9 + 8 * (size_t)W);
+    if (total < (size_t)kMaxProbe + 256) return 0;
+    return (uint32_t)std::min<size_t>(16384, total - kMaxProbe);
 }
+size_t table_smem(uint32_t slots, uint32_t W) {
+    return (((size_t)slots + kMaxProbe) * (9 + 8 * (size_t)W) + 15) & ~size_t(15);
+}
+// Bucket count: the distinct k-mers of a bucket must fit its shared-memory table at a load of about 0.55.
+// The pan-genome of the context is estimated from the largest genome (1.9x its text; a bucket that turns out
+// too full is split into key sub-ranges by the kernel, so the estimate only costs time, never correctness).
+// Fewer buckets = longer runs per scatter tile = fewer store requests, the scatter's bound.
 uint32_t auto_bucket_bits(const grmkm_ctx* c, uint32_t G) {
     std::vector<uint64_t> row_bytes(std::max(G, 1u), 0);
     for (const Input& in : c->inputs) if (in.row < G) row_bytes[in.row] += in.len;
     const uint64_t max_row = *std::max_element(row_bytes.begin(), row_bytes.end());
     const uint32_t slots = table_slots(c, (G + 63) / 64);
-    const uint64_t u_est = 3 * max_row + 1024;
-    const uint64_t per = std::max<uint64_t>(1, slots / 2);
+    const uint64_t u_est = max_row + max_row * 9 / 10 + 1024;
+    const uint64_t per = std::max<uint64_t>(1, (uint64_t)slots * 55 / 100);
     const uint32_t row_bits = std::max(1u, ceil_log2(G));
     return std::max(row_bits, std::min(15u, std::max(6u, ceil_log2((u_est + per - 1) / per))));
 }
@@ -339,7 +349,7 @@ void grmkm_destroy(grmkm_ctx* c) {
     DevBuf* all[] = {&c->in, &c->files, &c->hdr0, &c->tsum, &c->tile_file, &c->tile_state, &c->tile_pos, &c->bsum,
                      &c->bstate, &c->bpos, &c->fss, &c->codes, &c->valid, &c->hist, &c->offsets, &c->offsets2,
                      &c->bcounts, &c->records, &c->records2, &c->ukeys, &c->uwords, &c->skeys, &c->sidx_a, &c->sidx_b,
-                     &c->shist, &c->kmers, &c->matrix, &c->scalars, &c->fmt, &c->synth, &c->owner_start, &c->refs, &c->spart, &c->stile_file};
+                     &c->shist, &c->kmers, &c->matrix, &c->scalars, &c->fmt, &c->synth, &c->owner_start, &c->refs, &c->spart, &c->stile_file, &c->bbase};
     for (DevBuf* b : all) release(c, *b);
     if (c->ev_ok) for (int i = 0; i < T_N; ++i) cudaEventDestroy(c->ev[i]);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -446,10 +456,9 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
     // ---- aggregate table geometry and bucket count
     const uint32_t Wtab = P.W;
     const size_t budget = agg_smem_budget(c);
-    P.slots = (uint32_t)(budget / (8 * (1 + (size_t)Wtab)));
+    P.slots = table_slots(c, Wtab);
     if (P.slots < 256) return fail(c, GRMKM_E_UNSUPPORTED, "too many genomes for the shared-memory column table");
-    P.slots = std::min(P.slots, 16384u);
-    P.agg_smem = (size_t)P.slots * 8 * (1 + Wtab);
+    P.agg_smem = table_smem(P.slots, Wtab);
     P.bucket_bits = c->cfg.bucket_bits ? c->cfg.bucket_bits : auto_bucket_bits(c, P.G);
     P.bucket_bits = std::max(P.bucket_bits, P.row_bits);
     if (P.bucket_bits > 15) return fail(c, GRMKM_E_UNSUPPORTED, "bucket_bits > 15");
@@ -645,34 +654,27 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         // ---- aggregate (dsk2kover): retry with a larger output if the first guess was too small
         ucap = std::min<uint64_t>(P.max_stream, std::max<uint64_t>(1 << 16, P.max_stream / 4));
         ucap = std::min<uint64_t>(ucap, 0xFFFFFFFFULL);
+        ENSURE(c, c->bbase, (size_t)B * 8);
+        ENSURE(c, c->bcounts, (size_t)B * 8);
         for (int attempt = 0; attempt < 2; ++attempt) {
             ENSURE(c, c->ukeys, ucap * 8);
             ENSURE(c, c->uwords, (size_t)ucap * P.W * 8);
-            if (mode == 1) { ENSURE(c, c->bcounts, (size_t)B * 8); CU_TRY(c, cudaMemsetAsync(c->bcounts.p, 0, (size_t)B * 8, st)); }
-            AggParams ap{};
-            ap.records = agg_records; ap.begin = agg_begin; ap.end = agg_end; ap.B = B; ap.bucket_bits = P.bucket_bits;
+            AggParams2 ap{};
+            ap.records = agg_records; ap.begin = agg_begin; ap.end = agg_end; ap.bucket_bits = P.bucket_bits;
             ap.row_bits = P.row_bits; ap.n_words = P.W; ap.slots = P.slots;
-            ap.keep_singletons = c->cfg.keep_singletons; ap.mode = mode;
+            ap.keep_singletons = c->cfg.keep_singletons; ap.init_depth = 0;
             ap.out_keys = (unsigned long long*)c->ukeys.p; ap.out_words = (unsigned long long*)c->uwords.p;
             ap.cap = ucap; ap.scalars = (unsigned long long*)d_scalars;
-            ap.bucket_out_counts = (unsigned long long*)c->bcounts.p;
-            ENSURE(c, c->owner_start, (size_t)(n_ranges + 1) * 8);
-            uint64_t* d_owner = (uint64_t*)c->owner_start.p;
-            for (uint32_t r = 0; r < n_ranges; ++r) {
-                ap.b_begin = (uint32_t)((uint64_t)B * r / n_ranges);
-                ap.b_end = (uint32_t)((uint64_t)B * (r + 1) / n_ranges);
-                CU_TRY(c, cudaMemcpyAsync(d_owner + r, d_scalars + S_U_NEEDED, 8, cudaMemcpyDeviceToDevice, st));
-                const uint32_t grid = std::max(1u, std::min<uint32_t>(ap.b_end - ap.b_begin, (uint32_t)c->sm_count));
-                if (mode == 0) {
-                    CU_TRY(c, cudaFuncSetAttribute(k_aggregate_cols<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.agg_smem));
-                    k_aggregate_cols<0><<<grid, kAggThreads, P.agg_smem, st>>>(ap);
-                } else {
-                    CU_TRY(c, cudaFuncSetAttribute(k_aggregate_cols<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.agg_smem));
-                    k_aggregate_cols<1><<<grid, kAggThreads, P.agg_smem, st>>>(ap);
-                }
-                L.n++;
+            ap.bucket_base = (unsigned long long*)c->bbase.p; ap.bucket_count = (unsigned long long*)c->bcounts.p;
+            ap.b_begin = 0; ap.b_end = B;
+            if (mode == 0) {
+                CU_TRY(c, cudaFuncSetAttribute(k_aggregate_cols<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.agg_smem));
+                k_aggregate_cols<0><<<agrid, kAggThreads, P.agg_smem, st>>>(ap);
+            } else {
+                CU_TRY(c, cudaFuncSetAttribute(k_aggregate_cols<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.agg_smem));
+                k_aggregate_cols<1><<<agrid, kAggThreads, P.agg_smem, st>>>(ap);
             }
-            CU_TRY(c, cudaMemcpyAsync(d_owner + n_ranges, d_scalars + S_U_NEEDED, 8, cudaMemcpyDeviceToDevice, st));
+            L.n++;
             CU_TRY(c, cudaGetLastError());
             CU_TRY(c, cudaMemcpyAsync(sc, d_scalars, sizeof sc, cudaMemcpyDeviceToHost, st));
             CU_TRY(c, cudaStreamSynchronize(st));
@@ -690,10 +692,30 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
     if (c->ev_ok) cudaEventRecord(c->ev[T_AGG], st);
     const uint64_t U = sc[S_U_NEEDED];
 
-    // ---- final order + gather
-    if (mode == 0) {
-        int r = sort_and_gather(c, U, P.W, ucap, 2 * c->cfg.k, (c->cfg.flags & GRMKM_FLAG_HASH_ORDER) != 0, L);
+    // ---- final order.  Default: ascending hash (bucket order; every bucket chunk is already sorted), which is
+    // identical for any GPU count.  GRMKM_FLAG_KMER_ORDER: ascending canonical k-mer (one extra sort).
+    std::vector<uint64_t> h_off;
+    if (mode == 0 && (c->cfg.flags & GRMKM_FLAG_KMER_ORDER)) {
+        int r = sort_and_gather(c, U, P.W, ucap, 2 * c->cfg.k, false, L);
         if (r) return r;
+    } else {
+        ENSURE(c, c->offsets2, (size_t)(B + 1) * 8);
+        ENSURE(c, c->kmers, U * 8);
+        ENSURE(c, c->matrix, (size_t)U * P.W * 8);
+        k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->bcounts.p, (unsigned long long*)c->offsets2.p, B,
+                                             d_scalars, S_N_SOLID, 1);
+        if (U) {
+            k_gather_buckets<<<std::min<uint32_t>(B, (uint32_t)c->sm_count * 8), 256, 0, st>>>(
+                (const unsigned long long*)c->ukeys.p, (const unsigned long long*)c->uwords.p, ucap,
+                (const unsigned long long*)c->bbase.p, (const unsigned long long*)c->offsets2.p, B, P.W, U,
+                (unsigned long long*)c->kmers.p, (unsigned long long*)c->matrix.p, U);
+        }
+        L.n += 2;
+        CU_TRY(c, cudaGetLastError());
+        if (mode == 1) {
+            h_off.resize(B + 1);
+            CU_TRY(c, cudaMemcpyAsync(h_off.data(), c->offsets2.p, (size_t)(B + 1) * 8, cudaMemcpyDeviceToHost, st));
+        }
     }
     if (c->ev_ok) cudaEventRecord(c->ev[T_SORT], st);
     CU_TRY(c, cudaStreamSynchronize(st));
@@ -701,12 +723,12 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
     c->U = U;
     c->built = (mode == 0);
     if (mode == 1) {
-        std::vector<uint64_t> own(n_ranges + 1);
-        CU_TRY(c, cudaMemcpy(own.data(), c->owner_start.p, (n_ranges + 1) * 8, cudaMemcpyDeviceToHost));
+        // partial columns are in bucket order: owner r holds buckets [r*B/P, (r+1)*B/P)
         c->part_ranks = n_ranges;
         c->part_counts.resize(n_ranges);
-        for (uint32_t r = 0; r < n_ranges; ++r) c->part_counts[r] = own[r + 1] - own[r];
-        c->part_total = U; c->part_cap = ucap; c->part_words = P.W;
+        for (uint32_t r = 0; r < n_ranges; ++r)
+            c->part_counts[r] = h_off[(uint64_t)B * (r + 1) / n_ranges] - h_off[(uint64_t)B * r / n_ranges];
+        c->part_total = U; c->part_cap = U; c->part_words = P.W;
     }
     grmkm_stats& s = c->stats;
     s.n_input_bytes = P.in_bytes;
@@ -894,7 +916,7 @@ int grmkm_export_partials(grmkm_ctx* c, void* dev_dst, uint64_t dst_bytes) {
     if (!dev_dst) return fail(c, GRMKM_E_INVALID, "null dst");
     CU_TRY(c, cudaSetDevice(c->device));
     k_export_aos<<<(uint32_t)((c->part_total + 255) / 256), 256, 0, c->stream>>>(
-        (const unsigned long long*)c->ukeys.p, (const unsigned long long*)c->uwords.p, c->part_total, c->part_words,
+        (const unsigned long long*)c->kmers.p, (const unsigned long long*)c->matrix.p, c->part_total, c->part_words,
         c->part_cap, (unsigned long long*)dev_dst);
     CU_TRY(c, cudaGetLastError());
     c->stats.n_launches++;
@@ -914,10 +936,10 @@ int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
     ms.n_src = n_ranks;
     uint64_t n_total = 0, words = 0;
     uint32_t W_total = 0;
-    AggParams ap{};
+    uint32_t src_woff_h[16] = {0};
     for (uint32_t s = 0; s < n_ranks; ++s) {
         ms.ent_off[s] = n_total; ms.word_off[s] = words; ms.width[s] = 1 + src_words[s];
-        ap.src_words[s] = src_words[s]; ap.src_woff[s] = W_total;
+        src_woff_h[s] = W_total;
         n_total += src_counts[s]; words += src_counts[s] * (1 + (uint64_t)src_words[s]); W_total += src_words[s];
     }
     ms.ent_off[n_ranks] = n_total; ms.word_off[n_ranks] = words;
@@ -929,7 +951,7 @@ int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
     if (n_total == 0) { c->built = true; c->stats.n_kmers = 0; return GRMKM_OK; }
     const uint32_t slots = table_slots(c, W_total);
     if (slots < 256) return fail(c, GRMKM_E_UNSUPPORTED, "too many genomes for the shared-memory column table");
-    const size_t smem = (size_t)slots * 8 * (1 + W_total);
+    const size_t smem = table_smem(slots, W_total);
     // every rank sees 1/P of the hash space: size the buckets for n_total * P entries over the full range
     const uint64_t per = std::max<uint64_t>(1, slots / 2);
     uint32_t mb = std::min(20u, std::max(6u, ceil_log2((n_total * n_ranks + per - 1) / per)));
@@ -937,6 +959,9 @@ int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
     ENSURE(c, c->scalars, S_COUNT * 8);
     ENSURE(c, c->hist, (size_t)B * 8);
     ENSURE(c, c->offsets, (size_t)(B + 1) * 8);
+    ENSURE(c, c->offsets2, (size_t)(B + 1) * 8);
+    ENSURE(c, c->bbase, (size_t)B * 8);
+    ENSURE(c, c->bcounts, (size_t)B * 8);
     ENSURE(c, c->refs, n_total * 8);
     uint64_t ucap = std::min<uint64_t>(n_total, 0xFFFFFFFFULL);
     ENSURE(c, c->ukeys, ucap * 8);
@@ -955,14 +980,17 @@ int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
     L.n += 3;
     CU_TRY(c, cudaGetLastError());
     if (c->ev_ok) cudaEventRecord(c->ev[T_SCATTER], st);
+    AggParams2 ap{};
+    for (uint32_t s2 = 0; s2 < n_ranks; ++s2) { ap.src_words[s2] = src_words[s2]; ap.src_woff[s2] = src_woff_h[s2]; }
     ap.records = (const unsigned long long*)c->refs.p; ap.begin = (const unsigned long long*)c->offsets.p; ap.end = ap.begin + 1;
-    ap.B = B; ap.bucket_bits = mb; ap.row_bits = 0; ap.n_words = W_total; ap.slots = slots;
-    ap.keep_singletons = c->cfg.keep_singletons; ap.mode = 3;
+    ap.bucket_bits = mb; ap.row_bits = 0; ap.n_words = W_total; ap.slots = slots;
+    ap.keep_singletons = c->cfg.keep_singletons; ap.init_depth = 0;
     ap.out_keys = (unsigned long long*)c->ukeys.p; ap.out_words = (unsigned long long*)c->uwords.p;
     ap.cap = ucap; ap.scalars = (unsigned long long*)d_scalars; ap.parts = parts;
+    ap.bucket_base = (unsigned long long*)c->bbase.p; ap.bucket_count = (unsigned long long*)c->bcounts.p;
     ap.b_begin = 0; ap.b_end = B;
-    CU_TRY(c, cudaFuncSetAttribute(k_aggregate<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_aggregate<3><<<std::min<uint32_t>(B, (uint32_t)c->sm_count * 2), kAggThreads, smem, st>>>(ap);
+    CU_TRY(c, cudaFuncSetAttribute(k_aggregate_cols<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_aggregate_cols<3><<<std::min<uint32_t>(B, (uint32_t)c->sm_count), kAggThreads, smem, st>>>(ap);
     L.n++;
     CU_TRY(c, cudaGetLastError());
     uint64_t sc[S_COUNT];
@@ -970,8 +998,23 @@ int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
     CU_TRY(c, cudaStreamSynchronize(st));
     if (c->ev_ok) cudaEventRecord(c->ev[T_AGG], st);
     const uint64_t U = sc[S_U_NEEDED];
-    int r = sort_and_gather(c, U, W_total, ucap, 2 * c->cfg.k, (c->cfg.flags & GRMKM_FLAG_HASH_ORDER) != 0, L);
-    if (r) return r;
+    if (c->cfg.flags & GRMKM_FLAG_KMER_ORDER) {
+        int r = sort_and_gather(c, U, W_total, ucap, 2 * c->cfg.k, false, L);
+        if (r) return r;
+    } else {
+        ENSURE(c, c->kmers, U * 8);
+        ENSURE(c, c->matrix, (size_t)U * W_total * 8);
+        k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->bcounts.p, (unsigned long long*)c->offsets2.p, B,
+                                             d_scalars, S_N_SOLID, 1);
+        if (U) {
+            k_gather_buckets<<<std::min<uint32_t>(B, (uint32_t)c->sm_count * 8), 256, 0, st>>>(
+                (const unsigned long long*)c->ukeys.p, (const unsigned long long*)c->uwords.p, ucap,
+                (const unsigned long long*)c->bbase.p, (const unsigned long long*)c->offsets2.p, B, W_total, U,
+                (unsigned long long*)c->kmers.p, (unsigned long long*)c->matrix.p, U);
+        }
+        L.n += 2;
+        CU_TRY(c, cudaGetLastError());
+    }
     if (c->ev_ok) cudaEventRecord(c->ev[T_SORT], st);
     CU_TRY(c, cudaStreamSynchronize(st));
     c->U = U; c->built = true;

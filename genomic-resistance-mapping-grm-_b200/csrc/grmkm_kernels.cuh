@@ -865,19 +865,62 @@ k_aggregate(const AggParams p) {
     (void)warp; (void)s_red;
 }
 
-// ---- column aggregation, tight version (modes 0 = final columns, 1 = partial columns) -------------------
-// Same algorithm as k_aggregate<0/1>; differences that matter for the instruction count and for latency:
-// eight coalesced record loads in flight per thread, the key-range filter only exists on the (rare) split
-// path, presence bits live in 32-bit half-word planes w32[h][slot] (h = (row >> 5) ^ 1, so that
-// word = w32[2w+1] : w32[2w] has genome row g at bit 63 - (g & 63), kover/utils.py:144-154), and the
-// overflow flag is polled once per batch.
+// ---- column aggregation (modes 0 = final columns, 1 = partial columns, 3 = owner-side merge of partials) ----
+// One CTA per hash bucket.  The bucket's records stream through a shared-memory table
+//   keys[slots + tail] (u64), w32[2W][slots + tail] (presence half-words), kept[slots + tail] (u8)
+// with eight coalesced loads in flight per thread.  Genome row g lives in half-word plane (g >> 5) ^ 1 at bit
+// 31 - (g & 31), so that word w = w32[2w+1] : w32[2w] has row g at bit 63 - (g & 63) (kover/utils.py:144-154).
+//
+// The home slot is MONOTONE in the key (its top bits scaled to the table; the multiplicative hash already
+// spreads them uniformly) and probing never wraps (tail slots), so clusters hold disjoint ascending key ranges:
+// the table is almost sorted, and a key's exact rank is (kept slots before it) corrected by the inversions
+// inside its own cluster.  Columns therefore leave the kernel in ascending hash order per bucket with no
+// sort pass.  A bucket that does not fit is split into key sub-ranges (processed in ascending order): one
+// counting sweep to size the bucket's output, one emitting sweep.
 constexpr int kAggBatch = 8;
 
-template <bool FILTER>
-__device__ __forceinline__ void agg_stream(const unsigned long long* __restrict__ recs, uint32_t n, unsigned long long* keys,
-                                           uint32_t* w32, uint32_t slots, uint32_t row_bits, uint32_t row_mask,
-                                           uint32_t key_bits, uint32_t depth, unsigned long long ridx,
+struct AggTable {
+    unsigned long long* keys;
+    uint32_t* w32;
+    uint8_t* kept;
+    uint32_t slots;        // home slots
+    uint32_t total;        // slots + tail
+};
+
+__device__ __forceinline__ uint32_t home_slot(unsigned long long key, uint32_t shift, uint32_t slots) {
+    // top 32 bits of the key below the bits that are fixed inside the current (sub-)range; shift = 64 - key_bits + depth
+    return __umulhi((uint32_t)((key << shift) >> 32), slots);
+}
+
+struct AggParams2 {
+    const unsigned long long* records;   // MODE 0/1: (hash << row_bits) | row;  MODE 3: refs (word offset << 8) | source
+    const unsigned long long* begin;     // [B]
+    const unsigned long long* end;       // [B]
+    uint32_t bucket_bits, row_bits, n_words, slots, keep_singletons, init_depth;
+    unsigned long long* out_keys;        // [cap]   bucket chunks, at bucket_base[b]
+    unsigned long long* out_words;       // [n_words][cap]
+    unsigned long long cap;
+    unsigned long long* scalars;
+    unsigned long long* bucket_base;     // [B] where the bucket's chunk starts in out_*
+    unsigned long long* bucket_count;    // [B] columns the bucket emitted
+    uint32_t b_begin, b_end;
+    const unsigned long long* parts;     // MODE 3
+    uint32_t src_words[16];
+    uint32_t src_woff[16];
+};
+
+// Stream the bucket's records through the table.  Probing starts at the (monotone) home slot and never wraps:
+// kMaxProbe tail slots follow the home range, and a chain longer than kMaxProbe means "does not fit".
+template <int MODE, bool FILTER>
+__device__ __forceinline__ void agg_stream(const AggParams2& p, const AggTable& t, const unsigned long long* __restrict__ recs,
+                                           uint32_t n, uint32_t key_bits, uint32_t depth, unsigned long long ridx,
                                            volatile uint32_t* overflow) {
+    const uint32_t row_bits = p.row_bits;
+    const uint32_t row_mask = (1u << row_bits) - 1u;
+    const uint32_t shift = 64 - key_bits + depth;
+    const uint32_t slots = t.slots, total = t.total;
+    unsigned long long* const keys = t.keys;
+    uint32_t* const w32 = t.w32;
     for (uint32_t base = threadIdx.x; base < n; base += kAggThreads * kAggBatch) {
         unsigned long long r[kAggBatch];
 #pragma unroll
@@ -889,10 +932,17 @@ __device__ __forceinline__ void agg_stream(const unsigned long long* __restrict_
 #pragma unroll
         for (int j = 0; j < kAggBatch; ++j) {
             if (base + j * kAggThreads >= n) break;
-            const unsigned long long key = r[j] >> row_bits;
-            const uint32_t row = (uint32_t)r[j] & row_mask;
-            if (FILTER && ((key & ((1ULL << key_bits) - 1)) >> (key_bits - depth)) != ridx) continue;
-            uint32_t slot = slot_of(key, slots);
+            unsigned long long key;
+            const unsigned long long* ent = nullptr;
+            if (MODE == 3) {
+                ent = p.parts + (r[j] >> 8);
+                key = ent[0] & ((1ULL << key_bits) - 1);
+                if (FILTER && (key >> (key_bits - depth)) != ridx) continue;
+            } else {
+                key = r[j] >> row_bits;          // carries (bucket_bits - row_bits) redundant bucket bits on top
+                if (FILTER && ((key << (64 - key_bits)) >> (64 - depth)) != ridx) continue;
+            }
+            uint32_t slot = home_slot(key, shift, slots);
             int probe = 0;
             while (true) {
                 unsigned long long k0 = *(volatile unsigned long long*)&keys[slot];
@@ -901,115 +951,187 @@ __device__ __forceinline__ void agg_stream(const unsigned long long* __restrict_
                     k0 = atomicCAS(&keys[slot], kEmptyKey, key);
                     if (k0 == kEmptyKey || k0 == key) break;
                 }
-                slot = slot + 1 == slots ? 0 : slot + 1;
+                ++slot;
                 if (++probe >= kMaxProbe) { *overflow = 1; break; }
             }
-            if (probe < kMaxProbe) atomicOr(&w32[((row >> 5) ^ 1u) * slots + slot], 0x80000000u >> (row & 31u));
+            if (probe < kMaxProbe) {
+                if (MODE == 3) {
+                    const uint32_t src = (uint32_t)(r[j] & 255u), nw = p.src_words[src], wo = p.src_woff[src];
+                    for (uint32_t w = 0; w < nw; ++w) {
+                        const unsigned long long v = ent[1 + w];
+                        if ((uint32_t)v) atomicOr(&w32[(2 * (wo + w)) * total + slot], (uint32_t)v);
+                        if ((uint32_t)(v >> 32)) atomicOr(&w32[(2 * (wo + w) + 1) * total + slot], (uint32_t)(v >> 32));
+                    }
+                } else {
+                    const uint32_t row = (uint32_t)r[j] & row_mask;
+                    atomicOr(&w32[((row >> 5) ^ 1u) * total + slot], 0x80000000u >> (row & 31u));
+                }
+            }
+        }
+    }
+}
+
+// Pass A over the table: kept flags, per-thread kept counts.  Returns this thread's kept count; occ = occupied.
+template <int MODE>
+__device__ __forceinline__ uint32_t agg_mark(const AggParams2& p, const AggTable& t, uint32_t lo, uint32_t hi, uint32_t& occ) {
+    uint32_t kept = 0;
+    occ = 0;
+    for (uint32_t i = lo; i < hi; ++i) {
+        uint8_t kf = 0;
+        if (t.keys[i] != kEmptyKey) {
+            occ++;
+            if (MODE == 1 || p.keep_singletons) kf = 1;
+            else {
+                uint32_t pc = 0;
+                for (uint32_t h = 0; h < 2 * p.n_words; ++h) pc += __popc(t.w32[h * t.total + i]);
+                kf = pc >= 2;
+            }
+        }
+        t.kept[i] = kf;
+        kept += kf;
+    }
+    return kept;
+}
+
+// Pass B: exact rank of every kept slot of [lo, hi) and emission at out[base + rank]
+template <int MODE>
+__device__ __forceinline__ void agg_emit(const AggParams2& p, const AggTable& t, uint32_t lo, uint32_t hi, uint32_t before,
+                                         unsigned long long base, uint32_t b, uint32_t key_bits) {
+    const unsigned long long key_mask = (1ULL << key_bits) - 1;
+    uint32_t running = before;
+    for (uint32_t i = lo; i < hi; ++i) {
+        if (!t.kept[i]) continue;
+        const unsigned long long key = t.keys[i];
+        uint32_t rank = running++;
+        for (uint32_t j = i; j-- > 0;) {                 // inversions with earlier slots of the cluster
+            const unsigned long long kj = t.keys[j];
+            if (kj == kEmptyKey) break;
+            rank -= (t.kept[j] && kj > key);
+        }
+        for (uint32_t j = i + 1; j < t.total; ++j) {      // and with later ones
+            const unsigned long long kj = t.keys[j];
+            if (kj == kEmptyKey) break;
+            rank += (t.kept[j] && kj < key);
+        }
+        const unsigned long long o = base + rank;
+        if (o < p.cap) {
+            const unsigned long long h = ((unsigned long long)b << key_bits) | (key & key_mask);
+            p.out_keys[o] = MODE == 1 ? h : kunhash(h);
+            for (uint32_t w = 0; w < p.n_words; ++w)
+                p.out_words[w * p.cap + o] = ((unsigned long long)t.w32[(2 * w + 1) * t.total + i] << 32) | t.w32[2 * w * t.total + i];
         }
     }
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(kAggThreads, 1)
-k_aggregate_cols(const AggParams p) {
-    extern __shared__ unsigned long long s_tab[];   // keys[slots] then w32[2W][slots]
-    __shared__ uint32_t s_overflow, s_sp, s_cnt, s_kept;
+k_aggregate_cols(const AggParams2 p) {
+    extern __shared__ unsigned long long s_tab[];
+    __shared__ uint32_t s_overflow, s_sp;
     __shared__ uint32_t s_depth[72];
     __shared__ unsigned long long s_idx[72];
+    __shared__ uint32_t s_warp[33];
     __shared__ unsigned long long s_base;
-    const uint32_t slots = p.slots;
-    const uint32_t W = p.n_words;
-    unsigned long long* keys = s_tab;
-    uint32_t* w32 = reinterpret_cast<uint32_t*>(s_tab + slots);
+    AggTable t;
+    t.slots = p.slots; t.total = p.slots + kMaxProbe;
+    t.keys = s_tab;
+    t.w32 = reinterpret_cast<uint32_t*>(s_tab + t.total);
+    t.kept = reinterpret_cast<uint8_t*>(t.w32 + 2 * (size_t)p.n_words * t.total);
     const uint32_t key_bits = 64 - p.bucket_bits;
-    const uint32_t row_mask = (1u << p.row_bits) - 1u;
-    const int lane = threadIdx.x & 31;
+    const uint32_t chunk = (t.total + kAggThreads - 1) / kAggThreads;
+    const uint32_t lo = min(threadIdx.x * chunk, t.total), hi = min(lo + chunk, t.total);
 
     for (uint32_t b = p.b_begin + blockIdx.x; b < p.b_end; b += gridDim.x) {
         const unsigned long long rbeg = p.begin[b], rend = p.end[b];
-        if (rbeg >= rend) continue;
+        if (rbeg >= rend) { if (threadIdx.x == 0) { p.bucket_base[b] = 0; p.bucket_count[b] = 0; } continue; }
         const uint32_t n = (uint32_t)(rend - rbeg);
+        const unsigned long long* recs = p.records + rbeg;
+        // phase 0: the whole bucket in one table (when init_depth == 0); on overflow, or when sub-ranges are planned:
+        // phase 1 counts over the sub-ranges, phase 2 emits them in ascending order
+        uint32_t phase = p.init_depth ? 1u : 0u;
+        uint32_t bucket_total = 0, emitted = 0, bucket_occ = 0, splits = 0;
         __syncthreads();
-        if (threadIdx.x == 0) { s_sp = 1; s_depth[0] = 0; s_idx[0] = 0; }
+        if (threadIdx.x == 0) {
+            if (phase == 0) { s_sp = 1; s_depth[0] = 0; s_idx[0] = 0; }
+            else { s_sp = 0; for (uint32_t r = (1u << p.init_depth); r-- > 0;) { s_depth[s_sp] = p.init_depth; s_idx[s_sp] = r; s_sp++; } }
+        }
         while (true) {
             __syncthreads();
-            if (s_sp == 0) break;
+            if (s_sp == 0) {
+                if (phase != 1) break;
+                __syncthreads();          // everyone has seen the empty stack before it is refilled
+                // counting sweep done: reserve the bucket's chunk, then emit
+                if (threadIdx.x == 0) {
+                    s_base = atomicAdd(&p.scalars[S_U_NEEDED], (unsigned long long)bucket_total);
+                    s_sp = 0;
+                    const uint32_t d0 = p.init_depth ? p.init_depth : 1u;
+                    for (uint32_t r = (1u << d0); r-- > 0;) { s_depth[s_sp] = d0; s_idx[s_sp] = r; s_sp++; }
+                }
+                phase = 2;
+                continue;
+            }
             const uint32_t depth = s_depth[s_sp - 1];
             const unsigned long long ridx = s_idx[s_sp - 1];
             __syncthreads();
-            if (threadIdx.x == 0) { s_sp--; s_overflow = 0; s_cnt = 0; s_kept = 0; }
-            for (uint32_t i = threadIdx.x; i < slots; i += kAggThreads) keys[i] = kEmptyKey;
-            for (uint32_t i = threadIdx.x; i < slots * W; i += kAggThreads) reinterpret_cast<unsigned long long*>(w32)[i] = 0;
+            if (threadIdx.x == 0) { s_sp--; s_overflow = 0; }
+            for (uint32_t i = threadIdx.x; i < t.total; i += kAggThreads) t.keys[i] = kEmptyKey;
+            for (uint32_t i = threadIdx.x; i < t.total * p.n_words; i += kAggThreads) reinterpret_cast<unsigned long long*>(t.w32)[i] = 0;
             __syncthreads();
-            if (depth == 0) agg_stream<false>(p.records + rbeg, n, keys, w32, slots, p.row_bits, row_mask, key_bits, 0, 0, &s_overflow);
-            else agg_stream<true>(p.records + rbeg, n, keys, w32, slots, p.row_bits, row_mask, key_bits, depth, ridx, &s_overflow);
+            if (depth == 0) agg_stream<MODE, false>(p, t, recs, n, key_bits, 0, 0, &s_overflow);
+            else agg_stream<MODE, true>(p, t, recs, n, key_bits, depth, ridx, &s_overflow);
             __syncthreads();
             if (s_overflow) {
-                // split this key range in two and retry (terminates: a range of one key needs one slot)
+                // split this key range in two, lower half first (terminates: a range of one key needs one slot)
                 if (threadIdx.x == 0) {
-                    s_depth[s_sp] = depth + 1; s_idx[s_sp] = ridx * 2 + 1; s_sp++;
-                    s_depth[s_sp] = depth + 1; s_idx[s_sp] = ridx * 2; s_sp++;
-                    atomicAdd(&p.scalars[S_N_SPLITS], 1ULL);
+                    if (phase == 0) {
+                        s_depth[s_sp] = 1; s_idx[s_sp] = 1; s_sp++;
+                        s_depth[s_sp] = 1; s_idx[s_sp] = 0; s_sp++;
+                    } else {
+                        s_depth[s_sp] = depth + 1; s_idx[s_sp] = ridx * 2 + 1; s_sp++;
+                        s_depth[s_sp] = depth + 1; s_idx[s_sp] = ridx * 2; s_sp++;
+                    }
                 }
+                if (phase == 0) phase = 1;
+                if (phase == 1) splits++;
                 continue;
             }
-            // ---- count what this range emits
-            uint32_t occ = 0, kept = 0;
-            for (uint32_t i = threadIdx.x; i < slots; i += kAggThreads) {
-                if (keys[i] != kEmptyKey) {
-                    occ++;
-                    if (MODE == 1 || p.keep_singletons) kept++;
-                    else {
-                        uint32_t pc = 0;
-                        for (uint32_t h = 0; h < 2 * W; ++h) pc += __popc(w32[h * slots + i]);
-                        kept += (pc >= 2);
-                    }
-                }
+            uint32_t occ;
+            const uint32_t kept = agg_mark<MODE>(p, t, lo, hi, occ);
+            uint32_t total_kept, total_occ;
+            const uint32_t before = block_excl_scan<kAggThreads>(kept, s_warp, total_kept);
+            if (phase != 2) { block_excl_scan<kAggThreads>(occ, s_warp, total_occ); bucket_occ += total_occ; }
+            if (phase == 1) { bucket_total += total_kept; continue; }
+            if (phase == 0) {
+                bucket_total = total_kept;
+                if (threadIdx.x == 0) s_base = atomicAdd(&p.scalars[S_U_NEEDED], (unsigned long long)total_kept);
+                __syncthreads();
             }
-            occ = __reduce_add_sync(0xffffffffu, occ);
-            kept = __reduce_add_sync(0xffffffffu, kept);
-            if (lane == 0) { atomicAdd(&s_cnt, occ); atomicAdd(&s_kept, kept); }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                s_base = atomicAdd(&p.scalars[S_U_NEEDED], (unsigned long long)s_kept);
-                atomicAdd(&p.scalars[S_N_DISTINCT], (unsigned long long)s_cnt);
-                if (MODE == 1) atomicAdd(&p.bucket_out_counts[b], (unsigned long long)s_kept);
-                s_cnt = 0;
-            }
-            __syncthreads();
-            // ---- emit
-            const unsigned long long base = s_base;
-            for (uint32_t i0 = 0; i0 < slots; i0 += kAggThreads) {
-                const uint32_t i = i0 + threadIdx.x;
-                bool keep = false;
-                unsigned long long key = 0;
-                if (i < slots) {
-                    key = keys[i];
-                    if (key != kEmptyKey) {
-                        if (MODE == 1 || p.keep_singletons) keep = true;
-                        else {
-                            uint32_t pc = 0;
-                            for (uint32_t h = 0; h < 2 * W; ++h) pc += __popc(w32[h * slots + i]);
-                            keep = (pc >= 2);
-                        }
-                    }
-                }
-                const uint32_t m = __ballot_sync(0xffffffffu, keep);
-                uint32_t wbase = 0;
-                if (lane == 0 && m) wbase = atomicAdd(&s_cnt, __popc(m));
-                wbase = __shfl_sync(0xffffffffu, wbase, 0);
-                if (keep) {
-                    const unsigned long long o = base + wbase + __popc(m & lanemask_lt());
-                    if (o < p.cap) {
-                        const unsigned long long h = ((unsigned long long)b << key_bits) | (key & ((1ULL << key_bits) - 1));
-                        p.out_keys[o] = MODE == 0 ? kunhash(h) : h;
-                        for (uint32_t w = 0; w < W; ++w)
-                            p.out_words[w * p.cap + o] = ((unsigned long long)w32[(2 * w + 1) * slots + i] << 32) | w32[2 * w * slots + i];
-                    }
-                }
-            }
+            agg_emit<MODE>(p, t, lo, hi, before, s_base + emitted, b, key_bits);
+            emitted += total_kept;
+        }
+        if (threadIdx.x == 0) {
+            p.bucket_base[b] = s_base;
+            p.bucket_count[b] = bucket_total;
+            atomicAdd(&p.scalars[S_N_DISTINCT], (unsigned long long)bucket_occ);
+            if (splits) atomicAdd(&p.scalars[S_N_SPLITS], (unsigned long long)splits);
         }
     }
+}
+
+// bucket chunks (arbitrary order in tmp) -> final arrays in bucket order: one CTA per bucket
+__global__ void __launch_bounds__(256)
+k_gather_buckets(const unsigned long long* __restrict__ tmp_keys, const unsigned long long* __restrict__ tmp_words,
+                 unsigned long long tmp_cap, const unsigned long long* __restrict__ bucket_base,
+                 const unsigned long long* __restrict__ offsets, uint32_t B, uint32_t W, unsigned long long U,
+                 unsigned long long* __restrict__ keys, unsigned long long* __restrict__ words, unsigned long long out_stride) {
+    for (uint32_t b = blockIdx.x; b < B; b += gridDim.x) {
+        const unsigned long long src = bucket_base[b], dst = offsets[b], n = offsets[b + 1] - dst;
+        for (unsigned long long i = threadIdx.x; i < n; i += blockDim.x) {
+            keys[dst + i] = tmp_keys[src + i];
+            for (uint32_t w = 0; w < W; ++w) words[(unsigned long long)w * out_stride + dst + i] = tmp_words[(unsigned long long)w * tmp_cap + src + i];
+        }
+    }
+    (void)U;
 }
 
 // ------------------------------------------------------------------------------------------

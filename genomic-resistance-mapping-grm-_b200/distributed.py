@@ -103,7 +103,7 @@ class DistributedBuilder:
 
     Rows are LOCAL indices into ``local_rows`` (the global genome rows this rank holds).
     After build(), kmers()/matrix() return this rank's slice of the columns (all word rows);
-    gather() assembles the global matrix in ascending k-mer order on rank 0.
+    gather() assembles the global matrix (ascending hash order, as a one-GPU build) on rank 0.
     """
 
     def __init__(self, k=31, min_abundance=1, keep_singletons=False, n_genomes=0, rank=0, world=1,
@@ -204,7 +204,7 @@ class DistributedBuilder:
         return self.engine.result()[1] if self.world > 1 else self.builder.matrix()
 
     def gather(self):
-        """Global (kmers ascending, matrix [W][U]) on rank 0, None elsewhere.  Host-side P-way merge."""
+        """Global (kmers, matrix [W][U]) in ascending hash order on rank 0, None elsewhere."""
         km, mat = self.kmers(), self.matrix()
         if self.world == 1:
             return km, mat
@@ -213,10 +213,11 @@ class DistributedBuilder:
         dist.gather_object((km, mat), objs, dst=0)
         if self.rank != 0:
             return None
+        # rank r owns the r-th contiguous range of the hash space and its slice is in ascending hash order, so
+        # the concatenation in rank order IS the global column order -- the same bytes as a one-GPU build
         allk = np.concatenate([o[0] for o in objs])
         allm = np.concatenate([o[1] for o in objs], axis=1)
-        order = np.argsort(allk, kind="stable")
-        return allk[order], np.ascontiguousarray(allm[:, order])
+        return allk, np.ascontiguousarray(allm)
 
     def close(self):
         if self.builder is not None:

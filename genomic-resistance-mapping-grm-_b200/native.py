@@ -11,7 +11,7 @@ ABI_VERSION = 3
 OK = 0
 E_INVALID, E_UNSUPPORTED_K, E_NOMEM, E_CUDA, E_IO, E_CAPACITY, E_NO_DEVICE, E_UNSUPPORTED = -1, -2, -3, -4, -5, -6, -7, -8
 FASTA, FASTQ = 0, 1
-FLAG_HASH_ORDER = 1
+FLAG_KMER_ORDER = 1
 FLAG_SIMPLE_SCATTER = 2
 FLAG_RADIX_ORDER = 4
 FLAG_EXACT_OFFSETS = 8

@@ -47,7 +47,7 @@ enum {
 enum { GRMKM_FASTA = 0, GRMKM_FASTQ = 1 };
 
 /* cfg.flags */
-#define GRMKM_FLAG_HASH_ORDER 1u /* keep columns in internal hash order (skip the final sort) */
+#define GRMKM_FLAG_KMER_ORDER 1u /* columns ascending by canonical k-mer (one extra sort); default: ascending hash order */
 #define GRMKM_FLAG_RADIX_ORDER 4u /* order the columns with the LSD radix sort only (A/B timing, fallback test) */
 #define GRMKM_FLAG_SIMPLE_SCATTER 2u /* per-record global-atomic scatter instead of the staged one (A/B timing) */
 #define GRMKM_FLAG_EXACT_OFFSETS 8u /* count pass + exact bucket offsets instead of over-provisioned regions (fallback test) */
@@ -131,7 +131,10 @@ int grmkm_dims(const grmkm_ctx* ctx, uint64_t* n_kmers, uint32_t* n_words, uint3
 int grmkm_get_stats(const grmkm_ctx* ctx, grmkm_stats* out);
 int grmkm_stage_times(const grmkm_ctx* ctx, grmkm_times* out);
 
-/* canonical k-mers as integers (A0 C1 T2 G3, first base most significant), ascending; cap in elements */
+/* canonical k-mers as integers (A0 C1 T2 G3, first base most significant); cap in elements.
+ * Column order: ascending grmkm_hash64(k-mer) = k-mer * 0x9E3779B97F4A7C15 mod 2^64 (the order the hash
+ * partitions come out in, identical for any GPU count; the reference's own column order is the unspecified
+ * partition order of DSK), or ascending k-mer with GRMKM_FLAG_KMER_ORDER. */
 int grmkm_copy_kmers_packed(grmkm_ctx* ctx, uint64_t* dst, uint64_t cap);
 /* kmer_sequences: U x k bytes, upper-case, no terminator (create.py:216-220, ds.py:84); cap in bytes */
 int grmkm_copy_kmer_strings(grmkm_ctx* ctx, char* dst, uint64_t cap);

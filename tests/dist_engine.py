@@ -7,18 +7,16 @@ from oracle import oracle
 M64 = (1 << 64) - 1
 
 
+MUL = 0x9E3779B97F4A7C15            # the product's multiplicative hash (grmkm_device.cuh: khash / kunhash)
+INV = pow(MUL, -1, 1 << 64)
+
+
 def fmix64(h):
-    h ^= h >> 33; h = (h * 0xff51afd7ed558ccd) & M64
-    h ^= h >> 33; h = (h * 0xc4ceb9fe1a85ec53) & M64
-    h ^= h >> 33
-    return h
+    return (h * MUL) & M64
 
 
 def unfmix64(h):
-    h ^= h >> 33; h = (h * 0x9cb4b2f8129337db) & M64
-    h ^= h >> 33; h = (h * 0x4f74430c22a54005) & M64
-    h ^= h >> 33
-    return h
+    return (h * INV) & M64
 
 
 class OracleEngine:
@@ -78,8 +76,8 @@ class OracleEngine:
                     w[woff + j] |= rec[1 + j]
             pos += src_counts[s] * width
             woff += src_words[s]
-        keep = [(unfmix64(h), w) for h, w in cols.items() if self.keep or sum(bin(x).count("1") for x in w) >= 2]
-        keep.sort()
+        keep = sorted((h, w) for h, w in cols.items() if self.keep or sum(bin(x).count("1") for x in w) >= 2)
+        keep = [(unfmix64(h), w) for h, w in keep]           # ascending hash order, k-mers out
         self._k = np.array([k for k, _ in keep], dtype=np.uint64)
         self._m = np.array([w for _, w in keep], dtype=np.uint64).reshape(len(keep), W).T.copy()
 

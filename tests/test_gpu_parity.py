@@ -20,7 +20,9 @@ def gpu_build(genomes, k, min_abundance=1, keep_singletons=False, kind=0, **kw):
 
 
 def check(genomes, k, min_abundance=1, keep_singletons=False, kind=0, **kw):
-    ref = oracle.build([[(f, kind) for f in files] for files in genomes], k, min_abundance, keep_singletons)
+    from grm_b200 import native
+    order = "kmer" if kw.get("flags", 0) & native.FLAG_KMER_ORDER else "hash"
+    ref = oracle.build([[(f, kind) for f in files] for files in genomes], k, min_abundance, keep_singletons, order=order)
     kmers, mat, stats = gpu_build(genomes, k, min_abundance, keep_singletons, kind, **kw)
     assert stats["n_bases"] == ref.n_bases, (stats, ref.n_bases)
     assert stats["n_windows"] == ref.n_windows, (stats, ref.n_windows)
@@ -34,7 +36,11 @@ def check(genomes, k, min_abundance=1, keep_singletons=False, kind=0, **kw):
 def test_known_answer_k4(gpu):
     fa = b">r1\nGATTACAGGTNACCTGTAATC\n"
     kmers, mat, stats = gpu_build([[fa]], 5, keep_singletons=True)
-    assert [hex(int(x)) for x in kmers] == ["0x4f", "0x5b", "0xa1", "0x1b8", "0x209", "0x284"]
+    want = np.array([0x4F, 0x5B, 0xA1, 0x1B8, 0x209, 0x284], dtype=np.uint64)
+    assert np.array_equal(kmers, want[oracle.column_order(want)])          # default column order: ascending hash
+    from grm_b200 import native
+    kmers2, _, _ = gpu_build([[fa]], 5, keep_singletons=True, flags=native.FLAG_KMER_ORDER)
+    assert np.array_equal(kmers2, want)
     assert stats["n_windows"] == 12 and stats["n_bases"] == 21 and stats["n_records"] == 1
     assert (mat == np.uint64(1) << np.uint64(63)).all()
 
@@ -228,13 +234,12 @@ def test_partial_merge_emulated_ranks(gpu, world, G, keep):
         recv = torch.cat(chunks) if chunks else torch.empty(0, dtype=torch.int64, device="cuda")
         engines[dst].merge(recv, world, dst, src_counts, sw, G)
         k_, m_ = engines[dst].result()
-        assert np.all(k_[1:] > k_[:-1])
         slices_k.append(k_); slices_m.append(m_)
+    # owner slices concatenated in rank order = the one-GPU column order (ascending hash), byte for byte
     allk = np.concatenate(slices_k); allm = np.concatenate(slices_m, axis=1)
-    order = np.argsort(allk, kind="stable")
     ref = oracle.build([[(g, 0)] for g in genomes], 19, 1, keep)
-    assert np.array_equal(allk[order], ref.kmers)
-    assert np.array_equal(allm[:, order], ref.matrix)
+    assert np.array_equal(allk, ref.kmers)
+    assert np.array_equal(allm, ref.matrix)
     for e in engines:
         e.b.close()
 
@@ -245,6 +250,8 @@ def test_radix_order_fallback_and_simple_scatter(gpu):
     rng = np.random.default_rng(21)
     shared = [inputs.rand_seq(rng, 50_000)]
     genomes = [[inputs.fasta(rng, n_records=3, min_len=20_000, max_len=40_000, shared=shared)] for _ in range(4)]
-    for flags in (native.FLAG_RADIX_ORDER, native.FLAG_SIMPLE_SCATTER, native.FLAG_RADIX_ORDER | native.FLAG_SIMPLE_SCATTER):
+    K = native.FLAG_KMER_ORDER
+    for flags in (K, K | native.FLAG_RADIX_ORDER, native.FLAG_SIMPLE_SCATTER, native.FLAG_EXACT_OFFSETS,
+                  K | native.FLAG_RADIX_ORDER | native.FLAG_SIMPLE_SCATTER):
         check(genomes, 31, keep_singletons=True, flags=flags)
         check(genomes, 32, keep_singletons=False, flags=flags)
