@@ -509,22 +509,34 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
 
     // ---- parse
     k_first_header<<<(P.F * 32 + 255) / 256, 256, 0, st>>>(d_files, P.F, (uint64_t*)c->hdr0.p);
-    k_tile_summary<<<(uint32_t)P.n_tiles, kParseThreads, 0, st>>>(d_files, P.F, (const uint64_t*)c->hdr0.p, P.n_tiles,
-                                                                  (Sum*)c->tsum.p, (uint32_t*)c->tile_file.p);
-    k_scan_reduce<<<(uint32_t)P.n_sblk, kParseThreads, 0, st>>>((const Sum*)c->tsum.p, P.n_tiles, (Sum*)c->bsum.p);
+    k_tile_files<<<(uint32_t)((P.n_tiles + 255) / 256), 256, 0, st>>>(d_files, P.F, P.n_tiles, (uint32_t*)c->tile_file.p);
+    if (c->cfg.input_kind == GRMKM_FASTA)
+        k_tile_summary<0><<<(uint32_t)P.n_tiles, kParseThreads, 0, st>>>(d_files, (const uint64_t*)c->hdr0.p, P.n_tiles,
+                                                                         (const uint32_t*)c->tile_file.p, (Sum*)c->tsum.p);
+    else
+        k_tile_summary<1><<<(uint32_t)P.n_tiles, kParseThreads, 0, st>>>(d_files, (const uint64_t*)c->hdr0.p, P.n_tiles,
+                                                                         (const uint32_t*)c->tile_file.p, (Sum*)c->tsum.p);
+    k_scan_reduce<<<(uint32_t)P.n_sblk, kScanThreads, 0, st>>>((const Sum*)c->tsum.p, P.n_tiles, (Sum*)c->bsum.p);
     k_scan_blocks<<<1, 1024, 0, st>>>((const Sum*)c->bsum.p, (uint32_t)P.n_sblk, (uint32_t*)c->bstate.p,
                                       (uint64_t*)c->bpos.p, d_scalars, (uint64_t*)c->fss.p, P.F);
-    k_scan_apply<<<(uint32_t)P.n_sblk, kParseThreads, 0, st>>>((const Sum*)c->tsum.p, P.n_tiles,
-                                                               (const uint32_t*)c->bstate.p, (const uint64_t*)c->bpos.p,
-                                                               (const uint32_t*)c->tile_file.p, d_files,
-                                                               (uint8_t*)c->tile_state.p, (uint64_t*)c->tile_pos.p,
-                                                               (uint64_t*)c->fss.p);
-    L.n += 5;
+    k_scan_apply<<<(uint32_t)P.n_sblk, kScanThreads, 0, st>>>((const Sum*)c->tsum.p, P.n_tiles,
+                                                              (const uint32_t*)c->bstate.p, (const uint64_t*)c->bpos.p,
+                                                              (const uint32_t*)c->tile_file.p, d_files,
+                                                              (uint8_t*)c->tile_state.p, (uint64_t*)c->tile_pos.p,
+                                                              (uint64_t*)c->fss.p);
+    L.n += 6;
     CU_TRY(c, cudaGetLastError());
     if (c->ev_ok) cudaEventRecord(c->ev[T_PARSE], st);
-    k_pack<<<(uint32_t)P.n_tiles, kParseThreads, 0, st>>>(d_files, P.F, (const uint64_t*)c->hdr0.p, P.n_tiles,
-                                                          (const uint8_t*)c->tile_state.p, (const uint64_t*)c->tile_pos.p,
-                                                          (unsigned long long*)c->codes.p, (uint32_t*)c->valid.p, d_scalars);
+    if (c->cfg.input_kind == GRMKM_FASTA)
+        k_pack<0><<<(uint32_t)P.n_tiles, kParseThreads, 0, st>>>(d_files, (const uint64_t*)c->hdr0.p, P.n_tiles,
+                                                                 (const uint32_t*)c->tile_file.p, (const uint8_t*)c->tile_state.p,
+                                                                 (const uint64_t*)c->tile_pos.p, (unsigned long long*)c->codes.p,
+                                                                 (uint32_t*)c->valid.p, d_scalars);
+    else
+        k_pack<1><<<(uint32_t)P.n_tiles, kParseThreads, 0, st>>>(d_files, (const uint64_t*)c->hdr0.p, P.n_tiles,
+                                                                 (const uint32_t*)c->tile_file.p, (const uint8_t*)c->tile_state.p,
+                                                                 (const uint64_t*)c->tile_pos.p, (unsigned long long*)c->codes.p,
+                                                                 (uint32_t*)c->valid.p, d_scalars);
     L.n++;
     CU_TRY(c, cudaGetLastError());
     if (c->ev_ok) cudaEventRecord(c->ev[T_PACK], st);

@@ -7,10 +7,12 @@
 
 namespace grmkm {
 
-constexpr int kTileBytes = 4096;      // input bytes per parse tile (256 threads x 16 B)
-constexpr int kParseThreads = 256;
+constexpr int kParseThreads = 128;
+constexpr int kChunksPerThread = 4;    // 16-byte chunks per thread: 64 contiguous bytes
+constexpr int kTileBytes = kParseThreads * kChunksPerThread * 16;   // 8192 input bytes per parse tile
+constexpr int kScanThreads = 256;      // block size of the tile-summary scan kernels
 constexpr int kScanTilesPerThread = 4;
-constexpr int kScanTilesPerBlock = kParseThreads * kScanTilesPerThread;  // 1024
+constexpr int kScanTilesPerBlock = kScanThreads * kScanTilesPerThread;  // 1024
 constexpr int kExtractThreads = 256;
 constexpr int kAggThreads = 1024;
 constexpr int kMaxProbe = 96;
@@ -288,6 +290,134 @@ __device__ __forceinline__ FaChunk fa_chunk(const Chunk16& ch, uint32_t prev, ui
     r.sum = rn | (hn << 14) | (t << 28);
     return r;
 }
+
+// ---- SWAR fast path for FASTA text --------------------------------------------------------------
+// A 16-byte chunk whose only bytes below 0x40 are '\n' (no '>', '\r', digits, blanks ...) is classified four
+// bytes at a time: newline mask, ACGT validity mask and 2-bit codes come out of a handful of word operations
+// instead of a 16-iteration byte loop.  Everything else (header lines, CR-LF text, the first / last bytes of a
+// file) goes through fa_chunk().
+__device__ __forceinline__ uint32_t swar_zero_bytes(uint32_t v) {      // 0x80 in every byte of v that is zero (exact)
+    return ~(((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t swar_movemask(uint32_t m) {         // bits 7, 15, 23, 31 -> bits 0..3
+    return (m * 0x00204081u) >> 28;
+}
+
+struct FaBits { uint32_t nl, low, valid, codes; };   // 16-bit position masks; codes: position j at bits 2j
+
+template <bool CODES>
+__device__ __forceinline__ FaBits fa_classify(const Chunk16& ch) {
+    FaBits r; r.nl = r.low = r.valid = r.codes = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const uint32_t x = ch.w[w];
+        r.nl |= swar_movemask(swar_zero_bytes(x ^ 0x0A0A0A0Au)) << (4 * w);
+        r.low |= swar_movemask(swar_zero_bytes(x & 0xC0C0C0C0u)) << (4 * w);
+        if (CODES) {
+            const uint32_t c = (x >> 1) & 0x03030303u;                      // A0 C1 T2 G3
+            r.codes |= ((c * 0x01041040u) >> 24) << (8 * w);
+            const uint32_t t = c | (c >> 4);                                // nibble pairs c0|c1<<4 in byte 0, c2|c3<<4 in byte 2
+            const uint32_t sel = __byte_perm(t, 0u, 0x4420);                // selector nibbles c0, c1, c2, c3
+            const uint32_t expect = __byte_perm(0x47544341u, 0u, sel);      // 'A' 'C' 'T' 'G' by code
+            r.valid |= swar_movemask(swar_zero_bytes((x & 0xDFDFDFDFu) ^ expect)) << (4 * w);
+        }
+    }
+    return r;
+}
+
+__device__ __forceinline__ bool fa_fast_ok(uint64_t pos0, uint64_t len, uint64_t hdr0) {
+    return pos0 > hdr0 && pos0 + 16 <= len;          // every byte live, no forced line start inside
+}
+
+// Entries of one chunk, kept apart for the bytes before its first line start (head: emitted only when the chunk
+// starts inside a sequence line) and after it (rest).  Compacted: entry j at bits 2j / j.
+struct FaParts {
+    uint32_t hc, rc;        // head / rest codes
+    uint32_t hv_rv;         // head validity (low 16) | rest validity << 16
+    uint32_t meta;          // hn | rn << 8 | t << 16 | nrec << 20   (t: type of the last line start, 0 none 1 header 2 seq)
+    __device__ __forceinline__ uint32_t hn() const { return meta & 0xFFu; }
+    __device__ __forceinline__ uint32_t rn() const { return (meta >> 8) & 0xFFu; }
+    __device__ __forceinline__ uint32_t t() const { return (meta >> 16) & 0xFu; }
+    __device__ __forceinline__ uint32_t nrec() const { return meta >> 20; }
+    __device__ __forceinline__ uint32_t sum() const { return rn() | (hn() << 14) | (t() << 28); }
+};
+
+// the byte-loop versions stay out of line: they are rare, and inlining four copies of them costs ~200 registers
+__device__ __noinline__ uint32_t fa_chunk_sum_slow(const Chunk16& ch, uint32_t prev, uint64_t pos0, uint64_t len, uint64_t hdr0) {
+    return fa_chunk<false>(ch, prev, pos0, len, hdr0).sum;
+}
+__device__ __noinline__ FaParts fa_chunk_parts_slow(const Chunk16& ch, uint32_t prev, uint64_t pos0, uint64_t len, uint64_t hdr0) {
+    const FaChunk fc = fa_chunk<true>(ch, prev, pos0, len, hdr0);
+    FaParts r;
+    r.hc = fc.head_c; r.rc = fc.rest_c; r.hv_rv = fc.head_v | (fc.rest_v << 16);
+    r.meta = ((fc.sum >> 14) & 0x3FFFu) | ((fc.sum & 0x3FFFu) << 8) | ((fc.sum >> 28) << 16) | (fc.nrec << 20);
+    return r;
+}
+
+// compact summary only (pass 1)
+__device__ __forceinline__ uint32_t fa_chunk_sum(const Chunk16& ch, uint32_t prev, uint64_t pos0, uint64_t len, uint64_t hdr0) {
+    if (fa_fast_ok(pos0, len, hdr0)) {
+        const FaBits b = fa_classify<false>(ch);
+        if (b.low == b.nl) {
+            const uint32_t ls = ((b.nl << 1) | (prev == '\n')) & 0xFFFFu;
+            if (ls == 0) return (16u - (b.nl >> 15)) << 14;
+            const uint32_t q = __ffs(ls) - 1;
+            const uint32_t hn = q ? q - 1 : 0u;
+            const uint32_t rn = (16u - q) - __popc(b.nl >> q);
+            return rn | (hn << 14) | (2u << 28);
+        }
+    }
+    return fa_chunk_sum_slow(ch, prev, pos0, len, hdr0);
+}
+
+// full entries (pass 2)
+__device__ __forceinline__ FaParts fa_chunk_parts(const Chunk16& ch, uint32_t prev, uint64_t pos0, uint64_t len, uint64_t hdr0) {
+    FaParts r;
+    if (fa_fast_ok(pos0, len, hdr0)) {
+        const FaBits b = fa_classify<true>(ch);
+        if (b.low == b.nl) {
+            const uint32_t ls = ((b.nl << 1) | (prev == '\n')) & 0xFFFFu;
+            if (ls == 0) {
+                const uint32_t hn = 16u - (b.nl >> 15);            // a newline can only sit at position 15
+                r.hc = hn == 16 ? b.codes : (b.codes & 0x3FFFFFFFu);
+                r.rc = 0; r.hv_rv = b.valid & 0xFFFFu; r.meta = hn;
+                return r;
+            }
+            const uint32_t q = __ffs(ls) - 1;
+            const uint32_t hn = q ? q - 1 : 0u;                    // the byte before the line start is its newline
+            r.hc = b.codes & ((1u << (2 * hn)) - 1u);
+            const uint32_t hv = b.valid & ((1u << hn) - 1u);
+            uint32_t rc = b.codes >> (2 * q), rv = b.valid >> q, rnl = b.nl >> q, rn = 16u - q;
+            while (rnl) {                                          // further newlines: lines shorter than the chunk
+                const uint32_t pz = 31u - __clz(rnl);
+                const uint32_t lo_c = (1u << (2 * pz)) - 1u, lo_v = (1u << pz) - 1u;
+                rc = (rc & lo_c) | ((rc >> 2) & ~lo_c);
+                rv = (rv & lo_v) | ((rv >> 1) & ~lo_v);
+                rnl ^= 1u << pz;
+                --rn;
+            }
+            r.rc = rc; r.hv_rv = hv | (rv << 16); r.meta = hn | (rn << 8) | (2u << 16);
+            return r;
+        }
+    }
+    return fa_chunk_parts_slow(ch, prev, pos0, len, hdr0);
+}
+
+// per-thread accumulator of up to 64 packed entries
+struct Acc64 {
+    unsigned long long clo, chi, v;
+    uint32_t n;
+    __device__ __forceinline__ void init() { clo = chi = v = 0; n = 0; }
+    // codes: 2*cnt significant bits, vbits: cnt significant bits, upper bits zero
+    __device__ __forceinline__ void append(uint32_t codes, uint32_t vbits, uint32_t cnt) {
+        if (cnt == 0) return;
+        const uint32_t s = 2 * n;
+        if (s < 64) { clo |= (unsigned long long)codes << s; if (s > 32) chi |= (unsigned long long)codes >> (64 - s); }
+        else chi |= (unsigned long long)codes << (s - 64);
+        v |= (unsigned long long)vbits << n;
+        n += cnt;
+    }
+};
 
 // exclusive scan of one u32 per thread over a 1024-thread block; s_warp must hold 33 words
 __device__ __forceinline__ uint32_t block_excl_scan_1024(uint32_t v, uint32_t* s_warp, uint32_t& total) {

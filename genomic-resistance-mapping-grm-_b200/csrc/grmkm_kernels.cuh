@@ -52,64 +52,95 @@ __device__ __forceinline__ uint32_t find_file(const FileDesc* __restrict__ files
 struct TileCtx {
     FileDesc fd;
     uint64_t hdr0;
-    uint64_t off;   // byte offset of this thread's chunk in the file
+    uint64_t off;   // byte offset of this thread's first chunk in the file (64 contiguous bytes per thread)
     uint32_t f;
     bool first_tile;
 };
 
-__device__ __forceinline__ TileCtx tile_context(const FileDesc* __restrict__ files, uint32_t n_files,
-                                                const uint64_t* __restrict__ hdr0, uint64_t tile, uint32_t* s_f) {
-    if (threadIdx.x == 0) *s_f = find_file(files, n_files, tile);
-    __syncthreads();
+__device__ __forceinline__ TileCtx tile_context(const FileDesc* __restrict__ files, const uint64_t* __restrict__ hdr0,
+                                                uint64_t tile, uint32_t f) {
     TileCtx t;
-    t.f = *s_f;
-    t.fd = files[t.f];
-    t.hdr0 = hdr0[t.f];
+    t.f = f;
+    t.fd = files[f];
+    t.hdr0 = hdr0[f];
     t.first_tile = (tile == t.fd.tile_begin);
-    t.off = (tile - t.fd.tile_begin) * (uint64_t)kTileBytes + (uint64_t)threadIdx.x * 16;
+    t.off = (tile - t.fd.tile_begin) * (uint64_t)kTileBytes + (uint64_t)threadIdx.x * (16 * kChunksPerThread);
     return t;
 }
 
-__device__ __forceinline__ uint32_t prev_byte(const TileCtx& t, const Chunk16& ch) {
-    // last byte of the previous thread's chunk; lane 0 reads it from memory
-    uint32_t last = ch.byte(15);
-    uint32_t p = __shfl_up_sync(0xffffffffu, last, 1);
+// the thread's four chunks and the byte before each of them
+struct ThreadText {
+    Chunk16 ch[kChunksPerThread];
+    uint32_t prev[kChunksPerThread];
+};
+__device__ __forceinline__ ThreadText load_thread_text(const TileCtx& t) {
+    ThreadText x;
+#pragma unroll
+    for (int c = 0; c < kChunksPerThread; ++c) x.ch[c] = load_chunk(t.fd.ptr, t.off + 16 * c, t.fd.len);
+    uint32_t p = __shfl_up_sync(0xffffffffu, x.ch[kChunksPerThread - 1].byte(15), 1);
     if ((threadIdx.x & 31) == 0) p = (t.off > 0 && t.off - 1 < t.fd.len) ? t.fd.ptr[t.off - 1] : (uint32_t)'\n';
-    return p;
+    x.prev[0] = p;
+#pragma unroll
+    for (int c = 1; c < kChunksPerThread; ++c) x.prev[c] = x.ch[c - 1].byte(15);
+    return x;
 }
 
-// per-tile transducer summary
+// file of every parse tile (one thread per tile), so that no block has to binary-search on its own
+__global__ void k_tile_files(const FileDesc* __restrict__ files, uint32_t n_files, uint64_t n_tiles,
+                             uint32_t* __restrict__ tile_file) {
+    const uint64_t tile = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile < n_tiles) tile_file[tile] = find_file(files, n_files, tile);
+}
+
+// ordered fold of the compact FASTA summaries of a block (result valid in thread 0)
+__device__ __forceinline__ uint32_t block_fold_fa(uint32_t v, uint32_t* s_w) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_down_sync(0xffffffffu, v, d);
+        if (lane + d < 32) v = fa_combine(v, o);      // lane i: fold of lanes [i, i + 2d)
+    }
+    if (lane == 0) s_w[warp] = v;
+    __syncthreads();
+    uint32_t tot = 0;
+    if (threadIdx.x == 0) for (int w = 0; w < kParseThreads / 32; ++w) tot = fa_combine(tot, s_w[w]);
+    return tot;
+}
+
+// per-tile transducer summary (KIND: all inputs of a context share cfg.input_kind)
+template <int KIND>
 __global__ void __launch_bounds__(kParseThreads)
-k_tile_summary(const FileDesc* __restrict__ files, uint32_t n_files, const uint64_t* __restrict__ hdr0,
-               uint64_t n_tiles, Sum* __restrict__ tsum, uint32_t* __restrict__ tile_file) {
+k_tile_summary(const FileDesc* __restrict__ files, const uint64_t* __restrict__ hdr0, uint64_t n_tiles,
+               const uint32_t* __restrict__ tile_file, Sum* __restrict__ tsum) {
     __shared__ Sum s_w[kParseThreads / 32];
-    __shared__ uint32_t s_f;
     const uint64_t tile = blockIdx.x;
     if (tile >= n_tiles) return;
-    const TileCtx t = tile_context(files, n_files, hdr0, tile, &s_f);
-    const Chunk16 ch = load_chunk(t.fd.ptr, t.off, t.fd.len);
-    const uint32_t prev = prev_byte(t, ch);
+    const TileCtx t = tile_context(files, hdr0, tile, tile_file[tile]);
+    const ThreadText x = load_thread_text(t);
     Sum total;
-    if (t.fd.kind == 0) {
-        const FaChunk fc = fa_chunk<false>(ch, prev, t.off, t.fd.len, t.hdr0);
-        uint32_t ex, tot;
-        block_scan_fa(fc.sum, ex, tot, reinterpret_cast<uint32_t*>(s_w));
-        total = fa_to_sum(tot);
+    if (KIND == 0) {
+        uint32_t mine = 0;
+#pragma unroll
+        for (int c = 0; c < kChunksPerThread; ++c)
+            mine = fa_combine(mine, fa_chunk_sum(x.ch[c], x.prev[c], t.off + 16 * c, t.fd.len, t.hdr0));
+        total = fa_to_sum(block_fold_fa(mine, reinterpret_cast<uint32_t*>(s_w)));
     } else {
-        Sum excl;
-        block_scan_sum(chunk_summary<1>(ch, prev, t.off, t.fd.len, t.hdr0), excl, total, s_w);
+        Sum mine = sum_identity(), excl;
+#pragma unroll
+        for (int c = 0; c < kChunksPerThread; ++c)
+            mine = sum_combine(mine, chunk_summary<1>(x.ch[c], x.prev[c], t.off + 16 * c, t.fd.len, t.hdr0));
+        block_scan_sum(mine, excl, total, s_w);
     }
     if (threadIdx.x == 0) {
         if (t.first_tile) total = sum_fix_start(total, 0);
         tsum[tile] = total;
-        tile_file[tile] = t.f;
     }
 }
 
 // fold of kScanTilesPerBlock consecutive tile summaries
-__global__ void __launch_bounds__(kParseThreads)
+__global__ void __launch_bounds__(kScanThreads)
 k_scan_reduce(const Sum* __restrict__ tsum, uint64_t n_tiles, Sum* __restrict__ bsum) {
-    __shared__ Sum s_w[kParseThreads / 32];
+    __shared__ Sum s_w[kScanThreads / 32];
     const uint64_t base = (uint64_t)blockIdx.x * kScanTilesPerBlock + (uint64_t)threadIdx.x * kScanTilesPerThread;
     Sum mine = sum_identity();
 #pragma unroll
@@ -147,12 +178,12 @@ __global__ void k_scan_blocks(const Sum* __restrict__ bsum, uint32_t n_blocks, u
 }
 
 // per-tile incoming state and stream position
-__global__ void __launch_bounds__(kParseThreads)
+__global__ void __launch_bounds__(kScanThreads)
 k_scan_apply(const Sum* __restrict__ tsum, uint64_t n_tiles, const uint32_t* __restrict__ bstate,
              const uint64_t* __restrict__ bpos, const uint32_t* __restrict__ tile_file,
              const FileDesc* __restrict__ files, uint8_t* __restrict__ tile_state, uint64_t* __restrict__ tile_pos,
              uint64_t* __restrict__ file_stream_start) {
-    __shared__ Sum s_w[kParseThreads / 32];
+    __shared__ Sum s_w[kScanThreads / 32];
     const uint64_t base = (uint64_t)blockIdx.x * kScanTilesPerBlock + (uint64_t)threadIdx.x * kScanTilesPerThread;
     Sum t[kScanTilesPerThread];
     Sum mine = sum_identity();
@@ -180,73 +211,102 @@ k_scan_apply(const Sum* __restrict__ tsum, uint64_t n_tiles, const uint32_t* __r
 }
 
 // text tile -> packed stream: codes64[g] holds entries 32g..32g+31 (entry j at bits 2j), valid32[g] bit j.
+// Every thread turns its 64 bytes into at most 64 entries (register accumulator), the block scan of the
+// thread summaries gives each thread its entry offset, and the tile is assembled in shared memory.
+template <int KIND>
 __global__ void __launch_bounds__(kParseThreads)
-k_pack(const FileDesc* __restrict__ files, uint32_t n_files, const uint64_t* __restrict__ hdr0, uint64_t n_tiles,
-       const uint8_t* __restrict__ tile_state, const uint64_t* __restrict__ tile_pos,
+k_pack(const FileDesc* __restrict__ files, const uint64_t* __restrict__ hdr0, uint64_t n_tiles,
+       const uint32_t* __restrict__ tile_file, const uint8_t* __restrict__ tile_state, const uint64_t* __restrict__ tile_pos,
        unsigned long long* __restrict__ codes, uint32_t* __restrict__ valid, uint64_t* __restrict__ scalars) {
     constexpr int kGroups = kTileBytes / 32 + 2;
     __shared__ Sum s_w[kParseThreads / 32];
-    __shared__ uint32_t s_f;
-    __shared__ uint32_t s_codes[kGroups * 2];
-    __shared__ uint32_t s_valid[kGroups];
+    __shared__ uint32_t s_codes[kGroups * 2 + 4];
+    __shared__ uint32_t s_valid[kGroups + 2];
     __shared__ uint32_t s_nrec;
     const uint64_t tile = blockIdx.x;
     if (tile >= n_tiles) return;
-    for (int i = threadIdx.x; i < kGroups * 2; i += blockDim.x) s_codes[i] = 0;
-    for (int i = threadIdx.x; i < kGroups; i += blockDim.x) s_valid[i] = 0;
+    for (int i = threadIdx.x; i < kGroups * 2 + 4; i += blockDim.x) s_codes[i] = 0;
+    for (int i = threadIdx.x; i < kGroups + 2; i += blockDim.x) s_valid[i] = 0;
     if (threadIdx.x == 0) s_nrec = 0;
-    const TileCtx t = tile_context(files, n_files, hdr0, tile, &s_f);
-    const Chunk16 ch = load_chunk(t.fd.ptr, t.off, t.fd.len);
-    uint32_t prev = prev_byte(t, ch);
+    const TileCtx t = tile_context(files, hdr0, tile, tile_file[tile]);
+    const ThreadText x = load_thread_text(t);
     const uint32_t st_in = tile_state[tile];
     const uint64_t tpos = tile_pos[tile];
-    uint32_t cbits = 0, vbits = 0, n = 0, nrec = 0, local, e_total;
-    if (t.fd.kind == 0) {
-        const FaChunk fc = fa_chunk<true>(ch, prev, t.off, t.fd.len, t.hdr0);
+    Acc64 acc; acc.init();
+    uint32_t nrec = 0, local, e_total;
+    if (KIND == 0) {
+        FaParts part[kChunksPerThread];
+        uint32_t mine = 0;
+#pragma unroll
+        for (int c = 0; c < kChunksPerThread; ++c) {
+            part[c] = fa_chunk_parts(x.ch[c], x.prev[c], t.off + 16 * c, t.fd.len, t.hdr0);
+            mine = fa_combine(mine, part[c].sum());
+        }
         uint32_t ex, tot;
-        block_scan_fa(fc.sum, ex, tot, reinterpret_cast<uint32_t*>(s_w));
+        block_scan_fa(mine, ex, tot, reinterpret_cast<uint32_t*>(s_w));
         const bool tile_seq = (st_in == ST_SEQ);
         const uint32_t ex_t = ex >> 28;
-        const bool in_seq = ex_t ? (ex_t == 2) : tile_seq;          // line type at this chunk's first byte
+        bool in_seq = ex_t ? (ex_t == 2) : tile_seq;                // line type at this thread's first byte
         local = (ex & 0x3FFFu) + (tile_seq ? ((ex >> 14) & 0x3FFFu) : 0u);
         e_total = (tot & 0x3FFFu) + (tile_seq ? ((tot >> 14) & 0x3FFFu) : 0u);
-        const uint32_t hn = in_seq ? ((fc.sum >> 14) & 0x3FFFu) : 0u, rn = fc.sum & 0x3FFFu;
-        n = hn + rn;
-        // head entries (if any) come first; hn + rn <= 16 so the shifts stay below 32 unless hn == 16
-        cbits = (in_seq ? fc.head_c : 0u) | (hn < 16 ? fc.rest_c << (2 * hn) : 0u);
-        vbits = (in_seq ? fc.head_v : 0u) | (fc.rest_v << hn);
-        nrec = fc.nrec;
+#pragma unroll
+        for (int c = 0; c < kChunksPerThread; ++c) {
+            if (in_seq) acc.append(part[c].hc, part[c].hv_rv & 0xFFFFu, part[c].hn());
+            acc.append(part[c].rc, part[c].hv_rv >> 16, part[c].rn());
+            nrec += part[c].nrec();
+            if (part[c].t()) in_seq = (part[c].t() == 2);
+        }
     } else {
-        const Sum mine = chunk_summary<1>(ch, prev, t.off, t.fd.len, t.hdr0);
-        Sum excl, total;
+        Sum sums[kChunksPerThread];
+        Sum mine = sum_identity(), excl, total;
+#pragma unroll
+        for (int c = 0; c < kChunksPerThread; ++c) {
+            sums[c] = chunk_summary<1>(x.ch[c], x.prev[c], t.off + 16 * c, t.fd.len, t.hdr0);
+            mine = sum_combine(mine, sums[c]);
+        }
         block_scan_sum(mine, excl, total, s_w);
         uint32_t st = sum_end(excl, st_in);
         local = sum_cnt(excl, st_in);
         e_total = sum_cnt(total, st_in);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const uint64_t pos = t.off + i;
-            const uint32_t c = ch.byte(i);
-            if (pos < t.fd.len && pos >= t.hdr0) {
-                const bool ls = (pos == t.hdr0) || (prev == '\n');
-                if (c == '\n') st = (st + 1) & 3;
-                else if (st == 0) { if (ls) { n++; nrec++; } }
-                else if (st == 1 && c != '\r') {
-                    if (is_acgt(c)) { cbits |= ((c >> 1) & 3u) << (2 * n); vbits |= 1u << n; }
-                    n++;
+        for (int c = 0; c < kChunksPerThread; ++c) {
+            uint32_t cbits = 0, vbits = 0, n = 0, prev = x.prev[c];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const uint64_t pos = t.off + 16 * c + i;
+                const uint32_t ch = x.ch[c].byte(i);
+                if (pos < t.fd.len && pos >= t.hdr0) {
+                    const bool ls = (pos == t.hdr0) || (prev == '\n');
+                    if (ch == '\n') st = (st + 1) & 3;
+                    else if (st == 0) { if (ls) { n++; nrec++; } }
+                    else if (st == 1 && ch != '\r') {
+                        if (is_acgt(ch)) { cbits |= ((ch >> 1) & 3u) << (2 * n); vbits |= 1u << n; }
+                        n++;
+                    }
                 }
+                prev = ch;
             }
-            prev = c;
+            acc.append(cbits, vbits, n);
         }
     }
-    const uint32_t rel = (uint32_t)(tpos & 31) + local;   // entry offset from the tile's first group
-    if (n) {
+    __syncthreads();                                                // s_codes / s_valid cleared
+    if (acc.n) {
+        const uint32_t rel = (uint32_t)(tpos & 31) + local;         // entry offset from the tile's first group
         const uint32_t cb = rel * 2, cw = cb >> 5, cs = cb & 31;
-        atomicOr(&s_codes[cw], cbits << cs);
-        if (cs && (cbits >> (32 - cs))) atomicOr(&s_codes[cw + 1], cbits >> (32 - cs));
+        const uint32_t c0 = (uint32_t)acc.clo, c1 = (uint32_t)(acc.clo >> 32), c2 = (uint32_t)acc.chi, c3 = (uint32_t)(acc.chi >> 32);
+        const uint32_t w0 = c0 << cs, w1 = __funnelshift_l(c0, c1, cs), w2 = __funnelshift_l(c1, c2, cs),
+                       w3 = __funnelshift_l(c2, c3, cs), w4 = cs ? (c3 >> (32 - cs)) : 0u;
+        if (w0) atomicOr(&s_codes[cw], w0);
+        if (w1) atomicOr(&s_codes[cw + 1], w1);
+        if (w2) atomicOr(&s_codes[cw + 2], w2);
+        if (w3) atomicOr(&s_codes[cw + 3], w3);
+        if (w4) atomicOr(&s_codes[cw + 4], w4);
         const uint32_t vw = rel >> 5, vs = rel & 31;
-        atomicOr(&s_valid[vw], vbits << vs);
-        if (vs && (vbits >> (32 - vs))) atomicOr(&s_valid[vw + 1], vbits >> (32 - vs));
+        const uint32_t v0 = (uint32_t)acc.v, v1 = (uint32_t)(acc.v >> 32);
+        const uint32_t u0 = v0 << vs, u1 = __funnelshift_l(v0, v1, vs), u2 = vs ? (v1 >> (32 - vs)) : 0u;
+        if (u0) atomicOr(&s_valid[vw], u0);
+        if (u1) atomicOr(&s_valid[vw + 1], u1);
+        if (u2) atomicOr(&s_valid[vw + 2], u2);
     }
     if (nrec) atomicAdd(&s_nrec, nrec);
     __syncthreads();
