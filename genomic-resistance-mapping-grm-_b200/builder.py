@@ -115,6 +115,18 @@ class KmerMatrixBuilder:
         self._check(self._lib.grmkm_copy_matrix(self._ctx, C.c_void_p(out.ctypes.data), U * W))
         return out
 
+    def result_host(self) -> tuple[np.ndarray, np.ndarray]:
+        """(kmers[U], matrix[W][U]) as views of the context's page-locked result buffer: one device->host
+        copy at PCIe speed.  The views are valid until the next build / reset / close; copy them to keep them."""
+        U, W, _ = self.dims
+        a, b = C.c_void_p(), C.c_void_p()
+        self._check(self._lib.grmkm_host_result(self._ctx, C.byref(a), C.byref(b)))
+        if U == 0:
+            return np.empty(0, dtype=np.uint64), np.empty((W, 0), dtype=np.uint64)
+        km = np.ctypeslib.as_array(C.cast(a, C.POINTER(C.c_uint64)), shape=(U,))
+        mat = np.ctypeslib.as_array(C.cast(b, C.POINTER(C.c_uint64)), shape=(W, U))
+        return km, mat
+
     def kmer_strings(self) -> np.ndarray:
         U, _, _ = self.dims
         out = np.empty(U, dtype=f"S{self.k}")

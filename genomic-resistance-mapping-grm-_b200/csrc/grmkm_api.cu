@@ -57,6 +57,10 @@ struct grmkm_ctx {
     cudaEvent_t ev[T_N]{};
     bool ev_ok = false;
 
+    // page-locked host copy of the result (grmkm_host_result)
+    void* host_res = nullptr;
+    size_t host_res_cap = 0;
+
     // result
     bool built = false;
     uint64_t U = 0;
@@ -352,6 +356,7 @@ void grmkm_destroy(grmkm_ctx* c) {
                      &c->shist, &c->kmers, &c->matrix, &c->scalars, &c->fmt, &c->synth, &c->owner_start, &c->refs, &c->spart, &c->stile_file, &c->bbase};
     for (DevBuf* b : all) release(c, *b);
     if (c->ev_ok) for (int i = 0; i < T_N; ++i) cudaEventDestroy(c->ev[i]);
+    if (c->host_res) cudaFreeHost(c->host_res);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -869,6 +874,27 @@ int grmkm_format_tsv(grmkm_ctx* c, const char* const* names, char* dst, uint64_t
         CU_TRY(c, cudaMemcpyAsync(p + j0 * roww, c->fmt.p, nb, cudaMemcpyDeviceToHost, c->stream));
         CU_TRY(c, cudaStreamSynchronize(c->stream));
     }
+    return GRMKM_OK;
+}
+
+int grmkm_host_result(grmkm_ctx* c, const uint64_t** kmers, const uint64_t** matrix) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    if (!c->built) return fail(c, GRMKM_E_INVALID, "no result: call grmkm_build first");
+    const size_t nk = (size_t)c->U * 8, nm = (size_t)c->U * c->W * 8;
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (c->host_res_cap < nk + nm + 16) {
+        if (c->host_res) { cudaFreeHost(c->host_res); c->host_res = nullptr; c->host_res_cap = 0; }
+        const size_t want = ((nk + nm) * 5 / 4 + (1 << 20)) & ~size_t(4095);
+        cudaError_t e = cudaHostAlloc(&c->host_res, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) { c->host_res = nullptr; return fail(c, GRMKM_E_NOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); }
+        c->host_res_cap = want;
+    }
+    uint8_t* h = (uint8_t*)c->host_res;
+    if (nk) CU_TRY(c, cudaMemcpyAsync(h, c->kmers.p, nk, cudaMemcpyDeviceToHost, c->stream));
+    if (nm) CU_TRY(c, cudaMemcpyAsync(h + nk, c->matrix.p, nm, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (kmers) *kmers = (const uint64_t*)h;
+    if (matrix) *matrix = (const uint64_t*)(h + nk);
     return GRMKM_OK;
 }
 

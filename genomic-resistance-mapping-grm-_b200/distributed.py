@@ -97,6 +97,9 @@ class CudaEngine:
     def result(self):
         return self.b.kmers(), self.b.matrix()
 
+    def result_host(self):
+        return self.b.result_host()
+
 
 class DistributedBuilder:
     """Same surface as KmerMatrixBuilder, for rank `rank` of `world` processes.
@@ -202,6 +205,14 @@ class DistributedBuilder:
 
     def matrix(self):
         return self.engine.result()[1] if self.world > 1 else self.builder.matrix()
+
+    def result_host(self):
+        """This rank's (kmers, matrix) as views of page-locked host memory (valid until the next build)."""
+        if self.world > 1 and hasattr(self.engine, "result_host"):
+            return self.engine.result_host()
+        if self.world > 1:
+            return self.engine.result()
+        return self.builder.result_host()
 
     def gather(self):
         """Global (kmers, matrix [W][U]) in ascending hash order on rank 0, None elsewhere."""

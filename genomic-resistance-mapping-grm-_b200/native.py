@@ -6,7 +6,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgrmkm.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 OK = 0
 E_INVALID, E_UNSUPPORTED_K, E_NOMEM, E_CUDA, E_IO, E_CAPACITY, E_NO_DEVICE, E_UNSUPPORTED = -1, -2, -3, -4, -5, -6, -7, -8
@@ -21,7 +21,7 @@ SYMBOLS = [
     "grmkm_abi_version", "grmkm_device_count", "grmkm_create", "grmkm_destroy", "grmkm_last_error", "grmkm_reset",
     "grmkm_add_genome_bytes", "grmkm_add_genome_device", "grmkm_add_genome_files", "grmkm_set_genome_count",
     "grmkm_build", "grmkm_dims", "grmkm_get_stats", "grmkm_stage_times", "grmkm_copy_kmers_packed",
-    "grmkm_copy_kmer_strings", "grmkm_copy_matrix", "grmkm_format_tsv", "grmkm_device_result",
+    "grmkm_copy_kmer_strings", "grmkm_copy_matrix", "grmkm_format_tsv", "grmkm_device_result", "grmkm_host_result",
     "grmkm_synth_fasta_device", "grmkm_build_partial", "grmkm_export_partials", "grmkm_merge_partials",
     "grmkm_plan_bucket_bits", "grmkm_set_bucket_bits",
 ]
@@ -91,6 +91,7 @@ def load() -> C.CDLL:
         "grmkm_copy_matrix": (i32, [vp, vp, u64]),
         "grmkm_format_tsv": (i32, [vp, C.POINTER(C.c_char_p), vp, u64, C.POINTER(u64)]),
         "grmkm_device_result": (i32, [vp, C.POINTER(vp), C.POINTER(vp)]),
+        "grmkm_host_result": (i32, [vp, C.POINTER(vp), C.POINTER(vp)]),
         "grmkm_synth_fasta_device": (i32, [vp, vp, u64, vp, u64]),
         "grmkm_build_partial": (i32, [vp, u32, C.POINTER(u64)]),
         "grmkm_export_partials": (i32, [vp, vp, u64]),

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GRMKM_ABI_VERSION 3
+#define GRMKM_ABI_VERSION 4
 
 enum {
     GRMKM_OK = 0,
@@ -146,6 +146,13 @@ int grmkm_copy_matrix(grmkm_ctx* ctx, uint64_t* dst, uint64_t cap);
  * dst may be NULL to query the size (returned in *written with GRMKM_E_CAPACITY).
  */
 int grmkm_format_tsv(grmkm_ctx* ctx, const char* const* names, char* dst, uint64_t cap, uint64_t* written);
+
+/*
+ * The result in page-locked host memory owned by the context: one device->host copy at PCIe speed (a copy
+ * into pageable caller memory runs 10x slower).  kmers[U], matrix[n_words][U] row-major; the pointers stay
+ * valid until the next build / reset / destroy of this context.
+ */
+int grmkm_host_result(grmkm_ctx* ctx, const uint64_t** kmers, const uint64_t** matrix);
 
 /* Device pointers of the result (kmers[U], matrix[n_words][U]) for callers that stay on the GPU. */
 int grmkm_device_result(const grmkm_ctx* ctx, const uint64_t** d_kmers, const uint64_t** d_matrix);

@@ -186,6 +186,26 @@ def test_rebuild_reuses_context(gpu):
             assert np.array_equal(b.kmers(), ref.kmers) and np.array_equal(b.matrix(), ref.matrix)
 
 
+def test_result_host_is_the_same_result(gpu):
+    from grm_b200.builder import KmerMatrixBuilder
+    rng = np.random.default_rng(31)
+    shared = [inputs.rand_seq(rng, 3000)]
+    with KmerMatrixBuilder(k=21, keep_singletons=True) as b:
+        for n_gen in (70, 3):                       # the pinned buffer is reused (and re-sized) across builds
+            b.reset()
+            for row in range(n_gen):
+                b.add_genome_bytes(row, inputs.fasta(rng, shared=shared, max_len=900))
+            b.build()
+            km, mat = b.result_host()
+            assert km.dtype == np.uint64 and mat.shape == (b.dims[1], b.dims[0])
+            assert np.array_equal(km, b.kmers()) and np.array_equal(mat, b.matrix())
+        b.reset()
+        b.set_genome_count(2)
+        b.build()                                    # no input at all
+        km, mat = b.result_host()
+        assert km.size == 0 and mat.shape == (1, 0)
+
+
 def test_errors(gpu):
     from grm_b200.builder import KmerMatrixBuilder, GrmkmError
     with pytest.raises(GrmkmError) as e:
