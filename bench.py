@@ -50,7 +50,8 @@ def traffic_from_profiles(kernel: str):
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(p) as f:
-            return json.load(f).get(kernel)
+            v = json.load(f).get(kernel)
+            return v.get("dram_bytes_per_launch") if isinstance(v, dict) else v
     except Exception:
         return None
 
