@@ -970,17 +970,17 @@ int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
     CU_TRY(c, cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     Launches L;
-    MergeSrc ms{};
-    ms.n_src = n_ranks;
+    AggParams2 ap{};
     uint64_t n_total = 0, words = 0;
     uint32_t W_total = 0;
-    uint32_t src_woff_h[16] = {0};
+    std::vector<uint64_t> h_meta(3 * 16, 0);          // src_off[16], src_count[16], src_width[16] (as u64 / u32 below)
+    uint32_t h_width[16] = {0};
     for (uint32_t s = 0; s < n_ranks; ++s) {
-        ms.ent_off[s] = n_total; ms.word_off[s] = words; ms.width[s] = 1 + src_words[s];
-        src_woff_h[s] = W_total;
+        ap.src_off[s] = words; ap.src_words[s] = src_words[s]; ap.src_woff[s] = W_total;
+        h_meta[s] = words; h_meta[16 + s] = src_counts[s]; h_width[s] = 1 + src_words[s];
         n_total += src_counts[s]; words += src_counts[s] * (1 + (uint64_t)src_words[s]); W_total += src_words[s];
     }
-    ms.ent_off[n_ranks] = n_total; ms.word_off[n_ranks] = words;
+    ap.n_src = n_ranks;
     if (W_total != (total_genomes + 63) / 64) return fail(c, GRMKM_E_INVALID, "source words do not add up to the genome count");
     if (n_total && !dev_parts) return fail(c, GRMKM_E_INVALID, "null parts");
     c->built = false; c->U = 0; c->W = W_total; c->G = total_genomes;
@@ -992,43 +992,43 @@ int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
     const size_t smem = table_smem(slots, W_total);
     // every rank sees 1/P of the hash space: size the buckets for n_total * P entries over the full range
     const uint64_t per = std::max<uint64_t>(1, slots / 2);
-    uint32_t mb = std::min(20u, std::max(6u, ceil_log2((n_total * n_ranks + per - 1) / per)));
-    const uint32_t B = 1u << mb;
+    const uint32_t mb = std::min(24u, std::max(6u, ceil_log2((n_total * n_ranks + per - 1) / per)));
+    const uint64_t Bfull = 1ULL << mb;
+    // this owner's slice of the bucket space (the partial columns of owner r lie in hash range [r/P, (r+1)/P))
+    const uint32_t b_lo = (uint32_t)(Bfull * rank / n_ranks);
+    const uint32_t b_hi = (uint32_t)((Bfull * (rank + 1) + n_ranks - 1) / n_ranks);
+    const uint32_t nb = b_hi - b_lo, nb1 = nb + 1;
     ENSURE(c, c->scalars, S_COUNT * 8);
-    ENSURE(c, c->hist, (size_t)B * 8);
-    ENSURE(c, c->offsets, (size_t)(B + 1) * 8);
-    ENSURE(c, c->offsets2, (size_t)(B + 1) * 8);
-    ENSURE(c, c->bbase, (size_t)B * 8);
-    ENSURE(c, c->bcounts, (size_t)B * 8);
-    ENSURE(c, c->refs, n_total * 8);
+    ENSURE(c, c->offsets2, (size_t)(nb + 1) * 8);
+    ENSURE(c, c->bbase, (size_t)nb * 8);
+    ENSURE(c, c->bcounts, (size_t)nb * 8);
+    ENSURE(c, c->refs, (size_t)n_ranks * nb1 * 8 + 16 * 8 * 3);      // bounds + source tables
     uint64_t ucap = std::min<uint64_t>(n_total, 0xFFFFFFFFULL);
     ENSURE(c, c->ukeys, ucap * 8);
     ENSURE(c, c->uwords, (size_t)ucap * W_total * 8);
     uint64_t* d_scalars = (uint64_t*)c->scalars.p;
+    unsigned long long* d_bounds = (unsigned long long*)c->refs.p;
+    unsigned long long* d_meta = d_bounds + (size_t)n_ranks * nb1;
     if (c->ev_ok) cudaEventRecord(c->ev[T_START], st);
     CU_TRY(c, cudaMemsetAsync(c->scalars.p, 0, S_COUNT * 8, st));
-    CU_TRY(c, cudaMemsetAsync(c->hist.p, 0, (size_t)B * 8, st));
-    const uint32_t pgrid = (uint32_t)((n_total + 255) / 256);
+    for (uint32_t s = 0; s < 16; ++s) h_meta[32 + s] = 0;
+    memcpy(&h_meta[32], h_width, sizeof h_width);
+    CU_TRY(c, cudaMemcpyAsync(d_meta, h_meta.data(), 48 * 8, cudaMemcpyHostToDevice, st));
     const unsigned long long* parts = (const unsigned long long*)dev_parts;
-    k_merge_partition<0><<<pgrid, 256, 0, st>>>(parts, ms, n_total, mb, (unsigned long long*)c->hist.p, nullptr);
-    k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->hist.p, (unsigned long long*)c->offsets.p, B, d_scalars,
-                                         S_N_WINDOWS, 1);
-    k_merge_partition<1><<<pgrid, 256, 0, st>>>(parts, ms, n_total, mb, (unsigned long long*)c->hist.p,
-                                                (unsigned long long*)c->refs.p);
-    L.n += 3;
+    const uint64_t n_search = (uint64_t)n_ranks * nb1;
+    k_merge_bounds<<<(uint32_t)((n_search + 255) / 256), 256, 0, st>>>(parts, n_ranks, nb1, b_lo, mb, d_meta, d_meta + 16,
+                                                                      (const uint32_t*)(d_meta + 32), d_bounds);
+    L.n++;
     CU_TRY(c, cudaGetLastError());
     if (c->ev_ok) cudaEventRecord(c->ev[T_SCATTER], st);
-    AggParams2 ap{};
-    for (uint32_t s2 = 0; s2 < n_ranks; ++s2) { ap.src_words[s2] = src_words[s2]; ap.src_woff[s2] = src_woff_h[s2]; }
-    ap.records = (const unsigned long long*)c->refs.p; ap.begin = (const unsigned long long*)c->offsets.p; ap.end = ap.begin + 1;
     ap.bucket_bits = mb; ap.row_bits = 0; ap.n_words = W_total; ap.slots = slots;
     ap.keep_singletons = c->cfg.keep_singletons; ap.init_depth = 0;
     ap.out_keys = (unsigned long long*)c->ukeys.p; ap.out_words = (unsigned long long*)c->uwords.p;
-    ap.cap = ucap; ap.scalars = (unsigned long long*)d_scalars; ap.parts = parts;
+    ap.cap = ucap; ap.scalars = (unsigned long long*)d_scalars; ap.parts = parts; ap.bounds = d_bounds;
     ap.bucket_base = (unsigned long long*)c->bbase.p; ap.bucket_count = (unsigned long long*)c->bcounts.p;
-    ap.b_begin = 0; ap.b_end = B;
+    ap.b_begin = b_lo; ap.b_end = b_hi;
     CU_TRY(c, cudaFuncSetAttribute(k_aggregate_cols<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_aggregate_cols<3><<<std::min<uint32_t>(B, (uint32_t)c->sm_count), kAggThreads, smem, st>>>(ap);
+    k_aggregate_cols<3><<<std::max(1u, std::min<uint32_t>(nb, (uint32_t)c->sm_count)), kAggThreads, smem, st>>>(ap);
     L.n++;
     CU_TRY(c, cudaGetLastError());
     uint64_t sc[S_COUNT];
@@ -1042,12 +1042,12 @@ int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
     } else {
         ENSURE(c, c->kmers, U * 8);
         ENSURE(c, c->matrix, (size_t)U * W_total * 8);
-        k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->bcounts.p, (unsigned long long*)c->offsets2.p, B,
+        k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->bcounts.p, (unsigned long long*)c->offsets2.p, nb,
                                              d_scalars, S_N_SOLID, 1);
         if (U) {
-            k_gather_buckets<<<std::min<uint32_t>(B, (uint32_t)c->sm_count * 8), 256, 0, st>>>(
+            k_gather_buckets<<<std::max(1u, std::min<uint32_t>(nb, (uint32_t)c->sm_count * 8)), 256, 0, st>>>(
                 (const unsigned long long*)c->ukeys.p, (const unsigned long long*)c->uwords.p, ucap,
-                (const unsigned long long*)c->bbase.p, (const unsigned long long*)c->offsets2.p, B, W_total, U,
+                (const unsigned long long*)c->bbase.p, (const unsigned long long*)c->offsets2.p, nb, W_total, U,
                 (unsigned long long*)c->kmers.p, (unsigned long long*)c->matrix.p, U);
         }
         L.n += 2;

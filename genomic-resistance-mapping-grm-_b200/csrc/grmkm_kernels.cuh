@@ -963,15 +963,34 @@ struct AggParams2 {
     unsigned long long* scalars;
     unsigned long long* bucket_base;     // [B] where the bucket's chunk starts in out_*
     unsigned long long* bucket_count;    // [B] columns the bucket emitted
-    uint32_t b_begin, b_end;
-    const unsigned long long* parts;     // MODE 3
+    uint32_t b_begin, b_end;             // bucket_base / bucket_count are indexed by b - b_begin
+    // MODE 3: partial columns [hash, words...] of n_src sources, each list ascending by hash; the entries of
+    // bucket b in source s are bounds[s * (b_end - b_begin + 1) + (b - b_begin)] .. [.. + 1]
+    const unsigned long long* parts;
+    const unsigned long long* bounds;
+    uint32_t n_src;
+    unsigned long long src_off[16];      // first u64 word of the source in parts
     uint32_t src_words[16];
     uint32_t src_woff[16];
 };
 
 // Stream the bucket's records through the table.  Probing starts at the (monotone) home slot and never wraps:
 // kMaxProbe tail slots follow the home range, and a chain longer than kMaxProbe means "does not fit".
-template <int MODE, bool FILTER>
+__device__ __forceinline__ bool agg_probe(unsigned long long* keys, uint32_t& slot, unsigned long long key) {
+    int probe = 0;
+    while (true) {
+        unsigned long long k0 = *(volatile unsigned long long*)&keys[slot];
+        if (k0 == key) return true;
+        if (k0 == kEmptyKey) {
+            k0 = atomicCAS(&keys[slot], kEmptyKey, key);
+            if (k0 == kEmptyKey || k0 == key) return true;
+        }
+        ++slot;
+        if (++probe >= kMaxProbe) return false;
+    }
+}
+
+template <bool FILTER>
 __device__ __forceinline__ void agg_stream(const AggParams2& p, const AggTable& t, const unsigned long long* __restrict__ recs,
                                            uint32_t n, uint32_t key_bits, uint32_t depth, unsigned long long ridx,
                                            volatile uint32_t* overflow) {
@@ -992,16 +1011,8 @@ __device__ __forceinline__ void agg_stream(const AggParams2& p, const AggTable& 
 #pragma unroll
         for (int j = 0; j < kAggBatch; ++j) {
             if (base + j * kAggThreads >= n) break;
-            unsigned long long key;
-            const unsigned long long* ent = nullptr;
-            if (MODE == 3) {
-                ent = p.parts + (r[j] >> 8);
-                key = ent[0] & ((1ULL << key_bits) - 1);
-                if (FILTER && (key >> (key_bits - depth)) != ridx) continue;
-            } else {
-                key = r[j] >> row_bits;          // carries (bucket_bits - row_bits) redundant bucket bits on top
-                if (FILTER && ((key << (64 - key_bits)) >> (64 - depth)) != ridx) continue;
-            }
+            const unsigned long long key = r[j] >> row_bits;      // carries (bucket_bits - row_bits) redundant bucket bits on top
+            if (FILTER && ((key << (64 - key_bits)) >> (64 - depth)) != ridx) continue;
             uint32_t slot = home_slot(key, shift, slots);
             int probe = 0;
             while (true) {
@@ -1015,20 +1026,63 @@ __device__ __forceinline__ void agg_stream(const AggParams2& p, const AggTable& 
                 if (++probe >= kMaxProbe) { *overflow = 1; break; }
             }
             if (probe < kMaxProbe) {
-                if (MODE == 3) {
-                    const uint32_t src = (uint32_t)(r[j] & 255u), nw = p.src_words[src], wo = p.src_woff[src];
-                    for (uint32_t w = 0; w < nw; ++w) {
-                        const unsigned long long v = ent[1 + w];
-                        if ((uint32_t)v) atomicOr(&w32[(2 * (wo + w)) * total + slot], (uint32_t)v);
-                        if ((uint32_t)(v >> 32)) atomicOr(&w32[(2 * (wo + w) + 1) * total + slot], (uint32_t)(v >> 32));
-                    }
-                } else {
-                    const uint32_t row = (uint32_t)r[j] & row_mask;
-                    atomicOr(&w32[((row >> 5) ^ 1u) * total + slot], 0x80000000u >> (row & 31u));
-                }
+                const uint32_t row = (uint32_t)r[j] & row_mask;
+                atomicOr(&w32[((row >> 5) ^ 1u) * total + slot], 0x80000000u >> (row & 31u));
             }
         }
     }
+}
+
+// MODE 3: the bucket's entries are one contiguous range per source (the lists arrive sorted by hash)
+template <bool FILTER>
+__device__ __forceinline__ void agg_stream_parts(const AggParams2& p, const AggTable& t, uint32_t b, uint32_t key_bits,
+                                                 uint32_t depth, unsigned long long ridx, volatile uint32_t* overflow) {
+    const uint32_t shift = 64 - key_bits + depth;
+    const unsigned long long key_mask = (1ULL << key_bits) - 1;
+    const uint32_t nb1 = p.b_end - p.b_begin + 1;
+    for (uint32_t s = 0; s < p.n_src; ++s) {
+        const unsigned long long lo = p.bounds[(size_t)s * nb1 + (b - p.b_begin)], hi = p.bounds[(size_t)s * nb1 + (b - p.b_begin) + 1];
+        const uint32_t nw = p.src_words[s], wo = p.src_woff[s], width = 1 + nw;
+        const unsigned long long* src = p.parts + p.src_off[s];
+        for (unsigned long long i = lo + threadIdx.x; i < hi; i += kAggThreads) {
+            if (*overflow) break;
+            const unsigned long long* ent = src + i * width;
+            const unsigned long long key = ent[0] & key_mask;
+            if (FILTER && (key >> (key_bits - depth)) != ridx) continue;
+            uint32_t slot = home_slot(key, shift, t.slots);
+            if (!agg_probe(t.keys, slot, key)) { *overflow = 1; break; }
+            for (uint32_t w = 0; w < nw; ++w) {
+                const unsigned long long v = ent[1 + w];
+                if ((uint32_t)v) atomicOr(&t.w32[(2 * (wo + w)) * t.total + slot], (uint32_t)v);
+                if ((uint32_t)(v >> 32)) atomicOr(&t.w32[(2 * (wo + w) + 1) * t.total + slot], (uint32_t)(v >> 32));
+            }
+        }
+    }
+}
+
+// bounds[s][j] = first entry of source s whose hash is >= (b_begin + j) << key_bits  (j = 0 .. nb; j with
+// b_begin + j == 2^bucket_bits means "the end")
+__global__ void k_merge_bounds(const unsigned long long* __restrict__ parts, uint32_t n_src, uint32_t nb1, uint32_t b_begin,
+                               uint32_t bucket_bits, const unsigned long long* __restrict__ src_off,
+                               const unsigned long long* __restrict__ src_count, const uint32_t* __restrict__ src_width,
+                               unsigned long long* __restrict__ bounds) {
+    const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= (uint64_t)n_src * nb1) return;
+    const uint32_t s = (uint32_t)(id / nb1), j = (uint32_t)(id % nb1);
+    const unsigned long long n = src_count[s];
+    const uint64_t bb = (uint64_t)b_begin + j;
+    unsigned long long lo = 0, hi = n;
+    if (bb >= (1ULL << bucket_bits)) lo = n;
+    else {
+        const unsigned long long target = bb << (64 - bucket_bits);
+        const unsigned long long* src = parts + src_off[s];
+        const uint32_t width = src_width[s];
+        while (lo < hi) {
+            const unsigned long long mid = (lo + hi) >> 1;
+            if (src[mid * width] < target) lo = mid + 1; else hi = mid;
+        }
+    }
+    bounds[id] = lo;
 }
 
 // Pass A over the table: kept flags, per-thread kept counts.  Returns this thread's kept count; occ = occupied.
@@ -1102,10 +1156,18 @@ k_aggregate_cols(const AggParams2 p) {
     const uint32_t lo = min(threadIdx.x * chunk, t.total), hi = min(lo + chunk, t.total);
 
     for (uint32_t b = p.b_begin + blockIdx.x; b < p.b_end; b += gridDim.x) {
-        const unsigned long long rbeg = p.begin[b], rend = p.end[b];
-        if (rbeg >= rend) { if (threadIdx.x == 0) { p.bucket_base[b] = 0; p.bucket_count[b] = 0; } continue; }
-        const uint32_t n = (uint32_t)(rend - rbeg);
-        const unsigned long long* recs = p.records + rbeg;
+        uint32_t n = 0;
+        const unsigned long long* recs = nullptr;
+        if (MODE == 3) {
+            const uint32_t nb1 = p.b_end - p.b_begin + 1;
+            for (uint32_t s = 0; s < p.n_src; ++s)
+                n += (uint32_t)(p.bounds[(size_t)s * nb1 + (b - p.b_begin) + 1] - p.bounds[(size_t)s * nb1 + (b - p.b_begin)]);
+        } else {
+            const unsigned long long rbeg = p.begin[b], rend = p.end[b];
+            n = rbeg < rend ? (uint32_t)(rend - rbeg) : 0u;
+            recs = p.records + rbeg;
+        }
+        if (n == 0) { if (threadIdx.x == 0) { p.bucket_base[b - p.b_begin] = 0; p.bucket_count[b - p.b_begin] = 0; } continue; }
         // phase 0: the whole bucket in one table (when init_depth == 0); on overflow, or when sub-ranges are planned:
         // phase 1 counts over the sub-ranges, phase 2 emits them in ascending order
         uint32_t phase = p.init_depth ? 1u : 0u;
@@ -1137,8 +1199,13 @@ k_aggregate_cols(const AggParams2 p) {
             for (uint32_t i = threadIdx.x; i < t.total; i += kAggThreads) t.keys[i] = kEmptyKey;
             for (uint32_t i = threadIdx.x; i < t.total * p.n_words; i += kAggThreads) reinterpret_cast<unsigned long long*>(t.w32)[i] = 0;
             __syncthreads();
-            if (depth == 0) agg_stream<MODE, false>(p, t, recs, n, key_bits, 0, 0, &s_overflow);
-            else agg_stream<MODE, true>(p, t, recs, n, key_bits, depth, ridx, &s_overflow);
+            if (MODE == 3) {
+                if (depth == 0) agg_stream_parts<false>(p, t, b, key_bits, 0, 0, &s_overflow);
+                else agg_stream_parts<true>(p, t, b, key_bits, depth, ridx, &s_overflow);
+            } else {
+                if (depth == 0) agg_stream<false>(p, t, recs, n, key_bits, 0, 0, &s_overflow);
+                else agg_stream<true>(p, t, recs, n, key_bits, depth, ridx, &s_overflow);
+            }
             __syncthreads();
             if (s_overflow) {
                 // split this key range in two, lower half first (terminates: a range of one key needs one slot)
@@ -1170,8 +1237,8 @@ k_aggregate_cols(const AggParams2 p) {
             emitted += total_kept;
         }
         if (threadIdx.x == 0) {
-            p.bucket_base[b] = s_base;
-            p.bucket_count[b] = bucket_total;
+            p.bucket_base[b - p.b_begin] = s_base;
+            p.bucket_count[b - p.b_begin] = bucket_total;
             atomicAdd(&p.scalars[S_N_DISTINCT], (unsigned long long)bucket_occ);
             if (splits) atomicAdd(&p.scalars[S_N_SPLITS], (unsigned long long)splits);
         }
@@ -1205,29 +1272,6 @@ __global__ void k_export_aos(const unsigned long long* __restrict__ keys, const 
     unsigned long long* d = dst + i * (1 + W);
     d[0] = keys[i];
     for (uint32_t w = 0; w < W; ++w) d[1 + w] = words[(uint64_t)w * cap + i];
-}
-
-struct MergeSrc {
-    unsigned long long ent_off[17];    // first entry index of each source (prefix sum of counts)
-    unsigned long long word_off[17];   // first u64 word of each source in the receive buffer
-    uint32_t width[16];                // 1 + words of the source
-    uint32_t n_src;
-};
-
-// count (SCATTER=0) or scatter refs (SCATTER=1) of received partial columns by hash bucket
-template <int SCATTER>
-__global__ void k_merge_partition(const unsigned long long* __restrict__ parts, const MergeSrc ms, uint64_t n_total,
-                                  uint32_t bucket_bits, unsigned long long* __restrict__ hist_cursor,
-                                  unsigned long long* __restrict__ refs) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_total) return;
-    uint32_t s = 0;
-    while (s + 1 < ms.n_src && ms.ent_off[s + 1] <= i) ++s;
-    const unsigned long long woff = ms.word_off[s] + (i - ms.ent_off[s]) * ms.width[s];
-    const unsigned long long h = parts[woff];
-    const uint32_t b = (uint32_t)(h >> (64 - bucket_bits));
-    if (SCATTER == 0) atomicAdd(&hist_cursor[b], 1ULL);
-    else refs[atomicAdd(&hist_cursor[b], 1ULL)] = (woff << 8) | s;
 }
 
 // compact per-bucket filtered records (mode 2 leaves them at the bucket's old offset) into new offsets
