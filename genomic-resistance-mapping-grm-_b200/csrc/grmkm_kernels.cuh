@@ -558,20 +558,18 @@ __device__ __forceinline__ uint32_t scatter_hash_group(const uint32_t (&r)[4], c
     return ALL ? 0xFFFFFFFFu : have;
 }
 
-// phase 3 body: record = (hash << row_bits) | row (the top row_bits bits of the hash are bucket bits and fall off)
-template <bool ALL>
+// phase 3 body: the hash goes to its sorted slot; the row only when the tile spans several genome rows
+template <bool ALL, bool ROWS>
 __device__ __forceinline__ void scatter_place_group(const unsigned long long (&hsh)[kStPerThread], uint32_t have, uint32_t key_bits,
-                                                    uint32_t row_bits, uint32_t row0, bool one_row, uint32_t f, uint64_t pos0,
+                                                    uint32_t row0, bool one_row, uint32_t f, uint64_t pos0,
                                                     const ScatterParams& p, uint32_t* s_off, unsigned long long* s_rec,
-                                                    uint16_t* s_bin) {
+                                                    uint16_t* s_row) {
 #pragma unroll
     for (int e = 0; e < kStPerThread; ++e) {
         if (ALL || ((have >> e) & 1u)) {
-            const uint32_t b = (uint32_t)(hsh[e] >> key_bits);
-            const uint32_t dst = atomicAdd(&s_off[b], 1u);      // s_off[b] walks through the bucket's run
-            const uint32_t row = (ALL || one_row) ? row0 : row_of_position(p.file_stream_start, p.files, p.n_files, f, pos0 + e);
-            s_rec[dst] = (hsh[e] << row_bits) | row;
-            s_bin[dst] = (uint16_t)b;
+            const uint32_t dst = atomicAdd(&s_off[(uint32_t)(hsh[e] >> key_bits)], 1u);   // s_off[b] walks through the bucket's run
+            s_rec[dst] = hsh[e];
+            if (ROWS) s_row[dst] = (uint16_t)(one_row ? row0 : row_of_position(p.file_stream_start, p.files, p.n_files, f, pos0 + e));
         }
     }
 }
@@ -587,7 +585,7 @@ k_scatter(const ScatterParams p) {
     unsigned long long* s_rec = s_delta + B;                     // [kStTile]
     uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_rec + kStTile);   // [B]
     uint32_t* s_off = s_cnt + B;                                 // [B]
-    uint16_t* s_bin = reinterpret_cast<uint16_t*>(s_off + B);    // [kStTile]
+    uint16_t* s_row = reinterpret_cast<uint16_t*>(s_off + B);    // [kStTile] genome rows, only for tiles that span several
     const uint64_t stream_len = p.scalars[S_STREAM_LEN];
     const uint64_t n_groups = (stream_len + 31) >> 5;
     const uint64_t n_tiles = (n_groups + kStThreads - 1) / kStThreads;
@@ -597,7 +595,6 @@ k_scatter(const ScatterParams p) {
     const uint32_t kbits = k == 32 ? 0xFFFFFFFFu : ((1u << k) - 1u);
     const uint32_t key_bits = 64 - p.bucket_bits;
     const uint32_t row_bits = p.row_bits;
-    const uint32_t per = B >= (uint32_t)kStThreads ? B / kStThreads : 1u;   // bins per thread in phase 2
     for (uint32_t i = threadIdx.x; i < B; i += kStThreads) s_cnt[i] = 0;
     __syncthreads();
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -637,47 +634,72 @@ k_scatter(const ScatterParams p) {
             else have = scatter_hash_group<false>(r, y, n0, n1, kbits, kmask_lo, kmask_hi, key_bits, s_cnt, hsh);
         }
         __syncthreads();
-        // ---- phase 2: scan the tile histogram, reserve global space, clear the histogram
+        // ---- phase 2: scan the tile histogram, reserve global space, clear the histogram.  Thread t owns bins
+        // t, t + 512, ... (conflict-free); the tile is laid out thread-major, which is as good as bucket order.
         {
-            const uint32_t b0 = threadIdx.x * per;
             uint32_t cnt[kStMaxBins];
             uint32_t sum = 0;
 #pragma unroll
             for (uint32_t i = 0; i < (uint32_t)kStMaxBins; ++i) {
+                const uint32_t bin = i * kStThreads + threadIdx.x;
                 cnt[i] = 0;
-                if (i < per && b0 < B) { cnt[i] = s_cnt[b0 + i]; s_cnt[b0 + i] = 0; sum += cnt[i]; }
+                if (bin < B) { cnt[i] = s_cnt[bin]; s_cnt[bin] = 0; sum += cnt[i]; }
+            }
+            unsigned long long gb[kStMaxBins];
+#pragma unroll
+            for (uint32_t i = 0; i < (uint32_t)kStMaxBins; ++i) {      // all reservations in flight together
+                const uint32_t bin = i * kStThreads + threadIdx.x;
+                gb[i] = cnt[i] ? atomicAdd(&p.cursors[bin], (unsigned long long)cnt[i]) : 0ULL;
             }
             uint32_t total;
             uint32_t off = block_excl_scan<kStThreads>(sum, s_warp, total);
             if (threadIdx.x == 0) s_total = total;
 #pragma unroll
             for (uint32_t i = 0; i < (uint32_t)kStMaxBins; ++i) {
-                if (i < per && b0 < B) {
-                    s_off[b0 + i] = off;
+                const uint32_t bin = i * kStThreads + threadIdx.x;
+                if (bin < B) {
+                    s_off[bin] = off;
                     if (cnt[i]) {
-                        const unsigned long long gb = atomicAdd(&p.cursors[b0 + i], (unsigned long long)cnt[i]);
-                        if (p.cap && gb + cnt[i] > (unsigned long long)(b0 + i + 1) * p.cap) {
+                        if (p.cap && gb[i] + cnt[i] > (unsigned long long)(bin + 1) * p.cap) {
                             *p.overflow = 1ULL;           // region too small: divert, the host re-runs the exact path
-                            s_delta[b0 + i] = p.dump;
+                            s_delta[bin] = p.dump;
                         } else {
-                            s_delta[b0 + i] = gb - off;
+                            s_delta[bin] = gb[i] - off;
                         }
                     }
                     off += cnt[i];
                 }
             }
         }
+        // does the tile lie inside one file (one genome row)?  Then the row is not staged per record.
+        const uint32_t tf = p.tile_file[tile];
+        const bool tile_one_row = (tf + 1 >= p.n_files) || p.file_stream_start[tf + 1] >= (tile + 1) * (uint64_t)kStTile;
+        const uint32_t tile_row = p.files[tf].row;
         __syncthreads();
         // ---- phase 3: counting sort into shared memory
-        if (have == 0xFFFFFFFFu && one_row) scatter_place_group<true>(hsh, have, key_bits, row_bits, row0, one_row, f, pos0, p, s_off, s_rec, s_bin);
-        else if (have) scatter_place_group<false>(hsh, have, key_bits, row_bits, row0, one_row, f, pos0, p, s_off, s_rec, s_bin);
+        if (tile_one_row) {
+            if (have == 0xFFFFFFFFu) scatter_place_group<true, false>(hsh, have, key_bits, row0, one_row, f, pos0, p, s_off, s_rec, s_row);
+            else if (have) scatter_place_group<false, false>(hsh, have, key_bits, row0, one_row, f, pos0, p, s_off, s_rec, s_row);
+        } else if (have) {
+            scatter_place_group<false, true>(hsh, have, key_bits, row0, one_row, f, pos0, p, s_off, s_rec, s_row);
+        }
         __syncthreads();
-        // ---- phase 4: copy out; consecutive threads write consecutive records of a bucket.  No barrier after
-        // it: phase 1 of the next tile touches only s_cnt (already cleared) and registers.
+        // ---- phase 4: copy out; consecutive threads write consecutive records of a bucket.  Record =
+        // (hash << row_bits) | row: the top row_bits bits of the hash are bucket bits and fall off.  No barrier
+        // after it: phase 1 of the next tile touches only s_cnt (already cleared) and registers.
         const uint32_t total = s_total;
+        if (tile_one_row) {
 #pragma unroll 4
-        for (uint32_t i = threadIdx.x; i < total; i += kStThreads)
-            p.records[s_delta[s_bin[i]] + i] = s_rec[i];
+            for (uint32_t i = threadIdx.x; i < total; i += kStThreads) {
+                const unsigned long long h = s_rec[i];
+                p.records[s_delta[(uint32_t)(h >> key_bits)] + i] = (h << row_bits) | tile_row;
+            }
+        } else {
+            for (uint32_t i = threadIdx.x; i < total; i += kStThreads) {
+                const unsigned long long h = s_rec[i];
+                p.records[s_delta[(uint32_t)(h >> key_bits)] + i] = (h << row_bits) | s_row[i];
+            }
+        }
     }
 }
 
