@@ -33,6 +33,8 @@ struct Input {
     std::vector<uint8_t> owned;
 };
 
+constexpr uint64_t kBatchBytes = 32ull << 20;      // text per pipelined H2D batch (GRMKM_BATCH_BYTES overrides, for tests)
+
 enum Stage { T_START = 0, T_H2D, T_PARSE, T_PACK, T_COUNT, T_SCATTER, T_ABUND, T_AGG, T_SORT, T_N };
 
 }  // namespace
@@ -56,6 +58,11 @@ struct grmkm_ctx {
 
     cudaEvent_t ev[T_N]{};
     bool ev_ok = false;
+
+    // H2D pipeline: copy stream, "batch copied" / "staging half free" events
+    uint64_t batch_bytes = kBatchBytes;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2]{}, ev_free[2]{};
 
     // page-locked host copy of the result (grmkm_host_result)
     void* host_res = nullptr;
@@ -331,6 +338,7 @@ int grmkm_create(const grmkm_config* cfg, grmkm_ctx** out) {
         x->sm_count = prop.multiProcessorCount;
         x->smem_optin = prop.sharedMemPerBlockOptin;
     }
+    if (const char* bb = getenv("GRMKM_BATCH_BYTES")) { const long long v = atoll(bb); if (v > 0) x->batch_bytes = (uint64_t)v; }
     if (c.stream) x->stream = (cudaStream_t)c.stream;
     else {
         if ((e = cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking)) != cudaSuccess) {
@@ -357,6 +365,10 @@ void grmkm_destroy(grmkm_ctx* c) {
     for (DevBuf* b : all) release(c, *b);
     if (c->ev_ok) for (int i = 0; i < T_N; ++i) cudaEventDestroy(c->ev[i]);
     if (c->host_res) cudaFreeHost(c->host_res);
+    if (c->copy_stream) {
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->ev_copied[i]); cudaEventDestroy(c->ev_free[i]); }
+        cudaStreamDestroy(c->copy_stream);
+    }
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -441,22 +453,28 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
     P.row_bits = std::max(1u, ceil_log2(P.G));
     if (P.row_bits > 15) return fail(c, GRMKM_E_UNSUPPORTED, "more than 32768 genomes in one context");
 
-    // ---- file table, staging offsets, tiles
-    std::vector<FileDesc> fds(P.F);
-    std::vector<uint64_t> stage_off(P.F, 0);
-    uint64_t stage_total = 0, tiles = 0;
-    for (uint32_t f = 0; f < P.F; ++f) {
-        const Input& in = c->inputs[f];
-        if (!in.dev) { stage_off[f] = stage_total; stage_total += (in.len + 15) & ~15ULL; }
-        fds[f].len = in.len; fds[f].row = in.row; fds[f].kind = in.kind; fds[f].tile_begin = tiles;
-        tiles += std::max<uint64_t>(1, (in.len + kTileBytes - 1) / kTileBytes);
-        P.max_stream += in.len;
-    }
+    // ---- batches.  Host inputs are staged batch by batch on a copy stream (two staging halves), so that the
+    // H2D copy of batch i+1 overlaps parse / pack / scatter of batch i; the scatter appends to the bucket
+    // regions, so batches need no merge.  Device-resident inputs (and the exact-offset fallback, which needs
+    // a count over everything first) run as one batch.
+    struct Batch { uint32_t f0, f1; uint64_t bytes, staged, tiles; };
+    bool any_host = false;
+    for (const Input& in : c->inputs) { P.max_stream += in.len; any_host = any_host || !in.dev; }
     P.in_bytes = P.max_stream;
-    P.n_tiles = tiles;
-    P.n_sblk = (tiles + kScanTilesPerBlock - 1) / kScanTilesPerBlock;
-    P.n_groups_max = P.max_stream / 32 + 2;
-    if (P.n_tiles > 0x7fffffffULL) return fail(c, GRMKM_E_UNSUPPORTED, "input too large for one build (tile count)");
+    auto make_batches = [&](bool pipelined) {
+        std::vector<Batch> v;
+        const uint64_t target = pipelined ? c->batch_bytes : ~0ULL;
+        Batch cur{0, 0, 0, 0, 0};
+        for (uint32_t f = 0; f < P.F; ++f) {
+            const Input& in = c->inputs[f];
+            if (cur.f1 > cur.f0 && cur.bytes + in.len > target) { v.push_back(cur); cur = Batch{f, f, 0, 0, 0}; }
+            cur.f1 = f + 1; cur.bytes += in.len;
+            if (!in.dev) cur.staged += (in.len + 15) & ~15ULL;
+            cur.tiles += std::max<uint64_t>(1, (in.len + kTileBytes - 1) / kTileBytes);
+        }
+        v.push_back(cur);
+        return v;
+    };
 
     // ---- aggregate table geometry and bucket count
     const uint32_t Wtab = P.W;
@@ -470,93 +488,97 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
     c->cur_bucket_bits = P.bucket_bits;
     const uint32_t B = 1u << P.bucket_bits;
 
-    // ---- device buffers
     ENSURE(c, c->scalars, S_COUNT * 8);
-    ENSURE(c, c->in, stage_total);
-    ENSURE(c, c->files, P.F * sizeof(FileDesc));
-    ENSURE(c, c->hdr0, P.F * 8);
-    ENSURE(c, c->fss, (P.F + 1) * 8);
-    ENSURE(c, c->tsum, P.n_tiles * sizeof(Sum));
-    ENSURE(c, c->tile_file, P.n_tiles * 4);
-    ENSURE(c, c->tile_state, P.n_tiles);
-    ENSURE(c, c->tile_pos, P.n_tiles * 8);
-    ENSURE(c, c->bsum, P.n_sblk * sizeof(Sum));
-    ENSURE(c, c->bstate, P.n_sblk * 4);
-    ENSURE(c, c->bpos, P.n_sblk * 8);
-    ENSURE(c, c->codes, P.n_groups_max * 8);
-    ENSURE(c, c->valid, P.n_groups_max * 4);
     ENSURE(c, c->hist, (size_t)B * 8 * kCursorStride);
     ENSURE(c, c->offsets, (size_t)(B + 1) * 8);
+    uint64_t* d_scalars = (uint64_t*)c->scalars.p;
+    const FileDesc* d_files = nullptr;
 
     if (c->ev_ok) cudaEventRecord(c->ev[T_START], st);
-    // ---- stage host inputs
-    uint64_t h2d = 0;
-    for (uint32_t f = 0; f < P.F; ++f) {
-        const Input& in = c->inputs[f];
-        if (in.dev) fds[f].ptr = in.dev;
-        else {
-            fds[f].ptr = (const uint8_t*)c->in.p + stage_off[f];
-            if (in.len) {
-                CU_TRY(c, cudaMemcpyAsync((void*)fds[f].ptr, in.host, in.len, cudaMemcpyHostToDevice, st));
-                h2d += in.len;
-            }
-        }
-    }
-    CU_TRY(c, cudaMemcpyAsync(c->files.p, fds.data(), P.F * sizeof(FileDesc), cudaMemcpyHostToDevice, st));
     CU_TRY(c, cudaMemsetAsync(c->scalars.p, 0, S_COUNT * 8, st));
-    CU_TRY(c, cudaMemsetAsync(c->codes.p, 0, P.n_groups_max * 8, st));
-    CU_TRY(c, cudaMemsetAsync(c->valid.p, 0, P.n_groups_max * 4, st));
-    CU_TRY(c, cudaMemsetAsync(c->hist.p, 0, (size_t)B * 8 * kCursorStride, st));
-    if (c->ev_ok) cudaEventRecord(c->ev[T_H2D], st);
+    uint64_t h2d = 0;
+    std::vector<std::vector<FileDesc>> fds_keep;      // host tables stay alive until the final synchronize
 
-    const FileDesc* d_files = (const FileDesc*)c->files.p;
-    uint64_t* d_scalars = (uint64_t*)c->scalars.p;
-
-    // ---- parse
-    k_first_header<<<(P.F * 32 + 255) / 256, 256, 0, st>>>(d_files, P.F, (uint64_t*)c->hdr0.p);
-    k_tile_files<<<(uint32_t)((P.n_tiles + 255) / 256), 256, 0, st>>>(d_files, P.F, P.n_tiles, (uint32_t*)c->tile_file.p);
-    if (c->cfg.input_kind == GRMKM_FASTA)
-        k_tile_summary<0><<<(uint32_t)P.n_tiles, kParseThreads, 0, st>>>(d_files, (const uint64_t*)c->hdr0.p, P.n_tiles,
-                                                                         (const uint32_t*)c->tile_file.p, (Sum*)c->tsum.p);
-    else
-        k_tile_summary<1><<<(uint32_t)P.n_tiles, kParseThreads, 0, st>>>(d_files, (const uint64_t*)c->hdr0.p, P.n_tiles,
-                                                                         (const uint32_t*)c->tile_file.p, (Sum*)c->tsum.p);
-    k_scan_reduce<<<(uint32_t)P.n_sblk, kScanThreads, 0, st>>>((const Sum*)c->tsum.p, P.n_tiles, (Sum*)c->bsum.p);
-    k_scan_blocks<<<1, 1024, 0, st>>>((const Sum*)c->bsum.p, (uint32_t)P.n_sblk, (uint32_t*)c->bstate.p,
-                                      (uint64_t*)c->bpos.p, d_scalars, (uint64_t*)c->fss.p, P.F);
-    k_scan_apply<<<(uint32_t)P.n_sblk, kScanThreads, 0, st>>>((const Sum*)c->tsum.p, P.n_tiles,
-                                                              (const uint32_t*)c->bstate.p, (const uint64_t*)c->bpos.p,
-                                                              (const uint32_t*)c->tile_file.p, d_files,
-                                                              (uint8_t*)c->tile_state.p, (uint64_t*)c->tile_pos.p,
-                                                              (uint64_t*)c->fss.p);
-    L.n += 6;
-    CU_TRY(c, cudaGetLastError());
-    if (c->ev_ok) cudaEventRecord(c->ev[T_PARSE], st);
-    if (c->cfg.input_kind == GRMKM_FASTA)
-        k_pack<0><<<(uint32_t)P.n_tiles, kParseThreads, 0, st>>>(d_files, (const uint64_t*)c->hdr0.p, P.n_tiles,
-                                                                 (const uint32_t*)c->tile_file.p, (const uint8_t*)c->tile_state.p,
-                                                                 (const uint64_t*)c->tile_pos.p, (unsigned long long*)c->codes.p,
-                                                                 (uint32_t*)c->valid.p, d_scalars);
-    else
-        k_pack<1><<<(uint32_t)P.n_tiles, kParseThreads, 0, st>>>(d_files, (const uint64_t*)c->hdr0.p, P.n_tiles,
-                                                                 (const uint32_t*)c->tile_file.p, (const uint8_t*)c->tile_state.p,
-                                                                 (const uint64_t*)c->tile_pos.p, (unsigned long long*)c->codes.p,
-                                                                 (uint32_t*)c->valid.p, d_scalars);
-    L.n++;
-    CU_TRY(c, cudaGetLastError());
-    if (c->ev_ok) cudaEventRecord(c->ev[T_PACK], st);
+    // parse + pack of one batch: leaves codes / valid / fss / S_STREAM_LEN of the batch
+    auto front = [&](const Batch& bt, const uint8_t* staged_base, bool timed) -> int {
+        const uint32_t F = bt.f1 - bt.f0;
+        const uint64_t n_tiles = bt.tiles, n_sblk = (n_tiles + kScanTilesPerBlock - 1) / kScanTilesPerBlock;
+        const uint64_t n_groups_max = bt.bytes / 32 + 2;
+        if (n_tiles > 0x7fffffffULL) return fail(c, GRMKM_E_UNSUPPORTED, "input too large for one build (tile count)");
+        ENSURE(c, c->files, F * sizeof(FileDesc));
+        ENSURE(c, c->hdr0, F * 8);
+        ENSURE(c, c->fss, (F + 1) * 8);
+        ENSURE(c, c->tsum, n_tiles * sizeof(Sum));
+        ENSURE(c, c->tile_file, n_tiles * 4);
+        ENSURE(c, c->tile_state, n_tiles);
+        ENSURE(c, c->tile_pos, n_tiles * 8);
+        ENSURE(c, c->bsum, n_sblk * sizeof(Sum));
+        ENSURE(c, c->bstate, n_sblk * 4);
+        ENSURE(c, c->bpos, n_sblk * 8);
+        ENSURE(c, c->codes, n_groups_max * 8);
+        ENSURE(c, c->valid, n_groups_max * 4);
+        fds_keep.emplace_back(F);
+        std::vector<FileDesc>& fds = fds_keep.back();
+        uint64_t tiles = 0, soff = 0;
+        for (uint32_t i = 0; i < F; ++i) {
+            const Input& in = c->inputs[bt.f0 + i];
+            fds[i].len = in.len; fds[i].row = in.row; fds[i].kind = in.kind; fds[i].tile_begin = tiles;
+            tiles += std::max<uint64_t>(1, (in.len + kTileBytes - 1) / kTileBytes);
+            if (in.dev) fds[i].ptr = in.dev;
+            else { fds[i].ptr = staged_base + soff; soff += (in.len + 15) & ~15ULL; }
+        }
+        d_files = (const FileDesc*)c->files.p;
+        CU_TRY(c, cudaMemcpyAsync(c->files.p, fds.data(), F * sizeof(FileDesc), cudaMemcpyHostToDevice, st));
+        CU_TRY(c, cudaMemsetAsync(c->codes.p, 0, n_groups_max * 8, st));
+        CU_TRY(c, cudaMemsetAsync(c->valid.p, 0, n_groups_max * 4, st));
+        if (timed && c->ev_ok) cudaEventRecord(c->ev[T_H2D], st);
+        k_first_header<<<(F * 32 + 255) / 256, 256, 0, st>>>(d_files, F, (uint64_t*)c->hdr0.p);
+        k_tile_files<<<(uint32_t)((n_tiles + 255) / 256), 256, 0, st>>>(d_files, F, n_tiles, (uint32_t*)c->tile_file.p);
+        if (c->cfg.input_kind == GRMKM_FASTA)
+            k_tile_summary<0><<<(uint32_t)n_tiles, kParseThreads, 0, st>>>(d_files, (const uint64_t*)c->hdr0.p, n_tiles,
+                                                                           (const uint32_t*)c->tile_file.p, (Sum*)c->tsum.p);
+        else
+            k_tile_summary<1><<<(uint32_t)n_tiles, kParseThreads, 0, st>>>(d_files, (const uint64_t*)c->hdr0.p, n_tiles,
+                                                                           (const uint32_t*)c->tile_file.p, (Sum*)c->tsum.p);
+        k_scan_reduce<<<(uint32_t)n_sblk, kScanThreads, 0, st>>>((const Sum*)c->tsum.p, n_tiles, (Sum*)c->bsum.p);
+        k_scan_blocks<<<1, 1024, 0, st>>>((const Sum*)c->bsum.p, (uint32_t)n_sblk, (uint32_t*)c->bstate.p,
+                                          (uint64_t*)c->bpos.p, d_scalars, (uint64_t*)c->fss.p, F);
+        k_scan_apply<<<(uint32_t)n_sblk, kScanThreads, 0, st>>>((const Sum*)c->tsum.p, n_tiles,
+                                                                (const uint32_t*)c->bstate.p, (const uint64_t*)c->bpos.p,
+                                                                (const uint32_t*)c->tile_file.p, d_files,
+                                                                (uint8_t*)c->tile_state.p, (uint64_t*)c->tile_pos.p,
+                                                                (uint64_t*)c->fss.p);
+        L.n += 6;
+        CU_TRY(c, cudaGetLastError());
+        if (timed && c->ev_ok) cudaEventRecord(c->ev[T_PARSE], st);
+        if (c->cfg.input_kind == GRMKM_FASTA)
+            k_pack<0><<<(uint32_t)n_tiles, kParseThreads, 0, st>>>(d_files, (const uint64_t*)c->hdr0.p, n_tiles,
+                                                                   (const uint32_t*)c->tile_file.p, (const uint8_t*)c->tile_state.p,
+                                                                   (const uint64_t*)c->tile_pos.p, (unsigned long long*)c->codes.p,
+                                                                   (uint32_t*)c->valid.p, d_scalars);
+        else
+            k_pack<1><<<(uint32_t)n_tiles, kParseThreads, 0, st>>>(d_files, (const uint64_t*)c->hdr0.p, n_tiles,
+                                                                   (const uint32_t*)c->tile_file.p, (const uint8_t*)c->tile_state.p,
+                                                                   (const uint64_t*)c->tile_pos.p, (unsigned long long*)c->codes.p,
+                                                                   (uint32_t*)c->valid.p, d_scalars);
+        L.n++;
+        CU_TRY(c, cudaGetLastError());
+        if (timed && c->ev_ok) cudaEventRecord(c->ev[T_PACK], st);
+        return GRMKM_OK;
+    };
 
     // ---- extract + scatter, (abundance), aggregate.  Pass 0 scatters into over-provisioned bucket regions
     // without a count pass; if a region overflows (heavily skewed k-mer spectrum) pass 1 redoes the
     // scatter with exact offsets from a count pass.
     const bool staged = B <= (uint32_t)kStMaxBuckets && !(c->cfg.flags & GRMKM_FLAG_SIMPLE_SCATTER);
     const bool try_regions = staged && !(c->cfg.flags & GRMKM_FLAG_EXACT_OFFSETS);
-    const uint64_t n_stiles = (P.n_groups_max + (kStTile / 32) - 1) / (kStTile / 32);
     const uint32_t agrid = std::min<uint32_t>(B, (uint32_t)c->sm_count);
     uint64_t sc[S_COUNT];
     uint64_t ucap = 0;
     for (int pass = try_regions ? 0 : 1; pass < 2; ++pass) {
         const bool regions = (pass == 0);
+        const std::vector<Batch> batches = make_batches(regions && any_host);
+        const bool pipelined = batches.size() > 1;
         uint64_t cap = 0;
         if (regions) {
             cap = (uint64_t)((double)P.max_stream / B * 1.25) + 2048;
@@ -565,70 +587,108 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         } else {
             ENSURE(c, c->records, P.max_stream * 8);
         }
+        uint64_t half_bytes = 0;
+        for (const Batch& bt : batches) half_bytes = std::max(half_bytes, bt.staged);
+        ENSURE(c, c->in, half_bytes * (pipelined ? 2 : 1));
+        if (pipelined && !c->copy_stream) {
+            CU_TRY(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i) {
+                CU_TRY(c, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+                CU_TRY(c, cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
+            }
+        }
         {
             const uint64_t zeros[S_COUNT] = {0};
-            // keep S_STREAM_LEN and S_N_RECORDS (parse results), clear the rest
-            CU_TRY(c, cudaMemcpyAsync(d_scalars + S_N_WINDOWS, zeros, (S_COUNT - S_N_WINDOWS) * 8, cudaMemcpyHostToDevice, st));
+            CU_TRY(c, cudaMemcpyAsync(d_scalars, zeros, S_COUNT * 8, cudaMemcpyHostToDevice, st));
         }
-        ExtractParams ep{};
-        ep.codes = (const unsigned long long*)c->codes.p;
-        ep.valid = (const uint32_t*)c->valid.p;
-        ep.scalars = d_scalars;
-        ep.file_stream_start = (const uint64_t*)c->fss.p;
-        ep.files = d_files;
-        ep.n_files = P.F;
-        ep.k = c->cfg.k;
-        ep.bucket_bits = P.bucket_bits;
-        ep.row_bits = P.row_bits;
-        ep.hist = (unsigned long long*)c->hist.p;
-        ep.records = (unsigned long long*)c->records.p;
-        ep.dbg = 0;
-        ep.offsets = (const unsigned long long*)c->offsets.p;
-        const uint64_t n_etiles_max = (P.n_groups_max + kExtractThreads - 1) / kExtractThreads;
-        const uint32_t egrid = (uint32_t)std::min<uint64_t>(n_etiles_max, (uint64_t)c->sm_count * 8);
         if (regions) {
             k_init_regions<<<(B + 1 + 255) / 256, 256, 0, st>>>((unsigned long long*)c->offsets.p,
                                                                 (unsigned long long*)c->hist.p, B, cap);
             L.n++;
-        } else {
-            CU_TRY(c, cudaMemsetAsync(c->hist.p, 0, (size_t)B * 8, st));
-            const size_t hist_smem = (size_t)B * 4;
-            CU_TRY(c, cudaFuncSetAttribute(k_extract<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
-            k_extract<0><<<egrid, kExtractThreads, hist_smem, st>>>(ep);
-            k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->hist.p, (unsigned long long*)c->offsets.p, B,
-                                                 d_scalars, S_N_WINDOWS, kCursorStride);
-            L.n += 2;
         }
-        CU_TRY(c, cudaGetLastError());
-        if (c->ev_ok) cudaEventRecord(c->ev[T_COUNT], st);
-        if (staged) {
-            ENSURE(c, c->stile_file, n_stiles * 4);
-            ScatterParams sp{};
-            sp.codes = ep.codes; sp.valid = ep.valid; sp.scalars = d_scalars; sp.file_stream_start = ep.file_stream_start;
-            sp.files = d_files; sp.tile_file = (const uint32_t*)c->stile_file.p; sp.n_files = P.F; sp.k = c->cfg.k;
-            sp.bucket_bits = P.bucket_bits; sp.row_bits = P.row_bits; sp.cursors = (unsigned long long*)c->hist.p;
-            sp.records = (unsigned long long*)c->records.p; sp.cap = cap; sp.dump = (uint64_t)B * cap;
-            sp.overflow = (unsigned long long*)(d_scalars + S_OVERFLOW);
-            k_scatter_tile_files<<<(uint32_t)((n_stiles + 255) / 256), 256, 0, st>>>(d_scalars, sp.file_stream_start, P.F,
-                                                                                  (uint32_t*)c->stile_file.p, n_stiles);
-            const size_t ssm = staged_smem_bytes(B);
-            const uint32_t sgrid = (uint32_t)std::min<uint64_t>(n_stiles, (uint64_t)c->sm_count);
+        if (pipelined && c->ev_ok)
+            for (int e : {T_H2D, T_PARSE, T_PACK, T_COUNT}) cudaEventRecord(c->ev[e], st);   // stages interleave: only "scatter" is timed
+        h2d = 0;
+        for (size_t bi = 0; bi < batches.size(); ++bi) {
+            const Batch& bt = batches[bi];
+            uint8_t* half = (uint8_t*)c->in.p + (pipelined ? (bi & 1) * half_bytes : 0);
+            cudaStream_t cs = pipelined ? c->copy_stream : st;
+            if (pipelined && bi >= 2) CU_TRY(c, cudaStreamWaitEvent(cs, c->ev_free[bi & 1], 0));
+            uint64_t soff = 0;
+            for (uint32_t f = bt.f0; f < bt.f1; ++f) {
+                const Input& in = c->inputs[f];
+                if (in.dev) continue;
+                if (in.len) { CU_TRY(c, cudaMemcpyAsync(half + soff, in.host, in.len, cudaMemcpyHostToDevice, cs)); h2d += in.len; }
+                soff += (in.len + 15) & ~15ULL;
+            }
+            if (pipelined) {
+                CU_TRY(c, cudaEventRecord(c->ev_copied[bi & 1], cs));
+                CU_TRY(c, cudaStreamWaitEvent(st, c->ev_copied[bi & 1], 0));
+            }
+            int fr = front(bt, half, !pipelined);
+            if (fr) return fr;
+            if (pipelined) CU_TRY(c, cudaEventRecord(c->ev_free[bi & 1], st));     // the staged text has been consumed
+
+            const uint32_t F = bt.f1 - bt.f0;
+            const uint64_t n_groups_max = bt.bytes / 32 + 2;
+            const uint64_t n_stiles = (n_groups_max + (kStTile / 32) - 1) / (kStTile / 32);
+            ExtractParams ep{};
+            ep.codes = (const unsigned long long*)c->codes.p;
+            ep.valid = (const uint32_t*)c->valid.p;
+            ep.scalars = d_scalars;
+            ep.file_stream_start = (const uint64_t*)c->fss.p;
+            ep.files = d_files;
+            ep.n_files = F;
+            ep.k = c->cfg.k;
+            ep.bucket_bits = P.bucket_bits;
+            ep.row_bits = P.row_bits;
+            ep.hist = (unsigned long long*)c->hist.p;
+            ep.records = (unsigned long long*)c->records.p;
+            ep.dbg = 0;
+            ep.offsets = (const unsigned long long*)c->offsets.p;
+            const uint64_t n_etiles_max = (n_groups_max + kExtractThreads - 1) / kExtractThreads;
+            const uint32_t egrid = (uint32_t)std::min<uint64_t>(n_etiles_max, (uint64_t)c->sm_count * 8);
+            if (!regions) {
+                CU_TRY(c, cudaMemsetAsync(c->hist.p, 0, (size_t)B * 8, st));
+                const size_t hist_smem = (size_t)B * 4;
+                CU_TRY(c, cudaFuncSetAttribute(k_extract<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
+                k_extract<0><<<egrid, kExtractThreads, hist_smem, st>>>(ep);
+                k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->hist.p, (unsigned long long*)c->offsets.p, B,
+                                                     d_scalars, S_N_WINDOWS, kCursorStride);
+                L.n += 2;
+            }
+            CU_TRY(c, cudaGetLastError());
+            if (!pipelined && c->ev_ok) cudaEventRecord(c->ev[T_COUNT], st);
+            if (staged) {
+                ENSURE(c, c->stile_file, n_stiles * 4);
+                ScatterParams sp{};
+                sp.codes = ep.codes; sp.valid = ep.valid; sp.scalars = d_scalars; sp.file_stream_start = ep.file_stream_start;
+                sp.files = d_files; sp.tile_file = (const uint32_t*)c->stile_file.p; sp.n_files = F; sp.k = c->cfg.k;
+                sp.bucket_bits = P.bucket_bits; sp.row_bits = P.row_bits; sp.cursors = (unsigned long long*)c->hist.p;
+                sp.records = (unsigned long long*)c->records.p; sp.cap = cap; sp.dump = (uint64_t)B * cap;
+                sp.overflow = (unsigned long long*)(d_scalars + S_OVERFLOW);
+                k_scatter_tile_files<<<(uint32_t)((n_stiles + 255) / 256), 256, 0, st>>>(d_scalars, sp.file_stream_start, F,
+                                                                                      (uint32_t*)c->stile_file.p, n_stiles);
+                const size_t ssm = staged_smem_bytes(B);
+                const uint32_t sgrid = (uint32_t)std::min<uint64_t>(n_stiles, (uint64_t)c->sm_count);
 #define GRMKM_SCATTER(KT)                                                                                       \
     do {                                                                                                        \
         CU_TRY(c, cudaFuncSetAttribute(k_scatter<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));  \
         k_scatter<KT><<<sgrid, kStThreads, ssm, st>>>(sp);                                                      \
     } while (0)
-            switch (c->cfg.k) {
-                case 31: GRMKM_SCATTER(31); break;
-                case 21: GRMKM_SCATTER(21); break;
-                case 15: GRMKM_SCATTER(15); break;
-                default: GRMKM_SCATTER(0); break;
-            }
+                switch (c->cfg.k) {
+                    case 31: GRMKM_SCATTER(31); break;
+                    case 21: GRMKM_SCATTER(21); break;
+                    case 15: GRMKM_SCATTER(15); break;
+                    default: GRMKM_SCATTER(0); break;
+                }
 #undef GRMKM_SCATTER
-            L.n += 2;
-        } else {
-            k_extract<1><<<egrid, kExtractThreads, 0, st>>>(ep);
-            L.n++;
+                L.n += 2;
+            } else {
+                k_extract<1><<<egrid, kExtractThreads, 0, st>>>(ep);
+                L.n++;
+            }
+            CU_TRY(c, cudaGetLastError());
         }
         // bucket b = records[begin[b], end[b]): begin = offsets, end = the cursors (clamped to the region)
         k_finish_regions<<<1, 1024, 0, st>>>((const unsigned long long*)c->offsets.p, (unsigned long long*)c->hist.p, B, cap,
@@ -750,7 +810,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
     grmkm_stats& s = c->stats;
     s.n_input_bytes = P.in_bytes;
     s.n_records = sc[S_N_RECORDS];
-    s.n_bases = sc[S_STREAM_LEN] - sc[S_N_RECORDS];
+    s.n_bases = sc[S_STREAM_TOTAL] - sc[S_N_RECORDS];
     s.n_windows = sc[S_N_WINDOWS];
     s.n_kmers = U;
     s.n_distinct = sc[S_N_DISTINCT];

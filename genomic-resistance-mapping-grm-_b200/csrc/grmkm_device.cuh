@@ -30,6 +30,7 @@ enum Scalar : int {
     S_N_SOLID,          // records surviving the abundance filter
     S_WORK,             // local-sort overflow flag
     S_OVERFLOW,         // a bucket region of the over-provisioned scatter was too small
+    S_STREAM_TOTAL,     // packed-stream entries summed over the batches of a build
     S_COUNT
 };
 

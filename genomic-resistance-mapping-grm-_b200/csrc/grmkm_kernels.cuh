@@ -174,7 +174,7 @@ __global__ void k_scan_blocks(const Sum* __restrict__ bsum, uint32_t n_blocks, u
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) { scalars[S_STREAM_LEN] = s_pos; file_stream_start[n_files] = s_pos; }
+    if (threadIdx.x == 0) { scalars[S_STREAM_LEN] = s_pos; scalars[S_STREAM_TOTAL] += s_pos; file_stream_start[n_files] = s_pos; }
 }
 
 // per-tile incoming state and stream position

@@ -186,6 +186,25 @@ def test_rebuild_reuses_context(gpu):
             assert np.array_equal(b.kmers(), ref.kmers) and np.array_equal(b.matrix(), ref.matrix)
 
 
+def test_pipelined_host_batches(gpu, monkeypatch):
+    """Host inputs are staged in batches whose H2D copy overlaps the previous batch's kernels; a tiny batch
+    size forces many batches (and both staging halves to be reused) on a small input."""
+    monkeypatch.setenv("GRMKM_BATCH_BYTES", "3000")
+    rng = np.random.default_rng(41)
+    shared = [inputs.rand_seq(rng, 4000), inputs.rand_seq(rng, 900)]
+    genomes = [[inputs.fasta(rng, n_records=3, shared=shared, max_len=2500), inputs.fasta(rng, shared=shared, max_len=700)]
+               for _ in range(23)]
+    genomes[5] = [b""]
+    genomes[9] = [inputs.fasta(rng, n_records=6, min_len=3000, max_len=9000)]         # larger than a batch
+    st = check(genomes, 31, keep_singletons=True)
+    assert st["h2d_bytes"] == sum(len(f) for g in genomes for f in g)
+    check(genomes, 15, keep_singletons=False)
+    from grm_b200 import native
+    check(genomes, 21, keep_singletons=True, flags=native.FLAG_EXACT_OFFSETS)       # single-batch fallback path
+    fq = [[inputs.fastq(rng, shared[0], n_reads=120, read_len=70)] for _ in range(9)]
+    check(fq, 21, min_abundance=2, keep_singletons=True, kind=1)
+
+
 def test_result_host_is_the_same_result(gpu):
     from grm_b200.builder import KmerMatrixBuilder
     rng = np.random.default_rng(31)
