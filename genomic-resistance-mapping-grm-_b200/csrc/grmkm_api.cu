@@ -157,7 +157,7 @@ int read_file(grmkm_ctx* c, const char* path, std::vector<uint8_t>& out) {
 struct Plan {
     uint32_t F = 0, G = 0, W = 0;
     uint64_t n_tiles = 0, n_sblk = 0, max_stream = 0, n_groups_max = 0, in_bytes = 0;
-    uint32_t bucket_bits = 0, row_bits = 0, slots = 0;
+    uint32_t bucket_bits = 0, row_bits = 0, slots = 0, sub_bits = 0;
     size_t agg_smem = 0;
 };
 
@@ -486,6 +486,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
     P.bucket_bits = std::max(P.bucket_bits, P.row_bits);
     if (P.bucket_bits > 15) return fail(c, GRMKM_E_UNSUPPORTED, "bucket_bits > 15");
     c->cur_bucket_bits = P.bucket_bits;
+    if (const char* sbv = getenv("GRMKM_SUB_BITS")) P.sub_bits = (uint32_t)std::min(3, std::max(0, atoi(sbv)));
     const uint32_t B = 1u << P.bucket_bits;
 
     ENSURE(c, c->scalars, S_COUNT * 8);
@@ -573,6 +574,8 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
     const bool staged = B <= (uint32_t)kStMaxBuckets && !(c->cfg.flags & GRMKM_FLAG_SIMPLE_SCATTER);
     const bool try_regions = staged && !(c->cfg.flags & GRMKM_FLAG_EXACT_OFFSETS);
     const uint32_t agrid = std::min<uint32_t>(B, (uint32_t)c->sm_count);
+    const uint32_t VB = B << P.sub_bits;            // virtual buckets of the column aggregate
+    const uint32_t vgrid = std::min<uint32_t>(VB, (uint32_t)c->sm_count);
     uint64_t sc[S_COUNT];
     uint64_t ucap = 0;
     for (int pass = try_regions ? 0 : 1; pass < 2; ++pass) {
@@ -731,25 +734,25 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         // ---- aggregate (dsk2kover): retry with a larger output if the first guess was too small
         ucap = std::min<uint64_t>(P.max_stream, std::max<uint64_t>(1 << 16, P.max_stream / 4));
         ucap = std::min<uint64_t>(ucap, 0xFFFFFFFFULL);
-        ENSURE(c, c->bbase, (size_t)B * 8);
-        ENSURE(c, c->bcounts, (size_t)B * 8);
+        ENSURE(c, c->bbase, (size_t)VB * 8);
+        ENSURE(c, c->bcounts, (size_t)VB * 8);
         for (int attempt = 0; attempt < 2; ++attempt) {
             ENSURE(c, c->ukeys, ucap * 8);
             ENSURE(c, c->uwords, (size_t)ucap * P.W * 8);
             AggParams2 ap{};
             ap.records = agg_records; ap.begin = agg_begin; ap.end = agg_end; ap.bucket_bits = P.bucket_bits;
             ap.row_bits = P.row_bits; ap.n_words = P.W; ap.slots = P.slots;
-            ap.keep_singletons = c->cfg.keep_singletons; ap.init_depth = 0;
+            ap.keep_singletons = c->cfg.keep_singletons; ap.sub_bits = P.sub_bits;
             ap.out_keys = (unsigned long long*)c->ukeys.p; ap.out_words = (unsigned long long*)c->uwords.p;
             ap.cap = ucap; ap.scalars = (unsigned long long*)d_scalars;
             ap.bucket_base = (unsigned long long*)c->bbase.p; ap.bucket_count = (unsigned long long*)c->bcounts.p;
             ap.b_begin = 0; ap.b_end = B;
             if (mode == 0) {
                 CU_TRY(c, cudaFuncSetAttribute(k_aggregate_cols<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.agg_smem));
-                k_aggregate_cols<0><<<agrid, kAggThreads, P.agg_smem, st>>>(ap);
+                k_aggregate_cols<0><<<vgrid, kAggThreads, P.agg_smem, st>>>(ap);
             } else {
                 CU_TRY(c, cudaFuncSetAttribute(k_aggregate_cols<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.agg_smem));
-                k_aggregate_cols<1><<<agrid, kAggThreads, P.agg_smem, st>>>(ap);
+                k_aggregate_cols<1><<<vgrid, kAggThreads, P.agg_smem, st>>>(ap);
             }
             L.n++;
             CU_TRY(c, cudaGetLastError());
@@ -776,22 +779,22 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         int r = sort_and_gather(c, U, P.W, ucap, 2 * c->cfg.k, false, L);
         if (r) return r;
     } else {
-        ENSURE(c, c->offsets2, (size_t)(B + 1) * 8);
+        ENSURE(c, c->offsets2, (size_t)(VB + 1) * 8);
         ENSURE(c, c->kmers, U * 8);
         ENSURE(c, c->matrix, (size_t)U * P.W * 8);
-        k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->bcounts.p, (unsigned long long*)c->offsets2.p, B,
+        k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->bcounts.p, (unsigned long long*)c->offsets2.p, VB,
                                              d_scalars, S_N_SOLID, 1);
         if (U) {
-            k_gather_buckets<<<std::min<uint32_t>(B, (uint32_t)c->sm_count * 8), 256, 0, st>>>(
+            k_gather_buckets<<<std::min<uint32_t>(VB, (uint32_t)c->sm_count * 8), 256, 0, st>>>(
                 (const unsigned long long*)c->ukeys.p, (const unsigned long long*)c->uwords.p, ucap,
-                (const unsigned long long*)c->bbase.p, (const unsigned long long*)c->offsets2.p, B, P.W, U,
+                (const unsigned long long*)c->bbase.p, (const unsigned long long*)c->offsets2.p, VB, P.W, U,
                 (unsigned long long*)c->kmers.p, (unsigned long long*)c->matrix.p, U);
         }
         L.n += 2;
         CU_TRY(c, cudaGetLastError());
         if (mode == 1) {
-            h_off.resize(B + 1);
-            CU_TRY(c, cudaMemcpyAsync(h_off.data(), c->offsets2.p, (size_t)(B + 1) * 8, cudaMemcpyDeviceToHost, st));
+            h_off.resize(VB + 1);
+            CU_TRY(c, cudaMemcpyAsync(h_off.data(), c->offsets2.p, (size_t)(VB + 1) * 8, cudaMemcpyDeviceToHost, st));
         }
     }
     if (c->ev_ok) cudaEventRecord(c->ev[T_SORT], st);
@@ -804,7 +807,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         c->part_ranks = n_ranges;
         c->part_counts.resize(n_ranges);
         for (uint32_t r = 0; r < n_ranges; ++r)
-            c->part_counts[r] = h_off[(uint64_t)B * (r + 1) / n_ranges] - h_off[(uint64_t)B * r / n_ranges];
+            c->part_counts[r] = h_off[((uint64_t)B * (r + 1) / n_ranges) << P.sub_bits] - h_off[((uint64_t)B * r / n_ranges) << P.sub_bits];
         c->part_total = U; c->part_cap = U; c->part_words = P.W;
     }
     grmkm_stats& s = c->stats;
@@ -1082,7 +1085,7 @@ int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
     CU_TRY(c, cudaGetLastError());
     if (c->ev_ok) cudaEventRecord(c->ev[T_SCATTER], st);
     ap.bucket_bits = mb; ap.row_bits = 0; ap.n_words = W_total; ap.slots = slots;
-    ap.keep_singletons = c->cfg.keep_singletons; ap.init_depth = 0;
+    ap.keep_singletons = c->cfg.keep_singletons; ap.sub_bits = 0;
     ap.out_keys = (unsigned long long*)c->ukeys.p; ap.out_words = (unsigned long long*)c->uwords.p;
     ap.cap = ucap; ap.scalars = (unsigned long long*)d_scalars; ap.parts = parts; ap.bounds = d_bounds;
     ap.bucket_base = (unsigned long long*)c->bbase.p; ap.bucket_count = (unsigned long long*)c->bcounts.p;

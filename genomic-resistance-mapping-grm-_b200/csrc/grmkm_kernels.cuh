@@ -978,14 +978,15 @@ struct AggParams2 {
     const unsigned long long* records;   // MODE 0/1: (hash << row_bits) | row;  MODE 3: refs (word offset << 8) | source
     const unsigned long long* begin;     // [B]
     const unsigned long long* end;       // [B]
-    uint32_t bucket_bits, row_bits, n_words, slots, keep_singletons, init_depth;
+    uint32_t bucket_bits, row_bits, n_words, slots, keep_singletons;
+    uint32_t sub_bits;                   // every bucket is aggregated as 2^sub_bits key sub-ranges (virtual buckets), one CTA pass each
     unsigned long long* out_keys;        // [cap]   bucket chunks, at bucket_base[b]
     unsigned long long* out_words;       // [n_words][cap]
     unsigned long long cap;
     unsigned long long* scalars;
     unsigned long long* bucket_base;     // [B] where the bucket's chunk starts in out_*
     unsigned long long* bucket_count;    // [B] columns the bucket emitted
-    uint32_t b_begin, b_end;             // bucket_base / bucket_count are indexed by b - b_begin
+    uint32_t b_begin, b_end;             // bucket_base / bucket_count are indexed by (virtual bucket) - (b_begin << sub_bits)
     // MODE 3: partial columns [hash, words...] of n_src sources, each list ascending by hash; the entries of
     // bucket b in source s are bounds[s * (b_end - b_begin + 1) + (b - b_begin)] .. [.. + 1]
     const unsigned long long* parts;
@@ -1177,7 +1178,13 @@ k_aggregate_cols(const AggParams2 p) {
     const uint32_t chunk = (t.total + kAggThreads - 1) / kAggThreads;
     const uint32_t lo = min(threadIdx.x * chunk, t.total), hi = min(lo + chunk, t.total);
 
-    for (uint32_t b = p.b_begin + blockIdx.x; b < p.b_end; b += gridDim.x) {
+    // A virtual bucket = bucket b restricted to the key sub-range `sub` of 2^sub_bits: the scatter can then use
+    // 2^sub_bits fewer buckets (longer runs per tile) than the table size demands.  The CTAs of one bucket's
+    // sub-ranges have adjacent block indices, run at the same time and share the bucket's records through L2.
+    const uint32_t sb = p.sub_bits;
+    const uint32_t vb_base = p.b_begin << sb;
+    for (uint32_t vb = vb_base + blockIdx.x; vb < (p.b_end << sb); vb += gridDim.x) {
+        const uint32_t b = vb >> sb, sub = vb & ((1u << sb) - 1u);
         uint32_t n = 0;
         const unsigned long long* recs = nullptr;
         if (MODE == 3) {
@@ -1189,16 +1196,13 @@ k_aggregate_cols(const AggParams2 p) {
             n = rbeg < rend ? (uint32_t)(rend - rbeg) : 0u;
             recs = p.records + rbeg;
         }
-        if (n == 0) { if (threadIdx.x == 0) { p.bucket_base[b - p.b_begin] = 0; p.bucket_count[b - p.b_begin] = 0; } continue; }
-        // phase 0: the whole bucket in one table (when init_depth == 0); on overflow, or when sub-ranges are planned:
-        // phase 1 counts over the sub-ranges, phase 2 emits them in ascending order
-        uint32_t phase = p.init_depth ? 1u : 0u;
+        if (n == 0) { if (threadIdx.x == 0) { p.bucket_base[vb - vb_base] = 0; p.bucket_count[vb - vb_base] = 0; } continue; }
+        // phase 0: the whole (virtual) bucket in one table; on overflow phase 1 counts over its key sub-ranges and
+        // phase 2 emits them in ascending order
+        uint32_t phase = 0;
         uint32_t bucket_total = 0, emitted = 0, bucket_occ = 0, splits = 0;
         __syncthreads();
-        if (threadIdx.x == 0) {
-            if (phase == 0) { s_sp = 1; s_depth[0] = 0; s_idx[0] = 0; }
-            else { s_sp = 0; for (uint32_t r = (1u << p.init_depth); r-- > 0;) { s_depth[s_sp] = p.init_depth; s_idx[s_sp] = r; s_sp++; } }
-        }
+        if (threadIdx.x == 0) { s_sp = 1; s_depth[0] = sb; s_idx[0] = sub; }
         while (true) {
             __syncthreads();
             if (s_sp == 0) {
@@ -1208,8 +1212,8 @@ k_aggregate_cols(const AggParams2 p) {
                 if (threadIdx.x == 0) {
                     s_base = atomicAdd(&p.scalars[S_U_NEEDED], (unsigned long long)bucket_total);
                     s_sp = 0;
-                    const uint32_t d0 = p.init_depth ? p.init_depth : 1u;
-                    for (uint32_t r = (1u << d0); r-- > 0;) { s_depth[s_sp] = d0; s_idx[s_sp] = r; s_sp++; }
+                    s_depth[s_sp] = sb + 1; s_idx[s_sp] = 2ULL * sub + 1; s_sp++;
+                    s_depth[s_sp] = sb + 1; s_idx[s_sp] = 2ULL * sub; s_sp++;
                 }
                 phase = 2;
                 continue;
@@ -1233,8 +1237,8 @@ k_aggregate_cols(const AggParams2 p) {
                 // split this key range in two, lower half first (terminates: a range of one key needs one slot)
                 if (threadIdx.x == 0) {
                     if (phase == 0) {
-                        s_depth[s_sp] = 1; s_idx[s_sp] = 1; s_sp++;
-                        s_depth[s_sp] = 1; s_idx[s_sp] = 0; s_sp++;
+                        s_depth[s_sp] = sb + 1; s_idx[s_sp] = 2ULL * sub + 1; s_sp++;
+                        s_depth[s_sp] = sb + 1; s_idx[s_sp] = 2ULL * sub; s_sp++;
                     } else {
                         s_depth[s_sp] = depth + 1; s_idx[s_sp] = ridx * 2 + 1; s_sp++;
                         s_depth[s_sp] = depth + 1; s_idx[s_sp] = ridx * 2; s_sp++;
@@ -1259,8 +1263,8 @@ k_aggregate_cols(const AggParams2 p) {
             emitted += total_kept;
         }
         if (threadIdx.x == 0) {
-            p.bucket_base[b - p.b_begin] = s_base;
-            p.bucket_count[b - p.b_begin] = bucket_total;
+            p.bucket_base[vb - vb_base] = s_base;
+            p.bucket_count[vb - vb_base] = bucket_total;
             atomicAdd(&p.scalars[S_N_DISTINCT], (unsigned long long)bucket_occ);
             if (splits) atomicAdd(&p.scalars[S_N_SPLITS], (unsigned long long)splits);
         }
