@@ -2,6 +2,7 @@
 // One context = one GPU.  No CPU fallback: without a device grmkm_create fails.
 #include "../../include/grmkm.h"
 #include "grmkm_kernels.cuh"
+#include "grmkm_units.cuh"
 #include "grmkm_synth.cuh"
 
 #include <zlib.h>
@@ -35,7 +36,7 @@ struct Input {
 
 constexpr uint64_t kBatchBytes = 32ull << 20;      // text per pipelined H2D batch (GRMKM_BATCH_BYTES overrides, for tests)
 
-enum Stage { T_START = 0, T_H2D, T_PARSE, T_PACK, T_COUNT, T_SCATTER, T_ABUND, T_AGG, T_SORT, T_N };
+enum Stage { T_START = 0, T_H2D, T_PARSE, T_PACK, T_COUNT, T_BOUNDS, T_SCATTER, T_ABUND, T_DEDUPE, T_EXPAND, T_AGG, T_SORT, T_N };
 
 }  // namespace
 
@@ -53,7 +54,7 @@ struct grmkm_ctx {
     // device buffers (grow-only, reused across builds)
     DevBuf in, files, hdr0, tsum, tile_file, tile_state, tile_pos, bsum, bstate, bpos, fss, codes, valid, hist,
         offsets, offsets2, bcounts, records, records2, ukeys, uwords, skeys, sidx_a, sidx_b, shist, kmers, matrix,
-        scalars, fmt, synth, owner_start, refs, spart, stile_file, bbase;
+        scalars, fmt, synth, owner_start, refs, spart, stile_file, bbase, masks, units, ucur, ubeg, wu, wide;
     size_t device_bytes = 0;
 
     cudaEvent_t ev[T_N]{};
@@ -361,7 +362,8 @@ void grmkm_destroy(grmkm_ctx* c) {
     DevBuf* all[] = {&c->in, &c->files, &c->hdr0, &c->tsum, &c->tile_file, &c->tile_state, &c->tile_pos, &c->bsum,
                      &c->bstate, &c->bpos, &c->fss, &c->codes, &c->valid, &c->hist, &c->offsets, &c->offsets2,
                      &c->bcounts, &c->records, &c->records2, &c->ukeys, &c->uwords, &c->skeys, &c->sidx_a, &c->sidx_b,
-                     &c->shist, &c->kmers, &c->matrix, &c->scalars, &c->fmt, &c->synth, &c->owner_start, &c->refs, &c->spart, &c->stile_file, &c->bbase};
+                     &c->shist, &c->kmers, &c->matrix, &c->scalars, &c->fmt, &c->synth, &c->owner_start, &c->refs, &c->spart, &c->stile_file, &c->bbase,
+                     &c->masks, &c->units, &c->ucur, &c->ubeg, &c->wu, &c->wide};
     for (DevBuf* b : all) release(c, *b);
     if (c->ev_ok) for (int i = 0; i < T_N; ++i) cudaEventDestroy(c->ev[i]);
     if (c->host_res) cudaFreeHost(c->host_res);
@@ -572,6 +574,24 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
     // without a count pass; if a region overflows (heavily skewed k-mer spectrum) pass 1 redoes the
     // scatter with exact offsets from a count pass.
     const bool staged = B <= (uint32_t)kStMaxBuckets && !(c->cfg.flags & GRMKM_FLAG_SIMPLE_SCATTER);
+    // ---- unit (super-k-mer) path: contigs and reads without an abundance filter (grmkm_units.cuh)
+    const bool use_units = staged && c->cfg.min_abundance <= 1 && !(c->cfg.flags & GRMKM_FLAG_KMER_RECORDS);
+    const UnitGeom ug = unit_geom(c->cfg.k);
+    const uint32_t wbits = std::max(1u, ceil_log2(P.W));
+    uint32_t MB = (uint32_t)c->sm_count;
+    if (use_units) {
+        // distinct (unit, 64-genome block) entries of a bucket should fit the dedupe table about once
+        std::vector<uint64_t> row_bytes(std::max(P.G, 1u), 0);
+        for (const Input& in : c->inputs) if (in.row < P.G) row_bytes[in.row] += in.len;
+        const uint64_t max_row = *std::max_element(row_bytes.begin(), row_bytes.end());
+        const uint64_t entries = (max_row * 19 / 10) * 2 / (ug.w + 1) * 13 / 10 * P.W;
+        const uint64_t per_wave = (uint64_t)kUdSlots * 6 / 10 * c->sm_count;
+        const uint64_t waves = std::max<uint64_t>(1, (entries + per_wave - 1) / per_wave);
+        MB = (uint32_t)std::min<uint64_t>(kUsMaxBuckets, waves * c->sm_count);
+        if (const char* ub = getenv("GRMKM_UNIT_BUCKETS")) MB = (uint32_t)std::min(kUsMaxBuckets, std::max(1, atoi(ub)));
+        ENSURE(c, c->ucur, (size_t)MB * 8);
+        ENSURE(c, c->ubeg, (size_t)(MB + 1) * 8);
+    }
     const bool try_regions = staged && !(c->cfg.flags & GRMKM_FLAG_EXACT_OFFSETS);
     const uint32_t agrid = std::min<uint32_t>(B, (uint32_t)c->sm_count);
     const uint32_t VB = B << P.sub_bits;            // virtual buckets of the column aggregate
@@ -583,7 +603,16 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         const std::vector<Batch> batches = make_batches(regions && any_host);
         const bool pipelined = batches.size() > 1;
         uint64_t cap = 0;
-        if (regions) {
+        if (use_units) {
+            if (regions) {
+                const double est_units = (double)P.max_stream * 2.0 / (ug.w + 1) * 1.15;
+                cap = (uint64_t)(est_units / MB * 1.25) + 4096;
+                cap = (cap + 15) & ~15ULL;
+                ENSURE(c, c->units, ((uint64_t)MB * cap + kUsStage) * 16);
+            } else {
+                ENSURE(c, c->units, (P.max_stream + kUsStage) * 16);
+            }
+        } else if (regions) {
             cap = (uint64_t)((double)P.max_stream / B * 1.25) + 2048;
             cap = (cap + 15) & ~15ULL;
             ENSURE(c, c->records, ((uint64_t)B * cap + kStTile) * 8);
@@ -605,12 +634,16 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
             CU_TRY(c, cudaMemcpyAsync(d_scalars, zeros, S_COUNT * 8, cudaMemcpyHostToDevice, st));
         }
         if (regions) {
-            k_init_regions<<<(B + 1 + 255) / 256, 256, 0, st>>>((unsigned long long*)c->offsets.p,
-                                                                (unsigned long long*)c->hist.p, B, cap);
+            if (use_units)
+                k_init_regions<<<(MB + 1 + 255) / 256, 256, 0, st>>>((unsigned long long*)c->ubeg.p,
+                                                                     (unsigned long long*)c->ucur.p, MB, cap);
+            else
+                k_init_regions<<<(B + 1 + 255) / 256, 256, 0, st>>>((unsigned long long*)c->offsets.p,
+                                                                    (unsigned long long*)c->hist.p, B, cap);
             L.n++;
         }
         if (pipelined && c->ev_ok)
-            for (int e : {T_H2D, T_PARSE, T_PACK, T_COUNT}) cudaEventRecord(c->ev[e], st);   // stages interleave: only "scatter" is timed
+            for (int e : {T_H2D, T_PARSE, T_PACK, T_COUNT, T_BOUNDS}) cudaEventRecord(c->ev[e], st);   // stages interleave: only "scatter" is timed
         h2d = 0;
         for (size_t bi = 0; bi < batches.size(); ++bi) {
             const Batch& bt = batches[bi];
@@ -635,6 +668,52 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
             const uint32_t F = bt.f1 - bt.f0;
             const uint64_t n_groups_max = bt.bytes / 32 + 2;
             const uint64_t n_stiles = (n_groups_max + (kStTile / 32) - 1) / (kStTile / 32);
+            if (use_units) {
+                ENSURE(c, c->masks, n_groups_max * 8);
+                const uint64_t n_utiles = (n_groups_max + kUsTileGroups - 1) / kUsTileGroups;
+                ENSURE(c, c->stile_file, n_utiles * 4);
+                if (!pipelined && c->ev_ok) cudaEventRecord(c->ev[T_COUNT], st);
+                const uint32_t bgrid = (uint32_t)((n_groups_max + 255) / 256);
+#define GRMKM_BOUNDS(WW)                                                                                        \
+    k_unit_bounds<WW><<<bgrid, 256, 0, st>>>((const unsigned long long*)c->codes.p, (const uint32_t*)c->valid.p, d_scalars, \
+                                             ug.k, ug.m, (uint2*)c->masks.p)
+                switch (ug.w) {
+                    case 21: GRMKM_BOUNDS(21); break;
+                    case 13: GRMKM_BOUNDS(13); break;
+                    case 7: GRMKM_BOUNDS(7); break;
+                    case 4: GRMKM_BOUNDS(4); break;
+                    case 2: GRMKM_BOUNDS(2); break;
+                    default: GRMKM_BOUNDS(1); break;
+                }
+#undef GRMKM_BOUNDS
+                k_stream_tile_files<<<(uint32_t)((n_utiles + 255) / 256), 256, 0, st>>>(
+                    d_scalars, (const uint64_t*)c->fss.p, F, (uint32_t*)c->stile_file.p, n_utiles, (uint64_t)kUsTileGroups * 32);
+                L.n += 2;
+                CU_TRY(c, cudaGetLastError());
+                if (!pipelined && c->ev_ok) cudaEventRecord(c->ev[T_BOUNDS], st);
+                UnitScatterParams up{};
+                up.codes = (const unsigned long long*)c->codes.p; up.masks = (const uint2*)c->masks.p; up.scalars = d_scalars;
+                up.file_stream_start = (const uint64_t*)c->fss.p; up.files = d_files; up.tile_file = (const uint32_t*)c->stile_file.p;
+                up.n_files = F; up.k = ug.k; up.lmax = ug.lmax; up.n_buckets = MB;
+                up.cursors = (unsigned long long*)c->ucur.p; up.units = (uint4*)c->units.p; up.cap = cap;
+                up.dump = (uint64_t)MB * cap; up.overflow = (unsigned long long*)(d_scalars + S_OVERFLOW);
+                up.n_windows = (unsigned long long*)(d_scalars + S_N_WINDOWS);
+                const size_t usm = unit_scatter_smem(MB);
+                const uint32_t ugrid = (uint32_t)std::min<uint64_t>(n_utiles, (uint64_t)c->sm_count);
+                if (!regions) {
+                    CU_TRY(c, cudaMemsetAsync(c->ucur.p, 0, (size_t)MB * 8, st));
+                    CU_TRY(c, cudaFuncSetAttribute(k_units_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usm));
+                    k_units_scatter<true><<<ugrid, kUsThreads, usm, st>>>(up);
+                    k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->ucur.p, (unsigned long long*)c->ubeg.p, MB,
+                                                         d_scalars, S_N_UNITS, 1);
+                    L.n += 2;
+                }
+                CU_TRY(c, cudaFuncSetAttribute(k_units_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usm));
+                k_units_scatter<false><<<ugrid, kUsThreads, usm, st>>>(up);
+                L.n++;
+                CU_TRY(c, cudaGetLastError());
+                continue;
+            }
             ExtractParams ep{};
             ep.codes = (const unsigned long long*)c->codes.p;
             ep.valid = (const uint32_t*)c->valid.p;
@@ -661,7 +740,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
                 L.n += 2;
             }
             CU_TRY(c, cudaGetLastError());
-            if (!pipelined && c->ev_ok) cudaEventRecord(c->ev[T_COUNT], st);
+            if (!pipelined && c->ev_ok) { cudaEventRecord(c->ev[T_COUNT], st); cudaEventRecord(c->ev[T_BOUNDS], st); }
             if (staged) {
                 ENSURE(c, c->stile_file, n_stiles * 4);
                 ScatterParams sp{};
@@ -694,8 +773,12 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
             CU_TRY(c, cudaGetLastError());
         }
         // bucket b = records[begin[b], end[b]): begin = offsets, end = the cursors (clamped to the region)
-        k_finish_regions<<<1, 1024, 0, st>>>((const unsigned long long*)c->offsets.p, (unsigned long long*)c->hist.p, B, cap,
-                                             (unsigned long long*)d_scalars, S_N_WINDOWS);
+        if (use_units)
+            k_finish_unit_regions<<<1, 1024, 0, st>>>((const unsigned long long*)c->ubeg.p, (unsigned long long*)c->ucur.p, MB,
+                                                      cap, (unsigned long long*)d_scalars, S_N_UNITS);
+        else
+            k_finish_regions<<<1, 1024, 0, st>>>((const unsigned long long*)c->offsets.p, (unsigned long long*)c->hist.p, B, cap,
+                                                 (unsigned long long*)d_scalars, S_N_WINDOWS);
         L.n++;
         CU_TRY(c, cudaGetLastError());
         if (c->ev_ok) cudaEventRecord(c->ev[T_SCATTER], st);
@@ -704,6 +787,60 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         const unsigned long long* agg_records = (const unsigned long long*)c->records.p;
         const unsigned long long* agg_begin = (const unsigned long long*)c->offsets.p;
         const unsigned long long* agg_end = (const unsigned long long*)c->hist.p;
+        bool unit_overflow = false;
+        if (use_units) {
+            if (c->ev_ok) cudaEventRecord(c->ev[T_ABUND], st);
+            // ---- dedupe: distinct (unit, block) entries; retried with a larger list if the guess was too small
+            uint64_t wcap = std::min<uint64_t>(P.max_stream, std::max<uint64_t>(1 << 16, P.max_stream / 16));
+            const size_t dsm = (size_t)kUdSlots * 24;
+            CU_TRY(c, cudaFuncSetAttribute(k_units_dedupe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+            CU_TRY(c, cudaFuncSetAttribute(k_units_expand<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_smem_bytes(B)));
+            CU_TRY(c, cudaFuncSetAttribute(k_units_expand<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_smem_bytes(B)));
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                ENSURE(c, c->wu, wcap * 24);
+                UnitDedupeParams dp{};
+                dp.units = (const uint4*)c->units.p; dp.begin = (const unsigned long long*)c->ubeg.p;
+                dp.end = (const unsigned long long*)c->ucur.p; dp.n_buckets = MB; dp.out = (unsigned long long*)c->wu.p;
+                dp.cap = wcap; dp.needed = (unsigned long long*)(d_scalars + S_WU_NEEDED);
+                k_units_dedupe<<<std::min<uint32_t>(MB, (uint32_t)c->sm_count), kUdThreads, dsm, st>>>(dp);
+                L.n++;
+                CU_TRY(c, cudaGetLastError());
+                if (c->ev_ok) cudaEventRecord(c->ev[T_DEDUPE], st);
+                // ---- expand, pass 1: wide records per hash bucket -> exact offsets
+                UnitExpandParams xp{};
+                xp.wu = (const unsigned long long*)c->wu.p; xp.n_ptr = (const unsigned long long*)(d_scalars + S_WU_NEEDED);
+                xp.cap = wcap; xp.k = c->cfg.k; xp.bucket_bits = P.bucket_bits; xp.wbits = wbits;
+                xp.cursors = (unsigned long long*)c->hist.p; xp.records = nullptr;
+                const uint32_t xgrid = (uint32_t)std::min<uint64_t>((wcap + kStThreads - 1) / kStThreads, (uint64_t)c->sm_count);
+                CU_TRY(c, cudaMemsetAsync(c->hist.p, 0, (size_t)B * 8, st));
+                k_units_expand<true><<<xgrid, kStThreads, staged_smem_bytes(B), st>>>(xp);
+                k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->hist.p, (unsigned long long*)c->offsets.p, B,
+                                                     d_scalars, S_N_WIDE, kCursorStride);
+                L.n += 2;
+                CU_TRY(c, cudaGetLastError());
+                CU_TRY(c, cudaMemcpyAsync(sc, d_scalars, sizeof sc, cudaMemcpyDeviceToHost, st));
+                CU_TRY(c, cudaStreamSynchronize(st));
+                if (regions && sc[S_OVERFLOW]) { unit_overflow = true; break; }
+                if (sc[S_WU_NEEDED] <= wcap) {
+                    // ---- expand, pass 2: scatter the wide records
+                    ENSURE(c, c->wide, (sc[S_N_WIDE] + 1) * 16);
+                    xp.records = (unsigned long long*)c->wide.p;
+                    k_units_expand<false><<<xgrid, kStThreads, staged_smem_bytes(B), st>>>(xp);
+                    L.n++;
+                    CU_TRY(c, cudaGetLastError());
+                    break;
+                }
+                if (attempt == 1) return fail(c, GRMKM_E_UNSUPPORTED, "unit list overflow after resize");
+                wcap = sc[S_WU_NEEDED];
+                const uint64_t zero2[2] = {0, 0};
+                CU_TRY(c, cudaMemcpyAsync(d_scalars + S_WU_NEEDED, zero2, 2 * 8, cudaMemcpyHostToDevice, st));
+            }
+            if (c->ev_ok) cudaEventRecord(c->ev[T_EXPAND], st);
+            if (unit_overflow) { c->stats.n_region_overflows++; continue; }
+            agg_records = (const unsigned long long*)c->wide.p;
+            agg_begin = (const unsigned long long*)c->offsets.p;
+            agg_end = agg_begin + 1;
+        }
         if (c->cfg.min_abundance > 1) {
             ENSURE(c, c->records2, c->records.cap);
             ENSURE(c, c->bcounts, (size_t)B * 8);
@@ -729,7 +866,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
             agg_begin = (const unsigned long long*)c->offsets2.p;
             agg_end = agg_begin + 1;
         }
-        if (c->ev_ok) cudaEventRecord(c->ev[T_ABUND], st);
+        if (!use_units && c->ev_ok) for (int e : {T_ABUND, T_DEDUPE, T_EXPAND}) cudaEventRecord(c->ev[e], st);
 
         // ---- aggregate (dsk2kover): retry with a larger output if the first guess was too small
         ucap = std::min<uint64_t>(P.max_stream, std::max<uint64_t>(1 << 16, P.max_stream / 4));
@@ -741,13 +878,19 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
             ENSURE(c, c->uwords, (size_t)ucap * P.W * 8);
             AggParams2 ap{};
             ap.records = agg_records; ap.begin = agg_begin; ap.end = agg_end; ap.bucket_bits = P.bucket_bits;
-            ap.row_bits = P.row_bits; ap.n_words = P.W; ap.slots = P.slots;
+            ap.row_bits = use_units ? wbits : P.row_bits; ap.n_words = P.W; ap.slots = P.slots;
             ap.keep_singletons = c->cfg.keep_singletons; ap.sub_bits = P.sub_bits;
             ap.out_keys = (unsigned long long*)c->ukeys.p; ap.out_words = (unsigned long long*)c->uwords.p;
             ap.cap = ucap; ap.scalars = (unsigned long long*)d_scalars;
             ap.bucket_base = (unsigned long long*)c->bbase.p; ap.bucket_count = (unsigned long long*)c->bcounts.p;
             ap.b_begin = 0; ap.b_end = B;
-            if (mode == 0) {
+            if (use_units && mode == 0) {
+                CU_TRY(c, cudaFuncSetAttribute(k_aggregate_cols<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.agg_smem));
+                k_aggregate_cols<4><<<vgrid, kAggThreads, P.agg_smem, st>>>(ap);
+            } else if (use_units) {
+                CU_TRY(c, cudaFuncSetAttribute(k_aggregate_cols<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.agg_smem));
+                k_aggregate_cols<5><<<vgrid, kAggThreads, P.agg_smem, st>>>(ap);
+            } else if (mode == 0) {
                 CU_TRY(c, cudaFuncSetAttribute(k_aggregate_cols<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.agg_smem));
                 k_aggregate_cols<0><<<vgrid, kAggThreads, P.agg_smem, st>>>(ap);
             } else {
@@ -822,10 +965,21 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
     s.h2d_bytes = h2d;
     s.device_bytes = c->device_bytes;
     s.n_splits = sc[S_N_SPLITS];
+    s.n_units = use_units ? sc[S_N_UNITS] : 0;
+    s.n_unit_entries = use_units ? sc[S_WU_NEEDED] : 0;
+    s.n_wide = use_units ? sc[S_N_WIDE] : 0;
+    s.n_unit_buckets = use_units ? MB : 0;
     if (c->ev_ok) {
-        float* t[] = {&c->times.h2d, &c->times.parse, &c->times.pack, &c->times.count, &c->times.scatter,
-                      &c->times.abundance, &c->times.aggregate, &c->times.sort};
-        for (int i = 1; i < T_N; ++i) cudaEventElapsedTime(t[i - 1], c->ev[i - 1], c->ev[i]);
+        float* t[] = {&c->times.h2d, &c->times.parse, &c->times.pack, &c->times.count, &c->times.bounds, &c->times.scatter,
+                      &c->times.abundance, &c->times.dedupe, &c->times.expand, &c->times.aggregate, &c->times.sort};
+        for (int i = 1; i < T_N; ++i) {
+            const cudaError_t te = cudaEventElapsedTime(t[i - 1], c->ev[i - 1], c->ev[i]);
+            if (te != cudaSuccess) {
+                cudaGetLastError();
+                if (getenv("GRMKM_DEBUG")) fprintf(stderr, "grmkm: stage event %d: %s\n", i, cudaGetErrorString(te));
+                *t[i - 1] = 0.f;
+            }
+        }
         cudaEventElapsedTime(&c->times.total, c->ev[T_START], c->ev[T_SORT]);
     }
     return GRMKM_OK;

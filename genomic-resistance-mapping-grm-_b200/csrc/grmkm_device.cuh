@@ -31,6 +31,9 @@ enum Scalar : int {
     S_WORK,             // local-sort overflow flag
     S_OVERFLOW,         // a bucket region of the over-provisioned scatter was too small
     S_STREAM_TOTAL,     // packed-stream entries summed over the batches of a build
+    S_N_UNITS,          // units (super-k-mers) scattered
+    S_WU_NEEDED,        // distinct (unit, 64-genome block) entries the dedupe produced
+    S_N_WIDE,           // wide records the expansion produced
     S_COUNT
 };
 

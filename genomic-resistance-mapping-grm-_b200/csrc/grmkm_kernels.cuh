@@ -1056,6 +1056,54 @@ __device__ __forceinline__ void agg_stream(const AggParams2& p, const AggTable& 
     }
 }
 
+// MODE 4 / 5: wide records [(hash << row_bits) | word index, presence word] (the unit path, grmkm_units.cuh)
+template <bool FILTER>
+__device__ __forceinline__ void agg_stream_wide(const AggParams2& p, const AggTable& t, const unsigned long long* __restrict__ recs,
+                                                uint32_t n, uint32_t key_bits, uint32_t depth, unsigned long long ridx,
+                                                volatile uint32_t* overflow) {
+    const uint32_t wbits = p.row_bits;
+    const uint32_t wmask = (1u << wbits) - 1u;
+    const uint32_t shift = 64 - key_bits + depth;
+    const uint32_t slots = t.slots, total = t.total;
+    unsigned long long* const keys = t.keys;
+    uint32_t* const w32 = t.w32;
+    const ulonglong2* const rec2 = reinterpret_cast<const ulonglong2*>(recs);
+    constexpr int kWideBatch = 4;
+    for (uint32_t base = threadIdx.x; base < n; base += kAggThreads * kWideBatch) {
+        ulonglong2 r[kWideBatch];
+#pragma unroll
+        for (int j = 0; j < kWideBatch; ++j) {
+            const uint32_t idx = base + j * kAggThreads;
+            r[j] = idx < n ? __ldcs(rec2 + idx) : make_ulonglong2(0ULL, 0ULL);
+        }
+        if (*overflow) break;
+#pragma unroll
+        for (int j = 0; j < kWideBatch; ++j) {
+            if (base + j * kAggThreads >= n) break;
+            const unsigned long long key = r[j].x >> wbits;
+            if (FILTER && ((key << (64 - key_bits)) >> (64 - depth)) != ridx) continue;
+            uint32_t slot = home_slot(key, shift, slots);
+            int probe = 0;
+            while (true) {
+                unsigned long long k0 = *(volatile unsigned long long*)&keys[slot];
+                if (k0 == key) break;
+                if (k0 == kEmptyKey) {
+                    k0 = atomicCAS(&keys[slot], kEmptyKey, key);
+                    if (k0 == kEmptyKey || k0 == key) break;
+                }
+                ++slot;
+                if (++probe >= kMaxProbe) { *overflow = 1; break; }
+            }
+            if (probe < kMaxProbe) {
+                const uint32_t wi = (uint32_t)r[j].x & wmask;
+                const uint32_t vlo = (uint32_t)r[j].y, vhi = (uint32_t)(r[j].y >> 32);
+                if (vlo) atomicOr(&w32[(2 * wi) * total + slot], vlo);
+                if (vhi) atomicOr(&w32[(2 * wi + 1) * total + slot], vhi);
+            }
+        }
+    }
+}
+
 // MODE 3: the bucket's entries are one contiguous range per source (the lists arrive sorted by hash)
 template <bool FILTER>
 __device__ __forceinline__ void agg_stream_parts(const AggParams2& p, const AggTable& t, uint32_t b, uint32_t key_bits,
@@ -1117,7 +1165,7 @@ __device__ __forceinline__ uint32_t agg_mark(const AggParams2& p, const AggTable
         uint8_t kf = 0;
         if (t.keys[i] != kEmptyKey) {
             occ++;
-            if (MODE == 1 || p.keep_singletons) kf = 1;
+            if (MODE == 1 || MODE == 5 || p.keep_singletons) kf = 1;
             else {
                 uint32_t pc = 0;
                 for (uint32_t h = 0; h < 2 * p.n_words; ++h) pc += __popc(t.w32[h * t.total + i]);
@@ -1153,7 +1201,7 @@ __device__ __forceinline__ void agg_emit(const AggParams2& p, const AggTable& t,
         const unsigned long long o = base + rank;
         if (o < p.cap) {
             const unsigned long long h = ((unsigned long long)b << key_bits) | (key & key_mask);
-            p.out_keys[o] = MODE == 1 ? h : kunhash(h);
+            p.out_keys[o] = (MODE == 1 || MODE == 5) ? h : kunhash(h);
             for (uint32_t w = 0; w < p.n_words; ++w)
                 p.out_words[w * p.cap + o] = ((unsigned long long)t.w32[(2 * w + 1) * t.total + i] << 32) | t.w32[2 * w * t.total + i];
         }
@@ -1194,7 +1242,7 @@ k_aggregate_cols(const AggParams2 p) {
         } else {
             const unsigned long long rbeg = p.begin[b], rend = p.end[b];
             n = rbeg < rend ? (uint32_t)(rend - rbeg) : 0u;
-            recs = p.records + rbeg;
+            recs = p.records + (MODE >= 4 ? 2 * rbeg : rbeg);
         }
         if (n == 0) { if (threadIdx.x == 0) { p.bucket_base[vb - vb_base] = 0; p.bucket_count[vb - vb_base] = 0; } continue; }
         // phase 0: the whole (virtual) bucket in one table; on overflow phase 1 counts over its key sub-ranges and
@@ -1228,6 +1276,9 @@ k_aggregate_cols(const AggParams2 p) {
             if (MODE == 3) {
                 if (depth == 0) agg_stream_parts<false>(p, t, b, key_bits, 0, 0, &s_overflow);
                 else agg_stream_parts<true>(p, t, b, key_bits, depth, ridx, &s_overflow);
+            } else if (MODE >= 4) {
+                if (depth == 0) agg_stream_wide<false>(p, t, recs, n, key_bits, 0, 0, &s_overflow);
+                else agg_stream_wide<true>(p, t, recs, n, key_bits, depth, ridx, &s_overflow);
             } else {
                 if (depth == 0) agg_stream<false>(p, t, recs, n, key_bits, 0, 0, &s_overflow);
                 else agg_stream<true>(p, t, recs, n, key_bits, depth, ridx, &s_overflow);

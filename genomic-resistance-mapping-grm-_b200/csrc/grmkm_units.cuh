@@ -1,0 +1,539 @@
+// grmkm_units.cuh -- the super-k-mer ("unit") path of the k-mer matrix build.
+//
+// The genomes Kover learns from belong to one species: most of every genome is shared with the others.  A
+// *unit* is a maximal run of consecutive valid k-mers of one record that have the same minimizer (smallest
+// hashed canonical m-mer), at most lmax k-mers long, stored as its L + k - 1 bases in the strand with the
+// smaller value.  Unit boundaries depend on the sequence only, so the same stretch of DNA yields the same
+// units in every genome, whatever its offset, contig layout or strand.  The pipeline is then
+//
+//   k_unit_bounds     packed stream -> per position "a unit starts here" / "a valid k-mer ends here" bits
+//   k_units_scatter   units (16 bytes each, ~11 k-mers at k = 31) -> buckets by a hash of the unit's content
+//   k_units_dedupe    per bucket: shared-memory table keyed by (content, 64-genome block) -> one presence word
+//   k_units_expand    every DISTINCT (unit, block) -> its k-mers -> records [hash, presence word] by hash range
+//   k_aggregate_cols  (grmkm_kernels.cuh, wide input) merges the words of equal k-mers into columns
+//
+// so the per-occurrence work is one table insert per ~11 k-mers, and the per-k-mer work is done once per
+// distinct unit instead of once per genome.  Unit boundaries only affect how much is shared, never the
+// result: every valid k-mer window lies in exactly one unit (checked through stats.n_windows).
+// Reference semantics are unchanged (multidsk / dsk2kover, kmer_count.py:28-37, kmer_pack.py:28-36).
+#pragma once
+#include "grmkm_kernels.cuh"
+
+namespace grmkm {
+
+// ---- geometry -------------------------------------------------------------------------------
+// unit = L k-mers (1 <= L <= lmax), nb = L + k - 1 <= 53 bases.
+//   lo = bases 0..28 (entry j at bits 2j) | (L - 1) << 58
+//   hi = bases 29..52                     | row << 48
+struct UnitGeom { uint32_t k, m, w, lmax; };
+
+__host__ __device__ inline UnitGeom unit_geom(uint32_t k) {
+    UnitGeom g;
+    g.k = k;
+    g.lmax = 54 - k < 32 ? 54 - k : 32;
+    const uint32_t mmin = k < 5 ? k : 5;
+    uint32_t wmax = k - mmin + 1;
+    if (wmax > g.lmax) wmax = g.lmax;
+    g.w = wmax >= 21 ? 21 : wmax >= 13 ? 13 : wmax >= 7 ? 7 : wmax >= 4 ? 4 : wmax >= 2 ? 2 : 1;
+    g.m = k - g.w + 1;       // k-mer = w consecutive m-mers
+    return g;
+}
+
+constexpr unsigned long long kUnitLoMask = (1ULL << 58) - 1;
+constexpr unsigned long long kUnitHiMask = (1ULL << 48) - 1;
+constexpr unsigned long long kUnitEmptyLo = ~0ULL;     // bit 63 of lo is always 0 (L - 1 <= 31)
+constexpr unsigned long long kUnitEmptyHi = ~0ULL;     // block field 0xFFFF never occurs
+constexpr uint32_t kMmerSeed = 0x5bd1e995u, kMmerMul = 0x9E3779B1u;
+
+__device__ __forceinline__ unsigned long long rev2_64(unsigned long long x) {
+    x = __brevll(x);
+    return ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
+}
+
+// hash of a unit's content (lo, hi without the row): bucket from the top half, table slot from the middle
+__device__ __forceinline__ unsigned long long unit_hash(unsigned long long lo, unsigned long long hik) {
+    unsigned long long h = (lo * kHashMul) ^ (hik * 0xC2B2AE3D27D4EB4FULL);
+    h ^= h >> 29;
+    return h * 0x94D049BB133111EBULL;
+}
+
+// ---- k_unit_bounds: per group of 32 stream entries, start mask and valid-k-mer mask ---------
+// Bit e of .y: the k-mer ENDING at entry e of the group is valid.  Bit e of .x: it is valid and it starts a
+// run (the previous k-mer is invalid or has another minimizer).  W = m-mers per k-mer (compile time: the
+// sliding minimum is two prefix/suffix sweeps over blocks of W, all in registers).
+template <int W>
+__global__ void __launch_bounds__(256)
+k_unit_bounds(const unsigned long long* __restrict__ codes, const uint32_t* __restrict__ valid,
+              const uint64_t* __restrict__ scalars, uint32_t k, uint32_t m, uint2* __restrict__ masks) {
+    const uint64_t n_groups = (scalars[S_STREAM_LEN] + 31) >> 5;
+    const uint64_t g = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (g >= n_groups) return;
+    const unsigned long long cur_c = codes[g];
+    const uint32_t cur_v = valid[g];
+    unsigned long long prev_c = 0; uint32_t prev_v = 0;
+    if (g > 0) { prev_c = codes[g - 1]; prev_v = valid[g - 1]; }
+    // smear the invalid entries over the k - 1 entries that follow them
+    unsigned long long s = ~((unsigned long long)prev_v | ((unsigned long long)cur_v << 32));
+    for (uint32_t c = 1; c < k;) { const uint32_t d = c < k - c ? c : k - c; s |= s << d; c += d; }
+    const uint32_t vk = ~(uint32_t)(s >> 32);
+    if (vk == 0) { masks[g] = make_uint2(0u, 0u); return; }
+    const uint32_t vk_before = (uint32_t)((s >> 31) & 1ULL) ^ 1u;      // the k-mer ending at the previous group's last entry
+    // 128-bit window: entry q of [previous group | my group] at bits 2q
+    const uint32_t x[4] = {(uint32_t)prev_c, (uint32_t)(prev_c >> 32), (uint32_t)cur_c, (uint32_t)(cur_c >> 32)};
+    const uint32_t r[5] = {rev2_32(x[3]), rev2_32(x[2]), rev2_32(x[1]), rev2_32(x[0]), 0u};   // digit p = entry 63 - p
+    const uint32_t S0 = 2 * (32 - k);
+    const unsigned long long Yl = S0 ? (prev_c >> S0) | (cur_c << (64 - S0)) : prev_c, Yh = cur_c >> S0;
+    const uint32_t y[5] = {(uint32_t)Yl, (uint32_t)(Yl >> 32), (uint32_t)Yh, (uint32_t)(Yh >> 32), 0u};
+    const uint32_t mmask = m >= 16 ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1u);
+    const uint32_t cm = 0xAAAAAAAAu & mmask;
+    // h[t] = hashed canonical m-mer ending at window entry 32 - W + t   (t = 0 .. 31 + W)
+    constexpr int N = 32 + W;
+    uint32_t h[N];
+#pragma unroll
+    for (int t = 0; t < N; ++t) {
+        const int fs = 2 * (31 + W - t), rs = 2 * t;
+        const uint32_t fw = __funnelshift_r(r[fs >> 5], r[(fs >> 5) + 1], fs & 31) & mmask;         // first base most significant
+        const uint32_t rc = (__funnelshift_r(y[rs >> 5], y[(rs >> 5) + 1], rs & 31) & mmask) ^ cm;  // reverse complement
+        h[t] = ((fw < rc ? fw : rc) ^ kMmerSeed) * kMmerMul;
+    }
+    // minimizer of the k-mer ending at entry j - 1 = min h[j .. j + W - 1]  (j = 0 .. 32)
+    uint32_t pre[N], suf[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) pre[i] = (i % W == 0) ? h[i] : min(pre[i - 1], h[i]);
+#pragma unroll
+    for (int i = N - 1; i >= 0; --i) suf[i] = (i % W == W - 1 || i == N - 1) ? h[i] : min(suf[i + 1], h[i]);
+    uint32_t changed = 0, prev_min = min(suf[0], pre[W - 1]);
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+        // a run ends when the minimum changes, or when an m-mer equal to it leaves on the left or enters on the
+        // right (the same rule read from either strand): a run is never longer than W <= lmax k-mers
+        const uint32_t mn = min(suf[e + 1], pre[e + W]);
+        changed |= (uint32_t)((mn != prev_min) | (h[e] == prev_min) | (h[e + W] == mn)) << e;
+        prev_min = mn;
+    }
+    const uint32_t before = (vk << 1) | vk_before;
+    masks[g] = make_uint2(vk & (~before | changed), vk);
+}
+
+// ---- k_units_scatter: units -> content-hash buckets ------------------------------------------
+// One tile = 1024 groups (32768 stream entries) per CTA iteration; a thread owns one group and holds up to
+// kUsMax of its units in registers per round (more units = more rounds, so any input is handled with bounded
+// shared memory).  Round: histogram with returning shared-memory atomics (the rank inside the bucket's run) ->
+// scan + ONE global reservation per (round, bucket) -> units to their sorted slot -> copy out in bucket runs.
+constexpr int kUsThreads = 1024;
+constexpr int kUsMax = 6;
+constexpr int kUsStage = kUsThreads * kUsMax;
+constexpr int kUsTileGroups = kUsThreads;
+constexpr int kUsMaxBuckets = 1024;
+
+struct UnitScatterParams {
+    const unsigned long long* codes;
+    const uint2* masks;
+    const uint64_t* scalars;
+    const uint64_t* file_stream_start;
+    const FileDesc* files;
+    const uint32_t* tile_file;          // file of the first entry of every tile
+    uint32_t n_files;
+    uint32_t k, lmax, n_buckets;
+    unsigned long long* cursors;        // [n_buckets]; COUNT: histogram
+    uint4* units;
+    unsigned long long cap;             // units per bucket region, 0 = exact offsets
+    unsigned long long dump;            // index of the dump area (kUsStage units)
+    unsigned long long* overflow;
+    unsigned long long* n_windows;
+};
+
+__host__ __device__ inline size_t unit_scatter_smem(uint32_t MB) {
+    return (size_t)kUsStage * 16 + (size_t)MB * 8 + (size_t)(kUsTileGroups + 3) * 8 + (size_t)MB * 8 + (size_t)kUsStage * 2;
+}
+
+__global__ void k_stream_tile_files(const uint64_t* __restrict__ scalars, const uint64_t* __restrict__ fss, uint32_t n_files,
+                                    uint32_t* __restrict__ tile_file, uint64_t max_tiles, uint64_t tile_entries) {
+    const uint64_t tile = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= max_tiles) return;
+    const uint64_t p0 = tile * tile_entries;
+    if (p0 >= scalars[S_STREAM_LEN]) return;
+    uint32_t lo = 0, hi = n_files - 1;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (fss[mid] <= p0) lo = mid; else hi = mid - 1;
+    }
+    tile_file[tile] = lo;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kUsThreads, 1)
+k_units_scatter(const UnitScatterParams p) {
+    extern __shared__ uint4 s_units[];                                   // [kUsStage] sorted units of the round
+    __shared__ uint32_t s_total;
+    __shared__ uint32_t s_warp[33];
+    const uint32_t MB = p.n_buckets;
+    unsigned long long* s_delta = reinterpret_cast<unsigned long long*>(s_units + kUsStage);   // [MB]
+    unsigned long long* s_codes = s_delta + MB;                          // [kUsTileGroups + 3], [0] = the group before the tile
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_codes + kUsTileGroups + 3);   // [MB]
+    uint32_t* s_off = s_cnt + MB;                                        // [MB]
+    uint16_t* s_b = reinterpret_cast<uint16_t*>(s_off + MB);             // [kUsStage]
+    const uint64_t stream_len = p.scalars[S_STREAM_LEN];
+    const uint64_t n_groups = (stream_len + 31) >> 5;
+    const uint64_t n_tiles = (n_groups + kUsTileGroups - 1) / kUsTileGroups;
+    const uint32_t k = p.k, lmax = p.lmax;
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t i = tid; i < MB; i += kUsThreads) s_cnt[i] = 0;
+    unsigned long long my_windows = 0;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t g0 = tile * kUsTileGroups, g = g0 + tid;
+        for (uint32_t i = tid; i < (uint32_t)kUsTileGroups + 3; i += kUsThreads) {
+            const uint64_t gi = g0 + i;      // group gi - 1
+            s_codes[i] = (gi >= 1 && gi - 1 < n_groups) ? p.codes[gi - 1] : 0ULL;
+        }
+        uint2 mk = make_uint2(0u, 0u), mk1 = make_uint2(0u, 0u);
+        if (g < n_groups) mk = p.masks[g];
+        if (g + 1 < n_groups) mk1 = p.masks[g + 1];
+        const uint32_t st = mk.x, vk = mk.y;
+        // natural breaks after a position: an invalid k-mer or the start of another run
+        const unsigned long long brk = (unsigned long long)(~vk | mk.x) | ((unsigned long long)(~mk1.y | mk1.x) << 32);
+        uint32_t rem = st;
+        uint32_t f = 0;
+        if (rem) {
+            f = p.tile_file[tile];
+            while (f + 1 < p.n_files && p.file_stream_start[f + 1] <= g * 32ULL) ++f;
+        }
+        __syncthreads();       // s_codes staged
+        bool more;
+        do {
+            unsigned long long ulo[kUsMax], uhi[kUsMax];
+            uint32_t ubr[kUsMax];
+            uint32_t n = 0;
+#pragma unroll
+            for (int j = 0; j < kUsMax; ++j) {
+                if (rem) {
+                    const uint32_t e = (uint32_t)__ffs(rem) - 1u;
+                    rem &= rem - 1u;
+                    const unsigned long long after = brk >> (e + 1);
+                    const uint32_t dist = after ? (uint32_t)__ffsll((long long)after) : 64u;
+                    const uint32_t L = dist < lmax ? dist : lmax;
+                    const uint32_t P = 32u * tid + e;            // tile-local entry where the first k-mer ends
+                    const uint32_t a = P + 32u - (k - 1u);       // first entry of the unit, counted from the group before the tile
+                    const uint32_t nb = L + k - 1u;
+                    const uint32_t wi = a >> 5, sh = 2u * (a & 31u);
+                    const unsigned long long w0 = s_codes[wi], w1 = s_codes[wi + 1], w2 = s_codes[wi + 2];
+                    unsigned long long Vlo = sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0;
+                    unsigned long long Vhi = sh ? (w1 >> sh) | (w2 << (64 - sh)) : w1;
+                    unsigned long long mlo, mhi;
+                    if (nb >= 32) { mlo = ~0ULL; mhi = (1ULL << (2 * nb - 64)) - 1ULL; }
+                    else { mlo = (1ULL << (2 * nb)) - 1ULL; mhi = 0ULL; }
+                    Vlo &= mlo; Vhi &= mhi;
+                    // the other strand: digits reversed and complemented
+                    const unsigned long long Fh = rev2_64(Vlo), Fl = rev2_64(Vhi);
+                    const uint32_t s2 = 128u - 2u * nb;
+                    unsigned long long Rlo, Rhi;
+                    if (s2 >= 64) { Rlo = Fh >> (s2 - 64); Rhi = 0ULL; }
+                    else { Rlo = (Fl >> s2) | (Fh << (64 - s2)); Rhi = Fh >> s2; }
+                    Rlo ^= 0xAAAAAAAAAAAAAAAAULL & mlo; Rhi ^= 0xAAAAAAAAAAAAAAAAULL & mhi;
+                    if (Rhi < Vhi || (Rhi == Vhi && Rlo < Vlo)) { Vlo = Rlo; Vhi = Rhi; }
+                    while (f + 1 < p.n_files && p.file_stream_start[f + 1] <= g0 * 32ULL + P) ++f;
+                    const unsigned long long lo = (Vlo & kUnitLoMask) | ((unsigned long long)(L - 1u) << 58);
+                    const unsigned long long hik = (Vlo >> 58) | (Vhi << 6);
+                    const uint32_t b = __umulhi((uint32_t)(unit_hash(lo, hik) >> 32), MB);
+                    const uint32_t rank = atomicAdd(&s_cnt[b], 1u);
+                    ulo[j] = lo;
+                    uhi[j] = hik | ((unsigned long long)p.files[f].row << 48);
+                    ubr[j] = b | (rank << 16);
+                    n = j + 1;
+                    my_windows += L;
+                }
+            }
+            __syncthreads();
+            // scan the round's histogram, reserve global space (thread t owns bucket t)
+            {
+                uint32_t cnt = 0;
+                if (tid < MB) { cnt = s_cnt[tid]; s_cnt[tid] = 0; }
+                unsigned long long gb = 0;
+                if (cnt) gb = atomicAdd(&p.cursors[tid], (unsigned long long)cnt);
+                if (!COUNT) {
+                    uint32_t total;
+                    const uint32_t off = block_excl_scan<kUsThreads>(cnt, s_warp, total);
+                    if (tid == 0) s_total = total;
+                    if (tid < MB) {
+                        s_off[tid] = off;
+                        if (cnt) {
+                            if (p.cap && gb + cnt > (unsigned long long)(tid + 1) * p.cap) {
+                                *p.overflow = 1ULL;
+                                s_delta[tid] = p.dump;
+                            } else {
+                                s_delta[tid] = gb - off;
+                            }
+                        }
+                    }
+                }
+            }
+            if (!COUNT) {
+                __syncthreads();
+#pragma unroll
+                for (int j = 0; j < kUsMax; ++j) {
+                    if ((uint32_t)j < n) {
+                        const uint32_t b = ubr[j] & 0xFFFFu;
+                        const uint32_t dst = s_off[b] + (ubr[j] >> 16);
+                        s_units[dst] = make_uint4((uint32_t)ulo[j], (uint32_t)(ulo[j] >> 32), (uint32_t)uhi[j], (uint32_t)(uhi[j] >> 32));
+                        s_b[dst] = (uint16_t)b;
+                    }
+                }
+                __syncthreads();
+                const uint32_t total = s_total;
+                for (uint32_t i = tid; i < total; i += kUsThreads) p.units[s_delta[s_b[i]] + i] = s_units[i];
+            }
+            more = __syncthreads_or(rem != 0u);
+        } while (more);
+    }
+    if (!COUNT) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) my_windows += __shfl_down_sync(0xffffffffu, my_windows, d);
+        if ((tid & 31u) == 0 && my_windows) atomicAdd(p.n_windows, my_windows);
+    }
+}
+
+// ---- k_units_dedupe: per bucket, distinct (unit content, 64-genome block) -> presence word --------
+constexpr int kUdThreads = 1024;
+constexpr int kUdSlotsLog2 = 13;
+constexpr int kUdSlots = 1 << kUdSlotsLog2;           // 8192 x 24 bytes = 192 KB
+constexpr int kUdLimit = kUdSlots * 3 / 4 - 2 * kUdThreads;
+
+struct UnitDedupeParams {
+    const uint4* units;
+    const unsigned long long* begin;     // [n_buckets]
+    const unsigned long long* end;       // [n_buckets]
+    uint32_t n_buckets;
+    unsigned long long* out;             // weighted units [lo, hi (row field = block), word]
+    unsigned long long cap;              // entries
+    unsigned long long* needed;          // scalar: entries produced (may exceed cap; the host retries)
+};
+
+__global__ void __launch_bounds__(kUdThreads, 1)
+k_units_dedupe(const UnitDedupeParams p) {
+    extern __shared__ unsigned long long s_tab[];
+    __shared__ uint32_t s_distinct;
+    __shared__ uint32_t s_warp[33];
+    __shared__ unsigned long long s_base;
+    unsigned long long* k_lo = s_tab;
+    unsigned long long* k_hi = s_tab + kUdSlots;
+    unsigned long long* wd = s_tab + 2 * kUdSlots;
+    const uint32_t tid = threadIdx.x;
+    constexpr uint32_t per = kUdSlots / kUdThreads;
+    for (uint32_t i = tid; i < (uint32_t)kUdSlots; i += kUdThreads) { k_lo[i] = kUnitEmptyLo; k_hi[i] = kUnitEmptyHi; wd[i] = 0ULL; }
+    if (tid == 0) s_distinct = 0;
+    __syncthreads();
+    // emit the table's entries and clear it (all inserts are complete when this is called)
+    auto flush = [&]() {
+        uint32_t cnt = 0;
+        for (uint32_t j = 0; j < per; ++j) cnt += k_lo[j * kUdThreads + tid] != kUnitEmptyLo;
+        uint32_t total;
+        uint32_t off = block_excl_scan<kUdThreads>(cnt, s_warp, total);
+        if (tid == 0) { s_base = total ? atomicAdd(p.needed, (unsigned long long)total) : 0ULL; s_distinct = 0; }
+        __syncthreads();
+        const unsigned long long base = s_base;
+        for (uint32_t j = 0; j < per; ++j) {
+            const uint32_t i = j * kUdThreads + tid;
+            const unsigned long long lo = k_lo[i];
+            if (lo != kUnitEmptyLo) {
+                const unsigned long long o = base + off++;
+                if (o < p.cap) { p.out[3 * o] = lo; p.out[3 * o + 1] = k_hi[i]; p.out[3 * o + 2] = wd[i]; }
+                k_lo[i] = kUnitEmptyLo; k_hi[i] = kUnitEmptyHi; wd[i] = 0ULL;
+            }
+        }
+        __syncthreads();
+    };
+    for (uint32_t b = blockIdx.x; b < p.n_buckets; b += gridDim.x) {
+        const unsigned long long rb = p.begin[b], re = p.end[b];
+        if (re <= rb) continue;
+        const unsigned long long n = re - rb;
+        const uint4* src = p.units + rb;
+        uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+        if (tid < n) nxt = __ldcs(src + tid);
+        for (unsigned long long base = 0; base < n; base += kUdThreads) {
+            const uint4 u = nxt;
+            const bool have = base + tid < n;
+            if (base + kUdThreads + tid < n) nxt = __ldcs(src + base + kUdThreads + tid);
+            // the previous batch is in the table; thread 0's view of s_distinct may miss that batch (<= 1024 keys),
+            // which the limit allows for
+            if (__syncthreads_or(tid == 0 && s_distinct > (uint32_t)kUdLimit)) flush();
+            if (have) {
+                const unsigned long long lo = ((unsigned long long)u.y << 32) | u.x;
+                const unsigned long long hi = ((unsigned long long)u.w << 32) | u.z;
+                const uint32_t row = (uint32_t)(hi >> 48);
+                const unsigned long long hik = (hi & kUnitHiMask) | ((unsigned long long)(row >> 6) << 48);
+                uint32_t slot = (uint32_t)(unit_hash(lo, hi & kUnitHiMask) >> 8) + (row >> 6) * 0x9E3779B1u;
+                slot &= (uint32_t)kUdSlots - 1u;
+                while (true) {
+                    unsigned long long l0 = *(volatile unsigned long long*)&k_lo[slot];
+                    if (l0 == kUnitEmptyLo) {
+                        l0 = atomicCAS(&k_lo[slot], kUnitEmptyLo, lo);
+                        if (l0 == kUnitEmptyLo) { atomicAdd(&s_distinct, 1u); l0 = lo; }
+                    }
+                    if (l0 == lo) {
+                        unsigned long long h0 = *(volatile unsigned long long*)&k_hi[slot];
+                        if (h0 == kUnitEmptyHi) {
+                            h0 = atomicCAS(&k_hi[slot], kUnitEmptyHi, hik);
+                            if (h0 == kUnitEmptyHi) h0 = hik;
+                        }
+                        if (h0 == hik) break;
+                    }
+                    slot = (slot + 1u) & ((uint32_t)kUdSlots - 1u);
+                }
+                atomicOr(&wd[slot], 1ULL << (63u - (row & 63u)));
+            }
+        }
+        __syncthreads();
+        flush();
+    }
+}
+
+// ---- k_units_expand: distinct (unit, block) -> wide records [(hash << wbits) | block, word] by hash range ----
+// Same tile machinery as k_scatter (32 hashed k-mers per thread in registers, counting sort in shared memory,
+// bucket runs on the way out); a thread expands one weighted unit.  COUNT: histogram only (exact offsets).
+struct UnitExpandParams {
+    const unsigned long long* wu;        // [n][3]
+    const unsigned long long* n_ptr;     // entries produced by the dedupe
+    unsigned long long cap;              // entries the buffer holds
+    uint32_t k, bucket_bits, wbits;
+    unsigned long long* cursors;         // [B] histogram (COUNT) or exact offsets
+    unsigned long long* records;         // [total][2]
+};
+
+__device__ __forceinline__ void expand_hash_group(const uint32_t (&r)[4], const uint32_t (&y)[4], uint32_t have,
+                                                  uint32_t kmask_lo, uint32_t kmask_hi, uint32_t key_bits, uint32_t* s_cnt,
+                                                  unsigned long long (&hsh)[kStPerThread]) {
+#pragma unroll
+    for (int e = 0; e < kStPerThread; ++e) {
+        if ((have >> e) & 1u) {
+            const int fs = 2 * (31 - e), fw_w = fs >> 5, fw_s = fs & 31;
+            const int rs = 2 * e, rc_w = rs >> 5, rc_s = rs & 31;
+            const uint32_t fw_lo = __funnelshift_r(r[fw_w], r[fw_w + 1], fw_s) & kmask_lo;
+            const uint32_t fw_hi = __funnelshift_r(r[fw_w + 1], r[fw_w + 2], fw_s) & kmask_hi;
+            const uint32_t rc_lo = __funnelshift_r(y[rc_w], y[rc_w + 1], rc_s) & kmask_lo;
+            const uint32_t rc_hi = __funnelshift_r(y[rc_w + 1], y[rc_w + 2], rc_s) & kmask_hi;
+            const uint64_t fw = ((uint64_t)fw_hi << 32) | fw_lo, rc = ((uint64_t)rc_hi << 32) | rc_lo;
+            const uint64_t h = khash(fw < rc ? fw : rc);
+            atomicAdd(&s_cnt[(uint32_t)(h >> key_bits)], 1u);
+            hsh[e] = h;
+        }
+    }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kStThreads, 1)
+k_units_expand(const UnitExpandParams p) {
+    extern __shared__ unsigned long long s_dyn[];
+    __shared__ uint32_t s_total;
+    __shared__ uint32_t s_warp[33];
+    __shared__ unsigned long long s_word[kStThreads];
+    __shared__ uint16_t s_blk[kStThreads];
+    const uint32_t B = 1u << p.bucket_bits;
+    unsigned long long* s_delta = s_dyn;
+    unsigned long long* s_rec = s_delta + B;
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_rec + kStTile);
+    uint32_t* s_off = s_cnt + B;
+    uint16_t* s_src = reinterpret_cast<uint16_t*>(s_off + B);
+    const unsigned long long n_all = *p.n_ptr;
+    const unsigned long long n = n_all < p.cap ? n_all : p.cap;
+    const unsigned long long n_tiles = (n + kStThreads - 1) / kStThreads;
+    const uint32_t k = p.k;
+    const uint32_t kmask_lo = k >= 16 ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
+    const uint32_t kmask_hi = k <= 16 ? 0u : (k == 32 ? 0xFFFFFFFFu : ((1u << (2 * k - 32)) - 1u));
+    const uint32_t key_bits = 64 - p.bucket_bits;
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t i = tid; i < B; i += kStThreads) s_cnt[i] = 0;
+    __syncthreads();
+    for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const unsigned long long i = tile * kStThreads + tid;
+        unsigned long long hsh[kStPerThread];
+        uint32_t have = 0;
+        if (i < n) {
+            const unsigned long long lo = p.wu[3 * i], hik = p.wu[3 * i + 1];
+            if (!COUNT) { s_word[tid] = p.wu[3 * i + 2]; s_blk[tid] = (uint16_t)(hik >> 48); }
+            const uint32_t L = (uint32_t)(lo >> 58) + 1u;
+            const unsigned long long Vlo = (lo & kUnitLoMask) | (hik << 58), Vhi = (hik & kUnitHiMask) >> 6;
+            // window: the unit's entry t at window entry 33 - k + t, so that its first k-mer ends at window entry 32
+            const uint32_t sh = 2u * (33u - k);
+            unsigned long long Xlo, Xhi;
+            if (sh == 64) { Xlo = 0ULL; Xhi = Vlo; }
+            else { Xlo = Vlo << sh; Xhi = (Vhi << sh) | (Vlo >> (64 - sh)); }
+            const uint32_t x[4] = {(uint32_t)Xlo, (uint32_t)(Xlo >> 32), (uint32_t)Xhi, (uint32_t)(Xhi >> 32)};
+            const uint32_t y[4] = {(uint32_t)Vlo ^ 0xAAAAAAAAu, (uint32_t)(Vlo >> 32) ^ 0xAAAAAAAAu,
+                                   (uint32_t)Vhi ^ 0xAAAAAAAAu, (uint32_t)(Vhi >> 32) ^ 0xAAAAAAAAu};
+            const uint32_t r[4] = {rev2_32(x[3]), rev2_32(x[2]), rev2_32(x[1]), rev2_32(x[0])};
+            have = L >= 32 ? 0xFFFFFFFFu : ((1u << L) - 1u);
+            expand_hash_group(r, y, have, kmask_lo, kmask_hi, key_bits, s_cnt, hsh);
+        }
+        __syncthreads();
+        {
+            uint32_t cnt[kStMaxBins];
+            uint32_t sum = 0;
+#pragma unroll
+            for (uint32_t j = 0; j < (uint32_t)kStMaxBins; ++j) {
+                const uint32_t bin = j * kStThreads + tid;
+                cnt[j] = 0;
+                if (bin < B) { cnt[j] = s_cnt[bin]; s_cnt[bin] = 0; sum += cnt[j]; }
+            }
+            unsigned long long gb[kStMaxBins];
+#pragma unroll
+            for (uint32_t j = 0; j < (uint32_t)kStMaxBins; ++j) {
+                const uint32_t bin = j * kStThreads + tid;
+                gb[j] = cnt[j] ? atomicAdd(&p.cursors[bin], (unsigned long long)cnt[j]) : 0ULL;
+            }
+            if (!COUNT) {
+                uint32_t total;
+                uint32_t off = block_excl_scan<kStThreads>(sum, s_warp, total);
+                if (tid == 0) s_total = total;
+#pragma unroll
+                for (uint32_t j = 0; j < (uint32_t)kStMaxBins; ++j) {
+                    const uint32_t bin = j * kStThreads + tid;
+                    if (bin < B) {
+                        s_off[bin] = off;
+                        if (cnt[j]) s_delta[bin] = gb[j] - off;
+                        off += cnt[j];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (!COUNT) {
+#pragma unroll
+            for (int e = 0; e < kStPerThread; ++e) {
+                if ((have >> e) & 1u) {
+                    const uint32_t dst = atomicAdd(&s_off[(uint32_t)(hsh[e] >> key_bits)], 1u);
+                    s_rec[dst] = hsh[e];
+                    s_src[dst] = (uint16_t)tid;
+                }
+            }
+            __syncthreads();
+            const uint32_t total = s_total;
+            ulonglong2* out = reinterpret_cast<ulonglong2*>(p.records);
+            for (uint32_t j = tid; j < total; j += kStThreads) {
+                const unsigned long long h = s_rec[j];
+                const uint32_t src = s_src[j];
+                out[s_delta[(uint32_t)(h >> key_bits)] + j] = make_ulonglong2((h << p.wbits) | s_blk[src], s_word[src]);
+            }
+            __syncthreads();      // s_word / s_blk / s_rec are rewritten by the next tile
+        }
+    }
+}
+
+// region ends for the over-provisioned unit regions + total units (one block)
+__global__ void __launch_bounds__(1024)
+k_finish_unit_regions(const unsigned long long* __restrict__ begin, unsigned long long* __restrict__ end, uint32_t MB,
+                      unsigned long long cap, unsigned long long* __restrict__ scalars, int which) {
+    __shared__ unsigned long long s_sum;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    unsigned long long v = 0;
+    for (uint32_t b = threadIdx.x; b < MB; b += blockDim.x) {
+        unsigned long long e = end[b];
+        if (cap && e > (unsigned long long)(b + 1) * cap) { e = (unsigned long long)(b + 1) * cap; end[b] = e; }
+        v += e - begin[b];
+    }
+    atomicAdd(&s_sum, v);
+    __syncthreads();
+    if (threadIdx.x == 0) scalars[which] = s_sum;
+}
+
+}  // namespace grmkm

@@ -6,7 +6,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgrmkm.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 OK = 0
 E_INVALID, E_UNSUPPORTED_K, E_NOMEM, E_CUDA, E_IO, E_CAPACITY, E_NO_DEVICE, E_UNSUPPORTED = -1, -2, -3, -4, -5, -6, -7, -8
@@ -15,6 +15,7 @@ FLAG_KMER_ORDER = 1
 FLAG_SIMPLE_SCATTER = 2
 FLAG_RADIX_ORDER = 4
 FLAG_EXACT_OFFSETS = 8
+FLAG_KMER_RECORDS = 16
 
 # every symbol include/grmkm.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
@@ -44,7 +45,9 @@ class Stats(C.Structure):
                 ("n_records", C.c_uint64), ("n_kmers", C.c_uint64), ("n_distinct", C.c_uint64),
                 ("n_words", C.c_uint32), ("n_genomes", C.c_uint32), ("n_buckets", C.c_uint32),
                 ("n_launches", C.c_uint32), ("h2d_bytes", C.c_uint64), ("device_bytes", C.c_uint64),
-                ("n_splits", C.c_uint64), ("n_region_overflows", C.c_uint64)]
+                ("n_splits", C.c_uint64), ("n_region_overflows", C.c_uint64), ("n_units", C.c_uint64),
+                ("n_unit_entries", C.c_uint64), ("n_wide", C.c_uint64), ("n_unit_buckets", C.c_uint32),
+                ("reserved0", C.c_uint32)]
 
     def asdict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -52,7 +55,7 @@ class Stats(C.Structure):
 
 class Times(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d", "parse", "pack", "count", "scatter", "abundance", "aggregate",
-                                         "sort", "total")]
+                                         "sort", "total", "bounds", "dedupe", "expand")]
 
     def asdict(self):
         return {n: float(getattr(self, n)) for n, _ in self._fields_}

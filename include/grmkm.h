@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GRMKM_ABI_VERSION 4
+#define GRMKM_ABI_VERSION 5
 
 enum {
     GRMKM_OK = 0,
@@ -51,6 +51,8 @@ enum { GRMKM_FASTA = 0, GRMKM_FASTQ = 1 };
 #define GRMKM_FLAG_RADIX_ORDER 4u /* order the columns with the LSD radix sort only (A/B timing, fallback test) */
 #define GRMKM_FLAG_SIMPLE_SCATTER 2u /* per-record global-atomic scatter instead of the staged one (A/B timing) */
 #define GRMKM_FLAG_EXACT_OFFSETS 8u /* count pass + exact bucket offsets instead of over-provisioned regions (fallback test) */
+#define GRMKM_FLAG_KMER_RECORDS 16u /* one 8-byte record per k-mer occurrence instead of super-k-mer units (A/B timing; builds with
+                                       min_abundance > 1 always take this path) */
 
 typedef struct grmkm_ctx grmkm_ctx;
 
@@ -88,11 +90,17 @@ typedef struct grmkm_stats {
     uint64_t device_bytes;  /* device memory held by the context                   */
     uint64_t n_splits;      /* bucket sub-range splits (table overflows handled)   */
     uint64_t n_region_overflows; /* builds redone with exact offsets (a bucket region was too small) */
+    uint64_t n_units;        /* super-k-mer units scattered (0 on the k-mer record path)  */
+    uint64_t n_unit_entries; /* distinct (unit, 64-genome block) entries after the dedupe  */
+    uint64_t n_wide;         /* [hash, presence word] records the distinct units expand to */
+    uint32_t n_unit_buckets; /* content-hash buckets of the unit scatter                   */
+    uint32_t reserved0;
 } grmkm_stats;
 
 /* per-stage device time of the last build, milliseconds (CUDA events on the build stream) */
 typedef struct grmkm_times {
     float h2d, parse, pack, count, scatter, abundance, aggregate, sort, total;
+    float bounds, dedupe, expand; /* unit path: run boundaries, per-bucket dedupe, expansion to k-mer records */
 } grmkm_times;
 
 int grmkm_abi_version(void);
