@@ -796,7 +796,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
             CU_TRY(c, cudaFuncSetAttribute(k_units_dedupe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
             CU_TRY(c, cudaFuncSetAttribute(k_units_expand<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_smem_bytes(B)));
             CU_TRY(c, cudaFuncSetAttribute(k_units_expand<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_smem_bytes(B)));
-            for (int attempt = 0; attempt < 2; ++attempt) {
+            for (int attempt = 0; attempt < 4; ++attempt) {
                 ENSURE(c, c->wu, wcap * 24);
                 UnitDedupeParams dp{};
                 dp.units = (const uint4*)c->units.p; dp.begin = (const unsigned long long*)c->ubeg.p;
@@ -830,8 +830,9 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
                     CU_TRY(c, cudaGetLastError());
                     break;
                 }
-                if (attempt == 1) return fail(c, GRMKM_E_UNSUPPORTED, "unit list overflow after resize");
-                wcap = sc[S_WU_NEEDED];
+                if (attempt == 3) return fail(c, GRMKM_E_UNSUPPORTED, "unit list overflow after resize");
+                // the entry count depends on the order the table fills in (bypass, flush points): leave headroom
+                wcap = sc[S_WU_NEEDED] + sc[S_WU_NEEDED] / 4 + 4096;
                 const uint64_t zero2[2] = {0, 0};
                 CU_TRY(c, cudaMemcpyAsync(d_scalars + S_WU_NEEDED, zero2, 2 * 8, cudaMemcpyHostToDevice, st));
             }

@@ -1156,14 +1156,20 @@ __global__ void k_merge_bounds(const unsigned long long* __restrict__ parts, uin
     bounds[id] = lo;
 }
 
-// Pass A over the table: kept flags, per-thread kept counts.  Returns this thread's kept count; occ = occupied.
+// Emission.  Slots are handled in chunks of kAggThreads consecutive slots, lane = slot: shared-memory accesses are
+// conflict-free, the inversion walks of neighbouring lanes touch neighbouring slots, and the columns leave in
+// (almost) consecutive order.
+// Pass A: kept flags; kept slots per (chunk, warp) in s_wc.  Returns this thread's occupied count.
+constexpr int kAggMaxChunks = 18;      // (16384 + kMaxProbe) slots / kAggThreads, rounded up
 template <int MODE>
-__device__ __forceinline__ uint32_t agg_mark(const AggParams2& p, const AggTable& t, uint32_t lo, uint32_t hi, uint32_t& occ) {
-    uint32_t kept = 0;
-    occ = 0;
-    for (uint32_t i = lo; i < hi; ++i) {
-        uint8_t kf = 0;
-        if (t.keys[i] != kEmptyKey) {
+__device__ __forceinline__ uint32_t agg_mark(const AggParams2& p, const AggTable& t, uint32_t* s_wc) {
+    uint32_t occ = 0;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t c = 0;
+    for (uint32_t i0 = 0; i0 < t.total; i0 += kAggThreads, ++c) {
+        const uint32_t i = i0 + threadIdx.x;
+        uint32_t kf = 0;
+        if (i < t.total && t.keys[i] != kEmptyKey) {
             occ++;
             if (MODE == 1 || MODE == 5 || p.keep_singletons) kf = 1;
             else {
@@ -1172,22 +1178,27 @@ __device__ __forceinline__ uint32_t agg_mark(const AggParams2& p, const AggTable
                 kf = pc >= 2;
             }
         }
-        t.kept[i] = kf;
-        kept += kf;
+        if (i < t.total) t.kept[i] = (uint8_t)kf;
+        const uint32_t bal = __ballot_sync(0xffffffffu, kf != 0);
+        if (lane == 0) s_wc[c * 32 + warp] = (uint32_t)__popc(bal);
     }
-    return kept;
+    return occ;
 }
 
-// Pass B: exact rank of every kept slot of [lo, hi) and emission at out[base + rank]
+// Pass B: exact rank of every kept slot and emission at out[base + rank].  s_wp = exclusive scan of s_wc.
 template <int MODE>
-__device__ __forceinline__ void agg_emit(const AggParams2& p, const AggTable& t, uint32_t lo, uint32_t hi, uint32_t before,
+__device__ __forceinline__ void agg_emit(const AggParams2& p, const AggTable& t, const uint32_t* s_wp,
                                          unsigned long long base, uint32_t b, uint32_t key_bits) {
     const unsigned long long key_mask = (1ULL << key_bits) - 1;
-    uint32_t running = before;
-    for (uint32_t i = lo; i < hi; ++i) {
-        if (!t.kept[i]) continue;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t c = 0;
+    for (uint32_t i0 = 0; i0 < t.total; i0 += kAggThreads, ++c) {
+        const uint32_t i = i0 + threadIdx.x;
+        const bool kf = i < t.total && t.kept[i];
+        const uint32_t bal = __ballot_sync(0xffffffffu, kf);
+        if (!kf) continue;
         const unsigned long long key = t.keys[i];
-        uint32_t rank = running++;
+        uint32_t rank = s_wp[c * 32 + warp] + (uint32_t)__popc(bal & ((1u << lane) - 1u));
         for (uint32_t j = i; j-- > 0;) {                 // inversions with earlier slots of the cluster
             const unsigned long long kj = t.keys[j];
             if (kj == kEmptyKey) break;
@@ -1223,8 +1234,8 @@ k_aggregate_cols(const AggParams2 p) {
     t.w32 = reinterpret_cast<uint32_t*>(s_tab + t.total);
     t.kept = reinterpret_cast<uint8_t*>(t.w32 + 2 * (size_t)p.n_words * t.total);
     const uint32_t key_bits = 64 - p.bucket_bits;
-    const uint32_t chunk = (t.total + kAggThreads - 1) / kAggThreads;
-    const uint32_t lo = min(threadIdx.x * chunk, t.total), hi = min(lo + chunk, t.total);
+    const uint32_t n_chunks = (t.total + kAggThreads - 1) / kAggThreads;     // <= kAggMaxChunks (slots <= 16384)
+    __shared__ uint32_t s_wc[kAggMaxChunks * 32];
 
     // A virtual bucket = bucket b restricted to the key sub-range `sub` of 2^sub_bits: the scatter can then use
     // 2^sub_bits fewer buckets (longer runs per tile) than the table size demands.  The CTAs of one bucket's
@@ -1299,18 +1310,22 @@ k_aggregate_cols(const AggParams2 p) {
                 if (phase == 1) splits++;
                 continue;
             }
-            uint32_t occ;
-            const uint32_t kept = agg_mark<MODE>(p, t, lo, hi, occ);
+            const uint32_t occ = agg_mark<MODE>(p, t, s_wc);
+            __syncthreads();
             uint32_t total_kept, total_occ;
-            const uint32_t before = block_excl_scan<kAggThreads>(kept, s_warp, total_kept);
+            {
+                const uint32_t v = threadIdx.x < (uint32_t)kAggMaxChunks * 32u && threadIdx.x < n_chunks * 32u ? s_wc[threadIdx.x] : 0u;
+                const uint32_t e = block_excl_scan<kAggThreads>(v, s_warp, total_kept);
+                if (threadIdx.x < n_chunks * 32u) s_wc[threadIdx.x] = e;
+            }
             if (phase != 2) { block_excl_scan<kAggThreads>(occ, s_warp, total_occ); bucket_occ += total_occ; }
             if (phase == 1) { bucket_total += total_kept; continue; }
             if (phase == 0) {
                 bucket_total = total_kept;
                 if (threadIdx.x == 0) s_base = atomicAdd(&p.scalars[S_U_NEEDED], (unsigned long long)total_kept);
-                __syncthreads();
             }
-            agg_emit<MODE>(p, t, lo, hi, before, s_base + emitted, b, key_bits);
+            __syncthreads();
+            agg_emit<MODE>(p, t, s_wc, s_base + emitted, b, key_bits);
             emitted += total_kept;
         }
         if (threadIdx.x == 0) {

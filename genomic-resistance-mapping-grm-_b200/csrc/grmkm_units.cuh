@@ -116,14 +116,17 @@ k_unit_bounds(const unsigned long long* __restrict__ codes, const uint32_t* __re
 }
 
 // ---- k_units_scatter: units -> content-hash buckets ------------------------------------------
-// One tile = 1024 groups (32768 stream entries) per CTA iteration; a thread owns one group and holds up to
-// kUsMax of its units in registers per round (more units = more rounds, so any input is handled with bounded
-// shared memory).  Round: histogram with returning shared-memory atomics (the rank inside the bucket's run) ->
-// scan + ONE global reservation per (round, bucket) -> units to their sorted slot -> copy out in bucket runs.
+// One tile = 1024 groups (32768 stream entries) per CTA iteration.  The unit starts of the tile are compacted
+// into a list (block scan of the start-mask popcounts), so every thread handles the same number of units
+// whatever their distribution over the groups; a round takes up to kUsMax units per thread (more units =
+// more rounds, so any input is handled with bounded shared memory).  Round: histogram with returning
+// shared-memory atomics (the rank inside the bucket's run) -> scan + ONE global reservation per (round,
+// bucket) -> units to their sorted slot -> copy out in bucket runs.
 constexpr int kUsThreads = 1024;
-constexpr int kUsMax = 6;
+constexpr int kUsMax = 4;
 constexpr int kUsStage = kUsThreads * kUsMax;
 constexpr int kUsTileGroups = kUsThreads;
+constexpr int kUsTileEntries = kUsTileGroups * 32;
 constexpr int kUsMaxBuckets = 1024;
 
 struct UnitScatterParams {
@@ -144,7 +147,8 @@ struct UnitScatterParams {
 };
 
 __host__ __device__ inline size_t unit_scatter_smem(uint32_t MB) {
-    return (size_t)kUsStage * 16 + (size_t)MB * 8 + (size_t)(kUsTileGroups + 3) * 8 + (size_t)MB * 8 + (size_t)kUsStage * 2;
+    return (size_t)kUsStage * 16 + (size_t)MB * 8 + (size_t)(kUsTileGroups + 3) * 8 + (size_t)MB * 8 +
+           (size_t)(kUsTileGroups + 1) * 4 + (size_t)kUsStage * 2 + (size_t)kUsTileEntries * 2 + (size_t)kUsTileGroups * 2;
 }
 
 __global__ void k_stream_tile_files(const uint64_t* __restrict__ scalars, const uint64_t* __restrict__ fss, uint32_t n_files,
@@ -172,7 +176,10 @@ k_units_scatter(const UnitScatterParams p) {
     unsigned long long* s_codes = s_delta + MB;                          // [kUsTileGroups + 3], [0] = the group before the tile
     uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_codes + kUsTileGroups + 3);   // [MB]
     uint32_t* s_off = s_cnt + MB;                                        // [MB]
-    uint16_t* s_b = reinterpret_cast<uint16_t*>(s_off + MB);             // [kUsStage]
+    uint32_t* s_brk = s_off + MB;                                        // [kUsTileGroups + 1] natural breaks per group
+    uint16_t* s_b = reinterpret_cast<uint16_t*>(s_brk + kUsTileGroups + 1);   // [kUsStage]
+    uint16_t* s_list = s_b + kUsStage;                                   // [kUsTileEntries] tile-local entry where a unit's first k-mer ends
+    uint16_t* s_gf = s_list + kUsTileEntries;                            // [kUsTileGroups] file of the group's first entry - tile file
     const uint64_t stream_len = p.scalars[S_STREAM_LEN];
     const uint64_t n_groups = (stream_len + 31) >> 5;
     const uint64_t n_tiles = (n_groups + kUsTileGroups - 1) / kUsTileGroups;
@@ -186,33 +193,41 @@ k_units_scatter(const UnitScatterParams p) {
             const uint64_t gi = g0 + i;      // group gi - 1
             s_codes[i] = (gi >= 1 && gi - 1 < n_groups) ? p.codes[gi - 1] : 0ULL;
         }
-        uint2 mk = make_uint2(0u, 0u), mk1 = make_uint2(0u, 0u);
+        uint2 mk = make_uint2(0u, 0u);
         if (g < n_groups) mk = p.masks[g];
-        if (g + 1 < n_groups) mk1 = p.masks[g + 1];
-        const uint32_t st = mk.x, vk = mk.y;
-        // natural breaks after a position: an invalid k-mer or the start of another run
-        const unsigned long long brk = (unsigned long long)(~vk | mk.x) | ((unsigned long long)(~mk1.y | mk1.x) << 32);
-        uint32_t rem = st;
-        uint32_t f = 0;
-        if (rem) {
-            f = p.tile_file[tile];
-            while (f + 1 < p.n_files && p.file_stream_start[f + 1] <= g * 32ULL) ++f;
+        s_brk[tid] = ~mk.y | mk.x;           // after a position: an invalid k-mer or the start of another run
+        if (tid == 0) {
+            uint2 mn = make_uint2(0u, 0u);
+            if (g0 + kUsTileGroups < n_groups) mn = p.masks[g0 + kUsTileGroups];
+            s_brk[kUsTileGroups] = ~mn.y | mn.x;
         }
-        __syncthreads();       // s_codes staged
-        bool more;
-        do {
+        const uint32_t tile_f = p.tile_file[tile];
+        {
+            uint32_t f = tile_f;
+            if (mk.x) while (f + 1 < p.n_files && p.file_stream_start[f + 1] <= g * 32ULL) ++f;
+            s_gf[tid] = (uint16_t)min(f - tile_f, 0xFFFFu);
+        }
+        // compact the unit starts of the tile
+        uint32_t n_units;
+        {
+            uint32_t o = block_excl_scan<kUsThreads>((uint32_t)__popc(mk.x), s_warp, n_units);
+            for (uint32_t m = mk.x; m; m &= m - 1u) s_list[o++] = (uint16_t)(32u * tid + (uint32_t)__ffs(m) - 1u);
+        }
+        __syncthreads();       // s_codes, s_brk, s_gf, s_list staged
+        for (uint32_t base = 0; base < n_units; base += kUsStage) {
             unsigned long long ulo[kUsMax], uhi[kUsMax];
             uint32_t ubr[kUsMax];
-            uint32_t n = 0;
 #pragma unroll
             for (int j = 0; j < kUsMax; ++j) {
-                if (rem) {
-                    const uint32_t e = (uint32_t)__ffs(rem) - 1u;
-                    rem &= rem - 1u;
+                const uint32_t idx = base + j * kUsThreads + tid;
+                ubr[j] = 0xFFFFFFFFu;
+                if (idx < n_units) {
+                    const uint32_t P = s_list[idx];              // tile-local entry where the first k-mer ends
+                    const uint32_t gl = P >> 5, e = P & 31u;
+                    const unsigned long long brk = (unsigned long long)s_brk[gl] | ((unsigned long long)s_brk[gl + 1] << 32);
                     const unsigned long long after = brk >> (e + 1);
                     const uint32_t dist = after ? (uint32_t)__ffsll((long long)after) : 64u;
                     const uint32_t L = dist < lmax ? dist : lmax;
-                    const uint32_t P = 32u * tid + e;            // tile-local entry where the first k-mer ends
                     const uint32_t a = P + 32u - (k - 1u);       // first entry of the unit, counted from the group before the tile
                     const uint32_t nb = L + k - 1u;
                     const uint32_t wi = a >> 5, sh = 2u * (a & 31u);
@@ -231,6 +246,7 @@ k_units_scatter(const UnitScatterParams p) {
                     else { Rlo = (Fl >> s2) | (Fh << (64 - s2)); Rhi = Fh >> s2; }
                     Rlo ^= 0xAAAAAAAAAAAAAAAAULL & mlo; Rhi ^= 0xAAAAAAAAAAAAAAAAULL & mhi;
                     if (Rhi < Vhi || (Rhi == Vhi && Rlo < Vlo)) { Vlo = Rlo; Vhi = Rhi; }
+                    uint32_t f = tile_f + s_gf[gl];
                     while (f + 1 < p.n_files && p.file_stream_start[f + 1] <= g0 * 32ULL + P) ++f;
                     const unsigned long long lo = (Vlo & kUnitLoMask) | ((unsigned long long)(L - 1u) << 58);
                     const unsigned long long hik = (Vlo >> 58) | (Vhi << 6);
@@ -239,7 +255,6 @@ k_units_scatter(const UnitScatterParams p) {
                     ulo[j] = lo;
                     uhi[j] = hik | ((unsigned long long)p.files[f].row << 48);
                     ubr[j] = b | (rank << 16);
-                    n = j + 1;
                     my_windows += L;
                 }
             }
@@ -267,11 +282,11 @@ k_units_scatter(const UnitScatterParams p) {
                     }
                 }
             }
+            __syncthreads();
             if (!COUNT) {
-                __syncthreads();
 #pragma unroll
                 for (int j = 0; j < kUsMax; ++j) {
-                    if ((uint32_t)j < n) {
+                    if (ubr[j] != 0xFFFFFFFFu) {
                         const uint32_t b = ubr[j] & 0xFFFFu;
                         const uint32_t dst = s_off[b] + (ubr[j] >> 16);
                         s_units[dst] = make_uint4((uint32_t)ulo[j], (uint32_t)(ulo[j] >> 32), (uint32_t)uhi[j], (uint32_t)(uhi[j] >> 32));
@@ -281,9 +296,10 @@ k_units_scatter(const UnitScatterParams p) {
                 __syncthreads();
                 const uint32_t total = s_total;
                 for (uint32_t i = tid; i < total; i += kUsThreads) p.units[s_delta[s_b[i]] + i] = s_units[i];
+                __syncthreads();
             }
-            more = __syncthreads_or(rem != 0u);
-        } while (more);
+        }
+        __syncthreads();       // the tile's staging is rewritten by the next tile
     }
     if (!COUNT) {
 #pragma unroll
@@ -296,7 +312,9 @@ k_units_scatter(const UnitScatterParams p) {
 constexpr int kUdThreads = 1024;
 constexpr int kUdSlotsLog2 = 13;
 constexpr int kUdSlots = 1 << kUdSlotsLog2;           // 8192 x 24 bytes = 192 KB
-constexpr int kUdLimit = kUdSlots * 3 / 4 - 2 * kUdThreads;
+constexpr int kUdCheck = 8;                            // batches between "is the table filling up" checkpoints
+constexpr int kUdSoft = kUdSlots * 6 / 10;             // flush at a checkpoint above this many entries
+constexpr int kUdHard = kUdSlots - kUdThreads - 64;    // between checkpoints: new keys beyond this bypass the table
 
 struct UnitDedupeParams {
     const uint4* units;
@@ -349,23 +367,28 @@ k_units_dedupe(const UnitDedupeParams p) {
         const uint4* src = p.units + rb;
         uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
         if (tid < n) nxt = __ldcs(src + tid);
-        for (unsigned long long base = 0; base < n; base += kUdThreads) {
+        uint32_t bi = 0;
+        for (unsigned long long base = 0; base < n; base += kUdThreads, ++bi) {
             const uint4 u = nxt;
             const bool have = base + tid < n;
             if (base + kUdThreads + tid < n) nxt = __ldcs(src + base + kUdThreads + tid);
-            // the previous batch is in the table; thread 0's view of s_distinct may miss that batch (<= 1024 keys),
-            // which the limit allows for
-            if (__syncthreads_or(tid == 0 && s_distinct > (uint32_t)kUdLimit)) flush();
+            // Checkpoint every kUdCheck batches (one barrier): flush when the table is filling up.  In between, a
+            // NEW key that finds the table nearly full goes straight to the output (duplicates are merged by the
+            // column aggregate), so no thread ever waits for a flush.
+            if (bi % kUdCheck == 0 && __syncthreads_or(tid == 0 && s_distinct > (uint32_t)kUdSoft)) flush();
             if (have) {
                 const unsigned long long lo = ((unsigned long long)u.y << 32) | u.x;
                 const unsigned long long hi = ((unsigned long long)u.w << 32) | u.z;
                 const uint32_t row = (uint32_t)(hi >> 48);
                 const unsigned long long hik = (hi & kUnitHiMask) | ((unsigned long long)(row >> 6) << 48);
+                const unsigned long long bit = 1ULL << (63u - (row & 63u));
                 uint32_t slot = (uint32_t)(unit_hash(lo, hi & kUnitHiMask) >> 8) + (row >> 6) * 0x9E3779B1u;
                 slot &= (uint32_t)kUdSlots - 1u;
+                bool placed = true;
                 while (true) {
                     unsigned long long l0 = *(volatile unsigned long long*)&k_lo[slot];
                     if (l0 == kUnitEmptyLo) {
+                        if (*(volatile uint32_t*)&s_distinct >= (uint32_t)kUdHard) { placed = false; break; }
                         l0 = atomicCAS(&k_lo[slot], kUnitEmptyLo, lo);
                         if (l0 == kUnitEmptyLo) { atomicAdd(&s_distinct, 1u); l0 = lo; }
                     }
@@ -379,7 +402,11 @@ k_units_dedupe(const UnitDedupeParams p) {
                     }
                     slot = (slot + 1u) & ((uint32_t)kUdSlots - 1u);
                 }
-                atomicOr(&wd[slot], 1ULL << (63u - (row & 63u)));
+                if (placed) atomicOr(&wd[slot], bit);
+                else {
+                    const unsigned long long o = atomicAdd(p.needed, 1ULL);
+                    if (o < p.cap) { p.out[3 * o] = lo; p.out[3 * o + 1] = hik; p.out[3 * o + 2] = bit; }
+                }
             }
         }
         __syncthreads();
