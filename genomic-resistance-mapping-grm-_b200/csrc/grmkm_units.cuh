@@ -2,7 +2,7 @@
 //
 // The genomes Kover learns from belong to one species: most of every genome is shared with the others.  A
 // *unit* is a maximal run of consecutive valid k-mers of one record that have the same minimizer (smallest
-// hashed canonical m-mer), at most lmax k-mers long, stored as its L + k - 1 bases in the strand with the
+// strand-neutral m-mer hash), at most lmax k-mers long, stored as its L + k - 1 bases in the strand with the
 // smaller value.  Unit boundaries depend on the sequence only, so the same stretch of DNA yields the same
 // units in every genome, whatever its offset, contig layout or strand.  The pipeline is then
 //
@@ -50,11 +50,13 @@ __device__ __forceinline__ unsigned long long rev2_64(unsigned long long x) {
     return ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
 }
 
-// hash of a unit's content (lo, hi without the row): bucket from the top half, table slot from the middle
-__device__ __forceinline__ unsigned long long unit_hash(unsigned long long lo, unsigned long long hik) {
-    unsigned long long h = (lo * kHashMul) ^ (hik * 0xC2B2AE3D27D4EB4FULL);
-    h ^= h >> 29;
-    return h * 0x94D049BB133111EBULL;
+// hash of a unit's content (lo, hi without the row), 32-bit arithmetic only: the scatter takes the bucket from
+// the top bits (mulhi), the dedupe table takes its slot from a second multiply
+__device__ __forceinline__ uint32_t unit_hash32(uint32_t lo0, uint32_t lo1, uint32_t hi0, uint32_t hi1) {
+    uint32_t h = (lo0 * 0x9E3779B1u) ^ (lo1 * 0x85EBCA77u) ^ (hi0 * 0xC2B2AE3Du) ^ (hi1 * 0x27D4EB2Fu);
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    return h ^ (h >> 13);
 }
 
 // ---- k_unit_bounds: per group of 32 stream entries, start mask and valid-k-mer mask ---------
@@ -86,7 +88,7 @@ k_unit_bounds(const unsigned long long* __restrict__ codes, const uint32_t* __re
     const uint32_t y[5] = {(uint32_t)Yl, (uint32_t)(Yl >> 32), (uint32_t)Yh, (uint32_t)(Yh >> 32), 0u};
     const uint32_t mmask = m >= 16 ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1u);
     const uint32_t cm = 0xAAAAAAAAu & mmask;
-    // h[t] = hashed canonical m-mer ending at window entry 32 - W + t   (t = 0 .. 31 + W)
+    // h[t] = strand-neutral hash of the m-mer ending at window entry 32 - W + t   (t = 0 .. 31 + W)
     constexpr int N = 32 + W;
     uint32_t h[N];
 #pragma unroll
@@ -94,7 +96,7 @@ k_unit_bounds(const unsigned long long* __restrict__ codes, const uint32_t* __re
         const int fs = 2 * (31 + W - t), rs = 2 * t;
         const uint32_t fw = __funnelshift_r(r[fs >> 5], r[(fs >> 5) + 1], fs & 31) & mmask;         // first base most significant
         const uint32_t rc = (__funnelshift_r(y[rs >> 5], y[(rs >> 5) + 1], rs & 31) & mmask) ^ cm;  // reverse complement
-        h[t] = ((fw < rc ? fw : rc) ^ kMmerSeed) * kMmerMul;
+        h[t] = (fw + rc + kMmerSeed) * kMmerMul;      // the same for an m-mer and its reverse complement
     }
     // minimizer of the k-mer ending at entry j - 1 = min h[j .. j + W - 1]  (j = 0 .. 32)
     uint32_t pre[N], suf[N];
@@ -105,10 +107,10 @@ k_unit_bounds(const unsigned long long* __restrict__ codes, const uint32_t* __re
     uint32_t changed = 0, prev_min = min(suf[0], pre[W - 1]);
 #pragma unroll
     for (int e = 0; e < 32; ++e) {
-        // a run ends when the minimum changes, or when an m-mer equal to it leaves on the left or enters on the
-        // right (the same rule read from either strand): a run is never longer than W <= lmax k-mers
+        // a run ends when an m-mer equal to the window minimum leaves on the left or enters on the right -- which
+        // covers every change of the minimum, reads the same from either strand, and bounds a run by W <= lmax
         const uint32_t mn = min(suf[e + 1], pre[e + W]);
-        changed |= (uint32_t)((mn != prev_min) | (h[e] == prev_min) | (h[e + W] == mn)) << e;
+        changed |= (uint32_t)((h[e] == prev_min) | (h[e + W] == mn)) << e;
         prev_min = mn;
     }
     const uint32_t before = (vk << 1) | vk_before;
@@ -146,9 +148,20 @@ struct UnitScatterParams {
     unsigned long long* n_windows;
 };
 
+constexpr int kUsCodeWords = kUsTileGroups + 3;          // staged 64-bit code words: the group before the tile .. two after it
+constexpr int kUsCode32 = 2 * kUsCodeWords + 6;          // as 32-bit words, padded for the 5-word window reads
+
 __host__ __device__ inline size_t unit_scatter_smem(uint32_t MB) {
-    return (size_t)kUsStage * 16 + (size_t)MB * 8 + (size_t)(kUsTileGroups + 3) * 8 + (size_t)MB * 8 +
+    return (size_t)kUsStage * 16 + (size_t)MB * 8 + (size_t)kUsCode32 * 4 * 2 + (size_t)MB * 8 +
            (size_t)(kUsTileGroups + 1) * 4 + (size_t)kUsStage * 2 + (size_t)kUsTileEntries * 2 + (size_t)kUsTileGroups * 2;
+}
+
+// 2 * nb bits starting at entry a of a staged 2-bit array, as four 32-bit words (not yet masked)
+__device__ __forceinline__ void unit_window(const uint32_t* __restrict__ s32, uint32_t a, uint32_t (&v)[4]) {
+    const uint32_t wi = a >> 4, sh = 2u * (a & 15u);
+    const uint32_t t0 = s32[wi], t1 = s32[wi + 1], t2 = s32[wi + 2], t3 = s32[wi + 3], t4 = s32[wi + 4];
+    v[0] = __funnelshift_r(t0, t1, sh); v[1] = __funnelshift_r(t1, t2, sh);
+    v[2] = __funnelshift_r(t2, t3, sh); v[3] = __funnelshift_r(t3, t4, sh);
 }
 
 __global__ void k_stream_tile_files(const uint64_t* __restrict__ scalars, const uint64_t* __restrict__ fss, uint32_t n_files,
@@ -173,8 +186,9 @@ k_units_scatter(const UnitScatterParams p) {
     __shared__ uint32_t s_warp[33];
     const uint32_t MB = p.n_buckets;
     unsigned long long* s_delta = reinterpret_cast<unsigned long long*>(s_units + kUsStage);   // [MB]
-    unsigned long long* s_codes = s_delta + MB;                          // [kUsTileGroups + 3], [0] = the group before the tile
-    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_codes + kUsTileGroups + 3);   // [MB]
+    uint32_t* s_fw = reinterpret_cast<uint32_t*>(s_delta + MB);          // [kUsCode32] codes, word 0 = the group before the tile
+    uint32_t* s_rc = s_fw + kUsCode32;                                   // [kUsCode32] the same entries reversed and complemented
+    uint32_t* s_cnt = s_rc + kUsCode32;                                  // [MB]
     uint32_t* s_off = s_cnt + MB;                                        // [MB]
     uint32_t* s_brk = s_off + MB;                                        // [kUsTileGroups + 1] natural breaks per group
     uint16_t* s_b = reinterpret_cast<uint16_t*>(s_brk + kUsTileGroups + 1);   // [kUsStage]
@@ -185,16 +199,31 @@ k_units_scatter(const UnitScatterParams p) {
     const uint64_t n_tiles = (n_groups + kUsTileGroups - 1) / kUsTileGroups;
     const uint32_t k = p.k, lmax = p.lmax;
     const uint32_t tid = threadIdx.x;
+    constexpr uint32_t T = (uint32_t)kUsCodeWords * 32u;                 // staged entries
     for (uint32_t i = tid; i < MB; i += kUsThreads) s_cnt[i] = 0;
+    if (tid < 6) { s_fw[2 * kUsCodeWords + tid] = 0; s_rc[2 * kUsCodeWords + tid] = 0; }
     unsigned long long my_windows = 0;
+    // this thread's share of a tile's inputs: code words tid (and tid + 1024 for the first three threads), one mask
+    auto fetch = [&](uint64_t tile, unsigned long long& c0, unsigned long long& c1, uint2& mk) {
+        const uint64_t g0 = tile * kUsTileGroups;
+        const uint64_t gi = g0 + tid;        // code word i holds group g0 + i - 1
+        c0 = (tile < n_tiles && gi >= 1 && gi - 1 < n_groups) ? p.codes[gi - 1] : 0ULL;
+        c1 = (tile < n_tiles && tid < 3 && gi + kUsThreads - 1 < n_groups) ? p.codes[gi + kUsThreads - 1] : 0ULL;
+        mk = (tile < n_tiles && gi < n_groups) ? p.masks[gi] : make_uint2(0u, 0u);
+    };
+    unsigned long long nc0, nc1; uint2 nmk;
+    fetch(blockIdx.x, nc0, nc1, nmk);
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t g0 = tile * kUsTileGroups, g = g0 + tid;
-        for (uint32_t i = tid; i < (uint32_t)kUsTileGroups + 3; i += kUsThreads) {
-            const uint64_t gi = g0 + i;      // group gi - 1
-            s_codes[i] = (gi >= 1 && gi - 1 < n_groups) ? p.codes[gi - 1] : 0ULL;
+        const uint2 mk = nmk;
+        {
+            reinterpret_cast<unsigned long long*>(s_fw)[tid] = nc0;
+            reinterpret_cast<unsigned long long*>(s_rc)[kUsCodeWords - 1 - tid] = rev2_64(nc0) ^ 0xAAAAAAAAAAAAAAAAULL;
+            if (tid < 3) {
+                reinterpret_cast<unsigned long long*>(s_fw)[tid + kUsThreads] = nc1;
+                reinterpret_cast<unsigned long long*>(s_rc)[kUsCodeWords - 1 - tid - kUsThreads] = rev2_64(nc1) ^ 0xAAAAAAAAAAAAAAAAULL;
+            }
         }
-        uint2 mk = make_uint2(0u, 0u);
-        if (g < n_groups) mk = p.masks[g];
         s_brk[tid] = ~mk.y | mk.x;           // after a position: an invalid k-mer or the start of another run
         if (tid == 0) {
             uint2 mn = make_uint2(0u, 0u);
@@ -213,10 +242,10 @@ k_units_scatter(const UnitScatterParams p) {
             uint32_t o = block_excl_scan<kUsThreads>((uint32_t)__popc(mk.x), s_warp, n_units);
             for (uint32_t m = mk.x; m; m &= m - 1u) s_list[o++] = (uint16_t)(32u * tid + (uint32_t)__ffs(m) - 1u);
         }
-        __syncthreads();       // s_codes, s_brk, s_gf, s_list staged
+        __syncthreads();       // the tile's staging is complete
+        fetch(tile + gridDim.x, nc0, nc1, nmk);        // the next tile's inputs travel while this one is processed
         for (uint32_t base = 0; base < n_units; base += kUsStage) {
-            unsigned long long ulo[kUsMax], uhi[kUsMax];
-            uint32_t ubr[kUsMax];
+            uint32_t u0[kUsMax], u1[kUsMax], u2[kUsMax], u3[kUsMax], ubr[kUsMax];
 #pragma unroll
             for (int j = 0; j < kUsMax; ++j) {
                 const uint32_t idx = base + j * kUsThreads + tid;
@@ -230,30 +259,27 @@ k_units_scatter(const UnitScatterParams p) {
                     const uint32_t L = dist < lmax ? dist : lmax;
                     const uint32_t a = P + 32u - (k - 1u);       // first entry of the unit, counted from the group before the tile
                     const uint32_t nb = L + k - 1u;
-                    const uint32_t wi = a >> 5, sh = 2u * (a & 31u);
-                    const unsigned long long w0 = s_codes[wi], w1 = s_codes[wi + 1], w2 = s_codes[wi + 2];
-                    unsigned long long Vlo = sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0;
-                    unsigned long long Vhi = sh ? (w1 >> sh) | (w2 << (64 - sh)) : w1;
-                    unsigned long long mlo, mhi;
-                    if (nb >= 32) { mlo = ~0ULL; mhi = (1ULL << (2 * nb - 64)) - 1ULL; }
-                    else { mlo = (1ULL << (2 * nb)) - 1ULL; mhi = 0ULL; }
-                    Vlo &= mlo; Vhi &= mhi;
-                    // the other strand: digits reversed and complemented
-                    const unsigned long long Fh = rev2_64(Vlo), Fl = rev2_64(Vhi);
-                    const uint32_t s2 = 128u - 2u * nb;
-                    unsigned long long Rlo, Rhi;
-                    if (s2 >= 64) { Rlo = Fh >> (s2 - 64); Rhi = 0ULL; }
-                    else { Rlo = (Fl >> s2) | (Fh << (64 - s2)); Rhi = Fh >> s2; }
-                    Rlo ^= 0xAAAAAAAAAAAAAAAAULL & mlo; Rhi ^= 0xAAAAAAAAAAAAAAAAULL & mhi;
-                    if (Rhi < Vhi || (Rhi == Vhi && Rlo < Vlo)) { Vlo = Rlo; Vhi = Rhi; }
+                    uint32_t v[4], r[4];
+                    unit_window(s_fw, a, v);
+                    unit_window(s_rc, T - a - nb, r);            // the other strand: the same entries reversed and complemented
+                    const uint32_t bits = 2u * nb;               // <= 106
+                    const uint32_t m0 = bits >= 32u ? 0xFFFFFFFFu : ((1u << bits) - 1u);
+                    const uint32_t m1 = bits >= 64u ? 0xFFFFFFFFu : (bits > 32u ? ((1u << (bits - 32u)) - 1u) : 0u);
+                    const uint32_t m2 = bits >= 96u ? 0xFFFFFFFFu : (bits > 64u ? ((1u << (bits - 64u)) - 1u) : 0u);
+                    const uint32_t m3 = bits > 96u ? ((1u << (bits - 96u)) - 1u) : 0u;
+                    v[0] &= m0; v[1] &= m1; v[2] &= m2; v[3] &= m3;
+                    r[0] &= m0; r[1] &= m1; r[2] &= m2; r[3] &= m3;
+                    const unsigned long long vh = ((unsigned long long)v[3] << 32) | v[2], vl = ((unsigned long long)v[1] << 32) | v[0];
+                    const unsigned long long rh = ((unsigned long long)r[3] << 32) | r[2], rl = ((unsigned long long)r[1] << 32) | r[0];
+                    if (rh < vh || (rh == vh && rl < vl)) { v[0] = r[0]; v[1] = r[1]; v[2] = r[2]; v[3] = r[3]; }
                     uint32_t f = tile_f + s_gf[gl];
                     while (f + 1 < p.n_files && p.file_stream_start[f + 1] <= g0 * 32ULL + P) ++f;
-                    const unsigned long long lo = (Vlo & kUnitLoMask) | ((unsigned long long)(L - 1u) << 58);
-                    const unsigned long long hik = (Vlo >> 58) | (Vhi << 6);
-                    const uint32_t b = __umulhi((uint32_t)(unit_hash(lo, hik) >> 32), MB);
+                    // lo = bases 0..28 | (L - 1) << 58;  hi = bases 29..52 | row << 48
+                    const uint32_t lo0 = v[0], lo1 = (v[1] & 0x03FFFFFFu) | ((L - 1u) << 26);
+                    const uint32_t hi0 = __funnelshift_r(v[1], v[2], 26), hi1 = __funnelshift_r(v[2], v[3], 26);
+                    const uint32_t b = __umulhi(unit_hash32(lo0, lo1, hi0, hi1), MB);
                     const uint32_t rank = atomicAdd(&s_cnt[b], 1u);
-                    ulo[j] = lo;
-                    uhi[j] = hik | ((unsigned long long)p.files[f].row << 48);
+                    u0[j] = lo0; u1[j] = lo1; u2[j] = hi0; u3[j] = hi1 | (p.files[f].row << 16);
                     ubr[j] = b | (rank << 16);
                     my_windows += L;
                 }
@@ -289,7 +315,7 @@ k_units_scatter(const UnitScatterParams p) {
                     if (ubr[j] != 0xFFFFFFFFu) {
                         const uint32_t b = ubr[j] & 0xFFFFu;
                         const uint32_t dst = s_off[b] + (ubr[j] >> 16);
-                        s_units[dst] = make_uint4((uint32_t)ulo[j], (uint32_t)(ulo[j] >> 32), (uint32_t)uhi[j], (uint32_t)(uhi[j] >> 32));
+                        s_units[dst] = make_uint4(u0[j], u1[j], u2[j], u3[j]);
                         s_b[dst] = (uint16_t)b;
                     }
                 }
@@ -379,11 +405,9 @@ k_units_dedupe(const UnitDedupeParams p) {
             if (have) {
                 const unsigned long long lo = ((unsigned long long)u.y << 32) | u.x;
                 const unsigned long long hi = ((unsigned long long)u.w << 32) | u.z;
-                const uint32_t row = (uint32_t)(hi >> 48);
+                const uint32_t row = u.w >> 16;
                 const unsigned long long hik = (hi & kUnitHiMask) | ((unsigned long long)(row >> 6) << 48);
-                const unsigned long long bit = 1ULL << (63u - (row & 63u));
-                uint32_t slot = (uint32_t)(unit_hash(lo, hi & kUnitHiMask) >> 8) + (row >> 6) * 0x9E3779B1u;
-                slot &= (uint32_t)kUdSlots - 1u;
+                uint32_t slot = ((unit_hash32(u.x, u.y, u.z, u.w & 0xFFFFu) + (row >> 6)) * 0x297A2D39u) >> (32 - kUdSlotsLog2);
                 bool placed = true;
                 while (true) {
                     unsigned long long l0 = *(volatile unsigned long long*)&k_lo[slot];
@@ -402,10 +426,13 @@ k_units_dedupe(const UnitDedupeParams p) {
                     }
                     slot = (slot + 1u) & ((uint32_t)kUdSlots - 1u);
                 }
-                if (placed) atomicOr(&wd[slot], bit);
+                // presence bit 63 - (row & 63) of the word: a native 32-bit shared-memory OR on the right half
+                // (a 64-bit atomicOr on shared memory compiles to a compare-and-swap loop)
+                const uint32_t r6 = row & 63u;
+                if (placed) atomicOr(reinterpret_cast<uint32_t*>(&wd[slot]) + (r6 < 32u ? 1 : 0), 0x80000000u >> (r6 & 31u));
                 else {
                     const unsigned long long o = atomicAdd(p.needed, 1ULL);
-                    if (o < p.cap) { p.out[3 * o] = lo; p.out[3 * o + 1] = hik; p.out[3 * o + 2] = bit; }
+                    if (o < p.cap) { p.out[3 * o] = lo; p.out[3 * o + 1] = hik; p.out[3 * o + 2] = 1ULL << (63u - r6); }
                 }
             }
         }
