@@ -577,15 +577,17 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
     // ---- unit (super-k-mer) path: contigs and reads without an abundance filter (grmkm_units.cuh)
     const bool use_units = staged && c->cfg.min_abundance <= 1 && !(c->cfg.flags & GRMKM_FLAG_KMER_RECORDS);
     const UnitGeom ug = unit_geom(c->cfg.k);
-    const uint32_t wbits = std::max(1u, ceil_log2(P.W));
+    const uint32_t WB = unit_words_per_entry(P.W);            // presence words per dedupe entry / wide record
+    const uint32_t wbits = std::max(1u, ceil_log2((P.W + WB - 1) / WB));
+    const uint32_t ES = 2 + WB, RS = unit_record_stride(WB);
     uint32_t MB = (uint32_t)c->sm_count;
     if (use_units) {
         // distinct (unit, 64-genome block) entries of a bucket should fit the dedupe table about once
         std::vector<uint64_t> row_bytes(std::max(P.G, 1u), 0);
         for (const Input& in : c->inputs) if (in.row < P.G) row_bytes[in.row] += in.len;
         const uint64_t max_row = *std::max_element(row_bytes.begin(), row_bytes.end());
-        const uint64_t entries = (max_row * 19 / 10) * 2 / (ug.w + 1) * 13 / 10 * P.W;
-        const uint64_t per_wave = (uint64_t)kUdSlots * 6 / 10 * c->sm_count;
+        const uint64_t entries = (max_row * 19 / 10) * 2 / (ug.w + 1) * 13 / 10 * ((P.W + WB - 1) / WB);
+        const uint64_t per_wave = (uint64_t)unit_dedupe_slots(WB) * 6 / 10 * c->sm_count;
         const uint64_t waves = std::max<uint64_t>(1, (entries + per_wave - 1) / per_wave);
         MB = (uint32_t)std::min<uint64_t>(kUsMaxBuckets, waves * c->sm_count);
         if (const char* ub = getenv("GRMKM_UNIT_BUCKETS")) MB = (uint32_t)std::min(kUsMaxBuckets, std::max(1, atoi(ub)));
@@ -792,17 +794,20 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
             if (c->ev_ok) cudaEventRecord(c->ev[T_ABUND], st);
             // ---- dedupe: distinct (unit, block) entries; retried with a larger list if the guess was too small
             uint64_t wcap = std::min<uint64_t>(P.max_stream, std::max<uint64_t>(1 << 16, P.max_stream / 16));
-            const size_t dsm = (size_t)kUdSlots * 24;
-            CU_TRY(c, cudaFuncSetAttribute(k_units_dedupe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-            CU_TRY(c, cudaFuncSetAttribute(k_units_expand<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_smem_bytes(B)));
-            CU_TRY(c, cudaFuncSetAttribute(k_units_expand<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_smem_bytes(B)));
+            const size_t dsm = unit_dedupe_smem(WB), xsm = staged_smem_bytes(B);
+            void (*k_dedupe)(UnitDedupeParams) = WB == 1 ? k_units_dedupe<1> : WB == 2 ? k_units_dedupe<2> : k_units_dedupe<4>;
+            void (*k_xcount)(UnitExpandParams) = WB == 1 ? k_units_expand<true, 1> : WB == 2 ? k_units_expand<true, 2> : k_units_expand<true, 4>;
+            void (*k_xscat)(UnitExpandParams) = WB == 1 ? k_units_expand<false, 1> : WB == 2 ? k_units_expand<false, 2> : k_units_expand<false, 4>;
+            CU_TRY(c, cudaFuncSetAttribute(k_dedupe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+            CU_TRY(c, cudaFuncSetAttribute(k_xcount, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsm));
+            CU_TRY(c, cudaFuncSetAttribute(k_xscat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsm));
             for (int attempt = 0; attempt < 4; ++attempt) {
-                ENSURE(c, c->wu, wcap * 24);
+                ENSURE(c, c->wu, wcap * ES * 8);
                 UnitDedupeParams dp{};
                 dp.units = (const uint4*)c->units.p; dp.begin = (const unsigned long long*)c->ubeg.p;
                 dp.end = (const unsigned long long*)c->ucur.p; dp.n_buckets = MB; dp.out = (unsigned long long*)c->wu.p;
                 dp.cap = wcap; dp.needed = (unsigned long long*)(d_scalars + S_WU_NEEDED);
-                k_units_dedupe<<<std::min<uint32_t>(MB, (uint32_t)c->sm_count), kUdThreads, dsm, st>>>(dp);
+                k_dedupe<<<std::min<uint32_t>(MB, (uint32_t)c->sm_count), kUdThreads, dsm, st>>>(dp);
                 L.n++;
                 CU_TRY(c, cudaGetLastError());
                 if (c->ev_ok) cudaEventRecord(c->ev[T_DEDUPE], st);
@@ -813,7 +818,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
                 xp.cursors = (unsigned long long*)c->hist.p; xp.records = nullptr;
                 const uint32_t xgrid = (uint32_t)std::min<uint64_t>((wcap + kStThreads - 1) / kStThreads, (uint64_t)c->sm_count);
                 CU_TRY(c, cudaMemsetAsync(c->hist.p, 0, (size_t)B * 8, st));
-                k_units_expand<true><<<xgrid, kStThreads, staged_smem_bytes(B), st>>>(xp);
+                k_xcount<<<xgrid, kStThreads, xsm, st>>>(xp);
                 k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->hist.p, (unsigned long long*)c->offsets.p, B,
                                                      d_scalars, S_N_WIDE, kCursorStride);
                 L.n += 2;
@@ -823,9 +828,9 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
                 if (regions && sc[S_OVERFLOW]) { unit_overflow = true; break; }
                 if (sc[S_WU_NEEDED] <= wcap) {
                     // ---- expand, pass 2: scatter the wide records
-                    ENSURE(c, c->wide, (sc[S_N_WIDE] + 1) * 16);
+                    ENSURE(c, c->wide, (sc[S_N_WIDE] + 1) * RS * 8);
                     xp.records = (unsigned long long*)c->wide.p;
-                    k_units_expand<false><<<xgrid, kStThreads, staged_smem_bytes(B), st>>>(xp);
+                    k_xscat<<<xgrid, kStThreads, xsm, st>>>(xp);
                     L.n++;
                     CU_TRY(c, cudaGetLastError());
                     break;
@@ -881,6 +886,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
             ap.records = agg_records; ap.begin = agg_begin; ap.end = agg_end; ap.bucket_bits = P.bucket_bits;
             ap.row_bits = use_units ? wbits : P.row_bits; ap.n_words = P.W; ap.slots = P.slots;
             ap.keep_singletons = c->cfg.keep_singletons; ap.sub_bits = P.sub_bits;
+            ap.wide_words = WB; ap.wide_stride = RS;
             ap.out_keys = (unsigned long long*)c->ukeys.p; ap.out_words = (unsigned long long*)c->uwords.p;
             ap.cap = ucap; ap.scalars = (unsigned long long*)d_scalars;
             ap.bucket_base = (unsigned long long*)c->bbase.p; ap.bucket_count = (unsigned long long*)c->bcounts.p;

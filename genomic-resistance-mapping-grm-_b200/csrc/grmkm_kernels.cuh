@@ -980,6 +980,7 @@ struct AggParams2 {
     const unsigned long long* end;       // [B]
     uint32_t bucket_bits, row_bits, n_words, slots, keep_singletons;
     uint32_t sub_bits;                   // every bucket is aggregated as 2^sub_bits key sub-ranges (virtual buckets), one CTA pass each
+    uint32_t wide_words, wide_stride;    // MODE 4/5: presence words per wide record, u64 per record
     unsigned long long* out_keys;        // [cap]   bucket chunks, at bucket_base[b]
     unsigned long long* out_words;       // [n_words][cap]
     unsigned long long cap;
@@ -1056,7 +1057,8 @@ __device__ __forceinline__ void agg_stream(const AggParams2& p, const AggTable& 
     }
 }
 
-// MODE 4 / 5: wide records [(hash << row_bits) | word index, presence word] (the unit path, grmkm_units.cuh)
+// MODE 4 / 5: wide records [(hash << row_bits) | genome group, wide_words presence words (, padding)] of
+// wide_stride u64 each (the unit path, grmkm_units.cuh); the words of group g are matrix words g * wide_words ..
 template <bool FILTER>
 __device__ __forceinline__ void agg_stream_wide(const AggParams2& p, const AggTable& t, const unsigned long long* __restrict__ recs,
                                                 uint32_t n, uint32_t key_bits, uint32_t depth, unsigned long long ridx,
@@ -1065,6 +1067,7 @@ __device__ __forceinline__ void agg_stream_wide(const AggParams2& p, const AggTa
     const uint32_t wmask = (1u << wbits) - 1u;
     const uint32_t shift = 64 - key_bits + depth;
     const uint32_t slots = t.slots, total = t.total;
+    const uint32_t WB = p.wide_words, stride2 = p.wide_stride / 2;          // record = stride2 x 16 bytes
     unsigned long long* const keys = t.keys;
     uint32_t* const w32 = t.w32;
     const ulonglong2* const rec2 = reinterpret_cast<const ulonglong2*>(recs);
@@ -1074,12 +1077,13 @@ __device__ __forceinline__ void agg_stream_wide(const AggParams2& p, const AggTa
 #pragma unroll
         for (int j = 0; j < kWideBatch; ++j) {
             const uint32_t idx = base + j * kAggThreads;
-            r[j] = idx < n ? __ldcs(rec2 + idx) : make_ulonglong2(0ULL, 0ULL);
+            r[j] = idx < n ? __ldcs(rec2 + (size_t)idx * stride2) : make_ulonglong2(0ULL, 0ULL);
         }
         if (*overflow) break;
 #pragma unroll
         for (int j = 0; j < kWideBatch; ++j) {
-            if (base + j * kAggThreads >= n) break;
+            const uint32_t idx = base + j * kAggThreads;
+            if (idx >= n) break;
             const unsigned long long key = r[j].x >> wbits;
             if (FILTER && ((key << (64 - key_bits)) >> (64 - depth)) != ridx) continue;
             uint32_t slot = home_slot(key, shift, slots);
@@ -1095,10 +1099,19 @@ __device__ __forceinline__ void agg_stream_wide(const AggParams2& p, const AggTa
                 if (++probe >= kMaxProbe) { *overflow = 1; break; }
             }
             if (probe < kMaxProbe) {
-                const uint32_t wi = (uint32_t)r[j].x & wmask;
-                const uint32_t vlo = (uint32_t)r[j].y, vhi = (uint32_t)(r[j].y >> 32);
-                if (vlo) atomicOr(&w32[(2 * wi) * total + slot], vlo);
-                if (vhi) atomicOr(&w32[(2 * wi + 1) * total + slot], vhi);
+                const uint32_t w0 = ((uint32_t)r[j].x & wmask) * WB;
+                {
+                    const uint32_t vlo = (uint32_t)r[j].y, vhi = (uint32_t)(r[j].y >> 32);
+                    if (vlo) atomicOr(&w32[(2 * w0) * total + slot], vlo);
+                    if (vhi) atomicOr(&w32[(2 * w0 + 1) * total + slot], vhi);
+                }
+                const unsigned long long* more = recs + (size_t)idx * p.wide_stride;
+                for (uint32_t w = 1; w < WB; ++w) {
+                    const unsigned long long v = __ldcs(more + 1 + w);
+                    const uint32_t vlo = (uint32_t)v, vhi = (uint32_t)(v >> 32);
+                    if (vlo) atomicOr(&w32[(2 * (w0 + w)) * total + slot], vlo);
+                    if (vhi) atomicOr(&w32[(2 * (w0 + w) + 1) * total + slot], vhi);
+                }
             }
         }
     }
@@ -1253,7 +1266,7 @@ k_aggregate_cols(const AggParams2 p) {
         } else {
             const unsigned long long rbeg = p.begin[b], rend = p.end[b];
             n = rbeg < rend ? (uint32_t)(rend - rbeg) : 0u;
-            recs = p.records + (MODE >= 4 ? 2 * rbeg : rbeg);
+            recs = p.records + (MODE >= 4 ? (unsigned long long)p.wide_stride * rbeg : rbeg);
         }
         if (n == 0) { if (threadIdx.x == 0) { p.bucket_base[vb - vb_base] = 0; p.bucket_count[vb - vb_base] = 0; } continue; }
         // phase 0: the whole (virtual) bucket in one table; on overflow phase 1 counts over its key sub-ranges and

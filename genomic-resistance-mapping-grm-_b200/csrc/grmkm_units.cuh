@@ -334,36 +334,46 @@ k_units_scatter(const UnitScatterParams p) {
     }
 }
 
-// ---- k_units_dedupe: per bucket, distinct (unit content, 64-genome block) -> presence word --------
+// ---- k_units_dedupe: per bucket, distinct (unit content, genome group) -> WB presence words --------
+// An entry holds the presence of WB x 64 consecutive genomes (WB = 1, 2 or 4: all of them when there are at most
+// 256 genomes), so a unit shared by everybody is ONE entry.  Table: slots x (16-byte key + WB words).
 constexpr int kUdThreads = 1024;
-constexpr int kUdSlotsLog2 = 13;
-constexpr int kUdSlots = 1 << kUdSlotsLog2;           // 8192 x 24 bytes = 192 KB
 constexpr int kUdCheck = 8;                            // batches between "is the table filling up" checkpoints
-constexpr int kUdSoft = kUdSlots * 6 / 10;             // flush at a checkpoint above this many entries
-constexpr int kUdHard = kUdSlots - kUdThreads - 64;    // between checkpoints: new keys beyond this bypass the table
+
+__host__ __device__ inline uint32_t unit_words_per_entry(uint32_t W) { return W <= 1 ? 1u : W == 2 ? 2u : 4u; }
+__host__ __device__ inline uint32_t unit_dedupe_slots(uint32_t WB) { return WB == 1 ? 8192u : WB == 2 ? 6144u : 4096u; }
+__host__ __device__ inline size_t unit_dedupe_smem(uint32_t WB) { return (size_t)unit_dedupe_slots(WB) * (16 + 8 * WB); }
+__host__ __device__ inline uint32_t unit_record_stride(uint32_t WB) { return WB == 1 ? 2u : 2u * WB; }   // u64 per wide record
 
 struct UnitDedupeParams {
     const uint4* units;
     const unsigned long long* begin;     // [n_buckets]
     const unsigned long long* end;       // [n_buckets]
     uint32_t n_buckets;
-    unsigned long long* out;             // weighted units [lo, hi (row field = block), word]
+    unsigned long long* out;             // entries [lo, hi (row field = genome group), WB words]
     unsigned long long cap;              // entries
     unsigned long long* needed;          // scalar: entries produced (may exceed cap; the host retries)
 };
 
+template <int WB>
 __global__ void __launch_bounds__(kUdThreads, 1)
 k_units_dedupe(const UnitDedupeParams p) {
     extern __shared__ unsigned long long s_tab[];
     __shared__ uint32_t s_distinct;
     __shared__ uint32_t s_warp[33];
     __shared__ unsigned long long s_base;
+    constexpr uint32_t S = WB == 1 ? 8192u : WB == 2 ? 6144u : 4096u;
+    constexpr uint32_t kSoft = S * 6 / 10;             // flush at a checkpoint above this many entries
+    constexpr uint32_t kHard = S - kUdThreads - 64;    // between checkpoints: new keys beyond this bypass the table
+    constexpr uint32_t GS = WB == 1 ? 6 : WB == 2 ? 7 : 8;   // genome group = row >> GS
+    constexpr uint32_t ES = 2 + WB;                    // u64 per output entry
     unsigned long long* k_lo = s_tab;
-    unsigned long long* k_hi = s_tab + kUdSlots;
-    unsigned long long* wd = s_tab + 2 * kUdSlots;
+    unsigned long long* k_hi = s_tab + S;
+    unsigned long long* wd = s_tab + 2 * S;            // [WB][S]
     const uint32_t tid = threadIdx.x;
-    constexpr uint32_t per = kUdSlots / kUdThreads;
-    for (uint32_t i = tid; i < (uint32_t)kUdSlots; i += kUdThreads) { k_lo[i] = kUnitEmptyLo; k_hi[i] = kUnitEmptyHi; wd[i] = 0ULL; }
+    constexpr uint32_t per = S / kUdThreads;
+    for (uint32_t i = tid; i < S; i += kUdThreads) { k_lo[i] = kUnitEmptyLo; k_hi[i] = kUnitEmptyHi; }
+    for (uint32_t i = tid; i < S * WB; i += kUdThreads) wd[i] = 0ULL;
     if (tid == 0) s_distinct = 0;
     __syncthreads();
     // emit the table's entries and clear it (all inserts are complete when this is called)
@@ -380,8 +390,14 @@ k_units_dedupe(const UnitDedupeParams p) {
             const unsigned long long lo = k_lo[i];
             if (lo != kUnitEmptyLo) {
                 const unsigned long long o = base + off++;
-                if (o < p.cap) { p.out[3 * o] = lo; p.out[3 * o + 1] = k_hi[i]; p.out[3 * o + 2] = wd[i]; }
-                k_lo[i] = kUnitEmptyLo; k_hi[i] = kUnitEmptyHi; wd[i] = 0ULL;
+                if (o < p.cap) {
+                    p.out[ES * o] = lo; p.out[ES * o + 1] = k_hi[i];
+#pragma unroll
+                    for (int w = 0; w < WB; ++w) p.out[ES * o + 2 + w] = wd[w * S + i];
+                }
+                k_lo[i] = kUnitEmptyLo; k_hi[i] = kUnitEmptyHi;
+#pragma unroll
+                for (int w = 0; w < WB; ++w) wd[w * S + i] = 0ULL;
             }
         }
         __syncthreads();
@@ -401,18 +417,19 @@ k_units_dedupe(const UnitDedupeParams p) {
             // Checkpoint every kUdCheck batches (one barrier): flush when the table is filling up.  In between, a
             // NEW key that finds the table nearly full goes straight to the output (duplicates are merged by the
             // column aggregate), so no thread ever waits for a flush.
-            if (bi % kUdCheck == 0 && __syncthreads_or(tid == 0 && s_distinct > (uint32_t)kUdSoft)) flush();
+            if (bi % kUdCheck == 0 && __syncthreads_or(tid == 0 && s_distinct > kSoft)) flush();
             if (have) {
                 const unsigned long long lo = ((unsigned long long)u.y << 32) | u.x;
                 const unsigned long long hi = ((unsigned long long)u.w << 32) | u.z;
                 const uint32_t row = u.w >> 16;
-                const unsigned long long hik = (hi & kUnitHiMask) | ((unsigned long long)(row >> 6) << 48);
-                uint32_t slot = ((unit_hash32(u.x, u.y, u.z, u.w & 0xFFFFu) + (row >> 6)) * 0x297A2D39u) >> (32 - kUdSlotsLog2);
+                const uint32_t grp = row >> GS;
+                const unsigned long long hik = (hi & kUnitHiMask) | ((unsigned long long)grp << 48);
+                uint32_t slot = __umulhi((unit_hash32(u.x, u.y, u.z, u.w & 0xFFFFu) + grp) * 0x297A2D39u, S);
                 bool placed = true;
                 while (true) {
                     unsigned long long l0 = *(volatile unsigned long long*)&k_lo[slot];
                     if (l0 == kUnitEmptyLo) {
-                        if (*(volatile uint32_t*)&s_distinct >= (uint32_t)kUdHard) { placed = false; break; }
+                        if (*(volatile uint32_t*)&s_distinct >= kHard) { placed = false; break; }
                         l0 = atomicCAS(&k_lo[slot], kUnitEmptyLo, lo);
                         if (l0 == kUnitEmptyLo) { atomicAdd(&s_distinct, 1u); l0 = lo; }
                     }
@@ -424,15 +441,19 @@ k_units_dedupe(const UnitDedupeParams p) {
                         }
                         if (h0 == hik) break;
                     }
-                    slot = (slot + 1u) & ((uint32_t)kUdSlots - 1u);
+                    if (++slot == S) slot = 0;
                 }
-                // presence bit 63 - (row & 63) of the word: a native 32-bit shared-memory OR on the right half
-                // (a 64-bit atomicOr on shared memory compiles to a compare-and-swap loop)
-                const uint32_t r6 = row & 63u;
-                if (placed) atomicOr(reinterpret_cast<uint32_t*>(&wd[slot]) + (r6 < 32u ? 1 : 0), 0x80000000u >> (r6 & 31u));
+                // presence bit 63 - (row & 63) of word (row >> 6) % WB: a native 32-bit shared-memory OR on the right
+                // half (a 64-bit atomicOr on shared memory compiles to a compare-and-swap loop)
+                const uint32_t r6 = row & 63u, wj = (row >> 6) & (uint32_t)(WB - 1);
+                if (placed) atomicOr(reinterpret_cast<uint32_t*>(&wd[wj * S + slot]) + (r6 < 32u ? 1 : 0), 0x80000000u >> (r6 & 31u));
                 else {
                     const unsigned long long o = atomicAdd(p.needed, 1ULL);
-                    if (o < p.cap) { p.out[3 * o] = lo; p.out[3 * o + 1] = hik; p.out[3 * o + 2] = 1ULL << (63u - r6); }
+                    if (o < p.cap) {
+                        p.out[ES * o] = lo; p.out[ES * o + 1] = hik;
+#pragma unroll
+                        for (int w = 0; w < WB; ++w) p.out[ES * o + 2 + w] = (uint32_t)w == wj ? 1ULL << (63u - r6) : 0ULL;
+                    }
                 }
             }
         }
@@ -441,16 +462,16 @@ k_units_dedupe(const UnitDedupeParams p) {
     }
 }
 
-// ---- k_units_expand: distinct (unit, block) -> wide records [(hash << wbits) | block, word] by hash range ----
+// ---- k_units_expand: distinct (unit, group) -> wide records [(hash << wbits) | group, WB words (, padding)] by hash range ----
 // Same tile machinery as k_scatter (32 hashed k-mers per thread in registers, counting sort in shared memory,
 // bucket runs on the way out); a thread expands one weighted unit.  COUNT: histogram only (exact offsets).
 struct UnitExpandParams {
-    const unsigned long long* wu;        // [n][3]
+    const unsigned long long* wu;        // [n][2 + WB]
     const unsigned long long* n_ptr;     // entries produced by the dedupe
     unsigned long long cap;              // entries the buffer holds
     uint32_t k, bucket_bits, wbits;
     unsigned long long* cursors;         // [B] histogram (COUNT) or exact offsets
-    unsigned long long* records;         // [total][2]
+    unsigned long long* records;         // [total][unit_record_stride(WB)]
 };
 
 __device__ __forceinline__ void expand_hash_group(const uint32_t (&r)[4], const uint32_t (&y)[4], uint32_t have,
@@ -473,13 +494,14 @@ __device__ __forceinline__ void expand_hash_group(const uint32_t (&r)[4], const 
     }
 }
 
-template <bool COUNT>
+template <bool COUNT, int WB>
 __global__ void __launch_bounds__(kStThreads, 1)
 k_units_expand(const UnitExpandParams p) {
+    constexpr uint32_t ES = 2 + WB;
     extern __shared__ unsigned long long s_dyn[];
     __shared__ uint32_t s_total;
     __shared__ uint32_t s_warp[33];
-    __shared__ unsigned long long s_word[kStThreads];
+    __shared__ unsigned long long s_word[WB][kStThreads];
     __shared__ uint16_t s_blk[kStThreads];
     const uint32_t B = 1u << p.bucket_bits;
     unsigned long long* s_delta = s_dyn;
@@ -502,8 +524,12 @@ k_units_expand(const UnitExpandParams p) {
         unsigned long long hsh[kStPerThread];
         uint32_t have = 0;
         if (i < n) {
-            const unsigned long long lo = p.wu[3 * i], hik = p.wu[3 * i + 1];
-            if (!COUNT) { s_word[tid] = p.wu[3 * i + 2]; s_blk[tid] = (uint16_t)(hik >> 48); }
+            const unsigned long long lo = p.wu[ES * i], hik = p.wu[ES * i + 1];
+            if (!COUNT) {
+#pragma unroll
+                for (int w = 0; w < WB; ++w) s_word[w][tid] = p.wu[ES * i + 2 + w];
+                s_blk[tid] = (uint16_t)(hik >> 48);
+            }
             const uint32_t L = (uint32_t)(lo >> 58) + 1u;
             const unsigned long long Vlo = (lo & kUnitLoMask) | (hik << 58), Vhi = (hik & kUnitHiMask) >> 6;
             // window: the unit's entry t at window entry 33 - k + t, so that its first k-mer ends at window entry 32
@@ -565,7 +591,15 @@ k_units_expand(const UnitExpandParams p) {
             for (uint32_t j = tid; j < total; j += kStThreads) {
                 const unsigned long long h = s_rec[j];
                 const uint32_t src = s_src[j];
-                out[s_delta[(uint32_t)(h >> key_bits)] + j] = make_ulonglong2((h << p.wbits) | s_blk[src], s_word[src]);
+                const unsigned long long o = s_delta[(uint32_t)(h >> key_bits)] + j;
+                const unsigned long long key = (h << p.wbits) | s_blk[src];
+                if (WB == 1) out[o] = make_ulonglong2(key, s_word[0][src]);
+                else {
+#pragma unroll
+                    for (int q = 0; q < WB; ++q)        // record = WB x 16 bytes: key, WB words, padding
+                        out[o * WB + q] = make_ulonglong2(q == 0 ? key : (2 * q <= WB ? s_word[(2 * q - 1) % WB][src] : 0ULL),
+                                                          2 * q < WB ? s_word[(2 * q) % WB][src] : 0ULL);
+                }
             }
             __syncthreads();      // s_word / s_blk / s_rec are rewritten by the next tile
         }
