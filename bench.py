@@ -4,7 +4,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W]          (N>1: launched by torch.distributed.run)
     python bench.py --impl reference [...]                        CPU arm: the oracle port on the host cores
 
-A "step" is one complete build of the workload: FASTA text -> packed stream -> canonical k-mers ->
+A "step" is one complete build of the workload: FASTA text -> packed stream -> minimizer-bounded units
+(super-k-mers) -> content-hash buckets -> per-bucket dedupe across genomes -> k-mers of the distinct units ->
 hash buckets -> shared-memory aggregation -> ordered columns (kmers[U] + matrix[W][U]).
   value : whole-job Gbases/s with the FASTA bytes already resident in HBM (CUDA events, max over ranks)
   e2e   : same metric through the public API with HOST (pinned) buffers: H2D of the text and D2H of
@@ -33,7 +34,7 @@ UNIT = "Gbases/s"
 K = 31
 GENOMES_N1 = 100          # configs[1]
 GENOMES_PER_GPU = 125     # configs[2]: 1000 genomes on 8 GPUs
-CPU_SAMPLE_GENOMES = 32
+CPU_SAMPLE_GENOMES = 100
 
 
 def peaks():
@@ -257,7 +258,7 @@ def main():
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop() if rank == 0 else None
         stats = dict(db.builder.stats)
-        stats.update({k2: v for k2, v in db.local_stats.items() if k2 in ("n_windows", "n_input_bytes", "n_bases", "n_records", "n_buckets")})
+        stats.update({k2: v for k2, v in db.local_stats.items() if k2 in ("n_windows", "n_input_bytes", "n_bases", "n_records", "n_buckets", "n_units", "n_unit_entries", "n_wide", "n_unit_buckets")})
         U_local = db.n_kmers
 
         # ---- e2e: host (pinned) buffers in, kmers + matrix out, every step
@@ -313,14 +314,29 @@ def main():
         W = stats["n_words"]
         n_windows, n_in, U0 = stats["n_windows"], stats["n_input_bytes"], stats["n_kmers"]
         stream_bytes = (stats["n_bases"] + stats["n_records"]) * 12 / 32
-        # algorithmic bytes per launch: scatter reads the packed stream (12 B per 32 entries)
-        # and writes one 8 B record per k-mer window; aggregate reads them back and writes the columns
-        kernels = {
-            "k_scatter": (stage_ms.get("scatter", 0.0), 8.0 * n_windows + stream_bytes),
-            "k_aggregate_cols": (stage_ms.get("aggregate", 0.0), 8.0 * n_windows + U0 * 8.0 * (1 + W)),
-            "k_pack": (stage_ms.get("pack", 0.0), n_in + stream_bytes),
-            "k_tile_summary": (stage_ms.get("parse", 0.0), n_in),
-        }
+        # algorithmic bytes per launch.  Unit path: the packed stream is 12 B and the run masks
+        # 8 B per 32 entries; a unit is 16 B; a dedupe entry (2 + WB) x 8 B; a wide record RS x 8 B.
+        n_units, n_ent, n_wide = stats.get("n_units", 0), stats.get("n_unit_entries", 0), stats.get("n_wide", 0)
+        mask_bytes = (stats["n_bases"] + stats["n_records"]) * 8 / 32
+        WB = 1 if W <= 1 else 2 if W == 2 else 4
+        ent_b, rec_b = (2 + WB) * 8.0, (2 if WB == 1 else 2 * WB) * 8.0
+        if n_units:
+            kernels = {
+                "k_units_scatter": (stage_ms.get("scatter", 0.0), stream_bytes + mask_bytes + 16.0 * n_units),
+                "k_unit_bounds": (stage_ms.get("bounds", 0.0), stream_bytes + mask_bytes),
+                "k_units_dedupe": (stage_ms.get("dedupe", 0.0), 16.0 * n_units + ent_b * n_ent),
+                "k_units_expand": (stage_ms.get("expand", 0.0), 2 * ent_b * n_ent + rec_b * n_wide),
+                "k_aggregate_cols": (stage_ms.get("aggregate", 0.0), rec_b * n_wide + U0 * 8.0 * (1 + W)),
+                "k_pack": (stage_ms.get("pack", 0.0), n_in + stream_bytes),
+                "k_tile_summary": (stage_ms.get("parse", 0.0), n_in),
+            }
+        else:
+            kernels = {
+                "k_scatter": (stage_ms.get("scatter", 0.0), 8.0 * n_windows + stream_bytes),
+                "k_aggregate_cols": (stage_ms.get("aggregate", 0.0), 8.0 * n_windows + U0 * 8.0 * (1 + W)),
+                "k_pack": (stage_ms.get("pack", 0.0), n_in + stream_bytes),
+                "k_tile_summary": (stage_ms.get("parse", 0.0), n_in),
+            }
         dom = max(kernels, key=lambda n: kernels[n][0])
         dom_ms, dom_bytes = kernels[dom]
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
@@ -344,8 +360,11 @@ def main():
                                   "frac": value * b_alg / peak, "unit": "GB/s",
                                   "model": "SURVEY.md 8d: F + 8 + 8 + O bytes per base"},
             "stage_ms": stage_ms,
+            "kernel_gbs": {n: (b / (t * 1e-3) / 1e9 if t > 0 else None) for n, (t, b) in kernels.items()},
             "result": {"n_bases": total_bases, "n_kmers": U_total, "n_genomes": G_total,
-                       "n_buckets": stats["n_buckets"], "n_splits": stats["n_splits"]},
+                       "n_buckets": stats["n_buckets"], "n_splits": stats["n_splits"],
+                       "n_units": n_units, "n_unit_entries": n_ent, "n_wide_records": n_wide,
+                       "n_unit_buckets": stats.get("n_unit_buckets", 0)},
         }
         if world == 1 and not args.no_cpu_baseline:
             host = buf.cpu().numpy()
