@@ -165,6 +165,7 @@ struct Plan {
 size_t agg_smem_budget(const grmkm_ctx* c) {
     // leave room for the kernel's static shared memory
     size_t lim = c->smem_optin ? c->smem_optin : 227 * 1024;
+    lim = (lim + 1024) / kAggCtasPerSm - 1024;       // every resident CTA also costs 1 KB of system shared memory
     return lim - 4096;
 }
 
@@ -175,7 +176,7 @@ uint32_t table_slots(const grmkm_ctx* c, uint32_t W) {
     const size_t budget = agg_smem_budget(c);
     const size_t total = budget / (9 + 8 * (size_t)W);
     if (total < (size_t)kMaxProbe + 256) return 0;
-    return (uint32_t)std::min<size_t>(16384, total - kMaxProbe);
+    return (uint32_t)std::min<size_t>(kAggMaxSlots, total - kMaxProbe);
 }
 size_t table_smem(uint32_t slots, uint32_t W) {
     return (((size_t)slots + kMaxProbe) * (9 + 8 * (size_t)W) + 15) & ~size_t(15);
@@ -595,9 +596,9 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         ENSURE(c, c->ubeg, (size_t)(MB + 1) * 8);
     }
     const bool try_regions = staged && !(c->cfg.flags & GRMKM_FLAG_EXACT_OFFSETS);
-    const uint32_t agrid = std::min<uint32_t>(B, (uint32_t)c->sm_count);
+    const uint32_t agrid = std::min<uint32_t>(B, (uint32_t)c->sm_count * kAggCtasPerSm);
     const uint32_t VB = B << P.sub_bits;            // virtual buckets of the column aggregate
-    const uint32_t vgrid = std::min<uint32_t>(VB, (uint32_t)c->sm_count);
+    const uint32_t vgrid = std::min<uint32_t>(VB, (uint32_t)c->sm_count * kAggCtasPerSm);
     uint64_t sc[S_COUNT];
     uint64_t ucap = 0;
     for (int pass = try_regions ? 0 : 1; pass < 2; ++pass) {
@@ -854,7 +855,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
             AggParams ap{};
             ap.records = agg_records; ap.begin = agg_begin; ap.end = agg_end; ap.B = B; ap.bucket_bits = P.bucket_bits;
             ap.row_bits = P.row_bits; ap.n_words = 1;
-            ap.slots = (uint32_t)std::min<size_t>(16384, budget / 16);
+            ap.slots = (uint32_t)std::min<size_t>(kAggMaxSlots, budget / 16);
             ap.mode = 2; ap.min_abundance = c->cfg.min_abundance; ap.b_begin = 0; ap.b_end = B;
             ap.scalars = (unsigned long long*)d_scalars;
             ap.bucket_out_counts = (unsigned long long*)c->bcounts.p;
@@ -1252,7 +1253,7 @@ int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
     ap.bucket_base = (unsigned long long*)c->bbase.p; ap.bucket_count = (unsigned long long*)c->bcounts.p;
     ap.b_begin = b_lo; ap.b_end = b_hi;
     CU_TRY(c, cudaFuncSetAttribute(k_aggregate_cols<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_aggregate_cols<3><<<std::max(1u, std::min<uint32_t>(nb, (uint32_t)c->sm_count)), kAggThreads, smem, st>>>(ap);
+    k_aggregate_cols<3><<<std::max(1u, std::min<uint32_t>(nb, (uint32_t)c->sm_count * kAggCtasPerSm)), kAggThreads, smem, st>>>(ap);
     L.n++;
     CU_TRY(c, cudaGetLastError());
     uint64_t sc[S_COUNT];

@@ -14,7 +14,12 @@ constexpr int kScanThreads = 256;      // block size of the tile-summary scan ke
 constexpr int kScanTilesPerThread = 4;
 constexpr int kScanTilesPerBlock = kScanThreads * kScanTilesPerThread;  // 1024
 constexpr int kExtractThreads = 256;
-constexpr int kAggThreads = 1024;
+#ifndef GRMKM_AGG_THREADS
+#define GRMKM_AGG_THREADS 1024
+#endif
+constexpr int kAggThreads = GRMKM_AGG_THREADS;      // 1024: one aggregate CTA per SM; 512: two, each with half the table
+constexpr int kAggCtasPerSm = 1024 / kAggThreads;
+constexpr int kAggMaxSlots = 16 * kAggThreads;
 constexpr int kMaxProbe = 96;
 constexpr uint64_t kEmptyKey = ~0ULL;
 constexpr int kCursorStride = 1;       // spacing of the bucket cursors (32 = 256 B apart was measured: no gain)

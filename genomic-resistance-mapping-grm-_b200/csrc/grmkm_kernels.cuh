@@ -998,20 +998,27 @@ struct AggParams2 {
     uint32_t src_woff[16];
 };
 
-// Stream the bucket's records through the table.  Probing starts at the (monotone) home slot and never wraps:
-// kMaxProbe tail slots follow the home range, and a chain longer than kMaxProbe means "does not fit".
-__device__ __forceinline__ bool agg_probe(unsigned long long* keys, uint32_t& slot, unsigned long long key) {
-    int probe = 0;
-    while (true) {
-        unsigned long long k0 = *(volatile unsigned long long*)&keys[slot];
-        if (k0 == key) return true;
-        if (k0 == kEmptyKey) {
-            k0 = atomicCAS(&keys[slot], kEmptyKey, key);
-            if (k0 == kEmptyKey || k0 == key) return true;
+// Probe loops split warps: a lane that finds its slot at the first probe does not wait for its neighbours by itself,
+// and everything after the loop would then run once per fragment (4.2 fragments per warp were measured,
+// profiles/r01_v3).  So every lane of the warp runs every iteration of the record loops (inactive ones predicated
+// off) and the warp is re-converged with __syncwarp() right after each probe loop.
+__device__ __forceinline__ bool agg_insert(unsigned long long* keys, uint32_t& slot, unsigned long long key, bool active) {
+    bool ok = active;
+    if (active) {
+        int probe = 0;
+        while (true) {
+            unsigned long long k0 = *(volatile unsigned long long*)&keys[slot];
+            if (k0 == key) break;
+            if (k0 == kEmptyKey) {
+                k0 = atomicCAS(&keys[slot], kEmptyKey, key);
+                if (k0 == kEmptyKey || k0 == key) break;
+            }
+            ++slot;
+            if (++probe >= kMaxProbe) { ok = false; break; }
         }
-        ++slot;
-        if (++probe >= kMaxProbe) return false;
     }
+    __syncwarp();
+    return ok;
 }
 
 template <bool FILTER>
@@ -1024,34 +1031,27 @@ __device__ __forceinline__ void agg_stream(const AggParams2& p, const AggTable& 
     const uint32_t slots = t.slots, total = t.total;
     unsigned long long* const keys = t.keys;
     uint32_t* const w32 = t.w32;
-    for (uint32_t base = threadIdx.x; base < n; base += kAggThreads * kAggBatch) {
+    for (uint32_t base0 = 0; base0 < n; base0 += kAggThreads * kAggBatch) {
+        const uint32_t base = base0 + threadIdx.x;
         unsigned long long r[kAggBatch];
 #pragma unroll
         for (int j = 0; j < kAggBatch; ++j) {
             const uint32_t idx = base + j * kAggThreads;
             r[j] = idx < n ? __ldcs(recs + idx) : 0ULL;
         }
-        if (*overflow) break;
+        if (__any_sync(0xffffffffu, *overflow != 0)) break;
 #pragma unroll
         for (int j = 0; j < kAggBatch; ++j) {
-            if (base + j * kAggThreads >= n) break;
             const unsigned long long key = r[j] >> row_bits;      // carries (bucket_bits - row_bits) redundant bucket bits on top
-            if (FILTER && ((key << (64 - key_bits)) >> (64 - depth)) != ridx) continue;
+            bool act = base + j * kAggThreads < n;
+            if (FILTER) act = act && ((key << (64 - key_bits)) >> (64 - depth)) == ridx;
             uint32_t slot = home_slot(key, shift, slots);
-            int probe = 0;
-            while (true) {
-                unsigned long long k0 = *(volatile unsigned long long*)&keys[slot];
-                if (k0 == key) break;
-                if (k0 == kEmptyKey) {
-                    k0 = atomicCAS(&keys[slot], kEmptyKey, key);
-                    if (k0 == kEmptyKey || k0 == key) break;
-                }
-                ++slot;
-                if (++probe >= kMaxProbe) { *overflow = 1; break; }
-            }
-            if (probe < kMaxProbe) {
-                const uint32_t row = (uint32_t)r[j] & row_mask;
-                atomicOr(&w32[((row >> 5) ^ 1u) * total + slot], 0x80000000u >> (row & 31u));
+            const bool ok = agg_insert(keys, slot, key, act);
+            if (act) {
+                if (ok) {
+                    const uint32_t row = (uint32_t)r[j] & row_mask;
+                    atomicOr(&w32[((row >> 5) ^ 1u) * total + slot], 0x80000000u >> (row & 31u));
+                } else *overflow = 1;
             }
         }
     }
@@ -1072,46 +1072,39 @@ __device__ __forceinline__ void agg_stream_wide(const AggParams2& p, const AggTa
     uint32_t* const w32 = t.w32;
     const ulonglong2* const rec2 = reinterpret_cast<const ulonglong2*>(recs);
     constexpr int kWideBatch = 4;
-    for (uint32_t base = threadIdx.x; base < n; base += kAggThreads * kWideBatch) {
-        ulonglong2 r[kWideBatch];
+    for (uint32_t base0 = 0; base0 < n; base0 += kAggThreads * kWideBatch) {
+        const uint32_t base = base0 + threadIdx.x;
+        ulonglong2 r[kWideBatch], r2[kWideBatch];                  // [key, word 0], [word 1, word 2]
 #pragma unroll
         for (int j = 0; j < kWideBatch; ++j) {
             const uint32_t idx = base + j * kAggThreads;
             r[j] = idx < n ? __ldcs(rec2 + (size_t)idx * stride2) : make_ulonglong2(0ULL, 0ULL);
+            r2[j] = (idx < n && WB > 1) ? __ldcs(rec2 + (size_t)idx * stride2 + 1) : make_ulonglong2(0ULL, 0ULL);
         }
-        if (*overflow) break;
+        if (__any_sync(0xffffffffu, *overflow != 0)) break;
 #pragma unroll
         for (int j = 0; j < kWideBatch; ++j) {
             const uint32_t idx = base + j * kAggThreads;
-            if (idx >= n) break;
             const unsigned long long key = r[j].x >> wbits;
-            if (FILTER && ((key << (64 - key_bits)) >> (64 - depth)) != ridx) continue;
+            bool act = idx < n;
+            if (FILTER) act = act && ((key << (64 - key_bits)) >> (64 - depth)) == ridx;
             uint32_t slot = home_slot(key, shift, slots);
-            int probe = 0;
-            while (true) {
-                unsigned long long k0 = *(volatile unsigned long long*)&keys[slot];
-                if (k0 == key) break;
-                if (k0 == kEmptyKey) {
-                    k0 = atomicCAS(&keys[slot], kEmptyKey, key);
-                    if (k0 == kEmptyKey || k0 == key) break;
-                }
-                ++slot;
-                if (++probe >= kMaxProbe) { *overflow = 1; break; }
-            }
-            if (probe < kMaxProbe) {
-                const uint32_t w0 = ((uint32_t)r[j].x & wmask) * WB;
-                {
-                    const uint32_t vlo = (uint32_t)r[j].y, vhi = (uint32_t)(r[j].y >> 32);
-                    if (vlo) atomicOr(&w32[(2 * w0) * total + slot], vlo);
-                    if (vhi) atomicOr(&w32[(2 * w0 + 1) * total + slot], vhi);
-                }
-                const unsigned long long* more = recs + (size_t)idx * p.wide_stride;
-                for (uint32_t w = 1; w < WB; ++w) {
-                    const unsigned long long v = __ldcs(more + 1 + w);
-                    const uint32_t vlo = (uint32_t)v, vhi = (uint32_t)(v >> 32);
-                    if (vlo) atomicOr(&w32[(2 * (w0 + w)) * total + slot], vlo);
-                    if (vhi) atomicOr(&w32[(2 * (w0 + w) + 1) * total + slot], vhi);
-                }
+            const bool ok = agg_insert(keys, slot, key, act);
+            if (act) {
+                if (ok) {
+                    const uint32_t w0 = ((uint32_t)r[j].x & wmask) * WB;
+                    {
+                        const uint32_t vlo = (uint32_t)r[j].y, vhi = (uint32_t)(r[j].y >> 32);
+                        if (vlo) atomicOr(&w32[(2 * w0) * total + slot], vlo);
+                        if (vhi) atomicOr(&w32[(2 * w0 + 1) * total + slot], vhi);
+                    }
+                    for (uint32_t w = 1; w < WB; ++w) {
+                        const unsigned long long v = w == 1 ? r2[j].x : w == 2 ? r2[j].y : __ldcs(recs + (size_t)idx * p.wide_stride + 1 + w);
+                        const uint32_t vlo = (uint32_t)v, vhi = (uint32_t)(v >> 32);
+                        if (vlo) atomicOr(&w32[(2 * (w0 + w)) * total + slot], vlo);
+                        if (vhi) atomicOr(&w32[(2 * (w0 + w) + 1) * total + slot], vhi);
+                    }
+                } else *overflow = 1;
             }
         }
     }
@@ -1128,17 +1121,22 @@ __device__ __forceinline__ void agg_stream_parts(const AggParams2& p, const AggT
         const unsigned long long lo = p.bounds[(size_t)s * nb1 + (b - p.b_begin)], hi = p.bounds[(size_t)s * nb1 + (b - p.b_begin) + 1];
         const uint32_t nw = p.src_words[s], wo = p.src_woff[s], width = 1 + nw;
         const unsigned long long* src = p.parts + p.src_off[s];
-        for (unsigned long long i = lo + threadIdx.x; i < hi; i += kAggThreads) {
-            if (*overflow) break;
-            const unsigned long long* ent = src + i * width;
+        for (unsigned long long i0 = lo; i0 < hi; i0 += kAggThreads) {
+            if (__any_sync(0xffffffffu, *overflow != 0)) break;
+            const unsigned long long i = i0 + threadIdx.x;
+            bool act = i < hi;
+            const unsigned long long* ent = src + (act ? i : lo) * width;
             const unsigned long long key = ent[0] & key_mask;
-            if (FILTER && (key >> (key_bits - depth)) != ridx) continue;
+            if (FILTER) act = act && (key >> (key_bits - depth)) == ridx;
             uint32_t slot = home_slot(key, shift, t.slots);
-            if (!agg_probe(t.keys, slot, key)) { *overflow = 1; break; }
-            for (uint32_t w = 0; w < nw; ++w) {
-                const unsigned long long v = ent[1 + w];
-                if ((uint32_t)v) atomicOr(&t.w32[(2 * (wo + w)) * t.total + slot], (uint32_t)v);
-                if ((uint32_t)(v >> 32)) atomicOr(&t.w32[(2 * (wo + w) + 1) * t.total + slot], (uint32_t)(v >> 32));
+            const bool ok = agg_insert(t.keys, slot, key, act);
+            if (act && !ok) *overflow = 1;
+            if (act && ok) {
+                for (uint32_t w = 0; w < nw; ++w) {
+                    const unsigned long long v = ent[1 + w];
+                    if ((uint32_t)v) atomicOr(&t.w32[(2 * (wo + w)) * t.total + slot], (uint32_t)v);
+                    if ((uint32_t)(v >> 32)) atomicOr(&t.w32[(2 * (wo + w) + 1) * t.total + slot], (uint32_t)(v >> 32));
+                }
             }
         }
     }
@@ -1173,7 +1171,8 @@ __global__ void k_merge_bounds(const unsigned long long* __restrict__ parts, uin
 // conflict-free, the inversion walks of neighbouring lanes touch neighbouring slots, and the columns leave in
 // (almost) consecutive order.
 // Pass A: kept flags; kept slots per (chunk, warp) in s_wc.  Returns this thread's occupied count.
-constexpr int kAggMaxChunks = 18;      // (16384 + kMaxProbe) slots / kAggThreads, rounded up
+constexpr int kAggMaxChunks = (kAggMaxSlots + kMaxProbe + kAggThreads - 1) / kAggThreads;
+static_assert(kAggMaxChunks * (kAggThreads / 32) <= kAggThreads, "the scan of the per-(chunk, warp) counts takes one value per thread");
 template <int MODE>
 __device__ __forceinline__ uint32_t agg_mark(const AggParams2& p, const AggTable& t, uint32_t* s_wc) {
     uint32_t occ = 0;
@@ -1191,37 +1190,47 @@ __device__ __forceinline__ uint32_t agg_mark(const AggParams2& p, const AggTable
                 kf = pc >= 2;
             }
         }
-        if (i < t.total) t.kept[i] = (uint8_t)kf;
+        if (i < t.total) t.kept[i] = (uint8_t)(kf << 7);        // bit 7 = kept, bits 0-6 = the rank correction of agg_fix
         const uint32_t bal = __ballot_sync(0xffffffffu, kf != 0);
-        if (lane == 0) s_wc[c * 32 + warp] = (uint32_t)__popc(bal);
+        if (lane == 0) s_wc[c * (kAggThreads / 32) + warp] = (uint32_t)__popc(bal);
     }
     return occ;
 }
 
-// Pass B: exact rank of every kept slot and emission at out[base + rank].  s_wp = exclusive scan of s_wc.
+// Rank of a kept slot = kept slots before it, corrected by the inversions it takes part in.  The home slot is monotone
+// in the key and probing never wraps, so a LATER slot i can only be out of order with the slots [home(key_i), i): a
+// larger key at j < i has home(key_j) >= home(key_i) and sits at or after its home.  Every inversion is therefore found
+// by its later element with a walk as long as that element's displacement (0.5 slots on average at half load, instead
+// of the whole cluster in both directions).
+// Pass B1: the later element of an inversion adds one to the earlier element's correction (bits 0-6 of its flag byte;
+// at most kMaxProbe - 1 = 95 later slots can reach back to a slot, so the counter never touches bit 7).
+__device__ __forceinline__ void agg_fix(const AggTable& t, uint32_t shift) {
+    uint32_t* const kept32 = reinterpret_cast<uint32_t*>(t.kept);
+    for (uint32_t i = threadIdx.x; i < t.total; i += kAggThreads) {
+        if (!(t.kept[i] & 0x80u)) continue;
+        const unsigned long long key = t.keys[i];
+        for (uint32_t j = home_slot(key, shift, t.slots); j < i; ++j)
+            if (t.keys[j] > key && (t.kept[j] & 0x80u)) atomicAdd(&kept32[j >> 2], 1u << (8u * (j & 3u)));
+    }
+}
+
+// Pass B2: emission at out[base + rank].  s_wp = exclusive scan of s_wc.
 template <int MODE>
 __device__ __forceinline__ void agg_emit(const AggParams2& p, const AggTable& t, const uint32_t* s_wp,
-                                         unsigned long long base, uint32_t b, uint32_t key_bits) {
+                                         unsigned long long base, uint32_t b, uint32_t key_bits, uint32_t shift) {
     const unsigned long long key_mask = (1ULL << key_bits) - 1;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t c = 0;
     for (uint32_t i0 = 0; i0 < t.total; i0 += kAggThreads, ++c) {
         const uint32_t i = i0 + threadIdx.x;
-        const bool kf = i < t.total && t.kept[i];
+        const uint32_t flag = i < t.total ? t.kept[i] : 0u;
+        const bool kf = (flag & 0x80u) != 0;
         const uint32_t bal = __ballot_sync(0xffffffffu, kf);
         if (!kf) continue;
         const unsigned long long key = t.keys[i];
-        uint32_t rank = s_wp[c * 32 + warp] + (uint32_t)__popc(bal & ((1u << lane) - 1u));
-        for (uint32_t j = i; j-- > 0;) {                 // inversions with earlier slots of the cluster
-            const unsigned long long kj = t.keys[j];
-            if (kj == kEmptyKey) break;
-            rank -= (t.kept[j] && kj > key);
-        }
-        for (uint32_t j = i + 1; j < t.total; ++j) {      // and with later ones
-            const unsigned long long kj = t.keys[j];
-            if (kj == kEmptyKey) break;
-            rank += (t.kept[j] && kj < key);
-        }
+        uint32_t rank = s_wp[c * (kAggThreads / 32) + warp] + (uint32_t)__popc(bal & ((1u << lane) - 1u)) + (flag & 0x7Fu);
+        for (uint32_t j = home_slot(key, shift, t.slots); j < i; ++j)      // larger keys in front of this one
+            rank -= (t.keys[j] > key && (t.kept[j] & 0x80u));
         const unsigned long long o = base + rank;
         if (o < p.cap) {
             const unsigned long long h = ((unsigned long long)b << key_bits) | (key & key_mask);
@@ -1233,7 +1242,7 @@ __device__ __forceinline__ void agg_emit(const AggParams2& p, const AggTable& t,
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kAggThreads, 1)
+__global__ void __launch_bounds__(kAggThreads, kAggCtasPerSm)
 k_aggregate_cols(const AggParams2 p) {
     extern __shared__ unsigned long long s_tab[];
     __shared__ uint32_t s_overflow, s_sp;
@@ -1248,7 +1257,7 @@ k_aggregate_cols(const AggParams2 p) {
     t.kept = reinterpret_cast<uint8_t*>(t.w32 + 2 * (size_t)p.n_words * t.total);
     const uint32_t key_bits = 64 - p.bucket_bits;
     const uint32_t n_chunks = (t.total + kAggThreads - 1) / kAggThreads;     // <= kAggMaxChunks (slots <= 16384)
-    __shared__ uint32_t s_wc[kAggMaxChunks * 32];
+    __shared__ uint32_t s_wc[kAggMaxChunks * (kAggThreads / 32)];
 
     // A virtual bucket = bucket b restricted to the key sub-range `sub` of 2^sub_bits: the scatter can then use
     // 2^sub_bits fewer buckets (longer runs per tile) than the table size demands.  The CTAs of one bucket's
@@ -1327,9 +1336,10 @@ k_aggregate_cols(const AggParams2 p) {
             __syncthreads();
             uint32_t total_kept, total_occ;
             {
-                const uint32_t v = threadIdx.x < (uint32_t)kAggMaxChunks * 32u && threadIdx.x < n_chunks * 32u ? s_wc[threadIdx.x] : 0u;
+                constexpr uint32_t kWarps = kAggThreads / 32;
+                const uint32_t v = threadIdx.x < n_chunks * kWarps ? s_wc[threadIdx.x] : 0u;
                 const uint32_t e = block_excl_scan<kAggThreads>(v, s_warp, total_kept);
-                if (threadIdx.x < n_chunks * 32u) s_wc[threadIdx.x] = e;
+                if (threadIdx.x < n_chunks * kWarps) s_wc[threadIdx.x] = e;
             }
             if (phase != 2) { block_excl_scan<kAggThreads>(occ, s_warp, total_occ); bucket_occ += total_occ; }
             if (phase == 1) { bucket_total += total_kept; continue; }
@@ -1337,8 +1347,9 @@ k_aggregate_cols(const AggParams2 p) {
                 bucket_total = total_kept;
                 if (threadIdx.x == 0) s_base = atomicAdd(&p.scalars[S_U_NEEDED], (unsigned long long)total_kept);
             }
+            agg_fix(t, 64 - key_bits + depth);
             __syncthreads();
-            agg_emit<MODE>(p, t, s_wc, s_base + emitted, b, key_bits);
+            agg_emit<MODE>(p, t, s_wc, s_base + emitted, b, key_bits, 64 - key_bits + depth);
             emitted += total_kept;
         }
         if (threadIdx.x == 0) {

@@ -418,14 +418,15 @@ k_units_dedupe(const UnitDedupeParams p) {
             // NEW key that finds the table nearly full goes straight to the output (duplicates are merged by the
             // column aggregate), so no thread ever waits for a flush.
             if (bi % kUdCheck == 0 && __syncthreads_or(tid == 0 && s_distinct > kSoft)) flush();
+            // (the warp is re-converged after the probe loop: see agg_insert in grmkm_kernels.cuh)
+            const unsigned long long lo = ((unsigned long long)u.y << 32) | u.x;
+            const unsigned long long hi = ((unsigned long long)u.w << 32) | u.z;
+            const uint32_t row = u.w >> 16;
+            const uint32_t grp = row >> GS;
+            const unsigned long long hik = (hi & kUnitHiMask) | ((unsigned long long)grp << 48);
+            uint32_t slot = __umulhi((unit_hash32(u.x, u.y, u.z, u.w & 0xFFFFu) + grp) * 0x297A2D39u, S);
+            bool placed = true;
             if (have) {
-                const unsigned long long lo = ((unsigned long long)u.y << 32) | u.x;
-                const unsigned long long hi = ((unsigned long long)u.w << 32) | u.z;
-                const uint32_t row = u.w >> 16;
-                const uint32_t grp = row >> GS;
-                const unsigned long long hik = (hi & kUnitHiMask) | ((unsigned long long)grp << 48);
-                uint32_t slot = __umulhi((unit_hash32(u.x, u.y, u.z, u.w & 0xFFFFu) + grp) * 0x297A2D39u, S);
-                bool placed = true;
                 while (true) {
                     unsigned long long l0 = *(volatile unsigned long long*)&k_lo[slot];
                     if (l0 == kUnitEmptyLo) {
@@ -443,6 +444,9 @@ k_units_dedupe(const UnitDedupeParams p) {
                     }
                     if (++slot == S) slot = 0;
                 }
+            }
+            __syncwarp();
+            if (have) {
                 // presence bit 63 - (row & 63) of word (row >> 6) % WB: a native 32-bit shared-memory OR on the right
                 // half (a 64-bit atomicOr on shared memory compiles to a compare-and-swap loop)
                 const uint32_t r6 = row & 63u, wj = (row >> 6) & (uint32_t)(WB - 1);
