@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <string>
 #include <vector>
 
@@ -52,7 +53,7 @@ struct grmkm_ctx {
     size_t smem_optin = 0;
 
     // device buffers (grow-only, reused across builds)
-    DevBuf in, files, hdr0, tsum, tile_file, tile_state, tile_pos, bsum, bstate, bpos, fss, codes, valid, hist,
+    DevBuf in, files, hdr0, tile_file, tile_pub, tile_order, fss, codes, valid, hist,
         offsets, offsets2, bcounts, records, records2, ukeys, uwords, skeys, sidx_a, sidx_b, shist, kmers, matrix,
         scalars, fmt, synth, owner_start, refs, spart, stile_file, bbase, masks, units, ucur, ubeg, wu, wide;
     size_t device_bytes = 0;
@@ -360,8 +361,8 @@ int grmkm_create(const grmkm_config* cfg, grmkm_ctx** out) {
 void grmkm_destroy(grmkm_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    DevBuf* all[] = {&c->in, &c->files, &c->hdr0, &c->tsum, &c->tile_file, &c->tile_state, &c->tile_pos, &c->bsum,
-                     &c->bstate, &c->bpos, &c->fss, &c->codes, &c->valid, &c->hist, &c->offsets, &c->offsets2,
+    DevBuf* all[] = {&c->in, &c->files, &c->hdr0, &c->tile_file, &c->tile_pub, &c->tile_order,
+                     &c->fss, &c->codes, &c->valid, &c->hist, &c->offsets, &c->offsets2,
                      &c->bcounts, &c->records, &c->records2, &c->ukeys, &c->uwords, &c->skeys, &c->sidx_a, &c->sidx_b,
                      &c->shist, &c->kmers, &c->matrix, &c->scalars, &c->fmt, &c->synth, &c->owner_start, &c->refs, &c->spart, &c->stile_file, &c->bbase,
                      &c->masks, &c->units, &c->ucur, &c->ubeg, &c->wu, &c->wide};
@@ -460,18 +461,19 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
     // H2D copy of batch i+1 overlaps parse / pack / scatter of batch i; the scatter appends to the bucket
     // regions, so batches need no merge.  Device-resident inputs (and the exact-offset fallback, which needs
     // a count over everything first) run as one batch.
-    struct Batch { uint32_t f0, f1; uint64_t bytes, staged, tiles; };
+    struct Batch { uint32_t f0, f1; uint64_t bytes, staged, tiles, stream; };
+    // stream entries reserved for a file: every byte yields at most one entry; files start on group boundaries
+    auto stream_cap = [](uint64_t len) { return ((len + 31) & ~31ULL) + 32; };
     bool any_host = false;
-    for (const Input& in : c->inputs) { P.max_stream += in.len; any_host = any_host || !in.dev; }
-    P.in_bytes = P.max_stream;
+    for (const Input& in : c->inputs) { P.max_stream += stream_cap(in.len); P.in_bytes += in.len; any_host = any_host || !in.dev; }
     auto make_batches = [&](bool pipelined) {
         std::vector<Batch> v;
         const uint64_t target = pipelined ? c->batch_bytes : ~0ULL;
-        Batch cur{0, 0, 0, 0, 0};
+        Batch cur{0, 0, 0, 0, 0, 0};
         for (uint32_t f = 0; f < P.F; ++f) {
             const Input& in = c->inputs[f];
-            if (cur.f1 > cur.f0 && cur.bytes + in.len > target) { v.push_back(cur); cur = Batch{f, f, 0, 0, 0}; }
-            cur.f1 = f + 1; cur.bytes += in.len;
+            if (cur.f1 > cur.f0 && cur.bytes + in.len > target) { v.push_back(cur); cur = Batch{f, f, 0, 0, 0, 0}; }
+            cur.f1 = f + 1; cur.bytes += in.len; cur.stream += stream_cap(in.len);
             if (!in.dev) cur.staged += (in.len + 15) & ~15ULL;
             cur.tiles += std::max<uint64_t>(1, (in.len + kTileBytes - 1) / kTileBytes);
         }
@@ -502,69 +504,73 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
     CU_TRY(c, cudaMemsetAsync(c->scalars.p, 0, S_COUNT * 8, st));
     uint64_t h2d = 0;
     std::vector<std::vector<FileDesc>> fds_keep;      // host tables stay alive until the final synchronize
+    std::deque<std::vector<uint64_t>> u64_keep;
+    std::deque<std::vector<uint32_t>> u32_keep;
 
     // parse + pack of one batch: leaves codes / valid / fss / S_STREAM_LEN of the batch
     auto front = [&](const Batch& bt, const uint8_t* staged_base, bool timed) -> int {
         const uint32_t F = bt.f1 - bt.f0;
-        const uint64_t n_tiles = bt.tiles, n_sblk = (n_tiles + kScanTilesPerBlock - 1) / kScanTilesPerBlock;
-        const uint64_t n_groups_max = bt.bytes / 32 + 2;
+        const uint64_t n_tiles = bt.tiles;
+        const uint64_t n_groups_max = bt.stream / 32 + 2;
         if (n_tiles > 0x7fffffffULL) return fail(c, GRMKM_E_UNSUPPORTED, "input too large for one build (tile count)");
         ENSURE(c, c->files, F * sizeof(FileDesc));
         ENSURE(c, c->hdr0, F * 8);
         ENSURE(c, c->fss, (F + 1) * 8);
-        ENSURE(c, c->tsum, n_tiles * sizeof(Sum));
         ENSURE(c, c->tile_file, n_tiles * 4);
-        ENSURE(c, c->tile_state, n_tiles);
-        ENSURE(c, c->tile_pos, n_tiles * 8);
-        ENSURE(c, c->bsum, n_sblk * sizeof(Sum));
-        ENSURE(c, c->bstate, n_sblk * 4);
-        ENSURE(c, c->bpos, n_sblk * 8);
+        ENSURE(c, c->tile_pub, (3 * n_tiles + 1) * 8);    // published tile summaries / states (look-back) + the ticket counter
         ENSURE(c, c->codes, n_groups_max * 8);
         ENSURE(c, c->valid, n_groups_max * 4);
+        ENSURE(c, c->tile_order, n_tiles * 4);
         fds_keep.emplace_back(F);
         std::vector<FileDesc>& fds = fds_keep.back();
-        uint64_t tiles = 0, soff = 0;
+        u64_keep.emplace_back(F + 1);
+        std::vector<uint64_t>& fss = u64_keep.back();                 // where every file's entries start in the stream
+        u32_keep.emplace_back((size_t)n_tiles);
+        std::vector<uint32_t>& order = u32_keep.back();               // ticket -> tile: round-robin over the files
+        uint64_t tiles = 0, soff = 0, spos = 0;
+        std::vector<std::pair<uint64_t, uint32_t>> by_tiles(F);       // (tile count, file), most tiles first
         for (uint32_t i = 0; i < F; ++i) {
             const Input& in = c->inputs[bt.f0 + i];
             fds[i].len = in.len; fds[i].row = in.row; fds[i].kind = in.kind; fds[i].tile_begin = tiles;
-            tiles += std::max<uint64_t>(1, (in.len + kTileBytes - 1) / kTileBytes);
+            const uint64_t nt = std::max<uint64_t>(1, (in.len + kTileBytes - 1) / kTileBytes);
+            by_tiles[i] = {nt, i};
+            tiles += nt;
+            fss[i] = spos; spos += stream_cap(in.len);
             if (in.dev) fds[i].ptr = in.dev;
             else { fds[i].ptr = staged_base + soff; soff += (in.len + 15) & ~15ULL; }
         }
+        fss[F] = spos;
+        std::sort(by_tiles.begin(), by_tiles.end(), [](const std::pair<uint64_t, uint32_t>& a, const std::pair<uint64_t, uint32_t>& b) {
+            return a.first != b.first ? a.first > b.first : a.second < b.second; });
+        {
+            size_t o = 0, live = F;                                    // files that still have a tile number `l`
+            for (uint64_t l = 0; o < n_tiles; ++l) {
+                while (live > 0 && by_tiles[live - 1].first <= l) --live;
+                for (size_t q = 0; q < live; ++q) order[o++] = (uint32_t)(fds[by_tiles[q].second].tile_begin + l);
+            }
+        }
         d_files = (const FileDesc*)c->files.p;
         CU_TRY(c, cudaMemcpyAsync(c->files.p, fds.data(), F * sizeof(FileDesc), cudaMemcpyHostToDevice, st));
+        CU_TRY(c, cudaMemcpyAsync(c->fss.p, fss.data(), (F + 1) * 8, cudaMemcpyHostToDevice, st));
+        CU_TRY(c, cudaMemcpyAsync(c->tile_order.p, order.data(), n_tiles * 4, cudaMemcpyHostToDevice, st));
         CU_TRY(c, cudaMemsetAsync(c->codes.p, 0, n_groups_max * 8, st));
         CU_TRY(c, cudaMemsetAsync(c->valid.p, 0, n_groups_max * 4, st));
+        CU_TRY(c, cudaMemsetAsync(c->tile_pub.p, 0, (3 * n_tiles + 1) * 8, st));
         if (timed && c->ev_ok) cudaEventRecord(c->ev[T_H2D], st);
         k_first_header<<<(F * 32 + 255) / 256, 256, 0, st>>>(d_files, F, (uint64_t*)c->hdr0.p);
         k_tile_files<<<(uint32_t)((n_tiles + 255) / 256), 256, 0, st>>>(d_files, F, n_tiles, (uint32_t*)c->tile_file.p);
-        if (c->cfg.input_kind == GRMKM_FASTA)
-            k_tile_summary<0><<<(uint32_t)n_tiles, kParseThreads, 0, st>>>(d_files, (const uint64_t*)c->hdr0.p, n_tiles,
-                                                                           (const uint32_t*)c->tile_file.p, (Sum*)c->tsum.p);
-        else
-            k_tile_summary<1><<<(uint32_t)n_tiles, kParseThreads, 0, st>>>(d_files, (const uint64_t*)c->hdr0.p, n_tiles,
-                                                                           (const uint32_t*)c->tile_file.p, (Sum*)c->tsum.p);
-        k_scan_reduce<<<(uint32_t)n_sblk, kScanThreads, 0, st>>>((const Sum*)c->tsum.p, n_tiles, (Sum*)c->bsum.p);
-        k_scan_blocks<<<1, 1024, 0, st>>>((const Sum*)c->bsum.p, (uint32_t)n_sblk, (uint32_t*)c->bstate.p,
-                                          (uint64_t*)c->bpos.p, d_scalars, (uint64_t*)c->fss.p, F);
-        k_scan_apply<<<(uint32_t)n_sblk, kScanThreads, 0, st>>>((const Sum*)c->tsum.p, n_tiles,
-                                                                (const uint32_t*)c->bstate.p, (const uint64_t*)c->bpos.p,
-                                                                (const uint32_t*)c->tile_file.p, d_files,
-                                                                (uint8_t*)c->tile_state.p, (uint64_t*)c->tile_pos.p,
-                                                                (uint64_t*)c->fss.p);
-        L.n += 6;
+        L.n += 2;
         CU_TRY(c, cudaGetLastError());
         if (timed && c->ev_ok) cudaEventRecord(c->ev[T_PARSE], st);
-        if (c->cfg.input_kind == GRMKM_FASTA)
-            k_pack<0><<<(uint32_t)n_tiles, kParseThreads, 0, st>>>(d_files, (const uint64_t*)c->hdr0.p, n_tiles,
-                                                                   (const uint32_t*)c->tile_file.p, (const uint8_t*)c->tile_state.p,
-                                                                   (const uint64_t*)c->tile_pos.p, (unsigned long long*)c->codes.p,
-                                                                   (uint32_t*)c->valid.p, d_scalars);
-        else
-            k_pack<1><<<(uint32_t)n_tiles, kParseThreads, 0, st>>>(d_files, (const uint64_t*)c->hdr0.p, n_tiles,
-                                                                   (const uint32_t*)c->tile_file.p, (const uint8_t*)c->tile_state.p,
-                                                                   (const uint64_t*)c->tile_pos.p, (unsigned long long*)c->codes.p,
-                                                                   (uint32_t*)c->valid.p, d_scalars);
+        // single pass: summaries are published and resolved by look-back inside k_pack (grmkm_kernels.cuh)
+        PackParams pp{};
+        pp.files = d_files; pp.hdr0 = (const uint64_t*)c->hdr0.p; pp.n_tiles = n_tiles; pp.n_files = F;
+        pp.tile_file = (const uint32_t*)c->tile_file.p; pp.ticket = (uint32_t*)((unsigned long long*)c->tile_pub.p + 3 * n_tiles);
+        pp.pub_a0 = (unsigned long long*)c->tile_pub.p; pp.pub_a1 = pp.pub_a0 + n_tiles; pp.pub_ps = pp.pub_a0 + 2 * n_tiles;
+        pp.file_stream_start = (const uint64_t*)c->fss.p; pp.order = (const uint32_t*)c->tile_order.p; pp.stream_len = bt.stream;
+        pp.codes = (unsigned long long*)c->codes.p; pp.valid = (uint32_t*)c->valid.p; pp.scalars = d_scalars;
+        if (c->cfg.input_kind == GRMKM_FASTA) k_pack<0><<<(uint32_t)n_tiles, kParseThreads, 0, st>>>(pp);
+        else k_pack<1><<<(uint32_t)n_tiles, kParseThreads, 0, st>>>(pp);
         L.n++;
         CU_TRY(c, cudaGetLastError());
         if (timed && c->ev_ok) cudaEventRecord(c->ev[T_PACK], st);
@@ -669,7 +675,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
             if (pipelined) CU_TRY(c, cudaEventRecord(c->ev_free[bi & 1], st));     // the staged text has been consumed
 
             const uint32_t F = bt.f1 - bt.f0;
-            const uint64_t n_groups_max = bt.bytes / 32 + 2;
+            const uint64_t n_groups_max = bt.stream / 32 + 2;
             const uint64_t n_stiles = (n_groups_max + (kStTile / 32) - 1) / (kStTile / 32);
             if (use_units) {
                 ENSURE(c, c->masks, n_groups_max * 8);

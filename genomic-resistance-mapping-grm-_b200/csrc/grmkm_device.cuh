@@ -7,12 +7,9 @@
 
 namespace grmkm {
 
-constexpr int kParseThreads = 128;
+constexpr int kParseThreads = 256;
 constexpr int kChunksPerThread = 4;    // 16-byte chunks per thread: 64 contiguous bytes
-constexpr int kTileBytes = kParseThreads * kChunksPerThread * 16;   // 8192 input bytes per parse tile
-constexpr int kScanThreads = 256;      // block size of the tile-summary scan kernels
-constexpr int kScanTilesPerThread = 4;
-constexpr int kScanTilesPerBlock = kScanThreads * kScanTilesPerThread;  // 1024
+constexpr int kTileBytes = kParseThreads * kChunksPerThread * 16;   // 16384 input bytes per parse tile
 constexpr int kExtractThreads = 256;
 #ifndef GRMKM_AGG_THREADS
 #define GRMKM_AGG_THREADS 1024
@@ -221,18 +218,20 @@ __device__ __forceinline__ Sum chunk_summary(const Chunk16& ch, uint32_t prev, u
 }
 
 // ---- compact FASTA path ------------------------------------------------------------------------
-// Inside a 4 KiB tile the FASTA transducer fits one u32: bits 0-13 entries emitted after the first
-// line start (c_rest), bits 14-27 sequence bytes before it (c_head, emitted only when the chunk
-// starts inside a sequence line), bits 28-29 type of the last line start (0 none, 1 header, 2 seq).
+// Inside one parse tile the FASTA transducer fits one u32: bits 0-14 entries emitted after the first line start
+// (c_rest), bits 15-29 sequence bytes before it (c_head, emitted only when the chunk starts inside a sequence
+// line), bits 30-31 type of the last line start (0 none, 1 header, 2 seq).
+constexpr uint32_t kFaH = 15, kFaT = 30, kFaMask = (1u << kFaH) - 1u;
+static_assert(kTileBytes <= (int)kFaMask, "the compact FASTA summary counts a tile's entries in 15 bits");
 __device__ __forceinline__ uint32_t fa_combine(uint32_t A, uint32_t B) {
-    const uint32_t ta = A >> 28, tb = B >> 28, hb = (B >> 14) & 0x3FFFu;
-    uint32_t r = (A & 0x0FFFFFFFu) + (B & 0x3FFFu);
-    r += (ta == 0) ? (hb << 14) : 0u;
+    const uint32_t ta = A >> kFaT, tb = B >> kFaT, hb = (B >> kFaH) & kFaMask;
+    uint32_t r = (A & ((1u << kFaT) - 1u)) + (B & kFaMask);
+    r += (ta == 0) ? (hb << kFaH) : 0u;
     r += (ta == 2) ? hb : 0u;
-    return r | ((tb ? tb : ta) << 28);
+    return r | ((tb ? tb : ta) << kFaT);
 }
 __device__ __forceinline__ Sum fa_to_sum(uint32_t a) {
-    const uint32_t t = a >> 28, c_rest = a & 0x3FFFu, c_head = (a >> 14) & 0x3FFFu;
+    const uint32_t t = a >> kFaT, c_rest = a & kFaMask, c_head = (a >> kFaH) & kFaMask;
     Sum r; r.e = t ? (t - 1) * 0x55u : 0xE4u; r.c0 = c_rest; r.c1 = c_rest + c_head; r.c2 = 0; r.c3 = 0;
     return r;
 }
@@ -296,7 +295,7 @@ __device__ __forceinline__ FaChunk fa_chunk(const Chunk16& ch, uint32_t prev, ui
         }
         prev = c;
     }
-    r.sum = rn | (hn << 14) | (t << 28);
+    r.sum = rn | (hn << kFaH) | (t << kFaT);
     return r;
 }
 
@@ -348,38 +347,19 @@ struct FaParts {
     __device__ __forceinline__ uint32_t rn() const { return (meta >> 8) & 0xFFu; }
     __device__ __forceinline__ uint32_t t() const { return (meta >> 16) & 0xFu; }
     __device__ __forceinline__ uint32_t nrec() const { return meta >> 20; }
-    __device__ __forceinline__ uint32_t sum() const { return rn() | (hn() << 14) | (t() << 28); }
+    __device__ __forceinline__ uint32_t sum() const { return rn() | (hn() << kFaH) | (t() << kFaT); }
 };
 
 // the byte-loop versions stay out of line: they are rare, and inlining four copies of them costs ~200 registers
-__device__ __noinline__ uint32_t fa_chunk_sum_slow(const Chunk16& ch, uint32_t prev, uint64_t pos0, uint64_t len, uint64_t hdr0) {
-    return fa_chunk<false>(ch, prev, pos0, len, hdr0).sum;
-}
 __device__ __noinline__ FaParts fa_chunk_parts_slow(const Chunk16& ch, uint32_t prev, uint64_t pos0, uint64_t len, uint64_t hdr0) {
     const FaChunk fc = fa_chunk<true>(ch, prev, pos0, len, hdr0);
     FaParts r;
     r.hc = fc.head_c; r.rc = fc.rest_c; r.hv_rv = fc.head_v | (fc.rest_v << 16);
-    r.meta = ((fc.sum >> 14) & 0x3FFFu) | ((fc.sum & 0x3FFFu) << 8) | ((fc.sum >> 28) << 16) | (fc.nrec << 20);
+    r.meta = ((fc.sum >> kFaH) & kFaMask) | ((fc.sum & kFaMask) << 8) | ((fc.sum >> kFaT) << 16) | (fc.nrec << 20);
     return r;
 }
 
-// compact summary only (pass 1)
-__device__ __forceinline__ uint32_t fa_chunk_sum(const Chunk16& ch, uint32_t prev, uint64_t pos0, uint64_t len, uint64_t hdr0) {
-    if (fa_fast_ok(pos0, len, hdr0)) {
-        const FaBits b = fa_classify<false>(ch);
-        if (b.low == b.nl) {
-            const uint32_t ls = ((b.nl << 1) | (prev == '\n')) & 0xFFFFu;
-            if (ls == 0) return (16u - (b.nl >> 15)) << 14;
-            const uint32_t q = __ffs(ls) - 1;
-            const uint32_t hn = q ? q - 1 : 0u;
-            const uint32_t rn = (16u - q) - __popc(b.nl >> q);
-            return rn | (hn << 14) | (2u << 28);
-        }
-    }
-    return fa_chunk_sum_slow(ch, prev, pos0, len, hdr0);
-}
-
-// full entries (pass 2)
+// entries of one chunk
 __device__ __forceinline__ FaParts fa_chunk_parts(const Chunk16& ch, uint32_t prev, uint64_t pos0, uint64_t len, uint64_t hdr0) {
     FaParts r;
     if (fa_fast_ok(pos0, len, hdr0)) {

@@ -1,6 +1,6 @@
 // grmkm_kernels.cuh -- the sm_100a kernels of the k-mer matrix path.
 //
-//   parse   : k_first_header, k_tile_summary, k_scan_reduce/blocks/apply, k_pack
+//   parse   : k_first_header, k_tile_files, k_pack (one pass: tile summaries resolved by decoupled look-back)
 //             FASTA/FASTQ text -> dense 2-bit base stream + validity mask   (multidsk's bank reader)
 //   extract : k_extract<COUNT|SCATTER>
 //             canonical k-mers -> hash buckets                              (multidsk's partitioning)
@@ -92,146 +92,188 @@ __global__ void k_tile_files(const FileDesc* __restrict__ files, uint32_t n_file
     if (tile < n_tiles) tile_file[tile] = find_file(files, n_files, tile);
 }
 
-// ordered fold of the compact FASTA summaries of a block (result valid in thread 0)
-__device__ __forceinline__ uint32_t block_fold_fa(uint32_t v, uint32_t* s_w) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// ---- single-pass parse: decoupled look-back over the tile summaries --------------------------------------
+// The parser is a transducer scan (tile summary = state -> (end state, entries emitted), composition associative).
+// Instead of summary kernel + scan kernels + pack kernel (the text read twice), k_pack publishes its tile's
+// summary as soon as the block scan has produced it, and one warp walks back over the earlier tiles' published
+// summaries until it meets a tile whose incoming (state, position) is already resolved.  Tiles take their index
+// from a ticket counter, so every tile a CTA waits for has started and publishes without waiting for anybody.
+// Every published word validates itself (bit 63; the arrays are zeroed before the launch), so a reader needs one
+// round trip per window of 64 tiles and no fences:
+//   a0[t] = 1<<63 | e << 48 | c0 << 24 | c1      summary: end states, entries emitted from state 0 / 1
+//   a1[t] = 1<<63 | c2 << 24 | c3                (FASTQ only: states 2 and 3)
+//   ps[t] = 1<<63 | state << 61 | position       state and stream position at the tile's first byte
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+constexpr unsigned long long kPubValid = 1ULL << 63;
+__device__ __forceinline__ unsigned long long pub_a0(const Sum& s) {
+    return kPubValid | ((unsigned long long)(s.e & 0xFFu) << 48) | ((unsigned long long)(s.c0 & 0xFFFFFFu) << 24) | (s.c1 & 0xFFFFFFu);
+}
+__device__ __forceinline__ unsigned long long pub_a1(const Sum& s) {
+    return kPubValid | ((unsigned long long)(s.c2 & 0xFFFFFFu) << 24) | (s.c3 & 0xFFFFFFu);
+}
+__device__ __forceinline__ Sum pub_sum(unsigned long long a0, unsigned long long a1) {
+    Sum r;
+    r.e = (uint32_t)(a0 >> 48) & 0xFFu; r.c0 = (uint32_t)(a0 >> 24) & 0xFFFFFFu; r.c1 = (uint32_t)a0 & 0xFFFFFFu;
+    r.c2 = (uint32_t)(a1 >> 24) & 0xFFFFFFu; r.c3 = (uint32_t)a1 & 0xFFFFFFu;
+    return r;
+}
+static_assert(kTileBytes < (1 << 24), "a tile's entry counts are published in 24 bits");
+__device__ __forceinline__ Sum sum_shfl_down(const Sum& a, int d) {
+    Sum r;
+    r.e = __shfl_down_sync(0xffffffffu, a.e, d);
+    r.c0 = __shfl_down_sync(0xffffffffu, a.c0, d);
+    r.c1 = __shfl_down_sync(0xffffffffu, a.c1, d);
+    r.c2 = __shfl_down_sync(0xffffffffu, a.c2, d);
+    r.c3 = __shfl_down_sync(0xffffffffu, a.c3, d);
+    return r;
+}
+// ordered fold of one Sum per lane (lane 0 first); the result is valid in every lane
+__device__ __forceinline__ Sum warp_fold_sum(Sum s) {
+    const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t o = __shfl_down_sync(0xffffffffu, v, d);
-        if (lane + d < 32) v = fa_combine(v, o);      // lane i: fold of lanes [i, i + 2d)
+        const Sum o = sum_shfl_down(s, d);
+        if (lane + d < 32) s = sum_combine(s, o);              // lane i: fold of lanes [i, i + 2d)
     }
-    if (lane == 0) s_w[warp] = v;
-    __syncthreads();
-    uint32_t tot = 0;
-    if (threadIdx.x == 0) for (int w = 0; w < kParseThreads / 32; ++w) tot = fa_combine(tot, s_w[w]);
-    return tot;
+    Sum w;
+    w.e = __shfl_sync(0xffffffffu, s.e, 0); w.c0 = __shfl_sync(0xffffffffu, s.c0, 0); w.c1 = __shfl_sync(0xffffffffu, s.c1, 0);
+    w.c2 = __shfl_sync(0xffffffffu, s.c2, 0); w.c3 = __shfl_sync(0xffffffffu, s.c3, 0);
+    return w;
 }
-
-// per-tile transducer summary (KIND: all inputs of a context share cfg.input_kind)
+// one full warp; state and stream position at the first byte of `tile`.  Every file starts in state 0 at a stream
+// position the host fixes in advance (file_stream_start: the file's length rounded up to whole groups bounds its
+// entries, the gap reads as invalid entries, and no window spans two files anyway), so the chain of a tile ends at
+// its file's first tile: tiles before it count as published (identity) and resolved (state 0, that position).
+// Tickets are dealt round-robin over the files (PackParams::order), so the tile a CTA depends on was started one
+// whole round earlier and is normally resolved by the time it is asked.
+// The counts folded here cover only tiles that are in flight, far below 2^32 entries.
+// kLbWindows x 32 tiles are polled per round trip (lane 31 of window 0 = the nearest tile): the resolved front
+// trails the newest published tile by (tiles per microsecond) x (poll latency), and a poll that does not reach it
+// costs a whole extra round trip.
+constexpr int kLbWindows = 2;
 template <int KIND>
-__global__ void __launch_bounds__(kParseThreads)
-k_tile_summary(const FileDesc* __restrict__ files, const uint64_t* __restrict__ hdr0, uint64_t n_tiles,
-               const uint32_t* __restrict__ tile_file, Sum* __restrict__ tsum) {
-    __shared__ Sum s_w[kParseThreads / 32];
-    const uint64_t tile = blockIdx.x;
-    if (tile >= n_tiles) return;
-    const TileCtx t = tile_context(files, hdr0, tile, tile_file[tile]);
-    const ThreadText x = load_thread_text(t);
-    Sum total;
-    if (KIND == 0) {
-        uint32_t mine = 0;
+__device__ __noinline__ void tile_lookback(uint64_t tile, uint64_t first, uint64_t pos_first, const unsigned long long* a0,
+                                           const unsigned long long* a1, const unsigned long long* ps, uint32_t& st, uint64_t& pos) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long ident = kPubValid | (0xE4ULL << 48);      // the identity summary, published
+    Sum acc = sum_identity();                      // fold of the tiles between the resolved one and `tile`
+    long long hi = (long long)tile - 1;            // nearest tile not folded yet
+    while (true) {
+        unsigned long long w0[kLbWindows], w1[kLbWindows], wp[kLbWindows];
 #pragma unroll
-        for (int c = 0; c < kChunksPerThread; ++c)
-            mine = fa_combine(mine, fa_chunk_sum(x.ch[c], x.prev[c], t.off + 16 * c, t.fd.len, t.hdr0));
-        total = fa_to_sum(block_fold_fa(mine, reinterpret_cast<uint32_t*>(s_w)));
-    } else {
-        Sum mine = sum_identity(), excl;
+        for (int w = 0; w < kLbWindows; ++w) {
+            const long long j = hi - 32 * w - 31 + lane;
+            w0[w] = ident; w1[w] = kPubValid; wp[w] = kPubValid | pos_first;
+            if (j >= (long long)first) { w0[w] = ld_relaxed_u64(a0 + j); wp[w] = ld_relaxed_u64(ps + j); if (KIND == 1) w1[w] = ld_relaxed_u64(a1 + j); }
+        }
+        bool done = false;
+        int folded = 0;                            // windows of this poll that are folded into acc
 #pragma unroll
-        for (int c = 0; c < kChunksPerThread; ++c)
-            mine = sum_combine(mine, chunk_summary<1>(x.ch[c], x.prev[c], t.off + 16 * c, t.fd.len, t.hdr0));
-        block_scan_sum(mine, excl, total, s_w);
-    }
-    if (threadIdx.x == 0) {
-        if (t.first_tile) total = sum_fix_start(total, 0);
-        tsum[tile] = total;
-    }
-}
-
-// fold of kScanTilesPerBlock consecutive tile summaries
-__global__ void __launch_bounds__(kScanThreads)
-k_scan_reduce(const Sum* __restrict__ tsum, uint64_t n_tiles, Sum* __restrict__ bsum) {
-    __shared__ Sum s_w[kScanThreads / 32];
-    const uint64_t base = (uint64_t)blockIdx.x * kScanTilesPerBlock + (uint64_t)threadIdx.x * kScanTilesPerThread;
-    Sum mine = sum_identity();
-#pragma unroll
-    for (int i = 0; i < kScanTilesPerThread; ++i)
-        if (base + i < n_tiles) mine = sum_combine(mine, tsum[base + i]);
-    Sum excl, total;
-    block_scan_sum(mine, excl, total, s_w);
-    if (threadIdx.x == 0) bsum[blockIdx.x] = total;
-}
-
-// serial resolution of the block aggregates (tile 0 is a file's first tile, so the start state is moot)
-__global__ void k_scan_blocks(const Sum* __restrict__ bsum, uint32_t n_blocks, uint32_t* __restrict__ bstate,
-                              uint64_t* __restrict__ bpos, uint64_t* __restrict__ scalars,
-                              uint64_t* __restrict__ file_stream_start, uint32_t n_files) {
-    __shared__ Sum s[1024];
-    __shared__ uint32_t s_state;
-    __shared__ uint64_t s_pos;
-    if (threadIdx.x == 0) { s_state = 0; s_pos = 0; }
-    for (uint32_t base = 0; base < n_blocks; base += 1024) {
-        const uint32_t n = min(1024u, n_blocks - base);
-        __syncthreads();
-        if (threadIdx.x < n) s[threadIdx.x] = bsum[base + threadIdx.x];
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t st = s_state; uint64_t pos = s_pos;
-            for (uint32_t i = 0; i < n; ++i) {
-                bstate[base + i] = st; bpos[base + i] = pos;
-                pos += sum_cnt(s[i], st); st = sum_end(s[i], st);
+        for (int w = 0; w < kLbWindows; ++w) {
+            const bool rdy_l = (w0[w] & w1[w] & kPubValid) != 0;
+            const uint32_t rdy = __ballot_sync(0xffffffffu, rdy_l);
+            const uint32_t res = __ballot_sync(0xffffffffu, rdy_l && (wp[w] & kPubValid));
+            if (w == 0 && (res >> 31)) {
+                // the usual case: the tile right before this one is resolved (no fold; a fold costs ~600 instructions)
+                const unsigned long long q0 = __shfl_sync(0xffffffffu, w0[0], 31), q1 = __shfl_sync(0xffffffffu, w1[0], 31);
+                const unsigned long long r = __shfl_sync(0xffffffffu, wp[0], 31);
+                const Sum a = sum_combine(pub_sum(q0, q1), acc);
+                const uint32_t st0 = (uint32_t)(r >> 61) & 3u;
+                st = sum_end(a, st0);
+                pos = (r & ((1ULL << 61) - 1)) + sum_cnt(a, st0);
+                return;
             }
-            s_state = st; s_pos = pos;
+            const int top = res ? 31 - __clz(res) : 0;             // nearest resolved tile of the window, if any
+            if ((rdy >> top) != (0xFFFFFFFFu >> top)) break;       // a tile this side of it has not published yet: poll again
+            acc = sum_combine(warp_fold_sum(lane < top ? sum_identity() : pub_sum(w0[w], w1[w])), acc);
+            folded = w + 1;
+            if (res) {
+                const unsigned long long r = __shfl_sync(0xffffffffu, wp[w], top);
+                const uint32_t st0 = (uint32_t)(r >> 61) & 3u;
+                st = sum_end(acc, st0);
+                pos = (r & ((1ULL << 61) - 1)) + sum_cnt(acc, st0);
+                done = true;
+                break;
+            }
         }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) { scalars[S_STREAM_LEN] = s_pos; scalars[S_STREAM_TOTAL] += s_pos; file_stream_start[n_files] = s_pos; }
-}
-
-// per-tile incoming state and stream position
-__global__ void __launch_bounds__(kScanThreads)
-k_scan_apply(const Sum* __restrict__ tsum, uint64_t n_tiles, const uint32_t* __restrict__ bstate,
-             const uint64_t* __restrict__ bpos, const uint32_t* __restrict__ tile_file,
-             const FileDesc* __restrict__ files, uint8_t* __restrict__ tile_state, uint64_t* __restrict__ tile_pos,
-             uint64_t* __restrict__ file_stream_start) {
-    __shared__ Sum s_w[kScanThreads / 32];
-    const uint64_t base = (uint64_t)blockIdx.x * kScanTilesPerBlock + (uint64_t)threadIdx.x * kScanTilesPerThread;
-    Sum t[kScanTilesPerThread];
-    Sum mine = sum_identity();
-#pragma unroll
-    for (int i = 0; i < kScanTilesPerThread; ++i) {
-        t[i] = (base + i < n_tiles) ? tsum[base + i] : sum_identity();
-        mine = sum_combine(mine, t[i]);
-    }
-    Sum excl, total;
-    block_scan_sum(mine, excl, total, s_w);
-    const uint32_t st_in = bstate[blockIdx.x];
-    uint32_t st = sum_end(excl, st_in);
-    uint64_t pos = bpos[blockIdx.x] + sum_cnt(excl, st_in);
-#pragma unroll
-    for (int i = 0; i < kScanTilesPerThread; ++i) {
-        if (base + i < n_tiles) {
-            const uint32_t f = tile_file[base + i];
-            // a file always starts in state 0, whatever state the previous file ended in
-            if (files[f].tile_begin == base + i) { file_stream_start[f] = pos; st = 0; }
-            tile_state[base + i] = (uint8_t)st;
-            tile_pos[base + i] = pos;
-            pos += sum_cnt(t[i], st); st = sum_end(t[i], st);
-        }
+        if (done) return;
+        hi -= 32 * folded;
     }
 }
 
 // text tile -> packed stream: codes64[g] holds entries 32g..32g+31 (entry j at bits 2j), valid32[g] bit j.
 // Every thread turns its 64 bytes into at most 64 entries (register accumulator), the block scan of the
-// thread summaries gives each thread its entry offset, and the tile is assembled in shared memory.
+// thread summaries gives each thread its entry offset inside the tile, the look-back gives the tile its state and
+// position, and the tile is assembled in shared memory.
+struct PackParams {
+    const FileDesc* files;
+    const uint64_t* hdr0;
+    uint64_t n_tiles;
+    uint32_t n_files;
+    const uint32_t* tile_file;
+    const uint32_t* order;              // [n_tiles] ticket -> tile, round-robin over the files
+    uint64_t stream_len;                // padded stream length of the batch (-> scalars[S_STREAM_LEN])
+    uint32_t* ticket;                   // zeroed before the launch
+    unsigned long long* pub_a0;         // [n_tiles] x 3, zeroed before the launch (see tile_lookback)
+    unsigned long long* pub_a1;
+    unsigned long long* pub_ps;
+    const uint64_t* file_stream_start;  // [n_files + 1], fixed by the host
+    unsigned long long* codes;
+    uint32_t* valid;
+    uint64_t* scalars;
+};
+
 template <int KIND>
-__global__ void __launch_bounds__(kParseThreads)
-k_pack(const FileDesc* __restrict__ files, const uint64_t* __restrict__ hdr0, uint64_t n_tiles,
-       const uint32_t* __restrict__ tile_file, const uint8_t* __restrict__ tile_state, const uint64_t* __restrict__ tile_pos,
-       unsigned long long* __restrict__ codes, uint32_t* __restrict__ valid, uint64_t* __restrict__ scalars) {
+__global__ void __launch_bounds__(kParseThreads, 1024 / kParseThreads)
+k_pack(const PackParams p) {
     constexpr int kGroups = kTileBytes / 32 + 2;
     __shared__ Sum s_w[kParseThreads / 32];
     __shared__ uint32_t s_codes[kGroups * 2 + 4];
     __shared__ uint32_t s_valid[kGroups + 2];
-    __shared__ uint32_t s_nrec;
-    const uint64_t tile = blockIdx.x;
-    if (tile >= n_tiles) return;
+    __shared__ uint32_t s_nrec, s_ticket, s_st;
+    __shared__ uint64_t s_pos;
+    if (threadIdx.x == 0) {
+        const uint32_t ticket = atomicAdd(p.ticket, 1u);
+        s_ticket = ticket < p.n_tiles ? p.order[ticket] : 0xFFFFFFFFu;
+        s_nrec = 0;
+        if (ticket == 0) p.scalars[S_STREAM_LEN] = p.stream_len;
+    }
     for (int i = threadIdx.x; i < kGroups * 2 + 4; i += blockDim.x) s_codes[i] = 0;
     for (int i = threadIdx.x; i < kGroups + 2; i += blockDim.x) s_valid[i] = 0;
-    if (threadIdx.x == 0) s_nrec = 0;
-    const TileCtx t = tile_context(files, hdr0, tile, tile_file[tile]);
+    __syncthreads();
+    const uint64_t tile = s_ticket;
+    if (tile >= p.n_tiles) return;
+    unsigned long long* __restrict__ codes = p.codes;
+    uint32_t* __restrict__ valid = p.valid;
+    const TileCtx t = tile_context(p.files, p.hdr0, tile, p.tile_file[tile]);
     const ThreadText x = load_thread_text(t);
-    const uint32_t st_in = tile_state[tile];
-    const uint64_t tpos = tile_pos[tile];
+    // publish the tile's summary, resolve its incoming state and position (warp 0), publish those
+    auto publish = [&](const Sum& total) {
+        if (threadIdx.x == 0) {
+            if (KIND == 1) st_relaxed_u64(p.pub_a1 + tile, pub_a1(total));
+            st_relaxed_u64(p.pub_a0 + tile, pub_a0(total));
+        }
+    };
+    auto resolve = [&](uint32_t& st_in, uint64_t& tpos) {
+        if (threadIdx.x < 32) {
+            uint32_t st; uint64_t pos;
+            tile_lookback<KIND>(tile, t.fd.tile_begin, p.file_stream_start[t.f], p.pub_a0, p.pub_a1, p.pub_ps, st, pos);
+            if (threadIdx.x == 0) {
+                st_relaxed_u64(p.pub_ps + tile, kPubValid | ((unsigned long long)st << 61) | pos);
+                s_st = st; s_pos = pos;
+            }
+        }
+        __syncthreads();
+        st_in = s_st; tpos = s_pos;
+    };
+    uint32_t st_in; uint64_t tpos;
     Acc64 acc; acc.init();
     uint32_t nrec = 0, local, e_total;
     if (KIND == 0) {
@@ -244,18 +286,26 @@ k_pack(const FileDesc* __restrict__ files, const uint64_t* __restrict__ hdr0, ui
         }
         uint32_t ex, tot;
         block_scan_fa(mine, ex, tot, reinterpret_cast<uint32_t*>(s_w));
-        const bool tile_seq = (st_in == ST_SEQ);
-        const uint32_t ex_t = ex >> 28;
-        bool in_seq = ex_t ? (ex_t == 2) : tile_seq;                // line type at this thread's first byte
-        local = (ex & 0x3FFFu) + (tile_seq ? ((ex >> 14) & 0x3FFFu) : 0u);
-        e_total = (tot & 0x3FFFu) + (tile_seq ? ((tot >> 14) & 0x3FFFu) : 0u);
+        publish(fa_to_sum(tot));
+        // The entries are accumulated while the look-back is still in flight, as if the tile started inside a sequence
+        // line; the few threads in front of the tile's first line start redo it when it started inside a header.
+        const uint32_t ex_t = ex >> kFaT;
+        auto build = [&](bool in_seq) {                              // in_seq: line type at this thread's first byte
+            acc.init(); nrec = 0;
 #pragma unroll
-        for (int c = 0; c < kChunksPerThread; ++c) {
-            if (in_seq) acc.append(part[c].hc, part[c].hv_rv & 0xFFFFu, part[c].hn());
-            acc.append(part[c].rc, part[c].hv_rv >> 16, part[c].rn());
-            nrec += part[c].nrec();
-            if (part[c].t()) in_seq = (part[c].t() == 2);
-        }
+            for (int c = 0; c < kChunksPerThread; ++c) {
+                if (in_seq) acc.append(part[c].hc, part[c].hv_rv & 0xFFFFu, part[c].hn());
+                acc.append(part[c].rc, part[c].hv_rv >> 16, part[c].rn());
+                nrec += part[c].nrec();
+                if (part[c].t()) in_seq = (part[c].t() == 2);
+            }
+        };
+        build(ex_t ? (ex_t == 2) : true);
+        resolve(st_in, tpos);
+        const bool tile_seq = (st_in == ST_SEQ);
+        if (!tile_seq && ex_t == 0) build(false);
+        local = (ex & kFaMask) + (tile_seq ? ((ex >> kFaH) & kFaMask) : 0u);
+        e_total = (tot & kFaMask) + (tile_seq ? ((tot >> kFaH) & kFaMask) : 0u);
     } else {
         Sum sums[kChunksPerThread];
         Sum mine = sum_identity(), excl, total;
@@ -265,6 +315,8 @@ k_pack(const FileDesc* __restrict__ files, const uint64_t* __restrict__ hdr0, ui
             mine = sum_combine(mine, sums[c]);
         }
         block_scan_sum(mine, excl, total, s_w);
+        publish(total);
+        resolve(st_in, tpos);
         uint32_t st = sum_end(excl, st_in);
         local = sum_cnt(excl, st_in);
         e_total = sum_cnt(total, st_in);
@@ -289,7 +341,6 @@ k_pack(const FileDesc* __restrict__ files, const uint64_t* __restrict__ hdr0, ui
             acc.append(cbits, vbits, n);
         }
     }
-    __syncthreads();                                                // s_codes / s_valid cleared
     if (acc.n) {
         const uint32_t rel = (uint32_t)(tpos & 31) + local;         // entry offset from the tile's first group
         const uint32_t cb = rel * 2, cw = cb >> 5, cs = cb & 31;
@@ -327,7 +378,10 @@ k_pack(const FileDesc* __restrict__ files, const uint64_t* __restrict__ hdr0, ui
             }
         }
     }
-    if (threadIdx.x == 0 && s_nrec) atomicAdd((unsigned long long*)&scalars[S_N_RECORDS], (unsigned long long)s_nrec);
+    if (threadIdx.x == 0) {
+        if (s_nrec) atomicAdd((unsigned long long*)&p.scalars[S_N_RECORDS], (unsigned long long)s_nrec);
+        if (e_total) atomicAdd((unsigned long long*)&p.scalars[S_STREAM_TOTAL], (unsigned long long)e_total);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
