@@ -72,6 +72,24 @@ class KmerMatrixBuilder:
     def add_genome_device(self, row: int, dev_ptr: int, n_bytes: int) -> None:
         self._check(self._lib.grmkm_add_genome_device(self._ctx, int(row), C.c_void_p(int(dev_ptr)), int(n_bytes)))
 
+    def add_genomes(self, rows, data, lens=None, on_device: bool = False) -> None:
+        """Every input of the build in one call.  rows[i] = genome row of input i; data = device pointers (ints,
+        with lens) when on_device, else host buffers (bytes / uint8 arrays, borrowed until build returns)."""
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        if on_device:
+            ptrs = np.ascontiguousarray(data, dtype=np.uint64)
+            lens = np.ascontiguousarray(lens, dtype=np.uint64)
+        else:
+            arrs = [np.ascontiguousarray(d, dtype=np.uint8) if isinstance(d, np.ndarray) else np.frombuffer(d, dtype=np.uint8)
+                    for d in data]
+            self._keep.extend(arrs)
+            ptrs = np.array([a.ctypes.data for a in arrs], dtype=np.uint64)
+            lens = np.array([a.size for a in arrs], dtype=np.uint64)
+        if not (len(rows) == len(ptrs) == len(lens)):
+            raise ValueError("rows, data and lens differ in length")
+        self._check(self._lib.grmkm_add_genomes(self._ctx, len(rows), C.c_void_p(rows.ctypes.data), C.c_void_p(ptrs.ctypes.data),
+                                                C.c_void_p(lens.ctypes.data), int(bool(on_device))))
+
     def add_genome_files(self, row: int, paths: Sequence[str]) -> None:
         paths = [paths] if isinstance(paths, (str, bytes)) else list(paths)
         arr = (C.c_char_p * max(len(paths), 1))(*[p.encode() if isinstance(p, str) else p for p in paths])

@@ -408,6 +408,19 @@ int grmkm_add_genome_device(grmkm_ctx* c, uint32_t row, const void* dev_data, ui
     return GRMKM_OK;
 }
 
+int grmkm_add_genomes(grmkm_ctx* c, uint32_t n, const uint32_t* rows, const void* const* data, const uint64_t* lens,
+                      int on_device) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    if (n && (!rows || !data || !lens)) return fail(c, GRMKM_E_INVALID, "null input list");
+    c->inputs.reserve(c->inputs.size() + n);
+    for (uint32_t i = 0; i < n; ++i) {
+        const int r = on_device ? grmkm_add_genome_device(c, rows[i], data[i], lens[i])
+                                : grmkm_add_genome_bytes(c, rows[i], (const uint8_t*)data[i], lens[i]);
+        if (r) return r;
+    }
+    return GRMKM_OK;
+}
+
 int grmkm_add_genome_files(grmkm_ctx* c, uint32_t row, const char* const* paths, int n_paths) {
     if (check_ctx(c)) return GRMKM_E_INVALID;
     if (n_paths < 0 || (!paths && n_paths)) return fail(c, GRMKM_E_INVALID, "bad path list");

@@ -135,6 +135,9 @@ class DistributedBuilder:
     def add_genome_device(self, local_row: int, ptr: int, n: int):
         self.builder.add_genome_device(local_row, ptr, n)
 
+    def add_genomes(self, local_rows, data, lens=None, on_device: bool = False):
+        self.builder.add_genomes(local_rows, data, lens, on_device)
+
     def add_genome_files(self, local_row: int, paths):
         self.builder.add_genome_files(local_row, paths)
 

@@ -6,7 +6,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GRMKM_LIB") or os.path.join(_HERE, "libgrmkm.so")   # GRMKM_LIB: another build of the same library (kernel experiments)
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 OK = 0
 E_INVALID, E_UNSUPPORTED_K, E_NOMEM, E_CUDA, E_IO, E_CAPACITY, E_NO_DEVICE, E_UNSUPPORTED = -1, -2, -3, -4, -5, -6, -7, -8
@@ -20,7 +20,7 @@ FLAG_KMER_RECORDS = 16
 # every symbol include/grmkm.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "grmkm_abi_version", "grmkm_device_count", "grmkm_create", "grmkm_destroy", "grmkm_last_error", "grmkm_reset",
-    "grmkm_add_genome_bytes", "grmkm_add_genome_device", "grmkm_add_genome_files", "grmkm_set_genome_count",
+    "grmkm_add_genome_bytes", "grmkm_add_genome_device", "grmkm_add_genome_files", "grmkm_add_genomes", "grmkm_set_genome_count",
     "grmkm_build", "grmkm_dims", "grmkm_get_stats", "grmkm_stage_times", "grmkm_copy_kmers_packed",
     "grmkm_copy_kmer_strings", "grmkm_copy_matrix", "grmkm_format_tsv", "grmkm_device_result", "grmkm_host_result",
     "grmkm_synth_fasta_device", "grmkm_build_partial", "grmkm_export_partials", "grmkm_merge_partials",
@@ -92,6 +92,7 @@ def load() -> C.CDLL:
         "grmkm_copy_kmers_packed": (i32, [vp, vp, u64]),
         "grmkm_copy_kmer_strings": (i32, [vp, vp, u64]),
         "grmkm_copy_matrix": (i32, [vp, vp, u64]),
+        "grmkm_add_genomes": (i32, [vp, u32, vp, vp, vp, i32]),
         "grmkm_format_tsv": (i32, [vp, C.POINTER(C.c_char_p), vp, u64, C.POINTER(u64)]),
         "grmkm_device_result": (i32, [vp, C.POINTER(vp), C.POINTER(vp)]),
         "grmkm_host_result": (i32, [vp, C.POINTER(vp), C.POINTER(vp)]),

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GRMKM_ABI_VERSION 5
+#define GRMKM_ABI_VERSION 6
 
 enum {
     GRMKM_OK = 0,
@@ -124,6 +124,10 @@ int grmkm_reset(grmkm_ctx* ctx);
 int grmkm_add_genome_bytes(grmkm_ctx* ctx, uint32_t genome_row, const uint8_t* data, uint64_t n);
 int grmkm_add_genome_device(grmkm_ctx* ctx, uint32_t genome_row, const void* dev_data, uint64_t n);
 int grmkm_add_genome_files(grmkm_ctx* ctx, uint32_t genome_row, const char* const* paths, int n_paths);
+/* The whole "-file" list in one call (the n lines of create.py:361-362 at once): input i belongs to row rows[i],
+ * is lens[i] bytes at data[i]; on_device = 0 host memory (as *_bytes), 1 device memory (as *_device). */
+int grmkm_add_genomes(grmkm_ctx* ctx, uint32_t n, const uint32_t* rows, const void* const* data, const uint64_t* lens,
+                      int on_device);
 /* Declare rows without input (trailing empty genomes still get a matrix row). */
 int grmkm_set_genome_count(grmkm_ctx* ctx, uint32_t n_genomes);
 

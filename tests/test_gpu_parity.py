@@ -294,3 +294,60 @@ def test_radix_order_fallback_and_simple_scatter(gpu):
                   K | native.FLAG_RADIX_ORDER | native.FLAG_SIMPLE_SCATTER):
         check(genomes, 31, keep_singletons=True, flags=flags)
         check(genomes, 32, keep_singletons=False, flags=flags)
+
+
+def test_single_pass_parser_chains(gpu):
+    """The parse tiles (16 KiB) are resolved by look-back along per-file chains with the tickets dealt round-robin
+    over the files: files of 1 .. 40 tiles, headers and sequence lines longer than several tiles, a file that is
+    one header only, CRLF, and states that differ at every tile boundary."""
+    rng = np.random.default_rng(4242)
+    shared = [inputs.rand_seq(rng, 60000), inputs.rand_seq(rng, 9000)]
+    big_header = b">" + bytes(rng.choice(np.frombuffer(b"ACGT>@ \t", dtype=np.uint8), size=70000)) + b"\n"
+    one_line = b">one line\n" + shared[0] + shared[1] + b"\n"                     # 69 kB sequence line, no breaks
+    genomes = [
+        [inputs.fasta(rng, n_records=40, max_len=30000, shared=shared, width=60)],   # ~40 tiles
+        [big_header + inputs.fasta(rng, n_records=3, max_len=3000, shared=shared)],  # header spans 5 tiles
+        [one_line],
+        [big_header.rstrip(b"\n")],                                                  # a header and nothing else
+        [inputs.fasta(rng, n_records=12, max_len=20000, shared=shared, width=17, crlf=True)],
+        [inputs.fasta(rng, n_records=2, max_len=100, shared=shared)],                # one tile
+        [b""],
+        [inputs.fasta(rng, n_records=25, max_len=9000, shared=shared, width=0),      # two files in one row
+         inputs.fasta(rng, n_records=5, max_len=50000, shared=shared, width=251, blank=True)],
+    ]
+    check(genomes, 31, keep_singletons=True)
+    check(genomes, 15, keep_singletons=False)
+
+
+def test_single_pass_parser_fastq_chains(gpu):
+    rng = np.random.default_rng(4243)
+    src = inputs.rand_seq(rng, 30000)
+    genomes = [
+        [inputs.fastq(rng, src, n_reads=900, read_len=150)],                        # ~20 tiles
+        [inputs.fastq(rng, src, n_reads=40, read_len=20000, crlf=True)],            # reads longer than a tile
+        [inputs.fastq(rng, src, n_reads=3, read_len=70)],
+        [inputs.fastq(rng, src, n_reads=300, read_len=250, final_nl=False)],
+    ]
+    check(genomes, 21, keep_singletons=True, kind=1)
+    check(genomes, 21, min_abundance=2, keep_singletons=True, kind=1)
+
+
+def test_add_genomes_in_one_call(gpu):
+    """grmkm_add_genomes (the whole file list at once) gives the same build as one call per input, for host and
+    for device-resident inputs."""
+    import torch
+    from grm_b200.builder import KmerMatrixBuilder
+    rng = np.random.default_rng(99)
+    shared = [inputs.rand_seq(rng, 3000)]
+    files = [inputs.fasta(rng, n_records=4, max_len=1500, shared=shared) for _ in range(9)]
+    rows = [0, 1, 1, 2, 3, 4, 4, 4, 6]                                   # pooled rows, an empty row 5
+    ref = oracle.build([[(f, 0) for f, r in zip(files, rows) if r == g] for g in range(7)], 19, 1, False)
+    with KmerMatrixBuilder(k=19) as b:
+        b.add_genomes(rows, files)
+        b.build()
+        assert np.array_equal(b.kmers(), ref.kmers) and np.array_equal(b.matrix(), ref.matrix)
+        b.reset()
+        dev = [torch.frombuffer(bytearray(f + b"\0" * 16), dtype=torch.uint8).cuda() for f in files]
+        b.add_genomes(rows, [d.data_ptr() for d in dev], [len(f) for f in files], on_device=True)
+        b.build()
+        assert np.array_equal(b.kmers(), ref.kmers) and np.array_equal(b.matrix(), ref.matrix)
