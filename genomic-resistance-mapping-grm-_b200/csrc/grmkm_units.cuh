@@ -193,7 +193,7 @@ k_units_scatter(const UnitScatterParams p) {
     uint32_t* s_brk = s_off + MB;                                        // [kUsTileGroups + 1] natural breaks per group
     uint16_t* s_b = reinterpret_cast<uint16_t*>(s_brk + kUsTileGroups + 1);   // [kUsStage]
     uint16_t* s_list = s_b + kUsStage;                                   // [kUsTileEntries] tile-local entry where a unit's first k-mer ends
-    uint16_t* s_gf = s_list + kUsTileEntries;                            // [kUsTileGroups] file of the group's first entry - tile file
+    uint16_t* s_gf = s_list + kUsTileEntries;                            // [kUsTileGroups] genome row of the group (groups with unit starts)
     const uint64_t stream_len = p.scalars[S_STREAM_LEN];
     const uint64_t n_groups = (stream_len + 31) >> 5;
     const uint64_t n_tiles = (n_groups + kUsTileGroups - 1) / kUsTileGroups;
@@ -231,10 +231,10 @@ k_units_scatter(const UnitScatterParams p) {
             s_brk[kUsTileGroups] = ~mn.y | mn.x;
         }
         const uint32_t tile_f = p.tile_file[tile];
-        {
+        if (mk.x) {        // files start on group boundaries (grmkm_api.cu: stream_cap), so a group lies in ONE file
             uint32_t f = tile_f;
-            if (mk.x) while (f + 1 < p.n_files && p.file_stream_start[f + 1] <= g * 32ULL) ++f;
-            s_gf[tid] = (uint16_t)min(f - tile_f, 0xFFFFu);
+            while (f + 1 < p.n_files && p.file_stream_start[f + 1] <= g * 32ULL) ++f;
+            s_gf[tid] = (uint16_t)p.files[f].row;
         }
         // compact the unit starts of the tile
         uint32_t n_units;
@@ -272,14 +272,12 @@ k_units_scatter(const UnitScatterParams p) {
                     const unsigned long long vh = ((unsigned long long)v[3] << 32) | v[2], vl = ((unsigned long long)v[1] << 32) | v[0];
                     const unsigned long long rh = ((unsigned long long)r[3] << 32) | r[2], rl = ((unsigned long long)r[1] << 32) | r[0];
                     if (rh < vh || (rh == vh && rl < vl)) { v[0] = r[0]; v[1] = r[1]; v[2] = r[2]; v[3] = r[3]; }
-                    uint32_t f = tile_f + s_gf[gl];
-                    while (f + 1 < p.n_files && p.file_stream_start[f + 1] <= g0 * 32ULL + P) ++f;
                     // lo = bases 0..28 | (L - 1) << 58;  hi = bases 29..52 | row << 48
                     const uint32_t lo0 = v[0], lo1 = (v[1] & 0x03FFFFFFu) | ((L - 1u) << 26);
                     const uint32_t hi0 = __funnelshift_r(v[1], v[2], 26), hi1 = __funnelshift_r(v[2], v[3], 26);
                     const uint32_t b = __umulhi(unit_hash32(lo0, lo1, hi0, hi1), MB);
                     const uint32_t rank = atomicAdd(&s_cnt[b], 1u);
-                    u0[j] = lo0; u1[j] = lo1; u2[j] = hi0; u3[j] = hi1 | (p.files[f].row << 16);
+                    u0[j] = lo0; u1[j] = lo1; u2[j] = hi0; u3[j] = hi1 | ((uint32_t)s_gf[gl] << 16);
                     ubr[j] = b | (rank << 16);
                     my_windows += L;
                 }
