@@ -695,7 +695,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
                 const uint64_t n_utiles = (n_groups_max + kUsTileGroups - 1) / kUsTileGroups;
                 ENSURE(c, c->stile_file, n_utiles * 4);
                 if (!pipelined && c->ev_ok) cudaEventRecord(c->ev[T_COUNT], st);
-                const uint32_t bgrid = (uint32_t)((n_groups_max + 255) / 256);
+                const uint32_t bgrid = (uint32_t)((n_groups_max + 511) / 512);       // two groups per thread
 #define GRMKM_BOUNDS(WW)                                                                                        \
     k_unit_bounds<WW><<<bgrid, 256, 0, st>>>((const unsigned long long*)c->codes.p, (const uint32_t*)c->valid.p, d_scalars, \
                                              ug.k, ug.m, (uint2*)c->masks.p)

@@ -61,60 +61,94 @@ __device__ __forceinline__ uint32_t unit_hash32(uint32_t lo0, uint32_t lo1, uint
 
 // ---- k_unit_bounds: per group of 32 stream entries, start mask and valid-k-mer mask ---------
 // Bit e of .y: the k-mer ENDING at entry e of the group is valid.  Bit e of .x: it is valid and it starts a
-// run (the previous k-mer is invalid or has another minimizer).  W = m-mers per k-mer (compile time: the
-// sliding minimum is two prefix/suffix sweeps over blocks of W, all in registers).
+// run (the previous k-mer is invalid or has another minimizer).  W = m-mers per k-mer (compile time).
+//
+// The kernel is bound by the integer ALU pipe (LOP3 / SHF / VIMNMX / ISETP issue every other cycle per scheduler;
+// IMAD goes to the FMA pipe), so the work is arranged to need few of those per position (profiles/r01_v3: 16.5):
+//  * a thread takes TWO adjacent groups, so neighbouring windows share their m-mer hashes (64 + W instead of
+//    2 x (32 + W)), and both groups go through the sliding minimum as the two halves of 16x2 SIMD words;
+//  * the m-mer needs no mask: it sits in the low 2m bits of a funnel shift, and multiplying by (mul << (32 - 2m))
+//    discards everything above them; strand neutrality comes from adding the two strands' m-mers BEFORE that
+//    multiply (two IMADs);
+//  * a run ends at k-mer e when an m-mer equal to the window minimum leaves on the left or enters on the right:
+//    with inner = min of the W - 1 m-mers both windows share, that is  min(h[e], h[e + W]) <= inner  -- one
+//    __vibmin_u16x2, whose predicate outputs are the answer for both groups.  It covers every change of the
+//    minimum, reads the same from either strand, and bounds a run by W <= lmax.
 template <int W>
 __global__ void __launch_bounds__(256)
 k_unit_bounds(const unsigned long long* __restrict__ codes, const uint32_t* __restrict__ valid,
               const uint64_t* __restrict__ scalars, uint32_t k, uint32_t m, uint2* __restrict__ masks) {
     const uint64_t n_groups = (scalars[S_STREAM_LEN] + 31) >> 5;
-    const uint64_t g = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    const uint64_t g = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 2;          // groups g and g + 1
     if (g >= n_groups) return;
-    const unsigned long long cur_c = codes[g];
-    const uint32_t cur_v = valid[g];
-    unsigned long long prev_c = 0; uint32_t prev_v = 0;
-    if (g > 0) { prev_c = codes[g - 1]; prev_v = valid[g - 1]; }
-    // smear the invalid entries over the k - 1 entries that follow them
-    unsigned long long s = ~((unsigned long long)prev_v | ((unsigned long long)cur_v << 32));
-    for (uint32_t c = 1; c < k;) { const uint32_t d = c < k - c ? c : k - c; s |= s << d; c += d; }
-    const uint32_t vk = ~(uint32_t)(s >> 32);
-    if (vk == 0) { masks[g] = make_uint2(0u, 0u); return; }
-    const uint32_t vk_before = (uint32_t)((s >> 31) & 1ULL) ^ 1u;      // the k-mer ending at the previous group's last entry
-    // 128-bit window: entry q of [previous group | my group] at bits 2q
-    const uint32_t x[4] = {(uint32_t)prev_c, (uint32_t)(prev_c >> 32), (uint32_t)cur_c, (uint32_t)(cur_c >> 32)};
-    const uint32_t r[5] = {rev2_32(x[3]), rev2_32(x[2]), rev2_32(x[1]), rev2_32(x[0]), 0u};   // digit p = entry 63 - p
-    const uint32_t S0 = 2 * (32 - k);
-    const unsigned long long Yl = S0 ? (prev_c >> S0) | (cur_c << (64 - S0)) : prev_c, Yh = cur_c >> S0;
-    const uint32_t y[5] = {(uint32_t)Yl, (uint32_t)(Yl >> 32), (uint32_t)Yh, (uint32_t)(Yh >> 32), 0u};
-    const uint32_t mmask = m >= 16 ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1u);
-    const uint32_t cm = 0xAAAAAAAAu & mmask;
-    // h[t] = strand-neutral hash of the m-mer ending at window entry 32 - W + t   (t = 0 .. 31 + W)
+    const bool two = g + 1 < n_groups;
+    const unsigned long long c0 = codes[g], c1 = two ? codes[g + 1] : 0ULL;
+    const uint32_t v0 = valid[g], v1 = two ? valid[g + 1] : 0u;
+    unsigned long long cp = 0; uint32_t vp = 0;
+    if (g > 0) { cp = codes[g - 1]; vp = valid[g - 1]; }
+    // valid k-mers: smear the invalid entries over the k - 1 entries that follow them
+    unsigned long long sa = ~((unsigned long long)vp | ((unsigned long long)v0 << 32));
+    unsigned long long sb = ~((unsigned long long)v0 | ((unsigned long long)v1 << 32));
+    for (uint32_t c = 1; c < k;) { const uint32_t d = c < k - c ? c : k - c; sa |= sa << d; sb |= sb << d; c += d; }
+    const uint32_t vka = ~(uint32_t)(sa >> 32), vkb = ~(uint32_t)(sb >> 32);
+    if ((vka | vkb) == 0) {
+        masks[g] = make_uint2(0u, 0u);
+        if (two) masks[g + 1] = make_uint2(0u, 0u);
+        return;
+    }
+    const uint32_t vka_before = (uint32_t)((sa >> 31) & 1ULL) ^ 1u;             // the k-mer ending at the last entry of group g - 1
+    // 96-entry window [group g - 1 | g | g + 1]: entry q at bits 2q of x[]
+    const uint32_t x[6] = {(uint32_t)cp, (uint32_t)(cp >> 32), (uint32_t)c0, (uint32_t)(c0 >> 32), (uint32_t)c1, (uint32_t)(c1 >> 32)};
+    // forward strand, first base most significant: digit p of r[] = entry 95 - p
+    const uint32_t r[7] = {rev2_32(x[5]), rev2_32(x[4]), rev2_32(x[3]), rev2_32(x[2]), rev2_32(x[1]), rev2_32(x[0]), 0u};
+    // reverse complement: digit j of y[] = complement of entry j + 32 - k
+    const uint32_t S0 = 2 * (32 - k), sw = S0 >> 5, sb5 = S0 & 31;
+    uint32_t y[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        const uint32_t lo = i + sw < 6 ? x[i + sw] : 0u, hi = i + sw + 1 < 6 ? x[i + sw + 1] : 0u;
+        y[i] = __funnelshift_r(lo, hi, sb5) ^ 0xAAAAAAAAu;
+    }
+    const uint32_t mul = kMmerMul << (32 - 2 * m);      // keeps the low 2m bits of its operand only
+    const uint32_t seed = kMmerSeed * mul;
+    // P[t] = 16-bit hashes of the m-mers ending at window entries 32 - W + t (low half: group g) and 64 - W + t (high half)
     constexpr int N = 32 + W;
-    uint32_t h[N];
+    uint32_t P[N];
+    {
+        uint32_t h[64 + W];
 #pragma unroll
-    for (int t = 0; t < N; ++t) {
-        const int fs = 2 * (31 + W - t), rs = 2 * t;
-        const uint32_t fw = __funnelshift_r(r[fs >> 5], r[(fs >> 5) + 1], fs & 31) & mmask;         // first base most significant
-        const uint32_t rc = (__funnelshift_r(y[rs >> 5], y[(rs >> 5) + 1], rs & 31) & mmask) ^ cm;  // reverse complement
-        h[t] = (fw + rc + kMmerSeed) * kMmerMul;      // the same for an m-mer and its reverse complement
+        for (int t = 0; t < 64 + W; ++t) {
+            const int fs = 2 * (63 + W - t), rs = 2 * t;
+            const uint32_t fw = __funnelshift_r(r[fs >> 5], r[(fs >> 5) + 1], fs & 31);      // m-mer in the low 2m bits
+            const uint32_t rc = __funnelshift_r(y[rs >> 5], y[(rs >> 5) + 1], rs & 31);
+            h[t] = fw * mul + (rc * mul + seed);        // = (fw + rc + seed) * mul: the same for an m-mer and its reverse complement
+        }
+#pragma unroll
+        for (int t = 0; t < N; ++t) P[t] = __byte_perm(h[t], h[t + 32], 0x7632);
     }
-    // minimizer of the k-mer ending at entry j - 1 = min h[j .. j + W - 1]  (j = 0 .. 32)
-    uint32_t pre[N], suf[N];
+    // inner(e) = min P[e + 1 .. e + W - 1]: prefix / suffix minima over blocks of V = W - 1 starting at index 1
+    constexpr int V = W > 1 ? W - 1 : 1;
+    uint32_t changed_a = 0, changed_b = 0;
+    if (W == 1) { changed_a = changed_b = 0xFFFFFFFFu; }        // every k-mer is its own m-mer
+    else {
+        constexpr int HI = 30 + W;                      // last index a window touches
+        uint32_t pre[HI + 1], suf[HI + 1];
 #pragma unroll
-    for (int i = 0; i < N; ++i) pre[i] = (i % W == 0) ? h[i] : min(pre[i - 1], h[i]);
+        for (int i = 1; i <= HI; ++i) pre[i] = ((i - 1) % V == 0) ? P[i] : __vminu2(pre[i - 1], P[i]);
 #pragma unroll
-    for (int i = N - 1; i >= 0; --i) suf[i] = (i % W == W - 1 || i == N - 1) ? h[i] : min(suf[i + 1], h[i]);
-    uint32_t changed = 0, prev_min = min(suf[0], pre[W - 1]);
+        for (int i = HI; i >= 1; --i) suf[i] = ((i - 1) % V == V - 1 || i == HI) ? P[i] : __vminu2(suf[i + 1], P[i]);
 #pragma unroll
-    for (int e = 0; e < 32; ++e) {
-        // a run ends when an m-mer equal to the window minimum leaves on the left or enters on the right -- which
-        // covers every change of the minimum, reads the same from either strand, and bounds a run by W <= lmax
-        const uint32_t mn = min(suf[e + 1], pre[e + W]);
-        changed |= (uint32_t)((h[e] == prev_min) | (h[e + W] == mn)) << e;
-        prev_min = mn;
+        for (int e = 0; e < 32; ++e) {
+            const uint32_t inner = __vminu2(suf[e + 1], pre[e + V]);
+            bool hi, lo;
+            __vibmin_u16x2(__vminu2(P[e], P[e + W]), inner, &hi, &lo);      // hi / lo = (ends <= inner) per half
+            changed_a |= (uint32_t)lo << e;
+            changed_b |= (uint32_t)hi << e;
+        }
     }
-    const uint32_t before = (vk << 1) | vk_before;
-    masks[g] = make_uint2(vk & (~before | changed), vk);
+    const uint32_t before_a = (vka << 1) | vka_before, before_b = (vkb << 1) | (vka >> 31);
+    masks[g] = make_uint2(vka & (~before_a | changed_a), vka);
+    if (two) masks[g + 1] = make_uint2(vkb & (~before_b | changed_b), vkb);
 }
 
 // ---- k_units_scatter: units -> content-hash buckets ------------------------------------------
