@@ -51,6 +51,7 @@ struct grmkm_ctx {
     uint32_t n_genomes_decl = 0;
     int sm_count = 148;
     size_t smem_optin = 0;
+    uint64_t wide_hint = 0;        // wide records of the previous build (sizes the expansion's bucket regions)
 
     // device buffers (grow-only, reused across builds)
     DevBuf in, files, hdr0, tile_file, tile_pub, tile_order, fss, codes, valid, hist,
@@ -809,11 +810,26 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         const unsigned long long* agg_records = (const unsigned long long*)c->records.p;
         const unsigned long long* agg_begin = (const unsigned long long*)c->offsets.p;
         const unsigned long long* agg_end = (const unsigned long long*)c->hist.p;
-        bool unit_overflow = false;
+        // Unit path: dedupe -> expand -> aggregate run back to back without a host round trip.  The dedupe's entry list
+        // and the expansion's bucket regions are sized from estimates; the one synchronisation after the aggregate
+        // reads what was really needed, and a guess that was too small repeats the round (entry list: larger; regions:
+        // exact offsets from a count pass).
+        uint64_t wcap = std::min<uint64_t>(P.max_stream, std::max<uint64_t>(1 << 16, P.max_stream / 16));
+        bool wide_exact = !try_regions;
+        if (getenv("GRMKM_WIDE_EXACT")) wide_exact = true;
+        if (const char* e = getenv("GRMKM_WU_CAP")) wcap = std::max<uint64_t>(16, (uint64_t)atoll(e));     // tests: force the retry
+        bool again = true, unit_overflow = false;
+        for (int round = 0; again; ++round) {
+        again = false;
+        if (round > 6) return fail(c, GRMKM_E_UNSUPPORTED, "unit path does not converge");
+        if (round > 0) {
+            const uint64_t zero3[3] = {0, 0, 0};
+            CU_TRY(c, cudaMemcpyAsync(d_scalars + S_U_NEEDED, zero3, 3 * 8, cudaMemcpyHostToDevice, st));      // + S_N_DISTINCT, S_N_SPLITS
+            CU_TRY(c, cudaMemcpyAsync(d_scalars + S_WU_NEEDED, zero3, 3 * 8, cudaMemcpyHostToDevice, st));     // + S_N_WIDE, S_WIDE_OVERFLOW
+            CU_TRY(c, cudaStreamSynchronize(st));          // zero3 lives on this stack frame
+        }
         if (use_units) {
             if (c->ev_ok) cudaEventRecord(c->ev[T_ABUND], st);
-            // ---- dedupe: distinct (unit, block) entries; retried with a larger list if the guess was too small
-            uint64_t wcap = std::min<uint64_t>(P.max_stream, std::max<uint64_t>(1 << 16, P.max_stream / 16));
             const size_t dsm = unit_dedupe_smem(WB), xsm = staged_smem_bytes(B);
             void (*k_dedupe)(UnitDedupeParams) = WB == 1 ? k_units_dedupe<1> : WB == 2 ? k_units_dedupe<2> : k_units_dedupe<4>;
             void (*k_xcount)(UnitExpandParams) = WB == 1 ? k_units_expand<true, 1> : WB == 2 ? k_units_expand<true, 2> : k_units_expand<true, 4>;
@@ -821,22 +837,47 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
             CU_TRY(c, cudaFuncSetAttribute(k_dedupe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
             CU_TRY(c, cudaFuncSetAttribute(k_xcount, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsm));
             CU_TRY(c, cudaFuncSetAttribute(k_xscat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsm));
-            for (int attempt = 0; attempt < 4; ++attempt) {
-                ENSURE(c, c->wu, wcap * ES * 8);
-                UnitDedupeParams dp{};
-                dp.units = (const uint4*)c->units.p; dp.begin = (const unsigned long long*)c->ubeg.p;
-                dp.end = (const unsigned long long*)c->ucur.p; dp.n_buckets = MB; dp.out = (unsigned long long*)c->wu.p;
-                dp.cap = wcap; dp.needed = (unsigned long long*)(d_scalars + S_WU_NEEDED);
-                k_dedupe<<<std::min<uint32_t>(MB, (uint32_t)c->sm_count), kUdThreads, dsm, st>>>(dp);
-                L.n++;
+            // ---- dedupe: distinct (unit, block) entries
+            ENSURE(c, c->wu, wcap * ES * 8);
+            UnitDedupeParams dp{};
+            dp.units = (const uint4*)c->units.p; dp.begin = (const unsigned long long*)c->ubeg.p;
+            dp.end = (const unsigned long long*)c->ucur.p; dp.n_buckets = MB; dp.out = (unsigned long long*)c->wu.p;
+            dp.cap = wcap; dp.needed = (unsigned long long*)(d_scalars + S_WU_NEEDED);
+            k_dedupe<<<std::min<uint32_t>(MB, (uint32_t)c->sm_count), kUdThreads, dsm, st>>>(dp);
+            L.n++;
+            CU_TRY(c, cudaGetLastError());
+            if (c->ev_ok) cudaEventRecord(c->ev[T_DEDUPE], st);
+            // ---- expand: every distinct entry -> wide records of its k-mers, by hash bucket
+            UnitExpandParams xp{};
+            xp.wu = (const unsigned long long*)c->wu.p; xp.n_ptr = (const unsigned long long*)(d_scalars + S_WU_NEEDED);
+            xp.cap = wcap; xp.k = c->cfg.k; xp.bucket_bits = P.bucket_bits; xp.wbits = wbits;
+            xp.cursors = (unsigned long long*)c->hist.p; xp.records = nullptr;
+            xp.overflow = (unsigned long long*)(d_scalars + S_WIDE_OVERFLOW);
+            const uint32_t xgrid = (uint32_t)std::min<uint64_t>((wcap + kStThreads - 1) / kStThreads, (uint64_t)c->sm_count);
+            if (!wide_exact) {
+                // over-provisioned bucket regions, no count pass: the distinct k-mers are estimated as 1.9 x the largest genome
+                // plus 5 % of all input (what every further genome adds to a species' pan-genome), 1.3 records per distinct
+                // k-mer and genome group, 1.4 x headroom per bucket; the previous build of this context corrects the guess
+                std::vector<uint64_t> row_bytes(std::max(P.G, 1u), 0);
+                for (const Input& in : c->inputs) if (in.row < P.G) row_bytes[in.row] += in.len;
+                const uint64_t max_row = *std::max_element(row_bytes.begin(), row_bytes.end());
+                const uint64_t groups = (P.W + WB - 1) / WB;
+                uint64_t est = std::max<uint64_t>(c->wide_hint, std::min<uint64_t>(P.in_bytes, max_row * 19 / 10 + P.in_bytes / 20) * 13 / 10 * groups);
+                if (const char* wc = getenv("GRMKM_WIDE_EST")) est = (uint64_t)atoll(wc);
+                uint64_t rcap = (uint64_t)((double)est / B * 1.4) + 1024;
+                rcap = (rcap + 15) & ~15ULL;
+                ENSURE(c, c->wide, ((uint64_t)B * rcap + kStTile) * RS * 8);
+                k_init_regions<<<(B + 1 + 255) / 256, 256, 0, st>>>((unsigned long long*)c->offsets.p, (unsigned long long*)c->hist.p, B, rcap);
+                xp.records = (unsigned long long*)c->wide.p; xp.region_cap = rcap; xp.dump = (uint64_t)B * rcap;
+                k_xscat<<<xgrid, kStThreads, xsm, st>>>(xp);
+                k_finish_regions<<<1, 1024, 0, st>>>((const unsigned long long*)c->offsets.p, (unsigned long long*)c->hist.p, B, rcap,
+                                                     (unsigned long long*)d_scalars, S_N_WIDE);
+                L.n += 3;
                 CU_TRY(c, cudaGetLastError());
-                if (c->ev_ok) cudaEventRecord(c->ev[T_DEDUPE], st);
-                // ---- expand, pass 1: wide records per hash bucket -> exact offsets
-                UnitExpandParams xp{};
-                xp.wu = (const unsigned long long*)c->wu.p; xp.n_ptr = (const unsigned long long*)(d_scalars + S_WU_NEEDED);
-                xp.cap = wcap; xp.k = c->cfg.k; xp.bucket_bits = P.bucket_bits; xp.wbits = wbits;
-                xp.cursors = (unsigned long long*)c->hist.p; xp.records = nullptr;
-                const uint32_t xgrid = (uint32_t)std::min<uint64_t>((wcap + kStThreads - 1) / kStThreads, (uint64_t)c->sm_count);
+                agg_begin = (const unsigned long long*)c->offsets.p;
+                agg_end = (const unsigned long long*)c->hist.p;
+            } else {
+                // exact offsets: count pass, scan, one synchronisation to size the record array
                 CU_TRY(c, cudaMemsetAsync(c->hist.p, 0, (size_t)B * 8, st));
                 k_xcount<<<xgrid, kStThreads, xsm, st>>>(xp);
                 k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->hist.p, (unsigned long long*)c->offsets.p, B,
@@ -846,26 +887,22 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
                 CU_TRY(c, cudaMemcpyAsync(sc, d_scalars, sizeof sc, cudaMemcpyDeviceToHost, st));
                 CU_TRY(c, cudaStreamSynchronize(st));
                 if (regions && sc[S_OVERFLOW]) { unit_overflow = true; break; }
-                if (sc[S_WU_NEEDED] <= wcap) {
-                    // ---- expand, pass 2: scatter the wide records
-                    ENSURE(c, c->wide, (sc[S_N_WIDE] + 1) * RS * 8);
-                    xp.records = (unsigned long long*)c->wide.p;
-                    k_xscat<<<xgrid, kStThreads, xsm, st>>>(xp);
-                    L.n++;
-                    CU_TRY(c, cudaGetLastError());
-                    break;
+                if (sc[S_WU_NEEDED] > wcap) {
+                    // the entry count depends on the order the table fills in (bypass, flush points): leave headroom
+                    wcap = sc[S_WU_NEEDED] + sc[S_WU_NEEDED] / 4 + 4096;
+                    again = true;
+                    continue;
                 }
-                if (attempt == 3) return fail(c, GRMKM_E_UNSUPPORTED, "unit list overflow after resize");
-                // the entry count depends on the order the table fills in (bypass, flush points): leave headroom
-                wcap = sc[S_WU_NEEDED] + sc[S_WU_NEEDED] / 4 + 4096;
-                const uint64_t zero2[2] = {0, 0};
-                CU_TRY(c, cudaMemcpyAsync(d_scalars + S_WU_NEEDED, zero2, 2 * 8, cudaMemcpyHostToDevice, st));
+                ENSURE(c, c->wide, (sc[S_N_WIDE] + 1) * RS * 8);
+                xp.records = (unsigned long long*)c->wide.p;
+                k_xscat<<<xgrid, kStThreads, xsm, st>>>(xp);
+                L.n++;
+                CU_TRY(c, cudaGetLastError());
+                agg_begin = (const unsigned long long*)c->offsets.p;
+                agg_end = agg_begin + 1;
             }
             if (c->ev_ok) cudaEventRecord(c->ev[T_EXPAND], st);
-            if (unit_overflow) { c->stats.n_region_overflows++; continue; }
             agg_records = (const unsigned long long*)c->wide.p;
-            agg_begin = (const unsigned long long*)c->offsets.p;
-            agg_end = agg_begin + 1;
         }
         if (c->cfg.min_abundance > 1) {
             ENSURE(c, c->records2, c->records.cap);
@@ -929,6 +966,15 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
             CU_TRY(c, cudaMemcpyAsync(sc, d_scalars, sizeof sc, cudaMemcpyDeviceToHost, st));
             CU_TRY(c, cudaStreamSynchronize(st));
             if (regions && sc[S_OVERFLOW]) break;
+            if (use_units && sc[S_WU_NEEDED] > wcap) {
+                wcap = sc[S_WU_NEEDED] + sc[S_WU_NEEDED] / 4 + 4096;
+                again = true;
+                break;
+            }
+            if (use_units && !wide_exact && sc[S_WIDE_OVERFLOW]) {
+                wide_exact = true; again = true; c->stats.n_region_overflows++;
+                break;
+            }
             if (sc[S_U_NEEDED] <= ucap) break;
             if (attempt == 1 || sc[S_U_NEEDED] > 0xFFFFFFFFULL)
                 return fail(c, GRMKM_E_UNSUPPORTED, "more than 2^32 columns in one context");
@@ -936,7 +982,9 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
             const uint64_t zero3[3] = {0, 0, 0};
             CU_TRY(c, cudaMemcpyAsync(d_scalars + S_U_NEEDED, zero3, 3 * 8, cudaMemcpyHostToDevice, st));
         }
-        if (!(regions && sc[S_OVERFLOW])) break;
+        }   // round
+        if (use_units && !unit_overflow && !(regions && sc[S_OVERFLOW])) c->wide_hint = sc[S_N_WIDE];
+        if (!(regions && (sc[S_OVERFLOW] || unit_overflow))) break;
         c->stats.n_region_overflows++;
     }
     if (c->ev_ok) cudaEventRecord(c->ev[T_AGG], st);

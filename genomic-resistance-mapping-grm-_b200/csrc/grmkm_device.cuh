@@ -36,6 +36,7 @@ enum Scalar : int {
     S_N_UNITS,          // units (super-k-mers) scattered
     S_WU_NEEDED,        // distinct (unit, 64-genome block) entries the dedupe produced
     S_N_WIDE,           // wide records the expansion produced
+    S_WIDE_OVERFLOW,    // a region of the over-provisioned expansion was too small
     S_COUNT
 };
 

@@ -506,8 +506,11 @@ struct UnitExpandParams {
     const unsigned long long* n_ptr;     // entries produced by the dedupe
     unsigned long long cap;              // entries the buffer holds
     uint32_t k, bucket_bits, wbits;
-    unsigned long long* cursors;         // [B] histogram (COUNT) or exact offsets
+    unsigned long long* cursors;         // [B] histogram (COUNT), exact offsets, or region cursors (region_cap != 0)
     unsigned long long* records;         // [total][unit_record_stride(WB)]
+    unsigned long long region_cap;       // records per over-provisioned bucket region; 0 = exact offsets from a count pass
+    unsigned long long dump;             // first record of the dump area (kStTile records) behind the regions
+    unsigned long long* overflow;        // set when a region was too small (the host redoes the expansion with exact offsets)
 };
 
 __device__ __forceinline__ void expand_hash_group(const uint32_t (&r)[4], const uint32_t (&y)[4], uint32_t have,
@@ -605,7 +608,14 @@ k_units_expand(const UnitExpandParams p) {
                     const uint32_t bin = j * kStThreads + tid;
                     if (bin < B) {
                         s_off[bin] = off;
-                        if (cnt[j]) s_delta[bin] = gb[j] - off;
+                        if (cnt[j]) {
+                            if (p.region_cap && gb[j] + cnt[j] > (unsigned long long)(bin + 1) * p.region_cap) {
+                                *p.overflow = 1ULL;
+                                s_delta[bin] = p.dump;          // the tile's records of this bucket land in the dump area
+                            } else {
+                                s_delta[bin] = gb[j] - off;
+                            }
+                        }
                         off += cnt[j];
                     }
                 }

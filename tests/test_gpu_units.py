@@ -130,3 +130,29 @@ def test_fastq_without_abundance_filter_uses_units(gpu):
     assert st["n_units"] > 0
     st = check(genomes, 21, min_abundance=2, keep_singletons=True, kind=1)
     assert st["n_units"] == 0
+
+
+def test_expansion_regions_too_small_fall_back_to_exact_offsets(gpu, monkeypatch):
+    """The wide records go to over-provisioned bucket regions sized from an estimate (no count pass, no host round
+    trip); an estimate that is far too small sets the overflow flag and the round is repeated with exact offsets."""
+    rng = np.random.default_rng(41)
+    genomes = shared_population(rng, 70, core_len=20000, snp=0.003)
+    monkeypatch.setenv("GRMKM_WIDE_EST", "64")
+    st = check(genomes, 31, keep_singletons=True)
+    assert st["n_region_overflows"] >= 1 and st["n_wide"] > 20000
+    monkeypatch.delenv("GRMKM_WIDE_EST")
+    check(genomes, 31, keep_singletons=False)
+    monkeypatch.setenv("GRMKM_WIDE_EXACT", "1")                      # the count-pass path by itself
+    check(genomes, 21, keep_singletons=True)
+
+
+def test_entry_list_too_small_is_retried(gpu, monkeypatch):
+    """The dedupe's entry list is sized from an estimate as well; the build is repeated with the size it asked for,
+    with the regions (first) and with exact offsets (second)."""
+    rng = np.random.default_rng(43)
+    genomes = shared_population(rng, 9, core_len=30000, snp=0.01)
+    monkeypatch.setenv("GRMKM_WU_CAP", "100")
+    st = check(genomes, 31, keep_singletons=True)
+    assert st["n_unit_entries"] > 100
+    monkeypatch.setenv("GRMKM_WIDE_EXACT", "1")
+    check(genomes, 31, keep_singletons=False)
