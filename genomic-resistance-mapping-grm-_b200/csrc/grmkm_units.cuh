@@ -218,6 +218,7 @@ k_units_scatter(const UnitScatterParams p) {
     extern __shared__ uint4 s_units[];                                   // [kUsStage] sorted units of the round
     __shared__ uint32_t s_total;
     __shared__ uint32_t s_warp[33];
+    __shared__ uint4 s_mask[33];                                          // [L] masks of a unit of L k-mers (L + k - 1 bases)
     const uint32_t MB = p.n_buckets;
     unsigned long long* s_delta = reinterpret_cast<unsigned long long*>(s_units + kUsStage);   // [MB]
     uint32_t* s_fw = reinterpret_cast<uint32_t*>(s_delta + MB);          // [kUsCode32] codes, word 0 = the group before the tile
@@ -236,6 +237,15 @@ k_units_scatter(const UnitScatterParams p) {
     constexpr uint32_t T = (uint32_t)kUsCodeWords * 32u;                 // staged entries
     for (uint32_t i = tid; i < MB; i += kUsThreads) s_cnt[i] = 0;
     if (tid < 6) { s_fw[2 * kUsCodeWords + tid] = 0; s_rc[2 * kUsCodeWords + tid] = 0; }
+    if (tid < 33) {
+        const uint32_t bits = 2u * (tid + k - 1u);                        // <= 106
+        uint4 mk;
+        mk.x = bits >= 32u ? 0xFFFFFFFFu : ((1u << bits) - 1u);
+        mk.y = bits >= 64u ? 0xFFFFFFFFu : (bits > 32u ? ((1u << (bits - 32u)) - 1u) : 0u);
+        mk.z = bits >= 96u ? 0xFFFFFFFFu : (bits > 64u ? ((1u << (bits - 64u)) - 1u) : 0u);
+        mk.w = bits > 96u ? ((1u << (bits - 96u)) - 1u) : 0u;
+        s_mask[tid] = mk;
+    }
     unsigned long long my_windows = 0;
     // this thread's share of a tile's inputs: code words tid (and tid + 1024 for the first three threads), one mask
     auto fetch = [&](uint64_t tile, unsigned long long& c0, unsigned long long& c1, uint2& mk) {
@@ -293,19 +303,32 @@ k_units_scatter(const UnitScatterParams p) {
                     const uint32_t L = dist < lmax ? dist : lmax;
                     const uint32_t a = P + 32u - (k - 1u);       // first entry of the unit, counted from the group before the tile
                     const uint32_t nb = L + k - 1u;
-                    uint32_t v[4], r[4];
-                    unit_window(s_fw, a, v);
-                    unit_window(s_rc, T - a - nb, r);            // the other strand: the same entries reversed and complemented
-                    const uint32_t bits = 2u * nb;               // <= 106
-                    const uint32_t m0 = bits >= 32u ? 0xFFFFFFFFu : ((1u << bits) - 1u);
-                    const uint32_t m1 = bits >= 64u ? 0xFFFFFFFFu : (bits > 32u ? ((1u << (bits - 32u)) - 1u) : 0u);
-                    const uint32_t m2 = bits >= 96u ? 0xFFFFFFFFu : (bits > 64u ? ((1u << (bits - 64u)) - 1u) : 0u);
-                    const uint32_t m3 = bits > 96u ? ((1u << (bits - 96u)) - 1u) : 0u;
-                    v[0] &= m0; v[1] &= m1; v[2] &= m2; v[3] &= m3;
-                    r[0] &= m0; r[1] &= m1; r[2] &= m2; r[3] &= m3;
-                    const unsigned long long vh = ((unsigned long long)v[3] << 32) | v[2], vl = ((unsigned long long)v[1] << 32) | v[0];
-                    const unsigned long long rh = ((unsigned long long)r[3] << 32) | r[2], rl = ((unsigned long long)r[1] << 32) | r[0];
-                    if (rh < vh || (rh == vh && rl < vl)) { v[0] = r[0]; v[1] = r[1]; v[2] = r[2]; v[3] = r[3]; }
+                    // The unit is stored in the strand whose words (first 16 bases first) compare smaller -- any rule works
+                    // that picks the same strand from either side.  Word 0 of both strands decides almost always, so only
+                    // the winner's other three words are extracted.
+                    const uint4 mk4 = s_mask[L];                 // low 2 * nb bits of the four words
+                    const uint32_t ar = T - a - nb;              // the other strand: the same entries reversed and complemented
+                    const uint32_t wf = a >> 4, sf = 2u * (a & 15u), wr = ar >> 4, sr = 2u * (ar & 15u);
+                    const uint32_t f0 = __funnelshift_r(s_fw[wf], s_fw[wf + 1], sf) & mk4.x;
+                    const uint32_t r0 = __funnelshift_r(s_rc[wr], s_rc[wr + 1], sr) & mk4.x;
+                    bool use_rc = r0 < f0;
+                    if (f0 == r0) {                              // (palindromic starts: compare the rest)
+                        uint32_t fv[4], rv[4];
+                        unit_window(s_fw, a, fv);
+                        unit_window(s_rc, ar, rv);
+                        fv[1] &= mk4.y; fv[2] &= mk4.z; fv[3] &= mk4.w; rv[1] &= mk4.y; rv[2] &= mk4.z; rv[3] &= mk4.w;
+                        use_rc = rv[1] != fv[1] ? rv[1] < fv[1] : rv[2] != fv[2] ? rv[2] < fv[2] : rv[3] < fv[3];
+                    }
+                    const uint32_t* const src = use_rc ? s_rc : s_fw;
+                    const uint32_t wi = use_rc ? wr : wf, sh = use_rc ? sr : sf;
+                    uint32_t v[4];
+                    {
+                        const uint32_t t1 = src[wi + 1], t2 = src[wi + 2], t3 = src[wi + 3], t4 = src[wi + 4];
+                        v[0] = use_rc ? r0 : f0;
+                        v[1] = __funnelshift_r(t1, t2, sh) & mk4.y;
+                        v[2] = __funnelshift_r(t2, t3, sh) & mk4.z;
+                        v[3] = __funnelshift_r(t3, t4, sh) & mk4.w;
+                    }
                     // lo = bases 0..28 | (L - 1) << 58;  hi = bases 29..52 | row << 48
                     const uint32_t lo0 = v[0], lo1 = (v[1] & 0x03FFFFFFu) | ((L - 1u) << 26);
                     const uint32_t hi0 = __funnelshift_r(v[1], v[2], 26), hi1 = __funnelshift_r(v[2], v[3], 26);

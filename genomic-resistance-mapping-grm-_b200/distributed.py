@@ -142,7 +142,10 @@ class DistributedBuilder:
         self.builder.add_genome_files(local_row, paths)
 
     # -- build -------------------------------------------------------------------------------------
-    def build(self):
+    def build(self, reuse_partition: bool = False):
+        """reuse_partition: keep the bucket count agreed for the previous build of this object instead of agreeing
+        again (one all-reduce and a host round trip less).  Collective: every rank passes the same value.  The bucket
+        count only sizes the shared-memory tables (a bucket that does not fit is split), never the result."""
         if self.world == 1:
             self.builder.build()
             self.launches = self.builder.stats["n_launches"]
@@ -154,9 +157,11 @@ class DistributedBuilder:
         import torch.distributed as dist
         dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
         # 1. identical hash partition on every rank
-        bits = torch.tensor([self.engine.plan_bucket_bits()], dtype=torch.int64, device=dev)
-        dist.all_reduce(bits, op=dist.ReduceOp.MAX)
-        self.engine.set_bucket_bits(int(bits.item()))
+        if not (reuse_partition and getattr(self, "_agreed_bits", None)):
+            bits = torch.tensor([self.engine.plan_bucket_bits()], dtype=torch.int64, device=dev)
+            dist.all_reduce(bits, op=dist.ReduceOp.MAX)
+            self._agreed_bits = int(bits.item())
+        self.engine.set_bucket_bits(self._agreed_bits)
         # 2. local stages -> partial columns grouped by owner
         wl = self.src_words[self.rank]
         ev = None
