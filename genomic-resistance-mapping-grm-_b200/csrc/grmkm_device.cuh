@@ -312,30 +312,50 @@ __device__ __forceinline__ uint32_t swar_movemask(uint32_t m) {         // bits 
     return (m * 0x00204081u) >> 28;
 }
 
-struct FaBits { uint32_t nl, low, valid, codes; };   // 16-bit position masks; codes: position j at bits 2j
+// Line structure first, bases second.  The ALU pipe is the bound (LOP3 / SHF / PRMT issue every other cycle, IMAD goes to
+// the FMA pipe), so the tests are phrased with as few of those as possible.
+struct FaLines { uint32_t nl; bool fast; };          // nl: 16-bit newline mask; fast: see fa_lines
 
-template <bool CODES>
-__device__ __forceinline__ FaBits fa_classify(const Chunk16& ch) {
-    FaBits r; r.nl = r.low = r.valid = r.codes = 0;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-        const uint32_t x = ch.w[w];
-        r.nl |= swar_movemask(swar_zero_bytes(x ^ 0x0A0A0A0Au)) << (4 * w);
-        r.low |= swar_movemask(swar_zero_bytes(x & 0xC0C0C0C0u)) << (4 * w);
-        if (CODES) {
-            const uint32_t c = (x >> 1) & 0x03030303u;                      // A0 C1 T2 G3
-            r.codes |= ((c * 0x01041040u) >> 24) << (8 * w);
-            const uint32_t t = c | (c >> 4);                                // nibble pairs c0|c1<<4 in byte 0, c2|c3<<4 in byte 2
-            const uint32_t sel = __byte_perm(t, 0u, 0x4420);                // selector nibbles c0, c1, c2, c3
-            const uint32_t expect = __byte_perm(0x47544341u, 0u, sel);      // 'A' 'C' 'T' 'G' by code
-            r.valid |= swar_movemask(swar_zero_bytes((x & 0xDFDFDFDFu) ^ expect)) << (4 * w);
-        }
-    }
-    return r;
+__device__ __forceinline__ uint32_t prmt_sign(uint32_t x) {              // 0xFF in every byte of x whose bit 7 is set
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(d) : "r"(x));
+    return d;
 }
 
 __device__ __forceinline__ bool fa_fast_ok(uint64_t pos0, uint64_t len, uint64_t hdr0) {
     return pos0 > hdr0 && pos0 + 16 <= len;          // every byte live, no forced line start inside
+}
+
+// fast <=> every byte of the chunk is live and its only bytes below 0x40 are '\n' (no '>', '\r', digits, blanks ...):
+// then nl is the newline mask and the chunk is handled four bytes per instruction.  Everything else (header lines,
+// CR-LF text, the first / last bytes of a file) goes through the byte loop fa_chunk().
+__device__ __forceinline__ FaLines fa_lines(const Chunk16& ch, uint64_t pos0, uint64_t len, uint64_t hdr0) {
+    FaLines r; r.nl = 0;
+    uint32_t bad = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const uint32_t x = ch.w[w];
+        const uint32_t low = ~(x | (x * 2u)) & 0x80808080u;              // bit 7 of every byte below 0x40
+        bad |= (x ^ 0x0A0A0A0Au) & prmt_sign(low);                       // ... that is not a newline
+        r.nl |= swar_movemask(low) << (4 * w);
+    }
+    r.fast = bad == 0 && fa_fast_ok(pos0, len, hdr0);
+    return r;
+}
+
+// validity mask (ACGT, either case) and 2-bit codes (position j at bits 2j) of a chunk
+__device__ __forceinline__ void fa_bases(const Chunk16& ch, uint32_t& valid, uint32_t& codes) {
+    valid = codes = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const uint32_t x = ch.w[w];
+        const uint32_t c = (x >> 1) & 0x03030303u;                      // A0 C1 T2 G3
+        codes |= ((c * 0x01041040u) >> 24) << (8 * w);
+        const uint32_t t = c | (c >> 4);                                // nibble pairs c0|c1<<4 in byte 0, c2|c3<<4 in byte 2
+        const uint32_t sel = __byte_perm(t, 0u, 0x4420);                // selector nibbles c0, c1, c2, c3
+        const uint32_t expect = __byte_perm(0x47544341u, 0u, sel);      // 'A' 'C' 'T' 'G' by code
+        valid |= swar_movemask(swar_zero_bytes((x & 0xDFDFDFDFu) ^ expect)) << (4 * w);
+    }
 }
 
 // Entries of one chunk, kept apart for the bytes before its first line start (head: emitted only when the chunk
@@ -361,34 +381,34 @@ __device__ __noinline__ FaParts fa_chunk_parts_slow(const Chunk16& ch, uint32_t 
 }
 
 // entries of one chunk
-__device__ __forceinline__ FaParts fa_chunk_parts(const Chunk16& ch, uint32_t prev, uint64_t pos0, uint64_t len, uint64_t hdr0) {
+__device__ __forceinline__ FaParts fa_chunk_parts(const Chunk16& ch, const FaLines& ln, uint32_t prev, uint64_t pos0, uint64_t len,
+                                                  uint64_t hdr0) {
     FaParts r;
-    if (fa_fast_ok(pos0, len, hdr0)) {
-        const FaBits b = fa_classify<true>(ch);
-        if (b.low == b.nl) {
-            const uint32_t ls = ((b.nl << 1) | (prev == '\n')) & 0xFFFFu;
-            if (ls == 0) {
-                const uint32_t hn = 16u - (b.nl >> 15);            // a newline can only sit at position 15
-                r.hc = hn == 16 ? b.codes : (b.codes & 0x3FFFFFFFu);
-                r.rc = 0; r.hv_rv = b.valid & 0xFFFFu; r.meta = hn;
-                return r;
-            }
-            const uint32_t q = __ffs(ls) - 1;
-            const uint32_t hn = q ? q - 1 : 0u;                    // the byte before the line start is its newline
-            r.hc = b.codes & ((1u << (2 * hn)) - 1u);
-            const uint32_t hv = b.valid & ((1u << hn) - 1u);
-            uint32_t rc = b.codes >> (2 * q), rv = b.valid >> q, rnl = b.nl >> q, rn = 16u - q;
-            while (rnl) {                                          // further newlines: lines shorter than the chunk
-                const uint32_t pz = 31u - __clz(rnl);
-                const uint32_t lo_c = (1u << (2 * pz)) - 1u, lo_v = (1u << pz) - 1u;
-                rc = (rc & lo_c) | ((rc >> 2) & ~lo_c);
-                rv = (rv & lo_v) | ((rv >> 1) & ~lo_v);
-                rnl ^= 1u << pz;
-                --rn;
-            }
-            r.rc = rc; r.hv_rv = hv | (rv << 16); r.meta = hn | (rn << 8) | (2u << 16);
+    if (ln.fast) {
+        uint32_t valid, codes;
+        fa_bases(ch, valid, codes);
+        const uint32_t ls = ((ln.nl << 1) | (prev == '\n')) & 0xFFFFu;
+        if (ls == 0) {
+            const uint32_t hn = 16u - (ln.nl >> 15);           // a newline can only sit at position 15
+            r.hc = hn == 16 ? codes : (codes & 0x3FFFFFFFu);
+            r.rc = 0; r.hv_rv = valid & 0xFFFFu; r.meta = hn;
             return r;
         }
+        const uint32_t q = __ffs(ls) - 1;
+        const uint32_t hn = q ? q - 1 : 0u;                    // the byte before the line start is its newline
+        r.hc = codes & ((1u << (2 * hn)) - 1u);
+        const uint32_t hv = valid & ((1u << hn) - 1u);
+        uint32_t rc = codes >> (2 * q), rv = valid >> q, rnl = ln.nl >> q, rn = 16u - q;
+        while (rnl) {                                          // further newlines: lines shorter than the chunk
+            const uint32_t pz = 31u - __clz(rnl);
+            const uint32_t lo_c = (1u << (2 * pz)) - 1u, lo_v = (1u << pz) - 1u;
+            rc = (rc & lo_c) | ((rc >> 2) & ~lo_c);
+            rv = (rv & lo_v) | ((rv >> 1) & ~lo_v);
+            rnl ^= 1u << pz;
+            --rn;
+        }
+        r.rc = rc; r.hv_rv = hv | (rv << 16); r.meta = hn | (rn << 8) | (2u << 16);
+        return r;
     }
     return fa_chunk_parts_slow(ch, prev, pos0, len, hdr0);
 }

@@ -281,7 +281,8 @@ k_pack(const PackParams p) {
         uint32_t mine = 0;
 #pragma unroll
         for (int c = 0; c < kChunksPerThread; ++c) {
-            part[c] = fa_chunk_parts(x.ch[c], x.prev[c], t.off + 16 * c, t.fd.len, t.hdr0);
+            const FaLines ln = fa_lines(x.ch[c], t.off + 16 * c, t.fd.len, t.hdr0);
+            part[c] = fa_chunk_parts(x.ch[c], ln, x.prev[c], t.off + 16 * c, t.fd.len, t.hdr0);
             mine = fa_combine(mine, part[c].sum());
         }
         uint32_t ex, tot;
