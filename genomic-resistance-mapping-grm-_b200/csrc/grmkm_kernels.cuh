@@ -758,24 +758,37 @@ k_scatter(const ScatterParams p) {
     }
 }
 
+// sum of one u64 per thread over a block of up to 1024 threads (valid in thread 0); a 64-bit atomicAdd on shared
+// memory is a compare-and-swap loop, 1024 of them on one word took 40 us
+__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v) {
+    __shared__ unsigned long long s_part[32];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31u) == 0) s_part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    unsigned long long t = 0;
+    if (threadIdx.x < 32) {
+        t = threadIdx.x < (blockDim.x + 31) / 32 ? s_part[threadIdx.x] : 0ULL;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) t += __shfl_down_sync(0xffffffffu, t, d);
+    }
+    return t;
+}
+
 // After the scatter: end[b] = cursor[b], clamped to the region when regions are over-provisioned (an
 // overflowing bucket is re-done by the exact path, but nothing may read past its region meanwhile);
 // scalars[which] = number of records = n_windows.  One block.
 __global__ void __launch_bounds__(1024)
 k_finish_regions(const unsigned long long* __restrict__ begin, unsigned long long* __restrict__ end, uint32_t B,
                  unsigned long long cap, unsigned long long* __restrict__ scalars, int which) {
-    __shared__ unsigned long long s_sum;
-    if (threadIdx.x == 0) s_sum = 0;
-    __syncthreads();
     unsigned long long v = 0;
     for (uint32_t b = threadIdx.x; b < B; b += blockDim.x) {
         unsigned long long e = end[b];
         if (cap && e > (unsigned long long)(b + 1) * cap) { e = (unsigned long long)(b + 1) * cap; end[b] = e; }
         v += e - begin[b];
     }
-    atomicAdd(&s_sum, v);
-    __syncthreads();
-    if (threadIdx.x == 0) scalars[which] = s_sum;
+    const unsigned long long sum = block_sum_u64(v);
+    if (threadIdx.x == 0) scalars[which] = sum;
 }
 
 // region starts for the over-provisioned layout: begin[b] = cursors[b] = b * cap

@@ -679,18 +679,14 @@ k_units_expand(const UnitExpandParams p) {
 __global__ void __launch_bounds__(1024)
 k_finish_unit_regions(const unsigned long long* __restrict__ begin, unsigned long long* __restrict__ end, uint32_t MB,
                       unsigned long long cap, unsigned long long* __restrict__ scalars, int which) {
-    __shared__ unsigned long long s_sum;
-    if (threadIdx.x == 0) s_sum = 0;
-    __syncthreads();
     unsigned long long v = 0;
     for (uint32_t b = threadIdx.x; b < MB; b += blockDim.x) {
         unsigned long long e = end[b];
         if (cap && e > (unsigned long long)(b + 1) * cap) { e = (unsigned long long)(b + 1) * cap; end[b] = e; }
         v += e - begin[b];
     }
-    atomicAdd(&s_sum, v);
-    __syncthreads();
-    if (threadIdx.x == 0) scalars[which] = s_sum;
+    const unsigned long long sum = block_sum_u64(v);
+    if (threadIdx.x == 0) scalars[which] = sum;
 }
 
 }  // namespace grmkm
