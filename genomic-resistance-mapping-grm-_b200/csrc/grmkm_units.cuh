@@ -248,12 +248,20 @@ k_units_scatter(const UnitScatterParams p) {
     }
     unsigned long long my_windows = 0;
     // this thread's share of a tile's inputs: code words tid (and tid + 1024 for the first three threads), one mask
+    // ... and the tile's file: its index, where the NEXT file starts in the stream, its genome row (three dependent
+    // loads: fetched a tile ahead like the rest, they were 9 % of the kernel's stall samples on the critical path)
+    uint32_t n_tf = 0, n_row = 0; unsigned long long n_next = ~0ULL;
     auto fetch = [&](uint64_t tile, unsigned long long& c0, unsigned long long& c1, uint2& mk) {
         const uint64_t g0 = tile * kUsTileGroups;
         const uint64_t gi = g0 + tid;        // code word i holds group g0 + i - 1
         c0 = (tile < n_tiles && gi >= 1 && gi - 1 < n_groups) ? p.codes[gi - 1] : 0ULL;
         c1 = (tile < n_tiles && tid < 3 && gi + kUsThreads - 1 < n_groups) ? p.codes[gi + kUsThreads - 1] : 0ULL;
         mk = (tile < n_tiles && gi < n_groups) ? p.masks[gi] : make_uint2(0u, 0u);
+        if (tile < n_tiles) {
+            n_tf = p.tile_file[tile];
+            n_next = n_tf + 1 < p.n_files ? p.file_stream_start[n_tf + 1] : ~0ULL;
+            n_row = p.files[n_tf].row;
+        }
     };
     unsigned long long nc0, nc1; uint2 nmk;
     fetch(blockIdx.x, nc0, nc1, nmk);
@@ -274,11 +282,14 @@ k_units_scatter(const UnitScatterParams p) {
             if (g0 + kUsTileGroups < n_groups) mn = p.masks[g0 + kUsTileGroups];
             s_brk[kUsTileGroups] = ~mn.y | mn.x;
         }
-        const uint32_t tile_f = p.tile_file[tile];
         if (mk.x) {        // files start on group boundaries (grmkm_api.cu: stream_cap), so a group lies in ONE file
-            uint32_t f = tile_f;
-            while (f + 1 < p.n_files && p.file_stream_start[f + 1] <= g * 32ULL) ++f;
-            s_gf[tid] = (uint16_t)p.files[f].row;
+            uint32_t row = n_row;
+            if (g * 32ULL >= n_next) {       // (a tile that holds the start of another file)
+                uint32_t f = n_tf + 1;
+                while (f + 1 < p.n_files && p.file_stream_start[f + 1] <= g * 32ULL) ++f;
+                row = p.files[f].row;
+            }
+            s_gf[tid] = (uint16_t)row;
         }
         // compact the unit starts of the tile
         uint32_t n_units;
