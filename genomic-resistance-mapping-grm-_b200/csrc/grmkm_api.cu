@@ -943,7 +943,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
             ap.records = agg_records; ap.begin = agg_begin; ap.end = agg_end; ap.bucket_bits = P.bucket_bits;
             ap.row_bits = use_units ? wbits : P.row_bits; ap.n_words = P.W; ap.slots = P.slots;
             ap.keep_singletons = c->cfg.keep_singletons; ap.sub_bits = P.sub_bits;
-            ap.wide_words = WB; ap.wide_stride = RS;
+            ap.wide_words = WB; ap.wide_stride = RS; ap.table_u32 = 2 * P.W;
             ap.out_keys = (unsigned long long*)c->ukeys.p; ap.out_words = (unsigned long long*)c->uwords.p;
             ap.cap = ucap; ap.scalars = (unsigned long long*)d_scalars;
             ap.bucket_base = (unsigned long long*)c->bbase.p; ap.bucket_count = (unsigned long long*)c->bcounts.p;
@@ -1279,9 +1279,13 @@ int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
     c->times = grmkm_times{};
     const uint32_t launches_before = c->stats.n_launches;
     if (n_total == 0) { c->built = true; c->stats.n_kmers = 0; return GRMKM_OK; }
-    const uint32_t slots = table_slots(c, W_total);
-    if (slots < 256) return fail(c, GRMKM_E_UNSUPPORTED, "too many genomes for the shared-memory column table");
-    const size_t smem = table_smem(slots, W_total);
+    // the merge table keeps one entry reference per source and slot instead of the words (k_aggregate_cols<3>)
+    const uint32_t tw = (n_ranks + 1) & ~1u;
+    const size_t slot_bytes = 9 + 4 * (size_t)tw;
+    const uint32_t slots = (uint32_t)std::min<size_t>(kAggMaxSlots, agg_smem_budget(c) / slot_bytes - kMaxProbe);
+    const size_t smem = (((size_t)slots + kMaxProbe) * slot_bytes + 15) & ~size_t(15);
+    for (uint32_t s = 0; s < n_ranks; ++s)
+        if (src_counts[s] >= 0xFFFFFFFFULL) return fail(c, GRMKM_E_UNSUPPORTED, "more than 2^32 partial columns from one source");
     // every rank sees 1/P of the hash space: size the buckets for n_total * P entries over the full range
     const uint64_t per = std::max<uint64_t>(1, slots / 2);
     const uint32_t mb = std::min(24u, std::max(6u, ceil_log2((n_total * n_ranks + per - 1) / per)));
@@ -1314,7 +1318,7 @@ int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
     CU_TRY(c, cudaGetLastError());
     if (c->ev_ok) cudaEventRecord(c->ev[T_SCATTER], st);
     ap.bucket_bits = mb; ap.row_bits = 0; ap.n_words = W_total; ap.slots = slots;
-    ap.keep_singletons = c->cfg.keep_singletons; ap.sub_bits = 0;
+    ap.keep_singletons = c->cfg.keep_singletons; ap.sub_bits = 0; ap.table_u32 = tw;
     ap.out_keys = (unsigned long long*)c->ukeys.p; ap.out_words = (unsigned long long*)c->uwords.p;
     ap.cap = ucap; ap.scalars = (unsigned long long*)d_scalars; ap.parts = parts; ap.bounds = d_bounds;
     ap.bucket_base = (unsigned long long*)c->bbase.p; ap.bucket_count = (unsigned long long*)c->bcounts.p;
