@@ -81,7 +81,8 @@ struct grmkm_ctx {
     // multi-GPU partial state
     uint32_t part_ranks = 0;
     std::vector<uint64_t> part_counts;
-    uint64_t part_total = 0, part_cap = 0;
+    uint64_t part_total = 0, part_cap = 0;      // partial columns of the last partial build; stride of its bucket chunks
+    uint32_t part_buckets = 0;
     uint32_t part_words = 0;
     uint32_t cur_bucket_bits = 0;
 };
@@ -1002,13 +1003,14 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         ENSURE(c, c->matrix, (size_t)U * P.W * 8);
         k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->bcounts.p, (unsigned long long*)c->offsets2.p, VB,
                                              d_scalars, S_N_SOLID, 1);
-        if (U) {
+        if (U && mode == 0) {
             k_gather_buckets<<<std::min<uint32_t>(VB, (uint32_t)c->sm_count * 8), 256, 0, st>>>(
                 (const unsigned long long*)c->ukeys.p, (const unsigned long long*)c->uwords.p, ucap,
                 (const unsigned long long*)c->bbase.p, (const unsigned long long*)c->offsets2.p, VB, P.W, U,
                 (unsigned long long*)c->kmers.p, (unsigned long long*)c->matrix.p, U);
-        }
-        L.n += 2;
+            L.n++;
+        }                               // partial build: grmkm_export_partials gathers straight into the caller's AoS buffer
+        L.n++;
         CU_TRY(c, cudaGetLastError());
         if (mode == 1) {
             h_off.resize(VB + 1);
@@ -1026,7 +1028,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         c->part_counts.resize(n_ranges);
         for (uint32_t r = 0; r < n_ranges; ++r)
             c->part_counts[r] = h_off[((uint64_t)B * (r + 1) / n_ranges) << P.sub_bits] - h_off[((uint64_t)B * r / n_ranges) << P.sub_bits];
-        c->part_total = U; c->part_cap = U; c->part_words = P.W;
+        c->part_total = U; c->part_cap = ucap; c->part_words = P.W; c->part_buckets = VB;
     }
     grmkm_stats& s = c->stats;
     s.n_input_bytes = P.in_bytes;
@@ -1245,9 +1247,10 @@ int grmkm_export_partials(grmkm_ctx* c, void* dev_dst, uint64_t dst_bytes) {
     if (!c->part_total) return GRMKM_OK;
     if (!dev_dst) return fail(c, GRMKM_E_INVALID, "null dst");
     CU_TRY(c, cudaSetDevice(c->device));
-    k_export_aos<<<(uint32_t)((c->part_total + 255) / 256), 256, 0, c->stream>>>(
-        (const unsigned long long*)c->kmers.p, (const unsigned long long*)c->matrix.p, c->part_total, c->part_words,
-        c->part_cap, (unsigned long long*)dev_dst);
+    k_gather_buckets_aos<<<std::min<uint32_t>(c->part_buckets, (uint32_t)c->sm_count * 8), 256, 0, c->stream>>>(
+        (const unsigned long long*)c->ukeys.p, (const unsigned long long*)c->uwords.p, c->part_cap,
+        (const unsigned long long*)c->bbase.p, (const unsigned long long*)c->offsets2.p, c->part_buckets, c->part_words,
+        (unsigned long long*)dev_dst);
     CU_TRY(c, cudaGetLastError());
     c->stats.n_launches++;
     CU_TRY(c, cudaStreamSynchronize(c->stream));

@@ -1465,13 +1465,22 @@ k_gather_buckets(const unsigned long long* __restrict__ tmp_keys, const unsigned
 // multi-GPU: partial columns out (AoS records for the all-to-all) and owner-side partition
 // ------------------------------------------------------------------------------------------
 // record i = [hash, word_0 .. word_{W-1}]
-__global__ void k_export_aos(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ words,
-                             uint64_t n, uint32_t W, uint64_t cap, unsigned long long* __restrict__ dst) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    unsigned long long* d = dst + i * (1 + W);
-    d[0] = keys[i];
-    for (uint32_t w = 0; w < W; ++w) d[1 + w] = words[(uint64_t)w * cap + i];
+// bucket chunks (completion order) -> AoS records [hash, word_0 .. word_{W-1}] in bucket order: the gather and the
+// export of a partial build in one pass
+__global__ void __launch_bounds__(256)
+k_gather_buckets_aos(const unsigned long long* __restrict__ tmp_keys, const unsigned long long* __restrict__ tmp_words,
+                     unsigned long long tmp_cap, const unsigned long long* __restrict__ bucket_base,
+                     const unsigned long long* __restrict__ offsets, uint32_t B, uint32_t W, unsigned long long* __restrict__ dst) {
+    for (uint32_t b = blockIdx.x; b < B; b += gridDim.x) {
+        const unsigned long long src = bucket_base[b], d0 = offsets[b], n = offsets[b + 1] - d0;
+        // one u64 of the AoS output per thread and step: coalesced stores, the loads hit W + 1 runs
+        const unsigned long long cells = n * (1 + W);
+        for (unsigned long long c = threadIdx.x; c < cells; c += blockDim.x) {
+            const unsigned long long i = c / (1 + W);
+            const uint32_t f = (uint32_t)(c - i * (1 + W));
+            dst[d0 * (1 + W) + c] = f == 0 ? tmp_keys[src + i] : tmp_words[(unsigned long long)(f - 1) * tmp_cap + src + i];
+        }
+    }
 }
 
 // compact per-bucket filtered records (mode 2 leaves them at the bucket's old offset) into new offsets

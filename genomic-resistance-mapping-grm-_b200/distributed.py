@@ -70,15 +70,20 @@ class CudaEngine:
     def set_bucket_bits(self, bits: int):
         self.b._check(self.b._lib.grmkm_set_bucket_bits(self.b._ctx, int(bits)))
 
-    def build_partial(self, world: int, n_local_words: int):
-        """-> (counts per owner [world], send tensor int64 on the GPU, AoS records of 1+n_local_words)."""
+    def build_partial(self, world: int, n_local_words: int, after_counts=None):
+        """-> (counts per owner [world], send tensor int64 on the GPU, AoS records of 1+n_local_words).
+        after_counts(counts), if given, runs as soon as the counts are known -- before the records are exported, so the
+        exchange of the counts overlaps the export kernel."""
         import torch
         counts = (C.c_uint64 * world)()
         self.b._check(self.b._lib.grmkm_build_partial(self.b._ctx, world, counts))
         counts = [int(x) for x in counts]
-        self.launches = self.b.stats["n_launches"]
+        if after_counts is not None:
+            after_counts(counts)
+        st = self.b.stats
+        self.launches = st["n_launches"]
         self.local_times = self.b.times
-        self.local_stats = self.b.stats
+        self.local_stats = st
         n = sum(counts) * (1 + n_local_words)
         send = torch.empty(max(n, 1), dtype=torch.int64, device="cuda")
         self.b._check(self.b._lib.grmkm_export_partials(self.b._ctx, C.c_void_p(send.data_ptr()), send.numel() * 8))
@@ -167,14 +172,24 @@ class DistributedBuilder:
         ev = None
         if dev == "cuda":
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        counts, send = self.engine.build_partial(self.world, wl)
-        if ev:
-            ev[0].record()
-        # 3. one all-to-all: counts first, then the records
-        c_out = torch.tensor(counts, dtype=torch.int64, device=dev)
-        c_in = torch.empty_like(c_out)
-        dist.all_to_all_single(c_in, c_out)
-        src_counts = [int(x) for x in c_in.tolist()]
+        # 3. one all-to-all: counts first (sent while the records are still being exported), then the records
+        box = {}
+
+        def send_counts(counts):
+            if ev:
+                ev[0].record()
+            c_out = torch.tensor(counts, dtype=torch.int64, device=dev)
+            box["c_in"] = torch.empty_like(c_out)
+            box["work"] = dist.all_to_all_single(box["c_in"], c_out, async_op=True)
+
+        try:
+            counts, send = self.engine.build_partial(self.world, wl, after_counts=send_counts)
+        except TypeError:                      # an injected engine without the hook
+            counts, send = self.engine.build_partial(self.world, wl)
+        if "work" not in box:
+            send_counts(counts)
+        box["work"].wait()
+        src_counts = [int(x) for x in box["c_in"].tolist()]
         in_split = [c * (1 + wl) for c in counts]
         out_split = [src_counts[s] * (1 + self.src_words[s]) for s in range(self.world)]
         recv = torch.empty(sum(out_split), dtype=torch.int64, device=send.device)
