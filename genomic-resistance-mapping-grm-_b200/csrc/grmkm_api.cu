@@ -866,7 +866,14 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
                 uint64_t est = std::max<uint64_t>(c->wide_hint, std::min<uint64_t>(P.in_bytes, max_row * 19 / 10 + P.in_bytes / 20) * 13 / 10 * groups);
                 if (const char* wc = getenv("GRMKM_WIDE_EST")) est = (uint64_t)atoll(wc);
                 uint64_t rcap = (uint64_t)((double)est / B * 1.4) + 1024;
-                rcap = (rcap + 15) & ~15ULL;
+                {   // never more than a quarter of what is free (a region that turns out too small only costs the count pass)
+                    size_t free_b = 0, total_b = 0;
+                    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+                        const uint64_t have = c->wide.cap + free_b / 4;
+                        rcap = std::min<uint64_t>(rcap, have / ((uint64_t)B * RS * 8));
+                    }
+                }
+                rcap = std::max<uint64_t>(64, rcap & ~15ULL);
                 ENSURE(c, c->wide, ((uint64_t)B * rcap + kStTile) * RS * 8);
                 k_init_regions<<<(B + 1 + 255) / 256, 256, 0, st>>>((unsigned long long*)c->offsets.p, (unsigned long long*)c->hist.p, B, rcap);
                 xp.records = (unsigned long long*)c->wide.p; xp.region_cap = rcap; xp.dump = (uint64_t)B * rcap;

@@ -351,3 +351,49 @@ def test_add_genomes_in_one_call(gpu):
         b.add_genomes(rows, [d.data_ptr() for d in dev], [len(f) for f in files], on_device=True)
         b.build()
         assert np.array_equal(b.kmers(), ref.kmers) and np.array_equal(b.matrix(), ref.matrix)
+
+
+def test_full_size_c2_workload(gpu):
+    """BASELINE.json configs[1] at full size (100 synthetic 5 Mbp genomes, k = 31, singletons kept): bit-exact against the
+    oracle (6 s on 16 cores), plus the properties that do not need it -- every valid window in exactly one unit, columns
+    strictly ascending in hash order, padding bits clear, the same bytes from a second build and from permuted rows."""
+    import ctypes as C
+    import torch
+    from grm_b200 import synth
+    from grm_b200.builder import KmerMatrixBuilder
+    cfg = synth.SynthConfig(seed=synth.MASTER_SEED + 1)
+    G, k = 100, 31
+    ids = list(range(G))
+    lay, total, spans = synth.build_layout(cfg, ids)
+    buf = torch.empty(total, dtype=torch.uint8, device="cuda")
+    with KmerMatrixBuilder(k=k, keep_singletons=True) as b:
+        b._check(b._lib.grmkm_synth_fasta_device(b._ctx, C.c_void_p(lay.ctypes.data), lay.nbytes,
+                                                 C.c_void_p(buf.data_ptr()), total))
+        ptrs = [buf.data_ptr() + off for off, _ in spans]
+        lens = [ln for _, ln in spans]
+        b.add_genomes(list(range(G)), ptrs, lens, on_device=True)
+        b.build()
+        st = b.stats
+        km, mat = b.kmers(), b.matrix()
+        assert st["n_bases"] == synth.n_bases_of(cfg, ids)
+        assert st["n_windows"] == st["n_bases"] - (k - 1) * st["n_records"]          # ACGT only: every window is valid
+        h = km * np.uint64(0x9E3779B97F4A7C15)
+        assert (h[1:] > h[:-1]).all()                                                  # strictly ascending hash order
+        assert mat.shape == (2, len(km)) and (mat[0] | mat[1]).all()                   # no empty column
+        assert not (mat[1] & np.uint64((1 << 28) - 1)).any()                           # rows 100..127 do not exist
+        # a second build of the same context, then the rows in reverse order
+        b.reset(); b.add_genomes(list(range(G)), ptrs, lens, on_device=True); b.build()
+        assert np.array_equal(b.kmers(), km) and np.array_equal(b.matrix(), mat)
+        b.reset(); b.add_genomes([G - 1 - r for r in range(G)], ptrs, lens, on_device=True); b.build()
+        km2, mat2 = b.kmers(), b.matrix()
+        assert np.array_equal(km2, km)
+        def rows_of(m):                                                                # [row][sampled column] presence bits
+            sub = np.ascontiguousarray(m[:, ::997])
+            by = sub.view(np.uint8).reshape(2, -1, 8)[:, :, ::-1]                      # most significant byte first
+            return np.unpackbits(by, axis=2).transpose(0, 2, 1).reshape(128, -1)[:G]
+        assert np.array_equal(rows_of(mat2), rows_of(mat)[::-1])
+        # the oracle on the same bytes
+        host = buf.cpu().numpy()
+        ref = oracle.build([[(host[o:o + n].tobytes(), 0)] for o, n in spans], k, 1, True)
+        assert st["n_bases"] == ref.n_bases and st["n_windows"] == ref.n_windows
+        assert np.array_equal(km, ref.kmers) and np.array_equal(mat, ref.matrix)
