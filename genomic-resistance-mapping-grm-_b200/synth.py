@@ -122,6 +122,34 @@ def genome_fasta(cfg: SynthConfig, g: int) -> bytes:
     return b"".join(out)
 
 
+def genome_reads_fastq(cfg: SynthConfig, g: int, n_reads: int, read_len: int = 150, err: float = 0.005) -> bytes:
+    """FASTQ read set of genome g: n_reads reads of read_len bases sampled from the genome's
+    linear sequence, start and strand from the counter hash, substitution errors at rate err (mostly count-1 k-mers: what
+    min-abundance 2 removes), 4-line records, constant quality 'I', header @g{g}_r{j}."""
+    seq = genome_sequence(cfg, g)
+    L = len(seq)
+    read_len = min(read_len, L)
+    j = np.arange(n_reads, dtype=_U)
+    gj = (_U(g) << _U(32)) + j
+    start = (h(cfg.seed, 10, gj) % _U(L - read_len + 1)).astype(np.int64)
+    strand = (h(cfg.seed, 11, gj) & _U(1)).astype(bool)
+    idx = start[:, None] + np.arange(read_len, dtype=np.int64)[None, :]
+    bases = seq[idx]                                                   # [n_reads][read_len], 0..3 = A C G T
+    bases = np.where(strand[:, None], 3 - bases[:, ::-1], bases)
+    cell = gj[:, None] * _U(1024) + np.arange(read_len, dtype=_U)[None, :]
+    hit = h(cfg.seed, 12, cell) < _U(int(err * 2.0 ** 64))
+    sub = (bases + 1 + (h(cfg.seed, 13, cell) % _U(3)).astype(np.int64)) & 3
+    bases = np.where(hit, sub, bases)
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)[bases]            # uint8 [n_reads][read_len]
+    qual = b"I" * read_len
+    out = []
+    for r in range(n_reads):
+        out.append(b"@g%d_r%d\n" % (g, r))
+        out.append(letters[r].tobytes())
+        out.append(b"\n+\n" + qual + b"\n")
+    return b"".join(out)
+
+
 def build_layout(cfg: SynthConfig, genome_ids) -> tuple[np.ndarray, int, list[tuple[int, int]]]:
     """Layout table for grmkm_synth_fasta_device.  Returns (u64 table, total bytes, [(offset, length)])."""
     C, NI, LW = cfg.n_contigs, cfg.n_islands, cfg.line_width

@@ -397,3 +397,42 @@ def test_full_size_c2_workload(gpu):
         ref = oracle.build([[(host[o:o + n].tobytes(), 0)] for o, n in spans], k, 1, True)
         assert st["n_bases"] == ref.n_bases and st["n_windows"] == ref.n_windows
         assert np.array_equal(km, ref.kmers) and np.array_equal(mat, ref.matrix)
+
+
+@pytest.mark.parametrize("k", [15, 21, 31])
+def test_c1_size_contigs_singletons_dropped(gpu, k):
+    """BASELINE.json configs[0] / configs[4] shape: 20 synthetic 5 Mbp genomes through the from-contigs settings (min
+    abundance 1, singleton k-mers dropped) at k = 15 / 21 / 31, full size, bit-exact against the oracle."""
+    import ctypes as C
+    import torch
+    from grm_b200 import synth
+    from grm_b200.builder import KmerMatrixBuilder
+    cfg = synth.SynthConfig(seed=synth.MASTER_SEED)
+    ids = list(range(20))
+    lay, total, spans = synth.build_layout(cfg, ids)
+    buf = torch.empty(total, dtype=torch.uint8, device="cuda")
+    with KmerMatrixBuilder(k=k, keep_singletons=False) as b:
+        b._check(b._lib.grmkm_synth_fasta_device(b._ctx, C.c_void_p(lay.ctypes.data), lay.nbytes,
+                                                 C.c_void_p(buf.data_ptr()), total))
+        b.add_genomes(ids, [buf.data_ptr() + off for off, _ in spans], [ln for _, ln in spans], on_device=True)
+        b.build()
+        host = buf.cpu().numpy()
+        ref = oracle.build([[(host[o:o + n].tobytes(), 0)] for o, n in spans], k, 1, False)
+        assert b.stats["n_windows"] == ref.n_windows
+        assert np.array_equal(b.kmers(), ref.kmers) and np.array_equal(b.matrix(), ref.matrix)
+
+
+def test_c4_style_read_sets(gpu):
+    """BASELINE.json configs[3] shape at a size the oracle finishes in seconds: 30x read sets (150 bp, 0.5 % substitution
+    errors) of 6 synthetic genomes, each one multi-megabyte FASTQ file (a long single-file look-back chain), min abundance
+    2 drops the error k-mers; also min abundance 1 (the unit path on reads)."""
+    from grm_b200 import synth
+    cfg = synth.SynthConfig(seed=synth.MASTER_SEED + 3).scaled(0.02)          # 90 kbp core
+    genomes = []
+    for g in range(6):
+        n_reads = 30 * len(synth.genome_sequence(cfg, g)) // 150
+        genomes.append([synth.genome_reads_fastq(cfg, g, n_reads)])
+    st2 = check(genomes, 31, min_abundance=2, keep_singletons=True, kind=1)
+    st1 = check(genomes, 31, min_abundance=1, keep_singletons=True, kind=1)
+    assert st1["n_kmers"] > 3 * st2["n_kmers"]                                # the error k-mers are most of the unfiltered set
+    check(genomes, 31, min_abundance=2, keep_singletons=False, kind=1)
