@@ -99,3 +99,22 @@ def test_tsv_grammar_is_what_from_tsv_expects():
     assert (len(r.tsv) - header) % (len(lines[1]) + 1) == 0
     assert (len(r.tsv) - header) // (len(lines[1]) + 1) == r.n_kmers
     assert r.tsv == oracle.py_format_tsv(r.kmers, r.matrix, names, 12)
+
+
+def test_synthetic_read_sets_and_min_abundance():
+    """The C4 generator (grm_b200.synth.genome_reads_fastq) is deterministic, and on 30x reads with 0.5 % substitution
+    errors min abundance 2 removes most of the k-mers (the error k-mers) while keeping the genome's own."""
+    from grm_b200 import synth
+    cfg = synth.SynthConfig(seed=synth.MASTER_SEED + 3).scaled(0.002)
+    L = len(synth.genome_sequence(cfg, 0))
+    fq = synth.genome_reads_fastq(cfg, 0, 30 * L // 150)
+    assert fq == synth.genome_reads_fastq(cfg, 0, 30 * L // 150)
+    assert fq.count(b"\n") == 4 * (30 * L // 150) and fq.startswith(b"@g0_r0\n")
+    fa = synth.genome_fasta(cfg, 0)
+    genome = oracle.build([[(fa, 0)]], 21, 1, True)
+    all_k = oracle.build([[(fq, 1)]], 21, 1, True)
+    solid = oracle.build([[(fq, 1)]], 21, 2, True)
+    assert len(all_k.kmers) > 2 * len(solid.kmers)
+    # contigs cut the genome, reads do not: the solid read k-mers cover (almost) every genome k-mer
+    assert np.isin(genome.kmers, solid.kmers).mean() > 0.95
+    assert np.isin(solid.kmers, all_k.kmers).all()
