@@ -502,11 +502,21 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
     P.slots = table_slots(c, Wtab);
     if (P.slots < 256) return fail(c, GRMKM_E_UNSUPPORTED, "too many genomes for the shared-memory column table");
     P.agg_smem = table_smem(P.slots, Wtab);
+    // the unit path (below) carries a genome GROUP in its records, not a row, and its expansion sorts tiles over at most
+    // 2^11 buckets: more distinct k-mers than 2^11 tables hold are handled as key sub-ranges of the buckets (virtual
+    // buckets: one aggregate pass each over the bucket's records, which stay in L2), and beyond 2^14 by the table's own
+    // overflow split -- instead of falling off to the per-record scatter
+    const bool units_wanted = c->cfg.min_abundance <= 1 && !(c->cfg.flags & (GRMKM_FLAG_KMER_RECORDS | GRMKM_FLAG_SIMPLE_SCATTER));
+    constexpr uint32_t kUnitMaxBucketBits = 11;
     P.bucket_bits = c->cfg.bucket_bits ? c->cfg.bucket_bits : auto_bucket_bits(c, P.G);
-    P.bucket_bits = std::max(P.bucket_bits, P.row_bits);
+    if (!units_wanted) P.bucket_bits = std::max(P.bucket_bits, P.row_bits);
     if (P.bucket_bits > 15) return fail(c, GRMKM_E_UNSUPPORTED, "bucket_bits > 15");
-    c->cur_bucket_bits = P.bucket_bits;
     if (const char* sbv = getenv("GRMKM_SUB_BITS")) P.sub_bits = (uint32_t)std::min(3, std::max(0, atoi(sbv)));
+    if (units_wanted && P.bucket_bits > kUnitMaxBucketBits) {
+        P.sub_bits = std::max(P.sub_bits, std::min(3u, P.bucket_bits - kUnitMaxBucketBits));
+        P.bucket_bits = kUnitMaxBucketBits;
+    }
+    c->cur_bucket_bits = P.bucket_bits;
     const uint32_t B = 1u << P.bucket_bits;
 
     ENSURE(c, c->scalars, S_COUNT * 8);

@@ -156,3 +156,19 @@ def test_entry_list_too_small_is_retried(gpu, monkeypatch):
     assert st["n_unit_entries"] > 100
     monkeypatch.setenv("GRMKM_WIDE_EXACT", "1")
     check(genomes, 31, keep_singletons=False)
+
+
+def test_more_buckets_than_the_expansion_sorts_become_key_sub_ranges(gpu, monkeypatch):
+    """More distinct k-mers than 2^11 shared-memory tables hold: the unit path keeps 2^11 hash buckets and aggregates each
+    as 2^s key sub-ranges (virtual buckets) instead of dropping to the per-record scatter."""
+    rng = np.random.default_rng(47)
+    genomes = shared_population(rng, 12, core_len=50000, snp=0.01)
+    st = check(genomes, 31, keep_singletons=True, bucket_bits=13)          # 2^11 buckets x 2^2 sub-ranges
+    assert st["n_units"] > 0 and st["n_buckets"] == 2048
+    st = check(genomes, 21, keep_singletons=False, bucket_bits=15)
+    assert st["n_units"] > 0 and st["n_buckets"] == 2048
+    monkeypatch.setenv("GRMKM_SUB_BITS", "1")
+    st = check(genomes, 31, keep_singletons=False)
+    assert st["n_units"] > 0
+    genomes = shared_population(rng, 130, core_len=4000, snp=0.01)         # three word-rows, two genome groups
+    check(genomes, 31, keep_singletons=False)
