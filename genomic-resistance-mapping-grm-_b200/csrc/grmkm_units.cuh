@@ -404,7 +404,10 @@ k_units_scatter(const UnitScatterParams p) {
 // An entry holds the presence of WB x 64 consecutive genomes (WB = 1, 2 or 4: all of them when there are at most
 // 256 genomes), so a unit shared by everybody is ONE entry.  Table: slots x (16-byte key + WB words).
 constexpr int kUdThreads = 1024;
-constexpr int kUdCheck = 8;                            // batches between "is the table filling up" checkpoints
+#ifndef GRMKM_UD_CHECK
+#define GRMKM_UD_CHECK 16
+#endif
+constexpr int kUdCheck = GRMKM_UD_CHECK;                            // batches between "is the table filling up" checkpoints
 
 __host__ __device__ inline uint32_t unit_words_per_entry(uint32_t W) { return W <= 1 ? 1u : W == 2 ? 2u : 4u; }
 __host__ __device__ inline uint32_t unit_dedupe_slots(uint32_t WB) { return WB == 1 ? 8192u : WB == 2 ? 6144u : 4096u; }
