@@ -1274,6 +1274,30 @@ int grmkm_export_partials(grmkm_ctx* c, void* dev_dst, uint64_t dst_bytes) {
     return GRMKM_OK;
 }
 
+int grmkm_export_partials_peers(grmkm_ctx* c, uint32_t n_ranks, void* const* peer_dst, const uint64_t* peer_word_off) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    if (!c->part_ranks) return fail(c, GRMKM_E_INVALID, "no partial result: call grmkm_build_partial first");
+    if (n_ranks != c->part_ranks || n_ranks > 16 || !peer_dst || !peer_word_off)
+        return fail(c, GRMKM_E_INVALID, "bad peer export arguments");
+    if (!c->part_total) return GRMKM_OK;
+    CU_TRY(c, cudaSetDevice(c->device));
+    PeerSlices ps{};
+    ps.n = n_ranks;
+    const uint32_t sub = ceil_log2(std::max(1u, c->part_buckets >> c->cur_bucket_bits));      // virtual buckets per bucket
+    const uint64_t B = 1ULL << c->cur_bucket_bits;
+    for (uint32_t d = 0; d <= n_ranks; ++d) ps.first[d] = (uint32_t)((B * d / n_ranks) << sub);
+    for (uint32_t d = 0; d < n_ranks; ++d) {
+        if (c->part_counts[d] && !peer_dst[d]) return fail(c, GRMKM_E_INVALID, "null peer buffer");
+        ps.dst[d] = (unsigned long long*)peer_dst[d] + peer_word_off[d];
+    }
+    k_gather_buckets_peers<<<std::min<uint32_t>(c->part_buckets, (uint32_t)c->sm_count * 8), 256, 0, c->stream>>>(
+        (const unsigned long long*)c->ukeys.p, (const unsigned long long*)c->uwords.p, c->part_cap,
+        (const unsigned long long*)c->bbase.p, (const unsigned long long*)c->offsets2.p, c->part_buckets, c->part_words, ps);
+    CU_TRY(c, cudaGetLastError());
+    c->stats.n_launches++;
+    return GRMKM_OK;             // asynchronous on the context's stream: the caller's barrier follows on the same stream
+}
+
 int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, uint32_t rank, const uint64_t* src_counts,
                          const uint32_t* src_words, uint32_t total_genomes) {
     if (check_ctx(c)) return GRMKM_E_INVALID;

@@ -1465,6 +1465,32 @@ k_gather_buckets(const unsigned long long* __restrict__ tmp_keys, const unsigned
 // multi-GPU: partial columns out (AoS records for the all-to-all) and owner-side partition
 // ------------------------------------------------------------------------------------------
 // record i = [hash, word_0 .. word_{W-1}]
+// The same gather, fused with the all-to-all: owner d's slice (buckets [first[d], first[d + 1])) is stored straight into
+// rank d's receive buffer over NVLink (peer pointers from torch symmetric memory), at the word offset the counts
+// exchange assigned to this rank.  No send buffer, no NCCL send / recv; the ranks meet at one barrier afterwards.
+struct PeerSlices {
+    unsigned long long* dst[16];          // peer d's receive buffer + this rank's word offset in it
+    uint32_t first[17];                   // first (virtual) bucket of owner d; first[n] = B
+    uint32_t n;
+};
+__global__ void __launch_bounds__(256)
+k_gather_buckets_peers(const unsigned long long* __restrict__ tmp_keys, const unsigned long long* __restrict__ tmp_words,
+                       unsigned long long tmp_cap, const unsigned long long* __restrict__ bucket_base,
+                       const unsigned long long* __restrict__ offsets, uint32_t B, uint32_t W, const PeerSlices ps) {
+    for (uint32_t b = blockIdx.x; b < B; b += gridDim.x) {
+        uint32_t d = 0;
+        while (d + 1 < ps.n && b >= ps.first[d + 1]) ++d;
+        const unsigned long long src = bucket_base[b], d0 = offsets[b] - offsets[ps.first[d]], n = offsets[b + 1] - offsets[b];
+        unsigned long long* __restrict__ dst = ps.dst[d] + d0 * (1 + W);
+        const unsigned long long cells = n * (1 + W);
+        for (unsigned long long c = threadIdx.x; c < cells; c += blockDim.x) {
+            const unsigned long long i = c / (1 + W);
+            const uint32_t f = (uint32_t)(c - i * (1 + W));
+            dst[c] = f == 0 ? tmp_keys[src + i] : tmp_words[(unsigned long long)(f - 1) * tmp_cap + src + i];
+        }
+    }
+}
+
 // bucket chunks (completion order) -> AoS records [hash, word_0 .. word_{W-1}] in bucket order: the gather and the
 // export of a partial build in one pass
 __global__ void __launch_bounds__(256)

@@ -90,6 +90,23 @@ class CudaEngine:
         self.launches += 1
         return counts, send[:n]
 
+    def build_local(self, world: int):
+        """Local stages only -> counts per owner [world]; the partial columns stay in the context (export_peers)."""
+        counts = (C.c_uint64 * world)()
+        self.b._check(self.b._lib.grmkm_build_partial(self.b._ctx, world, counts))
+        st = self.b.stats
+        self.launches = st["n_launches"]
+        self.local_times = self.b.times
+        self.local_stats = st
+        return [int(x) for x in counts]
+
+    def export_peers(self, world: int, peer_ptrs: Sequence[int], word_offsets: Sequence[int]):
+        """Owner d's slice is stored straight into peer d's receive buffer (asynchronous on the context's stream)."""
+        ptrs = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        offs = (C.c_uint64 * world)(*[int(o) for o in word_offsets])
+        self.b._check(self.b._lib.grmkm_export_partials_peers(self.b._ctx, world, ptrs, offs))
+        self.launches += 1
+
     def merge(self, recv, world: int, rank: int, src_counts: Sequence[int], src_words: Sequence[int], n_genomes: int):
         sc = (C.c_uint64 * world)(*src_counts)
         sw = (C.c_uint32 * world)(*src_words)
@@ -121,13 +138,22 @@ class DistributedBuilder:
         self.src_words = words_per_rank(self.n_genomes, self.world)
         self.launches = 0
         self.builder = builder
+        self._stream = stream
         if engine is None:
             from .builder import KmerMatrixBuilder
+            if stream is None and self.world > 1:
+                import torch
+                self._stream = stream = torch.cuda.current_stream().cuda_stream      # kernels and collectives on ONE stream
             self.builder = KmerMatrixBuilder(k=k, min_abundance=min_abundance, keep_singletons=keep_singletons,
                                              input_kind=input_kind, device=device, stream=stream)
             engine = CudaEngine(self.builder)
         self.engine = engine
         self._n_kmers = 0
+        # peer exchange (NVLink stores into the owners' receive buffers, torch symmetric memory); None = not tried yet,
+        # False = unavailable (other backend, injected engine, GRM_EXCHANGE=nccl): NCCL all-to-all instead
+        self._peer = None
+        self._peer_buf = None
+        self._peer_cap = 0
 
     # -- inputs (local row index) ----------------------------------------------------------------
     def reset(self):
@@ -167,6 +193,11 @@ class DistributedBuilder:
             dist.all_reduce(bits, op=dist.ReduceOp.MAX)
             self._agreed_bits = int(bits.item())
         self.engine.set_bucket_bits(self._agreed_bits)
+        if self._peer is None:
+            self._peer = (dev == "cuda" and hasattr(self.engine, "export_peers")
+                          and os.environ.get("GRM_EXCHANGE", "peer") != "nccl" and self._peer_probe())
+        if self._peer:
+            return self._build_peer(torch, dist)
         # 2. local stages -> partial columns grouped by owner
         wl = self.src_words[self.rank]
         ev = None
@@ -213,6 +244,60 @@ class DistributedBuilder:
         self.local_stats = getattr(self.engine, "local_stats", {})
         self.launches = getattr(self.engine, "launches", 0)
         self._recv = recv  # keep alive until the next build
+        self._kmers_cache = None
+        self._n_kmers = None
+        return self
+
+    # -- fused export + exchange over peer memory ---------------------------------------------------
+    def _peer_probe(self) -> bool:
+        try:
+            import torch.distributed._symmetric_memory as sm      # noqa: F401
+            return True
+        except Exception:
+            return False
+
+    def _peer_alloc(self, words: int, torch, dist):
+        """(Re)allocate the symmetric receive buffer: collective, every rank calls it with the same size."""
+        import torch.distributed._symmetric_memory as sm
+        self._peer_buf = sm.empty(int(words), dtype=torch.int64, device=torch.device("cuda", torch.cuda.current_device()))
+        self._peer_hdl = sm.rendezvous(self._peer_buf, dist.group.WORLD)
+        self._peer_cap = int(words)
+
+    def _build_peer(self, torch, dist):
+        """Local stages, then ONE kernel per rank gathers its partial columns and stores every owner's slice straight
+        into that owner's receive buffer over NVLink; the ranks meet at a device-side barrier and merge.  The only
+        collective besides the barrier is the all-gather of the P x P counts that assigns the offsets."""
+        P, r = self.world, self.rank
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        counts = self.engine.build_local(P)
+        ev[0].record()
+        c_out = torch.tensor(counts, dtype=torch.int64, device="cuda")
+        c_all = torch.empty(P * P, dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(c_all, c_out)
+        M = c_all.view(P, P).tolist()                                    # M[s][d]: columns source s holds for owner d
+        width = [1 + w for w in self.src_words]
+        need = [sum(M[s][d] * width[s] for s in range(P)) for d in range(P)]
+        if max(need) > self._peer_cap:                                   # the same decision on every rank (same M)
+            self._peer_alloc(max(need) + max(need) // 4 + 1024, torch, dist)
+        offs = [sum(M[s][d] * width[s] for s in range(r)) for d in range(P)]
+        self.engine.export_peers(P, list(self._peer_hdl.buffer_ptrs), offs)
+        self._peer_hdl.barrier()                                         # every slice has landed (same stream as the kernel)
+        self.exchange_bytes = int(sum(counts) * width[r] * 8)
+        ev[1].record()
+        src_counts = [M[s][r] for s in range(P)]
+        self.engine.merge(self._peer_buf[:max(need[r], 1)], P, r, src_counts, self.src_words, self.n_genomes)
+        lt = dict(getattr(self.engine, "local_times", {}))
+        mt = getattr(self.engine, "merge_times", {})
+        lt.pop("total", None)
+        lt.pop("sort", None)
+        ev[1].synchronize()
+        lt["exchange"] = ev[0].elapsed_time(ev[1])
+        lt.update({"merge_partition": mt.get("scatter", 0.0), "merge_aggregate": mt.get("aggregate", 0.0),
+                   "merge_sort": mt.get("sort", 0.0)})
+        lt["total"] = sum(lt.values())
+        self.stage_times = lt
+        self.local_stats = getattr(self.engine, "local_stats", {})
+        self.launches = getattr(self.engine, "launches", 0)
         self._kmers_cache = None
         self._n_kmers = None
         return self

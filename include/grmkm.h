@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GRMKM_ABI_VERSION 6
+#define GRMKM_ABI_VERSION 7
 
 enum {
     GRMKM_OK = 0,
@@ -200,6 +200,11 @@ int grmkm_build_partial(grmkm_ctx* ctx, uint32_t n_ranks, uint64_t* counts);
 int grmkm_plan_bucket_bits(grmkm_ctx* ctx, uint32_t* bits);
 int grmkm_set_bucket_bits(grmkm_ctx* ctx, uint32_t bits);
 int grmkm_export_partials(grmkm_ctx* ctx, void* dev_dst, uint64_t dst_bytes);
+/* The export fused with the all-to-all: owner d's slice of the partial columns is stored straight into rank d's
+ * receive buffer (peer_dst[d], peer-accessible device memory, e.g. torch symmetric memory) at word offset
+ * peer_word_off[d] -- over NVLink, no send buffer and no NCCL send/recv (Ray's message routing, src/app.py:1310).
+ * Asynchronous on the context's stream; the ranks synchronise (barrier) before anybody merges. */
+int grmkm_export_partials_peers(grmkm_ctx* ctx, uint32_t n_ranks, void* const* peer_dst, const uint64_t* peer_word_off);
 int grmkm_merge_partials(grmkm_ctx* ctx, const void* dev_parts, uint32_t n_ranks, uint32_t rank,
                          const uint64_t* src_counts, const uint32_t* src_words, uint32_t total_genomes);
 

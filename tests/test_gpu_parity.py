@@ -283,6 +283,47 @@ def test_partial_merge_emulated_ranks(gpu, world, G, keep):
         e.b.close()
 
 
+@pytest.mark.parametrize("world,G,keep", [(2, 130, True), (3, 200, False), (8, 1000, False)])
+def test_partial_export_into_peer_buffers(gpu, world, G, keep):
+    """grmkm_export_partials_peers (the export fused with the all-to-all: every owner's slice is stored straight into
+    that owner's receive buffer at the offset the counts assign) with the P receive buffers as local tensors."""
+    import torch
+    from grm_b200.builder import KmerMatrixBuilder
+    from grm_b200.distributed import CudaEngine, row_partition, words_per_rank
+    rng = np.random.default_rng(1000 + G)
+    shared = [inputs.rand_seq(rng, 3000), inputs.rand_seq(rng, 700)]
+    genomes = [inputs.fasta(rng, n_records=2, max_len=400, shared=shared) for _ in range(G)]
+    parts, sw = row_partition(G, world), words_per_rank(G, world)
+    engines = []
+    for r in range(world):
+        b = KmerMatrixBuilder(k=21, keep_singletons=keep)
+        b.set_genome_count(len(parts[r]))
+        b.add_genomes(list(range(len(parts[r]))), [genomes[g] for g in parts[r]])
+        engines.append(CudaEngine(b))
+    bits = max(e.plan_bucket_bits() for e in engines)
+    M = []
+    for e in engines:
+        e.set_bucket_bits(bits)
+        M.append(e.build_local(world))                     # M[s][d]
+    width = [1 + w for w in sw]
+    need = [sum(M[s][d] * width[s] for s in range(world)) for d in range(world)]
+    recv = [torch.full((max(n, 1),), -1, dtype=torch.int64, device="cuda") for n in need]
+    for r, e in enumerate(engines):
+        offs = [sum(M[s][d] * width[s] for s in range(r)) for d in range(world)]
+        e.export_peers(world, [t.data_ptr() for t in recv], offs)
+    torch.cuda.synchronize()
+    slices_k, slices_m = [], []
+    for d, e in enumerate(engines):
+        e.merge(recv[d][:need[d]], world, d, [M[s][d] for s in range(world)], sw, G)
+        k_, m_ = e.result()
+        slices_k.append(k_); slices_m.append(m_)
+    ref = oracle.build([[(g, 0)] for g in genomes], 21, 1, keep)
+    assert np.array_equal(np.concatenate(slices_k), ref.kmers)
+    assert np.array_equal(np.concatenate(slices_m, axis=1), ref.matrix)
+    for e in engines:
+        e.b.close()
+
+
 def test_radix_order_fallback_and_simple_scatter(gpu):
     """The A/B flags select the older code paths; results must not change."""
     from grm_b200 import native
