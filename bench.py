@@ -12,7 +12,8 @@ hash buckets -> shared-memory aggregation -> ordered columns (kmers[U] + matrix[
           kmers + matrix inside the timed region
 Workload at N=1 = BASELINE.json configs[1] (Ray Surveyor matrix: 100 synthetic 5 Mbp genomes, k=31,
 min abundance 1, no singleton filter); at N>1 = configs[2] family (125 genomes per GPU, 1000 at N=8,
-rows split across ranks in 64-aligned blocks, k-mers exchanged by hash range with one NCCL all-to-all).
+rows split across ranks in 64-aligned blocks, partial columns exchanged by hash range: the export kernel stores
+every owner's slice into its receive buffer over NVLink (torch symmetric memory; NCCL all-to-all as the fallback)).
 """
 from __future__ import annotations
 
@@ -176,7 +177,7 @@ def workload_config(n_gpus):
     else:
         g = GENOMES_PER_GPU * n_gpus
         wl = (f"C3 family: {g} synthetic 5 Mbp genomes ({GENOMES_PER_GPU} per GPU) k=31, rows sharded across "
-              f"{n_gpus} GPUs in 64-aligned blocks, hash-range all-to-all")
+              f"{n_gpus} GPUs in 64-aligned blocks, hash-range exchange (NVLink peer stores fused into the export kernel)")
     return {"workload": wl, "genomes": g, "k": K, "min_abundance": 1, "keep_singletons": True,
             "l2": "inputs (>=500 MB FASTA per GPU) larger than the 126 MB L2; no flush needed"}
 
