@@ -174,17 +174,18 @@ size_t agg_smem_budget(const grmkm_ctx* c) {
 
 // table capacity for W words per column and the bucket count that keeps a bucket's distinct k-mers
 // (estimated as 3x the largest genome) at about half of it
-// table = (slots + kMaxProbe) x (u64 key + 2W u32 half-words + u8 kept flag); slots = home positions
+// table = (slots + kMaxProbe) x (u64 key + 2W u32 half-words + u8 kept flag / correction + u8 own inversions); slots = home positions
 uint32_t table_slots(const grmkm_ctx* c, uint32_t W) {
     const size_t budget = agg_smem_budget(c);
-    const size_t total = budget / (9 + 8 * (size_t)W);
+    const size_t total = (budget - 8) / (10 + 8 * (size_t)W);
     if (total < (size_t)kMaxProbe + 256) return 0;
     return (uint32_t)std::min<size_t>(kAggMaxSlots, total - kMaxProbe);
 }
 size_t table_smem(uint32_t slots, uint32_t W) {
-    return (((size_t)slots + kMaxProbe) * (9 + 8 * (size_t)W) + 15) & ~size_t(15);
+    return (((size_t)slots + kMaxProbe) * (10 + 8 * (size_t)W) + 8 + 15) & ~size_t(15);
 }
-// Bucket count: the distinct k-mers of a bucket must fit its shared-memory table at a load of about 0.55.
+// Bucket count: the distinct k-mers of a bucket must fit its shared-memory table at a load of about 0.6 by the estimate
+// (which is generous: C2 ends at 0.53).
 // The pan-genome of the context is estimated from the largest genome (1.9x its text; a bucket that turns out
 // too full is split into key sub-ranges by the kernel, so the estimate only costs time, never correctness).
 // Fewer buckets = longer runs per scatter tile = fewer store requests, the scatter's bound.
@@ -194,7 +195,7 @@ uint32_t auto_bucket_bits(const grmkm_ctx* c, uint32_t G) {
     const uint64_t max_row = *std::max_element(row_bytes.begin(), row_bytes.end());
     const uint32_t slots = table_slots(c, (G + 63) / 64);
     const uint64_t u_est = max_row + max_row * 9 / 10 + 1024;
-    const uint64_t per = std::max<uint64_t>(1, (uint64_t)slots * 55 / 100);
+    const uint64_t per = std::max<uint64_t>(1, (uint64_t)slots * 60 / 100);
     const uint32_t row_bits = std::max(1u, ceil_log2(G));
     return std::max(row_bits, std::min(15u, std::max(6u, ceil_log2((u_est + per - 1) / per))));
 }
@@ -1325,9 +1326,9 @@ int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
     if (n_total == 0) { c->built = true; c->stats.n_kmers = 0; return GRMKM_OK; }
     // the merge table keeps one entry reference per source and slot instead of the words (k_aggregate_cols<3>)
     const uint32_t tw = (n_ranks + 1) & ~1u;
-    const size_t slot_bytes = 9 + 4 * (size_t)tw;
-    const uint32_t slots = (uint32_t)std::min<size_t>(kAggMaxSlots, agg_smem_budget(c) / slot_bytes - kMaxProbe);
-    const size_t smem = (((size_t)slots + kMaxProbe) * slot_bytes + 15) & ~size_t(15);
+    const size_t slot_bytes = 10 + 4 * (size_t)tw;
+    const uint32_t slots = (uint32_t)std::min<size_t>(kAggMaxSlots, (agg_smem_budget(c) - 8) / slot_bytes - kMaxProbe);
+    const size_t smem = (((size_t)slots + kMaxProbe) * slot_bytes + 8 + 15) & ~size_t(15);
     for (uint32_t s = 0; s < n_ranks; ++s)
         if (src_counts[s] >= 0xFFFFFFFFULL) return fail(c, GRMKM_E_UNSUPPORTED, "more than 2^32 partial columns from one source");
     // every rank sees 1/P of the hash space: size the buckets for n_total * P entries over the full range

@@ -1032,7 +1032,8 @@ constexpr int kAggBatch = 8;
 struct AggTable {
     unsigned long long* keys;
     uint32_t* w32;
-    uint8_t* kept;
+    uint8_t* kept;         // [total rounded up to 4] bit 7: the slot's column is kept; bits 0-6: inversions found by LATER slots
+    uint8_t* dec;          // [total] inversions the slot found itself (larger kept keys between its home and itself)
     uint32_t slots;        // home slots
     uint32_t total;        // slots + tail
 };
@@ -1285,12 +1286,14 @@ __device__ __forceinline__ void agg_fix(const AggTable& t, uint32_t shift) {
     for (uint32_t i = threadIdx.x; i < t.total; i += kAggThreads) {
         if (!(t.kept[i] & 0x80u)) continue;
         const unsigned long long key = t.keys[i];
+        uint32_t dec = 0;
         for (uint32_t j = home_slot(key, shift, t.slots); j < i; ++j)
-            if (t.keys[j] > key && (t.kept[j] & 0x80u)) atomicAdd(&kept32[j >> 2], 1u << (8u * (j & 3u)));
+            if (t.keys[j] > key && (t.kept[j] & 0x80u)) { atomicAdd(&kept32[j >> 2], 1u << (8u * (j & 3u))); ++dec; }
+        t.dec[i] = (uint8_t)dec;             // the emission does not walk again
     }
 }
 
-// Pass B2: emission at out[base + rank].  s_wp = exclusive scan of s_wc.
+// Pass B2: emission at out[base + rank], rank = kept slots before + correction - own inversions.  s_wp = exclusive scan of s_wc.
 template <int MODE>
 __device__ __forceinline__ void agg_emit(const AggParams2& p, const AggTable& t, const uint32_t* s_wp,
                                          unsigned long long base, uint32_t b, uint32_t key_bits, uint32_t shift) {
@@ -1304,9 +1307,7 @@ __device__ __forceinline__ void agg_emit(const AggParams2& p, const AggTable& t,
         const uint32_t bal = __ballot_sync(0xffffffffu, kf);
         if (!kf) continue;
         const unsigned long long key = t.keys[i];
-        uint32_t rank = s_wp[c * (kAggThreads / 32) + warp] + (uint32_t)__popc(bal & ((1u << lane) - 1u)) + (flag & 0x7Fu);
-        for (uint32_t j = home_slot(key, shift, t.slots); j < i; ++j)      // larger keys in front of this one
-            rank -= (t.keys[j] > key && (t.kept[j] & 0x80u));
+        const uint32_t rank = s_wp[c * (kAggThreads / 32) + warp] + (uint32_t)__popc(bal & ((1u << lane) - 1u)) + (flag & 0x7Fu) - t.dec[i];
         const unsigned long long o = base + rank;
         if (o < p.cap) {
             const unsigned long long h = ((unsigned long long)b << key_bits) | (key & key_mask);
@@ -1339,6 +1340,7 @@ k_aggregate_cols(const AggParams2 p) {
     t.keys = s_tab;
     t.w32 = reinterpret_cast<uint32_t*>(s_tab + t.total);
     t.kept = reinterpret_cast<uint8_t*>(t.w32 + (size_t)p.table_u32 * t.total);
+    t.dec = t.kept + ((t.total + 3u) & ~3u);
     const uint32_t key_bits = 64 - p.bucket_bits;
     const uint32_t n_chunks = (t.total + kAggThreads - 1) / kAggThreads;     // <= kAggMaxChunks (slots <= 16384)
     __shared__ uint32_t s_wc[kAggMaxChunks * (kAggThreads / 32)];
