@@ -189,6 +189,10 @@ size_t table_smem(uint32_t slots, uint32_t W) {
 // The pan-genome of the context is estimated from the largest genome (1.9x its text; a bucket that turns out
 // too full is split into key sub-ranges by the kernel, so the estimate only costs time, never correctness).
 // Fewer buckets = longer runs per scatter tile = fewer store requests, the scatter's bound.
+constexpr uint32_t kUnitMaxBucketBits = 11;      // the unit expansion sorts tiles over at most 2^11 hash buckets
+bool units_wanted(const grmkm_ctx* c) {
+    return c->cfg.min_abundance <= 1 && !(c->cfg.flags & (GRMKM_FLAG_KMER_RECORDS | GRMKM_FLAG_SIMPLE_SCATTER));
+}
 uint32_t auto_bucket_bits(const grmkm_ctx* c, uint32_t G) {
     std::vector<uint64_t> row_bytes(std::max(G, 1u), 0);
     for (const Input& in : c->inputs) if (in.row < G) row_bytes[in.row] += in.len;
@@ -196,8 +200,15 @@ uint32_t auto_bucket_bits(const grmkm_ctx* c, uint32_t G) {
     const uint32_t slots = table_slots(c, (G + 63) / 64);
     const uint64_t u_est = max_row + max_row * 9 / 10 + 1024;
     const uint64_t per = std::max<uint64_t>(1, (uint64_t)slots * 60 / 100);
-    const uint32_t row_bits = std::max(1u, ceil_log2(G));
-    return std::max(row_bits, std::min(15u, std::max(6u, ceil_log2((u_est + per - 1) / per))));
+    uint32_t bits = std::min(15u, std::max(6u, ceil_log2((u_est + per - 1) / per)));
+    if (!units_wanted(c)) return std::max(std::max(1u, ceil_log2(G)), bits);     // k-mer records carry the row below the hash
+    // unit path: past 2^11 buckets every further bit doubles the aggregate's passes over the records (key sub-ranges),
+    // so a table that the estimate fills to 0.7 is still the better deal
+    if (bits > kUnitMaxBucketBits) {
+        const uint64_t per7 = std::max<uint64_t>(1, (uint64_t)slots * 70 / 100);
+        if (ceil_log2((u_est + per7 - 1) / per7) <= kUnitMaxBucketBits) bits = kUnitMaxBucketBits;
+    }
+    return bits;
 }
 
 // sort columns (ukeys/uwords, n items, stride ucap) by key into kmers/matrix
@@ -507,13 +518,12 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
     // 2^11 buckets: more distinct k-mers than 2^11 tables hold are handled as key sub-ranges of the buckets (virtual
     // buckets: one aggregate pass each over the bucket's records, which stay in L2), and beyond 2^14 by the table's own
     // overflow split -- instead of falling off to the per-record scatter
-    const bool units_wanted = c->cfg.min_abundance <= 1 && !(c->cfg.flags & (GRMKM_FLAG_KMER_RECORDS | GRMKM_FLAG_SIMPLE_SCATTER));
-    constexpr uint32_t kUnitMaxBucketBits = 11;
+    const bool units_ok = units_wanted(c);
     P.bucket_bits = c->cfg.bucket_bits ? c->cfg.bucket_bits : auto_bucket_bits(c, P.G);
-    if (!units_wanted) P.bucket_bits = std::max(P.bucket_bits, P.row_bits);
+    if (!units_ok) P.bucket_bits = std::max(P.bucket_bits, P.row_bits);
     if (P.bucket_bits > 15) return fail(c, GRMKM_E_UNSUPPORTED, "bucket_bits > 15");
     if (const char* sbv = getenv("GRMKM_SUB_BITS")) P.sub_bits = (uint32_t)std::min(3, std::max(0, atoi(sbv)));
-    if (units_wanted && P.bucket_bits > kUnitMaxBucketBits) {
+    if (units_ok && P.bucket_bits > kUnitMaxBucketBits) {
         P.sub_bits = std::max(P.sub_bits, std::min(3u, P.bucket_bits - kUnitMaxBucketBits));
         P.bucket_bits = kUnitMaxBucketBits;
     }
