@@ -251,6 +251,7 @@ k_units_scatter(const UnitScatterParams p) {
     // ... and the tile's file: its index, where the NEXT file starts in the stream, its genome row (three dependent
     // loads: fetched a tile ahead like the rest, they were 9 % of the kernel's stall samples on the critical path)
     uint32_t n_tf = 0, n_row = 0; unsigned long long n_next = ~0ULL;
+    uint32_t pf_tf = blockIdx.x < n_tiles ? p.tile_file[blockIdx.x] : 0u;      // the file index travels TWO tiles ahead
     auto fetch = [&](uint64_t tile, unsigned long long& c0, unsigned long long& c1, uint2& mk) {
         const uint64_t g0 = tile * kUsTileGroups;
         const uint64_t gi = g0 + tid;        // code word i holds group g0 + i - 1
@@ -258,9 +259,10 @@ k_units_scatter(const UnitScatterParams p) {
         c1 = (tile < n_tiles && tid < 3 && gi + kUsThreads - 1 < n_groups) ? p.codes[gi + kUsThreads - 1] : 0ULL;
         mk = (tile < n_tiles && gi < n_groups) ? p.masks[gi] : make_uint2(0u, 0u);
         if (tile < n_tiles) {
-            n_tf = p.tile_file[tile];
+            n_tf = pf_tf;
             n_next = n_tf + 1 < p.n_files ? p.file_stream_start[n_tf + 1] : ~0ULL;
             n_row = p.files[n_tf].row;
+            if (tile + gridDim.x < n_tiles) pf_tf = p.tile_file[tile + gridDim.x];
         }
     };
     unsigned long long nc0, nc1; uint2 nmk;
