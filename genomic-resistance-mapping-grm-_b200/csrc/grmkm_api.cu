@@ -552,7 +552,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         ENSURE(c, c->files, F * sizeof(FileDesc));
         ENSURE(c, c->hdr0, F * 8);
         ENSURE(c, c->fss, (F + 1) * 8);
-        ENSURE(c, c->tile_file, n_tiles * 4);
+        ENSURE(c, c->tile_file, n_tiles * sizeof(TileTicket));
         ENSURE(c, c->tile_pub, (3 * n_tiles + 1) * 8);    // published tile summaries / states (look-back) + the ticket counter
         ENSURE(c, c->codes, n_groups_max * 8);
         ENSURE(c, c->valid, n_groups_max * 4);
@@ -594,16 +594,17 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         CU_TRY(c, cudaMemsetAsync(c->tile_pub.p, 0, (3 * n_tiles + 1) * 8, st));
         if (timed && c->ev_ok) cudaEventRecord(c->ev[T_H2D], st);
         k_first_header<<<(F * 32 + 255) / 256, 256, 0, st>>>(d_files, F, (uint64_t*)c->hdr0.p);
-        k_tile_files<<<(uint32_t)((n_tiles + 255) / 256), 256, 0, st>>>(d_files, F, n_tiles, (uint32_t*)c->tile_file.p);
+        k_tile_tickets<<<(uint32_t)((n_tiles + 255) / 256), 256, 0, st>>>(d_files, F, (const uint64_t*)c->hdr0.p, (const uint64_t*)c->fss.p,
+                                                                           (const uint32_t*)c->tile_order.p, n_tiles, (TileTicket*)c->tile_file.p);
         L.n += 2;
         CU_TRY(c, cudaGetLastError());
         if (timed && c->ev_ok) cudaEventRecord(c->ev[T_PARSE], st);
         // single pass: summaries are published and resolved by look-back inside k_pack (grmkm_kernels.cuh)
         PackParams pp{};
         pp.files = d_files; pp.hdr0 = (const uint64_t*)c->hdr0.p; pp.n_tiles = n_tiles; pp.n_files = F;
-        pp.tile_file = (const uint32_t*)c->tile_file.p; pp.ticket = (uint32_t*)((unsigned long long*)c->tile_pub.p + 3 * n_tiles);
+        pp.tickets = (const TileTicket*)c->tile_file.p; pp.ticket = (uint32_t*)((unsigned long long*)c->tile_pub.p + 3 * n_tiles);
         pp.pub_a0 = (unsigned long long*)c->tile_pub.p; pp.pub_a1 = pp.pub_a0 + n_tiles; pp.pub_ps = pp.pub_a0 + 2 * n_tiles;
-        pp.file_stream_start = (const uint64_t*)c->fss.p; pp.order = (const uint32_t*)c->tile_order.p; pp.stream_len = bt.stream;
+        pp.stream_len = bt.stream;
         pp.codes = (unsigned long long*)c->codes.p; pp.valid = (uint32_t*)c->valid.p; pp.scalars = d_scalars;
         if (c->cfg.input_kind == GRMKM_FASTA) k_pack<0><<<(uint32_t)n_tiles, kParseThreads, 0, st>>>(pp);
         else k_pack<1><<<(uint32_t)n_tiles, kParseThreads, 0, st>>>(pp);

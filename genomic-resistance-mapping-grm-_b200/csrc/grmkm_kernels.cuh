@@ -1,6 +1,6 @@
 // grmkm_kernels.cuh -- the sm_100a kernels of the k-mer matrix path.
 //
-//   parse   : k_first_header, k_tile_files, k_pack (one pass: tile summaries resolved by decoupled look-back)
+//   parse   : k_first_header, k_tile_tickets, k_pack (one pass: tile summaries resolved by decoupled look-back)
 //             FASTA/FASTQ text -> dense 2-bit base stream + validity mask   (multidsk's bank reader)
 //   extract : k_extract<COUNT|SCATTER>
 //             canonical k-mers -> hash buckets                              (multidsk's partitioning)
@@ -40,15 +40,6 @@ __global__ void k_first_header(const FileDesc* __restrict__ files, uint32_t n_fi
     if (lane == 0) hdr0[f] = found;
 }
 
-__device__ __forceinline__ uint32_t find_file(const FileDesc* __restrict__ files, uint32_t n_files, uint64_t tile) {
-    uint32_t lo = 0, hi = n_files - 1;
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi + 1) >> 1;
-        if (files[mid].tile_begin <= tile) lo = mid; else hi = mid - 1;
-    }
-    return lo;
-}
-
 struct TileCtx {
     FileDesc fd;
     uint64_t hdr0;
@@ -56,17 +47,6 @@ struct TileCtx {
     uint32_t f;
     bool first_tile;
 };
-
-__device__ __forceinline__ TileCtx tile_context(const FileDesc* __restrict__ files, const uint64_t* __restrict__ hdr0,
-                                                uint64_t tile, uint32_t f) {
-    TileCtx t;
-    t.f = f;
-    t.fd = files[f];
-    t.hdr0 = hdr0[f];
-    t.first_tile = (tile == t.fd.tile_begin);
-    t.off = (tile - t.fd.tile_begin) * (uint64_t)kTileBytes + (uint64_t)threadIdx.x * (16 * kChunksPerThread);
-    return t;
-}
 
 // the thread's four chunks and the byte before each of them
 struct ThreadText {
@@ -85,11 +65,30 @@ __device__ __forceinline__ ThreadText load_thread_text(const TileCtx& t) {
     return x;
 }
 
-// file of every parse tile (one thread per tile), so that no block has to binary-search on its own
-__global__ void k_tile_files(const FileDesc* __restrict__ files, uint32_t n_files, uint64_t n_tiles,
-                             uint32_t* __restrict__ tile_file) {
-    const uint64_t tile = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tile < n_tiles) tile_file[tile] = find_file(files, n_files, tile);
+// Everything a CTA needs to start on ticket t, in one 64-byte record: ticket -> tile (order) -> file -> descriptor,
+// first header and stream start used to be four dependent loads at the head of every CTA.
+struct TileTicket {
+    FileDesc fd;
+    uint64_t hdr0;
+    uint64_t stream_start;      // where the file's entries start in the packed stream
+    uint32_t tile, f;
+    uint64_t pad;
+};
+static_assert(sizeof(TileTicket) == 64, "one ticket = four 16-byte loads");
+__global__ void k_tile_tickets(const FileDesc* __restrict__ files, uint32_t n_files, const uint64_t* __restrict__ hdr0,
+                               const uint64_t* __restrict__ fss, const uint32_t* __restrict__ order, uint64_t n_tiles,
+                               TileTicket* __restrict__ out) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    TileTicket k;
+    k.tile = order[t];
+    uint32_t lo = 0, hi = n_files - 1;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (files[mid].tile_begin <= k.tile) lo = mid; else hi = mid - 1;
+    }
+    k.f = lo; k.fd = files[lo]; k.hdr0 = hdr0[lo]; k.stream_start = fss[lo]; k.pad = 0;
+    out[t] = k;
 }
 
 // ---- single-pass parse: decoupled look-back over the tile summaries --------------------------------------
@@ -217,14 +216,12 @@ struct PackParams {
     const uint64_t* hdr0;
     uint64_t n_tiles;
     uint32_t n_files;
-    const uint32_t* tile_file;
-    const uint32_t* order;              // [n_tiles] ticket -> tile, round-robin over the files
+    const TileTicket* tickets;          // [n_tiles] ticket -> tile and its file, tickets dealt round-robin over the files
     uint64_t stream_len;                // padded stream length of the batch (-> scalars[S_STREAM_LEN])
     uint32_t* ticket;                   // zeroed before the launch
     unsigned long long* pub_a0;         // [n_tiles] x 3, zeroed before the launch (see tile_lookback)
     unsigned long long* pub_a1;
     unsigned long long* pub_ps;
-    const uint64_t* file_stream_start;  // [n_files + 1], fixed by the host
     unsigned long long* codes;
     uint32_t* valid;
     uint64_t* scalars;
@@ -237,22 +234,34 @@ k_pack(const PackParams p) {
     __shared__ Sum s_w[kParseThreads / 32];
     __shared__ uint32_t s_codes[kGroups * 2 + 4];
     __shared__ uint32_t s_valid[kGroups + 2];
-    __shared__ uint32_t s_nrec, s_ticket, s_st;
+    __shared__ uint32_t s_nrec, s_st;
     __shared__ uint64_t s_pos;
+    __shared__ uint4 s_tk[4];                                           // this CTA's TileTicket
     if (threadIdx.x == 0) {
         const uint32_t ticket = atomicAdd(p.ticket, 1u);
-        s_ticket = ticket < p.n_tiles ? p.order[ticket] : 0xFFFFFFFFu;
         s_nrec = 0;
         if (ticket == 0) p.scalars[S_STREAM_LEN] = p.stream_len;
+        if (ticket < p.n_tiles) {
+            const uint4* src = reinterpret_cast<const uint4*>(p.tickets + ticket);
+            const uint4 a = src[0], b = src[1], c = src[2], d = src[3];
+            s_tk[0] = a; s_tk[1] = b; s_tk[2] = c; s_tk[3] = d;
+        } else {
+            s_tk[3] = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);                 // no tile left
+        }
     }
     for (int i = threadIdx.x; i < kGroups * 2 + 4; i += blockDim.x) s_codes[i] = 0;
     for (int i = threadIdx.x; i < kGroups + 2; i += blockDim.x) s_valid[i] = 0;
     __syncthreads();
-    const uint64_t tile = s_ticket;
-    if (tile >= p.n_tiles) return;
+    const TileTicket& tk = *reinterpret_cast<const TileTicket*>(s_tk);
+    const uint64_t tile = tk.tile;
+    if (tk.tile == 0xFFFFFFFFu) return;
     unsigned long long* __restrict__ codes = p.codes;
     uint32_t* __restrict__ valid = p.valid;
-    const TileCtx t = tile_context(p.files, p.hdr0, tile, p.tile_file[tile]);
+    TileCtx t;
+    t.f = tk.f; t.fd = tk.fd; t.hdr0 = tk.hdr0;
+    t.first_tile = (tile == t.fd.tile_begin);
+    t.off = (tile - t.fd.tile_begin) * (uint64_t)kTileBytes + (uint64_t)threadIdx.x * (16 * kChunksPerThread);
+    const uint64_t file_stream_start = tk.stream_start;
     const ThreadText x = load_thread_text(t);
     // publish the tile's summary, resolve its incoming state and position (warp 0), publish those
     auto publish = [&](const Sum& total) {
@@ -264,7 +273,7 @@ k_pack(const PackParams p) {
     auto resolve = [&](uint32_t& st_in, uint64_t& tpos) {
         if (threadIdx.x < 32) {
             uint32_t st; uint64_t pos;
-            tile_lookback<KIND>(tile, t.fd.tile_begin, p.file_stream_start[t.f], p.pub_a0, p.pub_a1, p.pub_ps, st, pos);
+            tile_lookback<KIND>(tile, t.fd.tile_begin, file_stream_start, p.pub_a0, p.pub_a1, p.pub_ps, st, pos);
             if (threadIdx.x == 0) {
                 st_relaxed_u64(p.pub_ps + tile, kPubValid | ((unsigned long long)st << 61) | pos);
                 s_st = st; s_pos = pos;
