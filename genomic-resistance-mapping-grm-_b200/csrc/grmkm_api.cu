@@ -888,7 +888,9 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
                 uint64_t est = std::max<uint64_t>(c->wide_hint, std::min<uint64_t>(P.in_bytes, max_row * 19 / 10 + P.in_bytes / 20) * 13 / 10 * groups);
                 if (const char* wc = getenv("GRMKM_WIDE_EST")) est = (uint64_t)atoll(wc);
                 uint64_t rcap = (uint64_t)((double)est / B * 1.4) + 1024;
-                {   // never more than a quarter of what is free (a region that turns out too small only costs the count pass)
+                if (((uint64_t)B * rcap + kStTile) * RS * 8 > c->wide.cap) {
+                    // the buffer has to grow: never beyond a quarter of what is free (a region that turns out too small
+                    // only costs the count pass).  Not asked in the steady state -- cudaMemGetInfo is slow.
                     size_t free_b = 0, total_b = 0;
                     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
                         const uint64_t have = c->wide.cap + free_b / 4;
