@@ -51,6 +51,8 @@ struct grmkm_ctx {
     uint32_t n_genomes_decl = 0;
     int sm_count = 148;
     size_t smem_optin = 0;
+    void* h_tab = nullptr;         // page-locked arena for the per-batch host tables (files, stream starts, ticket order)
+    size_t h_tab_cap = 0, h_tab_used = 0;
     uint64_t wide_hint = 0;        // wide records of the previous build (sizes the expansion's bucket regions)
 
     // device buffers (grow-only, reused across builds)
@@ -387,6 +389,7 @@ void grmkm_destroy(grmkm_ctx* c) {
         for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->ev_copied[i]); cudaEventDestroy(c->ev_free[i]); }
         cudaStreamDestroy(c->copy_stream);
     }
+    if (c->h_tab) cudaFreeHost(c->h_tab);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -539,9 +542,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
     if (c->ev_ok) cudaEventRecord(c->ev[T_START], st);
     CU_TRY(c, cudaMemsetAsync(c->scalars.p, 0, S_COUNT * 8, st));
     uint64_t h2d = 0;
-    std::vector<std::vector<FileDesc>> fds_keep;      // host tables stay alive until the final synchronize
-    std::deque<std::vector<uint64_t>> u64_keep;
-    std::deque<std::vector<uint32_t>> u32_keep;
+
 
     // parse + pack of one batch: leaves codes / valid / fss / S_STREAM_LEN of the batch
     auto front = [&](const Batch& bt, const uint8_t* staged_base, bool timed) -> int {
@@ -557,12 +558,19 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         ENSURE(c, c->codes, n_groups_max * 8);
         ENSURE(c, c->valid, n_groups_max * 4);
         ENSURE(c, c->tile_order, n_tiles * 4);
-        fds_keep.emplace_back(F);
-        std::vector<FileDesc>& fds = fds_keep.back();
-        u64_keep.emplace_back(F + 1);
-        std::vector<uint64_t>& fss = u64_keep.back();                 // where every file's entries start in the stream
-        u32_keep.emplace_back((size_t)n_tiles);
-        std::vector<uint32_t>& order = u32_keep.back();               // ticket -> tile: round-robin over the files
+        // the memsets go first: the device clears while the host builds this batch's tables
+        CU_TRY(c, cudaMemsetAsync(c->codes.p, 0, n_groups_max * 8, st));
+        CU_TRY(c, cudaMemsetAsync(c->valid.p, 0, n_groups_max * 4, st));
+        CU_TRY(c, cudaMemsetAsync(c->tile_pub.p, 0, (3 * n_tiles + 1) * 8, st));
+        // host tables in page-locked memory (asynchronous copies without a staging hop); they stay untouched until the
+        // build's final synchronize
+        const size_t tab_bytes = (F * sizeof(FileDesc) + (F + 1) * 8 + (size_t)n_tiles * 4 + 63) & ~size_t(63);
+        if (c->h_tab_used + tab_bytes > c->h_tab_cap) return fail(c, GRMKM_E_NOMEM, "host table arena too small");
+        uint8_t* tab = (uint8_t*)c->h_tab + c->h_tab_used;
+        c->h_tab_used += tab_bytes;
+        FileDesc* fds = (FileDesc*)tab;
+        uint64_t* fss = (uint64_t*)(tab + F * sizeof(FileDesc));      // where every file's entries start in the stream
+        uint32_t* order = (uint32_t*)(fss + F + 1);                   // ticket -> tile: round-robin over the files
         uint64_t tiles = 0, soff = 0, spos = 0;
         std::vector<std::pair<uint64_t, uint32_t>> by_tiles(F);       // (tile count, file), most tiles first
         for (uint32_t i = 0; i < F; ++i) {
@@ -586,12 +594,9 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
             }
         }
         d_files = (const FileDesc*)c->files.p;
-        CU_TRY(c, cudaMemcpyAsync(c->files.p, fds.data(), F * sizeof(FileDesc), cudaMemcpyHostToDevice, st));
-        CU_TRY(c, cudaMemcpyAsync(c->fss.p, fss.data(), (F + 1) * 8, cudaMemcpyHostToDevice, st));
-        CU_TRY(c, cudaMemcpyAsync(c->tile_order.p, order.data(), n_tiles * 4, cudaMemcpyHostToDevice, st));
-        CU_TRY(c, cudaMemsetAsync(c->codes.p, 0, n_groups_max * 8, st));
-        CU_TRY(c, cudaMemsetAsync(c->valid.p, 0, n_groups_max * 4, st));
-        CU_TRY(c, cudaMemsetAsync(c->tile_pub.p, 0, (3 * n_tiles + 1) * 8, st));
+        CU_TRY(c, cudaMemcpyAsync(c->files.p, fds, F * sizeof(FileDesc), cudaMemcpyHostToDevice, st));
+        CU_TRY(c, cudaMemcpyAsync(c->fss.p, fss, (F + 1) * 8, cudaMemcpyHostToDevice, st));
+        CU_TRY(c, cudaMemcpyAsync(c->tile_order.p, order, n_tiles * 4, cudaMemcpyHostToDevice, st));
         if (timed && c->ev_ok) cudaEventRecord(c->ev[T_H2D], st);
         k_first_header<<<(F * 32 + 255) / 256, 256, 0, st>>>(d_files, F, (uint64_t*)c->hdr0.p);
         k_tile_tickets<<<(uint32_t)((n_tiles + 255) / 256), 256, 0, st>>>(d_files, F, (const uint64_t*)c->hdr0.p, (const uint64_t*)c->fss.p,
@@ -648,6 +653,19 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         const bool regions = (pass == 0);
         const std::vector<Batch> batches = make_batches(regions && any_host);
         const bool pipelined = batches.size() > 1;
+        {   // host table arena for all batches of this pass (nothing of an earlier pass / build is in flight: both end synchronised)
+            size_t need = 0;
+            for (const Batch& bt : batches)
+                need += (((size_t)(bt.f1 - bt.f0) * sizeof(FileDesc) + (bt.f1 - bt.f0 + 1) * 8 + (size_t)bt.tiles * 4 + 63) & ~size_t(63));
+            if (need > c->h_tab_cap) {
+                CU_TRY(c, cudaStreamSynchronize(st));
+                if (c->h_tab) cudaFreeHost(c->h_tab);
+                c->h_tab = nullptr; c->h_tab_cap = 0;
+                CU_TRY(c, cudaHostAlloc(&c->h_tab, need + need / 4, cudaHostAllocDefault));
+                c->h_tab_cap = need + need / 4;
+            }
+            c->h_tab_used = 0;
+        }
         uint64_t cap = 0;
         if (use_units) {
             if (regions) {

@@ -179,10 +179,11 @@ class DistributedBuilder:
         count only sizes the shared-memory tables (a bucket that does not fit is split), never the result."""
         if self.world == 1:
             self.builder.build()
-            self.launches = self.builder.stats["n_launches"]
-            self._n_kmers = self.builder.dims[0]
-            self.stage_times = dict(self.builder.times)
-            self.local_stats = self.builder.stats
+            st = self.builder.stats
+            self.launches = st["n_launches"]
+            self._n_kmers = st["n_kmers"]
+            self.stage_times = self.builder.times
+            self.local_stats = st
             return self
         import torch
         import torch.distributed as dist
