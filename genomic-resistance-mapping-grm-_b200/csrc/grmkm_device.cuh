@@ -236,7 +236,7 @@ __device__ __forceinline__ Sum fa_to_sum(uint32_t a) {
     Sum r; r.e = t ? (t - 1) * 0x55u : 0xE4u; r.c0 = c_rest; r.c1 = c_rest + c_head; r.c2 = 0; r.c3 = 0;
     return r;
 }
-// ordered scan of compact FASTA summaries over a 256-thread block; s_w holds 8 words
+// ordered scan of compact FASTA summaries over a block of up to 32 warps; s_w holds 2 x warps + 1 words
 __device__ __forceinline__ void block_scan_fa(uint32_t mine, uint32_t& excl, uint32_t& total, uint32_t* s_w) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     uint32_t inc = mine;
@@ -249,13 +249,23 @@ __device__ __forceinline__ void block_scan_fa(uint32_t mine, uint32_t& excl, uin
     if (lane == 0) prev = 0;
     if (lane == 31) s_w[warp] = inc;
     __syncthreads();
-    uint32_t wpre = 0, tot = 0;
-    for (int w = 0; w < nwarp; ++w) {
-        if (w == warp) wpre = tot;
-        tot = fa_combine(tot, s_w[w]);
+    // warp totals -> exclusive warp prefixes + block total, by the first warp (a serial fold in every thread was a
+    // tenth of k_pack's instructions); s_w[nwarp + w] = prefix of warp w, s_w[2 * nwarp] = total
+    if (warp == 0) {
+        uint32_t v = lane < nwarp ? s_w[lane] : 0u, wi = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi = fa_combine(o, wi);
+        }
+        uint32_t wp = __shfl_up_sync(0xffffffffu, wi, 1);
+        if (lane == 0) wp = 0;
+        if (lane < nwarp) s_w[nwarp + lane] = wp;
+        if (lane == nwarp - 1) s_w[2 * nwarp] = wi;
     }
-    excl = fa_combine(wpre, prev);
-    total = tot;
+    __syncthreads();
+    excl = fa_combine(s_w[nwarp + warp], prev);
+    total = s_w[2 * nwarp];
     __syncthreads();
 }
 

@@ -304,8 +304,11 @@ k_pack(const PackParams p) {
             acc.init(); nrec = 0;
 #pragma unroll
             for (int c = 0; c < kChunksPerThread; ++c) {
-                if (in_seq) acc.append(part[c].hc, part[c].hv_rv & 0xFFFFu, part[c].hn());
-                acc.append(part[c].rc, part[c].hv_rv >> 16, part[c].rn());
+                // head (only inside a sequence line) and rest of the chunk as ONE run of at most 16 entries
+                const uint32_t hn = in_seq ? part[c].hn() : 0u;
+                const uint32_t cc = (in_seq ? part[c].hc : 0u) | (hn < 16u ? part[c].rc << (2 * hn) : 0u);      // hn = 16: no rest
+                const uint32_t vv = (in_seq ? part[c].hv_rv & 0xFFFFu : 0u) | ((part[c].hv_rv >> 16) << hn);
+                acc.append(cc, vv, hn + part[c].rn());
                 nrec += part[c].nrec();
                 if (part[c].t()) in_seq = (part[c].t() == 2);
             }
