@@ -53,7 +53,8 @@ struct grmkm_ctx {
     size_t smem_optin = 0;
     void* h_tab = nullptr;         // page-locked arena for the per-batch host tables (files, stream starts, ticket order)
     size_t h_tab_cap = 0, h_tab_used = 0;
-    uint64_t wide_hint = 0;        // wide records of the previous build (sizes the expansion's bucket regions)
+    uint64_t wide_hint = 0;
+    uint64_t ucap_hint = 0;        // columns of the previous build + headroom (sizes the aggregate's output)        // wide records of the previous build (sizes the expansion's bucket regions)
 
     // device buffers (grow-only, reused across builds)
     DevBuf in, files, hdr0, tile_file, tile_pub, tile_order, fss, codes, valid, hist,
@@ -911,8 +912,9 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
                     // only costs the count pass).  Not asked in the steady state -- cudaMemGetInfo is slow.
                     size_t free_b = 0, total_b = 0;
                     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-                        const uint64_t have = c->wide.cap + free_b / 4;
-                        rcap = std::min<uint64_t>(rcap, have / ((uint64_t)B * RS * 8));
+                        // (what it has already counts as the budget when that is more: no re-allocation every build)
+                        const uint64_t have = std::max<uint64_t>(c->wide.cap, free_b / 4);
+                        rcap = std::min<uint64_t>(rcap, (have / (RS * 8) - kStTile) / B);
                     }
                 }
                 rcap = std::max<uint64_t>(64, rcap & ~15ULL);
@@ -982,7 +984,16 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         if (!use_units && c->ev_ok) for (int e : {T_ABUND, T_DEDUPE, T_EXPAND}) cudaEventRecord(c->ev[e], st);
 
         // ---- aggregate (dsk2kover): retry with a larger output if the first guess was too small
-        ucap = std::min<uint64_t>(P.max_stream, std::max<uint64_t>(1 << 16, P.max_stream / 4));
+        // columns: three pan-genome estimates (1.9 x the largest genome each) + 1 % of all input, at most a quarter of the
+        // windows (N / 4 alone asked for 163 GB of word rows at 1000 genomes); a guess that is too small is retried with
+        // the exact number
+        {
+            uint64_t max_row = 0;
+            std::vector<uint64_t> rb(std::max(P.G, 1u), 0);
+            for (const Input& in : c->inputs) if (in.row < P.G) { rb[in.row] += in.len; max_row = std::max(max_row, rb[in.row]); }
+            const uint64_t guess = 3 * (max_row * 19 / 10) + P.in_bytes / 100;
+            ucap = std::min<uint64_t>(P.max_stream, std::max<uint64_t>(1 << 16, std::min<uint64_t>(P.max_stream / 4, std::max<uint64_t>(guess, c->ucap_hint))));
+        }
         ucap = std::min<uint64_t>(ucap, 0xFFFFFFFFULL);
         ENSURE(c, c->bbase, (size_t)VB * 8);
         ENSURE(c, c->bcounts, (size_t)VB * 8);
@@ -1034,6 +1045,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         }
         }   // round
         if (use_units && !unit_overflow && !(regions && sc[S_OVERFLOW])) c->wide_hint = sc[S_N_WIDE];
+        if (!(regions && sc[S_OVERFLOW])) c->ucap_hint = sc[S_U_NEEDED] + sc[S_U_NEEDED] / 8;
         if (!(regions && (sc[S_OVERFLOW] || unit_overflow))) break;
         c->stats.n_region_overflows++;
     }
