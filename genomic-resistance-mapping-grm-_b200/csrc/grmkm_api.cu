@@ -54,12 +54,13 @@ struct grmkm_ctx {
     void* h_tab = nullptr;         // page-locked arena for the per-batch host tables (files, stream starts, ticket order)
     size_t h_tab_cap = 0, h_tab_used = 0;
     uint64_t wide_hint = 0;
+    uint64_t wide_capped_need = 0;   // an expansion-buffer request of up to this many bytes was capped by free memory
     uint64_t ucap_hint = 0;        // columns of the previous build + headroom (sizes the aggregate's output)        // wide records of the previous build (sizes the expansion's bucket regions)
 
     // device buffers (grow-only, reused across builds)
     DevBuf in, files, hdr0, tile_file, tile_pub, tile_order, fss, codes, valid, hist,
         offsets, offsets2, bcounts, records, records2, ukeys, uwords, skeys, sidx_a, sidx_b, shist, kmers, matrix,
-        scalars, fmt, synth, owner_start, refs, spart, stile_file, bbase, masks, units, ucur, ubeg, wu, wide;
+        scalars, fmt, synth, owner_start, refs, spart, stile_file, bbase, apub, masks, units, ucur, ubeg, wu, wide;
     size_t device_bytes = 0;
 
     cudaEvent_t ev[T_N]{};
@@ -381,7 +382,7 @@ void grmkm_destroy(grmkm_ctx* c) {
     DevBuf* all[] = {&c->in, &c->files, &c->hdr0, &c->tile_file, &c->tile_pub, &c->tile_order,
                      &c->fss, &c->codes, &c->valid, &c->hist, &c->offsets, &c->offsets2,
                      &c->bcounts, &c->records, &c->records2, &c->ukeys, &c->uwords, &c->skeys, &c->sidx_a, &c->sidx_b,
-                     &c->shist, &c->kmers, &c->matrix, &c->scalars, &c->fmt, &c->synth, &c->owner_start, &c->refs, &c->spart, &c->stile_file, &c->bbase,
+                     &c->shist, &c->kmers, &c->matrix, &c->scalars, &c->fmt, &c->synth, &c->owner_start, &c->refs, &c->spart, &c->stile_file, &c->bbase, &c->apub,
                      &c->masks, &c->units, &c->ucur, &c->ubeg, &c->wu, &c->wide};
     for (DevBuf* b : all) release(c, *b);
     if (c->ev_ok) for (int i = 0; i < T_N; ++i) cudaEventDestroy(c->ev[i]);
@@ -648,6 +649,8 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
     const uint32_t agrid = std::min<uint32_t>(B, (uint32_t)c->sm_count * kAggCtasPerSm);
     const uint32_t VB = B << P.sub_bits;            // virtual buckets of the column aggregate
     const uint32_t vgrid = std::min<uint32_t>(VB, (uint32_t)c->sm_count * kAggCtasPerSm);
+    // final build in hash order: the aggregate writes the columns at their final place (no gather pass)
+    const bool ordered = mode == 0 && !(c->cfg.flags & GRMKM_FLAG_KMER_ORDER) && !getenv("GRMKM_UNORDERED");
     uint64_t sc[S_COUNT];
     uint64_t ucap = 0;
     for (int pass = try_regions ? 0 : 1; pass < 2; ++pass) {
@@ -906,14 +909,22 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
                 const uint64_t groups = (P.W + WB - 1) / WB;
                 uint64_t est = std::max<uint64_t>(c->wide_hint, std::min<uint64_t>(P.in_bytes, max_row * 19 / 10 + P.in_bytes / 20) * 13 / 10 * groups);
                 if (const char* wc = getenv("GRMKM_WIDE_EST")) est = (uint64_t)atoll(wc);
-                uint64_t rcap = (uint64_t)((double)est / B * 1.4) + 1024;
-                if (((uint64_t)B * rcap + kStTile) * RS * 8 > c->wide.cap) {
+                // (rounded BEFORE the capacity test: tested unrounded, the size asked for was always a little more than the
+                // size allocated, and cudaMemGetInfo -- a driver round trip that takes anything from 0.1 to 90 ms while the
+                // GPU waits for the next launch -- ran in every build)
+                uint64_t rcap = std::max<uint64_t>(64, ((uint64_t)((double)est / B * 1.4) + 1024) & ~15ULL);
+                const uint64_t wide_need = ((uint64_t)B * rcap + kStTile) * RS * 8;
+                if (wide_need > c->wide.cap) {
                     // the buffer has to grow: never beyond a quarter of what is free (a region that turns out too small
                     // only costs the count pass).  Not asked in the steady state -- cudaMemGetInfo is slow.
                     size_t free_b = 0, total_b = 0;
-                    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+                    if (c->wide.cap && wide_need <= c->wide_capped_need) {
+                        // a request this large was already cut down to what the context holds now: keep the buffer
+                        rcap = std::min<uint64_t>(rcap, (c->wide.cap / (RS * 8) - kStTile) / B);
+                    } else if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
                         // (what it has already counts as the budget when that is more: no re-allocation every build)
                         const uint64_t have = std::max<uint64_t>(c->wide.cap, free_b / 4);
+                        if (wide_need > have) c->wide_capped_need = wide_need;
                         rcap = std::min<uint64_t>(rcap, (have / (RS * 8) - kStTile) / B);
                     }
                 }
@@ -997,9 +1008,18 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         ucap = std::min<uint64_t>(ucap, 0xFFFFFFFFULL);
         ENSURE(c, c->bbase, (size_t)VB * 8);
         ENSURE(c, c->bcounts, (size_t)VB * 8);
+        if (ordered) ENSURE(c, c->apub, (size_t)(VB + 1) * 8);
         for (int attempt = 0; attempt < 2; ++attempt) {
-            ENSURE(c, c->ukeys, ucap * 8);
-            ENSURE(c, c->uwords, (size_t)ucap * P.W * 8);
+            if (ordered) {
+                // the columns land at their final place: k-mers and word row 0 in the result arrays, rows >= 1 at stride ucap
+                ENSURE(c, c->kmers, ucap * 8);
+                ENSURE(c, c->matrix, (size_t)ucap * P.W * 8);
+                if (P.W > 1) ENSURE(c, c->uwords, (size_t)ucap * P.W * 8);
+                CU_TRY(c, cudaMemsetAsync(c->apub.p, 0, (size_t)(VB + 1) * 8, st));
+            } else {
+                ENSURE(c, c->ukeys, ucap * 8);
+                ENSURE(c, c->uwords, (size_t)ucap * P.W * 8);
+            }
             AggParams2 ap{};
             ap.records = agg_records; ap.begin = agg_begin; ap.end = agg_end; ap.bucket_bits = P.bucket_bits;
             ap.row_bits = use_units ? wbits : P.row_bits; ap.n_words = P.W; ap.slots = P.slots;
@@ -1009,6 +1029,11 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
             ap.cap = ucap; ap.scalars = (unsigned long long*)d_scalars;
             ap.bucket_base = (unsigned long long*)c->bbase.p; ap.bucket_count = (unsigned long long*)c->bcounts.p;
             ap.b_begin = 0; ap.b_end = B;
+            if (ordered) {
+                ap.ordered = 1;
+                ap.out_keys = (unsigned long long*)c->kmers.p; ap.out_row0 = (unsigned long long*)c->matrix.p;
+                ap.pub = (unsigned long long*)c->apub.p; ap.ticket = (unsigned int*)((unsigned long long*)c->apub.p + VB);
+            }
             if (use_units && mode == 0) {
                 CU_TRY(c, cudaFuncSetAttribute(k_aggregate_cols<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.agg_smem));
                 k_aggregate_cols<4><<<vgrid, kAggThreads, P.agg_smem, st>>>(ap);
@@ -1058,6 +1083,11 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
     if (mode == 0 && (c->cfg.flags & GRMKM_FLAG_KMER_ORDER)) {
         int r = sort_and_gather(c, U, P.W, ucap, 2 * c->cfg.k, false, L);
         if (r) return r;
+    } else if (ordered) {
+        // rows >= 1 move from stride ucap to the result's stride U (row 0 and the k-mers are already in place)
+        if (U && P.W > 1)
+            CU_TRY(c, cudaMemcpy2DAsync((unsigned long long*)c->matrix.p + U, U * 8, (const unsigned long long*)c->uwords.p + ucap, ucap * 8,
+                                        U * 8, P.W - 1, cudaMemcpyDeviceToDevice, st));
     } else {
         ENSURE(c, c->offsets2, (size_t)(VB + 1) * 8);
         ENSURE(c, c->kmers, U * 8);

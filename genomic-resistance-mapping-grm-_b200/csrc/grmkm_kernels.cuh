@@ -1070,6 +1070,14 @@ struct AggParams2 {
     unsigned long long* bucket_base;     // [B] where the bucket's chunk starts in out_*
     unsigned long long* bucket_count;    // [B] columns the bucket emitted
     uint32_t b_begin, b_end;             // bucket_base / bucket_count are indexed by (virtual bucket) - (b_begin << sub_bits)
+    // ordered emission (final build in hash order): the virtual buckets are dealt by ticket, every bucket publishes its
+    // column count and learns its offset by look-back over its predecessors, so the columns land at their final place:
+    // out_keys is the result's k-mer array, word row 0 goes to out_row0 (row 0 of the result matrix, whose stride is
+    // only known at the end), rows >= 1 to out_words at stride cap
+    uint32_t ordered;
+    unsigned long long* out_row0;        // nullptr: row 0 goes to out_words like the others
+    unsigned long long* pub;             // [virtual buckets] bit 63: inclusive prefix, bit 62: own count; zeroed before the launch
+    unsigned int* ticket;                // zeroed before the launch
     // MODE 3: partial columns [hash, words...] of n_src sources, each list ascending by hash; the entries of
     // bucket b in source s are bounds[s * (b_end - b_begin + 1) + (b - b_begin)] .. [.. + 1]
     const unsigned long long* parts;
@@ -1331,11 +1339,43 @@ __device__ __forceinline__ void agg_emit(const AggParams2& p, const AggTable& t,
                     for (uint32_t w = 0; w < nw; ++w) p.out_words[(unsigned long long)(wo + w) * p.cap + o] = e ? ent[1 + w] : 0ULL;
                 }
             } else {
-                for (uint32_t w = 0; w < p.n_words; ++w)
-                    p.out_words[w * p.cap + o] = ((unsigned long long)t.w32[(2 * w + 1) * t.total + i] << 32) | t.w32[2 * w * t.total + i];
+                for (uint32_t w = 0; w < p.n_words; ++w) {
+                    unsigned long long* const row = (w == 0 && p.out_row0) ? p.out_row0 : p.out_words + w * p.cap;
+                    row[o] = ((unsigned long long)t.w32[(2 * w + 1) * t.total + i] << 32) | t.w32[2 * w * t.total + i];
+                }
             }
         }
     }
+}
+
+// Ordered emission: where does (virtual) bucket idx start?  Called by the whole first warp.  The bucket publishes its own
+// count, sums its predecessors' words 32 at a time until one of them carries an inclusive prefix, then publishes its
+// own inclusive prefix.  The words are self-validating (flag bits + value in one 64-bit store), so relaxed accesses do;
+// buckets are dealt by ticket, so every predecessor belongs to a CTA that is already running (no deadlock whatever
+// the residency).
+constexpr unsigned long long kAggPubInc = 1ULL << 63, kAggPubOwn = 1ULL << 62, kAggPubMask = (1ULL << 62) - 1;
+__device__ __forceinline__ unsigned long long agg_reserve_ordered(const AggParams2& p, uint32_t idx, unsigned long long total) {
+    const uint32_t lane = threadIdx.x & 31u;
+    if (lane == 0) {
+        atomicAdd(&p.scalars[S_U_NEEDED], total);
+        st_relaxed_u64(p.pub + idx, (idx == 0 ? kAggPubInc : kAggPubOwn) | total);
+    }
+    if (idx == 0) return 0;
+    unsigned long long excl = 0;
+    for (long long j = (long long)idx - 1;; j -= 32) {
+        const long long q = j - (long long)lane;
+        unsigned long long v;
+        do { v = q >= 0 ? ld_relaxed_u64(p.pub + q) : kAggPubInc; } while (!__all_sync(0xffffffffu, (v >> 62) != 0));
+        const uint32_t inc = __ballot_sync(0xffffffffu, (v & kAggPubInc) != 0);
+        unsigned long long val = v & kAggPubMask;
+        if (inc && lane > (uint32_t)(__ffs(inc) - 1)) val = 0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+        excl += val;
+        if (inc) break;
+    }
+    if (lane == 0) st_relaxed_u64(p.pub + idx, kAggPubInc | (excl + total));
+    return excl;
 }
 
 template <int MODE>
@@ -1362,7 +1402,16 @@ k_aggregate_cols(const AggParams2 p) {
     // sub-ranges have adjacent block indices, run at the same time and share the bucket's records through L2.
     const uint32_t sb = p.sub_bits;
     const uint32_t vb_base = p.b_begin << sb;
-    for (uint32_t vb = vb_base + blockIdx.x; vb < (p.b_end << sb); vb += gridDim.x) {
+    __shared__ uint32_t s_vb;
+    for (uint32_t it = 0;; ++it) {
+        uint32_t vb = vb_base + blockIdx.x + it * gridDim.x;
+        if (p.ordered) {
+            __syncthreads();
+            if (threadIdx.x == 0) s_vb = atomicAdd(p.ticket, 1u);
+            __syncthreads();
+            vb = vb_base + s_vb;
+        }
+        if (vb >= (p.b_end << sb)) break;
         const uint32_t b = vb >> sb, sub = vb & ((1u << sb) - 1u);
         uint32_t n = 0;
         const unsigned long long* recs = nullptr;
@@ -1375,7 +1424,12 @@ k_aggregate_cols(const AggParams2 p) {
             n = rbeg < rend ? (uint32_t)(rend - rbeg) : 0u;
             recs = p.records + (MODE >= 4 ? (unsigned long long)p.wide_stride * rbeg : rbeg);
         }
-        if (n == 0) { if (threadIdx.x == 0) { p.bucket_base[vb - vb_base] = 0; p.bucket_count[vb - vb_base] = 0; } continue; }
+        if (n == 0) {
+            if (threadIdx.x == 0) { p.bucket_base[vb - vb_base] = 0; p.bucket_count[vb - vb_base] = 0; }
+            // an empty bucket only publishes its (zero) count: its successors look past it
+            if (p.ordered && threadIdx.x == 0) st_relaxed_u64(p.pub + (vb - vb_base), (vb == vb_base ? kAggPubInc : kAggPubOwn));
+            continue;
+        }
         // phase 0: the whole (virtual) bucket in one table; on overflow phase 1 counts over its key sub-ranges and
         // phase 2 emits them in ascending order
         uint32_t phase = 0;
@@ -1388,8 +1442,13 @@ k_aggregate_cols(const AggParams2 p) {
                 if (phase != 1) break;
                 __syncthreads();          // everyone has seen the empty stack before it is refilled
                 // counting sweep done: reserve the bucket's chunk, then emit
+                if (p.ordered) {
+                    if (threadIdx.x < 32) {
+                        const unsigned long long base = agg_reserve_ordered(p, vb - vb_base, bucket_total);
+                        if (threadIdx.x == 0) s_base = base;
+                    }
+                } else if (threadIdx.x == 0) s_base = atomicAdd(&p.scalars[S_U_NEEDED], (unsigned long long)bucket_total);
                 if (threadIdx.x == 0) {
-                    s_base = atomicAdd(&p.scalars[S_U_NEEDED], (unsigned long long)bucket_total);
                     s_sp = 0;
                     s_depth[s_sp] = sb + 1; s_idx[s_sp] = 2ULL * sub + 1; s_sp++;
                     s_depth[s_sp] = sb + 1; s_idx[s_sp] = 2ULL * sub; s_sp++;
@@ -1443,7 +1502,12 @@ k_aggregate_cols(const AggParams2 p) {
             if (phase == 1) { bucket_total += total_kept; continue; }
             if (phase == 0) {
                 bucket_total = total_kept;
-                if (threadIdx.x == 0) s_base = atomicAdd(&p.scalars[S_U_NEEDED], (unsigned long long)total_kept);
+                if (p.ordered) {
+                    if (threadIdx.x < 32) {
+                        const unsigned long long base = agg_reserve_ordered(p, vb - vb_base, total_kept);
+                        if (threadIdx.x == 0) s_base = base;
+                    }
+                } else if (threadIdx.x == 0) s_base = atomicAdd(&p.scalars[S_U_NEEDED], (unsigned long long)total_kept);
             }
             agg_fix(t, 64 - key_bits + depth);
             __syncthreads();
