@@ -477,3 +477,28 @@ def test_c4_style_read_sets(gpu):
     st1 = check(genomes, 31, min_abundance=1, keep_singletons=True, kind=1)
     assert st1["n_kmers"] > 3 * st2["n_kmers"]                                # the error k-mers are most of the unfiltered set
     check(genomes, 31, min_abundance=2, keep_singletons=False, kind=1)
+
+
+@pytest.mark.parametrize("G,k,keep,bucket_bits,kind,min_ab", [
+    (5, 31, True, 4, 0, 1),        # table overflow: the bucket's offset is reserved after the counting sweep
+    (130, 21, False, 0, 0, 1),     # three word rows: rows 1 and 2 go through the 2-D copy
+    (3, 15, True, 12, 0, 1),       # far more buckets than columns: most of the look-back chain is empty buckets
+    (4, 21, False, 0, 1, 2),       # reads with an abundance filter: the k-mer-record pipeline, one word row
+])
+def test_ordered_emission_equals_gather_path(gpu, monkeypatch, G, k, keep, bucket_bits, kind, min_ab):
+    """A final build writes its columns in place (buckets dealt by ticket, offsets by look-back over the published
+    bucket counts); GRMKM_UNORDERED=1 is the chunk + gather path it replaced.  Same bytes, and both equal the oracle."""
+    rng = np.random.default_rng(100 + G)
+    shared = [inputs.rand_seq(rng, 60_000)]
+    if kind == 0:
+        genomes = [[inputs.fasta(rng, n_records=3, min_len=20_000, max_len=50_000, shared=shared, p_shared=0.6)] for _ in range(G)]
+    else:
+        genomes = [[inputs.fastq(rng, shared[0], n_reads=3000)] for _ in range(G)]
+    kw = {"bucket_bits": bucket_bits} if bucket_bits else {}
+    stats = check(genomes, k, min_abundance=min_ab, keep_singletons=keep, kind=kind, **kw)
+    if bucket_bits == 4:
+        assert stats["n_splits"] > 0
+    km, mat, _ = gpu_build(genomes, k, min_ab, keep, kind, **kw)
+    monkeypatch.setenv("GRMKM_UNORDERED", "1")
+    km2, mat2, _ = gpu_build(genomes, k, min_ab, keep, kind, **kw)
+    assert np.array_equal(km, km2) and np.array_equal(mat, mat2)
