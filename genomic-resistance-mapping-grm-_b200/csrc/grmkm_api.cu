@@ -54,6 +54,14 @@ struct grmkm_ctx {
     void* h_tab = nullptr;         // page-locked arena for the per-batch host tables (files, stream starts, ticket order)
     size_t h_tab_cap = 0, h_tab_used = 0;
     uint64_t wide_hint = 0;
+    // the packed stream and the tile words of the NEXT build are cleared on a side stream while this build's dedupe /
+    // expand / aggregate run (they are dead once the scatter has consumed them)
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_scattered = nullptr, ev_cleared = nullptr;
+    bool pre_pending = false;
+    const void *pre_codes = nullptr, *pre_valid = nullptr, *pre_pub = nullptr;
+    uint64_t pre_groups = 0, pre_pub_bytes = 0;
+    uint64_t pass_groups = 0, pass_pub_bytes = 0;
     uint64_t wide_capped_need = 0;   // an expansion-buffer request of up to this many bytes was capped by free memory
     uint64_t ucap_hint = 0;        // columns of the previous build + headroom (sizes the aggregate's output)        // wide records of the previous build (sizes the expansion's bucket regions)
 
@@ -379,6 +387,7 @@ int grmkm_create(const grmkm_config* cfg, grmkm_ctx** out) {
 void grmkm_destroy(grmkm_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);      // the clear for a next build may still be running
     DevBuf* all[] = {&c->in, &c->files, &c->hdr0, &c->tile_file, &c->tile_pub, &c->tile_order,
                      &c->fss, &c->codes, &c->valid, &c->hist, &c->offsets, &c->offsets2,
                      &c->bcounts, &c->records, &c->records2, &c->ukeys, &c->uwords, &c->skeys, &c->sidx_a, &c->sidx_b,
@@ -387,6 +396,10 @@ void grmkm_destroy(grmkm_ctx* c) {
     for (DevBuf* b : all) release(c, *b);
     if (c->ev_ok) for (int i = 0; i < T_N; ++i) cudaEventDestroy(c->ev[i]);
     if (c->host_res) cudaFreeHost(c->host_res);
+    if (c->aux_stream) {
+        cudaEventDestroy(c->ev_scattered); cudaEventDestroy(c->ev_cleared);
+        cudaStreamDestroy(c->aux_stream);
+    }
     if (c->copy_stream) {
         for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->ev_copied[i]); cudaEventDestroy(c->ev_free[i]); }
         cudaStreamDestroy(c->copy_stream);
@@ -560,10 +573,22 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         ENSURE(c, c->codes, n_groups_max * 8);
         ENSURE(c, c->valid, n_groups_max * 4);
         ENSURE(c, c->tile_order, n_tiles * 4);
-        // the memsets go first: the device clears while the host builds this batch's tables
-        CU_TRY(c, cudaMemsetAsync(c->codes.p, 0, n_groups_max * 8, st));
-        CU_TRY(c, cudaMemsetAsync(c->valid.p, 0, n_groups_max * 4, st));
-        CU_TRY(c, cudaMemsetAsync(c->tile_pub.p, 0, (3 * n_tiles + 1) * 8, st));
+        // the memsets go first: the device clears while the host builds this batch's tables -- unless the previous build
+        // already cleared the buffers on the side stream (same buffers, at least this much of them)
+        bool cleared = false;
+        if (c->pre_pending) {
+            CU_TRY(c, cudaStreamWaitEvent(st, c->ev_cleared, 0));
+            cleared = c->pre_codes == c->codes.p && c->pre_valid == c->valid.p && c->pre_pub == c->tile_pub.p &&
+                      c->pre_groups >= n_groups_max && c->pre_pub_bytes >= (3 * n_tiles + 1) * 8;
+            c->pre_pending = false;
+        }
+        if (!cleared) {
+            CU_TRY(c, cudaMemsetAsync(c->codes.p, 0, n_groups_max * 8, st));
+            CU_TRY(c, cudaMemsetAsync(c->valid.p, 0, n_groups_max * 4, st));
+            CU_TRY(c, cudaMemsetAsync(c->tile_pub.p, 0, (3 * n_tiles + 1) * 8, st));
+        }
+        c->pass_groups = std::max<uint64_t>(c->pass_groups, n_groups_max);
+        c->pass_pub_bytes = std::max<uint64_t>(c->pass_pub_bytes, (3 * n_tiles + 1) * 8);
         // host tables in page-locked memory (asynchronous copies without a staging hop); they stay untouched until the
         // build's final synchronize
         const size_t tab_bytes = (F * sizeof(FileDesc) + (F + 1) * 8 + (size_t)n_tiles * 4 + 63) & ~size_t(63);
@@ -655,6 +680,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
     uint64_t ucap = 0;
     for (int pass = try_regions ? 0 : 1; pass < 2; ++pass) {
         const bool regions = (pass == 0);
+        c->pass_groups = 0; c->pass_pub_bytes = 0;
         const std::vector<Batch> batches = make_batches(regions && any_host);
         const bool pipelined = batches.size() > 1;
         {   // host table arena for all batches of this pass (nothing of an earlier pass / build is in flight: both end synchronised)
@@ -850,6 +876,24 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         L.n++;
         CU_TRY(c, cudaGetLastError());
         if (c->ev_ok) cudaEventRecord(c->ev[T_SCATTER], st);
+        // codes / valid / tile words are dead from here on: clear them for the next build (or the next pass) on the side
+        // stream, under the dedupe / expand / aggregate kernels, which leave most of the HBM bandwidth unused
+        if (c->pass_groups && !getenv("GRMKM_NO_PRECLEAR")) {
+            if (!c->aux_stream) {
+                CU_TRY(c, cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+                CU_TRY(c, cudaEventCreateWithFlags(&c->ev_scattered, cudaEventDisableTiming));
+                CU_TRY(c, cudaEventCreateWithFlags(&c->ev_cleared, cudaEventDisableTiming));
+            }
+            CU_TRY(c, cudaEventRecord(c->ev_scattered, st));
+            CU_TRY(c, cudaStreamWaitEvent(c->aux_stream, c->ev_scattered, 0));
+            CU_TRY(c, cudaMemsetAsync(c->codes.p, 0, c->pass_groups * 8, c->aux_stream));
+            CU_TRY(c, cudaMemsetAsync(c->valid.p, 0, c->pass_groups * 4, c->aux_stream));
+            CU_TRY(c, cudaMemsetAsync(c->tile_pub.p, 0, c->pass_pub_bytes, c->aux_stream));
+            CU_TRY(c, cudaEventRecord(c->ev_cleared, c->aux_stream));
+            c->pre_pending = true;
+            c->pre_codes = c->codes.p; c->pre_valid = c->valid.p; c->pre_pub = c->tile_pub.p;
+            c->pre_groups = c->pass_groups; c->pre_pub_bytes = c->pass_pub_bytes;
+        }
 
         // ---- optional abundance filter (reads: -abundance-min, kmer_count.py:48)
         const unsigned long long* agg_records = (const unsigned long long*)c->records.p;
