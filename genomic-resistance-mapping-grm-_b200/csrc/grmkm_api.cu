@@ -1093,6 +1093,17 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
             }
             L.n++;
             CU_TRY(c, cudaGetLastError());
+            if (ordered) {
+                // rows >= 1 move from stride ucap to the result's stride U (row 0 and the k-mers are already in place); U is read
+                // on the device, so the build ends with this one synchronisation
+                if (c->ev_ok) cudaEventRecord(c->ev[T_AGG], st);
+                if (P.W > 1) {
+                    k_move_rows<<<(uint32_t)c->sm_count * 8, 256, 0, st>>>((const unsigned long long*)c->uwords.p, ucap, (unsigned long long*)c->matrix.p,
+                                                                          (const unsigned long long*)(d_scalars + S_U_NEEDED), P.W);
+                    L.n++;
+                    CU_TRY(c, cudaGetLastError());
+                }
+            }
             CU_TRY(c, cudaMemcpyAsync(sc, d_scalars, sizeof sc, cudaMemcpyDeviceToHost, st));
             CU_TRY(c, cudaStreamSynchronize(st));
             if (regions && sc[S_OVERFLOW]) break;
@@ -1118,7 +1129,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         if (!(regions && (sc[S_OVERFLOW] || unit_overflow))) break;
         c->stats.n_region_overflows++;
     }
-    if (c->ev_ok) cudaEventRecord(c->ev[T_AGG], st);
+    if (c->ev_ok && !ordered) cudaEventRecord(c->ev[T_AGG], st);
     const uint64_t U = sc[S_U_NEEDED];
 
     // ---- final order.  Default: ascending hash (bucket order; every bucket chunk is already sorted), which is
@@ -1128,10 +1139,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         int r = sort_and_gather(c, U, P.W, ucap, 2 * c->cfg.k, false, L);
         if (r) return r;
     } else if (ordered) {
-        // rows >= 1 move from stride ucap to the result's stride U (row 0 and the k-mers are already in place)
-        if (U && P.W > 1)
-            CU_TRY(c, cudaMemcpy2DAsync((unsigned long long*)c->matrix.p + U, U * 8, (const unsigned long long*)c->uwords.p + ucap, ucap * 8,
-                                        U * 8, P.W - 1, cudaMemcpyDeviceToDevice, st));
+        // nothing left to do: k_move_rows ran behind the aggregate
     } else {
         ENSURE(c, c->offsets2, (size_t)(VB + 1) * 8);
         ENSURE(c, c->kmers, U * 8);

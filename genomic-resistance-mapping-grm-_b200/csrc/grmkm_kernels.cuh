@@ -1523,6 +1523,20 @@ k_aggregate_cols(const AggParams2 p) {
     }
 }
 
+// ordered emission: word rows >= 1 from stride cap (the aggregate's output) to the result's stride U, which only the
+// device knows when this is launched (no host round trip between the aggregate and the end of the build)
+__global__ void __launch_bounds__(256)
+k_move_rows(const unsigned long long* __restrict__ src, unsigned long long cap, unsigned long long* __restrict__ dst,
+            const unsigned long long* __restrict__ u_ptr, uint32_t W) {
+    const unsigned long long U = *u_ptr;
+    if (U > cap) return;                                   // the aggregate overflowed its guess: the host repeats it
+    const unsigned long long n = U * (W - 1);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long w = 1 + i / U, j = i - (w - 1) * U;
+        dst[w * U + j] = __ldcs(src + w * cap + j);
+    }
+}
+
 // bucket chunks (arbitrary order in tmp) -> final arrays in bucket order: one CTA per bucket
 __global__ void __launch_bounds__(256)
 k_gather_buckets(const unsigned long long* __restrict__ tmp_keys, const unsigned long long* __restrict__ tmp_words,
