@@ -166,6 +166,46 @@ class KmerMatrixBuilder:
         self._check(self._lib.grmkm_format_tsv(self._ctx, arr, C.c_void_p(out.ctypes.data), out.size, C.byref(need)))
         return out
 
+    # -- kernels over the resident result ------------------------------------------------------
+    def checksum(self) -> tuple[int, int]:
+        """Order-independent 128-bit digest of the columns (two wrapping 64-bit sums); the digests of the ranks'
+        slices of a multi-GPU build add up to the digest of the one-GPU matrix (bench.py parity_check)."""
+        out = (C.c_uint64 * 2)()
+        self._check(self._lib.grmkm_result_checksum(self._ctx, out))
+        return int(out[0]), int(out[1])
+
+    def sum_rows(self, row_mask) -> np.ndarray:
+        """Per column, the number of masked genome rows that hold the k-mer: popcount(matrix[:, j] & row_mask)
+        summed over the word rows (rules.py:201-267).  row_mask: uint64[W], genome g at bit 63-(g%64) of word g//64."""
+        U, W, _ = self.dims
+        mask = np.ascontiguousarray(row_mask, dtype=np.uint64)
+        if mask.shape != (W,):
+            raise ValueError(f"row mask of {mask.shape} words for {W} matrix word rows")
+        out = np.empty(U, dtype=np.uint32)
+        self._check(self._lib.grmkm_sum_rows(self._ctx, C.c_void_p(mask.ctypes.data), W, C.c_void_p(out.ctypes.data), U))
+        return out
+
+    def gram(self) -> np.ndarray:
+        """G x G shared-column counts (Ray Surveyor's similarity matrix)."""
+        _, _, G = self.dims
+        out = np.zeros((G, G), dtype=np.uint64)
+        self._check(self._lib.grmkm_gram(self._ctx, C.c_void_p(out.ctypes.data), G * G))
+        return out
+
+    def tsv_pack(self, body: np.ndarray, row_width: int, k: int, n_tsv_cols: int, sel) -> np.ndarray:
+        """from_tsv's bit packer: fixed-width TSV rows (uint8 body) -> matrix words [ceil(G/64)][n_rows]; matrix row g
+        takes TSV column sel[g] (create.py:241-271, utils.py:133-156)."""
+        body = np.ascontiguousarray(body, dtype=np.uint8).reshape(-1)
+        sel = np.ascontiguousarray(sel, dtype=np.uint32)
+        if row_width <= 0 or body.size % row_width:
+            raise ValueError("the TSV body is not a whole number of rows")
+        n_rows, G = body.size // row_width, int(sel.size)
+        out = np.zeros(((G + 63) // 64, n_rows), dtype=np.uint64)
+        self._check(self._lib.grmkm_tsv_pack(self._ctx, C.c_void_p(body.ctypes.data), n_rows, int(row_width), int(k),
+                                             int(n_tsv_cols), G, C.c_void_p(sel.ctypes.data),
+                                             C.c_void_p(out.ctypes.data), out.size))
+        return out
+
     def device_result(self) -> tuple[int, int]:
         a, b = C.c_void_p(), C.c_void_p()
         self._check(self._lib.grmkm_device_result(self._ctx, C.byref(a), C.byref(b)))

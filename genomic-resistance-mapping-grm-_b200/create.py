@@ -160,26 +160,76 @@ def _host_threads(nb_cores):
     return n if n > 0 else (os.cpu_count() or 1)
 
 
-def _build(files_per_genome, kmer_size, abundance_min, filter_singleton, input_kind, progress):
-    from .builder import KmerMatrixBuilder
+def _read_inputs(files_per_genome, threads):
+    """Every input file in page-locked host memory (one arena, files 16-byte aligned), read by a thread pool: the
+    H2D copies of the build then run at PCIe speed without a pageable staging hop.  ``.gz`` files are left to the
+    library's own inflater.  -> (arena tensor or None, rows, buffers, leftover [(row, path)])"""
+    from concurrent.futures import ThreadPoolExecutor
+    flat = [(row, p) for row, files in enumerate(files_per_genome) for p in files]
+    plain = [(row, p) for row, p in flat if not p.endswith(".gz")]
+    rest = [(row, p) for row, p in flat if p.endswith(".gz")]
+    sizes = [os.path.getsize(p) for _, p in plain]
+    offs, total = [], 0
+    for n in sizes:
+        offs.append(total)
+        total += (n + 15) & ~15
+    if not total:
+        return None, [], [], rest
+    import torch
+    try:
+        arena = torch.empty(total, dtype=torch.uint8).pin_memory()
+    except RuntimeError:                                   # not enough lockable memory: pageable works too, slower
+        arena = torch.empty(total, dtype=torch.uint8)
+    host = arena.numpy()
+
+    def load(i):
+        n, o = sizes[i], offs[i]
+        with open(plain[i][1], "rb", buffering=0) as f:
+            got = f.readinto(memoryview(host[o:o + n]))
+            while got < n:                                  # readinto may stop short on some file systems
+                more = f.readinto(memoryview(host[o + got:o + n]))
+                if not more:
+                    raise IOError("short read on %s" % plain[i][1])
+                got += more
+
+    with ThreadPoolExecutor(max_workers=max(1, min(threads, 32))) as ex:
+        list(ex.map(load, range(len(plain))))
+    return arena, [row for row, _ in plain], [host[o:o + n] for o, n in zip(offs, sizes)], rest
+
+
+def _build(files_per_genome, kmer_size, abundance_min, filter_singleton, input_kind, progress, gpus=None,
+           temp_dir=None, threads=8):
+    from . import multi
     k = int(kmer_size)
     keep = (filter_singleton == "nothing")
+    n_gpus = multi.requested_gpus(gpus)
+    if n_gpus > 1:
+        # GRM_GPUS / gpus=: one process per GPU, rows sharded in 64-aligned blocks (multi.py)
+        if progress:
+            print("grm_b200: counting and packing k-mers of %d genomes on %d GPUs" % (len(files_per_genome), n_gpus), flush=True)
+        return multi.build_matrix(files_per_genome, k, max(1, int(abundance_min)), keep, input_kind, n_gpus, temp_dir)
+    from .builder import KmerMatrixBuilder
     with KmerMatrixBuilder(k=k, min_abundance=max(1, int(abundance_min)), keep_singletons=keep,
                            input_kind=input_kind) as b:
         b.set_genome_count(len(files_per_genome))
-        for row, files in enumerate(files_per_genome):
-            b.add_genome_files(row, files)
+        arena, rows, bufs, rest = _read_inputs(files_per_genome, threads)
+        if rows:
+            b.add_genomes(rows, bufs)
+        for row, path in rest:
+            b.add_genome_files(row, [path])
         if progress:
             print("grm_b200: counting and packing k-mers of %d genomes on the GPU" % len(files_per_genome), flush=True)
         b.build()
+        del arena
         stats = b.stats
         logging.debug("k-mer matrix: %d columns, %d bases, device times %s", stats["n_kmers"], stats["n_bases"], b.times)
-        return b.kmer_strings(), b.matrix(), stats
+        _, mat = b.result_host()                     # one D2H at PCIe speed into the context's page-locked buffer
+        return b.kmer_strings(), np.array(mat), stats
 
 
 def from_contigs(contig_list_path, output_path, kmer_size, filter_singleton, phenotype_description,
                  phenotype_metadata_path, gzip, temp_dir, nb_cores, verbose, progress, warning_callback=None,
-                 error_callback=None):
+                 error_callback=None, gpus=None):
     """``kover dataset create from-contigs`` (kover:103-159 -> create.py:278-396)."""
     warning_callback, error_callback, _ = _callbacks(warning_callback, error_callback)
     gzip = int(gzip)
@@ -198,7 +248,8 @@ def from_contigs(contig_list_path, output_path, kmer_size, filter_singleton, phe
                                                        phenotype_metadata_path, warning_callback, error_callback)
     files = [[contig_file_by_genome_id[str(g)]] for g in genome_ids]
     logging.debug("Counting and packing k-mers (libgrmkm).")
-    kmer_strings, matrix, _ = _build(files, kmer_size, 1, filter_singleton, FASTA, progress)   # -abundance-min 1
+    kmer_strings, matrix, _ = _build(files, kmer_size, 1, filter_singleton, FASTA, progress, gpus, temp_dir,
+                                     _host_threads(nb_cores))                                   # -abundance-min 1
     attrs = _root_attrs("contigs", contig_list_path, phenotype_description, phenotype_metadata_path, gzip, ctype,
                         filter_singleton)
     _write_dataset(output_path, attrs, genome_ids, labels, tags, phenotype_description, kmer_strings, matrix, gzip,
@@ -208,7 +259,7 @@ def from_contigs(contig_list_path, output_path, kmer_size, filter_singleton, phe
 
 def from_reads(reads_folders_list_path, output_path, kmer_size, abundance_min, filter_singleton, phenotype_description,
                phenotype_metadata_path, gzip, temp_dir, nb_cores, verbose, progress, warning_callback=None,
-               error_callback=None):
+               error_callback=None, gpus=None):
     """``kover dataset create from-reads`` (kover:161-224 -> create.py:399-523)."""
     warning_callback, error_callback, _ = _callbacks(warning_callback, error_callback)
     gzip = int(gzip)
@@ -228,13 +279,35 @@ def from_reads(reads_folders_list_path, output_path, kmer_size, abundance_min, f
     files = []
     for g in genome_ids:
         d = reads_folder_by_genome_id[str(g)]
-        files.append([os.path.join(d, name) for name in os.listdir(d) if name.endswith(SUPPORTED_READ_EXTENSIONS)])
-    kmer_strings, matrix, _ = _build(files, kmer_size, abundance_min, filter_singleton, FASTQ, progress)
+        files.append([os.path.join(d, name) for name in sorted(os.listdir(d)) if name.endswith(SUPPORTED_READ_EXTENSIONS)])
+    kmer_strings, matrix, _ = _build(files, kmer_size, abundance_min, filter_singleton, FASTQ, progress, gpus, temp_dir,
+                                     _host_threads(nb_cores))
     attrs = _root_attrs("reads", reads_folders_list_path, phenotype_description, phenotype_metadata_path, gzip, ctype,
                         filter_singleton)
     _write_dataset(output_path, attrs, genome_ids, labels, tags, phenotype_description, kmer_strings, matrix, gzip,
                    _host_threads(nb_cores))
     logging.debug("Dataset creation completed.")
+
+
+def read_kmer_matrix_tsv_rows(tsv_path):
+    """Ray Surveyor KmerMatrix.tsv -> (genome ids, k, row width, body uint8[n][row width]) without touching the cells
+    (the GPU packer reads them, grmkm_tsv_pack).  The body is a memory map of the file."""
+    with open(tsv_path, "rb") as f:
+        header = f.readline()
+        hdr_len = f.tell()
+        first = f.readline()
+    genome_ids = header.rstrip(b"\r\n").decode().split("\t")[1:]
+    size = os.path.getsize(tsv_path) - hdr_len
+    if size == 0:
+        return genome_ids, 0, 0, np.zeros((0, 0), dtype=np.uint8)
+    roww = len(first)
+    if size % roww != 0:
+        raise Exception("The k-mer matrix rows do not all have the same width.")
+    k = first.index(b"\t")
+    if roww != k + 2 * len(genome_ids) + 1:
+        raise Exception("Unexpected k-mer matrix row width.")
+    body = np.memmap(tsv_path, dtype=np.uint8, mode="r", offset=hdr_len, shape=(size // roww, roww))
+    return genome_ids, k, roww, body
 
 
 def read_kmer_matrix_tsv(tsv_path):
@@ -262,8 +335,17 @@ def read_kmer_matrix_tsv(tsv_path):
 
 
 def from_tsv(tsv_path, output_path, phenotype_description, phenotype_metadata_path, gzip, warning_callback=None,
-             error_callback=None, progress_callback=None):
-    """``kover dataset create from-tsv`` (kover:41-100 -> create.py:119-275)."""
+             error_callback=None, progress_callback=None, use_gpu=None):
+    """``kover dataset create from-tsv`` (kover:41-100 -> create.py:119-275).  The reference parses the text with pandas
+    in chunks and packs the rows in a Python loop (create.py:241-271, utils.py:147-154); here the fixed-width rows go to
+    the GPU as they are and one kernel gathers the cells of the kept genomes into matrix words (grmkm_tsv_pack).
+    ``use_gpu=False`` (or GRM_TSV_PACKER=host) selects the numpy packer instead -- an explicit choice, never a
+    fallback: with the GPU packer selected and no device the call fails."""
+    if use_gpu is None:
+        use_gpu = os.environ.get("GRM_TSV_PACKER", "gpu") != "host"
+    if use_gpu:
+        return _from_tsv_gpu(tsv_path, output_path, phenotype_description, phenotype_metadata_path, gzip, warning_callback,
+                             error_callback, progress_callback)
     warning_callback, error_callback, progress_callback = _callbacks(warning_callback, error_callback, progress_callback)
     gzip = int(gzip)
     if (phenotype_description is None) != (phenotype_metadata_path is None):
@@ -280,6 +362,38 @@ def from_tsv(tsv_path, output_path, phenotype_description, phenotype_metadata_pa
     progress_callback("Creating", 0.5)
     matrix = _pack_binary_bytes_to_ints(np.ascontiguousarray(cells[:, sel].T) if cells.size else
                                         np.zeros((len(sel), 0), dtype=np.uint8), KMER_MATRIX_PACKING_SIZE)
+    attrs = _root_attrs("tsv", tsv_path, phenotype_description, phenotype_metadata_path, gzip, ctype)
+    _write_dataset(output_path, attrs, genome_ids, labels, tags, phenotype_description, kmers, matrix, gzip,
+                   os.cpu_count() or 1)
+    progress_callback("Creating", 1.0)
+    logging.debug("Dataset creation completed.")
+
+
+def _from_tsv_gpu(tsv_path, output_path, phenotype_description, phenotype_metadata_path, gzip, warning_callback,
+                  error_callback, progress_callback):
+    from .builder import KmerMatrixBuilder
+    warning_callback, error_callback, progress_callback = _callbacks(warning_callback, error_callback, progress_callback)
+    gzip = int(gzip)
+    if (phenotype_description is None) != (phenotype_metadata_path is None):
+        raise ValueError("If a phenotype is specified, it must have a description and a metadata file.")
+    progress_callback("Creating", 0.0)
+    tsv_ids, k, roww, body = read_kmer_matrix_tsv_rows(tsv_path)
+    logging.debug("The k-mer matrix contains %d genomes." % len(tsv_ids))
+    if len(set(tsv_ids)) < len(tsv_ids):
+        error_callback(Exception("The genomic data contains genomes with the same identifier."))
+    genome_ids, labels, tags, ctype = _ordered_genomes(tsv_ids, phenotype_description, phenotype_metadata_path,
+                                                       warning_callback, error_callback)
+    col = {g: i for i, g in enumerate(tsv_ids)}
+    sel = np.array([col[str(g)] for g in genome_ids], dtype=np.uint32)
+    progress_callback("Creating", 0.5)
+    n = int(body.shape[0])
+    if n:
+        kmers = np.ascontiguousarray(body[:, :k]).view("S%d" % k).reshape(-1)
+        with KmerMatrixBuilder(k=min(max(k, 1), 32)) as b:           # any context of the device will do
+            matrix = b.tsv_pack(body, roww, k, len(tsv_ids), sel)
+    else:
+        kmers = np.zeros(0, dtype="S1")
+        matrix = np.zeros(((len(sel) + 63) // 64, 0), dtype=np.uint64)
     attrs = _root_attrs("tsv", tsv_path, phenotype_description, phenotype_metadata_path, gzip, ctype)
     _write_dataset(output_path, attrs, genome_ids, labels, tags, phenotype_description, kmers, matrix, gzip,
                    os.cpu_count() or 1)

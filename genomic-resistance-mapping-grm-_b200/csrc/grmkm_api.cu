@@ -3,6 +3,7 @@
 #include "../../include/grmkm.h"
 #include "grmkm_kernels.cuh"
 #include "grmkm_units.cuh"
+#include "grmkm_result.cuh"
 #include "grmkm_synth.cuh"
 
 #include <zlib.h>
@@ -11,7 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <deque>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -35,6 +36,7 @@ struct Input {
     std::vector<uint8_t> owned;
 };
 
+constexpr uint32_t kMaxGenomes = 32768;
 constexpr uint64_t kBatchBytes = 32ull << 20;      // text per pipelined H2D batch (GRMKM_BATCH_BYTES overrides, for tests)
 
 enum Stage { T_START = 0, T_H2D, T_PARSE, T_PACK, T_COUNT, T_BOUNDS, T_SCATTER, T_ABUND, T_DEDUPE, T_EXPAND, T_AGG, T_SORT, T_N };
@@ -67,8 +69,11 @@ struct grmkm_ctx {
 
     // device buffers (grow-only, reused across builds)
     DevBuf in, files, hdr0, tile_file, tile_pub, tile_order, fss, codes, valid, hist,
-        offsets, offsets2, bcounts, records, records2, ukeys, uwords, skeys, sidx_a, sidx_b, shist, kmers, matrix,
-        scalars, fmt, synth, owner_start, refs, spart, stile_file, bbase, apub, masks, units, ucur, ubeg, wu, wide;
+        offsets, offsets2, bcounts, ukeys, uwords, kmers, matrix,
+        scalars, fmt, synth, refs, stile_file, bbase, apub, masks, units, ucur, ubeg, wu, wide,
+        racc,            // abundance builds: the solid presence records of the rounds done so far
+        aux;             // result-side kernels: row mask / per-column sums / checksum / bit rows / Gram matrix
+    uint64_t racc_hint = 0;        // records of the previous abundance build + headroom
     size_t device_bytes = 0;
 
     cudaEvent_t ev[T_N]{};
@@ -170,13 +175,6 @@ int read_file(grmkm_ctx* c, const char* path, std::vector<uint8_t>& out) {
     return GRMKM_OK;
 }
 
-struct Plan {
-    uint32_t F = 0, G = 0, W = 0;
-    uint64_t n_tiles = 0, n_sblk = 0, max_stream = 0, n_groups_max = 0, in_bytes = 0;
-    uint32_t bucket_bits = 0, row_bits = 0, slots = 0, sub_bits = 0;
-    size_t agg_smem = 0;
-};
-
 size_t agg_smem_budget(const grmkm_ctx* c) {
     // leave room for the kernel's static shared memory
     size_t lim = c->smem_optin ? c->smem_optin : 227 * 1024;
@@ -184,38 +182,65 @@ size_t agg_smem_budget(const grmkm_ctx* c) {
     return lim - 4096;
 }
 
-// table capacity for W words per column and the bucket count that keeps a bucket's distinct k-mers
-// (estimated as 3x the largest genome) at about half of it
-// table = (slots + kMaxProbe) x (u64 key + 2W u32 half-words + u8 kept flag / correction + u8 own inversions); slots = home positions
-uint32_t table_slots(const grmkm_ctx* c, uint32_t W) {
+// table = (slots + kMaxProbe) x (u64 key + `cells` u32 cells + u8 kept flag / correction + u8 own inversions); slots = home
+// positions.  cells = 2 W presence half-words (presence builds), one counter per genome row of the round rounded up to
+// even (abundance rounds), one entry reference per source (owner-side merge).
+uint32_t table_slots(const grmkm_ctx* c, uint32_t cells) {
     const size_t budget = agg_smem_budget(c);
-    const size_t total = (budget - 8) / (10 + 8 * (size_t)W);
+    const size_t total = (budget - 8) / (10 + 4 * (size_t)cells);
     if (total < (size_t)kMaxProbe + 256) return 0;
     return (uint32_t)std::min<size_t>(kAggMaxSlots, total - kMaxProbe);
 }
-size_t table_smem(uint32_t slots, uint32_t W) {
-    return (((size_t)slots + kMaxProbe) * (10 + 8 * (size_t)W) + 8 + 15) & ~size_t(15);
+size_t table_smem(uint32_t slots, uint32_t cells) {
+    return (((size_t)slots + kMaxProbe) * (10 + 4 * (size_t)cells) + 8 + 15) & ~size_t(15);
 }
-// Bucket count: the distinct k-mers of a bucket must fit its shared-memory table at a load of about 0.6 by the estimate
-// (which is generous: C2 ends at 0.53).
-// The pan-genome of the context is estimated from the largest genome (1.9x its text; a bucket that turns out
-// too full is split into key sub-ranges by the kernel, so the estimate only costs time, never correctness).
-// Fewer buckets = longer runs per scatter tile = fewer store requests, the scatter's bound.
+
 constexpr uint32_t kUnitMaxBucketBits = 11;      // the unit expansion sorts tiles over at most 2^11 hash buckets
-bool units_wanted(const grmkm_ctx* c) {
-    return c->cfg.min_abundance <= 1 && !(c->cfg.flags & (GRMKM_FLAG_KMER_RECORDS | GRMKM_FLAG_SIMPLE_SCATTER));
+constexpr uint32_t kMaxSubBits = 3;              // key sub-ranges (virtual buckets) per bucket: up to 2^3
+constexpr uint32_t kRoundMaxRows = 4;            // genome rows per abundance round (one u32 counter plane each)
+
+bool abundance_build(const grmkm_ctx* c) { return c->cfg.min_abundance > 1 || (c->cfg.flags & GRMKM_FLAG_COUNTS); }
+
+// ---- abundance rounds: the genomes of a -abundance-min > 1 build are counted a few rows at a time (the counters of a
+// round live in the shared-memory tables, and the distinct k-mers of read sets are mostly sequencing errors that are
+// unique to their genome).  A round holds consecutive rows of ONE 64-row matrix word, at most kRoundMaxRows of them,
+// and as much text as the tables of one pass hold (estimated: one distinct k-mer per 10 bytes of text).
+struct Round { uint32_t f0, f1, row0, n_rows; uint64_t bytes; };
+
+std::vector<Round> plan_rounds(const grmkm_ctx* c, uint32_t G, const std::vector<uint32_t>& first_file /* [G + 1] */,
+                               const std::vector<uint64_t>& row_bytes) {
+    std::vector<Round> rounds;
+    if (c->cfg.flags & GRMKM_FLAG_COUNTS) {          // pooled count table: everything is one row
+        rounds.push_back(Round{0, first_file[G], 0, 1, 0});
+        for (uint64_t b : row_bytes) rounds.back().bytes += b;
+        return rounds;
+    }
+    uint32_t max_rows = kRoundMaxRows;
+    if (const char* e = getenv("GRMKM_ROUND_ROWS")) max_rows = (uint32_t)std::min(16, std::max(1, atoi(e)));
+    uint32_t r = 0;
+    while (r < G) {
+        Round rd{first_file[r], first_file[r + 1], r, 1, row_bytes[r]};
+        while (rd.n_rows < max_rows && r + rd.n_rows < G && ((r + rd.n_rows) & 63u) != 0) {
+            const uint32_t nr = rd.n_rows + 1;
+            const uint64_t cap_keys = (uint64_t)table_slots(c, (nr + 1) & ~1u) * 6 / 10 << (kUnitMaxBucketBits + kMaxSubBits);
+            const uint64_t nb = rd.bytes + row_bytes[r + rd.n_rows];
+            if (nb / 10 > cap_keys) break;
+            rd.n_rows = nr; rd.bytes = nb; rd.f1 = first_file[r + nr];
+        }
+        rounds.push_back(rd);
+        r += rd.n_rows;
+    }
+    return rounds;
 }
-uint32_t auto_bucket_bits(const grmkm_ctx* c, uint32_t G) {
-    std::vector<uint64_t> row_bytes(std::max(G, 1u), 0);
-    for (const Input& in : c->inputs) if (in.row < G) row_bytes[in.row] += in.len;
-    const uint64_t max_row = *std::max_element(row_bytes.begin(), row_bytes.end());
-    const uint32_t slots = table_slots(c, (G + 63) / 64);
-    const uint64_t u_est = max_row + max_row * 9 / 10 + 1024;
+
+// Bucket count: the distinct k-mers of a bucket must fit its shared-memory table at a load of about 0.6 by the
+// estimate (a bucket that turns out too full is split into key sub-ranges by the kernel, so the estimate only costs
+// time, never correctness).  Fewer buckets = longer runs per scatter tile = fewer store requests.  Past 2^11 buckets
+// every further bit doubles the aggregate's passes over the records (key sub-ranges), so a table that the estimate
+// fills to 0.7 is still the better deal.
+uint32_t bits_for(uint64_t u_est, uint32_t slots) {
     const uint64_t per = std::max<uint64_t>(1, (uint64_t)slots * 60 / 100);
-    uint32_t bits = std::min(15u, std::max(6u, ceil_log2((u_est + per - 1) / per)));
-    if (!units_wanted(c)) return std::max(std::max(1u, ceil_log2(G)), bits);     // k-mer records carry the row below the hash
-    // unit path: past 2^11 buckets every further bit doubles the aggregate's passes over the records (key sub-ranges),
-    // so a table that the estimate fills to 0.7 is still the better deal
+    uint32_t bits = std::min(kUnitMaxBucketBits + kMaxSubBits, std::max(6u, ceil_log2((u_est + per - 1) / per)));
     if (bits > kUnitMaxBucketBits) {
         const uint64_t per7 = std::max<uint64_t>(1, (uint64_t)slots * 70 / 100);
         if (ceil_log2((u_est + per7 - 1) / per7) <= kUnitMaxBucketBits) bits = kUnitMaxBucketBits;
@@ -223,284 +248,192 @@ uint32_t auto_bucket_bits(const grmkm_ctx* c, uint32_t G) {
     return bits;
 }
 
-// sort columns (ukeys/uwords, n items, stride ucap) by key into kmers/matrix
-int sort_and_gather(grmkm_ctx* c, uint64_t U, uint32_t W, uint64_t ucap, uint32_t key_bits_total, bool keep_order,
-                    Launches& L) {
-    cudaStream_t st = c->stream;
-    ENSURE(c, c->kmers, U * 8);
-    ENSURE(c, c->matrix, (size_t)U * W * 8);
-    if (U == 0) return GRMKM_OK;
-    const uint32_t gblocks = (uint32_t)((U + 255) / 256);
-    if (keep_order) {
-        // identity order: reuse gather with idx = iota produced by a zero-pass "sort"
-        ENSURE(c, c->sidx_a, U * 4);
-        std::vector<uint32_t> iota;  // small helper path, only used with GRMKM_FLAG_HASH_ORDER
-        iota.resize(U);
-        for (uint64_t i = 0; i < U; ++i) iota[i] = (uint32_t)i;
-        CU_TRY(c, cudaMemcpyAsync(c->sidx_a.p, iota.data(), U * 4, cudaMemcpyHostToDevice, st));
-        CU_TRY(c, cudaStreamSynchronize(st));
-        k_gather<<<gblocks, 256, 0, st>>>((const unsigned long long*)c->ukeys.p, (const uint32_t*)c->sidx_a.p, U, W,
-                                          (const unsigned long long*)c->uwords.p, ucap,
-                                          (unsigned long long*)c->kmers.p, (unsigned long long*)c->matrix.p);
-        L.n++;
-        CU_TRY(c, cudaGetLastError());
-        return GRMKM_OK;
-    }
-    // ---- fast path: MSD partition + shared-memory sort fused with the gather
-    ENSURE(c, c->skeys, U * 8);
-    ENSURE(c, c->sidx_a, U * 4);
-    if (U <= 0xFFFFFFFFULL && !(c->cfg.flags & GRMKM_FLAG_RADIX_ORDER)) {
-        uint32_t pbits = std::min(key_bits_total, std::min(15u, ceil_log2((U + 4095) / 4096)));
-        const uint32_t Pn = 1u << pbits;
-        const uint32_t shift = key_bits_total - pbits;
-        ENSURE(c, c->hist, (size_t)std::max<uint32_t>(Pn, 1) * 8 * kCursorStride);
-        ENSURE(c, c->offsets2, (size_t)(Pn + 1) * 8);
-        uint64_t* d_scalars = (uint64_t*)c->scalars.p;
-        CU_TRY(c, cudaMemsetAsync(c->hist.p, 0, (size_t)Pn * 8, st));
-        CU_TRY(c, cudaMemsetAsync(d_scalars + S_WORK, 0, 8, st));
-        const uint32_t cgrid = (uint32_t)std::min<uint64_t>((U + 255) / 256, (uint64_t)c->sm_count * 8);
-        if (pbits == 0) {
-            const unsigned long long uu = U;   // one partition holds everything
-            CU_TRY(c, cudaMemcpyAsync(c->hist.p, &uu, 8, cudaMemcpyHostToDevice, st));
-        } else {
-            CU_TRY(c, cudaFuncSetAttribute(k_msd_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Pn * 4)));
-            k_msd_count<<<cgrid, 256, (size_t)Pn * 4, st>>>((const unsigned long long*)c->ukeys.p, U, shift, Pn,
-                                                           (unsigned long long*)c->hist.p);
-        }
-        k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->hist.p, (unsigned long long*)c->offsets2.p, Pn,
-                                             d_scalars, S_N_SOLID, 1);
-        k_msd_scatter<<<gblocks, 256, 0, st>>>((const unsigned long long*)c->ukeys.p, U, pbits ? shift : 64,
-                                               (unsigned long long*)c->hist.p, (unsigned long long*)c->skeys.p,
-                                               (uint32_t*)c->sidx_a.p);
-        const size_t lsm = (size_t)kLocalSortCap * 12;
-        CU_TRY(c, cudaFuncSetAttribute(k_local_sort_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
-        k_local_sort_gather<<<std::min<uint32_t>(Pn, (uint32_t)c->sm_count), kLocalSortThreads, lsm, st>>>(
-            (const unsigned long long*)c->skeys.p, (const uint32_t*)c->sidx_a.p, (const unsigned long long*)c->offsets2.p,
-            Pn, U, W, (const unsigned long long*)c->uwords.p, ucap, (unsigned long long*)c->kmers.p,
-            (unsigned long long*)c->matrix.p, (unsigned long long*)d_scalars);
-        L.n += 4;
-        CU_TRY(c, cudaGetLastError());
-        uint64_t overflow = 0;
-        CU_TRY(c, cudaMemcpyAsync(&overflow, d_scalars + S_WORK, 8, cudaMemcpyDeviceToHost, st));
-        CU_TRY(c, cudaStreamSynchronize(st));
-        if (!overflow) return GRMKM_OK;
-        // a partition did not fit shared memory (heavily skewed k-mer prefixes): radix sort below
-    }
-    const uint32_t n_seg = (uint32_t)((U + kSortSeg - 1) / kSortSeg);
-    const uint32_t sblocks = (n_seg + kSortWarps - 1) / kSortWarps;
-    ENSURE(c, c->sidx_b, U * 4);
-    ENSURE(c, c->shist, (size_t)256 * n_seg * 4);
-    const uint64_t hist_n = (uint64_t)256 * n_seg;
-    const uint32_t n_chunks = (uint32_t)((hist_n + kScanChunk - 1) / kScanChunk);
-    ENSURE(c, c->spart, (size_t)n_chunks * 4);
-    const uint32_t passes = (key_bits_total + 7) / 8;
-    unsigned long long* ka = (unsigned long long*)c->ukeys.p;
-    unsigned long long* kb = (unsigned long long*)c->skeys.p;
-    uint32_t* ia = nullptr;
-    uint32_t* ib = (uint32_t*)c->sidx_a.p;
-    uint32_t* ispare = (uint32_t*)c->sidx_b.p;
-    for (uint32_t pass = 0; pass < passes; ++pass) {
-        const uint32_t shift = pass * 8;
-        k_sort_hist<<<sblocks, kSortWarps * 32, 0, st>>>(ka, U, shift, n_seg, (uint32_t*)c->shist.p);
-        k_scan_u32_partial<<<n_chunks, 1024, 0, st>>>((const uint32_t*)c->shist.p, hist_n, (uint32_t*)c->spart.p);
-        k_scan_u32_mid<<<1, 1024, 0, st>>>((uint32_t*)c->spart.p, n_chunks);
-        k_scan_u32_final<<<n_chunks, 1024, 0, st>>>((uint32_t*)c->shist.p, hist_n, (const uint32_t*)c->spart.p);
-        k_sort_scatter<<<sblocks, kSortWarps * 32, 0, st>>>(ka, ia, U, shift, n_seg, (const uint32_t*)c->shist.p, kb, ib);
-        L.n += 5;
-        std::swap(ka, kb);
-        uint32_t* t = ia ? ia : ispare;
-        ia = ib; ib = t;
-    }
-    CU_TRY(c, cudaGetLastError());
-    k_gather<<<gblocks, 256, 0, st>>>(ka, ia, U, W, (const unsigned long long*)c->uwords.p, ucap,
-                                      (unsigned long long*)c->kmers.p, (unsigned long long*)c->matrix.p);
-    L.n++;
-    CU_TRY(c, cudaGetLastError());
-    return GRMKM_OK;
+struct InputTable {
+    uint32_t G = 0;
+    std::vector<uint32_t> first_file;      // [G + 1] (inputs sorted by row)
+    std::vector<uint64_t> row_bytes;       // [G]
+    uint64_t max_row = 0, in_bytes = 0;
+};
+
+// sorts the inputs by genome row (stable: the files of a row keep their order) and tabulates them
+InputTable tabulate_inputs(grmkm_ctx* c) {
+    InputTable t;
+    uint32_t maxrow = 0;
+    for (const Input& in : c->inputs) maxrow = std::max(maxrow, in.row + 1);
+    t.G = std::max(maxrow, c->n_genomes_decl);
+    if (abundance_build(c) && !(c->cfg.flags & GRMKM_FLAG_COUNTS))
+        std::stable_sort(c->inputs.begin(), c->inputs.end(), [](const Input& a, const Input& b) { return a.row < b.row; });
+    for (Input& in : c->inputs) if (!in.owned.empty()) in.host = in.owned.data();
+    t.first_file.assign(t.G + 1, 0);
+    t.row_bytes.assign(std::max(t.G, 1u), 0);
+    for (const Input& in : c->inputs) { t.first_file[in.row + 1]++; t.row_bytes[in.row] += in.len; t.in_bytes += in.len; }
+    for (uint32_t g = 0; g < t.G; ++g) t.first_file[g + 1] += t.first_file[g];
+    for (uint64_t b : t.row_bytes) t.max_row = std::max(t.max_row, b);
+    return t;
 }
+
+// the automatic bucket count of the inputs added so far (cfg.bucket_bits = 0); all ranks of a multi-GPU build agree on
+// the maximum of theirs before they build (grmkm_plan_bucket_bits / grmkm_set_bucket_bits)
+uint32_t auto_bucket_bits(grmkm_ctx* c, const InputTable& t) {
+    if (!abundance_build(c)) {
+        // the pan-genome of the context is estimated from the largest genome (1.9 x its text)
+        const uint64_t u_est = t.max_row + t.max_row * 9 / 10 + 1024;
+        return bits_for(u_est, table_slots(c, 2 * ((t.G + 63) / 64)));
+    }
+    uint64_t rb = 0; uint32_t rr = 1;
+    for (const Round& rd : plan_rounds(c, t.G, t.first_file, t.row_bytes)) { rb = std::max(rb, rd.bytes); rr = std::max(rr, rd.n_rows); }
+    return bits_for(rb / 4 + 1024, table_slots(c, (rr + 1) & ~1u));
+}
+
+// ------------------------------------------------------------------------------------------------
+// one pipeline pass over inputs [f0, f1): parse -> pack -> unit bounds -> unit scatter -> dedupe -> expand -> aggregate
+// ------------------------------------------------------------------------------------------------
+enum AggKind { AGG_FINAL = 4, AGG_PARTIAL = 5, AGG_ROUND = 6, AGG_COUNTS = 7 };
 
 int check_ctx(const grmkm_ctx* c) { return c ? GRMKM_OK : GRMKM_E_INVALID; }
 
-}  // namespace
+struct Geo {
+    uint32_t G = 0, W = 0;                   // genomes / matrix word rows of the whole build
+    uint32_t bucket_bits = 0, sub_bits = 0;  // hash buckets of the expansion, key sub-ranges of the aggregate
+    uint32_t B = 0, VB = 0;
+};
 
-// ------------------------------------------------------------------------------------------------
-extern "C" {
+struct Job {
+    uint32_t f0 = 0, f1 = 0;        // inputs
+    uint32_t row0 = 0, n_rows = 0;  // genome rows of the job (FileDesc.row = input row - row0)
+    AggKind agg = AGG_FINAL;
+    uint64_t max_row_bytes = 0;     // text of the job's largest genome row
+    // AGG_ROUND: where the round's records go
+    ulonglong2* round_out = nullptr;
+    uint64_t round_cap = 0;
+};
 
-int grmkm_abi_version(void) { return GRMKM_ABI_VERSION; }
+struct JobOut {
+    uint64_t sc[S_COUNT] = {0};
+    uint64_t ucap = 0;
+    uint64_t h2d = 0;
+    uint32_t launches = 0, MB = 0;
+    bool ordered = false;
+    bool round_full = false;        // AGG_ROUND: the output did not fit round_cap (nothing else is wrong)
+    std::vector<uint64_t> h_off;    // AGG_PARTIAL: offsets of the (virtual) bucket chunks
+};
 
-int grmkm_device_count(void) {
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
-    return n;
-}
-
-int grmkm_create(const grmkm_config* cfg, grmkm_ctx** out) {
-    if (!cfg || !out) return fail(nullptr, GRMKM_E_INVALID, "null argument");
-    *out = nullptr;
-    grmkm_config c{};
-    memcpy(&c, cfg, std::min<size_t>(sizeof c, cfg->struct_size ? cfg->struct_size : sizeof c));
-    if (c.k < 1 || c.k > 32)
-        return fail(nullptr, GRMKM_E_UNSUPPORTED_K, "k must be in 1..32 (got " + std::to_string(c.k) + ")");
-    if (c.min_abundance == 0) c.min_abundance = 1;
-    if (c.input_kind > GRMKM_FASTQ) return fail(nullptr, GRMKM_E_INVALID, "input_kind must be GRMKM_FASTA or GRMKM_FASTQ");
-    if (c.bucket_bits && (c.bucket_bits < 4 || c.bucket_bits > 15))
-        return fail(nullptr, GRMKM_E_INVALID, "bucket_bits must be 0 (auto) or 4..15");
-    int ndev = 0;
-    cudaError_t e = cudaGetDeviceCount(&ndev);
-    if (e != cudaSuccess || ndev == 0) {
-        cudaGetLastError();
-        return fail(nullptr, GRMKM_E_NO_DEVICE,
-                    std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "0 devices") +
-                        "); libgrmkm has no CPU fallback");
-    }
-    int dev = c.device;
-    if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
-    if (dev >= ndev) return fail(nullptr, GRMKM_E_INVALID, "device ordinal out of range");
-    if ((e = cudaSetDevice(dev)) != cudaSuccess)
-        return fail(nullptr, GRMKM_E_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
-    grmkm_ctx* x = new (std::nothrow) grmkm_ctx();
-    if (!x) return fail(nullptr, GRMKM_E_NOMEM, "out of host memory");
-    x->cfg = c;
-    x->device = dev;
-    cudaDeviceProp prop{};
-    if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) {
-        x->sm_count = prop.multiProcessorCount;
-        x->smem_optin = prop.sharedMemPerBlockOptin;
-    }
-    if (const char* bb = getenv("GRMKM_BATCH_BYTES")) { const long long v = atoll(bb); if (v > 0) x->batch_bytes = (uint64_t)v; }
-    if (c.stream) x->stream = (cudaStream_t)c.stream;
-    else {
-        if ((e = cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking)) != cudaSuccess) {
-            delete x;
-            return fail(nullptr, GRMKM_E_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+void add_stage_times(grmkm_ctx* c) {
+    if (!c->ev_ok) return;
+    float* t[] = {&c->times.h2d, &c->times.parse, &c->times.pack, &c->times.count, &c->times.bounds, &c->times.scatter,
+                  &c->times.abundance, &c->times.dedupe, &c->times.expand, &c->times.aggregate, &c->times.sort};
+    for (int i = 1; i < T_N; ++i) {
+        float v = 0.f;
+        const cudaError_t te = cudaEventElapsedTime(&v, c->ev[i - 1], c->ev[i]);
+        if (te != cudaSuccess) {
+            cudaGetLastError();
+            if (getenv("GRMKM_DEBUG")) fprintf(stderr, "grmkm: stage event %d: %s\n", i, cudaGetErrorString(te));
+            v = 0.f;
         }
-        x->own_stream = true;
+        *t[i - 1] += v;
     }
-    for (int i = 0; i < T_N; ++i) {
-        if (cudaEventCreate(&x->ev[i]) != cudaSuccess) { x->ev_ok = false; break; }
-        x->ev_ok = true;
-    }
-    *out = x;
-    return GRMKM_OK;
+    float tot = 0.f;
+    if (cudaEventElapsedTime(&tot, c->ev[T_START], c->ev[T_SORT]) == cudaSuccess) c->times.total += tot; else cudaGetLastError();
 }
 
-void grmkm_destroy(grmkm_ctx* c) {
-    if (!c) return;
-    cudaSetDevice(c->device);
-    if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);      // the clear for a next build may still be running
-    DevBuf* all[] = {&c->in, &c->files, &c->hdr0, &c->tile_file, &c->tile_pub, &c->tile_order,
-                     &c->fss, &c->codes, &c->valid, &c->hist, &c->offsets, &c->offsets2,
-                     &c->bcounts, &c->records, &c->records2, &c->ukeys, &c->uwords, &c->skeys, &c->sidx_a, &c->sidx_b,
-                     &c->shist, &c->kmers, &c->matrix, &c->scalars, &c->fmt, &c->synth, &c->owner_start, &c->refs, &c->spart, &c->stile_file, &c->bbase, &c->apub,
-                     &c->masks, &c->units, &c->ucur, &c->ubeg, &c->wu, &c->wide};
-    for (DevBuf* b : all) release(c, *b);
-    if (c->ev_ok) for (int i = 0; i < T_N; ++i) cudaEventDestroy(c->ev[i]);
-    if (c->host_res) cudaFreeHost(c->host_res);
-    if (c->aux_stream) {
-        cudaEventDestroy(c->ev_scattered); cudaEventDestroy(c->ev_cleared);
-        cudaStreamDestroy(c->aux_stream);
-    }
-    if (c->copy_stream) {
-        for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->ev_copied[i]); cudaEventDestroy(c->ev_free[i]); }
-        cudaStreamDestroy(c->copy_stream);
-    }
-    if (c->h_tab) cudaFreeHost(c->h_tab);
-    if (c->own_stream) cudaStreamDestroy(c->stream);
-    delete c;
-}
+// The column aggregate over bucketed wide records (final presence columns, partial columns, an abundance round or the
+// pooled count table), with its retry when the output guess was too small.  Leaves the scalars in out.sc.
+struct AggIn {
+    const unsigned long long* records; const unsigned long long* begin; const unsigned long long* end;
+    uint32_t wide_words, wide_stride, row_bits;     // record geometry
+    uint32_t cells, n_words;                        // table cells per slot, words per output column
+    AggKind agg;
+    uint32_t round_rows = 0, round_row0 = 0, out_wbits = 0, out_word = 0;
+    ulonglong2* round_out = nullptr;
+    uint64_t ucap_guess = 0;
+};
 
-const char* grmkm_last_error(const grmkm_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
-
-int grmkm_reset(grmkm_ctx* c) {
-    if (check_ctx(c)) return GRMKM_E_INVALID;
-    c->inputs.clear();
-    c->n_genomes_decl = 0;
-    c->built = false;
-    c->U = 0; c->W = 0; c->G = 0;
-    c->part_ranks = 0;
-    return GRMKM_OK;
-}
-
-int grmkm_add_genome_bytes(grmkm_ctx* c, uint32_t row, const uint8_t* data, uint64_t n) {
-    if (check_ctx(c)) return GRMKM_E_INVALID;
-    if (!data && n) return fail(c, GRMKM_E_INVALID, "null data");
-    Input in; in.row = row; in.kind = c->cfg.input_kind; in.host = data; in.len = n;
-    c->inputs.push_back(std::move(in));
-    c->built = false;
-    return GRMKM_OK;
-}
-
-int grmkm_add_genome_device(grmkm_ctx* c, uint32_t row, const void* dev_data, uint64_t n) {
-    if (check_ctx(c)) return GRMKM_E_INVALID;
-    if (!dev_data && n) return fail(c, GRMKM_E_INVALID, "null data");
-    if ((uintptr_t)dev_data & 15) return fail(c, GRMKM_E_INVALID, "device input must be 16-byte aligned");
-    Input in; in.row = row; in.kind = c->cfg.input_kind; in.dev = (const uint8_t*)dev_data; in.len = n;
-    c->inputs.push_back(std::move(in));
-    c->built = false;
-    return GRMKM_OK;
-}
-
-int grmkm_add_genomes(grmkm_ctx* c, uint32_t n, const uint32_t* rows, const void* const* data, const uint64_t* lens,
-                      int on_device) {
-    if (check_ctx(c)) return GRMKM_E_INVALID;
-    if (n && (!rows || !data || !lens)) return fail(c, GRMKM_E_INVALID, "null input list");
-    c->inputs.reserve(c->inputs.size() + n);
-    for (uint32_t i = 0; i < n; ++i) {
-        const int r = on_device ? grmkm_add_genome_device(c, rows[i], data[i], lens[i])
-                                : grmkm_add_genome_bytes(c, rows[i], (const uint8_t*)data[i], lens[i]);
-        if (r) return r;
-    }
-    return GRMKM_OK;
-}
-
-int grmkm_add_genome_files(grmkm_ctx* c, uint32_t row, const char* const* paths, int n_paths) {
-    if (check_ctx(c)) return GRMKM_E_INVALID;
-    if (n_paths < 0 || (!paths && n_paths)) return fail(c, GRMKM_E_INVALID, "bad path list");
-    for (int i = 0; i < n_paths; ++i) {
-        Input in; in.row = row; in.kind = c->cfg.input_kind;
-        int r = read_file(c, paths[i], in.owned);
-        if (r) return r;
-        in.len = in.owned.size();
-        c->inputs.push_back(std::move(in));
-        c->inputs.back().host = c->inputs.back().owned.data();
-    }
-    c->built = false;
-    return GRMKM_OK;
-}
-
-int grmkm_set_genome_count(grmkm_ctx* c, uint32_t n) {
-    if (check_ctx(c)) return GRMKM_E_INVALID;
-    c->n_genomes_decl = n;
-    return GRMKM_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-// the build
-// ------------------------------------------------------------------------------------------------
-static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32_t n_ranges) {
-    CU_TRY(c, cudaSetDevice(c->device));
+int run_aggregate(grmkm_ctx* c, const Geo& geo, const AggIn& in, JobOut& out, bool& retry_outer,
+                  const std::function<int(const uint64_t*)>& check_upstream) {
     cudaStream_t st = c->stream;
-    Launches L;
-    c->built = false;
-    c->stats = grmkm_stats{};
-    c->times = grmkm_times{};
-
-    Plan P;
-    P.F = (uint32_t)c->inputs.size();
-    uint32_t maxrow = 0;
-    for (const Input& in : c->inputs) maxrow = std::max(maxrow, in.row + 1);
-    P.G = std::max(maxrow, c->n_genomes_decl);
-    P.W = (P.G + 63) / 64;
-    c->G = P.G; c->W = P.W; c->U = 0;
-    c->part_ranks = 0; c->part_total = 0; c->part_words = P.W;
-    if (P.G == 0 || P.F == 0) {
-        c->built = (mode == 0);
-        c->stats.n_genomes = P.G; c->stats.n_words = P.W;
-        if (mode == 1) { c->part_ranks = n_ranges; c->part_counts.assign(n_ranges, 0); }
-        return GRMKM_OK;
+    uint64_t* d_scalars = (uint64_t*)c->scalars.p;
+    const uint32_t slots = table_slots(c, in.cells);
+    if (slots < 256) return fail(c, GRMKM_E_UNSUPPORTED, "too many genomes for the shared-memory column table");
+    const size_t smem = table_smem(slots, in.cells);
+    const uint32_t VB = geo.VB;
+    const uint32_t vgrid = std::min<uint32_t>(VB, (uint32_t)c->sm_count * kAggCtasPerSm);
+    const bool final_like = in.agg == AGG_FINAL || in.agg == AGG_COUNTS;
+    const bool ordered = final_like && !getenv("GRMKM_UNORDERED");
+    out.ordered = ordered;
+    // (an abundance round writes behind the earlier rounds' records: its capacity is what is left, possibly nothing)
+    uint64_t ucap = std::min<uint64_t>(in.agg == AGG_ROUND ? in.ucap_guess : std::max<uint64_t>(in.ucap_guess, 1), 0xFFFFFFFFULL);
+    ENSURE(c, c->bbase, (size_t)VB * 8);
+    ENSURE(c, c->bcounts, (size_t)VB * 8);
+    if (ordered) ENSURE(c, c->apub, (size_t)(VB + 1) * 8);
+    retry_outer = false;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (in.agg == AGG_ROUND) {
+            // the records go straight behind the earlier rounds' (the caller grows that buffer when a round does not fit)
+        } else if (ordered) {
+            // the columns land at their final place: k-mers and word row 0 in the result arrays, rows >= 1 at stride ucap
+            ENSURE(c, c->kmers, ucap * 8);
+            ENSURE(c, c->matrix, (size_t)ucap * in.n_words * 8);
+            if (in.n_words > 1) ENSURE(c, c->uwords, (size_t)ucap * in.n_words * 8);
+            CU_TRY(c, cudaMemsetAsync(c->apub.p, 0, (size_t)(VB + 1) * 8, st));
+        } else {
+            ENSURE(c, c->ukeys, ucap * 8);
+            ENSURE(c, c->uwords, (size_t)ucap * in.n_words * 8);
+        }
+        AggParams2 ap{};
+        ap.records = in.records; ap.begin = in.begin; ap.end = in.end; ap.bucket_bits = geo.bucket_bits;
+        ap.row_bits = in.row_bits; ap.n_words = in.n_words; ap.slots = slots;
+        ap.keep_singletons = c->cfg.keep_singletons; ap.sub_bits = geo.sub_bits;
+        ap.wide_words = in.wide_words; ap.wide_stride = in.wide_stride; ap.table_u32 = in.cells;
+        ap.out_keys = (unsigned long long*)c->ukeys.p; ap.out_words = (unsigned long long*)c->uwords.p;
+        ap.cap = ucap; ap.scalars = (unsigned long long*)d_scalars;
+        ap.bucket_base = (unsigned long long*)c->bbase.p; ap.bucket_count = (unsigned long long*)c->bcounts.p;
+        ap.b_begin = 0; ap.b_end = geo.B;
+        ap.min_abundance = c->cfg.min_abundance; ap.round_rows = in.round_rows; ap.round_row0 = in.round_row0;
+        ap.out_wbits = in.out_wbits; ap.out_word = in.out_word; ap.out_wide = in.round_out;
+        if (ordered) {
+            ap.ordered = 1;
+            ap.out_keys = (unsigned long long*)c->kmers.p; ap.out_row0 = (unsigned long long*)c->matrix.p;
+            ap.pub = (unsigned long long*)c->apub.p; ap.ticket = (unsigned int*)((unsigned long long*)c->apub.p + VB);
+        }
+        void (*kern)(AggParams2) = in.agg == AGG_FINAL ? k_aggregate_cols<4> : in.agg == AGG_PARTIAL ? k_aggregate_cols<5>
+                                   : in.agg == AGG_ROUND ? k_aggregate_cols<6> : k_aggregate_cols<7>;
+        CU_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<vgrid, kAggThreads, smem, st>>>(ap);
+        out.launches++;
+        CU_TRY(c, cudaGetLastError());
+        if (ordered) {
+            // rows >= 1 move from stride ucap to the result's stride U (row 0 and the k-mers are already in place); U is read
+            // on the device, so the build ends with this one synchronisation
+            if (c->ev_ok) cudaEventRecord(c->ev[T_AGG], st);
+            if (in.n_words > 1) {
+                k_move_rows<<<(uint32_t)c->sm_count * 8, 256, 0, st>>>((const unsigned long long*)c->uwords.p, ucap, (unsigned long long*)c->matrix.p,
+                                                                      (const unsigned long long*)(d_scalars + S_U_NEEDED), in.n_words);
+                out.launches++;
+                CU_TRY(c, cudaGetLastError());
+            }
+        }
+        CU_TRY(c, cudaMemcpyAsync(out.sc, d_scalars, sizeof out.sc, cudaMemcpyDeviceToHost, st));
+        CU_TRY(c, cudaStreamSynchronize(st));
+        const int up = check_upstream(out.sc);          // 1: an upstream guess was too small, the caller repeats the round
+        if (up < 0) return up;
+        if (up > 0) { retry_outer = true; break; }
+        if (out.sc[S_U_NEEDED] <= ucap) break;
+        if (in.agg == AGG_ROUND) { out.round_full = true; break; }
+        if (attempt == 1 || out.sc[S_U_NEEDED] > 0xFFFFFFFFULL)
+            return fail(c, GRMKM_E_UNSUPPORTED, "more than 2^32 columns in one context");
+        ucap = out.sc[S_U_NEEDED];
+        const uint64_t zero3[3] = {0, 0, 0};
+        CU_TRY(c, cudaMemcpyAsync(d_scalars + S_U_NEEDED, zero3, 3 * 8, cudaMemcpyHostToDevice, st));     // + S_N_DISTINCT, S_N_SPLITS
+        CU_TRY(c, cudaStreamSynchronize(st));           // zero3 lives on this stack frame
     }
-    P.row_bits = std::max(1u, ceil_log2(P.G));
-    if (P.row_bits > 15) return fail(c, GRMKM_E_UNSUPPORTED, "more than 32768 genomes in one context");
+    out.ucap = ucap;
+    return GRMKM_OK;
+}
+
+int run_job(grmkm_ctx* c, const Geo& geo, const Job& job, JobOut& out) {
+    cudaStream_t st = c->stream;
+    const bool counting = job.agg == AGG_ROUND || job.agg == AGG_COUNTS;
+    const uint32_t B = geo.B;
 
     // ---- batches.  Host inputs are staged batch by batch on a copy stream (two staging halves), so that the
     // H2D copy of batch i+1 overlaps parse / pack / scatter of batch i; the scatter appends to the bucket
@@ -510,12 +443,16 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
     // stream entries reserved for a file: every byte yields at most one entry; files start on group boundaries
     auto stream_cap = [](uint64_t len) { return ((len + 31) & ~31ULL) + 32; };
     bool any_host = false;
-    for (const Input& in : c->inputs) { P.max_stream += stream_cap(in.len); P.in_bytes += in.len; any_host = any_host || !in.dev; }
+    uint64_t max_stream = 0, in_bytes = 0;
+    for (uint32_t f = job.f0; f < job.f1; ++f) {
+        const Input& in = c->inputs[f];
+        max_stream += stream_cap(in.len); in_bytes += in.len; any_host = any_host || !in.dev;
+    }
     auto make_batches = [&](bool pipelined) {
         std::vector<Batch> v;
         const uint64_t target = pipelined ? c->batch_bytes : ~0ULL;
-        Batch cur{0, 0, 0, 0, 0, 0};
-        for (uint32_t f = 0; f < P.F; ++f) {
+        Batch cur{job.f0, job.f0, 0, 0, 0, 0};
+        for (uint32_t f = job.f0; f < job.f1; ++f) {
             const Input& in = c->inputs[f];
             if (cur.f1 > cur.f0 && cur.bytes + in.len > target) { v.push_back(cur); cur = Batch{f, f, 0, 0, 0, 0}; }
             cur.f1 = f + 1; cur.bytes += in.len; cur.stream += stream_cap(in.len);
@@ -526,28 +463,6 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         return v;
     };
 
-    // ---- aggregate table geometry and bucket count
-    const uint32_t Wtab = P.W;
-    const size_t budget = agg_smem_budget(c);
-    P.slots = table_slots(c, Wtab);
-    if (P.slots < 256) return fail(c, GRMKM_E_UNSUPPORTED, "too many genomes for the shared-memory column table");
-    P.agg_smem = table_smem(P.slots, Wtab);
-    // the unit path (below) carries a genome GROUP in its records, not a row, and its expansion sorts tiles over at most
-    // 2^11 buckets: more distinct k-mers than 2^11 tables hold are handled as key sub-ranges of the buckets (virtual
-    // buckets: one aggregate pass each over the bucket's records, which stay in L2), and beyond 2^14 by the table's own
-    // overflow split -- instead of falling off to the per-record scatter
-    const bool units_ok = units_wanted(c);
-    P.bucket_bits = c->cfg.bucket_bits ? c->cfg.bucket_bits : auto_bucket_bits(c, P.G);
-    if (!units_ok) P.bucket_bits = std::max(P.bucket_bits, P.row_bits);
-    if (P.bucket_bits > 15) return fail(c, GRMKM_E_UNSUPPORTED, "bucket_bits > 15");
-    if (const char* sbv = getenv("GRMKM_SUB_BITS")) P.sub_bits = (uint32_t)std::min(3, std::max(0, atoi(sbv)));
-    if (units_ok && P.bucket_bits > kUnitMaxBucketBits) {
-        P.sub_bits = std::max(P.sub_bits, std::min(3u, P.bucket_bits - kUnitMaxBucketBits));
-        P.bucket_bits = kUnitMaxBucketBits;
-    }
-    c->cur_bucket_bits = P.bucket_bits;
-    const uint32_t B = 1u << P.bucket_bits;
-
     ENSURE(c, c->scalars, S_COUNT * 8);
     ENSURE(c, c->hist, (size_t)B * 8 * kCursorStride);
     ENSURE(c, c->offsets, (size_t)(B + 1) * 8);
@@ -556,8 +471,6 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
 
     if (c->ev_ok) cudaEventRecord(c->ev[T_START], st);
     CU_TRY(c, cudaMemsetAsync(c->scalars.p, 0, S_COUNT * 8, st));
-    uint64_t h2d = 0;
-
 
     // parse + pack of one batch: leaves codes / valid / fss / S_STREAM_LEN of the batch
     auto front = [&](const Batch& bt, const uint8_t* staged_base, bool timed) -> int {
@@ -602,7 +515,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         std::vector<std::pair<uint64_t, uint32_t>> by_tiles(F);       // (tile count, file), most tiles first
         for (uint32_t i = 0; i < F; ++i) {
             const Input& in = c->inputs[bt.f0 + i];
-            fds[i].len = in.len; fds[i].row = in.row; fds[i].kind = in.kind; fds[i].tile_begin = tiles;
+            fds[i].len = in.len; fds[i].row = in.row - job.row0; fds[i].kind = in.kind; fds[i].tile_begin = tiles;
             const uint64_t nt = std::max<uint64_t>(1, (in.len + kTileBytes - 1) / kTileBytes);
             by_tiles[i] = {nt, i};
             tiles += nt;
@@ -628,7 +541,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         k_first_header<<<(F * 32 + 255) / 256, 256, 0, st>>>(d_files, F, (uint64_t*)c->hdr0.p);
         k_tile_tickets<<<(uint32_t)((n_tiles + 255) / 256), 256, 0, st>>>(d_files, F, (const uint64_t*)c->hdr0.p, (const uint64_t*)c->fss.p,
                                                                            (const uint32_t*)c->tile_order.p, n_tiles, (TileTicket*)c->tile_file.p);
-        L.n += 2;
+        out.launches += 2;
         CU_TRY(c, cudaGetLastError());
         if (timed && c->ev_ok) cudaEventRecord(c->ev[T_PARSE], st);
         // single pass: summaries are published and resolved by look-back inside k_pack (grmkm_kernels.cuh)
@@ -640,29 +553,25 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         pp.codes = (unsigned long long*)c->codes.p; pp.valid = (uint32_t*)c->valid.p; pp.scalars = d_scalars;
         if (c->cfg.input_kind == GRMKM_FASTA) k_pack<0><<<(uint32_t)n_tiles, kParseThreads, 0, st>>>(pp);
         else k_pack<1><<<(uint32_t)n_tiles, kParseThreads, 0, st>>>(pp);
-        L.n++;
+        out.launches++;
         CU_TRY(c, cudaGetLastError());
         if (timed && c->ev_ok) cudaEventRecord(c->ev[T_PACK], st);
         return GRMKM_OK;
     };
 
-    // ---- extract + scatter, (abundance), aggregate.  Pass 0 scatters into over-provisioned bucket regions
-    // without a count pass; if a region overflows (heavily skewed k-mer spectrum) pass 1 redoes the
-    // scatter with exact offsets from a count pass.
-    const bool staged = B <= (uint32_t)kStMaxBuckets && !(c->cfg.flags & GRMKM_FLAG_SIMPLE_SCATTER);
-    // ---- unit (super-k-mer) path: contigs and reads without an abundance filter (grmkm_units.cuh)
-    const bool use_units = staged && c->cfg.min_abundance <= 1 && !(c->cfg.flags & GRMKM_FLAG_KMER_RECORDS);
+    // ---- unit (super-k-mer) geometry (grmkm_units.cuh).  Presence: a dedupe entry / wide record holds WB presence
+    // words of one genome group.  Abundance: the "group" is the job-local genome row and the word a count.
     const UnitGeom ug = unit_geom(c->cfg.k);
-    const uint32_t WB = unit_words_per_entry(P.W);            // presence words per dedupe entry / wide record
-    const uint32_t wbits = std::max(1u, ceil_log2((P.W + WB - 1) / WB));
+    const uint32_t WB = counting ? 1u : unit_words_per_entry(geo.W);
+    const uint32_t n_groups_w = counting ? std::max(1u, job.n_rows) : (geo.W + WB - 1) / WB;
+    const uint32_t wbits = std::max(1u, ceil_log2(n_groups_w));
+    if (wbits > geo.bucket_bits) return fail(c, GRMKM_E_UNSUPPORTED, "more genome groups than hash buckets");
     const uint32_t ES = 2 + WB, RS = unit_record_stride(WB);
     uint32_t MB = (uint32_t)c->sm_count;
-    if (use_units) {
-        // distinct (unit, 64-genome block) entries of a bucket should fit the dedupe table about once
-        std::vector<uint64_t> row_bytes(std::max(P.G, 1u), 0);
-        for (const Input& in : c->inputs) if (in.row < P.G) row_bytes[in.row] += in.len;
-        const uint64_t max_row = *std::max_element(row_bytes.begin(), row_bytes.end());
-        const uint64_t entries = (max_row * 19 / 10) * 2 / (ug.w + 1) * 13 / 10 * ((P.W + WB - 1) / WB);
+    {
+        // distinct (unit, genome group) entries of a bucket should fit the dedupe table about once
+        const uint64_t entries = counting ? in_bytes / (ug.w + 1) / 2 + 1
+                                          : (job.max_row_bytes * 19 / 10) * 2 / (ug.w + 1) * 13 / 10 * n_groups_w;
         const uint64_t per_wave = (uint64_t)unit_dedupe_slots(WB) * 6 / 10 * c->sm_count;
         const uint64_t waves = std::max<uint64_t>(1, (entries + per_wave - 1) / per_wave);
         MB = (uint32_t)std::min<uint64_t>(kUsMaxBuckets, waves * c->sm_count);
@@ -670,15 +579,12 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
         ENSURE(c, c->ucur, (size_t)MB * 8);
         ENSURE(c, c->ubeg, (size_t)(MB + 1) * 8);
     }
-    const bool try_regions = staged && !(c->cfg.flags & GRMKM_FLAG_EXACT_OFFSETS);
-    const uint32_t agrid = std::min<uint32_t>(B, (uint32_t)c->sm_count * kAggCtasPerSm);
-    const uint32_t VB = B << P.sub_bits;            // virtual buckets of the column aggregate
-    const uint32_t vgrid = std::min<uint32_t>(VB, (uint32_t)c->sm_count * kAggCtasPerSm);
-    // final build in hash order: the aggregate writes the columns at their final place (no gather pass)
-    const bool ordered = mode == 0 && !(c->cfg.flags & GRMKM_FLAG_KMER_ORDER) && !getenv("GRMKM_UNORDERED");
-    uint64_t sc[S_COUNT];
-    uint64_t ucap = 0;
+    out.MB = MB;
+    const bool try_regions = !getenv("GRMKM_EXACT_OFFSETS");
+    uint64_t* sc = out.sc;
     for (int pass = try_regions ? 0 : 1; pass < 2; ++pass) {
+        // Pass 0 scatters into over-provisioned bucket regions without a count pass; if a region overflows (heavily
+        // skewed unit spectrum) pass 1 redoes the scatter with exact offsets from a count pass.
         const bool regions = (pass == 0);
         c->pass_groups = 0; c->pass_pub_bytes = 0;
         const std::vector<Batch> batches = make_batches(regions && any_host);
@@ -697,21 +603,13 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
             c->h_tab_used = 0;
         }
         uint64_t cap = 0;
-        if (use_units) {
-            if (regions) {
-                const double est_units = (double)P.max_stream * 2.0 / (ug.w + 1) * 1.15;
-                cap = (uint64_t)(est_units / MB * 1.25) + 4096;
-                cap = (cap + 15) & ~15ULL;
-                ENSURE(c, c->units, ((uint64_t)MB * cap + kUsStage) * 16);
-            } else {
-                ENSURE(c, c->units, (P.max_stream + kUsStage) * 16);
-            }
-        } else if (regions) {
-            cap = (uint64_t)((double)P.max_stream / B * 1.25) + 2048;
+        if (regions) {
+            const double est_units = (double)max_stream * 2.0 / (ug.w + 1) * 1.15;
+            cap = (uint64_t)(est_units / MB * 1.25) + 4096;
             cap = (cap + 15) & ~15ULL;
-            ENSURE(c, c->records, ((uint64_t)B * cap + kStTile) * 8);
+            ENSURE(c, c->units, ((uint64_t)MB * cap + kUsStage) * 16);
         } else {
-            ENSURE(c, c->records, P.max_stream * 8);
+            ENSURE(c, c->units, (max_stream + kUsStage) * 16);
         }
         uint64_t half_bytes = 0;
         for (const Batch& bt : batches) half_bytes = std::max(half_bytes, bt.staged);
@@ -723,22 +621,14 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
                 CU_TRY(c, cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
             }
         }
-        {
-            const uint64_t zeros[S_COUNT] = {0};
-            CU_TRY(c, cudaMemcpyAsync(d_scalars, zeros, S_COUNT * 8, cudaMemcpyHostToDevice, st));
-        }
+        CU_TRY(c, cudaMemsetAsync(d_scalars, 0, S_COUNT * 8, st));
         if (regions) {
-            if (use_units)
-                k_init_regions<<<(MB + 1 + 255) / 256, 256, 0, st>>>((unsigned long long*)c->ubeg.p,
-                                                                     (unsigned long long*)c->ucur.p, MB, cap);
-            else
-                k_init_regions<<<(B + 1 + 255) / 256, 256, 0, st>>>((unsigned long long*)c->offsets.p,
-                                                                    (unsigned long long*)c->hist.p, B, cap);
-            L.n++;
+            k_init_regions<<<(MB + 1 + 255) / 256, 256, 0, st>>>((unsigned long long*)c->ubeg.p, (unsigned long long*)c->ucur.p, MB, cap);
+            out.launches++;
         }
         if (pipelined && c->ev_ok)
             for (int e : {T_H2D, T_PARSE, T_PACK, T_COUNT, T_BOUNDS}) cudaEventRecord(c->ev[e], st);   // stages interleave: only "scatter" is timed
-        h2d = 0;
+        out.h2d = 0;
         for (size_t bi = 0; bi < batches.size(); ++bi) {
             const Batch& bt = batches[bi];
             uint8_t* half = (uint8_t*)c->in.p + (pipelined ? (bi & 1) * half_bytes : 0);
@@ -748,7 +638,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
             for (uint32_t f = bt.f0; f < bt.f1; ++f) {
                 const Input& in = c->inputs[f];
                 if (in.dev) continue;
-                if (in.len) { CU_TRY(c, cudaMemcpyAsync(half + soff, in.host, in.len, cudaMemcpyHostToDevice, cs)); h2d += in.len; }
+                if (in.len) { CU_TRY(c, cudaMemcpyAsync(half + soff, in.host, in.len, cudaMemcpyHostToDevice, cs)); out.h2d += in.len; }
                 soff += (in.len + 15) & ~15ULL;
             }
             if (pipelined) {
@@ -761,119 +651,54 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
 
             const uint32_t F = bt.f1 - bt.f0;
             const uint64_t n_groups_max = bt.stream / 32 + 2;
-            const uint64_t n_stiles = (n_groups_max + (kStTile / 32) - 1) / (kStTile / 32);
-            if (use_units) {
-                ENSURE(c, c->masks, n_groups_max * 8);
-                const uint64_t n_utiles = (n_groups_max + kUsTileGroups - 1) / kUsTileGroups;
-                ENSURE(c, c->stile_file, n_utiles * 4);
-                if (!pipelined && c->ev_ok) cudaEventRecord(c->ev[T_COUNT], st);
-                const uint32_t bgrid = (uint32_t)((n_groups_max + 511) / 512);       // two groups per thread
+            ENSURE(c, c->masks, n_groups_max * 8);
+            const uint64_t n_utiles = (n_groups_max + kUsTileGroups - 1) / kUsTileGroups;
+            ENSURE(c, c->stile_file, n_utiles * 4);
+            if (!pipelined && c->ev_ok) cudaEventRecord(c->ev[T_COUNT], st);
+            const uint32_t bgrid = (uint32_t)((n_groups_max + 511) / 512);       // two groups per thread
 #define GRMKM_BOUNDS(WW)                                                                                        \
     k_unit_bounds<WW><<<bgrid, 256, 0, st>>>((const unsigned long long*)c->codes.p, (const uint32_t*)c->valid.p, d_scalars, \
                                              ug.k, ug.m, (uint2*)c->masks.p)
-                switch (ug.w) {
-                    case 21: GRMKM_BOUNDS(21); break;
-                    case 13: GRMKM_BOUNDS(13); break;
-                    case 7: GRMKM_BOUNDS(7); break;
-                    case 4: GRMKM_BOUNDS(4); break;
-                    case 2: GRMKM_BOUNDS(2); break;
-                    default: GRMKM_BOUNDS(1); break;
-                }
+            switch (ug.w) {
+                case 21: GRMKM_BOUNDS(21); break;
+                case 13: GRMKM_BOUNDS(13); break;
+                case 7: GRMKM_BOUNDS(7); break;
+                case 4: GRMKM_BOUNDS(4); break;
+                case 2: GRMKM_BOUNDS(2); break;
+                default: GRMKM_BOUNDS(1); break;
+            }
 #undef GRMKM_BOUNDS
-                k_stream_tile_files<<<(uint32_t)((n_utiles + 255) / 256), 256, 0, st>>>(
-                    d_scalars, (const uint64_t*)c->fss.p, F, (uint32_t*)c->stile_file.p, n_utiles, (uint64_t)kUsTileGroups * 32);
-                L.n += 2;
-                CU_TRY(c, cudaGetLastError());
-                if (!pipelined && c->ev_ok) cudaEventRecord(c->ev[T_BOUNDS], st);
-                UnitScatterParams up{};
-                up.codes = (const unsigned long long*)c->codes.p; up.masks = (const uint2*)c->masks.p; up.scalars = d_scalars;
-                up.file_stream_start = (const uint64_t*)c->fss.p; up.files = d_files; up.tile_file = (const uint32_t*)c->stile_file.p;
-                up.n_files = F; up.k = ug.k; up.lmax = ug.lmax; up.n_buckets = MB;
-                up.cursors = (unsigned long long*)c->ucur.p; up.units = (uint4*)c->units.p; up.cap = cap;
-                up.dump = (uint64_t)MB * cap; up.overflow = (unsigned long long*)(d_scalars + S_OVERFLOW);
-                up.n_windows = (unsigned long long*)(d_scalars + S_N_WINDOWS);
-                const size_t usm = unit_scatter_smem(MB);
-                const uint32_t ugrid = (uint32_t)std::min<uint64_t>(n_utiles, (uint64_t)c->sm_count);
-                if (!regions) {
-                    CU_TRY(c, cudaMemsetAsync(c->ucur.p, 0, (size_t)MB * 8, st));
-                    CU_TRY(c, cudaFuncSetAttribute(k_units_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usm));
-                    k_units_scatter<true><<<ugrid, kUsThreads, usm, st>>>(up);
-                    k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->ucur.p, (unsigned long long*)c->ubeg.p, MB,
-                                                         d_scalars, S_N_UNITS, 1);
-                    L.n += 2;
-                }
-                CU_TRY(c, cudaFuncSetAttribute(k_units_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usm));
-                k_units_scatter<false><<<ugrid, kUsThreads, usm, st>>>(up);
-                L.n++;
-                CU_TRY(c, cudaGetLastError());
-                continue;
-            }
-            ExtractParams ep{};
-            ep.codes = (const unsigned long long*)c->codes.p;
-            ep.valid = (const uint32_t*)c->valid.p;
-            ep.scalars = d_scalars;
-            ep.file_stream_start = (const uint64_t*)c->fss.p;
-            ep.files = d_files;
-            ep.n_files = F;
-            ep.k = c->cfg.k;
-            ep.bucket_bits = P.bucket_bits;
-            ep.row_bits = P.row_bits;
-            ep.hist = (unsigned long long*)c->hist.p;
-            ep.records = (unsigned long long*)c->records.p;
-            ep.dbg = 0;
-            ep.offsets = (const unsigned long long*)c->offsets.p;
-            const uint64_t n_etiles_max = (n_groups_max + kExtractThreads - 1) / kExtractThreads;
-            const uint32_t egrid = (uint32_t)std::min<uint64_t>(n_etiles_max, (uint64_t)c->sm_count * 8);
-            if (!regions) {
-                CU_TRY(c, cudaMemsetAsync(c->hist.p, 0, (size_t)B * 8, st));
-                const size_t hist_smem = (size_t)B * 4;
-                CU_TRY(c, cudaFuncSetAttribute(k_extract<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
-                k_extract<0><<<egrid, kExtractThreads, hist_smem, st>>>(ep);
-                k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->hist.p, (unsigned long long*)c->offsets.p, B,
-                                                     d_scalars, S_N_WINDOWS, kCursorStride);
-                L.n += 2;
-            }
+            k_stream_tile_files<<<(uint32_t)((n_utiles + 255) / 256), 256, 0, st>>>(
+                d_scalars, (const uint64_t*)c->fss.p, F, (uint32_t*)c->stile_file.p, n_utiles, (uint64_t)kUsTileGroups * 32);
+            out.launches += 2;
             CU_TRY(c, cudaGetLastError());
-            if (!pipelined && c->ev_ok) { cudaEventRecord(c->ev[T_COUNT], st); cudaEventRecord(c->ev[T_BOUNDS], st); }
-            if (staged) {
-                ENSURE(c, c->stile_file, n_stiles * 4);
-                ScatterParams sp{};
-                sp.codes = ep.codes; sp.valid = ep.valid; sp.scalars = d_scalars; sp.file_stream_start = ep.file_stream_start;
-                sp.files = d_files; sp.tile_file = (const uint32_t*)c->stile_file.p; sp.n_files = F; sp.k = c->cfg.k;
-                sp.bucket_bits = P.bucket_bits; sp.row_bits = P.row_bits; sp.cursors = (unsigned long long*)c->hist.p;
-                sp.records = (unsigned long long*)c->records.p; sp.cap = cap; sp.dump = (uint64_t)B * cap;
-                sp.overflow = (unsigned long long*)(d_scalars + S_OVERFLOW);
-                k_scatter_tile_files<<<(uint32_t)((n_stiles + 255) / 256), 256, 0, st>>>(d_scalars, sp.file_stream_start, F,
-                                                                                      (uint32_t*)c->stile_file.p, n_stiles);
-                const size_t ssm = staged_smem_bytes(B);
-                const uint32_t sgrid = (uint32_t)std::min<uint64_t>(n_stiles, (uint64_t)c->sm_count);
-#define GRMKM_SCATTER(KT)                                                                                       \
-    do {                                                                                                        \
-        CU_TRY(c, cudaFuncSetAttribute(k_scatter<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));  \
-        k_scatter<KT><<<sgrid, kStThreads, ssm, st>>>(sp);                                                      \
-    } while (0)
-                switch (c->cfg.k) {
-                    case 31: GRMKM_SCATTER(31); break;
-                    case 21: GRMKM_SCATTER(21); break;
-                    case 15: GRMKM_SCATTER(15); break;
-                    default: GRMKM_SCATTER(0); break;
-                }
-#undef GRMKM_SCATTER
-                L.n += 2;
-            } else {
-                k_extract<1><<<egrid, kExtractThreads, 0, st>>>(ep);
-                L.n++;
+            if (!pipelined && c->ev_ok) cudaEventRecord(c->ev[T_BOUNDS], st);
+            UnitScatterParams up{};
+            up.codes = (const unsigned long long*)c->codes.p; up.masks = (const uint2*)c->masks.p; up.scalars = d_scalars;
+            up.file_stream_start = (const uint64_t*)c->fss.p; up.files = d_files; up.tile_file = (const uint32_t*)c->stile_file.p;
+            up.n_files = F; up.k = ug.k; up.lmax = ug.lmax; up.n_buckets = MB;
+            up.cursors = (unsigned long long*)c->ucur.p; up.units = (uint4*)c->units.p; up.cap = cap;
+            up.dump = (uint64_t)MB * cap; up.overflow = (unsigned long long*)(d_scalars + S_OVERFLOW);
+            up.n_windows = (unsigned long long*)(d_scalars + S_N_WINDOWS);
+            const size_t usm = unit_scatter_smem(MB);
+            const uint32_t ugrid = (uint32_t)std::min<uint64_t>(n_utiles, (uint64_t)c->sm_count);
+            if (!regions) {
+                CU_TRY(c, cudaMemsetAsync(c->ucur.p, 0, (size_t)MB * 8, st));
+                CU_TRY(c, cudaFuncSetAttribute(k_units_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usm));
+                k_units_scatter<true><<<ugrid, kUsThreads, usm, st>>>(up);
+                k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->ucur.p, (unsigned long long*)c->ubeg.p, MB,
+                                                     d_scalars, S_N_UNITS, 1);
+                out.launches += 2;
             }
+            CU_TRY(c, cudaFuncSetAttribute(k_units_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usm));
+            k_units_scatter<false><<<ugrid, kUsThreads, usm, st>>>(up);
+            out.launches++;
             CU_TRY(c, cudaGetLastError());
         }
-        // bucket b = records[begin[b], end[b]): begin = offsets, end = the cursors (clamped to the region)
-        if (use_units)
-            k_finish_unit_regions<<<1, 1024, 0, st>>>((const unsigned long long*)c->ubeg.p, (unsigned long long*)c->ucur.p, MB,
-                                                      cap, (unsigned long long*)d_scalars, S_N_UNITS);
-        else
-            k_finish_regions<<<1, 1024, 0, st>>>((const unsigned long long*)c->offsets.p, (unsigned long long*)c->hist.p, B, cap,
-                                                 (unsigned long long*)d_scalars, S_N_WINDOWS);
-        L.n++;
+        // bucket b = units[begin[b], end[b]): end = the cursors (clamped to the region)
+        k_finish_unit_regions<<<1, 1024, 0, st>>>((const unsigned long long*)c->ubeg.p, (unsigned long long*)c->ucur.p, MB,
+                                                  cap, (unsigned long long*)d_scalars, S_N_UNITS);
+        out.launches++;
         CU_TRY(c, cudaGetLastError());
         if (c->ev_ok) cudaEventRecord(c->ev[T_SCATTER], st);
         // codes / valid / tile words are dead from here on: clear them for the next build (or the next pass) on the side
@@ -895,63 +720,62 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
             c->pre_groups = c->pass_groups; c->pre_pub_bytes = c->pass_pub_bytes;
         }
 
-        // ---- optional abundance filter (reads: -abundance-min, kmer_count.py:48)
-        const unsigned long long* agg_records = (const unsigned long long*)c->records.p;
+        // Dedupe -> expand -> aggregate run back to back without a host round trip.  The dedupe's entry list and the
+        // expansion's bucket regions are sized from estimates; the one synchronisation after the aggregate reads what
+        // was really needed, and a guess that was too small repeats the round (entry list: larger; regions: exact
+        // offsets from a count pass).
         const unsigned long long* agg_begin = (const unsigned long long*)c->offsets.p;
         const unsigned long long* agg_end = (const unsigned long long*)c->hist.p;
-        // Unit path: dedupe -> expand -> aggregate run back to back without a host round trip.  The dedupe's entry list
-        // and the expansion's bucket regions are sized from estimates; the one synchronisation after the aggregate
-        // reads what was really needed, and a guess that was too small repeats the round (entry list: larger; regions:
-        // exact offsets from a count pass).
-        uint64_t wcap = std::min<uint64_t>(P.max_stream, std::max<uint64_t>(1 << 16, P.max_stream / 16));
+        uint64_t wcap = std::min<uint64_t>(max_stream, std::max<uint64_t>(1 << 16, max_stream / 16));
         bool wide_exact = !try_regions;
         if (getenv("GRMKM_WIDE_EXACT")) wide_exact = true;
         if (const char* e = getenv("GRMKM_WU_CAP")) wcap = std::max<uint64_t>(16, (uint64_t)atoll(e));     // tests: force the retry
         bool again = true, unit_overflow = false;
         for (int round = 0; again; ++round) {
-        again = false;
-        if (round > 6) return fail(c, GRMKM_E_UNSUPPORTED, "unit path does not converge");
-        if (round > 0) {
-            const uint64_t zero3[3] = {0, 0, 0};
-            CU_TRY(c, cudaMemcpyAsync(d_scalars + S_U_NEEDED, zero3, 3 * 8, cudaMemcpyHostToDevice, st));      // + S_N_DISTINCT, S_N_SPLITS
-            CU_TRY(c, cudaMemcpyAsync(d_scalars + S_WU_NEEDED, zero3, 3 * 8, cudaMemcpyHostToDevice, st));     // + S_N_WIDE, S_WIDE_OVERFLOW
-            CU_TRY(c, cudaStreamSynchronize(st));          // zero3 lives on this stack frame
-        }
-        if (use_units) {
+            again = false;
+            if (round > 6) return fail(c, GRMKM_E_UNSUPPORTED, "unit path does not converge");
+            if (round > 0) {
+                const uint64_t zero3[3] = {0, 0, 0};
+                CU_TRY(c, cudaMemcpyAsync(d_scalars + S_U_NEEDED, zero3, 3 * 8, cudaMemcpyHostToDevice, st));      // + S_N_DISTINCT, S_N_SPLITS
+                CU_TRY(c, cudaMemcpyAsync(d_scalars + S_WU_NEEDED, zero3, 3 * 8, cudaMemcpyHostToDevice, st));     // + S_N_WIDE, S_WIDE_OVERFLOW
+                CU_TRY(c, cudaStreamSynchronize(st));          // zero3 lives on this stack frame
+            }
             if (c->ev_ok) cudaEventRecord(c->ev[T_ABUND], st);
             const size_t dsm = unit_dedupe_smem(WB), xsm = staged_smem_bytes(B);
-            void (*k_dedupe)(UnitDedupeParams) = WB == 1 ? k_units_dedupe<1> : WB == 2 ? k_units_dedupe<2> : k_units_dedupe<4>;
+            void (*k_dedupe)(UnitDedupeParams) = counting ? k_units_dedupe<1, true>
+                                                 : WB == 1 ? k_units_dedupe<1, false> : WB == 2 ? k_units_dedupe<2, false> : k_units_dedupe<4, false>;
             void (*k_xcount)(UnitExpandParams) = WB == 1 ? k_units_expand<true, 1> : WB == 2 ? k_units_expand<true, 2> : k_units_expand<true, 4>;
             void (*k_xscat)(UnitExpandParams) = WB == 1 ? k_units_expand<false, 1> : WB == 2 ? k_units_expand<false, 2> : k_units_expand<false, 4>;
             CU_TRY(c, cudaFuncSetAttribute(k_dedupe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
             CU_TRY(c, cudaFuncSetAttribute(k_xcount, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsm));
             CU_TRY(c, cudaFuncSetAttribute(k_xscat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsm));
-            // ---- dedupe: distinct (unit, block) entries
+            // ---- dedupe: distinct (unit, group) entries
             ENSURE(c, c->wu, wcap * ES * 8);
             UnitDedupeParams dp{};
             dp.units = (const uint4*)c->units.p; dp.begin = (const unsigned long long*)c->ubeg.p;
             dp.end = (const unsigned long long*)c->ucur.p; dp.n_buckets = MB; dp.out = (unsigned long long*)c->wu.p;
             dp.cap = wcap; dp.needed = (unsigned long long*)(d_scalars + S_WU_NEEDED);
             k_dedupe<<<std::min<uint32_t>(MB, (uint32_t)c->sm_count), kUdThreads, dsm, st>>>(dp);
-            L.n++;
+            out.launches++;
             CU_TRY(c, cudaGetLastError());
             if (c->ev_ok) cudaEventRecord(c->ev[T_DEDUPE], st);
             // ---- expand: every distinct entry -> wide records of its k-mers, by hash bucket
             UnitExpandParams xp{};
             xp.wu = (const unsigned long long*)c->wu.p; xp.n_ptr = (const unsigned long long*)(d_scalars + S_WU_NEEDED);
-            xp.cap = wcap; xp.k = c->cfg.k; xp.bucket_bits = P.bucket_bits; xp.wbits = wbits;
+            xp.cap = wcap; xp.k = c->cfg.k; xp.bucket_bits = geo.bucket_bits; xp.wbits = wbits;
             xp.cursors = (unsigned long long*)c->hist.p; xp.records = nullptr;
             xp.overflow = (unsigned long long*)(d_scalars + S_WIDE_OVERFLOW);
             const uint32_t xgrid = (uint32_t)std::min<uint64_t>((wcap + kStThreads - 1) / kStThreads, (uint64_t)c->sm_count);
             if (!wide_exact) {
-                // over-provisioned bucket regions, no count pass: the distinct k-mers are estimated as 1.9 x the largest genome
-                // plus 5 % of all input (what every further genome adds to a species' pan-genome), 1.3 records per distinct
-                // k-mer and genome group, 1.4 x headroom per bucket; the previous build of this context corrects the guess
-                std::vector<uint64_t> row_bytes(std::max(P.G, 1u), 0);
-                for (const Input& in : c->inputs) if (in.row < P.G) row_bytes[in.row] += in.len;
-                const uint64_t max_row = *std::max_element(row_bytes.begin(), row_bytes.end());
-                const uint64_t groups = (P.W + WB - 1) / WB;
-                uint64_t est = std::max<uint64_t>(c->wide_hint, std::min<uint64_t>(P.in_bytes, max_row * 19 / 10 + P.in_bytes / 20) * 13 / 10 * groups);
+                // over-provisioned bucket regions, no count pass.  Presence: the distinct k-mers are estimated as 1.9 x the
+                // largest genome plus 5 % of all input (what every further genome adds to a species' pan-genome), 1.3
+                // records per distinct k-mer and genome group.  Abundance: every distinct (unit, genome) pair expands,
+                // about a quarter of the text for reads, all of it for contigs.  1.4 x headroom per bucket; the previous
+                // build (or round) of this context corrects the guess.
+                uint64_t est;
+                if (counting) est = c->cfg.input_kind == GRMKM_FASTQ ? in_bytes / 4 + 4096 : in_bytes + in_bytes / 8 + 4096;
+                else est = std::min<uint64_t>(in_bytes, job.max_row_bytes * 19 / 10 + in_bytes / 20) * 13 / 10 * n_groups_w;
+                est = std::max<uint64_t>(est, c->wide_hint);
                 if (const char* wc = getenv("GRMKM_WIDE_EST")) est = (uint64_t)atoll(wc);
                 // (rounded BEFORE the capacity test: tested unrounded, the size asked for was always a little more than the
                 // size allocated, and cudaMemGetInfo -- a driver round trip that takes anything from 0.1 to 90 ms while the
@@ -979,7 +803,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
                 k_xscat<<<xgrid, kStThreads, xsm, st>>>(xp);
                 k_finish_regions<<<1, 1024, 0, st>>>((const unsigned long long*)c->offsets.p, (unsigned long long*)c->hist.p, B, rcap,
                                                      (unsigned long long*)d_scalars, S_N_WIDE);
-                L.n += 3;
+                out.launches += 3;
                 CU_TRY(c, cudaGetLastError());
                 agg_begin = (const unsigned long long*)c->offsets.p;
                 agg_end = (const unsigned long long*)c->hist.p;
@@ -989,9 +813,9 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
                 k_xcount<<<xgrid, kStThreads, xsm, st>>>(xp);
                 k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->hist.p, (unsigned long long*)c->offsets.p, B,
                                                      d_scalars, S_N_WIDE, kCursorStride);
-                L.n += 2;
+                out.launches += 2;
                 CU_TRY(c, cudaGetLastError());
-                CU_TRY(c, cudaMemcpyAsync(sc, d_scalars, sizeof sc, cudaMemcpyDeviceToHost, st));
+                CU_TRY(c, cudaMemcpyAsync(sc, d_scalars, sizeof out.sc, cudaMemcpyDeviceToHost, st));
                 CU_TRY(c, cudaStreamSynchronize(st));
                 if (regions && sc[S_OVERFLOW]) { unit_overflow = true; break; }
                 if (sc[S_WU_NEEDED] > wcap) {
@@ -1003,211 +827,479 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
                 ENSURE(c, c->wide, (sc[S_N_WIDE] + 1) * RS * 8);
                 xp.records = (unsigned long long*)c->wide.p;
                 k_xscat<<<xgrid, kStThreads, xsm, st>>>(xp);
-                L.n++;
+                out.launches++;
                 CU_TRY(c, cudaGetLastError());
                 agg_begin = (const unsigned long long*)c->offsets.p;
                 agg_end = agg_begin + 1;
             }
             if (c->ev_ok) cudaEventRecord(c->ev[T_EXPAND], st);
-            agg_records = (const unsigned long long*)c->wide.p;
-        }
-        if (c->cfg.min_abundance > 1) {
-            ENSURE(c, c->records2, c->records.cap);
-            ENSURE(c, c->bcounts, (size_t)B * 8);
-            ENSURE(c, c->offsets2, (size_t)(B + 1) * 8);
-            AggParams ap{};
-            ap.records = agg_records; ap.begin = agg_begin; ap.end = agg_end; ap.B = B; ap.bucket_bits = P.bucket_bits;
-            ap.row_bits = P.row_bits; ap.n_words = 1;
-            ap.slots = (uint32_t)std::min<size_t>(kAggMaxSlots, budget / 16);
-            ap.mode = 2; ap.min_abundance = c->cfg.min_abundance; ap.b_begin = 0; ap.b_end = B;
-            ap.scalars = (unsigned long long*)d_scalars;
-            ap.bucket_out_counts = (unsigned long long*)c->bcounts.p;
-            ap.out_records = (unsigned long long*)c->records2.p;
-            const size_t sm = (size_t)ap.slots * 16;
-            CU_TRY(c, cudaFuncSetAttribute(k_aggregate<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            k_aggregate<2><<<agrid, kAggThreads, sm, st>>>(ap);
-            k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->bcounts.p, (unsigned long long*)c->offsets2.p, B,
-                                                 d_scalars, S_N_SOLID, 1);
-            k_compact_records<<<agrid * 4, 256, 0, st>>>((const unsigned long long*)c->records2.p, agg_begin,
-                                                         (const unsigned long long*)c->offsets2.p, B,
-                                                         (unsigned long long*)c->records.p);
-            L.n += 3;
-            CU_TRY(c, cudaGetLastError());
-            agg_begin = (const unsigned long long*)c->offsets2.p;
-            agg_end = agg_begin + 1;
-        }
-        if (!use_units && c->ev_ok) for (int e : {T_ABUND, T_DEDUPE, T_EXPAND}) cudaEventRecord(c->ev[e], st);
 
-        // ---- aggregate (dsk2kover): retry with a larger output if the first guess was too small
-        // columns: three pan-genome estimates (1.9 x the largest genome each) + 1 % of all input, at most a quarter of the
-        // windows (N / 4 alone asked for 163 GB of word rows at 1000 genomes); a guess that is too small is retried with
-        // the exact number
-        {
-            uint64_t max_row = 0;
-            std::vector<uint64_t> rb(std::max(P.G, 1u), 0);
-            for (const Input& in : c->inputs) if (in.row < P.G) { rb[in.row] += in.len; max_row = std::max(max_row, rb[in.row]); }
-            const uint64_t guess = 3 * (max_row * 19 / 10) + P.in_bytes / 100;
-            ucap = std::min<uint64_t>(P.max_stream, std::max<uint64_t>(1 << 16, std::min<uint64_t>(P.max_stream / 4, std::max<uint64_t>(guess, c->ucap_hint))));
-        }
-        ucap = std::min<uint64_t>(ucap, 0xFFFFFFFFULL);
-        ENSURE(c, c->bbase, (size_t)VB * 8);
-        ENSURE(c, c->bcounts, (size_t)VB * 8);
-        if (ordered) ENSURE(c, c->apub, (size_t)(VB + 1) * 8);
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            if (ordered) {
-                // the columns land at their final place: k-mers and word row 0 in the result arrays, rows >= 1 at stride ucap
-                ENSURE(c, c->kmers, ucap * 8);
-                ENSURE(c, c->matrix, (size_t)ucap * P.W * 8);
-                if (P.W > 1) ENSURE(c, c->uwords, (size_t)ucap * P.W * 8);
-                CU_TRY(c, cudaMemsetAsync(c->apub.p, 0, (size_t)(VB + 1) * 8, st));
+            // ---- aggregate.  Columns: three pan-genome estimates (1.9 x the largest genome each) + 1 % of all input, at
+            // most a quarter of the windows (N / 4 alone asked for 163 GB of word rows at 1000 genomes); a guess that is
+            // too small is retried with the exact number.
+            AggIn ai{};
+            ai.records = (const unsigned long long*)c->wide.p; ai.begin = agg_begin; ai.end = agg_end;
+            ai.wide_words = WB; ai.wide_stride = RS; ai.row_bits = wbits; ai.agg = job.agg;
+            if (job.agg == AGG_ROUND) {
+                ai.cells = (job.n_rows + 1) & ~1u; ai.n_words = 1;
+                ai.round_rows = job.n_rows; ai.round_row0 = job.row0;
+                ai.out_wbits = std::max(1u, ceil_log2(geo.W)); ai.out_word = job.row0 >> 6;
+                ai.round_out = job.round_out; ai.ucap_guess = job.round_cap;
+            } else if (job.agg == AGG_COUNTS) {
+                ai.cells = 2; ai.n_words = 1; ai.round_rows = 1; ai.round_row0 = 0;
+                ai.ucap_guess = std::min<uint64_t>(max_stream, std::max<uint64_t>(1 << 16, std::max<uint64_t>(in_bytes / 8, c->ucap_hint)));
             } else {
-                ENSURE(c, c->ukeys, ucap * 8);
-                ENSURE(c, c->uwords, (size_t)ucap * P.W * 8);
+                ai.cells = 2 * geo.W; ai.n_words = geo.W;
+                const uint64_t guess = 3 * (job.max_row_bytes * 19 / 10) + in_bytes / 100;
+                ai.ucap_guess = std::min<uint64_t>(max_stream, std::max<uint64_t>(1 << 16, std::min<uint64_t>(max_stream / 4, std::max<uint64_t>(guess, c->ucap_hint))));
             }
-            AggParams2 ap{};
-            ap.records = agg_records; ap.begin = agg_begin; ap.end = agg_end; ap.bucket_bits = P.bucket_bits;
-            ap.row_bits = use_units ? wbits : P.row_bits; ap.n_words = P.W; ap.slots = P.slots;
-            ap.keep_singletons = c->cfg.keep_singletons; ap.sub_bits = P.sub_bits;
-            ap.wide_words = WB; ap.wide_stride = RS; ap.table_u32 = 2 * P.W;
-            ap.out_keys = (unsigned long long*)c->ukeys.p; ap.out_words = (unsigned long long*)c->uwords.p;
-            ap.cap = ucap; ap.scalars = (unsigned long long*)d_scalars;
-            ap.bucket_base = (unsigned long long*)c->bbase.p; ap.bucket_count = (unsigned long long*)c->bcounts.p;
-            ap.b_begin = 0; ap.b_end = B;
-            if (ordered) {
-                ap.ordered = 1;
-                ap.out_keys = (unsigned long long*)c->kmers.p; ap.out_row0 = (unsigned long long*)c->matrix.p;
-                ap.pub = (unsigned long long*)c->apub.p; ap.ticket = (unsigned int*)((unsigned long long*)c->apub.p + VB);
-            }
-            if (use_units && mode == 0) {
-                CU_TRY(c, cudaFuncSetAttribute(k_aggregate_cols<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.agg_smem));
-                k_aggregate_cols<4><<<vgrid, kAggThreads, P.agg_smem, st>>>(ap);
-            } else if (use_units) {
-                CU_TRY(c, cudaFuncSetAttribute(k_aggregate_cols<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.agg_smem));
-                k_aggregate_cols<5><<<vgrid, kAggThreads, P.agg_smem, st>>>(ap);
-            } else if (mode == 0) {
-                CU_TRY(c, cudaFuncSetAttribute(k_aggregate_cols<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.agg_smem));
-                k_aggregate_cols<0><<<vgrid, kAggThreads, P.agg_smem, st>>>(ap);
-            } else {
-                CU_TRY(c, cudaFuncSetAttribute(k_aggregate_cols<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.agg_smem));
-                k_aggregate_cols<1><<<vgrid, kAggThreads, P.agg_smem, st>>>(ap);
-            }
-            L.n++;
-            CU_TRY(c, cudaGetLastError());
-            if (ordered) {
-                // rows >= 1 move from stride ucap to the result's stride U (row 0 and the k-mers are already in place); U is read
-                // on the device, so the build ends with this one synchronisation
-                if (c->ev_ok) cudaEventRecord(c->ev[T_AGG], st);
-                if (P.W > 1) {
-                    k_move_rows<<<(uint32_t)c->sm_count * 8, 256, 0, st>>>((const unsigned long long*)c->uwords.p, ucap, (unsigned long long*)c->matrix.p,
-                                                                          (const unsigned long long*)(d_scalars + S_U_NEEDED), P.W);
-                    L.n++;
-                    CU_TRY(c, cudaGetLastError());
-                }
-            }
-            CU_TRY(c, cudaMemcpyAsync(sc, d_scalars, sizeof sc, cudaMemcpyDeviceToHost, st));
-            CU_TRY(c, cudaStreamSynchronize(st));
+            bool retry = false;
+            auto upstream = [&](const uint64_t* s) -> int {
+                if (regions && s[S_OVERFLOW]) return 1;
+                if (s[S_WU_NEEDED] > wcap) { wcap = s[S_WU_NEEDED] + s[S_WU_NEEDED] / 4 + 4096; again = true; return 1; }
+                if (!wide_exact && s[S_WIDE_OVERFLOW]) { wide_exact = true; again = true; c->stats.n_region_overflows++; return 1; }
+                return 0;
+            };
+            const int ar = run_aggregate(c, geo, ai, out, retry, upstream);
+            if (ar) return ar;
             if (regions && sc[S_OVERFLOW]) break;
-            if (use_units && sc[S_WU_NEEDED] > wcap) {
-                wcap = sc[S_WU_NEEDED] + sc[S_WU_NEEDED] / 4 + 4096;
-                again = true;
-                break;
-            }
-            if (use_units && !wide_exact && sc[S_WIDE_OVERFLOW]) {
-                wide_exact = true; again = true; c->stats.n_region_overflows++;
-                break;
-            }
-            if (sc[S_U_NEEDED] <= ucap) break;
-            if (attempt == 1 || sc[S_U_NEEDED] > 0xFFFFFFFFULL)
-                return fail(c, GRMKM_E_UNSUPPORTED, "more than 2^32 columns in one context");
-            ucap = sc[S_U_NEEDED];
-            const uint64_t zero3[3] = {0, 0, 0};
-            CU_TRY(c, cudaMemcpyAsync(d_scalars + S_U_NEEDED, zero3, 3 * 8, cudaMemcpyHostToDevice, st));
-        }
         }   // round
-        if (use_units && !unit_overflow && !(regions && sc[S_OVERFLOW])) c->wide_hint = sc[S_N_WIDE];
-        if (!(regions && sc[S_OVERFLOW])) c->ucap_hint = sc[S_U_NEEDED] + sc[S_U_NEEDED] / 8;
-        if (!(regions && (sc[S_OVERFLOW] || unit_overflow))) break;
+        const bool redo = regions && (sc[S_OVERFLOW] || unit_overflow);
+        if (!redo) {
+            c->wide_hint = sc[S_N_WIDE];
+            if (job.agg != AGG_ROUND) c->ucap_hint = sc[S_U_NEEDED] + sc[S_U_NEEDED] / 8;
+            break;
+        }
         c->stats.n_region_overflows++;
     }
-    if (c->ev_ok && !ordered) cudaEventRecord(c->ev[T_AGG], st);
-    const uint64_t U = sc[S_U_NEEDED];
+    if (c->ev_ok && !out.ordered) cudaEventRecord(c->ev[T_AGG], st);
+    return GRMKM_OK;
+}
 
-    // ---- final order.  Default: ascending hash (bucket order; every bucket chunk is already sorted), which is
-    // identical for any GPU count.  GRMKM_FLAG_KMER_ORDER: ascending canonical k-mer (one extra sort).
-    std::vector<uint64_t> h_off;
-    if (mode == 0 && (c->cfg.flags & GRMKM_FLAG_KMER_ORDER)) {
-        int r = sort_and_gather(c, U, P.W, ucap, 2 * c->cfg.k, false, L);
-        if (r) return r;
-    } else if (ordered) {
-        // nothing left to do: k_move_rows ran behind the aggregate
-    } else {
+// After the aggregate of a final / partial build: bucket chunks -> result arrays (unordered emission), or the chunk
+// offsets of a partial build.  Ends with the build's last synchronisation.
+int finish_columns(grmkm_ctx* c, const Geo& geo, uint32_t n_words, bool partial, JobOut& out) {
+    cudaStream_t st = c->stream;
+    uint64_t* d_scalars = (uint64_t*)c->scalars.p;
+    const uint64_t U = out.sc[S_U_NEEDED];
+    const uint32_t VB = geo.VB;
+    if (!out.ordered) {
         ENSURE(c, c->offsets2, (size_t)(VB + 1) * 8);
         ENSURE(c, c->kmers, U * 8);
-        ENSURE(c, c->matrix, (size_t)U * P.W * 8);
+        ENSURE(c, c->matrix, (size_t)U * n_words * 8);
         k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->bcounts.p, (unsigned long long*)c->offsets2.p, VB,
                                              d_scalars, S_N_SOLID, 1);
-        if (U && mode == 0) {
+        out.launches++;
+        if (U && !partial) {
             k_gather_buckets<<<std::min<uint32_t>(VB, (uint32_t)c->sm_count * 8), 256, 0, st>>>(
-                (const unsigned long long*)c->ukeys.p, (const unsigned long long*)c->uwords.p, ucap,
-                (const unsigned long long*)c->bbase.p, (const unsigned long long*)c->offsets2.p, VB, P.W, U,
+                (const unsigned long long*)c->ukeys.p, (const unsigned long long*)c->uwords.p, out.ucap,
+                (const unsigned long long*)c->bbase.p, (const unsigned long long*)c->offsets2.p, VB, n_words, U,
                 (unsigned long long*)c->kmers.p, (unsigned long long*)c->matrix.p, U);
-            L.n++;
+            out.launches++;
         }                               // partial build: grmkm_export_partials gathers straight into the caller's AoS buffer
-        L.n++;
         CU_TRY(c, cudaGetLastError());
-        if (mode == 1) {
-            h_off.resize(VB + 1);
-            CU_TRY(c, cudaMemcpyAsync(h_off.data(), c->offsets2.p, (size_t)(VB + 1) * 8, cudaMemcpyDeviceToHost, st));
+        if (partial) {
+            out.h_off.resize(VB + 1);
+            CU_TRY(c, cudaMemcpyAsync(out.h_off.data(), c->offsets2.p, (size_t)(VB + 1) * 8, cudaMemcpyDeviceToHost, st));
         }
     }
     if (c->ev_ok) cudaEventRecord(c->ev[T_SORT], st);
     CU_TRY(c, cudaStreamSynchronize(st));
+    return GRMKM_OK;
+}
 
-    c->U = U;
-    c->built = (mode == 0);
-    if (mode == 1) {
-        // partial columns are in bucket order: owner r holds buckets [r*B/P, (r+1)*B/P)
-        c->part_ranks = n_ranges;
-        c->part_counts.resize(n_ranges);
-        for (uint32_t r = 0; r < n_ranges; ++r)
-            c->part_counts[r] = h_off[((uint64_t)B * (r + 1) / n_ranges) << P.sub_bits] - h_off[((uint64_t)B * r / n_ranges) << P.sub_bits];
-        c->part_total = U; c->part_cap = ucap; c->part_words = P.W; c->part_buckets = VB;
-    }
+void add_job_stats(grmkm_ctx* c, const JobOut& o, bool counts_are_final) {
     grmkm_stats& s = c->stats;
-    s.n_input_bytes = P.in_bytes;
-    s.n_records = sc[S_N_RECORDS];
-    s.n_bases = sc[S_STREAM_TOTAL] - sc[S_N_RECORDS];
-    s.n_windows = sc[S_N_WINDOWS];
-    s.n_kmers = U;
-    s.n_distinct = sc[S_N_DISTINCT];
-    s.n_words = P.W; s.n_genomes = P.G; s.n_buckets = B;
-    s.n_launches = L.n;
-    s.h2d_bytes = h2d;
-    s.device_bytes = c->device_bytes;
-    s.n_splits = sc[S_N_SPLITS];
-    s.n_units = use_units ? sc[S_N_UNITS] : 0;
-    s.n_unit_entries = use_units ? sc[S_WU_NEEDED] : 0;
-    s.n_wide = use_units ? sc[S_N_WIDE] : 0;
-    s.n_unit_buckets = use_units ? MB : 0;
-    if (c->ev_ok) {
-        float* t[] = {&c->times.h2d, &c->times.parse, &c->times.pack, &c->times.count, &c->times.bounds, &c->times.scatter,
-                      &c->times.abundance, &c->times.dedupe, &c->times.expand, &c->times.aggregate, &c->times.sort};
-        for (int i = 1; i < T_N; ++i) {
-            const cudaError_t te = cudaEventElapsedTime(t[i - 1], c->ev[i - 1], c->ev[i]);
-            if (te != cudaSuccess) {
-                cudaGetLastError();
-                if (getenv("GRMKM_DEBUG")) fprintf(stderr, "grmkm: stage event %d: %s\n", i, cudaGetErrorString(te));
-                *t[i - 1] = 0.f;
+    s.n_records += o.sc[S_N_RECORDS];
+    s.n_bases += o.sc[S_STREAM_TOTAL] - o.sc[S_N_RECORDS];
+    s.n_windows += o.sc[S_N_WINDOWS];
+    s.n_launches += o.launches;
+    s.h2d_bytes += o.h2d;
+    s.n_splits += o.sc[S_N_SPLITS];
+    s.n_units += o.sc[S_N_UNITS];
+    s.n_unit_entries += o.sc[S_WU_NEEDED];
+    s.n_wide += o.sc[S_N_WIDE];
+    s.n_unit_buckets = std::max(s.n_unit_buckets, o.MB);
+    if (counts_are_final) { s.n_kmers = o.sc[S_U_NEEDED]; s.n_distinct = o.sc[S_N_DISTINCT]; }
+}
+
+void set_partial_state(grmkm_ctx* c, const Geo& geo, uint32_t n_ranges, const JobOut& o) {
+    // partial columns are in bucket order: owner r holds buckets [r*B/P, (r+1)*B/P)
+    c->part_ranks = n_ranges;
+    c->part_counts.resize(n_ranges);
+    for (uint32_t r = 0; r < n_ranges; ++r)
+        c->part_counts[r] = o.h_off[((uint64_t)geo.B * (r + 1) / n_ranges) << geo.sub_bits] - o.h_off[((uint64_t)geo.B * r / n_ranges) << geo.sub_bits];
+    c->part_total = o.sc[S_U_NEEDED]; c->part_cap = o.ucap; c->part_buckets = geo.VB;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// the build
+// ------------------------------------------------------------------------------------------------
+static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32_t n_ranges) {
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    c->built = false;
+    c->stats = grmkm_stats{};
+    c->times = grmkm_times{};
+
+    const bool pooled = (c->cfg.flags & GRMKM_FLAG_COUNTS) != 0;
+    if (pooled) {
+        if (mode == 1) return fail(c, GRMKM_E_UNSUPPORTED, "the pooled count table is a one-GPU build");
+        for (Input& in : c->inputs) in.row = 0;              // dsk -file <list>: every file is pooled (src/app.py:1371-1372)
+        c->n_genomes_decl = std::min(c->n_genomes_decl, 1u);
+    }
+    const InputTable tab = tabulate_inputs(c);
+    Geo geo;
+    geo.G = tab.G; geo.W = (tab.G + 63) / 64;
+    const uint32_t F = (uint32_t)c->inputs.size();
+    c->G = geo.G; c->W = geo.W; c->U = 0;
+    c->part_ranks = 0; c->part_total = 0; c->part_words = geo.W;
+    c->stats.n_genomes = geo.G; c->stats.n_words = geo.W; c->stats.n_input_bytes = tab.in_bytes;
+    if (geo.G == 0 || F == 0) {
+        c->built = (mode == 0);
+        if (mode == 1) { c->part_ranks = n_ranges; c->part_counts.assign(n_ranges, 0); }
+        return GRMKM_OK;
+    }
+    if (geo.G > 32768) return fail(c, GRMKM_E_UNSUPPORTED, "more than 32768 genomes in one context");
+
+    // ---- bucket count.  The expansion sorts tiles over at most 2^11 buckets: more distinct k-mers than 2^11 tables
+    // hold are handled as key sub-ranges of the buckets (virtual buckets: one aggregate pass each over the bucket's
+    // records, which stay in L2), and beyond 2^14 by the table's own overflow split.
+    uint32_t bits = c->cfg.bucket_bits ? c->cfg.bucket_bits : auto_bucket_bits(c, tab);
+    // the records' group field replaces bucket bits; a partial build keeps the agreed count as it is (every rank must
+    // cut the hash space the same way whatever its share of the rows)
+    if (mode == 0) bits = std::max(bits, std::max(1u, ceil_log2(geo.W)));
+    if (bits > 15) return fail(c, GRMKM_E_UNSUPPORTED, "bucket_bits > 15");
+    if (const char* sbv = getenv("GRMKM_SUB_BITS")) geo.sub_bits = (uint32_t)std::min(3, std::max(0, atoi(sbv)));
+    if (bits > kUnitMaxBucketBits) {
+        geo.sub_bits = std::max(geo.sub_bits, std::min(kMaxSubBits, bits - kUnitMaxBucketBits));
+        bits = kUnitMaxBucketBits;
+    }
+    geo.bucket_bits = bits; geo.B = 1u << bits; geo.VB = geo.B << geo.sub_bits;
+    c->cur_bucket_bits = bits;
+
+    if (!abundance_build(c)) {
+        // ---- presence build (contigs, reads without an abundance filter): one pass over everything
+        Job job; job.f0 = 0; job.f1 = F; job.row0 = 0; job.n_rows = geo.G; job.max_row_bytes = tab.max_row;
+        job.agg = mode == 0 ? AGG_FINAL : AGG_PARTIAL;
+        JobOut out;
+        int r = run_job(c, geo, job, out);
+        if (r) return r;
+        r = finish_columns(c, geo, geo.W, mode == 1, out);
+        if (r) return r;
+        add_job_stats(c, out, true);
+        add_stage_times(c);
+        c->stats.n_buckets = geo.B; c->stats.device_bytes = c->device_bytes;
+        c->U = out.sc[S_U_NEEDED];
+        c->built = (mode == 0);
+        if (mode == 1) set_partial_state(c, geo, n_ranges, out);
+        return GRMKM_OK;
+    }
+
+    if (pooled) {
+        // ---- pooled count table (dsk): one round, the aggregate emits (k-mer, count) columns
+        Job job; job.f0 = 0; job.f1 = F; job.row0 = 0; job.n_rows = 1; job.max_row_bytes = tab.in_bytes; job.agg = AGG_COUNTS;
+        JobOut out;
+        int r = run_job(c, geo, job, out);
+        if (r) return r;
+        r = finish_columns(c, geo, 1, false, out);
+        if (r) return r;
+        add_job_stats(c, out, true);
+        add_stage_times(c);
+        c->stats.n_buckets = geo.B; c->stats.device_bytes = c->device_bytes;
+        c->U = out.sc[S_U_NEEDED];
+        c->built = true;
+        return GRMKM_OK;
+    }
+
+    // ---- abundance build (reads with -abundance-min > 1): rounds of a few genome rows, each leaving the solid
+    // presence of its rows as records [(hash << wbits) | matrix word, bits]; then ONE presence aggregate over the
+    // records of all rounds.
+    const std::vector<Round> rounds = plan_rounds(c, geo.G, tab.first_file, tab.row_bytes);
+    struct Seg { unsigned long long src, dst, n; };
+    std::vector<std::vector<uint64_t>> r_base(rounds.size()), r_cnt(rounds.size());
+    uint64_t used = 0;
+    {
+        // one record per solid (k-mer, round): about the text's 64th part for read sets; the buffer doubles when a round
+        // does not fit
+        const uint64_t guess = std::max<uint64_t>(1 << 16, std::max<uint64_t>(tab.in_bytes / 64, c->racc_hint));
+        ENSURE(c, c->racc, guess * 16);
+    }
+    for (size_t ri = 0; ri < rounds.size(); ++ri) {
+        const Round& rd = rounds[ri];
+        r_base[ri].assign(geo.VB, 0); r_cnt[ri].assign(geo.VB, 0);
+        if (rd.f1 == rd.f0) continue;                      // rows without input
+        Job job; job.f0 = rd.f0; job.f1 = rd.f1; job.row0 = rd.row0; job.n_rows = rd.n_rows; job.agg = AGG_ROUND;
+        for (uint32_t g = rd.row0; g < rd.row0 + rd.n_rows; ++g) job.max_row_bytes = std::max(job.max_row_bytes, tab.row_bytes[g]);
+        for (int attempt = 0;; ++attempt) {
+            job.round_out = (ulonglong2*)c->racc.p + used;
+            job.round_cap = c->racc.cap / 16 - used;
+            JobOut out;
+            int r = run_job(c, geo, job, out);
+            if (r) return r;
+            if (c->ev_ok) cudaEventRecord(c->ev[T_SORT], st);
+            if (out.round_full) {
+                if (attempt > 2) return fail(c, GRMKM_E_NOMEM, "abundance round output does not fit");
+                // grow: what is there + this round's need, doubled for the rounds to come
+                const uint64_t want = (used + out.sc[S_U_NEEDED]) * 2 + 4096;
+                DevBuf bigger;
+                ENSURE(c, bigger, want * 16);
+                if (used) CU_TRY(c, cudaMemcpyAsync(bigger.p, c->racc.p, used * 16, cudaMemcpyDeviceToDevice, st));
+                CU_TRY(c, cudaStreamSynchronize(st));
+                release(c, c->racc);
+                c->racc = bigger;
+                c->stats.n_launches += out.launches;
+                continue;
             }
+            CU_TRY(c, cudaMemcpyAsync(r_base[ri].data(), c->bbase.p, (size_t)geo.VB * 8, cudaMemcpyDeviceToHost, st));
+            CU_TRY(c, cudaMemcpyAsync(r_cnt[ri].data(), c->bcounts.p, (size_t)geo.VB * 8, cudaMemcpyDeviceToHost, st));
+            CU_TRY(c, cudaStreamSynchronize(st));
+            for (uint32_t v = 0; v < geo.VB; ++v) r_base[ri][v] += used;       // the aggregate counts from its own output pointer
+            used += out.sc[S_U_NEEDED];
+            add_job_stats(c, out, false);
+            add_stage_times(c);
+            break;
         }
-        cudaEventElapsedTime(&c->times.total, c->ev[T_START], c->ev[T_SORT]);
+    }
+    c->racc_hint = used + used / 8;
+    // ---- records of all rounds, bucket by bucket (exact offsets), then the presence aggregate
+    std::vector<Seg> segs;
+    std::vector<uint64_t> h_begin(geo.B + 1, 0);
+    {
+        uint64_t pos = 0;
+        for (uint32_t v = 0; v < geo.VB; ++v) {
+            if ((v & ((1u << geo.sub_bits) - 1u)) == 0) h_begin[v >> geo.sub_bits] = pos;
+            for (size_t ri = 0; ri < rounds.size(); ++ri)
+                if (r_cnt[ri][v]) { segs.push_back(Seg{r_base[ri][v], pos, r_cnt[ri][v]}); pos += r_cnt[ri][v]; }
+        }
+        h_begin[geo.B] = pos;
+    }
+    JobOut out;
+    ENSURE(c, c->scalars, S_COUNT * 8);
+    ENSURE(c, c->offsets, (size_t)(geo.B + 1) * 8);
+    ENSURE(c, c->wide, (used + 1) * 16);
+    ENSURE(c, c->refs, std::max<size_t>(1, segs.size()) * sizeof(Seg));
+    uint64_t* d_scalars = (uint64_t*)c->scalars.p;
+    if (c->ev_ok) for (int e = T_START; e < T_AGG; ++e) cudaEventRecord(c->ev[e], st);
+    CU_TRY(c, cudaMemsetAsync(d_scalars, 0, S_COUNT * 8, st));
+    CU_TRY(c, cudaMemcpyAsync(c->offsets.p, h_begin.data(), (size_t)(geo.B + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (!segs.empty()) {
+        CU_TRY(c, cudaMemcpyAsync(c->refs.p, segs.data(), segs.size() * sizeof(Seg), cudaMemcpyHostToDevice, st));
+        k_gather_segments<<<(uint32_t)std::min<size_t>(segs.size(), (size_t)c->sm_count * 16), 128, 0, st>>>(
+            (const ulonglong2*)c->racc.p, (const unsigned long long*)c->refs.p, (uint32_t)segs.size(), (ulonglong2*)c->wide.p);
+        out.launches++;
+        CU_TRY(c, cudaGetLastError());
+    }
+    if (c->ev_ok) cudaEventRecord(c->ev[T_EXPAND], st);
+    AggIn ai{};
+    ai.records = (const unsigned long long*)c->wide.p;
+    ai.begin = (const unsigned long long*)c->offsets.p; ai.end = ai.begin + 1;
+    ai.wide_words = 1; ai.wide_stride = 2; ai.row_bits = std::max(1u, ceil_log2(geo.W));
+    ai.cells = 2 * geo.W; ai.n_words = geo.W; ai.agg = mode == 0 ? AGG_FINAL : AGG_PARTIAL;
+    ai.ucap_guess = std::max<uint64_t>(1 << 12, std::min<uint64_t>(used, std::max<uint64_t>(c->ucap_hint, used / 2)));
+    bool retry = false;
+    int r = run_aggregate(c, geo, ai, out, retry, [](const uint64_t*) { return 0; });
+    if (r) return r;
+    if (c->ev_ok && !out.ordered) cudaEventRecord(c->ev[T_AGG], st);
+    c->ucap_hint = out.sc[S_U_NEEDED] + out.sc[S_U_NEEDED] / 8;
+    r = finish_columns(c, geo, geo.W, mode == 1, out);
+    if (r) return r;
+    c->stats.n_launches += out.launches;
+    c->stats.n_kmers = out.sc[S_U_NEEDED]; c->stats.n_distinct = out.sc[S_N_DISTINCT]; c->stats.n_splits += out.sc[S_N_SPLITS];
+    c->stats.n_solid_records = used; c->stats.n_rounds = (uint32_t)rounds.size();
+    add_stage_times(c);
+    c->stats.n_buckets = geo.B; c->stats.device_bytes = c->device_bytes;
+    c->U = out.sc[S_U_NEEDED];
+    c->built = (mode == 0);
+    if (mode == 1) set_partial_state(c, geo, n_ranges, out);
+    return GRMKM_OK;
+}
+
+// every failure of a build leaves the context quiet: nothing in flight reads borrowed host buffers any more, and no
+// side-stream clear is counted on
+static int build_guarded(grmkm_ctx* c, uint32_t mode, uint32_t n_ranges) {
+    const int r = build_impl(c, mode, n_ranges);
+    if (r != GRMKM_OK) {
+        const std::string msg = c->err;
+        cudaStreamSynchronize(c->stream);
+        if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+        if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
+        cudaGetLastError();
+        c->pre_pending = false;
+        c->built = false;
+        c->part_ranks = 0;
+        c->err = msg;
+    }
+    return r;
+}
+
+extern "C" {
+
+int grmkm_abi_version(void) { return GRMKM_ABI_VERSION; }
+
+int grmkm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int grmkm_create(const grmkm_config* cfg, grmkm_ctx** out) {
+    if (!cfg || !out) return fail(nullptr, GRMKM_E_INVALID, "null argument");
+    *out = nullptr;
+    grmkm_config c{};
+    memcpy(&c, cfg, std::min<size_t>(sizeof c, cfg->struct_size ? cfg->struct_size : sizeof c));
+    if (c.k < 1 || c.k > 32)
+        return fail(nullptr, GRMKM_E_UNSUPPORTED_K, "k must be in 1..32 (got " + std::to_string(c.k) + ")");
+    if (c.min_abundance == 0) c.min_abundance = 1;
+    if (c.input_kind > GRMKM_FASTQ) return fail(nullptr, GRMKM_E_INVALID, "input_kind must be GRMKM_FASTA or GRMKM_FASTQ");
+    if (c.flags & ~GRMKM_FLAG_COUNTS) return fail(nullptr, GRMKM_E_INVALID, "unknown flag bits");
+    if (c.bucket_bits && (c.bucket_bits < 4 || c.bucket_bits > 15))
+        return fail(nullptr, GRMKM_E_INVALID, "bucket_bits must be 0 (auto) or 4..15");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, GRMKM_E_NO_DEVICE,
+                    std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "0 devices") +
+                        "); libgrmkm has no CPU fallback");
+    }
+    int dev = c.device;
+    if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+    if (dev >= ndev) return fail(nullptr, GRMKM_E_INVALID, "device ordinal out of range");
+    if ((e = cudaSetDevice(dev)) != cudaSuccess)
+        return fail(nullptr, GRMKM_E_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    grmkm_ctx* x = new (std::nothrow) grmkm_ctx();
+    if (!x) return fail(nullptr, GRMKM_E_NOMEM, "out of host memory");
+    x->cfg = c;
+    x->device = dev;
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) {
+        x->sm_count = prop.multiProcessorCount;
+        x->smem_optin = prop.sharedMemPerBlockOptin;
+    }
+    if (const char* bb = getenv("GRMKM_BATCH_BYTES")) { const long long v = atoll(bb); if (v > 0) x->batch_bytes = (uint64_t)v; }
+    if (c.stream) x->stream = (cudaStream_t)c.stream;
+    else {
+        if ((e = cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+            delete x;
+            return fail(nullptr, GRMKM_E_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+        }
+        x->own_stream = true;
+    }
+    x->ev_ok = true;
+    for (int i = 0; i < T_N; ++i) {
+        if (cudaEventCreate(&x->ev[i]) != cudaSuccess) {
+            // no stage timing then; the events that were created are not kept
+            cudaGetLastError();
+            for (int j = 0; j < i; ++j) cudaEventDestroy(x->ev[j]);
+            x->ev_ok = false;
+            break;
+        }
+    }
+    *out = x;
+    return GRMKM_OK;
+}
+
+void grmkm_destroy(grmkm_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);      // the clear for a next build may still be running
+    DevBuf* all[] = {&c->in, &c->files, &c->hdr0, &c->tile_file, &c->tile_pub, &c->tile_order,
+                     &c->fss, &c->codes, &c->valid, &c->hist, &c->offsets, &c->offsets2,
+                     &c->bcounts, &c->ukeys, &c->uwords, &c->kmers, &c->matrix, &c->scalars, &c->fmt, &c->synth, &c->refs,
+                     &c->stile_file, &c->bbase, &c->apub, &c->masks, &c->units, &c->ucur, &c->ubeg, &c->wu, &c->wide,
+                     &c->racc, &c->aux};
+    for (DevBuf* b : all) release(c, *b);
+    if (c->ev_ok) for (int i = 0; i < T_N; ++i) cudaEventDestroy(c->ev[i]);
+    if (c->host_res) cudaFreeHost(c->host_res);
+    if (c->aux_stream) {
+        cudaEventDestroy(c->ev_scattered); cudaEventDestroy(c->ev_cleared);
+        cudaStreamDestroy(c->aux_stream);
+    }
+    if (c->copy_stream) {
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->ev_copied[i]); cudaEventDestroy(c->ev_free[i]); }
+        cudaStreamDestroy(c->copy_stream);
+    }
+    if (c->h_tab) cudaFreeHost(c->h_tab);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* grmkm_last_error(const grmkm_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int grmkm_reset(grmkm_ctx* c) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    c->inputs.clear();
+    c->n_genomes_decl = 0;
+    c->built = false;
+    c->U = 0; c->W = 0; c->G = 0;
+    c->part_ranks = 0;
+    return GRMKM_OK;
+}
+
+int grmkm_add_genome_bytes(grmkm_ctx* c, uint32_t row, const uint8_t* data, uint64_t n) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    if (!data && n) return fail(c, GRMKM_E_INVALID, "null data");
+    if (row >= kMaxGenomes) return fail(c, GRMKM_E_UNSUPPORTED, "genome row out of range (at most 32768 genomes in one context)");
+    Input in; in.row = row; in.kind = c->cfg.input_kind; in.host = data; in.len = n;
+    c->inputs.push_back(std::move(in));
+    c->built = false;
+    return GRMKM_OK;
+}
+
+int grmkm_add_genome_device(grmkm_ctx* c, uint32_t row, const void* dev_data, uint64_t n) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    if (!dev_data && n) return fail(c, GRMKM_E_INVALID, "null data");
+    if ((uintptr_t)dev_data & 15) return fail(c, GRMKM_E_INVALID, "device input must be 16-byte aligned");
+    if (row >= kMaxGenomes) return fail(c, GRMKM_E_UNSUPPORTED, "genome row out of range (at most 32768 genomes in one context)");
+    Input in; in.row = row; in.kind = c->cfg.input_kind; in.dev = (const uint8_t*)dev_data; in.len = n;
+    c->inputs.push_back(std::move(in));
+    c->built = false;
+    return GRMKM_OK;
+}
+
+int grmkm_add_genomes(grmkm_ctx* c, uint32_t n, const uint32_t* rows, const void* const* data, const uint64_t* lens,
+                      int on_device) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    if (n && (!rows || !data || !lens)) return fail(c, GRMKM_E_INVALID, "null input list");
+    c->inputs.reserve(c->inputs.size() + n);
+    for (uint32_t i = 0; i < n; ++i) {
+        const int r = on_device ? grmkm_add_genome_device(c, rows[i], data[i], lens[i])
+                                : grmkm_add_genome_bytes(c, rows[i], (const uint8_t*)data[i], lens[i]);
+        if (r) return r;
     }
     return GRMKM_OK;
 }
 
+int grmkm_add_genome_files(grmkm_ctx* c, uint32_t row, const char* const* paths, int n_paths) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    if (n_paths < 0 || (!paths && n_paths)) return fail(c, GRMKM_E_INVALID, "bad path list");
+    if (row >= kMaxGenomes) return fail(c, GRMKM_E_UNSUPPORTED, "genome row out of range (at most 32768 genomes in one context)");
+    for (int i = 0; i < n_paths; ++i) {
+        Input in; in.row = row; in.kind = c->cfg.input_kind;
+        int r = read_file(c, paths[i], in.owned);
+        if (r) return r;
+        in.len = in.owned.size();
+        c->inputs.push_back(std::move(in));
+        c->inputs.back().host = c->inputs.back().owned.data();
+    }
+    c->built = false;
+    return GRMKM_OK;
+}
+
+int grmkm_set_genome_count(grmkm_ctx* c, uint32_t n) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    if (n > kMaxGenomes) return fail(c, GRMKM_E_UNSUPPORTED, "at most 32768 genomes in one context");
+    c->n_genomes_decl = n;
+    return GRMKM_OK;
+}
+
+
 int grmkm_build(grmkm_ctx* c) {
     if (check_ctx(c)) return GRMKM_E_INVALID;
-    return build_impl(c, 0, 1);
+    return build_guarded(c, 0, 1);
 }
 
 int grmkm_dims(const grmkm_ctx* c, uint64_t* n_kmers, uint32_t* n_words, uint32_t* n_genomes) {
@@ -1367,16 +1459,17 @@ int grmkm_set_bucket_bits(grmkm_ctx* c, uint32_t bits) {
 
 int grmkm_plan_bucket_bits(grmkm_ctx* c, uint32_t* bits) {
     if (check_ctx(c) || !bits) return GRMKM_E_INVALID;
-    uint32_t maxrow = 0;
-    for (const Input& in : c->inputs) maxrow = std::max(maxrow, in.row + 1);
-    *bits = auto_bucket_bits(c, std::max(1u, std::max(maxrow, c->n_genomes_decl)));
+    const InputTable tab = tabulate_inputs(c);
+    *bits = tab.G ? auto_bucket_bits(c, tab) : 6;
     return GRMKM_OK;
 }
 
 int grmkm_build_partial(grmkm_ctx* c, uint32_t n_ranks, uint64_t* counts) {
     if (check_ctx(c)) return GRMKM_E_INVALID;
     if (n_ranks < 1 || n_ranks > 16 || !counts) return fail(c, GRMKM_E_INVALID, "n_ranks must be 1..16");
-    int r = build_impl(c, 1, n_ranks);
+    if (n_ranks > 1 && !c->cfg.bucket_bits)
+        return fail(c, GRMKM_E_INVALID, "the ranks of a multi-GPU build agree on the bucket count first (grmkm_plan_bucket_bits / grmkm_set_bucket_bits)");
+    int r = build_guarded(c, 1, n_ranks);
     if (r) return r;
     for (uint32_t i = 0; i < n_ranks; ++i) counts[i] = c->part_counts[i];
     return GRMKM_OK;
@@ -1458,11 +1551,19 @@ int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
         if (src_counts[s] >= 0xFFFFFFFFULL) return fail(c, GRMKM_E_UNSUPPORTED, "more than 2^32 partial columns from one source");
     // every rank sees 1/P of the hash space: size the buckets for n_total * P entries over the full range
     const uint64_t per = std::max<uint64_t>(1, slots / 2);
-    const uint32_t mb = std::min(24u, std::max(6u, ceil_log2((n_total * n_ranks + per - 1) / per)));
-    const uint64_t Bfull = 1ULL << mb;
-    // this owner's slice of the bucket space (the partial columns of owner r lie in hash range [r/P, (r+1)/P))
-    const uint32_t b_lo = (uint32_t)(Bfull * rank / n_ranks);
-    const uint32_t b_hi = (uint32_t)((Bfull * (rank + 1) + n_ranks - 1) / n_ranks);
+    uint32_t mb = std::min(24u, std::max(6u, ceil_log2((n_total * n_ranks + per - 1) / per)));
+    if (const char* e = getenv("GRMKM_MERGE_BITS")) mb = (uint32_t)std::min(24, std::max(6, atoi(e)));      // tests: a merge grid finer than the owners' grid
+    // This owner's slice of the bucket space.  Ownership was dealt on the grid of the partial builds (2^ob buckets, ob =
+    // the agreed bucket count capped like build_impl caps it): owner r holds buckets [floor(B r / P), floor(B (r + 1) / P))
+    // of THAT grid, so the merge grid's slice is the same hash range -- scaled exactly when the merge grid is finer, the
+    // enclosing buckets when it is coarser (the sources hold nothing outside the owner's range).
+    if (n_ranks > 1 && !c->cfg.bucket_bits)
+        return fail(c, GRMKM_E_INVALID, "grmkm_merge_partials needs the bucket count the partial builds agreed on (grmkm_set_bucket_bits)");
+    const uint32_t ob = n_ranks > 1 ? std::min(kUnitMaxBucketBits, c->cfg.bucket_bits) : 0u;
+    const uint64_t own_lo = ((1ULL << ob) * rank) / n_ranks, own_hi = ((1ULL << ob) * (rank + 1)) / n_ranks;
+    uint32_t b_lo, b_hi;
+    if (mb >= ob) { b_lo = (uint32_t)(own_lo << (mb - ob)); b_hi = (uint32_t)(own_hi << (mb - ob)); }
+    else { b_lo = (uint32_t)(own_lo >> (ob - mb)); b_hi = (uint32_t)((own_hi + (1ULL << (ob - mb)) - 1) >> (ob - mb)); }
     const uint32_t nb = b_hi - b_lo, nb1 = nb + 1;
     ENSURE(c, c->scalars, S_COUNT * 8);
     ENSURE(c, c->offsets2, (size_t)(nb + 1) * 8);
@@ -1502,10 +1603,7 @@ int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
     CU_TRY(c, cudaStreamSynchronize(st));
     if (c->ev_ok) cudaEventRecord(c->ev[T_AGG], st);
     const uint64_t U = sc[S_U_NEEDED];
-    if (c->cfg.flags & GRMKM_FLAG_KMER_ORDER) {
-        int r = sort_and_gather(c, U, W_total, ucap, 2 * c->cfg.k, false, L);
-        if (r) return r;
-    } else {
+    {
         ENSURE(c, c->kmers, U * 8);
         ENSURE(c, c->matrix, (size_t)U * W_total * 8);
         k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->bcounts.p, (unsigned long long*)c->offsets2.p, nb,
@@ -1531,6 +1629,111 @@ int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
         cudaEventElapsedTime(&c->times.sort, c->ev[T_AGG], c->ev[T_SORT]);
         cudaEventElapsedTime(&c->times.total, c->ev[T_START], c->ev[T_SORT]);
     }
+    return GRMKM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels over the finished result (grmkm_result.cuh)
+// ------------------------------------------------------------------------------------------------
+int grmkm_result_checksum(grmkm_ctx* c, uint64_t out[2]) {
+    if (check_ctx(c) || !out) return GRMKM_E_INVALID;
+    if (!c->built) return fail(c, GRMKM_E_INVALID, "no result: call grmkm_build first");
+    out[0] = out[1] = 0;
+    if (!c->U) return GRMKM_OK;
+    CU_TRY(c, cudaSetDevice(c->device));
+    ENSURE(c, c->aux, 16);
+    CU_TRY(c, cudaMemsetAsync(c->aux.p, 0, 16, c->stream));
+    k_checksum<<<(uint32_t)std::min<uint64_t>((c->U + 255) / 256, (uint64_t)c->sm_count * 8), 256, 0, c->stream>>>(
+        (const unsigned long long*)c->kmers.p, (const unsigned long long*)c->matrix.p, c->U, c->W, (unsigned long long*)c->aux.p);
+    CU_TRY(c, cudaGetLastError());
+    c->stats.n_launches++;
+    CU_TRY(c, cudaMemcpyAsync(out, c->aux.p, 16, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return GRMKM_OK;
+}
+
+int grmkm_sum_rows(grmkm_ctx* c, const uint64_t* row_mask, uint32_t n_mask_words, uint32_t* dst, uint64_t cap) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    if (!c->built) return fail(c, GRMKM_E_INVALID, "no result: call grmkm_build first");
+    if (cap < c->U) return fail(c, GRMKM_E_CAPACITY, "sum buffer too small");
+    if (n_mask_words != c->W || (c->W && !row_mask)) return fail(c, GRMKM_E_INVALID, "the row mask has one word per matrix word row");
+    if (c->W > 512) return fail(c, GRMKM_E_UNSUPPORTED, "row masks of more than 512 words");
+    if (!c->U) return GRMKM_OK;
+    if (!dst) return fail(c, GRMKM_E_INVALID, "null dst");
+    CU_TRY(c, cudaSetDevice(c->device));
+    const size_t mask_bytes = ((size_t)c->W * 8 + 255) & ~size_t(255);
+    ENSURE(c, c->aux, mask_bytes + c->U * 4);
+    uint32_t* d_out = (uint32_t*)((uint8_t*)c->aux.p + mask_bytes);
+    CU_TRY(c, cudaMemcpyAsync(c->aux.p, row_mask, (size_t)c->W * 8, cudaMemcpyHostToDevice, c->stream));
+    k_sum_rows<<<(uint32_t)std::min<uint64_t>((c->U + 255) / 256, (uint64_t)c->sm_count * 16), 256, 0, c->stream>>>(
+        (const unsigned long long*)c->matrix.p, c->U, c->W, (const unsigned long long*)c->aux.p, d_out);
+    CU_TRY(c, cudaGetLastError());
+    c->stats.n_launches++;
+    CU_TRY(c, cudaMemcpyAsync(dst, d_out, c->U * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return GRMKM_OK;
+}
+
+int grmkm_gram(grmkm_ctx* c, uint64_t* dst, uint64_t cap) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    if (!c->built) return fail(c, GRMKM_E_INVALID, "no result: call grmkm_build first");
+    const uint64_t G = c->G;
+    if (cap < G * G) return fail(c, GRMKM_E_CAPACITY, "gram buffer too small");
+    if (!G) return GRMKM_OK;
+    if (!dst) return fail(c, GRMKM_E_INVALID, "null dst");
+    if (!c->U) { memset(dst, 0, G * G * 8); return GRMKM_OK; }
+    CU_TRY(c, cudaSetDevice(c->device));
+    const uint64_t UW = (c->U + 63) / 64;
+    const size_t rows_bytes = (size_t)c->W * 64 * UW * 8;
+    ENSURE(c, c->aux, rows_bytes + G * G * 8);
+    unsigned long long* d_rows = (unsigned long long*)c->aux.p;
+    unsigned long long* d_gram = (unsigned long long*)((uint8_t*)c->aux.p + rows_bytes);
+    k_bit_rows<<<(uint32_t)std::min<uint64_t>(((uint64_t)c->W * UW + 7) / 8, (uint64_t)c->sm_count * 32), 256, 0, c->stream>>>(
+        (const unsigned long long*)c->matrix.p, c->U, c->W, UW, d_rows);
+    k_gram<<<(uint32_t)std::min<uint64_t>(G * (G + 1) / 2, (uint64_t)c->sm_count * 16), 256, 0, c->stream>>>(d_rows, UW, (uint32_t)G, d_gram);
+    CU_TRY(c, cudaGetLastError());
+    c->stats.n_launches += 2;
+    CU_TRY(c, cudaMemcpyAsync(dst, d_gram, G * G * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return GRMKM_OK;
+}
+
+int grmkm_tsv_pack(grmkm_ctx* c, const uint8_t* body, uint64_t n_rows, uint32_t row_width, uint32_t k, uint32_t n_tsv_cols,
+                   uint32_t n_genomes, const uint32_t* sel, uint64_t* dst, uint64_t cap) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    const uint32_t W = (n_genomes + 63) / 64;
+    if (row_width != k + 2 * n_tsv_cols + 1) return fail(c, GRMKM_E_INVALID, "row width is not k + 2 x columns + 1");
+    if (cap < n_rows * W) return fail(c, GRMKM_E_CAPACITY, "matrix buffer too small");
+    if (n_genomes && !sel) return fail(c, GRMKM_E_INVALID, "null column selection");
+    for (uint32_t g = 0; g < n_genomes; ++g) if (sel[g] >= n_tsv_cols) return fail(c, GRMKM_E_INVALID, "column selection out of range");
+    if (!n_rows || !W) return GRMKM_OK;
+    if (!body || !dst) return fail(c, GRMKM_E_INVALID, "null buffer");
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    // staged in chunks of rows: H2D of chunk i + 1 is queued behind the kernel of chunk i on the same stream (the text
+    // arrives from pageable memory, so the copy itself is the bound)
+    const uint64_t rows_per = std::max<uint64_t>(1, (256ULL << 20) / row_width);
+    const size_t sel_bytes = ((size_t)n_genomes * 4 + 255) & ~size_t(255);
+    ENSURE(c, c->aux, sel_bytes + 256 + (size_t)n_rows * W * 8);
+    ENSURE(c, c->fmt, std::min<uint64_t>(n_rows, rows_per) * row_width);
+    uint32_t* d_sel = (uint32_t*)c->aux.p;
+    unsigned int* d_bad = (unsigned int*)((uint8_t*)c->aux.p + sel_bytes);
+    unsigned long long* d_mat = (unsigned long long*)((uint8_t*)c->aux.p + sel_bytes + 256);
+    CU_TRY(c, cudaMemcpyAsync(d_sel, sel, (size_t)n_genomes * 4, cudaMemcpyHostToDevice, st));
+    CU_TRY(c, cudaMemsetAsync(d_bad, 0, 4, st));
+    for (uint64_t j0 = 0; j0 < n_rows; j0 += rows_per) {
+        const uint64_t rows = std::min(rows_per, n_rows - j0);
+        CU_TRY(c, cudaMemcpyAsync(c->fmt.p, body + j0 * row_width, rows * row_width, cudaMemcpyHostToDevice, st));
+        k_tsv_pack<<<(uint32_t)std::min<uint64_t>((rows + 7) / 8, (uint64_t)c->sm_count * 32), 256, 0, st>>>(
+            (const uint8_t*)c->fmt.p, rows, row_width, k, n_genomes, d_sel, j0, n_rows, d_mat, d_bad);
+        CU_TRY(c, cudaGetLastError());
+        c->stats.n_launches++;
+    }
+    unsigned int bad = 0;
+    CU_TRY(c, cudaMemcpyAsync(dst, d_mat, (size_t)n_rows * W * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(c, cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(c, cudaStreamSynchronize(st));
+    if (bad) return fail(c, GRMKM_E_INVALID, "the k-mer matrix is not binary (cells must be 0 or 1)");
     return GRMKM_OK;
 }
 

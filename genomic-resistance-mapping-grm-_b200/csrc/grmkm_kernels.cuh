@@ -2,12 +2,10 @@
 //
 //   parse   : k_first_header, k_tile_tickets, k_pack (one pass: tile summaries resolved by decoupled look-back)
 //             FASTA/FASTQ text -> dense 2-bit base stream + validity mask   (multidsk's bank reader)
-//   extract : k_extract<COUNT|SCATTER>
-//             canonical k-mers -> hash buckets                              (multidsk's partitioning)
-//   count   : k_abundance        per-(k-mer, genome) abundance filter       (multidsk -abundance-min)
-//   merge   : k_aggregate        per-bucket shared-memory hash aggregation: presence bits of all
-//             genomes ORed into 64-genome words + singleton filter         (dsk2kover)
-//   order   : k_sort_*           LSD radix sort of the columns by canonical k-mer, k_gather
+//   units   : grmkm_units.cuh      minimizer-bounded super-k-mers -> content buckets -> dedupe -> k-mer records
+//   merge   : k_aggregate_cols     per-bucket shared-memory hash aggregation.  Presence: the bits of all genomes
+//             ORed into 64-genome words + singleton filter (dsk2kover); abundance: per-(k-mer, genome) counters
+//             and the -abundance-min filter (multidsk); owner-side merge of partial columns (N GPUs)
 //   emit    : k_kmer_strings, k_format_tsv                                  (kmer_sequences / Ray TSV)
 #pragma once
 #include "grmkm_device.cuh"
@@ -397,172 +395,19 @@ k_pack(const PackParams p) {
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// extract: canonical k-mers -> hash buckets
-// ------------------------------------------------------------------------------------------
-struct ExtractParams {
-    const unsigned long long* codes;
-    const uint32_t* valid;
-    const uint64_t* scalars;            // S_STREAM_LEN
-    const uint64_t* file_stream_start;  // [n_files + 1]
-    const FileDesc* files;
-    uint32_t n_files;
-    uint32_t k;
-    uint32_t bucket_bits;
-    uint32_t row_bits;
-    unsigned long long* hist;     // [B] (COUNT) / cursors [B] (SCATTER)
-    unsigned long long* records;  // SCATTER
-    uint32_t dbg;                 // timing experiments only: 1 = no atomics, 2 = no stores
-    const unsigned long long* offsets;
-};
-
-template <int MODE>  // 0 = count per bucket, 1 = scatter records
-__global__ void __launch_bounds__(kExtractThreads)
-k_extract(const ExtractParams p) {
-    extern __shared__ uint32_t s_hist[];   // COUNT: B counters
-    __shared__ uint32_t s_f0;
-    const uint32_t B = 1u << p.bucket_bits;
-    const uint64_t stream_len = p.scalars[S_STREAM_LEN];
-    const uint64_t n_groups = (stream_len + 31) >> 5;
-    const uint64_t n_etiles = (n_groups + kExtractThreads - 1) / kExtractThreads;
-    const uint32_t k = p.k;
-    const uint64_t kmask = k == 32 ? ~0ULL : ((1ULL << (2 * k)) - 1);
-    const uint32_t key_bits = 64 - p.bucket_bits;
-    const uint64_t key_mask = (1ULL << key_bits) - 1;
-    const int lane = threadIdx.x & 31;
-    if (MODE == 0) {
-        for (uint32_t i = threadIdx.x; i < B; i += blockDim.x) s_hist[i] = 0;
-        __syncthreads();
-    }
-    for (uint64_t et = blockIdx.x; et < n_etiles; et += gridDim.x) {
-        const uint64_t g = et * kExtractThreads + threadIdx.x;
-        // file of the tile's first position
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const uint64_t p0 = et * kExtractThreads * 32ULL;
-            uint32_t lo = 0, hi = p.n_files - 1;
-            while (lo < hi) {
-                const uint32_t mid = (lo + hi + 1) >> 1;
-                if (p.file_stream_start[mid] <= p0) lo = mid; else hi = mid - 1;
-            }
-            s_f0 = lo;
-        }
-        __syncthreads();
-        unsigned long long cur_c = 0; uint32_t cur_v = 0;
-        if (g < n_groups) { cur_c = p.codes[g]; cur_v = p.valid[g]; }
-        unsigned long long prev_c = __shfl_up_sync(0xffffffffu, cur_c, 1);
-        uint32_t prev_v = __shfl_up_sync(0xffffffffu, cur_v, 1);
-        if (lane == 0) {
-            if (g > 0 && g - 1 < n_groups) { prev_c = p.codes[g - 1]; prev_v = p.valid[g - 1]; }
-            else { prev_c = 0; prev_v = 0; }
-        }
-        if (g >= n_groups || cur_v == 0) continue;
-        const uint64_t pos0 = g * 32ULL;
-        uint32_t f = s_f0;
-        while (f + 1 < p.n_files && p.file_stream_start[f + 1] <= pos0) ++f;
-        uint64_t next_start = (f + 1 < p.n_files) ? p.file_stream_start[f + 1] : ~0ULL;
-        uint32_t row = p.files[f].row;
-        // state after the last entry of the previous group
-        const uint64_t le = k == 32 ? prev_c : ((prev_c >> (2 * (32 - k))) & kmask);
-        uint64_t rc = le ^ (0xAAAAAAAAAAAAAAAAULL & kmask);
-        uint64_t fw = rev2(le) >> (64 - 2 * k);
-        uint32_t run = min((uint32_t)__clz(~prev_v), k);
-#pragma unroll 4
-        for (int e = 0; e < 32; ++e) {
-            const uint32_t c = (uint32_t)(cur_c >> (2 * e)) & 3u;
-            fw = ((fw << 2) | c) & kmask;
-            rc = (rc >> 2) | ((uint64_t)(c ^ 2u) << (2 * (k - 1)));
-            if ((cur_v >> e) & 1u) run = min(run + 1, k); else run = 0;
-            if (run == k) {
-                const uint64_t pos = pos0 + e;
-                if (pos >= next_start) {
-                    while (f + 1 < p.n_files && p.file_stream_start[f + 1] <= pos) ++f;
-                    next_start = (f + 1 < p.n_files) ? p.file_stream_start[f + 1] : ~0ULL;
-                    row = p.files[f].row;
-                }
-                const uint64_t canon = fw < rc ? fw : rc;
-                const uint64_t h = khash(canon);
-                const uint32_t b = (uint32_t)(h >> key_bits);
-                if (MODE == 0) {
-                    atomicAdd(&s_hist[b], 1u);
-                } else {
-                    unsigned long long slot;
-                    if (p.dbg & 1) {
-                        const unsigned long long o0 = p.offsets[b], o1 = p.offsets[b + 1];
-                        slot = o0 + (o1 > o0 ? (h & key_mask) % (o1 - o0) : 0);
-                    } else slot = atomicAdd(&p.hist[(size_t)b * kCursorStride], 1ULL);
-                    if (!(p.dbg & 2)) p.records[slot] = ((h & key_mask) << p.row_bits) | row;
-                }
-            }
-        }
-    }
-    if (MODE == 0) {
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < B; i += blockDim.x) {
-            const uint32_t v = s_hist[i];
-            if (v) atomicAdd(&p.hist[(size_t)i * kCursorStride], (unsigned long long)v);
-        }
-    }
-}
-
-// ---- staged scatter: one tile of 16384 stream positions per CTA iteration -------------------------
-// Phase 1: every thread turns one 32-entry stream group into up to 32 hashed k-mers held in registers.
-//   Forward and reverse-complement values are funnel-shift extractions from a 128-bit window of the
-//   packed stream (and of its 2-bit-reversed copy), so there is no serial rolling dependency.
-//   The tile histogram is built with non-returning shared-memory atomics.
-// Phase 2: scan of the tile histogram; ONE global atomic per (tile, non-empty bucket) reserves space.
-// Phase 3: counting sort of the tile into shared memory (slot = atomic walk of the bucket's run).
-// Phase 4: copy out; records of one bucket leave the SM as contiguous runs.
-// Bucket regions are either exact (cursors = prefix sums from a count pass, cap == 0) or
-// over-provisioned (region b = [b*cap, (b+1)*cap)); an overflowing bucket raises S_OVERFLOW and its
-// records are diverted to a dump area so nothing is corrupted; the host then re-runs the exact path.
+// ---- tile sort of hashed k-mers (k_units_expand): one tile = kStThreads x kStPerThread k-mers per CTA iteration;
+// tile histogram with shared-memory atomics, ONE global reservation per (tile, bucket), counting sort in shared
+// memory, bucket runs on the way out.  Bucket regions are exact (cursors = prefix sums of a count pass) or
+// over-provisioned (region b = [b * cap, (b + 1) * cap)); an overflowing bucket raises a flag and its records go
+// to a dump area, the host then re-runs with exact offsets.
 constexpr int kStThreads = 512;
-constexpr int kStPerThread = 32;                       // one 32-entry stream group per thread
+constexpr int kStPerThread = 32;                       // up to 32 k-mers per thread
 constexpr int kStTile = kStThreads * kStPerThread;     // 16384 positions = 512 groups
 constexpr int kStMaxBuckets = 4096;
 constexpr int kStMaxBins = kStMaxBuckets / kStThreads; // bins per thread in phase 2
 
 __host__ __device__ inline size_t staged_smem_bytes(uint32_t B) {
     return (size_t)B * (8 + 4 + 4) + (size_t)kStTile * (8 + 2);
-}
-
-struct ScatterParams {
-    const unsigned long long* codes;
-    const uint32_t* valid;
-    const uint64_t* scalars;            // S_STREAM_LEN
-    const uint64_t* file_stream_start;  // [n_files + 1]
-    const FileDesc* files;
-    const uint32_t* tile_file;          // file of the first position of every scatter tile
-    uint32_t n_files;
-    uint32_t k;
-    uint32_t bucket_bits;
-    uint32_t row_bits;
-    unsigned long long* cursors;        // [B]
-    unsigned long long* records;
-    unsigned long long cap;             // records per bucket region, 0 = exact offsets
-    unsigned long long dump;            // index of the dump area (kStTile records)
-    unsigned long long* overflow;       // scalar raised when a region is too small
-};
-
-// file of the first position of every scatter tile (one thread per tile)
-__global__ void k_scatter_tile_files(const uint64_t* __restrict__ scalars, const uint64_t* __restrict__ fss,
-                                     uint32_t n_files, uint32_t* __restrict__ tile_file, uint64_t max_tiles) {
-    const uint64_t tile = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tile >= max_tiles) return;
-    const uint64_t p0 = tile * (uint64_t)kStTile;
-    if (p0 >= scalars[S_STREAM_LEN]) return;
-    uint32_t lo = 0, hi = n_files - 1;
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi + 1) >> 1;
-        if (fss[mid] <= p0) lo = mid; else hi = mid - 1;
-    }
-    tile_file[tile] = lo;
-}
-
-__device__ __noinline__ uint32_t row_of_position(const uint64_t* __restrict__ fss, const FileDesc* __restrict__ files,
-                                                 uint32_t n_files, uint32_t f, uint64_t pos) {
-    while (f + 1 < n_files && fss[f + 1] <= pos) ++f;
-    return files[f].row;
 }
 
 __device__ __forceinline__ uint32_t rev2_32(uint32_t x) {
@@ -598,176 +443,6 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp
     const uint32_t r = s_warp[warp] + inc - v;
     __syncthreads();
     return r;
-}
-
-// phase 1 body: ALL = every window of this group is valid (no per-entry test)
-template <bool ALL>
-__device__ __forceinline__ uint32_t scatter_hash_group(const uint32_t (&r)[4], const uint32_t (&y)[4], uint32_t n0, uint32_t n1,
-                                                       uint32_t kbits, uint32_t kmask_lo, uint32_t kmask_hi, uint32_t key_bits,
-                                                       uint32_t* s_cnt, unsigned long long (&hsh)[kStPerThread]) {
-    uint32_t have = 0;
-#pragma unroll
-    for (int e = 0; e < kStPerThread; ++e) {
-        if (ALL || (__funnelshift_r(n0, n1, e) & kbits) == 0) {
-            const int fs = 2 * (31 - e), fw_w = fs >> 5, fw_s = fs & 31;
-            const int rs = 2 * e, rc_w = rs >> 5, rc_s = rs & 31;
-            const uint32_t fw_lo = __funnelshift_r(r[fw_w], r[fw_w + 1], fw_s) & kmask_lo;
-            const uint32_t fw_hi = __funnelshift_r(r[fw_w + 1], r[fw_w + 2], fw_s) & kmask_hi;
-            const uint32_t rc_lo = __funnelshift_r(y[rc_w], y[rc_w + 1], rc_s) & kmask_lo;
-            const uint32_t rc_hi = __funnelshift_r(y[rc_w + 1], y[rc_w + 2], rc_s) & kmask_hi;
-            const uint64_t fw = ((uint64_t)fw_hi << 32) | fw_lo, rc = ((uint64_t)rc_hi << 32) | rc_lo;
-            const uint64_t h = khash(fw < rc ? fw : rc);
-            atomicAdd(&s_cnt[(uint32_t)(h >> key_bits)], 1u);
-            hsh[e] = h;
-            if (!ALL) have |= 1u << e;
-        }
-    }
-    return ALL ? 0xFFFFFFFFu : have;
-}
-
-// phase 3 body: the hash goes to its sorted slot; the row only when the tile spans several genome rows
-template <bool ALL, bool ROWS>
-__device__ __forceinline__ void scatter_place_group(const unsigned long long (&hsh)[kStPerThread], uint32_t have, uint32_t key_bits,
-                                                    uint32_t row0, bool one_row, uint32_t f, uint64_t pos0,
-                                                    const ScatterParams& p, uint32_t* s_off, unsigned long long* s_rec,
-                                                    uint16_t* s_row) {
-#pragma unroll
-    for (int e = 0; e < kStPerThread; ++e) {
-        if (ALL || ((have >> e) & 1u)) {
-            const uint32_t dst = atomicAdd(&s_off[(uint32_t)(hsh[e] >> key_bits)], 1u);   // s_off[b] walks through the bucket's run
-            s_rec[dst] = hsh[e];
-            if (ROWS) s_row[dst] = (uint16_t)(one_row ? row0 : row_of_position(p.file_stream_start, p.files, p.n_files, f, pos0 + e));
-        }
-    }
-}
-
-template <int KT>   // compile-time k, or 0 = p.k
-__global__ void __launch_bounds__(kStThreads, 1)
-k_scatter(const ScatterParams p) {
-    extern __shared__ unsigned long long s_dyn[];
-    __shared__ uint32_t s_total;
-    __shared__ uint32_t s_warp[33];
-    const uint32_t B = 1u << p.bucket_bits;
-    unsigned long long* s_delta = s_dyn;                         // [B]   global base - tile offset
-    unsigned long long* s_rec = s_delta + B;                     // [kStTile]
-    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_rec + kStTile);   // [B]
-    uint32_t* s_off = s_cnt + B;                                 // [B]
-    uint16_t* s_row = reinterpret_cast<uint16_t*>(s_off + B);    // [kStTile] genome rows, only for tiles that span several
-    const uint64_t stream_len = p.scalars[S_STREAM_LEN];
-    const uint64_t n_groups = (stream_len + 31) >> 5;
-    const uint64_t n_tiles = (n_groups + kStThreads - 1) / kStThreads;
-    const uint32_t k = KT ? (uint32_t)KT : p.k;
-    const uint32_t kmask_lo = k >= 16 ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
-    const uint32_t kmask_hi = k <= 16 ? 0u : (k == 32 ? 0xFFFFFFFFu : ((1u << (2 * k - 32)) - 1u));
-    const uint32_t kbits = k == 32 ? 0xFFFFFFFFu : ((1u << k) - 1u);
-    const uint32_t key_bits = 64 - p.bucket_bits;
-    const uint32_t row_bits = p.row_bits;
-    for (uint32_t i = threadIdx.x; i < B; i += kStThreads) s_cnt[i] = 0;
-    __syncthreads();
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        // ---- phase 1: 32 hashed k-mers per thread into registers + tile histogram
-        const uint64_t g = tile * kStThreads + threadIdx.x;
-        unsigned long long cur_c = 0, prev_c = 0; uint32_t cur_v = 0, prev_v = 0;
-        if (g < n_groups) {
-            cur_c = p.codes[g]; cur_v = p.valid[g];
-            if (g > 0) { prev_c = p.codes[g - 1]; prev_v = p.valid[g - 1]; }
-        }
-        unsigned long long hsh[kStPerThread];     // kept across the barriers
-        uint32_t have = 0, row0 = 0, f = 0;
-        bool one_row = true;
-        const uint64_t pos0 = g * 32ULL;
-        if (cur_v) {
-            // 128-bit window: the 32 entries before mine (x[0], x[1]) and my 32 entries (x[2], x[3]); entry j at bits 2j
-            const uint32_t x[4] = {(uint32_t)prev_c, (uint32_t)(prev_c >> 32), (uint32_t)cur_c, (uint32_t)(cur_c >> 32)};
-            // invalid-entry bits, shifted so that bit e is the first entry of the window of my entry e
-            const unsigned long long nvs = (~((unsigned long long)prev_v | ((unsigned long long)cur_v << 32))) >> (33 - k);
-            const uint32_t n0 = (uint32_t)nvs, n1 = (uint32_t)(nvs >> 32);
-            // reverse-complement source: window >> 2(33-k), complemented (code ^ 2); forward source: 2-bit reversed window
-            const uint32_t S0 = 2 * (33 - k);
-            unsigned long long Yl, Yh;
-            if (S0 == 64) { Yl = cur_c; Yh = 0; }
-            else { Yl = (prev_c >> S0) | (cur_c << (64 - S0)); Yh = cur_c >> S0; }
-            const uint32_t y[4] = {(uint32_t)Yl ^ 0xAAAAAAAAu, (uint32_t)(Yl >> 32) ^ 0xAAAAAAAAu,
-                                   (uint32_t)Yh ^ 0xAAAAAAAAu, (uint32_t)(Yh >> 32) ^ 0xAAAAAAAAu};
-            const uint32_t r[4] = {rev2_32(x[3]), rev2_32(x[2]), rev2_32(x[1]), rev2_32(x[0])};
-            f = p.tile_file[tile];
-            while (f + 1 < p.n_files && p.file_stream_start[f + 1] <= pos0) ++f;
-            const uint64_t next_start = (f + 1 < p.n_files) ? p.file_stream_start[f + 1] : ~0ULL;
-            row0 = p.files[f].row;
-            one_row = pos0 + kStPerThread <= next_start;
-            // windows of my entries cover bits [0, 31 + k) of nvs
-            const bool all_valid = (n0 | (n1 & ((1u << (k - 1)) - 1u))) == 0;
-            if (all_valid) have = scatter_hash_group<true>(r, y, n0, n1, kbits, kmask_lo, kmask_hi, key_bits, s_cnt, hsh);
-            else have = scatter_hash_group<false>(r, y, n0, n1, kbits, kmask_lo, kmask_hi, key_bits, s_cnt, hsh);
-        }
-        __syncthreads();
-        // ---- phase 2: scan the tile histogram, reserve global space, clear the histogram.  Thread t owns bins
-        // t, t + 512, ... (conflict-free); the tile is laid out thread-major, which is as good as bucket order.
-        {
-            uint32_t cnt[kStMaxBins];
-            uint32_t sum = 0;
-#pragma unroll
-            for (uint32_t i = 0; i < (uint32_t)kStMaxBins; ++i) {
-                const uint32_t bin = i * kStThreads + threadIdx.x;
-                cnt[i] = 0;
-                if (bin < B) { cnt[i] = s_cnt[bin]; s_cnt[bin] = 0; sum += cnt[i]; }
-            }
-            unsigned long long gb[kStMaxBins];
-#pragma unroll
-            for (uint32_t i = 0; i < (uint32_t)kStMaxBins; ++i) {      // all reservations in flight together
-                const uint32_t bin = i * kStThreads + threadIdx.x;
-                gb[i] = cnt[i] ? atomicAdd(&p.cursors[bin], (unsigned long long)cnt[i]) : 0ULL;
-            }
-            uint32_t total;
-            uint32_t off = block_excl_scan<kStThreads>(sum, s_warp, total);
-            if (threadIdx.x == 0) s_total = total;
-#pragma unroll
-            for (uint32_t i = 0; i < (uint32_t)kStMaxBins; ++i) {
-                const uint32_t bin = i * kStThreads + threadIdx.x;
-                if (bin < B) {
-                    s_off[bin] = off;
-                    if (cnt[i]) {
-                        if (p.cap && gb[i] + cnt[i] > (unsigned long long)(bin + 1) * p.cap) {
-                            *p.overflow = 1ULL;           // region too small: divert, the host re-runs the exact path
-                            s_delta[bin] = p.dump;
-                        } else {
-                            s_delta[bin] = gb[i] - off;
-                        }
-                    }
-                    off += cnt[i];
-                }
-            }
-        }
-        // does the tile lie inside one file (one genome row)?  Then the row is not staged per record.
-        const uint32_t tf = p.tile_file[tile];
-        const bool tile_one_row = (tf + 1 >= p.n_files) || p.file_stream_start[tf + 1] >= (tile + 1) * (uint64_t)kStTile;
-        const uint32_t tile_row = p.files[tf].row;
-        __syncthreads();
-        // ---- phase 3: counting sort into shared memory
-        if (tile_one_row) {
-            if (have == 0xFFFFFFFFu) scatter_place_group<true, false>(hsh, have, key_bits, row0, one_row, f, pos0, p, s_off, s_rec, s_row);
-            else if (have) scatter_place_group<false, false>(hsh, have, key_bits, row0, one_row, f, pos0, p, s_off, s_rec, s_row);
-        } else if (have) {
-            scatter_place_group<false, true>(hsh, have, key_bits, row0, one_row, f, pos0, p, s_off, s_rec, s_row);
-        }
-        __syncthreads();
-        // ---- phase 4: copy out; consecutive threads write consecutive records of a bucket.  Record =
-        // (hash << row_bits) | row: the top row_bits bits of the hash are bucket bits and fall off.  No barrier
-        // after it: phase 1 of the next tile touches only s_cnt (already cleared) and registers.
-        const uint32_t total = s_total;
-        if (tile_one_row) {
-#pragma unroll 4
-            for (uint32_t i = threadIdx.x; i < total; i += kStThreads) {
-                const unsigned long long h = s_rec[i];
-                p.records[s_delta[(uint32_t)(h >> key_bits)] + i] = (h << row_bits) | tile_row;
-            }
-        } else {
-            for (uint32_t i = threadIdx.x; i < total; i += kStThreads) {
-                const unsigned long long h = s_rec[i];
-                p.records[s_delta[(uint32_t)(h >> key_bits)] + i] = (h << row_bits) | s_row[i];
-            }
-        }
-    }
 }
 
 // sum of one u64 per thread over a block of up to 1024 threads (valid in thread 0); a 64-bit atomicAdd on shared
@@ -841,193 +516,8 @@ k_bucket_offsets(unsigned long long* __restrict__ hist_cursor, unsigned long lon
     if (threadIdx.x == 1023) { offsets[B] = s_part[1023]; scalars[total_scalar] = s_part[1023]; }
 }
 
-// ------------------------------------------------------------------------------------------
-// aggregate: per-bucket shared-memory hash table
-// ------------------------------------------------------------------------------------------
-struct AggParams {
-    const unsigned long long* records;   // (key << row_bits) | row
-    const unsigned long long* begin;     // [B] first record of every bucket
-    const unsigned long long* end;       // [B] one past its last record
-    uint32_t B;
-    uint32_t bucket_bits;
-    uint32_t row_bits;
-    uint32_t n_words;        // words per column handled here
-    uint32_t slots;          // table capacity
-    uint32_t keep_singletons;
-    uint32_t mode;           // 0: final columns (k-mers), 1: partial columns (hash keys), 2: abundance filter
-    uint32_t min_abundance;  // mode 2
-    unsigned long long* out_keys;    // [cap]
-    unsigned long long* out_words;   // [n_words][cap]  (mode 0/1)
-    unsigned long long cap;
-    unsigned long long* scalars;
-    unsigned long long* bucket_out_counts;  // mode 1/2: entries emitted per bucket (atomic)
-    unsigned long long* out_records;        // mode 2: filtered records, written at the bucket's own offset
-    uint32_t b_begin, b_end;                // bucket range handled by this launch
-    // mode 3 (owner-side merge of partial columns): records are refs (word offset << 8 | source)
-    const unsigned long long* parts;
-    uint32_t src_words[16];
-    uint32_t src_woff[16];
-};
-
-__device__ __forceinline__ uint32_t slot_of(uint64_t key, uint32_t slots) {
-    uint32_t hh = (uint32_t)key ^ (uint32_t)(key >> 32);
-    hh *= 0x9E3779B1u;
-    return __umulhi(hh, slots);
-}
-
-// Table key for MODE 0/1 is the hash key; for MODE 2 it is the whole record (key, row) and the
-// single word per slot is an abundance counter.
-template <int MODE>
-__global__ void __launch_bounds__(kAggThreads, 1)
-k_aggregate(const AggParams p) {
-    extern __shared__ unsigned long long s_tab[];   // keys[slots] then words[n_words][slots]
-    __shared__ uint32_t s_overflow, s_sp, s_cnt, s_kept, s_wr;
-    __shared__ uint32_t s_depth[72];
-    __shared__ unsigned long long s_idx[72];
-    __shared__ unsigned long long s_base;
-    __shared__ uint32_t s_red[kAggThreads / 32];
-    const uint32_t slots = p.slots;
-    const uint32_t W = (MODE == 2) ? 1u : p.n_words;
-    constexpr bool kFinal = (MODE == 0 || MODE == 3);   // emits filtered k-mer columns
-    unsigned long long* keys = s_tab;
-    unsigned long long* words = s_tab + slots;
-    const uint32_t key_bits = (MODE == 2) ? (64 - p.bucket_bits + p.row_bits) : (64 - p.bucket_bits);
-    const uint64_t row_mask = (1ULL << p.row_bits) - 1;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-    for (uint32_t b = p.b_begin + blockIdx.x; b < p.b_end; b += gridDim.x) {
-        const unsigned long long rbeg = p.begin[b], rend = p.end[b];
-        if (rbeg == rend) continue;
-        __syncthreads();
-        if (threadIdx.x == 0) { s_sp = 1; s_depth[0] = 0; s_idx[0] = 0; s_wr = 0; }
-        __syncthreads();
-        while (true) {
-            __syncthreads();
-            if (s_sp == 0) break;
-            const uint32_t depth = s_depth[s_sp - 1];
-            const unsigned long long ridx = s_idx[s_sp - 1];
-            __syncthreads();
-            if (threadIdx.x == 0) { s_sp--; s_overflow = 0; s_cnt = 0; s_kept = 0; }
-            for (uint32_t i = threadIdx.x; i < slots; i += blockDim.x) keys[i] = kEmptyKey;
-            for (uint32_t i = threadIdx.x; i < slots * W; i += blockDim.x) words[i] = 0;
-            __syncthreads();
-            // ---- stream the bucket's records through the table
-            for (unsigned long long r = rbeg + threadIdx.x; r < rend; r += blockDim.x) {
-                if (*(volatile uint32_t*)&s_overflow) break;
-                const unsigned long long rec = p.records[r];
-                unsigned long long key; uint32_t row = 0;
-                const unsigned long long* ent = nullptr;
-                if (MODE == 2) key = rec;
-                else if (MODE == 3) { ent = p.parts + (rec >> 8); key = ent[0] & ((1ULL << key_bits) - 1); }
-                else { key = rec >> p.row_bits; row = (uint32_t)(rec & row_mask); }
-                // records carry (bucket_bits - row_bits) redundant bucket bits above the key: mask them for the range test
-                if (depth && ((key & (key_bits >= 64 ? ~0ULL : ((1ULL << key_bits) - 1))) >> (key_bits - depth)) != ridx) continue;
-                uint32_t slot = slot_of(key, slots);
-                bool hit = false;
-                for (int probe = 0; probe < kMaxProbe; ++probe) {
-                    unsigned long long k0 = *(volatile unsigned long long*)&keys[slot];
-                    if (k0 == kEmptyKey) k0 = atomicCAS(&keys[slot], kEmptyKey, key);
-                    if (k0 == kEmptyKey || k0 == key) { hit = true; break; }
-                    slot = slot + 1 == slots ? 0 : slot + 1;
-                }
-                if (!hit) { s_overflow = 1; break; }
-                if (MODE == 2) {
-                    atomicAdd((uint32_t*)&words[slot], 1u);
-                } else if (MODE == 3) {
-                    const uint32_t src = (uint32_t)(rec & 255u), nw = p.src_words[src], wo = p.src_woff[src];
-                    for (uint32_t w = 0; w < nw; ++w) {
-                        const unsigned long long v = ent[1 + w];
-                        if (v) atomicOr(&words[(wo + w) * slots + slot], v);
-                    }
-                } else {
-                    const uint32_t bit = 63u - (row & 63u);      // utils.py:144-154
-                    uint32_t* w32 = (uint32_t*)&words[(row >> 6) * slots + slot];
-                    atomicOr(&w32[bit >> 5], 1u << (bit & 31u));
-                }
-            }
-            __syncthreads();
-            if (s_overflow) {
-                // split this key range in two and retry (terminates: a range of one key needs one slot)
-                if (threadIdx.x == 0) {
-                    s_depth[s_sp] = depth + 1; s_idx[s_sp] = ridx * 2 + 1; s_sp++;
-                    s_depth[s_sp] = depth + 1; s_idx[s_sp] = ridx * 2; s_sp++;
-                    atomicAdd(&p.scalars[S_N_SPLITS], 1ULL);
-                }
-                continue;
-            }
-            // ---- count what this range emits
-            uint32_t occ = 0, kept = 0;
-            for (uint32_t i = threadIdx.x; i < slots; i += blockDim.x) {
-                if (keys[i] != kEmptyKey) {
-                    occ++;
-                    if (MODE == 2) kept += ((uint32_t)words[i] >= p.min_abundance);
-                    else if (MODE == 1) kept++;
-                    else {
-                        uint32_t pc = 0;
-                        for (uint32_t w = 0; w < W; ++w) pc += __popcll(words[w * slots + i]);
-                        kept += (pc >= 2 || p.keep_singletons);
-                    }
-                }
-            }
-            occ = __reduce_add_sync(0xffffffffu, occ);
-            kept = __reduce_add_sync(0xffffffffu, kept);
-            if (lane == 0) { atomicAdd(&s_cnt, occ); atomicAdd(&s_kept, kept); }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                if (MODE == 2) {
-                    s_base = rbeg + s_wr;           // filtered records stay inside the bucket's own range
-                    s_wr += s_kept;
-                } else {
-                    s_base = atomicAdd(&p.scalars[S_U_NEEDED], (unsigned long long)s_kept);
-                    atomicAdd(&p.scalars[S_N_DISTINCT], (unsigned long long)s_cnt);
-                    if (MODE == 1) atomicAdd(&p.bucket_out_counts[b], (unsigned long long)s_kept);
-                }
-                s_cnt = 0;
-            }
-            __syncthreads();
-            // ---- emit
-            const unsigned long long base = s_base;
-            for (uint32_t i0 = 0; i0 < slots; i0 += blockDim.x) {
-                const uint32_t i = i0 + threadIdx.x;
-                bool keep = false;
-                unsigned long long key = 0;
-                if (i < slots) {
-                    key = keys[i];
-                    if (key != kEmptyKey) {
-                        if (MODE == 2) keep = ((uint32_t)words[i] >= p.min_abundance);
-                        else if (MODE == 1) keep = true;
-                        else {
-                            uint32_t pc = 0;
-                            for (uint32_t w = 0; w < W; ++w) pc += __popcll(words[w * slots + i]);
-                            keep = (pc >= 2 || p.keep_singletons);
-                        }
-                    }
-                }
-                const uint32_t m = __ballot_sync(0xffffffffu, keep);
-                uint32_t wbase = 0;
-                if (lane == 0 && m) wbase = atomicAdd(&s_cnt, __popc(m));
-                wbase = __shfl_sync(0xffffffffu, wbase, 0);
-                if (keep) {
-                    const unsigned long long o = base + wbase + __popc(m & lanemask_lt());
-                    if (MODE == 2) {
-                        p.out_records[o] = key;
-                    } else if (o < p.cap) {
-                        const unsigned long long h = ((unsigned long long)b << key_bits) | key;
-                        p.out_keys[o] = kFinal ? kunhash(h) : h;
-                        for (uint32_t w = 0; w < W; ++w) p.out_words[w * p.cap + o] = words[w * slots + i];
-                    }
-                }
-            }
-        }
-        if (MODE == 2 && threadIdx.x == 0) {
-            p.bucket_out_counts[b] = s_wr;
-            atomicAdd(&p.scalars[S_N_SOLID], (unsigned long long)s_wr);
-        }
-    }
-    (void)warp; (void)s_red;
-}
-
-// ---- column aggregation (modes 0 = final columns, 1 = partial columns, 3 = owner-side merge of partials) ----
+// ---- column aggregation: MODE 4 = final columns, 5 = partial columns (N GPUs), 3 = owner-side merge of partial
+// columns, 6 = abundance round (per-genome counters -> solid presence records), 7 = pooled count table ----
 // One CTA per hash bucket.  The bucket's records stream through a shared-memory table
 //   keys[slots + tail] (u64), w32[2W][slots + tail] (presence half-words), kept[slots + tail] (u8)
 // with eight coalesced loads in flight per thread.  Genome row g lives in half-word plane (g >> 5) ^ 1 at bit
@@ -1056,7 +546,7 @@ __device__ __forceinline__ uint32_t home_slot(unsigned long long key, uint32_t s
 }
 
 struct AggParams2 {
-    const unsigned long long* records;   // MODE 0/1: (hash << row_bits) | row;  MODE 3: refs (word offset << 8) | source
+    const unsigned long long* records;   // MODE 4-7: wide records [(hash << row_bits) | group, words]; MODE 3: unused (parts / bounds)
     const unsigned long long* begin;     // [B]
     const unsigned long long* end;       // [B]
     uint32_t bucket_bits, row_bits, n_words, slots, keep_singletons;
@@ -1083,6 +573,13 @@ struct AggParams2 {
     const unsigned long long* parts;
     const unsigned long long* bounds;
     uint32_t n_src;
+    // MODE 6 / 7 (abundance): the table planes are u32 COUNTERS, one per genome row of the round (records
+    // [(hash << row_bits) | local row, count]); a row is solid when its counter reaches min_abundance (multidsk
+    // -abundance-min, kmer_count.py:48).  MODE 6 emits the round's solid presence as wide records of ONE word
+    // [(hash << out_wbits) | out_word, bits] for the final presence aggregate; MODE 7 (pooled counts, src/app.py:1372)
+    // emits (k-mer, count of local row 0).
+    uint32_t min_abundance, round_rows, round_row0, out_wbits, out_word;
+    ulonglong2* out_wide;
     unsigned long long src_off[16];      // first u64 word of the source in parts
     uint32_t src_words[16];
     uint32_t src_woff[16];
@@ -1111,45 +608,9 @@ __device__ __forceinline__ bool agg_insert(unsigned long long* keys, uint32_t& s
     return ok;
 }
 
-template <bool FILTER>
-__device__ __forceinline__ void agg_stream(const AggParams2& p, const AggTable& t, const unsigned long long* __restrict__ recs,
-                                           uint32_t n, uint32_t key_bits, uint32_t depth, unsigned long long ridx,
-                                           volatile uint32_t* overflow) {
-    const uint32_t row_bits = p.row_bits;
-    const uint32_t row_mask = (1u << row_bits) - 1u;
-    const uint32_t shift = 64 - key_bits + depth;
-    const uint32_t slots = t.slots, total = t.total;
-    unsigned long long* const keys = t.keys;
-    uint32_t* const w32 = t.w32;
-    for (uint32_t base0 = 0; base0 < n; base0 += kAggThreads * kAggBatch) {
-        const uint32_t base = base0 + threadIdx.x;
-        unsigned long long r[kAggBatch];
-#pragma unroll
-        for (int j = 0; j < kAggBatch; ++j) {
-            const uint32_t idx = base + j * kAggThreads;
-            r[j] = idx < n ? __ldcs(recs + idx) : 0ULL;
-        }
-        if (__any_sync(0xffffffffu, *overflow != 0)) break;
-#pragma unroll
-        for (int j = 0; j < kAggBatch; ++j) {
-            const unsigned long long key = r[j] >> row_bits;      // carries (bucket_bits - row_bits) redundant bucket bits on top
-            bool act = base + j * kAggThreads < n;
-            if (FILTER) act = act && ((key << (64 - key_bits)) >> (64 - depth)) == ridx;
-            uint32_t slot = home_slot(key, shift, slots);
-            const bool ok = agg_insert(keys, slot, key, act);
-            if (act) {
-                if (ok) {
-                    const uint32_t row = (uint32_t)r[j] & row_mask;
-                    atomicOr(&w32[((row >> 5) ^ 1u) * total + slot], 0x80000000u >> (row & 31u));
-                } else *overflow = 1;
-            }
-        }
-    }
-}
-
 // MODE 4 / 5: wide records [(hash << row_bits) | genome group, wide_words presence words (, padding)] of
 // wide_stride u64 each (the unit path, grmkm_units.cuh); the words of group g are matrix words g * wide_words ..
-template <bool FILTER>
+template <bool FILTER, bool COUNTS>
 __device__ __forceinline__ void agg_stream_wide(const AggParams2& p, const AggTable& t, const unsigned long long* __restrict__ recs,
                                                 uint32_t n, uint32_t key_bits, uint32_t depth, unsigned long long ridx,
                                                 volatile uint32_t* overflow) {
@@ -1181,7 +642,10 @@ __device__ __forceinline__ void agg_stream_wide(const AggParams2& p, const AggTa
             uint32_t slot = home_slot(key, shift, slots);
             const bool ok = agg_insert(keys, slot, key, act);
             if (act) {
-                if (ok) {
+                if (ok && COUNTS) {
+                    // abundance: the record's word is the number of occurrences it stands for
+                    atomicAdd(&w32[((uint32_t)r[j].x & wmask) * total + slot], (uint32_t)r[j].y);
+                } else if (ok) {
                     const uint32_t w0 = ((uint32_t)r[j].x & wmask) * WB;
                     {
                         const uint32_t vlo = (uint32_t)r[j].y, vhi = (uint32_t)(r[j].y >> 32);
@@ -1270,7 +734,9 @@ __device__ __forceinline__ uint32_t agg_mark(const AggParams2& p, const AggTable
         uint32_t kf = 0;
         if (i < t.total && t.keys[i] != kEmptyKey) {
             occ++;
-            if (MODE == 1 || MODE == 5 || p.keep_singletons) kf = 1;
+            if (MODE == 6 || MODE == 7) {
+                for (uint32_t r = 0; r < p.round_rows; ++r) kf |= t.w32[r * t.total + i] >= p.min_abundance;
+            } else if (MODE == 1 || MODE == 5 || p.keep_singletons) kf = 1;
             else if (MODE == 3) {
                 uint32_t pc = 0;
                 for (uint32_t s = 0; s < p.n_src; ++s) {
@@ -1331,6 +797,13 @@ __device__ __forceinline__ void agg_emit(const AggParams2& p, const AggTable& t,
         const unsigned long long o = base + rank;
         if (o < p.cap) {
             const unsigned long long h = ((unsigned long long)b << key_bits) | (key & key_mask);
+            if (MODE == 6) {
+                unsigned long long bits = 0;
+                for (uint32_t r = 0; r < p.round_rows; ++r)
+                    if (t.w32[r * t.total + i] >= p.min_abundance) bits |= 1ULL << (63u - ((p.round_row0 + r) & 63u));
+                p.out_wide[o] = make_ulonglong2((h << p.out_wbits) | p.out_word, bits);
+                continue;
+            }
             p.out_keys[o] = (MODE == 1 || MODE == 5) ? h : kunhash(h);
             if (MODE == 3) {
                 for (uint32_t s = 0; s < p.n_src; ++s) {
@@ -1466,12 +939,9 @@ k_aggregate_cols(const AggParams2 p) {
             if (MODE == 3) {
                 if (depth == 0) agg_stream_parts<false>(p, t, b, key_bits, 0, 0, &s_overflow);
                 else agg_stream_parts<true>(p, t, b, key_bits, depth, ridx, &s_overflow);
-            } else if (MODE >= 4) {
-                if (depth == 0) agg_stream_wide<false>(p, t, recs, n, key_bits, 0, 0, &s_overflow);
-                else agg_stream_wide<true>(p, t, recs, n, key_bits, depth, ridx, &s_overflow);
             } else {
-                if (depth == 0) agg_stream<false>(p, t, recs, n, key_bits, 0, 0, &s_overflow);
-                else agg_stream<true>(p, t, recs, n, key_bits, depth, ridx, &s_overflow);
+                if (depth == 0) agg_stream_wide<false, (MODE >= 6)>(p, t, recs, n, key_bits, 0, 0, &s_overflow);
+                else agg_stream_wide<true, (MODE >= 6)>(p, t, recs, n, key_bits, depth, ridx, &s_overflow);
             }
             __syncthreads();
             if (s_overflow) {
@@ -1553,6 +1023,17 @@ k_gather_buckets(const unsigned long long* __restrict__ tmp_keys, const unsigned
     (void)U;
 }
 
+// abundance builds: the solid presence records of all rounds (16 bytes each; a round leaves one chunk per virtual
+// bucket) -> bucket-contiguous order for the final presence aggregate.  segs = [source, destination, count] triples.
+__global__ void __launch_bounds__(128)
+k_gather_segments(const ulonglong2* __restrict__ src, const unsigned long long* __restrict__ segs, uint32_t n_segs,
+                  ulonglong2* __restrict__ dst) {
+    for (uint32_t s = blockIdx.x; s < n_segs; s += gridDim.x) {
+        const unsigned long long a = segs[3 * (size_t)s], d = segs[3 * (size_t)s + 1], n = segs[3 * (size_t)s + 2];
+        for (unsigned long long i = threadIdx.x; i < n; i += blockDim.x) dst[d + i] = __ldcs(src + a + i);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // multi-GPU: partial columns out (AoS records for the all-to-all) and owner-side partition
 // ------------------------------------------------------------------------------------------
@@ -1599,206 +1080,6 @@ k_gather_buckets_aos(const unsigned long long* __restrict__ tmp_keys, const unsi
             dst[d0 * (1 + W) + c] = f == 0 ? tmp_keys[src + i] : tmp_words[(unsigned long long)(f - 1) * tmp_cap + src + i];
         }
     }
-}
-
-// compact per-bucket filtered records (mode 2 leaves them at the bucket's old offset) into new offsets
-__global__ void k_compact_records(const unsigned long long* __restrict__ src, const unsigned long long* __restrict__ old_off,
-                                  const unsigned long long* __restrict__ new_off, uint32_t B,
-                                  unsigned long long* __restrict__ dst) {
-    for (uint32_t b = blockIdx.x; b < B; b += gridDim.x) {
-        const unsigned long long s = old_off[b], d = new_off[b], n = new_off[b + 1] - d;
-        for (unsigned long long i = threadIdx.x; i < n; i += blockDim.x) dst[d + i] = src[s + i];
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// order: LSD radix sort of (k-mer, column index), one warp per contiguous segment
-// ------------------------------------------------------------------------------------------
-constexpr int kSortSeg = 4096;        // items per warp segment
-constexpr int kSortWarps = 8;
-
-__global__ void __launch_bounds__(kSortWarps * 32)
-k_sort_hist(const unsigned long long* __restrict__ keys, uint64_t n, uint32_t shift, uint32_t n_seg,
-            uint32_t* __restrict__ hist /* [256][n_seg] */) {
-    __shared__ uint32_t s_h[kSortWarps][256];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t seg = blockIdx.x * kSortWarps + warp;
-    for (int i = lane; i < 256; i += 32) s_h[warp][i] = 0;
-    __syncwarp();
-    if (seg < n_seg) {
-        const uint64_t beg = (uint64_t)seg * kSortSeg, end = min(n, beg + kSortSeg);
-        for (uint64_t i = beg + lane; i < end; i += 32) atomicAdd(&s_h[warp][(keys[i] >> shift) & 255u], 1u);
-        __syncwarp();
-        for (int i = lane; i < 256; i += 32) hist[(uint64_t)i * n_seg + seg] = s_h[warp][i];
-    }
-}
-
-// exclusive scan of a u32 array (length n, multiple of 4) in place, three launches:
-//   k_scan_u32_partial: per-4096-chunk totals; k_scan_u32_mid: scan of the totals (one block);
-//   k_scan_u32_final: chunk-local scan + chunk offset.  All accesses are 16-byte coalesced.
-constexpr int kScanChunk = 4096;
-
-__global__ void __launch_bounds__(1024)
-k_scan_u32_partial(const uint32_t* __restrict__ a, uint64_t n, uint32_t* __restrict__ partial) {
-    __shared__ uint32_t s_warp[33];
-    const uint64_t i = (uint64_t)blockIdx.x * kScanChunk + (uint64_t)threadIdx.x * 4;
-    uint32_t v = 0;
-    if (i < n) { const uint4 q = *reinterpret_cast<const uint4*>(a + i); v = q.x + q.y + q.z + q.w; }
-    uint32_t total;
-    block_excl_scan_1024(v, s_warp, total);
-    if (threadIdx.x == 0) partial[blockIdx.x] = total;
-}
-
-__global__ void __launch_bounds__(1024)
-k_scan_u32_mid(uint32_t* __restrict__ partial, uint32_t nb) {
-    __shared__ uint32_t s_warp[33];
-    __shared__ uint32_t s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < nb; base += 1024) {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t v = i < nb ? partial[i] : 0;
-        uint32_t total;
-        const uint32_t ex = block_excl_scan_1024(v, s_warp, total);
-        const uint32_t carry = s_carry;
-        if (i < nb) partial[i] = carry + ex;
-        __syncthreads();
-        if (threadIdx.x == 0) s_carry = carry + total;
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(1024)
-k_scan_u32_final(uint32_t* __restrict__ a, uint64_t n, const uint32_t* __restrict__ partial) {
-    __shared__ uint32_t s_warp[33];
-    const uint64_t i = (uint64_t)blockIdx.x * kScanChunk + (uint64_t)threadIdx.x * 4;
-    uint4 q = make_uint4(0, 0, 0, 0);
-    if (i < n) q = *reinterpret_cast<const uint4*>(a + i);
-    uint32_t total;
-    uint32_t ex = block_excl_scan_1024(q.x + q.y + q.z + q.w, s_warp, total) + partial[blockIdx.x];
-    if (i < n) {
-        uint4 o;
-        o.x = ex; o.y = ex + q.x; o.z = o.y + q.y; o.w = o.z + q.z;
-        *reinterpret_cast<uint4*>(a + i) = o;
-    }
-}
-
-__global__ void __launch_bounds__(kSortWarps * 32)
-k_sort_scatter(const unsigned long long* __restrict__ keys_in, const uint32_t* __restrict__ idx_in, uint64_t n,
-               uint32_t shift, uint32_t n_seg, const uint32_t* __restrict__ hist,
-               unsigned long long* __restrict__ keys_out, uint32_t* __restrict__ idx_out) {
-    __shared__ uint32_t s_b[kSortWarps][256];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t seg = blockIdx.x * kSortWarps + warp;
-    if (seg >= n_seg) return;
-    for (int i = lane; i < 256; i += 32) s_b[warp][i] = hist[(uint64_t)i * n_seg + seg];
-    __syncwarp();
-    const uint64_t beg = (uint64_t)seg * kSortSeg, end = min(n, beg + kSortSeg);
-    for (uint64_t i0 = beg; i0 < end; i0 += 32) {
-        const uint64_t i = i0 + lane;
-        const bool act = i < end;
-        const uint32_t amask = __ballot_sync(0xffffffffu, act);
-        if (act) {
-            const unsigned long long key = keys_in[i];
-            const uint32_t idx = idx_in ? idx_in[i] : (uint32_t)i;
-            const uint32_t d = (uint32_t)(key >> shift) & 255u;
-            const uint32_t peers = __match_any_sync(amask, d);
-            const uint32_t rank = __popc(peers & lanemask_lt());
-            const uint32_t pos = s_b[warp][d] + rank;
-            __syncwarp(amask);
-            if (rank == 0) s_b[warp][d] += __popc(peers);
-            __syncwarp(amask);
-            keys_out[pos] = key;
-            idx_out[pos] = idx;
-        }
-    }
-}
-
-// ---- order, fast path: one MSD partition on the top bits of the k-mer, then a per-partition bitonic
-// sort in shared memory fused with the column gather (2 passes over U instead of 8 radix passes).
-// Canonical k-mers are denser near 0 (density 2(1-x)), so partitions hold up to ~2x the average;
-// the host sizes the partition count for a 4x margin and falls back to the radix sort on overflow.
-constexpr int kLocalSortCap = 16384;
-constexpr int kLocalSortThreads = 1024;
-
-__global__ void __launch_bounds__(256)
-k_msd_count(const unsigned long long* __restrict__ keys, uint64_t U, uint32_t shift, uint32_t P,
-            unsigned long long* __restrict__ hist) {
-    extern __shared__ uint32_t s_h[];
-    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) s_h[i] = 0;
-    __syncthreads();
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < U; i += (uint64_t)gridDim.x * blockDim.x)
-        atomicAdd(&s_h[(uint32_t)(keys[i] >> shift)], 1u);
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x)
-        if (s_h[i]) atomicAdd(&hist[i], (unsigned long long)s_h[i]);
-}
-
-__global__ void __launch_bounds__(256)
-k_msd_scatter(const unsigned long long* __restrict__ keys, uint64_t U, uint32_t shift,
-              unsigned long long* __restrict__ cursors, unsigned long long* __restrict__ out_keys,
-              uint32_t* __restrict__ out_idx) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= U) return;
-    const unsigned long long key = keys[i];
-    const unsigned long long o = atomicAdd(&cursors[shift >= 64 ? 0u : (uint32_t)(key >> shift)], 1ULL);
-    out_keys[o] = key;
-    out_idx[o] = (uint32_t)i;
-}
-
-__global__ void __launch_bounds__(kLocalSortThreads, 1)
-k_local_sort_gather(const unsigned long long* __restrict__ pkeys, const uint32_t* __restrict__ pidx,
-                    const unsigned long long* __restrict__ offsets, uint32_t P, uint64_t U, uint32_t W,
-                    const unsigned long long* __restrict__ uwords, uint64_t ucap,
-                    unsigned long long* __restrict__ kmers, unsigned long long* __restrict__ matrix,
-                    unsigned long long* __restrict__ scalars) {
-    extern __shared__ unsigned long long s_key[];          // [cap] keys, then [cap] u32 indices
-    for (uint32_t part = blockIdx.x; part < P; part += gridDim.x) {
-        const unsigned long long beg = offsets[part], end = offsets[part + 1];
-        const uint32_t n = (uint32_t)(end - beg);
-        if (n == 0) continue;
-        if (n > (uint32_t)kLocalSortCap) { if (threadIdx.x == 0) scalars[S_WORK] = 1; continue; }
-        uint32_t npad = 1;
-        while (npad < n) npad <<= 1;
-        uint32_t* s_idx = reinterpret_cast<uint32_t*>(s_key + npad);
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) {
-            s_key[i] = i < n ? pkeys[beg + i] : ~0ULL;
-            s_idx[i] = i < n ? pidx[beg + i] : 0u;
-        }
-        for (uint32_t size = 2; size <= npad; size <<= 1) {
-            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-                __syncthreads();
-                for (uint32_t t = threadIdx.x; t < (npad >> 1); t += blockDim.x) {
-                    const uint32_t i = 2 * t - (t & (stride - 1));
-                    const uint32_t j = i + stride;
-                    const unsigned long long a = s_key[i], b = s_key[j];
-                    const bool asc = (i & size) == 0;
-                    if ((a > b) == asc) {
-                        s_key[i] = b; s_key[j] = a;
-                        const uint32_t x = s_idx[i]; s_idx[i] = s_idx[j]; s_idx[j] = x;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-            kmers[beg + i] = s_key[i];
-            const uint32_t src = s_idx[i];
-            for (uint32_t w = 0; w < W; ++w) matrix[(uint64_t)w * U + beg + i] = uwords[(uint64_t)w * ucap + src];
-        }
-    }
-}
-
-// columns in final order: kmers[j], matrix[w][j] = uwords[w][idx[j]]
-__global__ void k_gather(const unsigned long long* __restrict__ sorted_keys, const uint32_t* __restrict__ idx,
-                         uint64_t U, uint32_t W, const unsigned long long* __restrict__ uwords, uint64_t ucap,
-                         unsigned long long* __restrict__ kmers, unsigned long long* __restrict__ matrix) {
-    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= U) return;
-    kmers[j] = sorted_keys[j];
-    const uint32_t src = idx[j];
-    for (uint32_t w = 0; w < W; ++w) matrix[(uint64_t)w * U + j] = uwords[(uint64_t)w * ucap + src];
 }
 
 // ------------------------------------------------------------------------------------------

@@ -426,7 +426,9 @@ struct UnitDedupeParams {
     unsigned long long* needed;          // scalar: entries produced (may exceed cap; the host retries)
 };
 
-template <int WB>
+// CNT (abundance builds, -abundance-min > 1): the key is (content, genome ROW) and the word is the number of times
+// the unit occurs in that genome, so that the expansion can hand every k-mer its multiplicity (WB = 1).
+template <int WB, bool CNT = false>
 __global__ void __launch_bounds__(kUdThreads, 1)
 k_units_dedupe(const UnitDedupeParams p) {
     extern __shared__ unsigned long long s_tab[];
@@ -436,7 +438,8 @@ k_units_dedupe(const UnitDedupeParams p) {
     constexpr uint32_t S = WB == 1 ? 8192u : WB == 2 ? 6144u : 4096u;
     constexpr uint32_t kSoft = S * 6 / 10;             // flush at a checkpoint above this many entries
     constexpr uint32_t kHard = S - kUdThreads - 64;    // between checkpoints: new keys beyond this bypass the table
-    constexpr uint32_t GS = WB == 1 ? 6 : WB == 2 ? 7 : 8;   // genome group = row >> GS
+    static_assert(!CNT || WB == 1, "abundance entries carry one counter word");
+    constexpr uint32_t GS = CNT ? 0 : WB == 1 ? 6 : WB == 2 ? 7 : 8;   // genome group = row >> GS
     constexpr uint32_t ES = 2 + WB;                    // u64 per output entry
     unsigned long long* k_lo = s_tab;
     unsigned long long* k_hi = s_tab + S;
@@ -521,13 +524,14 @@ k_units_dedupe(const UnitDedupeParams p) {
                 // presence bit 63 - (row & 63) of word (row >> 6) % WB: a native 32-bit shared-memory OR on the right
                 // half (a 64-bit atomicOr on shared memory compiles to a compare-and-swap loop)
                 const uint32_t r6 = row & 63u, wj = (row >> 6) & (uint32_t)(WB - 1);
-                if (placed) atomicOr(reinterpret_cast<uint32_t*>(&wd[wj * S + slot]) + (r6 < 32u ? 1 : 0), 0x80000000u >> (r6 & 31u));
+                if (placed && CNT) atomicAdd(reinterpret_cast<uint32_t*>(&wd[slot]), 1u);       // low half: the count
+                else if (placed) atomicOr(reinterpret_cast<uint32_t*>(&wd[wj * S + slot]) + (r6 < 32u ? 1 : 0), 0x80000000u >> (r6 & 31u));
                 else {
                     const unsigned long long o = atomicAdd(p.needed, 1ULL);
                     if (o < p.cap) {
                         p.out[ES * o] = lo; p.out[ES * o + 1] = hik;
 #pragma unroll
-                        for (int w = 0; w < WB; ++w) p.out[ES * o + 2 + w] = (uint32_t)w == wj ? 1ULL << (63u - r6) : 0ULL;
+                        for (int w = 0; w < WB; ++w) p.out[ES * o + 2 + w] = CNT ? 1ULL : (uint32_t)w == wj ? 1ULL << (63u - r6) : 0ULL;
                     }
                 }
             }

@@ -224,8 +224,15 @@ class DistributedBuilder:
         src_counts = [int(x) for x in box["c_in"].tolist()]
         in_split = [c * (1 + wl) for c in counts]
         out_split = [src_counts[s] * (1 + self.src_words[s]) for s in range(self.world)]
-        recv = torch.empty(sum(out_split), dtype=torch.int64, device=send.device)
-        dist.all_to_all_single(recv, send, output_split_sizes=out_split, input_split_sizes=in_split)
+        if dev == "cpu" and send.is_cuda:
+            # CUDA engine under the gloo backend (several ranks sharing one GPU in the tests): the records cross the
+            # host for the transport only
+            recv_h = torch.empty(sum(out_split), dtype=torch.int64)
+            dist.all_to_all_single(recv_h, send.cpu(), output_split_sizes=out_split, input_split_sizes=in_split)
+            recv = recv_h.to(send.device)
+        else:
+            recv = torch.empty(sum(out_split), dtype=torch.int64, device=send.device)
+            dist.all_to_all_single(recv, send, output_split_sizes=out_split, input_split_sizes=in_split)
         self.exchange_bytes = int(send.numel() * 8)
         if ev:
             ev[1].record()
@@ -268,6 +275,11 @@ class DistributedBuilder:
         """Local stages, then ONE kernel per rank gathers its partial columns and stores every owner's slice straight
         into that owner's receive buffer over NVLink; the ranks meet at a device-side barrier and merge.  The only
         collective besides the barrier is the all-gather of the P x P counts that assigns the offsets."""
+        if self._stream and torch.cuda.current_stream().cuda_stream != self._stream:
+            # the export kernel and the merge run on the builder's stream: the counts all-gather and the barrier must be
+            # ordered on that same stream, whatever stream the caller happens to be on
+            with torch.cuda.stream(torch.cuda.ExternalStream(self._stream)):
+                return self._build_peer(torch, dist)
         P, r = self.world, self.rank
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         counts = self.engine.build_local(P)
@@ -322,6 +334,49 @@ class DistributedBuilder:
         if self.world > 1:
             return self.engine.result()
         return self.builder.result_host()
+
+    def slice_counts(self) -> list[int]:
+        """Columns held by every rank (one all-gather); the global column order is the slices in rank order."""
+        if self.world == 1:
+            return [self.n_kmers]
+        import torch
+        import torch.distributed as dist
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        mine = torch.tensor([self.n_kmers], dtype=torch.int64, device=dev)
+        out = torch.empty(self.world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(out, mine)
+        return [int(x) for x in out.tolist()]
+
+    def write_tsv(self, path: str, names) -> int:
+        """Ray Surveyor KmerMatrix.tsv written by all ranks: every rank formats the rows of its own column slice on
+        its GPU (k_format_tsv) and writes them at their fixed offset (rows have a constant width).  Returns the
+        number of k-mers.  Collective."""
+        names = [n if isinstance(n, str) else n.decode() for n in names]
+        counts = self.slice_counts()
+        hdr = ("kmers" + "".join("\t" + n for n in names) + "\n").encode()
+        roww = self.k + 2 * len(names) + 1
+        if self.world > 1:
+            import torch.distributed as dist
+        if self.rank == 0:
+            with open(path, "wb") as f:
+                f.write(hdr)
+                f.truncate(len(hdr) + roww * sum(counts))
+        if self.world > 1:
+            dist.barrier()
+        if counts[self.rank]:
+            body = self.builder.tsv(names)[len(hdr):]
+            fd = os.open(path, os.O_WRONLY)
+            try:
+                off, view = len(hdr) + roww * sum(counts[:self.rank]), memoryview(body)
+                while len(view):
+                    n = os.pwrite(fd, view[:1 << 30], off)
+                    off += n
+                    view = view[n:]
+            finally:
+                os.close(fd)
+        if self.world > 1:
+            dist.barrier()
+        return sum(counts)
 
     def gather(self):
         """Global (kmers, matrix [W][U]) in ascending hash order on rank 0, None elsewhere."""

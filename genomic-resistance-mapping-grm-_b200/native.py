@@ -6,16 +6,12 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GRMKM_LIB") or os.path.join(_HERE, "libgrmkm.so")   # GRMKM_LIB: another build of the same library (kernel experiments)
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 OK = 0
 E_INVALID, E_UNSUPPORTED_K, E_NOMEM, E_CUDA, E_IO, E_CAPACITY, E_NO_DEVICE, E_UNSUPPORTED = -1, -2, -3, -4, -5, -6, -7, -8
 FASTA, FASTQ = 0, 1
-FLAG_KMER_ORDER = 1
-FLAG_SIMPLE_SCATTER = 2
-FLAG_RADIX_ORDER = 4
-FLAG_EXACT_OFFSETS = 8
-FLAG_KMER_RECORDS = 16
+FLAG_COUNTS = 32      # pooled count table (dsk mode): matrix row 0 = abundance of the k-mer over all inputs
 
 # every symbol include/grmkm.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
@@ -25,6 +21,7 @@ SYMBOLS = [
     "grmkm_copy_kmer_strings", "grmkm_copy_matrix", "grmkm_format_tsv", "grmkm_device_result", "grmkm_host_result",
     "grmkm_synth_fasta_device", "grmkm_build_partial", "grmkm_export_partials", "grmkm_export_partials_peers", "grmkm_merge_partials",
     "grmkm_plan_bucket_bits", "grmkm_set_bucket_bits",
+    "grmkm_result_checksum", "grmkm_sum_rows", "grmkm_gram", "grmkm_tsv_pack",
 ]
 
 
@@ -47,7 +44,7 @@ class Stats(C.Structure):
                 ("n_launches", C.c_uint32), ("h2d_bytes", C.c_uint64), ("device_bytes", C.c_uint64),
                 ("n_splits", C.c_uint64), ("n_region_overflows", C.c_uint64), ("n_units", C.c_uint64),
                 ("n_unit_entries", C.c_uint64), ("n_wide", C.c_uint64), ("n_unit_buckets", C.c_uint32),
-                ("reserved0", C.c_uint32)]
+                ("n_rounds", C.c_uint32), ("n_solid_records", C.c_uint64)]
 
     def asdict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -103,6 +100,10 @@ def load() -> C.CDLL:
         "grmkm_merge_partials": (i32, [vp, vp, u32, u32, C.POINTER(u64), C.POINTER(u32), u32]),
         "grmkm_plan_bucket_bits": (i32, [vp, C.POINTER(u32)]),
         "grmkm_set_bucket_bits": (i32, [vp, u32]),
+        "grmkm_result_checksum": (i32, [vp, C.POINTER(u64)]),
+        "grmkm_sum_rows": (i32, [vp, vp, u32, vp, u64]),
+        "grmkm_gram": (i32, [vp, vp, u64]),
+        "grmkm_tsv_pack": (i32, [vp, vp, u64, u32, u32, u32, u32, vp, vp, u64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

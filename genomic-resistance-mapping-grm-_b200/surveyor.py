@@ -7,7 +7,8 @@ presence matrix with min abundance 1 and no singleton filter (SURVEY.md Appendix
 fixed-width grammar ``kover dataset create from-tsv`` parses (create.py:121-137, 241-264).
 
     python -m grm_b200.surveyor survey.conf                          one GPU
-    torchrun --nproc-per-node N -m grm_b200.surveyor survey.conf     rows sharded over N GPUs
+    GRM_GPUS=N python -m grm_b200.surveyor survey.conf               rows sharded over N GPUs (spawns N ranks)
+    torchrun --nproc-per-node N -m grm_b200.surveyor survey.conf     the same, joining an existing launch
 """
 from __future__ import annotations
 
@@ -58,44 +59,33 @@ def parse_survey_conf(path) -> dict:
     return conf
 
 
-def run_surveyor(conf_path, device: int = -1) -> str | None:
-    """Build the matrix and write <output>/Surveyor/KmerMatrix.tsv.  Returns the path (rank 0)."""
+def run_surveyor(conf_path, device: int = -1, gpus=None) -> str | None:
+    """Build the matrix and write <output>/Surveyor/KmerMatrix.tsv.  Returns the path.  GRM_GPUS=N (or gpus=N): the
+    rows are sharded over N GPUs, one process each (the GUI runs Ray as ``mpiexec -n 4``, src/app.py:1310), and every
+    rank writes the rows of its own column slice into the file (multi.py, DistributedBuilder.write_tsv)."""
+    from . import multi
     conf = parse_survey_conf(conf_path)
     names = [n for n, _ in conf["samples"]]
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     out_dir = os.path.join(conf["output"], "Surveyor")
     out_path = os.path.join(out_dir, "KmerMatrix.tsv")
-    if world == 1:
-        from .builder import KmerMatrixBuilder
-        with KmerMatrixBuilder(k=conf["k"], min_abundance=1, keep_singletons=True, device=device) as b:
-            b.set_genome_count(len(names))
-            for row, (_, path) in enumerate(conf["samples"]):
-                b.add_genome_files(row, [path])
-            b.build()
-            os.makedirs(out_dir, exist_ok=True)
-            b.tsv(names).tofile(out_path)
-            print("[Surveyor] %d samples, %d k-mers -> %s" % (len(names), b.dims[0], out_path))
-        return out_path
-    import torch
-    from .distributed import DistributedBuilder, init_process_group_from_env
-    from .tsv import write_tsv
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dist = init_process_group_from_env()
-    db = DistributedBuilder(k=conf["k"], min_abundance=1, keep_singletons=True, n_genomes=len(names),
-                            rank=dist.get_rank(), world=world, device=local_rank)
-    db.reset()
-    for i, g in enumerate(db.local_rows):
-        db.add_genome_files(i, [conf["samples"][g][1]])
-    db.build()
-    res = db.gather()
-    if res is not None:
+    n_gpus = multi.requested_gpus(gpus)
+    under_torchrun = int(os.environ.get("WORLD_SIZE", "1")) > 1
+    if n_gpus > 1 or under_torchrun:
         os.makedirs(out_dir, exist_ok=True)
-        write_tsv(out_path, res[0], res[1], names, conf["k"])
-        print("[Surveyor] %d samples, %d k-mers -> %s" % (len(names), len(res[0]), out_path))
-    dist.barrier()
-    db.close()
-    return out_path if res is not None else None
+        job = {"files": [[p] for _, p in conf["samples"]], "k": conf["k"], "min_abundance": 1, "keep_singletons": True,
+               "input_kind": 0, "tsv": out_path, "names": names}
+        multi.cleanup(multi.launch(job, n_gpus))
+        return out_path
+    from .builder import KmerMatrixBuilder
+    with KmerMatrixBuilder(k=conf["k"], min_abundance=1, keep_singletons=True, device=device) as b:
+        b.set_genome_count(len(names))
+        for row, (_, path) in enumerate(conf["samples"]):
+            b.add_genome_files(row, [path])
+        b.build()
+        os.makedirs(out_dir, exist_ok=True)
+        b.tsv(names).tofile(out_path)
+        print("[Surveyor] %d samples, %d k-mers -> %s" % (len(names), b.dims[0], out_path))
+    return out_path
 
 
 def main(argv=None):

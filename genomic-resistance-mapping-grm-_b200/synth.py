@@ -150,6 +150,81 @@ def genome_reads_fastq(cfg: SynthConfig, g: int, n_reads: int, read_len: int = 1
     return b"".join(out)
 
 
+def _reads_header(g: int, n_reads: int) -> tuple[bytes, int]:
+    return b"@g%d_r" % g, len(str(max(n_reads - 1, 0)))
+
+
+def genome_reads_fastq_fixed(cfg: SynthConfig, g: int, n_reads: int, read_len: int = 150, err: float = 0.005) -> bytes:
+    """The read set of genome_reads_fastq with the read number zero-padded, so that every record of a genome has the
+    same width and the CUDA generator (k_synth_fastq) can place any byte directly: identical bytes on both sides."""
+    seq = genome_sequence(cfg, g)
+    L = len(seq)
+    read_len = min(read_len, L)
+    prefix, D = _reads_header(g, n_reads)
+    pl = len(prefix)
+    recw = pl + D + 1 + read_len + 3 + read_len + 1
+    out = np.empty((n_reads, recw), dtype=np.uint8)
+    j = np.arange(n_reads, dtype=_U)
+    gj = (_U(g) << _U(32)) + j
+    start = (h(cfg.seed, 10, gj) % _U(L - read_len + 1)).astype(np.int64)
+    strand = (h(cfg.seed, 11, gj) & _U(1)).astype(bool)
+    thr = _U(int(err * 2.0 ** 64))
+    out[:, :pl] = np.frombuffer(prefix, dtype=np.uint8)
+    v = np.arange(n_reads, dtype=np.int64)
+    for d in range(D - 1, -1, -1):
+        out[:, pl + d] = ord("0") + v % 10
+        v //= 10
+    out[:, pl + D] = 10
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)
+    step = max(1, (1 << 22) // max(read_len, 1))
+    t = np.arange(read_len, dtype=np.int64)
+    for a in range(0, n_reads, step):
+        b = min(n_reads, a + step)
+        bases = seq[start[a:b, None] + t[None, :]]
+        bases = np.where(strand[a:b, None], 3 - bases[:, ::-1], bases)
+        cell = gj[a:b, None] * _U(1024) + t.astype(_U)[None, :]
+        hit = h(cfg.seed, 12, cell) < thr
+        sub = (bases + 1 + (h(cfg.seed, 13, cell) % _U(3)).astype(np.int64)) & 3
+        out[a:b, pl + D + 1: pl + D + 1 + read_len] = letters[np.where(hit, sub, bases)]
+    o = pl + D + 1 + read_len
+    out[:, o] = 10
+    out[:, o + 1] = ord("+")
+    out[:, o + 2] = 10
+    out[:, o + 3: o + 3 + read_len] = ord("I")
+    out[:, recw - 1] = 10
+    return out.tobytes()
+
+
+def build_reads_layout(cfg: SynthConfig, genome_ids, n_reads: int, read_len: int = 150,
+                       err: float = 0.005) -> tuple[np.ndarray, int, list[tuple[int, int]]]:
+    """Layout table of grmkm_synth_fasta_device for read sets (k_synth_fastq): (u64 table, total bytes, [(offset, length)])."""
+    NI = cfg.n_islands
+    stride = 10 + NI
+    genome_ids = list(genome_ids)
+    G = len(genome_ids)
+    lay = np.zeros(HEADER_WORDS + G * stride, dtype=_U)
+    spans = []
+    off = 0
+    for n, g in enumerate(genome_ids):
+        isl = present_islands(cfg, g)
+        Lg = cfg.core_len + len(isl) * cfg.island_len
+        rl = min(read_len, Lg)
+        prefix, D = _reads_header(g, n_reads)
+        if len(prefix) > 16:
+            raise ValueError("read header prefix longer than 16 bytes")
+        recw = len(prefix) + D + 1 + rl + 3 + rl + 1
+        flen = n_reads * recw
+        blk = lay[HEADER_WORDS + n * stride: HEADER_WORDS + (n + 1) * stride]
+        blk[0:8] = [g, off, flen, len(isl), Lg, recw, len(prefix), D]
+        blk[8:10] = np.frombuffer(prefix + b"\0" * (16 - len(prefix)), dtype="<u8")
+        blk[10:10 + len(isl)] = isl.astype(_U)
+        spans.append((off, flen))
+        off += (flen + 15) & ~15
+    lay[0:10] = [MAGIC, cfg.seed, G, cfg.core_len, cfg.island_len, cfg.n_contigs, cfg.line_width, off, NI, stride]
+    lay[10:14] = [1, min(read_len, cfg.core_len), int(err * 2.0 ** 64), n_reads]
+    return lay, off, spans
+
+
 def build_layout(cfg: SynthConfig, genome_ids) -> tuple[np.ndarray, int, list[tuple[int, int]]]:
     """Layout table for grmkm_synth_fasta_device.  Returns (u64 table, total bytes, [(offset, length)])."""
     C, NI, LW = cfg.n_contigs, cfg.n_islands, cfg.line_width

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GRMKM_ABI_VERSION 7
+#define GRMKM_ABI_VERSION 8
 
 enum {
     GRMKM_OK = 0,
@@ -41,18 +41,15 @@ enum {
     GRMKM_E_IO = -5,            /* file could not be read / inflated                 */
     GRMKM_E_CAPACITY = -6,      /* caller buffer too small                           */
     GRMKM_E_NO_DEVICE = -7,     /* no usable CUDA device: there is no CPU fallback   */
-    GRMKM_E_UNSUPPORTED = -8    /* e.g. more genomes than one context can hold       */
+    GRMKM_E_UNSUPPORTED = -8    /* e.g. more than 32768 genomes in one context       */
 };
 
 enum { GRMKM_FASTA = 0, GRMKM_FASTQ = 1 };
 
 /* cfg.flags */
-#define GRMKM_FLAG_KMER_ORDER 1u /* columns ascending by canonical k-mer (one extra sort); default: ascending hash order */
-#define GRMKM_FLAG_RADIX_ORDER 4u /* order the columns with the LSD radix sort only (A/B timing, fallback test) */
-#define GRMKM_FLAG_SIMPLE_SCATTER 2u /* per-record global-atomic scatter instead of the staged one (A/B timing) */
-#define GRMKM_FLAG_EXACT_OFFSETS 8u /* count pass + exact bucket offsets instead of over-provisioned regions (fallback test) */
-#define GRMKM_FLAG_KMER_RECORDS 16u /* one 8-byte record per k-mer occurrence instead of super-k-mer units (A/B timing; builds with
-                                       min_abundance > 1 always take this path) */
+#define GRMKM_FLAG_COUNTS 32u /* pooled count table (bin/dsk/dsk -file <list> -kmer-size k, src/app.py:1371-1372): every input is
+                                 pooled on ONE row, the result has one column per canonical k-mer whose abundance over all inputs
+                                 is >= min_abundance, and matrix row 0 holds that abundance (a count, not presence bits) */
 
 typedef struct grmkm_ctx grmkm_ctx;
 
@@ -90,11 +87,12 @@ typedef struct grmkm_stats {
     uint64_t device_bytes;  /* device memory held by the context                   */
     uint64_t n_splits;      /* bucket sub-range splits (table overflows handled)   */
     uint64_t n_region_overflows; /* builds redone with exact offsets (a bucket region was too small) */
-    uint64_t n_units;        /* super-k-mer units scattered (0 on the k-mer record path)  */
+    uint64_t n_units;        /* super-k-mer units scattered                                */
     uint64_t n_unit_entries; /* distinct (unit, 64-genome block) entries after the dedupe  */
     uint64_t n_wide;         /* [hash, presence word] records the distinct units expand to */
     uint32_t n_unit_buckets; /* content-hash buckets of the unit scatter                   */
-    uint32_t reserved0;
+    uint32_t n_rounds;       /* abundance builds (min_abundance > 1): rounds of genome rows  */
+    uint64_t n_solid_records; /* abundance builds: solid (k-mer, round) presence records     */
 } grmkm_stats;
 
 /* per-stage device time of the last build, milliseconds (CUDA events on the build stream) */
@@ -136,6 +134,9 @@ int grmkm_set_genome_count(grmkm_ctx* ctx, uint32_t n_genomes);
  * min_abundance per genome, merge across genomes, apply the singleton filter,
  * pack 64 genomes per word (bit 63-(g%64) of word g/64, utils.py:144-154).
  * The result stays device-resident until the next reset/build/destroy.
+ * min_abundance > 1 (kmer_count.py:48): the genomes are counted a few rows at a time (per-genome abundance
+ * counters in the shared-memory tables), the solid presence of every round is kept, and one presence merge
+ * over all rounds follows.  GRMKM_FLAG_COUNTS: see the flag.
  */
 int grmkm_build(grmkm_ctx* ctx);
 
@@ -146,7 +147,7 @@ int grmkm_stage_times(const grmkm_ctx* ctx, grmkm_times* out);
 /* canonical k-mers as integers (A0 C1 T2 G3, first base most significant); cap in elements.
  * Column order: ascending grmkm_hash64(k-mer) = k-mer * 0x9E3779B97F4A7C15 mod 2^64 (the order the hash
  * partitions come out in, identical for any GPU count; the reference's own column order is the unspecified
- * partition order of DSK), or ascending k-mer with GRMKM_FLAG_KMER_ORDER. */
+ * partition order of DSK). */
 int grmkm_copy_kmers_packed(grmkm_ctx* ctx, uint64_t* dst, uint64_t cap);
 /* kmer_sequences: U x k bytes, upper-case, no terminator (create.py:216-220, ds.py:84); cap in bytes */
 int grmkm_copy_kmer_strings(grmkm_ctx* ctx, char* dst, uint64_t cap);
@@ -166,6 +167,31 @@ int grmkm_format_tsv(grmkm_ctx* ctx, const char* const* names, char* dst, uint64
  */
 int grmkm_host_result(grmkm_ctx* ctx, const uint64_t** kmers, const uint64_t** matrix);
 
+/*
+ * Kernels over the finished, device-resident result.
+ *
+ * grmkm_result_checksum: order-independent 128-bit digest of the columns (k-mer + its words); the digests of the
+ *   ranks' slices of a multi-GPU build add up (mod 2^64 per lane) to the digest of the one-GPU matrix.
+ * grmkm_sum_rows: KmerRuleClassifications.sum_rows (bin/kover/core/kover/learning/common/rules.py:201-267 with
+ *   popcount.pyx:76-95): dst[j] = sum over word rows w of popcount(matrix[w][j] & row_mask[w]); row_mask has
+ *   n_words words, example (genome row) g at bit 63-(g%64) of word g/64 (build_row_mask, rules.py:209-222).
+ * grmkm_gram: G x G matrix of shared columns, dst[a*G+b] = #columns present in genomes a and b (the similarity
+ *   matrix Ray Surveyor prints beside the k-mer matrix, src/app.py:1310).
+ */
+int grmkm_result_checksum(grmkm_ctx* ctx, uint64_t out[2]);
+int grmkm_sum_rows(grmkm_ctx* ctx, const uint64_t* row_mask, uint32_t n_mask_words, uint32_t* dst, uint64_t cap);
+int grmkm_gram(grmkm_ctx* ctx, uint64_t* dst, uint64_t cap);
+
+/*
+ * from_tsv's bit packer on the GPU (dataset/create.py:241-271 with utils.py:133-156): body = n_rows fixed-width
+ * rows "<k-mer>\t<c_0>\t<c_1>...\n" of a Ray Surveyor KmerMatrix.tsv (host memory, row_width = k + 2 x
+ * n_tsv_cols + 1); matrix row g takes TSV column sel[g]; dst = row-major ceil(n_genomes/64) x n_rows words
+ * (host memory).  A cell other than '0' / '1' fails with GRMKM_E_INVALID (create.py:121-137: binary matrix).
+ * Needs no build; any context of the device will do.
+ */
+int grmkm_tsv_pack(grmkm_ctx* ctx, const uint8_t* body, uint64_t n_rows, uint32_t row_width, uint32_t k,
+                   uint32_t n_tsv_cols, uint32_t n_genomes, const uint32_t* sel, uint64_t* dst, uint64_t cap);
+
 /* Device pointers of the result (kmers[U], matrix[n_words][U]) for callers that stay on the GPU. */
 int grmkm_device_result(const grmkm_ctx* ctx, const uint64_t** d_kmers, const uint64_t** d_matrix);
 
@@ -178,8 +204,9 @@ int grmkm_synth_fasta_device(grmkm_ctx* ctx, const void* layout, uint64_t layout
                              uint64_t dst_bytes);
 
 /*
- * Multi-GPU (one context per process/GPU; the exchange itself is done by the
- * host layer with torch.distributed all_to_all over NCCL).
+ * Multi-GPU (one context per process/GPU).  The exchange is either fused into the export
+ * (grmkm_export_partials_peers: NVLink stores into the owners' receive buffers) or done by the host layer with
+ * an all-to-all over NCCL on the buffer grmkm_export_partials fills.
  *
  * grmkm_build_partial: local stages only.  Produces partial columns
  * (hashed k-mer, n_local_words words) grouped by owner rank = hash range,
@@ -196,7 +223,8 @@ int grmkm_synth_fasta_device(grmkm_ctx* ctx, const void* layout, uint64_t layout
  */
 int grmkm_build_partial(grmkm_ctx* ctx, uint32_t n_ranks, uint64_t* counts);
 /* All ranks must partition the hash space identically: read this rank's automatic choice for
- * the inputs added so far, agree on the maximum over ranks, set it before grmkm_build_partial. */
+ * the inputs added so far, agree on the maximum over ranks, set it before grmkm_build_partial (which refuses
+ * n_ranks > 1 without it) and keep it set for grmkm_merge_partials: the owners' hash ranges are cut on that grid. */
 int grmkm_plan_bucket_bits(grmkm_ctx* ctx, uint32_t* bits);
 int grmkm_set_bucket_bits(grmkm_ctx* ctx, uint32_t bits);
 int grmkm_export_partials(grmkm_ctx* ctx, void* dev_dst, uint64_t dst_bytes);

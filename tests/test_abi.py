@@ -30,10 +30,10 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_the_header():
-    # grmkm_config: 8 x u32/i32 + pointer; grmkm_stats: 6 x u64 + 4 x u32 + 4 x u64 + 3 x u64 + 2 x u32;
+    # grmkm_config: 8 x u32/i32 + pointer; grmkm_stats: 6 x u64 + 4 x u32 + 4 x u64 + 3 x u64 + 2 x u32 + u64;
     # grmkm_times: 12 floats
     assert C.sizeof(native.Config) == 8 * 4 + 8
-    assert C.sizeof(native.Stats) == 6 * 8 + 4 * 4 + 4 * 8 + 3 * 8 + 2 * 4
+    assert C.sizeof(native.Stats) == 6 * 8 + 4 * 4 + 4 * 8 + 3 * 8 + 2 * 4 + 8
     assert C.sizeof(native.Times) == 12 * 4
 
 

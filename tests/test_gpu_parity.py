@@ -20,9 +20,7 @@ def gpu_build(genomes, k, min_abundance=1, keep_singletons=False, kind=0, **kw):
 
 
 def check(genomes, k, min_abundance=1, keep_singletons=False, kind=0, **kw):
-    from grm_b200 import native
-    order = "kmer" if kw.get("flags", 0) & native.FLAG_KMER_ORDER else "hash"
-    ref = oracle.build([[(f, kind) for f in files] for files in genomes], k, min_abundance, keep_singletons, order=order)
+    ref = oracle.build([[(f, kind) for f in files] for files in genomes], k, min_abundance, keep_singletons)
     kmers, mat, stats = gpu_build(genomes, k, min_abundance, keep_singletons, kind, **kw)
     assert stats["n_bases"] == ref.n_bases, (stats, ref.n_bases)
     assert stats["n_windows"] == ref.n_windows, (stats, ref.n_windows)
@@ -38,9 +36,7 @@ def test_known_answer_k4(gpu):
     kmers, mat, stats = gpu_build([[fa]], 5, keep_singletons=True)
     want = np.array([0x4F, 0x5B, 0xA1, 0x1B8, 0x209, 0x284], dtype=np.uint64)
     assert np.array_equal(kmers, want[oracle.column_order(want)])          # default column order: ascending hash
-    from grm_b200 import native
-    kmers2, _, _ = gpu_build([[fa]], 5, keep_singletons=True, flags=native.FLAG_KMER_ORDER)
-    assert np.array_equal(kmers2, want)
+    assert np.array_equal(np.sort(kmers), want)
     assert stats["n_windows"] == 12 and stats["n_bases"] == 21 and stats["n_records"] == 1
     assert (mat == np.uint64(1) << np.uint64(63)).all()
 
@@ -199,8 +195,9 @@ def test_pipelined_host_batches(gpu, monkeypatch):
     st = check(genomes, 31, keep_singletons=True)
     assert st["h2d_bytes"] == sum(len(f) for g in genomes for f in g)
     check(genomes, 15, keep_singletons=False)
-    from grm_b200 import native
-    check(genomes, 21, keep_singletons=True, flags=native.FLAG_EXACT_OFFSETS)       # single-batch fallback path
+    monkeypatch.setenv("GRMKM_EXACT_OFFSETS", "1")
+    check(genomes, 21, keep_singletons=True)                                        # single-batch fallback path
+    monkeypatch.delenv("GRMKM_EXACT_OFFSETS")
     fq = [[inputs.fastq(rng, shared[0], n_reads=120, read_len=70)] for _ in range(9)]
     check(fq, 21, min_abundance=2, keep_singletons=True, kind=1)
 
@@ -242,6 +239,20 @@ def test_errors(gpu):
 def test_partial_merge_emulated_ranks(gpu, world, G, keep):
     """The CUDA partial/export/merge entry points, with the all-to-all emulated by tensor slicing:
     P contexts on one GPU, one after the other (never concurrently)."""
+    _emulated_ranks(world, G, keep)
+
+
+@pytest.mark.parametrize("world,G,merge_bits", [(3, 200, 14), (5, 330, 13), (6, 400, 16), (7, 460, 12), (3, 200, 6)])
+def test_owner_slice_on_a_finer_merge_grid(gpu, monkeypatch, world, G, merge_bits):
+    """Owner ranges are cut on the grid of the partial builds (floor(B r / P) of 2^bits buckets); the owner-side merge
+    sizes its own grid from what it received.  With a world size that is not a power of two the two grids' boundaries
+    differ unless the merge derives its slice from the owners' grid: forced here with a merge grid much finer (and, last
+    case, coarser) than the owners'."""
+    monkeypatch.setenv("GRMKM_MERGE_BITS", str(merge_bits))
+    _emulated_ranks(world, G, False)
+
+
+def _emulated_ranks(world, G, keep):
     import torch
     from grm_b200.builder import KmerMatrixBuilder
     from grm_b200.distributed import CudaEngine, row_partition, words_per_rank
@@ -324,17 +335,17 @@ def test_partial_export_into_peer_buffers(gpu, world, G, keep):
         e.b.close()
 
 
-def test_radix_order_fallback_and_simple_scatter(gpu):
-    """The A/B flags select the older code paths; results must not change."""
-    from grm_b200 import native
+def test_exact_offset_fallback(gpu, monkeypatch):
+    """GRMKM_EXACT_OFFSETS=1 forces the path a region overflow falls back to (count pass + exact offsets for the unit
+    scatter and the expansion); results must not change."""
     rng = np.random.default_rng(21)
     shared = [inputs.rand_seq(rng, 50_000)]
     genomes = [[inputs.fasta(rng, n_records=3, min_len=20_000, max_len=40_000, shared=shared)] for _ in range(4)]
-    K = native.FLAG_KMER_ORDER
-    for flags in (K, K | native.FLAG_RADIX_ORDER, native.FLAG_SIMPLE_SCATTER, native.FLAG_EXACT_OFFSETS,
-                  K | native.FLAG_RADIX_ORDER | native.FLAG_SIMPLE_SCATTER):
-        check(genomes, 31, keep_singletons=True, flags=flags)
-        check(genomes, 32, keep_singletons=False, flags=flags)
+    monkeypatch.setenv("GRMKM_EXACT_OFFSETS", "1")
+    check(genomes, 31, keep_singletons=True)
+    check(genomes, 32, keep_singletons=False)
+    fq = [[inputs.fastq(rng, shared[0], n_reads=800, read_len=90)] for _ in range(5)]
+    check(fq, 21, min_abundance=2, keep_singletons=True, kind=1)
 
 
 def test_single_pass_parser_chains(gpu):
@@ -483,7 +494,7 @@ def test_c4_style_read_sets(gpu):
     (5, 31, True, 4, 0, 1),        # table overflow: the bucket's offset is reserved after the counting sweep
     (130, 21, False, 0, 0, 1),     # three word rows: rows 1 and 2 go through the 2-D copy
     (3, 15, True, 12, 0, 1),       # far more buckets than columns: most of the look-back chain is empty buckets
-    (4, 21, False, 0, 1, 2),       # reads with an abundance filter: the k-mer-record pipeline, one word row
+    (4, 21, False, 0, 1, 2),       # reads with an abundance filter: rounds + the presence merge of their records
 ])
 def test_ordered_emission_equals_gather_path(gpu, monkeypatch, G, k, keep, bucket_bits, kind, min_ab):
     """A final build writes its columns in place (buckets dealt by ticket, offsets by look-back over the published

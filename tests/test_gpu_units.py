@@ -1,5 +1,4 @@
-"""GPU parity of the super-k-mer ("unit") path (csrc/grmkm_units.cuh) and of the k-mer record path it
-replaces by default: both must give the oracle's matrix bit for bit (-m gpu)."""
+"""GPU parity of the super-k-mer ("unit") path (csrc/grmkm_units.cuh): the oracle's matrix bit for bit (-m gpu)."""
 import numpy as np
 import pytest
 
@@ -54,17 +53,15 @@ def test_units_share_work_across_genomes(gpu, k):
     check(genomes, k, keep_singletons=True)
 
 
-@pytest.mark.parametrize("flags_name", ["FLAG_KMER_RECORDS", "FLAG_EXACT_OFFSETS"])
-def test_kmer_record_path_and_exact_offsets(gpu, flags_name):
-    from grm_b200 import native
-    flags = getattr(native, flags_name)
+def test_exact_offsets_on_a_shared_population(gpu, monkeypatch):
     rng = np.random.default_rng(7)
     genomes = shared_population(rng, 12, core_len=20_000)
     genomes.append([inputs.fasta(rng, n_records=5, max_len=3000, p_n=0.05)])
+    monkeypatch.setenv("GRMKM_EXACT_OFFSETS", "1")
     for k in (31, 13, 5):
-        st = check(genomes, k, keep_singletons=True, flags=flags)
-        assert (st["n_units"] == 0) == (flags_name == "FLAG_KMER_RECORDS")
-        check(genomes, k, keep_singletons=False, flags=flags)
+        st = check(genomes, k, keep_singletons=True)
+        assert st["n_units"] > 0
+        check(genomes, k, keep_singletons=False)
 
 
 def test_low_complexity_and_ties(gpu):

@@ -107,6 +107,12 @@ def test_minimum_uint_size_matches_reference():
         assert np.dtype(create._minimum_uint_size(int(c["value"]))).name == c["dtype"]
 
 
+@pytest.fixture(autouse=True)
+def _host_tsv_packer(monkeypatch):
+    """These tests run without a GPU: from_tsv's numpy packer is selected explicitly (the GPU packer has its own -m gpu tests)."""
+    monkeypatch.setenv("GRM_TSV_PACKER", "host")
+
+
 # ---- Ray TSV text <-> matrix -------------------------------------------------------------------------
 def _random_matrix(rng, G, U, k):
     kmers = np.sort(rng.choice(1 << min(62, 2 * k), size=U, replace=False).astype(np.uint64))
