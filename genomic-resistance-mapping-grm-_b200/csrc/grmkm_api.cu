@@ -74,6 +74,9 @@ struct grmkm_ctx {
         racc,            // abundance builds: the solid presence records of the rounds done so far
         aux;             // result-side kernels: row mask / per-column sums / checksum / bit rows / Gram matrix
     uint64_t racc_hint = 0;        // records of the previous abundance build + headroom
+    std::vector<uint64_t> merge_h_off;   // row-block merge of a partial build: chunk offsets of the merge buckets
+    uint32_t merge_bits = 0;
+    uint64_t merge_cap = 0;
     size_t device_bytes = 0;
 
     cudaEvent_t ev[T_N]{};
@@ -198,6 +201,7 @@ size_t table_smem(uint32_t slots, uint32_t cells) {
 constexpr uint32_t kUnitMaxBucketBits = 11;      // the unit expansion sorts tiles over at most 2^11 hash buckets
 constexpr uint32_t kMaxSubBits = 3;              // key sub-ranges (virtual buckets) per bucket: up to 2^3
 constexpr uint32_t kRoundMaxRows = 4;            // genome rows per abundance round (one u32 counter plane each)
+constexpr uint32_t kBlockRows = 256;             // presence builds of more genomes than this run in row blocks (build_row_blocks)
 
 bool abundance_build(const grmkm_ctx* c) { return c->cfg.min_abundance > 1 || (c->cfg.flags & GRMKM_FLAG_COUNTS); }
 
@@ -261,7 +265,7 @@ InputTable tabulate_inputs(grmkm_ctx* c) {
     uint32_t maxrow = 0;
     for (const Input& in : c->inputs) maxrow = std::max(maxrow, in.row + 1);
     t.G = std::max(maxrow, c->n_genomes_decl);
-    if (abundance_build(c) && !(c->cfg.flags & GRMKM_FLAG_COUNTS))
+    if (!(c->cfg.flags & GRMKM_FLAG_COUNTS) && (abundance_build(c) || t.G > kBlockRows))
         std::stable_sort(c->inputs.begin(), c->inputs.end(), [](const Input& a, const Input& b) { return a.row < b.row; });
     for (Input& in : c->inputs) if (!in.owned.empty()) in.host = in.owned.data();
     t.first_file.assign(t.G + 1, 0);
@@ -937,6 +941,78 @@ void set_partial_state(grmkm_ctx* c, const Geo& geo, uint32_t n_ranges, const Jo
 // ------------------------------------------------------------------------------------------------
 // the build
 // ------------------------------------------------------------------------------------------------
+static int merge_sources(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, const uint64_t* src_counts, const uint32_t* src_words,
+                         uint32_t total_genomes, uint32_t ob, uint64_t own_lo, uint64_t own_hi, uint32_t owners, bool partial_out,
+                         bool inside_build);
+
+// ---- presence build of more than 256 genomes: row blocks.  A table slot of the column aggregate holds all the word rows of
+// a column, so with many word rows the tables hold few k-mers and split all the time (1,000 genomes on one B200: 10 k
+// splits, 62 ms).  Instead the rows are built in blocks of 256 (4 word rows: one dedupe entry / wide record per unit),
+// each block leaving sorted partial columns [hash, its words], and the blocks are merged like the ranks of a multi-GPU
+// build: k_aggregate_cols<3> keeps one entry REFERENCE per block in its table (10 + 4 x blocks bytes per slot).
+static int build_row_blocks(grmkm_ctx* c, const Geo& geo, const InputTable& tab, uint32_t mode, uint32_t n_ranges) {
+    cudaStream_t st = c->stream;
+    const uint32_t rows_per = kBlockRows * ((geo.W + 4 * 16 - 1) / (4 * 16));          // at most 16 blocks
+    const uint32_t R = (geo.G + rows_per - 1) / rows_per;
+    std::vector<uint64_t> cnt(R, 0);
+    std::vector<uint32_t> words(R, 0);
+    uint64_t used = 0;                                  // u64 words of c->racc in use
+    ENSURE(c, c->racc, std::max<uint64_t>(1 << 20, c->racc_hint * 8));
+    for (uint32_t r = 0; r < R; ++r) {
+        const uint32_t row0 = r * rows_per, n_rows = std::min(rows_per, geo.G - row0);
+        Geo gr = geo; gr.G = n_rows; gr.W = (n_rows + 63) / 64;
+        words[r] = gr.W;
+        Job job; job.f0 = tab.first_file[row0]; job.f1 = tab.first_file[row0 + n_rows]; job.row0 = row0; job.n_rows = n_rows;
+        job.agg = AGG_PARTIAL;
+        for (uint32_t g = row0; g < row0 + n_rows; ++g) job.max_row_bytes = std::max(job.max_row_bytes, tab.row_bytes[g]);
+        if (job.f0 == job.f1) continue;
+        JobOut out;
+        int rc = run_job(c, gr, job, out);
+        if (rc) return rc;
+        rc = finish_columns(c, gr, gr.W, true, out);
+        if (rc) return rc;
+        const uint64_t U = out.sc[S_U_NEEDED], need = used + U * (1 + gr.W);
+        if (need * 8 > c->racc.cap) {
+            DevBuf bigger;
+            ENSURE(c, bigger, (need + need / 2) * 8 * (R - r > 1 ? 2 : 1));
+            if (used) CU_TRY(c, cudaMemcpyAsync(bigger.p, c->racc.p, used * 8, cudaMemcpyDeviceToDevice, st));
+            CU_TRY(c, cudaStreamSynchronize(st));
+            release(c, c->racc);
+            c->racc = bigger;
+        }
+        if (U) {
+            k_gather_buckets_aos<<<std::min<uint32_t>(gr.VB, (uint32_t)c->sm_count * 8), 256, 0, st>>>(
+                (const unsigned long long*)c->ukeys.p, (const unsigned long long*)c->uwords.p, out.ucap,
+                (const unsigned long long*)c->bbase.p, (const unsigned long long*)c->offsets2.p, gr.VB, gr.W,
+                (unsigned long long*)c->racc.p + used);
+            out.launches++;
+            CU_TRY(c, cudaGetLastError());
+        }
+        cnt[r] = U; used = need;
+        add_job_stats(c, out, false);
+        add_stage_times(c);
+    }
+    c->racc_hint = used + used / 8;
+    const uint32_t ob = mode == 1 ? geo.bucket_bits : 0u;
+    int rc = merge_sources(c, c->racc.p, R, cnt.data(), words.data(), geo.G, ob, 0, 1ULL << ob, 1, mode == 1, true);
+    if (rc) return rc;
+    c->stats.n_buckets = geo.B; c->stats.device_bytes = c->device_bytes; c->stats.n_rounds = R;
+    c->stats.n_genomes = geo.G; c->stats.n_words = geo.W;
+    if (mode == 1) {
+        // the merged partial columns are bucket chunks on the merge grid (2^merge_bits >= 2^bucket_bits buckets)
+        const uint32_t sub = c->merge_bits > geo.bucket_bits ? c->merge_bits - geo.bucket_bits : 0u;
+        c->part_ranks = n_ranges;
+        c->part_counts.assign(n_ranges, 0);
+        if (c->merge_h_off.size() > 2)
+            for (uint32_t r = 0; r < n_ranges; ++r)
+                c->part_counts[r] = c->merge_h_off[((uint64_t)geo.B * (r + 1) / n_ranges) << sub] - c->merge_h_off[((uint64_t)geo.B * r / n_ranges) << sub];
+        c->part_total = c->U; c->part_cap = c->merge_cap; c->part_buckets = c->merge_bits ? (1u << c->merge_bits) : geo.B;
+        c->part_words = geo.W;
+        c->built = false;
+    }
+    return GRMKM_OK;
+}
+
 static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32_t n_ranges) {
     CU_TRY(c, cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
@@ -980,6 +1056,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
     geo.bucket_bits = bits; geo.B = 1u << bits; geo.VB = geo.B << geo.sub_bits;
     c->cur_bucket_bits = bits;
 
+    if (!abundance_build(c) && geo.G > kBlockRows && !getenv("GRMKM_NO_ROW_BLOCKS")) return build_row_blocks(c, geo, tab, mode, n_ranges);
     if (!abundance_build(c)) {
         // ---- presence build (contigs, reads without an abundance filter): one pass over everything
         Job job; job.f0 = 0; job.f1 = F; job.row0 = 0; job.n_rows = geo.G; job.max_row_bytes = tab.max_row;
@@ -1517,12 +1594,15 @@ int grmkm_export_partials_peers(grmkm_ctx* c, uint32_t n_ranks, void* const* pee
     return GRMKM_OK;             // asynchronous on the context's stream: the caller's barrier follows on the same stream
 }
 
-int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, uint32_t rank, const uint64_t* src_counts,
-                         const uint32_t* src_words, uint32_t total_genomes) {
-    if (check_ctx(c)) return GRMKM_E_INVALID;
-    if (n_ranks < 1 || n_ranks > 16 || rank >= n_ranks || !src_counts || !src_words)
-        return fail(c, GRMKM_E_INVALID, "bad merge arguments");
-    CU_TRY(c, cudaSetDevice(c->device));
+}  // extern "C"
+
+// Merge of n_src lists of partial columns [hash, words...] (each ascending by hash, back to back in dev_parts) into
+// columns: the owner-side merge of a multi-GPU build (own_lo .. own_hi of 2^ob = this owner's hash range) and the
+// merge of the row blocks of a one-GPU build with more than 256 genomes (the whole hash range).  partial_out: emit
+// partial columns again (hash keys, no singleton filter) -- the row blocks of ONE rank of a multi-GPU build.
+static int merge_sources(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, const uint64_t* src_counts, const uint32_t* src_words,
+                         uint32_t total_genomes, uint32_t ob, uint64_t own_lo, uint64_t own_hi, uint32_t owners, bool partial_out,
+                         bool inside_build) {
     cudaStream_t st = c->stream;
     Launches L;
     AggParams2 ap{};
@@ -1539,9 +1619,13 @@ int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
     if (W_total != (total_genomes + 63) / 64) return fail(c, GRMKM_E_INVALID, "source words do not add up to the genome count");
     if (n_total && !dev_parts) return fail(c, GRMKM_E_INVALID, "null parts");
     c->built = false; c->U = 0; c->W = W_total; c->G = total_genomes;
-    c->times = grmkm_times{};
+    if (!inside_build) c->times = grmkm_times{};
     const uint32_t launches_before = c->stats.n_launches;
-    if (n_total == 0) { c->built = true; c->stats.n_kmers = 0; return GRMKM_OK; }
+    if (n_total == 0) {
+        c->built = !partial_out; c->stats.n_kmers = 0;
+        if (partial_out) { c->merge_h_off.assign(2, 0); c->merge_bits = 0; c->merge_cap = 0; }
+        return GRMKM_OK;
+    }
     // the merge table keeps one entry reference per source and slot instead of the words (k_aggregate_cols<3>)
     const uint32_t tw = (n_ranks + 1) & ~1u;
     const size_t slot_bytes = 10 + 4 * (size_t)tw;
@@ -1549,18 +1633,14 @@ int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
     const size_t smem = (((size_t)slots + kMaxProbe) * slot_bytes + 8 + 15) & ~size_t(15);
     for (uint32_t s = 0; s < n_ranks; ++s)
         if (src_counts[s] >= 0xFFFFFFFFULL) return fail(c, GRMKM_E_UNSUPPORTED, "more than 2^32 partial columns from one source");
-    // every rank sees 1/P of the hash space: size the buckets for n_total * P entries over the full range
+    // an owner sees 1/P of the hash space: size the buckets for n_total * P entries over the full range
     const uint64_t per = std::max<uint64_t>(1, slots / 2);
-    uint32_t mb = std::min(24u, std::max(6u, ceil_log2((n_total * n_ranks + per - 1) / per)));
+    uint32_t mb = std::min(24u, std::max(6u, ceil_log2((n_total * owners + per - 1) / per)));
     if (const char* e = getenv("GRMKM_MERGE_BITS")) mb = (uint32_t)std::min(24, std::max(6, atoi(e)));      // tests: a merge grid finer than the owners' grid
-    // This owner's slice of the bucket space.  Ownership was dealt on the grid of the partial builds (2^ob buckets, ob =
-    // the agreed bucket count capped like build_impl caps it): owner r holds buckets [floor(B r / P), floor(B (r + 1) / P))
-    // of THAT grid, so the merge grid's slice is the same hash range -- scaled exactly when the merge grid is finer, the
-    // enclosing buckets when it is coarser (the sources hold nothing outside the owner's range).
-    if (n_ranks > 1 && !c->cfg.bucket_bits)
-        return fail(c, GRMKM_E_INVALID, "grmkm_merge_partials needs the bucket count the partial builds agreed on (grmkm_set_bucket_bits)");
-    const uint32_t ob = n_ranks > 1 ? std::min(kUnitMaxBucketBits, c->cfg.bucket_bits) : 0u;
-    const uint64_t own_lo = ((1ULL << ob) * rank) / n_ranks, own_hi = ((1ULL << ob) * (rank + 1)) / n_ranks;
+    if (partial_out) mb = std::max(mb, ob);          // the export cuts the merged chunks on the owners' grid: never coarser than that
+    // This owner's slice of the bucket space: the hash range [own_lo, own_hi) of the owners' grid (2^ob buckets), scaled
+    // exactly when the merge grid is finer, the enclosing buckets when it is coarser (the sources hold nothing outside
+    // the owner's range).
     uint32_t b_lo, b_hi;
     if (mb >= ob) { b_lo = (uint32_t)(own_lo << (mb - ob)); b_hi = (uint32_t)(own_hi << (mb - ob)); }
     else { b_lo = (uint32_t)(own_lo >> (ob - mb)); b_hi = (uint32_t)((own_hi + (1ULL << (ob - mb)) - 1) >> (ob - mb)); }
@@ -1571,13 +1651,24 @@ int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
     ENSURE(c, c->bcounts, (size_t)nb * 8);
     ENSURE(c, c->refs, (size_t)n_ranks * nb1 * 8 + 16 * 8 * 3);      // bounds + source tables
     uint64_t ucap = std::min<uint64_t>(n_total, 0xFFFFFFFFULL);
-    ENSURE(c, c->ukeys, ucap * 8);
-    ENSURE(c, c->uwords, (size_t)ucap * W_total * 8);
+    // ordered emission (as in a final one-GPU build): the merge buckets are dealt by ticket and every bucket learns its
+    // offset by look-back, so the slice's columns land at their final place and no gather pass follows
+    const bool ordered = !partial_out && !getenv("GRMKM_UNORDERED");
+    if (ordered) {
+        ENSURE(c, c->kmers, ucap * 8);
+        ENSURE(c, c->matrix, (size_t)ucap * W_total * 8);
+        if (W_total > 1) ENSURE(c, c->uwords, (size_t)ucap * W_total * 8);
+        ENSURE(c, c->apub, (size_t)(nb + 1) * 8);
+    } else {
+        ENSURE(c, c->ukeys, ucap * 8);
+        ENSURE(c, c->uwords, (size_t)ucap * W_total * 8);
+    }
     uint64_t* d_scalars = (uint64_t*)c->scalars.p;
     unsigned long long* d_bounds = (unsigned long long*)c->refs.p;
     unsigned long long* d_meta = d_bounds + (size_t)n_ranks * nb1;
     if (c->ev_ok) cudaEventRecord(c->ev[T_START], st);
     CU_TRY(c, cudaMemsetAsync(c->scalars.p, 0, S_COUNT * 8, st));
+    if (ordered) CU_TRY(c, cudaMemsetAsync(c->apub.p, 0, (size_t)(nb + 1) * 8, st));
     for (uint32_t s = 0; s < 16; ++s) h_meta[32 + s] = 0;
     memcpy(&h_meta[32], h_width, sizeof h_width);
     CU_TRY(c, cudaMemcpyAsync(d_meta, h_meta.data(), 48 * 8, cudaMemcpyHostToDevice, st));
@@ -1589,21 +1680,46 @@ int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
     CU_TRY(c, cudaGetLastError());
     if (c->ev_ok) cudaEventRecord(c->ev[T_SCATTER], st);
     ap.bucket_bits = mb; ap.row_bits = 0; ap.n_words = W_total; ap.slots = slots;
-    ap.keep_singletons = c->cfg.keep_singletons; ap.sub_bits = 0; ap.table_u32 = tw;
+    ap.keep_singletons = partial_out ? 1u : c->cfg.keep_singletons; ap.sub_bits = 0; ap.table_u32 = tw;
+    ap.partial_out = partial_out ? 1u : 0u;
     ap.out_keys = (unsigned long long*)c->ukeys.p; ap.out_words = (unsigned long long*)c->uwords.p;
     ap.cap = ucap; ap.scalars = (unsigned long long*)d_scalars; ap.parts = parts; ap.bounds = d_bounds;
     ap.bucket_base = (unsigned long long*)c->bbase.p; ap.bucket_count = (unsigned long long*)c->bcounts.p;
     ap.b_begin = b_lo; ap.b_end = b_hi;
+    if (ordered) {
+        ap.ordered = 1;
+        ap.out_keys = (unsigned long long*)c->kmers.p; ap.out_row0 = (unsigned long long*)c->matrix.p;
+        ap.pub = (unsigned long long*)c->apub.p; ap.ticket = (unsigned int*)((unsigned long long*)c->apub.p + nb);
+    }
     CU_TRY(c, cudaFuncSetAttribute(k_aggregate_cols<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_aggregate_cols<3><<<std::max(1u, std::min<uint32_t>(nb, (uint32_t)c->sm_count * kAggCtasPerSm)), kAggThreads, smem, st>>>(ap);
     L.n++;
     CU_TRY(c, cudaGetLastError());
+    if (c->ev_ok) cudaEventRecord(c->ev[T_AGG], st);
+    if (ordered && W_total > 1) {
+        k_move_rows<<<(uint32_t)c->sm_count * 8, 256, 0, st>>>((const unsigned long long*)c->uwords.p, ucap, (unsigned long long*)c->matrix.p,
+                                                              (const unsigned long long*)(d_scalars + S_U_NEEDED), W_total);
+        L.n++;
+        CU_TRY(c, cudaGetLastError());
+    }
     uint64_t sc[S_COUNT];
     CU_TRY(c, cudaMemcpyAsync(sc, d_scalars, sizeof sc, cudaMemcpyDeviceToHost, st));
+    if (ordered && c->ev_ok) cudaEventRecord(c->ev[T_SORT], st);
     CU_TRY(c, cudaStreamSynchronize(st));
-    if (c->ev_ok) cudaEventRecord(c->ev[T_AGG], st);
     const uint64_t U = sc[S_U_NEEDED];
-    {
+    if (partial_out) {
+        // the merged partial columns stay as bucket chunks (ukeys / uwords), like the output of a partial build
+        ENSURE(c, c->offsets2, (size_t)(nb + 1) * 8);
+        k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->bcounts.p, (unsigned long long*)c->offsets2.p, nb,
+                                             d_scalars, S_N_SOLID, 1);
+        L.n++;
+        CU_TRY(c, cudaGetLastError());
+        c->merge_h_off.resize(nb + 1);
+        CU_TRY(c, cudaMemcpyAsync(c->merge_h_off.data(), c->offsets2.p, (size_t)(nb + 1) * 8, cudaMemcpyDeviceToHost, st));
+        if (c->ev_ok) cudaEventRecord(c->ev[T_SORT], st);
+        CU_TRY(c, cudaStreamSynchronize(st));
+        c->merge_bits = mb; c->merge_cap = ucap;
+    } else if (!ordered) {
         ENSURE(c, c->kmers, U * 8);
         ENSURE(c, c->matrix, (size_t)U * W_total * 8);
         k_bucket_offsets<<<1, 1024, 0, st>>>((unsigned long long*)c->bcounts.p, (unsigned long long*)c->offsets2.p, nb,
@@ -1616,20 +1732,41 @@ int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
         }
         L.n += 2;
         CU_TRY(c, cudaGetLastError());
+        if (c->ev_ok) cudaEventRecord(c->ev[T_SORT], st);
+        CU_TRY(c, cudaStreamSynchronize(st));
     }
-    if (c->ev_ok) cudaEventRecord(c->ev[T_SORT], st);
-    CU_TRY(c, cudaStreamSynchronize(st));
-    c->U = U; c->built = true;
+    c->U = U; c->built = !partial_out;
     c->stats.n_kmers = U; c->stats.n_distinct = sc[S_N_DISTINCT]; c->stats.n_words = W_total;
     c->stats.n_genomes = total_genomes; c->stats.n_splits += sc[S_N_SPLITS];
     c->stats.n_launches = launches_before + L.n;
-    if (c->ev_ok) {
+    if (c->ev_ok && inside_build) {
+        float t = 0.f;                         // the row-block merge of a build counts as its ordering stage
+        if (cudaEventElapsedTime(&t, c->ev[T_START], c->ev[T_SORT]) == cudaSuccess) { c->times.sort += t; c->times.total += t; }
+        else cudaGetLastError();
+    } else if (c->ev_ok) {
         cudaEventElapsedTime(&c->times.scatter, c->ev[T_START], c->ev[T_SCATTER]);
         cudaEventElapsedTime(&c->times.aggregate, c->ev[T_SCATTER], c->ev[T_AGG]);
         cudaEventElapsedTime(&c->times.sort, c->ev[T_AGG], c->ev[T_SORT]);
         cudaEventElapsedTime(&c->times.total, c->ev[T_START], c->ev[T_SORT]);
     }
     return GRMKM_OK;
+}
+
+
+extern "C" {
+
+int grmkm_merge_partials(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, uint32_t rank, const uint64_t* src_counts,
+                         const uint32_t* src_words, uint32_t total_genomes) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    if (n_ranks < 1 || n_ranks > 16 || rank >= n_ranks || !src_counts || !src_words)
+        return fail(c, GRMKM_E_INVALID, "bad merge arguments");
+    // Ownership was dealt on the grid of the partial builds (2^ob buckets, ob = the agreed bucket count capped like
+    // build_impl caps it): owner r holds buckets [floor(B r / P), floor(B (r + 1) / P)) of THAT grid.
+    if (n_ranks > 1 && !c->cfg.bucket_bits)
+        return fail(c, GRMKM_E_INVALID, "grmkm_merge_partials needs the bucket count the partial builds agreed on (grmkm_set_bucket_bits)");
+    const uint32_t ob = n_ranks > 1 ? std::min(kUnitMaxBucketBits, c->cfg.bucket_bits) : 0u;
+    const uint64_t own_lo = ((1ULL << ob) * rank) / n_ranks, own_hi = ((1ULL << ob) * (rank + 1)) / n_ranks;
+    return merge_sources(c, dev_parts, n_ranks, src_counts, src_words, total_genomes, ob, own_lo, own_hi, n_ranks, false, false);
 }
 
 // ------------------------------------------------------------------------------------------------

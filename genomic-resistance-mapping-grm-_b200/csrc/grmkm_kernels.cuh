@@ -580,6 +580,7 @@ struct AggParams2 {
     // emits (k-mer, count of local row 0).
     uint32_t min_abundance, round_rows, round_row0, out_wbits, out_word;
     ulonglong2* out_wide;
+    uint32_t partial_out;                // MODE 3: emit partial columns again (hash keys; the caller sets keep_singletons)
     unsigned long long src_off[16];      // first u64 word of the source in parts
     uint32_t src_words[16];
     uint32_t src_woff[16];
@@ -736,7 +737,7 @@ __device__ __forceinline__ uint32_t agg_mark(const AggParams2& p, const AggTable
             occ++;
             if (MODE == 6 || MODE == 7) {
                 for (uint32_t r = 0; r < p.round_rows; ++r) kf |= t.w32[r * t.total + i] >= p.min_abundance;
-            } else if (MODE == 1 || MODE == 5 || p.keep_singletons) kf = 1;
+            } else if (MODE == 5 || p.keep_singletons) kf = 1;
             else if (MODE == 3) {
                 uint32_t pc = 0;
                 for (uint32_t s = 0; s < p.n_src; ++s) {
@@ -804,12 +805,15 @@ __device__ __forceinline__ void agg_emit(const AggParams2& p, const AggTable& t,
                 p.out_wide[o] = make_ulonglong2((h << p.out_wbits) | p.out_word, bits);
                 continue;
             }
-            p.out_keys[o] = (MODE == 1 || MODE == 5) ? h : kunhash(h);
+            p.out_keys[o] = (MODE == 5 || (MODE == 3 && p.partial_out)) ? h : kunhash(h);
             if (MODE == 3) {
                 for (uint32_t s = 0; s < p.n_src; ++s) {
                     const uint32_t e = t.w32[s * t.total + i], nw = p.src_words[s], wo = p.src_woff[s];
                     const unsigned long long* ent = p.parts + p.src_off[s] + (unsigned long long)(e ? e - 1u : 0u) * (1u + nw);
-                    for (uint32_t w = 0; w < nw; ++w) p.out_words[(unsigned long long)(wo + w) * p.cap + o] = e ? ent[1 + w] : 0ULL;
+                    for (uint32_t w = 0; w < nw; ++w) {
+                        unsigned long long* const row = (wo + w == 0 && p.out_row0) ? p.out_row0 : p.out_words + (unsigned long long)(wo + w) * p.cap;
+                        row[o] = e ? ent[1 + w] : 0ULL;
+                    }
                 }
             } else {
                 for (uint32_t w = 0; w < p.n_words; ++w) {

@@ -513,3 +513,28 @@ def test_ordered_emission_equals_gather_path(gpu, monkeypatch, G, k, keep, bucke
     monkeypatch.setenv("GRMKM_UNORDERED", "1")
     km2, mat2, _ = gpu_build(genomes, k, min_ab, keep, kind, **kw)
     assert np.array_equal(km, km2) and np.array_equal(mat, mat2)
+
+
+@pytest.mark.parametrize("G,keep", [(257, False), (300, True), (600, False)])
+def test_row_blocks_for_more_than_256_genomes(gpu, monkeypatch, G, keep):
+    """More than 256 genomes: the rows are built in blocks of 256 (partial columns per block) and the blocks are merged
+    with one entry reference per block in the table; GRMKM_NO_ROW_BLOCKS=1 is the single-pass build it replaces.
+    Same bytes, and both equal the oracle."""
+    rng = np.random.default_rng(G)
+    shared = [inputs.rand_seq(rng, 2500), inputs.rand_seq(rng, 600)]
+    genomes = [[inputs.fasta(rng, n_records=2, max_len=350, shared=shared)] for _ in range(G)]
+    genomes[G - 3] = []                                           # a row without input in the last block
+    st = check(genomes, 19, keep_singletons=keep)
+    assert st["n_rounds"] == (G + 255) // 256
+    km, mat, _ = gpu_build(genomes, 19, 1, keep)
+    monkeypatch.setenv("GRMKM_NO_ROW_BLOCKS", "1")
+    km2, mat2, st2 = gpu_build(genomes, 19, 1, keep)
+    assert st2["n_rounds"] == 0
+    assert np.array_equal(km, km2) and np.array_equal(mat, mat2)
+
+
+def test_row_blocks_in_partial_builds(gpu):
+    """Two emulated ranks with more than 256 rows each: every rank merges its row blocks into partial columns again
+    (hash keys, no filter) before the export; the owners' ranges are cut on the agreed grid inside the finer merge grid."""
+    _emulated_ranks(2, 700, False)
+    _emulated_ranks(3, 1000, True)

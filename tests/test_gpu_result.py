@@ -110,7 +110,7 @@ def test_from_tsv_on_the_gpu_writes_the_same_file(gpu, tmp_path):
     create.from_tsv(str(p), str(tmp_path / "host.kover"), "pheno", str(md), 4, use_gpu=False)
     a, c = hdf5min.H5Reader(str(tmp_path / "gpu.kover")), hdf5min.H5Reader(str(tmp_path / "host.kover"))
     for name in ("kmer_matrix", "kmer_sequences", "genome_identifiers", "phenotype", "kmer_by_matrix_column"):
-        assert np.array_equal(a.read(name), c.read(name)), name
+        assert np.array_equal(a[name].read(), c[name].read()), name
 
 
 def test_synth_reads_device_matches_numpy(gpu):
