@@ -201,6 +201,7 @@ size_t table_smem(uint32_t slots, uint32_t cells) {
 constexpr uint32_t kUnitMaxBucketBits = 11;      // the unit expansion sorts tiles over at most 2^11 hash buckets
 constexpr uint32_t kMaxSubBits = 3;              // key sub-ranges (virtual buckets) per bucket: up to 2^3
 constexpr uint32_t kRoundMaxRows = 4;            // genome rows per abundance round (one u32 counter plane each)
+constexpr uint64_t kTwoPassTilesPerFile = 2048;  // parse in two passes when the files average more tiles than this (32 MB)
 constexpr uint32_t kBlockRows = 256;             // presence builds of more genomes than this run in row blocks (build_row_blocks)
 
 bool abundance_build(const grmkm_ctx* c) { return c->cfg.min_abundance > 1 || (c->cfg.flags & GRMKM_FLAG_COUNTS); }
@@ -226,7 +227,10 @@ std::vector<Round> plan_rounds(const grmkm_ctx* c, uint32_t G, const std::vector
         Round rd{first_file[r], first_file[r + 1], r, 1, row_bytes[r]};
         while (rd.n_rows < max_rows && r + rd.n_rows < G && ((r + rd.n_rows) & 63u) != 0) {
             const uint32_t nr = rd.n_rows + 1;
-            const uint64_t cap_keys = (uint64_t)table_slots(c, (nr + 1) & ~1u) * 6 / 10 << (kUnitMaxBucketBits + kMaxSubBits);
+            // (further rows join only while the round still needs no key sub-ranges: every sub-range bit doubles the
+            // aggregate's passes over the round's records, and rows share nothing that would pay for it -- the distinct
+            // k-mers of read sets are mostly sequencing errors, unique to their genome)
+            const uint64_t cap_keys = (uint64_t)table_slots(c, (nr + 1) & ~1u) * 6 / 10 << kUnitMaxBucketBits;
             const uint64_t nb = rd.bytes + row_bytes[r + rd.n_rows];
             if (nb / 10 > cap_keys) break;
             rd.n_rows = nr; rd.bytes = nb; rd.f1 = first_file[r + nr];
@@ -286,7 +290,7 @@ uint32_t auto_bucket_bits(grmkm_ctx* c, const InputTable& t) {
     }
     uint64_t rb = 0; uint32_t rr = 1;
     for (const Round& rd : plan_rounds(c, t.G, t.first_file, t.row_bytes)) { rb = std::max(rb, rd.bytes); rr = std::max(rr, rd.n_rows); }
-    return bits_for(rb / 4 + 1024, table_slots(c, (rr + 1) & ~1u));
+    return bits_for(rb / 8 + 1024, table_slots(c, (rr + 1) & ~1u));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -555,6 +559,20 @@ int run_job(grmkm_ctx* c, const Geo& geo, const Job& job, JobOut& out) {
         pp.pub_a0 = (unsigned long long*)c->tile_pub.p; pp.pub_a1 = pp.pub_a0 + n_tiles; pp.pub_ps = pp.pub_a0 + 2 * n_tiles;
         pp.stream_len = bt.stream;
         pp.codes = (unsigned long long*)c->codes.p; pp.valid = (uint32_t*)c->valid.p; pp.scalars = d_scalars;
+        // files of very many tiles: summaries first, the chains resolved by a scan, so that the pack itself never waits
+        // (k_scan_tile_chains)
+        const bool two_pass = !getenv("GRMKM_ONE_PASS") && (getenv("GRMKM_TWO_PASS") || n_tiles / F > kTwoPassTilesPerFile);
+        if (two_pass) {
+            if (c->cfg.input_kind == GRMKM_FASTA) {
+                k_pack<0, true><<<(uint32_t)n_tiles, kParseThreads, 0, st>>>(pp);
+                k_scan_tile_chains<0><<<(F * 32 + 127) / 128, 128, 0, st>>>(d_files, F, (const uint64_t*)c->fss.p, n_tiles, pp.pub_a0, pp.pub_a1, pp.pub_ps);
+            } else {
+                k_pack<1, true><<<(uint32_t)n_tiles, kParseThreads, 0, st>>>(pp);
+                k_scan_tile_chains<1><<<(F * 32 + 127) / 128, 128, 0, st>>>(d_files, F, (const uint64_t*)c->fss.p, n_tiles, pp.pub_a0, pp.pub_a1, pp.pub_ps);
+            }
+            CU_TRY(c, cudaMemsetAsync(pp.ticket, 0, 4, st));
+            out.launches += 2;
+        }
         if (c->cfg.input_kind == GRMKM_FASTA) k_pack<0><<<(uint32_t)n_tiles, kParseThreads, 0, st>>>(pp);
         else k_pack<1><<<(uint32_t)n_tiles, kParseThreads, 0, st>>>(pp);
         out.launches++;

@@ -205,6 +205,46 @@ __device__ __noinline__ void tile_lookback(uint64_t tile, uint64_t first, uint64
     }
 }
 
+// Two-pass parse for very long files.  The look-back resolves a file's tiles one after the other in the worst case,
+// and with a handful of files of tens of thousands of tiles each (a 300 MB read set is 19 k tiles) almost every tile
+// waits for its predecessor: 8.5 ms for 620 MB.  Such inputs get a first pass that only publishes the tile summaries
+// (k_pack<KIND, true>: the text is read once more, at HBM speed) and this scan -- one warp per file, 32 tiles per step --
+// which resolves every tile's incoming (state, position).  The real k_pack then finds its predecessor resolved at
+// its first poll.
+template <int KIND>
+__global__ void __launch_bounds__(128)
+k_scan_tile_chains(const FileDesc* __restrict__ files, uint32_t n_files, const uint64_t* __restrict__ fss, uint64_t n_tiles,
+                   const unsigned long long* __restrict__ a0, const unsigned long long* __restrict__ a1,
+                   unsigned long long* __restrict__ ps) {
+    const uint32_t f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (f >= n_files) return;
+    const uint64_t t0 = files[f].tile_begin, t1 = f + 1 < n_files ? files[f + 1].tile_begin : n_tiles;
+    uint32_t st = 0;                              // every file starts in state 0 at its own stream position
+    uint64_t pos = fss[f];
+    for (uint64_t base = t0; base < t1; base += 32) {
+        const uint64_t t = base + lane;
+        Sum mine = sum_identity();
+        if (t < t1) mine = pub_sum(a0[t], KIND == 1 ? a1[t] : kPubValid);
+        Sum inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const Sum o = sum_shfl_up(inc, d);
+            if (lane >= d) inc = sum_combine(o, inc);
+        }
+        Sum excl = sum_shfl_up(inc, 1);
+        if (lane == 0) excl = sum_identity();
+        if (t < t1) ps[t] = kPubValid | ((unsigned long long)sum_end(excl, st) << 61) | (pos + sum_cnt(excl, st));
+        const uint32_t e_all = __shfl_sync(0xffffffffu, inc.e, 31);
+        Sum all;
+        all.e = e_all;
+        all.c0 = __shfl_sync(0xffffffffu, inc.c0, 31); all.c1 = __shfl_sync(0xffffffffu, inc.c1, 31);
+        all.c2 = __shfl_sync(0xffffffffu, inc.c2, 31); all.c3 = __shfl_sync(0xffffffffu, inc.c3, 31);
+        pos += sum_cnt(all, st);
+        st = sum_end(all, st);
+    }
+}
+
 // text tile -> packed stream: codes64[g] holds entries 32g..32g+31 (entry j at bits 2j), valid32[g] bit j.
 // Every thread turns its 64 bytes into at most 64 entries (register accumulator), the block scan of the
 // thread summaries gives each thread its entry offset inside the tile, the look-back gives the tile its state and
@@ -225,7 +265,9 @@ struct PackParams {
     uint64_t* scalars;
 };
 
-template <int KIND>
+// SUMMARY_ONLY: publish the tile's summary and stop (first pass of the two-pass parse of very long files, see
+// k_scan_tile_chains).
+template <int KIND, bool SUMMARY_ONLY = false>
 __global__ void __launch_bounds__(kParseThreads, 1024 / kParseThreads)
 k_pack(const PackParams p) {
     constexpr int kGroups = kTileBytes / 32 + 2;
@@ -295,6 +337,7 @@ k_pack(const PackParams p) {
         uint32_t ex, tot;
         block_scan_fa(mine, ex, tot, reinterpret_cast<uint32_t*>(s_w));
         publish(fa_to_sum(tot));
+        if (SUMMARY_ONLY) return;
         // The entries are accumulated while the look-back is still in flight, as if the tile started inside a sequence
         // line; the few threads in front of the tile's first line start redo it when it started inside a header.
         const uint32_t ex_t = ex >> kFaT;
@@ -327,6 +370,7 @@ k_pack(const PackParams p) {
         }
         block_scan_sum(mine, excl, total, s_w);
         publish(total);
+        if (SUMMARY_ONLY) return;
         resolve(st_in, tpos);
         uint32_t st = sum_end(excl, st_in);
         local = sum_cnt(excl, st_in);

@@ -538,3 +538,20 @@ def test_row_blocks_in_partial_builds(gpu):
     (hash keys, no filter) before the export; the owners' ranges are cut on the agreed grid inside the finer merge grid."""
     _emulated_ranks(2, 700, False)
     _emulated_ranks(3, 1000, True)
+
+
+def test_two_pass_parse_of_long_files(gpu, monkeypatch):
+    """Files of very many tiles are parsed in two passes (tile summaries, a chain scan, then the pack finds every
+    predecessor resolved); GRMKM_TWO_PASS=1 forces it on inputs of a few tiles per file, FASTA and FASTQ, with the
+    quirks that change the parser state across tile borders."""
+    monkeypatch.setenv("GRMKM_TWO_PASS", "1")
+    rng = np.random.default_rng(99)
+    shared = [inputs.rand_seq(rng, 90_000)]
+    genomes = [[inputs.fasta(rng, n_records=4, min_len=30_000, max_len=70_000, shared=shared, crlf=(g == 1), blank=(g == 2),
+                             junk_prefix=(g == 3), final_nl=(g != 4))] for g in range(6)]
+    genomes[5] = [b">" + b"h" * 40_000 + b"\n" + inputs.rand_seq(rng, 50_000) + b"\n"]       # a header longer than two tiles
+    check(genomes, 31, keep_singletons=True)
+    check(genomes, 15, keep_singletons=False)
+    fq = [[inputs.fastq(rng, shared[0], n_reads=1500, read_len=100, crlf=(g == 1), final_nl=(g != 2))] for g in range(4)]
+    check(fq, 21, min_abundance=1, keep_singletons=True, kind=1)
+    check(fq, 21, min_abundance=2, keep_singletons=True, kind=1)
