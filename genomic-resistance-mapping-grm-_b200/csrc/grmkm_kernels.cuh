@@ -361,11 +361,25 @@ k_pack(const PackParams p) {
         local = (ex & kFaMask) + (tile_seq ? ((ex >> kFaH) & kFaMask) : 0u);
         e_total = (tot & kFaMask) + (tile_seq ? ((tot >> kFaH) & kFaMask) : 0u);
     } else {
+        // A chunk without control characters (no '\n', no '\r': nine of ten chunks of 150-base reads, sequence and quality
+        // lines alike) lies inside ONE line: its summary is the identity on the state with 16 entries in state 1 (one
+        // entry in state 0 when it starts the header line), and its entries are the SWAR classification of fa_bases.
+        // Only the chunks that hold a line end go through the byte loops.
         Sum sums[kChunksPerThread];
         Sum mine = sum_identity(), excl, total;
+        uint32_t fastm = 0;
 #pragma unroll
         for (int c = 0; c < kChunksPerThread; ++c) {
-            sums[c] = chunk_summary<1>(x.ch[c], x.prev[c], t.off + 16 * c, t.fd.len, t.hdr0);
+            const uint64_t pos0 = t.off + 16 * c;
+            uint32_t ctrl = 0;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) ctrl |= swar_zero_bytes(x.ch[c].w[w] & 0xE0E0E0E0u);
+            if (ctrl == 0 && pos0 >= t.hdr0 && pos0 + 16 <= t.fd.len) {
+                fastm |= 1u << c;
+                sums[c].e = 0xE4u; sums[c].c0 = (pos0 == t.hdr0 || x.prev[c] == '\n') ? 1u : 0u; sums[c].c1 = 16u; sums[c].c2 = sums[c].c3 = 0u;
+            } else {
+                sums[c] = chunk_summary<1>(x.ch[c], x.prev[c], pos0, t.fd.len, t.hdr0);
+            }
             mine = sum_combine(mine, sums[c]);
         }
         block_scan_sum(mine, excl, total, s_w);
@@ -377,6 +391,14 @@ k_pack(const PackParams p) {
         e_total = sum_cnt(total, st_in);
 #pragma unroll
         for (int c = 0; c < kChunksPerThread; ++c) {
+            if ((fastm >> c) & 1u) {
+                if (st == 1) {
+                    uint32_t vb, cb;
+                    fa_bases(x.ch[c], vb, cb);
+                    acc.append(cb, vb, 16u);
+                } else if (st == 0 && sums[c].c0) { acc.append(0u, 0u, 1u); nrec++; }
+                continue;
+            }
             uint32_t cbits = 0, vbits = 0, n = 0, prev = x.prev[c];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
