@@ -74,6 +74,7 @@ struct grmkm_ctx {
         racc,            // abundance builds: the solid presence records of the rounds done so far
         aux;             // result-side kernels: row mask / per-column sums / checksum / bit rows / Gram matrix
     uint64_t racc_hint = 0;        // records of the previous abundance build + headroom
+    uint32_t pack_ctas[2] = {0, 0};      // resident CTAs of the persistent k_pack (FASTA / FASTQ)
     std::vector<uint64_t> merge_h_off;   // row-block merge of a partial build: chunk offsets of the merge buckets
     uint32_t merge_bits = 0;
     uint64_t merge_cap = 0;
@@ -561,7 +562,7 @@ int run_job(grmkm_ctx* c, const Geo& geo, const Job& job, JobOut& out) {
         pp.codes = (unsigned long long*)c->codes.p; pp.valid = (uint32_t*)c->valid.p; pp.scalars = d_scalars;
         // files of very many tiles: summaries first, the chains resolved by a scan, so that the pack itself never waits
         // (k_scan_tile_chains)
-        const bool two_pass = !getenv("GRMKM_ONE_PASS") && (getenv("GRMKM_TWO_PASS") || n_tiles / F > kTwoPassTilesPerFile);
+        const bool two_pass = getenv("GRMKM_TWO_PASS") != nullptr;        // measured on 300 MB read sets: the second read of the text costs more than the chain
         if (two_pass) {
             if (c->cfg.input_kind == GRMKM_FASTA) {
                 k_pack<0, true><<<(uint32_t)n_tiles, kParseThreads, 0, st>>>(pp);
@@ -573,7 +574,21 @@ int run_job(grmkm_ctx* c, const Geo& geo, const Job& job, JobOut& out) {
             CU_TRY(c, cudaMemsetAsync(pp.ticket, 0, 4, st));
             out.launches += 2;
         }
-        if (c->cfg.input_kind == GRMKM_FASTA) k_pack<0><<<(uint32_t)n_tiles, kParseThreads, 0, st>>>(pp);
+        if (!getenv("GRMKM_PACK_LDG")) {
+            // persistent CTAs (exactly what is resident at once), the next tile's text fetched by cp.async.bulk under the
+            // current tile's parse
+            const int kind = c->cfg.input_kind == GRMKM_FASTA ? 0 : 1;
+            if (!c->pack_ctas[kind]) {
+                int occ = 0;
+                CU_TRY(c, kind ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pack<1, false, true>, kParseThreads, 0)
+                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pack<0, false, true>, kParseThreads, 0));
+                if (occ < 1) return fail(c, GRMKM_E_CUDA, "k_pack does not fit an SM");
+                c->pack_ctas[kind] = (uint32_t)occ * (uint32_t)c->sm_count;
+            }
+            const uint32_t pgrid = (uint32_t)std::min<uint64_t>(n_tiles, c->pack_ctas[kind]);
+            if (kind) k_pack<1, false, true><<<pgrid, kParseThreads, 0, st>>>(pp);
+            else k_pack<0, false, true><<<pgrid, kParseThreads, 0, st>>>(pp);
+        } else if (c->cfg.input_kind == GRMKM_FASTA) k_pack<0><<<(uint32_t)n_tiles, kParseThreads, 0, st>>>(pp);
         else k_pack<1><<<(uint32_t)n_tiles, kParseThreads, 0, st>>>(pp);
         out.launches++;
         CU_TRY(c, cudaGetLastError());

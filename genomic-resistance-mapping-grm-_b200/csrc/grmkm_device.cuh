@@ -368,6 +368,53 @@ __device__ __forceinline__ void fa_bases(const Chunk16& ch, uint32_t& valid, uin
     }
 }
 
+// ---- SWAR path for FASTQ text ---------------------------------------------------------------------
+// A live chunk whose only control characters are '\n' is classified without a byte loop.  The line index of every
+// byte relative to the chunk's first byte (mod 4) comes from two prefix parities of the newline mask (bit 0: newlines
+// before the byte; bit 1: newlines that arrived while bit 0 was set), the four per-state entry counts are popcounts,
+// and the entries of the chunk for a known state are the SWAR base classification restricted to the sequence line's
+// bytes plus one break entry per header-line start.
+struct FqChunk { uint32_t nl, e0, e1, ls; };
+__device__ __forceinline__ uint32_t prefix_parity16(uint32_t v) {       // bit i = parity of bits 0..i
+    v ^= v << 1; v ^= v << 2; v ^= v << 4; v ^= v << 8;
+    return v;
+}
+__device__ __forceinline__ FqChunk fq_lines(uint32_t nl, bool first_is_line_start) {
+    FqChunk f;
+    f.nl = nl;
+    f.e0 = (prefix_parity16(nl) << 1) & 0xFFFFu;
+    f.e1 = (prefix_parity16(nl & f.e0) << 1) & 0xFFFFu;
+    f.ls = ((nl << 1) | (first_is_line_start ? 1u : 0u)) & 0xFFFFu;
+    return f;
+}
+__device__ __forceinline__ uint32_t fq_line_mask(const FqChunk& f, uint32_t r) {     // bytes of relative line r (mod 4)
+    return ((r & 1u) ? f.e0 : ~f.e0) & ((r & 2u) ? f.e1 : ~f.e1) & 0xFFFFu;
+}
+__device__ __forceinline__ Sum fq_summary(const FqChunk& f) {
+    const uint32_t nn = ~f.nl & 0xFFFFu;
+    uint32_t a[4], b[4];
+#pragma unroll
+    for (uint32_t r = 0; r < 4; ++r) {
+        const uint32_t m = fq_line_mask(f, r) & nn;
+        a[r] = (uint32_t)__popc(m);                 // bytes that would be sequence entries if line r is a sequence line
+        b[r] = (uint32_t)__popc(m & f.ls);          // line starts that would be record breaks if line r is a header line
+    }
+    const uint32_t n = (uint32_t)__popc(f.nl);
+    Sum s;
+    s.e = ((0 + n) & 3) | (((1 + n) & 3) << 2) | (((2 + n) & 3) << 4) | (((3 + n) & 3) << 6);
+    s.c0 = a[1] + b[0]; s.c1 = a[0] + b[3]; s.c2 = a[3] + b[2]; s.c3 = a[2] + b[1];
+    return s;
+}
+// positions of the chunk's control characters and of its newlines (16-bit masks)
+__device__ __forceinline__ void fq_control(const Chunk16& ch, uint32_t& ctrl, uint32_t& nl) {
+    ctrl = nl = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        ctrl |= swar_movemask(swar_zero_bytes(ch.w[w] & 0xE0E0E0E0u)) << (4 * w);
+        nl |= swar_movemask(swar_zero_bytes(ch.w[w] ^ 0x0A0A0A0Au)) << (4 * w);
+    }
+}
+
 // Entries of one chunk, kept apart for the bytes before its first line start (head: emitted only when the chunk
 // starts inside a sequence line) and after it (rest).  Compacted: entry j at bits 2j / j.
 struct FaParts {

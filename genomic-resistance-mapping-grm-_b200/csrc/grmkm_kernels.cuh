@@ -265,9 +265,39 @@ struct PackParams {
     uint64_t* scalars;
 };
 
+// ---- bulk asynchronous copies (TMA, 1-D): global -> shared, completion counted in bytes on an mbarrier -----------
+// SASS: UBLKCP.S.G / SYNCS.ARRIVE.TRANS64 / SYNCS.PHASECHK.  Source, destination and size are multiples of 16 bytes.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+    } while (!ok);
+}
+// generic-proxy reads of a shared buffer are ordered before the async proxy overwrites it
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// TMA: persistent variant.  The grid is what is resident at once (4 CTAs per SM), CTA b takes tickets b, b + grid, ... and
+// the 16 KiB text tile of its NEXT ticket is fetched by one cp.async.bulk into shared memory while the current tile is
+// parsed: the ticket record, the text and its HBM latency are off the tile's critical path, and the text is read with
+// LDS.128 instead of LDG.128.  (Tickets are still started in order -- every CTA is resident and works through its
+// tickets in ascending order, so the smallest unfinished ticket is always being worked on: the look-back cannot
+// deadlock.)
 // SUMMARY_ONLY: publish the tile's summary and stop (first pass of the two-pass parse of very long files, see
 // k_scan_tile_chains).
-template <int KIND, bool SUMMARY_ONLY = false>
+template <int KIND, bool SUMMARY_ONLY = false, bool TMA = false>
 __global__ void __launch_bounds__(kParseThreads, 1024 / kParseThreads)
 k_pack(const PackParams p) {
     constexpr int kGroups = kTileBytes / 32 + 2;
@@ -276,33 +306,23 @@ k_pack(const PackParams p) {
     __shared__ uint32_t s_valid[kGroups + 2];
     __shared__ uint32_t s_nrec, s_st;
     __shared__ uint64_t s_pos;
-    __shared__ uint4 s_tk[4];                                           // this CTA's TileTicket
-    if (threadIdx.x == 0) {
-        const uint32_t ticket = atomicAdd(p.ticket, 1u);
-        s_nrec = 0;
-        if (ticket == 0) p.scalars[S_STREAM_LEN] = p.stream_len;
-        if (ticket < p.n_tiles) {
-            const uint4* src = reinterpret_cast<const uint4*>(p.tickets + ticket);
-            const uint4 a = src[0], b = src[1], c = src[2], d = src[3];
-            s_tk[0] = a; s_tk[1] = b; s_tk[2] = c; s_tk[3] = d;
-        } else {
-            s_tk[3] = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);                 // no tile left
-        }
-    }
-    for (int i = threadIdx.x; i < kGroups * 2 + 4; i += blockDim.x) s_codes[i] = 0;
-    for (int i = threadIdx.x; i < kGroups + 2; i += blockDim.x) s_valid[i] = 0;
-    __syncthreads();
-    const TileTicket& tk = *reinterpret_cast<const TileTicket*>(s_tk);
+    __shared__ uint4 s_tk[TMA ? 8 : 4];                                 // this CTA's TileTicket (TMA: and the next one)
+    __shared__ __align__(128) uint8_t s_text[TMA ? kTileBytes : 16];    // TMA: the tile's text
+    __shared__ __align__(8) unsigned long long s_mbar;
+    static_assert(!(TMA && SUMMARY_ONLY), "the summary pass is not persistent");
+    auto make_ctx = [&](const TileTicket& tk) {
+        TileCtx t;
+        t.f = tk.f; t.fd = tk.fd; t.hdr0 = tk.hdr0;
+        t.first_tile = (tk.tile == t.fd.tile_begin);
+        t.off = (tk.tile - t.fd.tile_begin) * (uint64_t)kTileBytes + (uint64_t)threadIdx.x * (16 * kChunksPerThread);
+        return t;
+    };
+    // ---- everything after the thread's 64 bytes are in registers
+    auto tile_body = [&](const TileTicket& tk, const TileCtx& t, const ThreadText& x) {
     const uint64_t tile = tk.tile;
-    if (tk.tile == 0xFFFFFFFFu) return;
     unsigned long long* __restrict__ codes = p.codes;
     uint32_t* __restrict__ valid = p.valid;
-    TileCtx t;
-    t.f = tk.f; t.fd = tk.fd; t.hdr0 = tk.hdr0;
-    t.first_tile = (tile == t.fd.tile_begin);
-    t.off = (tile - t.fd.tile_begin) * (uint64_t)kTileBytes + (uint64_t)threadIdx.x * (16 * kChunksPerThread);
     const uint64_t file_stream_start = tk.stream_start;
-    const ThreadText x = load_thread_text(t);
     // publish the tile's summary, resolve its incoming state and position (warp 0), publish those
     auto publish = [&](const Sum& total) {
         if (threadIdx.x == 0) {
@@ -361,22 +381,22 @@ k_pack(const PackParams p) {
         local = (ex & kFaMask) + (tile_seq ? ((ex >> kFaH) & kFaMask) : 0u);
         e_total = (tot & kFaMask) + (tile_seq ? ((tot >> kFaH) & kFaMask) : 0u);
     } else {
-        // A chunk without control characters (no '\n', no '\r': nine of ten chunks of 150-base reads, sequence and quality
-        // lines alike) lies inside ONE line: its summary is the identity on the state with 16 entries in state 1 (one
-        // entry in state 0 when it starts the header line), and its entries are the SWAR classification of fa_bases.
-        // Only the chunks that hold a line end go through the byte loops.
+        // A live chunk whose only control characters are newlines is classified without a byte loop (fq_lines /
+        // fq_summary): nine chunks of ten of 150-base reads hold no newline at all, the rest one or two.  Byte loops
+        // are left for CR-LF text, tabs and the first / last bytes of a file.
         Sum sums[kChunksPerThread];
         Sum mine = sum_identity(), excl, total;
-        uint32_t fastm = 0;
+        uint32_t fastm = 0, nlm[kChunksPerThread];
 #pragma unroll
         for (int c = 0; c < kChunksPerThread; ++c) {
             const uint64_t pos0 = t.off + 16 * c;
-            uint32_t ctrl = 0;
-#pragma unroll
-            for (int w = 0; w < 4; ++w) ctrl |= swar_zero_bytes(x.ch[c].w[w] & 0xE0E0E0E0u);
-            if (ctrl == 0 && pos0 >= t.hdr0 && pos0 + 16 <= t.fd.len) {
+            uint32_t ctrl;
+            fq_control(x.ch[c], ctrl, nlm[c]);
+            if (ctrl == nlm[c] && pos0 >= t.hdr0 && pos0 + 16 <= t.fd.len) {
                 fastm |= 1u << c;
-                sums[c].e = 0xE4u; sums[c].c0 = (pos0 == t.hdr0 || x.prev[c] == '\n') ? 1u : 0u; sums[c].c1 = 16u; sums[c].c2 = sums[c].c3 = 0u;
+                const bool first = pos0 == t.hdr0 || x.prev[c] == '\n';
+                if (nlm[c] == 0) { sums[c].e = 0xE4u; sums[c].c0 = first ? 1u : 0u; sums[c].c1 = 16u; sums[c].c2 = sums[c].c3 = 0u; }
+                else sums[c] = fq_summary(fq_lines(nlm[c], first));
             } else {
                 sums[c] = chunk_summary<1>(x.ch[c], x.prev[c], pos0, t.fd.len, t.hdr0);
             }
@@ -392,11 +412,30 @@ k_pack(const PackParams p) {
 #pragma unroll
         for (int c = 0; c < kChunksPerThread; ++c) {
             if ((fastm >> c) & 1u) {
-                if (st == 1) {
-                    uint32_t vb, cb;
-                    fa_bases(x.ch[c], vb, cb);
-                    acc.append(cb, vb, 16u);
-                } else if (st == 0 && sums[c].c0) { acc.append(0u, 0u, 1u); nrec++; }
+                const bool first = (t.off + 16 * c) == t.hdr0 || x.prev[c] == '\n';
+                if (nlm[c] == 0) {
+                    if (st == 1) {
+                        uint32_t vb, cb;
+                        fa_bases(x.ch[c], vb, cb);
+                        acc.append(cb, vb, 16u);
+                    } else if (st == 0 && first) { acc.append(0u, 0u, 1u); nrec++; }
+                    continue;
+                }
+                const FqChunk f = fq_lines(nlm[c], first);
+                const uint32_t nn = ~f.nl & 0xFFFFu;
+                const uint32_t seq = fq_line_mask(f, (1u - st) & 3u) & nn;          // bytes of the sequence line
+                const uint32_t hdr = fq_line_mask(f, (4u - st) & 3u) & nn & f.ls;   // first bytes of header lines
+                uint32_t vb = 0, cb = 0;
+                if (seq) { fa_bases(x.ch[c], vb, cb); vb &= seq; }
+                nrec += (uint32_t)__popc(hdr);
+                for (uint32_t em = seq | hdr; em;) {               // runs of emitting bytes (one, seldom two)
+                    const uint32_t s0 = (uint32_t)__ffs(em) - 1u;
+                    const uint32_t run = (uint32_t)__ffs(~(em >> s0)) - 1u;
+                    const uint32_t lo = (1u << run) - 1u;
+                    acc.append((cb >> (2u * s0)) & (run >= 16u ? 0xFFFFFFFFu : ((1u << (2u * run)) - 1u)), (vb >> s0) & lo, run);
+                    em &= ~(lo << s0);
+                }
+                st = (st + (uint32_t)__popc(f.nl)) & 3u;
                 continue;
             }
             uint32_t cbits = 0, vbits = 0, n = 0, prev = x.prev[c];
@@ -458,6 +497,111 @@ k_pack(const PackParams p) {
     if (threadIdx.x == 0) {
         if (s_nrec) atomicAdd((unsigned long long*)&p.scalars[S_N_RECORDS], (unsigned long long)s_nrec);
         if (e_total) atomicAdd((unsigned long long*)&p.scalars[S_STREAM_TOTAL], (unsigned long long)e_total);
+    }
+    };  // tile_body
+
+    if (!TMA) {
+        // ---- one tile per CTA, tickets from the counter
+        if (threadIdx.x == 0) {
+            const uint32_t ticket = atomicAdd(p.ticket, 1u);
+            s_nrec = 0;
+            if (ticket == 0) p.scalars[S_STREAM_LEN] = p.stream_len;
+            if (ticket < p.n_tiles) {
+                const uint4* src = reinterpret_cast<const uint4*>(p.tickets + ticket);
+                const uint4 a = src[0], b = src[1], c = src[2], d = src[3];
+                s_tk[0] = a; s_tk[1] = b; s_tk[2] = c; s_tk[3] = d;
+            } else {
+                s_tk[3] = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);                 // no tile left
+            }
+        }
+        for (int i = threadIdx.x; i < kGroups * 2 + 4; i += blockDim.x) s_codes[i] = 0;
+        for (int i = threadIdx.x; i < kGroups + 2; i += blockDim.x) s_valid[i] = 0;
+        __syncthreads();
+        const TileTicket& tk = *reinterpret_cast<const TileTicket*>(s_tk);
+        if (tk.tile == 0xFFFFFFFFu) return;
+        const TileCtx t = make_ctx(tk);
+        const ThreadText x = load_thread_text(t);
+        tile_body(tk, t, x);
+        return;
+    }
+
+    // ---- persistent: the next ticket's text travels while this tile is parsed.  Tickets still come from the counter (a
+    // statically dealt tile could start later than a tile that waits for it): the ticket NUMBER is taken two tiles ahead,
+    // its record is loaded one tile ahead, so neither latency is on a tile's critical path.
+    const uint32_t mbar = smem_u32(&s_mbar), text = smem_u32(s_text);
+    auto issue = [&](const uint4 (&rec)[4]) {                 // thread 0: arm the barrier, start the bulk copy
+        const TileTicket& k = *reinterpret_cast<const TileTicket*>(rec);
+        const uint64_t off = (uint64_t)(k.tile - k.fd.tile_begin) * kTileBytes;
+        const uint64_t avail = k.fd.len > off ? k.fd.len - off : 0;
+        const uint32_t nb = (uint32_t)(avail < (uint64_t)kTileBytes ? avail : (uint64_t)kTileBytes) & ~15u;   // whole 16-byte chunks
+        fence_proxy_async();
+        mbar_expect_tx(mbar, nb);
+        if (nb) bulk_g2s(text, k.fd.ptr + off, nb, mbar);
+    };
+    const uint64_t n_tiles = p.n_tiles;
+    uint32_t tk1 = 0xFFFFFFFFu;                               // thread 0: ticket number of the next iteration
+    if (threadIdx.x == 0) {
+        mbar_init(mbar, 1);
+        const uint32_t t0 = atomicAdd(p.ticket, 1u);
+        tk1 = atomicAdd(p.ticket, 1u);
+        if (t0 == 0) p.scalars[S_STREAM_LEN] = p.stream_len;
+        if (t0 < n_tiles) {
+            const uint4* src = reinterpret_cast<const uint4*>(p.tickets + t0);
+            uint4 rec[4] = {src[0], src[1], src[2], src[3]};
+            s_tk[0] = rec[0]; s_tk[1] = rec[1]; s_tk[2] = rec[2]; s_tk[3] = rec[3];
+            issue(rec);
+        } else {
+            s_tk[3] = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);     // no tile at all for this CTA
+        }
+    }
+    __syncthreads();
+    for (uint32_t it = 0;; ++it) {
+        const uint32_t cur = (it & 1u) * 4u;
+        const TileTicket& tk = *reinterpret_cast<const TileTicket*>(s_tk + cur);
+        if (tk.tile == 0xFFFFFFFFu) break;
+        uint4 nxt[4];
+        uint32_t tk2 = 0xFFFFFFFFu;
+        const bool more = threadIdx.x == 0 && tk1 < n_tiles;
+        if (more) {                                            // record of the next ticket, number of the one after: both in flight
+            const uint4* src = reinterpret_cast<const uint4*>(p.tickets + tk1);
+            nxt[0] = src[0]; nxt[1] = src[1]; nxt[2] = src[2]; nxt[3] = src[3];
+            tk2 = atomicAdd(p.ticket, 1u);
+        }
+        for (int i = threadIdx.x; i < kGroups * 2 + 4; i += blockDim.x) s_codes[i] = 0;
+        for (int i = threadIdx.x; i < kGroups + 2; i += blockDim.x) s_valid[i] = 0;
+        if (threadIdx.x == 0) s_nrec = 0;
+        const TileCtx t = make_ctx(tk);
+        mbar_wait(mbar, it & 1u);
+        ThreadText x;
+#pragma unroll
+        for (int c = 0; c < kChunksPerThread; ++c) {
+            const uint64_t off = t.off + 16 * c;
+            if (off + 16 <= t.fd.len) {
+                const uint4 v = *reinterpret_cast<const uint4*>(s_text + threadIdx.x * (16 * kChunksPerThread) + 16 * c);
+                x.ch[c].w[0] = v.x; x.ch[c].w[1] = v.y; x.ch[c].w[2] = v.z; x.ch[c].w[3] = v.w;
+            } else {
+                x.ch[c] = load_chunk(t.fd.ptr, off, t.fd.len);           // the file's last, partial chunk (or nothing)
+            }
+        }
+        {
+            uint32_t pb = __shfl_up_sync(0xffffffffu, x.ch[kChunksPerThread - 1].byte(15), 1);
+            if ((threadIdx.x & 31) == 0) pb = (t.off > 0 && t.off - 1 < t.fd.len) ? t.fd.ptr[t.off - 1] : (uint32_t)'\n';
+            x.prev[0] = pb;
+#pragma unroll
+            for (int c = 1; c < kChunksPerThread; ++c) x.prev[c] = x.ch[c - 1].byte(15);
+        }
+        __syncthreads();                                       // the text is in registers, the tile arrays are clear
+        if (threadIdx.x == 0) {
+            if (more) {
+                s_tk[(cur ^ 4u) + 0] = nxt[0]; s_tk[(cur ^ 4u) + 1] = nxt[1]; s_tk[(cur ^ 4u) + 2] = nxt[2]; s_tk[(cur ^ 4u) + 3] = nxt[3];
+                issue(nxt);
+            } else {
+                s_tk[(cur ^ 4u) + 3] = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
+            }
+            tk1 = tk2;
+        }
+        tile_body(tk, t, x);
+        __syncthreads();                                       // the tile arrays are free again, the next ticket is visible
     }
 }
 
