@@ -202,7 +202,6 @@ size_t table_smem(uint32_t slots, uint32_t cells) {
 constexpr uint32_t kUnitMaxBucketBits = 11;      // the unit expansion sorts tiles over at most 2^11 hash buckets
 constexpr uint32_t kMaxSubBits = 3;              // key sub-ranges (virtual buckets) per bucket: up to 2^3
 constexpr uint32_t kRoundMaxRows = 4;            // genome rows per abundance round (one u32 counter plane each)
-constexpr uint64_t kTwoPassTilesPerFile = 2048;  // parse in two passes when the files average more tiles than this (32 MB)
 constexpr uint32_t kBlockRows = 256;             // presence builds of more genomes than this run in row blocks (build_row_blocks)
 
 bool abundance_build(const grmkm_ctx* c) { return c->cfg.min_abundance > 1 || (c->cfg.flags & GRMKM_FLAG_COUNTS); }
@@ -291,7 +290,7 @@ uint32_t auto_bucket_bits(grmkm_ctx* c, const InputTable& t) {
     }
     uint64_t rb = 0; uint32_t rr = 1;
     for (const Round& rd : plan_rounds(c, t.G, t.first_file, t.row_bytes)) { rb = std::max(rb, rd.bytes); rr = std::max(rr, rd.n_rows); }
-    return bits_for(rb / 8 + 1024, table_slots(c, (rr + 1) & ~1u));
+    return bits_for(rb / 12 + 1024, table_slots(c, (rr + 1) & ~1u));       // one distinct k-mer per 12 bytes of read text (measured: 12.4)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -574,9 +573,12 @@ int run_job(grmkm_ctx* c, const Geo& geo, const Job& job, JobOut& out) {
             CU_TRY(c, cudaMemsetAsync(pp.ticket, 0, 4, st));
             out.launches += 2;
         }
-        if (!getenv("GRMKM_PACK_LDG")) {
+        if (getenv("GRMKM_PACK_TMA")) {
             // persistent CTAs (exactly what is resident at once), the next tile's text fetched by cp.async.bulk under the
-            // current tile's parse
+            // current tile's parse.  Measured against the one-tile-per-CTA kernel on C2 (profiles/r02_pack_tma_ab.txt):
+            // 0.85 ms instead of 0.63 ms -- the resident CTAs serialise on their own look-back waits, while the hardware
+            // scheduler refills an SM with a fresh tile as soon as any CTA exits -- so it is kept as an option, not the
+            // default.
             const int kind = c->cfg.input_kind == GRMKM_FASTA ? 0 : 1;
             if (!c->pack_ctas[kind]) {
                 int occ = 0;
