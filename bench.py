@@ -352,6 +352,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--no-e2e-files", action="store_true")
+    ap.add_argument("--no-e2e-pipeline", action="store_true", help="e2e with one context only (no builds in flight side by side)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
@@ -472,6 +473,33 @@ def main():
                     torch.distributed.barrier()
                 res["ms_e2e"] = f0.elapsed_time(f1)
                 res["d2h"] = int(km.nbytes + mat.nbytes)
+                res["ms_e2e_serial"], res["e2e_serial_steps"] = res["ms_e2e"], res["e2e_steps"]
+                if world == 1 and not args.no_e2e_pipeline:
+                    # a series of builds through the public BuildPipeline (two contexts of this GPU, one worker thread each):
+                    # build i + 1's H2D copy runs while build i computes and copies its result out.  Every build copies its
+                    # whole input in and its whole result out, as above.
+                    from grm_b200.builder import BuildPipeline
+                    ps = [torch.cuda.Stream() for _ in range(2)]
+                    n_pipe = 2 * max(2, min(args.steps, 6) // 2 + 1)
+                    with BuildPipeline(depth=2, streams=[s_.cuda_stream for s_ in ps], k=k, min_abundance=conf["min_ab"],
+                                       keep_singletons=keep, input_kind=kind, device=local_rank) as pipe:
+                        with near_gpu(local_rank):
+                            for f_ in [pipe.submit(rows_np, host_np, n_genomes=G_total) for _ in range(4)]:
+                                pk, pm, _ = f_.result()
+                        if pk.shape != km.shape or not (np.array_equal(pk, km) and np.array_equal(pm, mat)):
+                            raise SystemExit("bench.py: the pipelined build differs from the single-context build")
+                        torch.cuda.synchronize()
+                        g0 = torch.cuda.Event(enable_timing=True)
+                        g0.record(ps[0])
+                        for f_ in [pipe.submit(rows_np, host_np, n_genomes=G_total) for _ in range(n_pipe)]:
+                            f_.result()
+                        g1 = [torch.cuda.Event(enable_timing=True) for _ in ps]
+                        for e_, s_ in zip(g1, ps):
+                            e_.record(s_)
+                        torch.cuda.synchronize()
+                        res["ms_e2e"], res["e2e_steps"] = max(g0.elapsed_time(e_) for e_ in g1), n_pipe
+                        res["e2e_mode"] = ("BuildPipeline(depth=2): two contexts of the GPU alternate, build i+1's H2D copy overlaps "
+                                           "build i's tail kernels and D2H copy; every build copies its own input and result")
                 if not args.no_parity_check:
                     res["parity"] = parity_check(db, cfg, conf, G_total, rank, world, dist, k, keep)
                 if world == 1 and rank == 0 and not conf["reads"] and not args.no_e2e_files:
@@ -540,7 +568,11 @@ def main():
             "scaling": "weak" if conf["per_gpu"] else "strong",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(name, conf, world, G_total),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps, "staging_numa_node": head.get("numa_node")},
+                    "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps, "staging_numa_node": head.get("numa_node"),
+                    "mode": head.get("e2e_mode", "one build at a time (DistributedBuilder.build + result_host per step)"),
+                    "serial": ({"value": total_bases / (head["ms_e2e_serial"] / head["e2e_serial_steps"] * 1e-3) / 1e9,
+                                "ms_per_step": head["ms_e2e_serial"] / head["e2e_serial_steps"], "steps": head["e2e_serial_steps"],
+                                "mode": "one build at a time"} if world == 1 and head.get("ms_e2e_serial") else None)},
             "gpu_launches": launches,
             "clocks": head["clocks"],
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",

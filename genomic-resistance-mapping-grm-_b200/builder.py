@@ -212,6 +212,64 @@ class KmerMatrixBuilder:
         return int(a.value or 0), int(b.value or 0)
 
 
+class BuildPipeline:
+    """Several builds in flight on ONE GPU (a series of datasets: one per antibiotic / species / parameter set).
+
+    ``depth`` contexts, each with its own stream, staging halves, page-locked result buffer and worker thread.
+    Build i + 1's text crosses PCIe host->device while build i's dedupe / expand / aggregate kernels and its
+    device->host copy of (kmers, matrix) are still in flight: the two directions of the link and the SMs are all
+    busy at once, so a stream of builds runs at the speed of the slowest leg (the H2D copy) instead of the sum of
+    the legs.  Every build still copies all of its own input in and all of its own result out.
+
+    submit(rows, data[, n_genomes]) -> Future of (kmers, matrix, stats): views of the slot's page-locked result buffer, valid
+    until ``depth`` further submissions have been made (copy them to keep them longer).
+    """
+
+    def __init__(self, depth: int = 2, streams: Sequence[int] | None = None, **builder_kw):
+        """streams: one CUDA stream handle per slot (default: every slot creates its own)."""
+        import concurrent.futures as cf
+        if depth < 1:
+            raise ValueError("depth must be at least 1")
+        if streams is not None and len(streams) != depth:
+            raise ValueError("one stream per slot")
+        builder_kw.pop("stream", None)
+        self.slots = [KmerMatrixBuilder(stream=streams[i] if streams else None, **builder_kw) for i in range(depth)]
+        self._workers = [cf.ThreadPoolExecutor(max_workers=1) for _ in range(depth)]
+        self._n = 0
+
+    @staticmethod
+    def _run(b: KmerMatrixBuilder, rows, data, lens, on_device, n_genomes):
+        # (the slot's previous build has finished: one worker per slot.  The library lets the H2D legs of builds in
+        # different contexts of one device follow one another -- grmkm_api.cu, h2d gate -- so the builds fall into step:
+        # one copies its text in while the other computes and copies its result out.)
+        b.reset()
+        if n_genomes:
+            b.set_genome_count(n_genomes)
+        b.add_genomes(rows, data, lens, on_device)
+        b.build()
+        km, mat = b.result_host()
+        return km, mat, b.stats
+
+    def submit(self, rows, data, lens=None, on_device: bool = False, n_genomes: int = 0):
+        i = self._n
+        self._n += 1
+        s = i % len(self.slots)
+        return self._workers[s].submit(self._run, self.slots[s], rows, data, lens, on_device, n_genomes)
+
+    def close(self):
+        for w in self._workers:
+            w.shutdown(wait=True)
+        for b in self.slots:
+            b.close()
+        self.slots = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
 def build_matrix(genomes: Sequence, k: int = 31, min_abundance: int = 1, keep_singletons: bool = False,
                  input_kind: int = FASTA, **kw):
     """One-shot helper: genomes = list (row order) of bytes or lists of bytes.  Returns (kmers, matrix, stats)."""

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -38,6 +39,17 @@ struct Input {
 
 constexpr uint32_t kMaxGenomes = 32768;
 constexpr uint64_t kBatchBytes = 32ull << 20;      // text per pipelined H2D batch (GRMKM_BATCH_BYTES overrides, for tests)
+
+// H2D gate.  Several contexts of one device may build at the same time (builder.BuildPipeline: a series of datasets,
+// one worker thread per context).  Their host->device legs follow one another instead of sharing the link: the first
+// copy of a build waits for the event the previous build recorded behind its last copy, so the builds fall into
+// step -- one copies its text in while the other runs its dedupe / expand / aggregate kernels and copies its result
+// out (PCIe is full duplex).  With one context the event is long complete and the wait costs nothing.
+struct H2dGate {
+    std::mutex mu;                    // held while a build enqueues its copies: the order of the legs = the order of the locks
+    cudaEvent_t done[64] = {};        // per device, created on first use, never destroyed (process lifetime)
+};
+H2dGate g_h2d;
 
 enum Stage { T_START = 0, T_H2D, T_PARSE, T_PACK, T_COUNT, T_BOUNDS, T_SCATTER, T_ABUND, T_DEDUPE, T_EXPAND, T_AGG, T_SORT, T_N };
 
@@ -668,6 +680,14 @@ int run_job(grmkm_ctx* c, const Geo& geo, const Job& job, JobOut& out) {
         if (pipelined && c->ev_ok)
             for (int e : {T_H2D, T_PARSE, T_PACK, T_COUNT, T_BOUNDS}) cudaEventRecord(c->ev[e], st);   // stages interleave: only "scatter" is timed
         out.h2d = 0;
+        std::unique_lock<std::mutex> gate;
+        cudaEvent_t* gate_ev = nullptr;
+        if (any_host && c->device >= 0 && c->device < 64) {
+            gate = std::unique_lock<std::mutex>(g_h2d.mu);
+            gate_ev = &g_h2d.done[c->device];
+            if (!*gate_ev) CU_TRY(c, cudaEventCreateWithFlags(gate_ev, cudaEventDisableTiming));
+            else CU_TRY(c, cudaStreamWaitEvent(pipelined ? c->copy_stream : st, *gate_ev, 0));
+        }
         for (size_t bi = 0; bi < batches.size(); ++bi) {
             const Batch& bt = batches[bi];
             uint8_t* half = (uint8_t*)c->in.p + (pipelined ? (bi & 1) * half_bytes : 0);
@@ -733,6 +753,10 @@ int run_job(grmkm_ctx* c, const Geo& geo, const Job& job, JobOut& out) {
             k_units_scatter<false><<<ugrid, kUsThreads, usm, st>>>(up);
             out.launches++;
             CU_TRY(c, cudaGetLastError());
+        }
+        if (gate_ev) {
+            CU_TRY(c, cudaEventRecord(*gate_ev, pipelined ? c->copy_stream : st));      // behind this build's last copy
+            gate.unlock();
         }
         // bucket b = units[begin[b], end[b]): end = the cursors (clamped to the region)
         k_finish_unit_regions<<<1, 1024, 0, st>>>((const unsigned long long*)c->ubeg.p, (unsigned long long*)c->ucur.p, MB,

@@ -170,3 +170,28 @@ def test_surveyor_conf_to_tsv_to_kover(gpu, tmp_path):
     r = hdf5min.H5Reader(str(out))
     assert np.array_equal(r["kmer_matrix"].read(), ref.matrix)
     assert surveyor.main([str(tmp_path / "missing.conf")]) == 1
+
+
+def test_build_pipeline_series_of_datasets(gpu):
+    """BuildPipeline: several builds in flight on one GPU (two contexts, one worker thread each, H2D legs gated one
+    after the other by the library).  Every dataset of the series equals the oracle's, whatever slot built it, and the
+    slots' result buffers stay valid for `depth` submissions."""
+    from grm_b200.builder import BuildPipeline
+    from grm_b200.synth import SynthConfig, genome_fasta, MASTER_SEED
+    rng = np.random.default_rng(77)
+    cfg = SynthConfig(seed=MASTER_SEED + 5).scaled(0.02)
+    sets = []
+    for d in range(7):
+        G = int(rng.integers(1, 9))
+        texts = [genome_fasta(cfg, int(g)) for g in rng.integers(0, 40, size=G)]
+        sets.append(texts)
+    with BuildPipeline(depth=2, k=31, keep_singletons=True) as pipe:
+        futs = [pipe.submit(np.arange(len(t), dtype=np.uint32), t, n_genomes=len(t)) for t in sets]
+        got = []
+        for f in futs:
+            km, mat, st = f.result()
+            got.append((km.copy(), mat.copy(), st))       # the views die two submissions later
+    for texts, (km, mat, st) in zip(sets, got):
+        ref = oracle.build([[(t, 0)] for t in texts], 31, 1, True)
+        assert np.array_equal(km, ref.kmers) and np.array_equal(mat, ref.matrix)
+        assert st["n_windows"] == ref.n_windows
