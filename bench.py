@@ -449,11 +449,18 @@ def main():
                 # library's result buffer in the first step): no cross-socket hop per byte
                 from grm_b200.numa import near_gpu
                 with near_gpu(local_rank) as numa_node:
-                    host_in = [torch.empty(ln, dtype=torch.uint8).pin_memory() for _, ln in spans]
-                    for t, (off, ln) in zip(host_in, spans):
-                        t.copy_(buf[off:off + ln])
+                    # one page-locked arena, files 16-byte aligned one after the other (what create._read_inputs makes of
+                    # the .fna files): the library then moves a whole staging batch with one copy
+                    offs, tot = [], 0
+                    for _, ln in spans:
+                        offs.append(tot)
+                        tot += (ln + 15) & ~15
+                    host_in = torch.zeros(max(tot, 16), dtype=torch.uint8).pin_memory()
+                    for o, (off, ln) in zip(offs, spans):
+                        host_in[o:o + ln].copy_(buf[off:off + ln])
                     stream.synchronize()
-                    host_np = [t.numpy() for t in host_in]
+                    arena = host_in.numpy()
+                    host_np = [arena[o:o + ln] for o, (_, ln) in zip(offs, spans)]
                     km, mat = step_e2e()
                 res["numa_node"] = numa_node
 

@@ -206,10 +206,12 @@ class KmerMatrixBuilder:
                                              C.c_void_p(out.ctypes.data), out.size))
         return out
 
-    def device_result(self) -> tuple[int, int]:
-        a, b = C.c_void_p(), C.c_void_p()
-        self._check(self._lib.grmkm_device_result(self._ctx, C.byref(a), C.byref(b)))
-        return int(a.value or 0), int(b.value or 0)
+    def device_result(self) -> tuple[int, int, int]:
+        """(device pointer of kmers[U], device pointer of the matrix, row pitch in words): word row w of the matrix
+        starts at pointer + 8 * w * pitch."""
+        a, b, p = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        self._check(self._lib.grmkm_device_result(self._ctx, C.byref(a), C.byref(b), C.byref(p)))
+        return int(a.value or 0), int(b.value or 0), int(p.value)
 
 
 class BuildPipeline:

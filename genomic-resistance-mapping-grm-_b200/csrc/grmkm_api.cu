@@ -107,6 +107,8 @@ struct grmkm_ctx {
     // result
     bool built = false;
     uint64_t U = 0;
+    uint64_t pitch = 0;            // u64 words between two word rows of `matrix` (>= U: the ordered emission writes every row at
+                                   // the stride of its capacity guess, because U is only known when the last bucket is done)
     uint32_t W = 0, G = 0;
     grmkm_stats stats{};
     grmkm_times times{};
@@ -390,10 +392,10 @@ int run_aggregate(grmkm_ctx* c, const Geo& geo, const AggIn& in, JobOut& out, bo
         if (in.agg == AGG_ROUND) {
             // the records go straight behind the earlier rounds' (the caller grows that buffer when a round does not fit)
         } else if (ordered) {
-            // the columns land at their final place: k-mers and word row 0 in the result arrays, rows >= 1 at stride ucap
+            // the columns land at their final place: k-mers in the result array, word row w at matrix + w * ucap (the
+            // result's row pitch is the capacity: no pass over the rows once U is known)
             ENSURE(c, c->kmers, ucap * 8);
             ENSURE(c, c->matrix, (size_t)ucap * in.n_words * 8);
-            if (in.n_words > 1) ENSURE(c, c->uwords, (size_t)ucap * in.n_words * 8);
             CU_TRY(c, cudaMemsetAsync(c->apub.p, 0, (size_t)(VB + 1) * 8, st));
         } else {
             ENSURE(c, c->ukeys, ucap * 8);
@@ -412,7 +414,7 @@ int run_aggregate(grmkm_ctx* c, const Geo& geo, const AggIn& in, JobOut& out, bo
         ap.out_wbits = in.out_wbits; ap.out_word = in.out_word; ap.out_wide = in.round_out;
         if (ordered) {
             ap.ordered = 1;
-            ap.out_keys = (unsigned long long*)c->kmers.p; ap.out_row0 = (unsigned long long*)c->matrix.p;
+            ap.out_keys = (unsigned long long*)c->kmers.p; ap.out_words = (unsigned long long*)c->matrix.p;
             ap.pub = (unsigned long long*)c->apub.p; ap.ticket = (unsigned int*)((unsigned long long*)c->apub.p + VB);
         }
         void (*kern)(AggParams2) = in.agg == AGG_FINAL ? k_aggregate_cols<4> : in.agg == AGG_PARTIAL ? k_aggregate_cols<5>
@@ -421,17 +423,7 @@ int run_aggregate(grmkm_ctx* c, const Geo& geo, const AggIn& in, JobOut& out, bo
         kern<<<vgrid, kAggThreads, smem, st>>>(ap);
         out.launches++;
         CU_TRY(c, cudaGetLastError());
-        if (ordered) {
-            // rows >= 1 move from stride ucap to the result's stride U (row 0 and the k-mers are already in place); U is read
-            // on the device, so the build ends with this one synchronisation
-            if (c->ev_ok) cudaEventRecord(c->ev[T_AGG], st);
-            if (in.n_words > 1) {
-                k_move_rows<<<(uint32_t)c->sm_count * 8, 256, 0, st>>>((const unsigned long long*)c->uwords.p, ucap, (unsigned long long*)c->matrix.p,
-                                                                      (const unsigned long long*)(d_scalars + S_U_NEEDED), in.n_words);
-                out.launches++;
-                CU_TRY(c, cudaGetLastError());
-            }
-        }
+        if (ordered && c->ev_ok) cudaEventRecord(c->ev[T_AGG], st);
         CU_TRY(c, cudaMemcpyAsync(out.sc, d_scalars, sizeof out.sc, cudaMemcpyDeviceToHost, st));
         CU_TRY(c, cudaStreamSynchronize(st));
         const int up = check_upstream(out.sc);          // 1: an upstream guess was too small, the caller repeats the round
@@ -682,7 +674,7 @@ int run_job(grmkm_ctx* c, const Geo& geo, const Job& job, JobOut& out) {
         out.h2d = 0;
         std::unique_lock<std::mutex> gate;
         cudaEvent_t* gate_ev = nullptr;
-        if (any_host && c->device >= 0 && c->device < 64) {
+        if (any_host && c->device >= 0 && c->device < 64 && !getenv("GRMKM_NO_H2D_GATE")) {
             gate = std::unique_lock<std::mutex>(g_h2d.mu);
             gate_ev = &g_h2d.done[c->device];
             if (!*gate_ev) CU_TRY(c, cudaEventCreateWithFlags(gate_ev, cudaEventDisableTiming));
@@ -693,13 +685,28 @@ int run_job(grmkm_ctx* c, const Geo& geo, const Job& job, JobOut& out) {
             uint8_t* half = (uint8_t*)c->in.p + (pipelined ? (bi & 1) * half_bytes : 0);
             cudaStream_t cs = pipelined ? c->copy_stream : st;
             if (pipelined && bi >= 2) CU_TRY(c, cudaStreamWaitEvent(cs, c->ev_free[bi & 1], 0));
-            uint64_t soff = 0;
+            // Host buffers that follow one another in memory the way they are staged (each padded to 16 bytes: the arena of
+            // create._read_inputs, bench.py) travel as ONE copy per batch.  A train of 5 MB copies loses the link to a large
+            // copy in the other direction (another context's result on its way out: profiles/r02_duplex_pattern.txt).
+            uint64_t soff = 0, run_dst = 0, run_len = 0;
+            const uint8_t* run_src = nullptr;
+            auto flush_run = [&]() -> int {
+                if (run_len) CU_TRY(c, cudaMemcpyAsync(half + run_dst, run_src, run_len, cudaMemcpyHostToDevice, cs));
+                run_len = 0; run_src = nullptr;
+                return GRMKM_OK;
+            };
             for (uint32_t f = bt.f0; f < bt.f1; ++f) {
                 const Input& in = c->inputs[f];
                 if (in.dev) continue;
-                if (in.len) { CU_TRY(c, cudaMemcpyAsync(half + soff, in.host, in.len, cudaMemcpyHostToDevice, cs)); out.h2d += in.len; }
-                soff += (in.len + 15) & ~15ULL;
+                const uint64_t padded = (in.len + 15) & ~15ULL;
+                if (in.len) {
+                    if (run_len && in.host == run_src + (soff - run_dst)) run_len = (soff - run_dst) + in.len;      // adjacent: extend the run
+                    else { int fr = flush_run(); if (fr) return fr; run_src = in.host; run_dst = soff; run_len = in.len; }
+                    out.h2d += in.len;
+                }
+                soff += padded;
             }
+            { int fr = flush_run(); if (fr) return fr; }
             if (pipelined) {
                 CU_TRY(c, cudaEventRecord(c->ev_copied[bi & 1], cs));
                 CU_TRY(c, cudaStreamWaitEvent(st, c->ev_copied[bi & 1], 0));
@@ -966,6 +973,7 @@ int finish_columns(grmkm_ctx* c, const Geo& geo, uint32_t n_words, bool partial,
             CU_TRY(c, cudaMemcpyAsync(out.h_off.data(), c->offsets2.p, (size_t)(VB + 1) * 8, cudaMemcpyDeviceToHost, st));
         }
     }
+    c->pitch = out.ordered ? out.ucap : U;
     if (c->ev_ok) cudaEventRecord(c->ev[T_SORT], st);
     CU_TRY(c, cudaStreamSynchronize(st));
     return GRMKM_OK;
@@ -1480,7 +1488,8 @@ int grmkm_copy_matrix(grmkm_ctx* c, uint64_t* dst, uint64_t cap) {
     if (!n) return GRMKM_OK;
     if (!dst) return fail(c, GRMKM_E_INVALID, "null dst");
     CU_TRY(c, cudaSetDevice(c->device));
-    CU_TRY(c, cudaMemcpyAsync(dst, c->matrix.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    // (rows are c->pitch words apart on the device, U words apart in the caller's array)
+    CU_TRY(c, cudaMemcpy2DAsync(dst, c->U * 8, c->matrix.p, c->pitch * 8, c->U * 8, c->W, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     return GRMKM_OK;
 }
@@ -1533,7 +1542,7 @@ int grmkm_format_tsv(grmkm_ctx* c, const char* const* names, char* dst, uint64_t
     for (uint64_t j0 = 0; j0 < c->U; j0 += rows_per) {
         const uint64_t rows = std::min(rows_per, c->U - j0), nb = rows * roww;
         k_format_tsv<<<(uint32_t)((nb + 255) / 256), 256, 0, c->stream>>>((const unsigned long long*)c->kmers.p,
-                                                                          (const unsigned long long*)c->matrix.p, c->U, G,
+                                                                          (const unsigned long long*)c->matrix.p, c->pitch, G,
                                                                           k, j0, nb, (char*)c->fmt.p);
         CU_TRY(c, cudaGetLastError());
         CU_TRY(c, cudaMemcpyAsync(p + j0 * roww, c->fmt.p, nb, cudaMemcpyDeviceToHost, c->stream));
@@ -1555,19 +1564,28 @@ int grmkm_host_result(grmkm_ctx* c, const uint64_t** kmers, const uint64_t** mat
         c->host_res_cap = want;
     }
     uint8_t* h = (uint8_t*)c->host_res;
-    if (nk) CU_TRY(c, cudaMemcpyAsync(h, c->kmers.p, nk, cudaMemcpyDeviceToHost, c->stream));
-    if (nm) CU_TRY(c, cudaMemcpyAsync(h + nk, c->matrix.p, nm, cudaMemcpyDeviceToHost, c->stream));
+    // In pieces of 4 MiB: a single large device->host copy starves the host->device copies of another context that is
+    // staging its text at the same time (BuildPipeline); in pieces both directions keep moving
+    // (profiles/r02_duplex_pattern.txt).  Rows are c->pitch words apart on the device, U words apart on the host.
+    constexpr size_t kPiece = 4u << 20;
+    for (size_t o = 0; o < nk; o += kPiece)
+        CU_TRY(c, cudaMemcpyAsync(h + o, (const uint8_t*)c->kmers.p + o, std::min(kPiece, nk - o), cudaMemcpyDeviceToHost, c->stream));
+    for (uint32_t w = 0; w < c->W && nm; ++w)
+        for (size_t o = 0; o < nk; o += kPiece)
+            CU_TRY(c, cudaMemcpyAsync(h + nk + (size_t)w * nk + o, (const uint8_t*)c->matrix.p + (size_t)w * c->pitch * 8 + o,
+                                      std::min(kPiece, nk - o), cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     if (kmers) *kmers = (const uint64_t*)h;
     if (matrix) *matrix = (const uint64_t*)(h + nk);
     return GRMKM_OK;
 }
 
-int grmkm_device_result(const grmkm_ctx* c, const uint64_t** d_kmers, const uint64_t** d_matrix) {
+int grmkm_device_result(const grmkm_ctx* c, const uint64_t** d_kmers, const uint64_t** d_matrix, uint64_t* pitch_words) {
     if (check_ctx(c)) return GRMKM_E_INVALID;
     if (!c->built) return fail(const_cast<grmkm_ctx*>(c), GRMKM_E_INVALID, "no result: call grmkm_build first");
     if (d_kmers) *d_kmers = (const uint64_t*)c->kmers.p;
     if (d_matrix) *d_matrix = (const uint64_t*)c->matrix.p;
+    if (pitch_words) *pitch_words = c->pitch;
     return GRMKM_OK;
 }
 
@@ -1716,7 +1734,6 @@ static int merge_sources(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
     if (ordered) {
         ENSURE(c, c->kmers, ucap * 8);
         ENSURE(c, c->matrix, (size_t)ucap * W_total * 8);
-        if (W_total > 1) ENSURE(c, c->uwords, (size_t)ucap * W_total * 8);
         ENSURE(c, c->apub, (size_t)(nb + 1) * 8);
     } else {
         ENSURE(c, c->ukeys, ucap * 8);
@@ -1747,7 +1764,7 @@ static int merge_sources(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
     ap.b_begin = b_lo; ap.b_end = b_hi;
     if (ordered) {
         ap.ordered = 1;
-        ap.out_keys = (unsigned long long*)c->kmers.p; ap.out_row0 = (unsigned long long*)c->matrix.p;
+        ap.out_keys = (unsigned long long*)c->kmers.p; ap.out_words = (unsigned long long*)c->matrix.p;      // row pitch = ucap
         ap.pub = (unsigned long long*)c->apub.p; ap.ticket = (unsigned int*)((unsigned long long*)c->apub.p + nb);
     }
     CU_TRY(c, cudaFuncSetAttribute(k_aggregate_cols<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1755,12 +1772,6 @@ static int merge_sources(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
     L.n++;
     CU_TRY(c, cudaGetLastError());
     if (c->ev_ok) cudaEventRecord(c->ev[T_AGG], st);
-    if (ordered && W_total > 1) {
-        k_move_rows<<<(uint32_t)c->sm_count * 8, 256, 0, st>>>((const unsigned long long*)c->uwords.p, ucap, (unsigned long long*)c->matrix.p,
-                                                              (const unsigned long long*)(d_scalars + S_U_NEEDED), W_total);
-        L.n++;
-        CU_TRY(c, cudaGetLastError());
-    }
     uint64_t sc[S_COUNT];
     CU_TRY(c, cudaMemcpyAsync(sc, d_scalars, sizeof sc, cudaMemcpyDeviceToHost, st));
     if (ordered && c->ev_ok) cudaEventRecord(c->ev[T_SORT], st);
@@ -1795,6 +1806,7 @@ static int merge_sources(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, 
         CU_TRY(c, cudaStreamSynchronize(st));
     }
     c->U = U; c->built = !partial_out;
+    c->pitch = ordered ? ucap : U;
     c->stats.n_kmers = U; c->stats.n_distinct = sc[S_N_DISTINCT]; c->stats.n_words = W_total;
     c->stats.n_genomes = total_genomes; c->stats.n_splits += sc[S_N_SPLITS];
     c->stats.n_launches = launches_before + L.n;
@@ -1840,7 +1852,7 @@ int grmkm_result_checksum(grmkm_ctx* c, uint64_t out[2]) {
     ENSURE(c, c->aux, 16);
     CU_TRY(c, cudaMemsetAsync(c->aux.p, 0, 16, c->stream));
     k_checksum<<<(uint32_t)std::min<uint64_t>((c->U + 255) / 256, (uint64_t)c->sm_count * 8), 256, 0, c->stream>>>(
-        (const unsigned long long*)c->kmers.p, (const unsigned long long*)c->matrix.p, c->U, c->W, (unsigned long long*)c->aux.p);
+        (const unsigned long long*)c->kmers.p, (const unsigned long long*)c->matrix.p, c->U, c->pitch, c->W, (unsigned long long*)c->aux.p);
     CU_TRY(c, cudaGetLastError());
     c->stats.n_launches++;
     CU_TRY(c, cudaMemcpyAsync(out, c->aux.p, 16, cudaMemcpyDeviceToHost, c->stream));
@@ -1862,7 +1874,7 @@ int grmkm_sum_rows(grmkm_ctx* c, const uint64_t* row_mask, uint32_t n_mask_words
     uint32_t* d_out = (uint32_t*)((uint8_t*)c->aux.p + mask_bytes);
     CU_TRY(c, cudaMemcpyAsync(c->aux.p, row_mask, (size_t)c->W * 8, cudaMemcpyHostToDevice, c->stream));
     k_sum_rows<<<(uint32_t)std::min<uint64_t>((c->U + 255) / 256, (uint64_t)c->sm_count * 16), 256, 0, c->stream>>>(
-        (const unsigned long long*)c->matrix.p, c->U, c->W, (const unsigned long long*)c->aux.p, d_out);
+        (const unsigned long long*)c->matrix.p, c->U, c->pitch, c->W, (const unsigned long long*)c->aux.p, d_out);
     CU_TRY(c, cudaGetLastError());
     c->stats.n_launches++;
     CU_TRY(c, cudaMemcpyAsync(dst, d_out, c->U * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -1885,7 +1897,7 @@ int grmkm_gram(grmkm_ctx* c, uint64_t* dst, uint64_t cap) {
     unsigned long long* d_rows = (unsigned long long*)c->aux.p;
     unsigned long long* d_gram = (unsigned long long*)((uint8_t*)c->aux.p + rows_bytes);
     k_bit_rows<<<(uint32_t)std::min<uint64_t>(((uint64_t)c->W * UW + 7) / 8, (uint64_t)c->sm_count * 32), 256, 0, c->stream>>>(
-        (const unsigned long long*)c->matrix.p, c->U, c->W, UW, d_rows);
+        (const unsigned long long*)c->matrix.p, c->U, c->pitch, c->W, UW, d_rows);
     k_gram<<<(uint32_t)std::min<uint64_t>(G * (G + 1) / 2, (uint64_t)c->sm_count * 16), 256, 0, c->stream>>>(d_rows, UW, (uint32_t)G, d_gram);
     CU_TRY(c, cudaGetLastError());
     c->stats.n_launches += 2;

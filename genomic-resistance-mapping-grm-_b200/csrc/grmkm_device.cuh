@@ -324,7 +324,7 @@ __device__ __forceinline__ uint32_t swar_movemask(uint32_t m) {         // bits 
 
 // Line structure first, bases second.  The ALU pipe is the bound (LOP3 / SHF / PRMT issue every other cycle, IMAD goes to
 // the FMA pipe), so the tests are phrased with as few of those as possible.
-struct FaLines { uint32_t nl; bool fast; };          // nl: 16-bit newline mask; fast: see fa_lines
+struct FaLines { uint32_t nl; bool fast; uint32_t nlb[4]; };   // nl: 16-bit newline mask; fast: see fa_lines; nlb: 0xFF in every byte below 0x40
 
 __device__ __forceinline__ uint32_t prmt_sign(uint32_t x) {              // 0xFF in every byte of x whose bit 7 is set
     uint32_t d;
@@ -346,7 +346,8 @@ __device__ __forceinline__ FaLines fa_lines(const Chunk16& ch, uint64_t pos0, ui
     for (int w = 0; w < 4; ++w) {
         const uint32_t x = ch.w[w];
         const uint32_t low = ~(x | (x * 2u)) & 0x80808080u;              // bit 7 of every byte below 0x40
-        bad |= (x ^ 0x0A0A0A0Au) & prmt_sign(low);                       // ... that is not a newline
+        r.nlb[w] = prmt_sign(low);
+        bad |= (x ^ 0x0A0A0A0Au) & r.nlb[w];                             // ... that is not a newline
         r.nl |= swar_movemask(low) << (4 * w);
     }
     r.fast = bad == 0 && fa_fast_ok(pos0, len, hdr0);
@@ -365,6 +366,32 @@ __device__ __forceinline__ void fa_bases(const Chunk16& ch, uint32_t& valid, uin
         const uint32_t sel = __byte_perm(t, 0u, 0x4420);                // selector nibbles c0, c1, c2, c3
         const uint32_t expect = __byte_perm(0x47544341u, 0u, sel);      // 'A' 'C' 'T' 'G' by code
         valid |= swar_movemask(swar_zero_bytes((x & 0xDFDFDFDFu) ^ expect)) << (4 * w);
+    }
+}
+
+// The same for a chunk that fa_lines() found fast (its only bytes below 0x40 are newlines, nlb marks them): nearly
+// every such chunk of a genome is all ACGT, so the per-byte zero tests and the four mask gathers are only done when
+// some byte that is not a newline differs from the letter its code stands for.  (The validity bits at newline
+// positions are never looked at: fa_chunk_parts squeezes those positions out.)
+__device__ __forceinline__ void fa_bases_fast(const Chunk16& ch, const uint32_t (&nlb)[4], uint32_t& valid, uint32_t& codes) {
+    codes = 0;
+    uint32_t d[4], any = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const uint32_t x = ch.w[w];
+        const uint32_t c = (x >> 1) & 0x03030303u;                      // A0 C1 T2 G3
+        codes |= ((c * 0x01041040u) >> 24) << (8 * w);
+        const uint32_t t = c | (c >> 4);
+        const uint32_t sel = __byte_perm(t, 0u, 0x4420);
+        const uint32_t expect = __byte_perm(0x47544341u, 0u, sel);      // 'A' 'C' 'T' 'G' by code
+        d[w] = (x & 0xDFDFDFDFu) ^ expect;
+        any |= d[w] & ~nlb[w];
+    }
+    valid = 0xFFFFu;
+    if (any) {
+        valid = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) valid |= swar_movemask(swar_zero_bytes(d[w])) << (4 * w);
     }
 }
 
@@ -443,12 +470,12 @@ __device__ __forceinline__ FaParts fa_chunk_parts(const Chunk16& ch, const FaLin
     FaParts r;
     if (ln.fast) {
         uint32_t valid, codes;
-        fa_bases(ch, valid, codes);
+        fa_bases_fast(ch, ln.nlb, valid, codes);
         const uint32_t ls = ((ln.nl << 1) | (prev == '\n')) & 0xFFFFu;
         if (ls == 0) {
             const uint32_t hn = 16u - (ln.nl >> 15);           // a newline can only sit at position 15
             r.hc = hn == 16 ? codes : (codes & 0x3FFFFFFFu);
-            r.rc = 0; r.hv_rv = valid & 0xFFFFu; r.meta = hn;
+            r.rc = 0; r.hv_rv = hn == 16 ? valid : (valid & 0x7FFFu); r.meta = hn;
             return r;
         }
         const uint32_t q = __ffs(ls) - 1;

@@ -302,8 +302,14 @@ __global__ void __launch_bounds__(kParseThreads, 1024 / kParseThreads)
 k_pack(const PackParams p) {
     constexpr int kGroups = kTileBytes / 32 + 2;
     __shared__ Sum s_w[kParseThreads / 32];
-    __shared__ uint32_t s_codes[kGroups * 2 + 4];
-    __shared__ uint32_t s_valid[kGroups + 2];
+    // the tile's groups, assembled with shared-memory ORs: codes (two words per group) and validity bits in ONE 16-byte
+    // aligned block, so that it is cleared with two 128-bit stores per thread
+    constexpr int kCodeWords = kGroups * 2 + 4, kValidWords = kGroups + 2;
+    constexpr int kCvVec = (kCodeWords + kValidWords + 3) / 4;
+    static_assert(kCodeWords % 4 == 0, "the validity words start on a 16-byte boundary");
+    __shared__ __align__(16) uint32_t s_cv[kCvVec * 4];
+    uint32_t* const s_codes = s_cv;
+    uint32_t* const s_valid = s_cv + kCodeWords;
     __shared__ uint32_t s_nrec, s_st;
     __shared__ uint64_t s_pos;
     __shared__ uint4 s_tk[TMA ? 8 : 4];                                 // this CTA's TileTicket (TMA: and the next one)
@@ -478,20 +484,24 @@ k_pack(const PackParams p) {
     if (nrec) atomicAdd(&s_nrec, nrec);
     __syncthreads();
     if (e_total) {
+        // groups [lo, hi) belong to this tile alone: plain stores; the first group (when the tile starts inside it) and
+        // the last one (when it ends inside it) are shared with the neighbouring tiles and ORed into the zeroed stream
         const uint64_t g0 = tpos >> 5;
-        const uint32_t first_off = (uint32_t)(tpos & 31);
-        const uint32_t ngroups = (first_off + e_total + 31) >> 5;
-        for (uint32_t gi = threadIdx.x; gi < ngroups; gi += blockDim.x) {
-            const unsigned long long cw = (unsigned long long)s_codes[2 * gi] | ((unsigned long long)s_codes[2 * gi + 1] << 32);
-            const uint32_t vw = s_valid[gi];
-            const bool partial = (gi == 0 && first_off) || (gi == ngroups - 1 && ((first_off + e_total) & 31));
-            if (partial) {
-                if (cw) atomicOr(&codes[g0 + gi], cw);
-                if (vw) atomicOr(&valid[g0 + gi], vw);
-            } else {
-                codes[g0 + gi] = cw;
-                valid[g0 + gi] = vw;
-            }
+        const uint32_t first_off = (uint32_t)(tpos & 31), end_off = first_off + e_total;
+        const uint32_t lo = first_off ? 1u : 0u, hi = end_off >> 5;
+        const unsigned long long* __restrict__ sc64 = reinterpret_cast<const unsigned long long*>(s_codes);
+        for (uint32_t gi = lo + threadIdx.x; gi < hi; gi += kParseThreads) {
+            codes[g0 + gi] = sc64[gi];
+            valid[g0 + gi] = s_valid[gi];
+        }
+        uint32_t pg = 0xFFFFFFFFu;
+        if (threadIdx.x == 0 && first_off) pg = 0;
+        if (threadIdx.x == 32 && (end_off & 31u) && (hi > 0 || !first_off)) pg = hi;
+        if (pg != 0xFFFFFFFFu) {
+            const unsigned long long cw = sc64[pg];
+            const uint32_t vw = s_valid[pg];
+            if (cw) atomicOr(&codes[g0 + pg], cw);
+            if (vw) atomicOr(&valid[g0 + pg], vw);
         }
     }
     if (threadIdx.x == 0) {
@@ -514,8 +524,7 @@ k_pack(const PackParams p) {
                 s_tk[3] = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);                 // no tile left
             }
         }
-        for (int i = threadIdx.x; i < kGroups * 2 + 4; i += blockDim.x) s_codes[i] = 0;
-        for (int i = threadIdx.x; i < kGroups + 2; i += blockDim.x) s_valid[i] = 0;
+        for (int i = threadIdx.x; i < kCvVec; i += kParseThreads) reinterpret_cast<uint4*>(s_cv)[i] = make_uint4(0u, 0u, 0u, 0u);
         __syncthreads();
         const TileTicket& tk = *reinterpret_cast<const TileTicket*>(s_tk);
         if (tk.tile == 0xFFFFFFFFu) return;
@@ -567,8 +576,7 @@ k_pack(const PackParams p) {
             nxt[0] = src[0]; nxt[1] = src[1]; nxt[2] = src[2]; nxt[3] = src[3];
             tk2 = atomicAdd(p.ticket, 1u);
         }
-        for (int i = threadIdx.x; i < kGroups * 2 + 4; i += blockDim.x) s_codes[i] = 0;
-        for (int i = threadIdx.x; i < kGroups + 2; i += blockDim.x) s_valid[i] = 0;
+        for (int i = threadIdx.x; i < kCvVec; i += kParseThreads) reinterpret_cast<uint4*>(s_cv)[i] = make_uint4(0u, 0u, 0u, 0u);
         if (threadIdx.x == 0) s_nrec = 0;
         const TileCtx t = make_ctx(tk);
         mbar_wait(mbar, it & 1u);
@@ -772,10 +780,9 @@ struct AggParams2 {
     uint32_t b_begin, b_end;             // bucket_base / bucket_count are indexed by (virtual bucket) - (b_begin << sub_bits)
     // ordered emission (final build in hash order): the virtual buckets are dealt by ticket, every bucket publishes its
     // column count and learns its offset by look-back over its predecessors, so the columns land at their final place:
-    // out_keys is the result's k-mer array, word row 0 goes to out_row0 (row 0 of the result matrix, whose stride is
-    // only known at the end), rows >= 1 to out_words at stride cap
+    // out_keys is the result's k-mer array and out_words the result matrix, whose row pitch is cap (the number of
+    // columns is only known at the end; every reader of the result takes the pitch)
     uint32_t ordered;
-    unsigned long long* out_row0;        // nullptr: row 0 goes to out_words like the others
     unsigned long long* pub;             // [virtual buckets] bit 63: inclusive prefix, bit 62: own count; zeroed before the launch
     unsigned int* ticket;                // zeroed before the launch
     // MODE 3: partial columns [hash, words...] of n_src sources, each list ascending by hash; the entries of
@@ -992,7 +999,7 @@ __device__ __forceinline__ void agg_fix(const AggTable& t, uint32_t shift) {
 
 // Pass B2: emission at out[base + rank], rank = kept slots before + correction - own inversions.  s_wp = exclusive scan of s_wc.
 template <int MODE>
-__device__ __forceinline__ void agg_emit(const AggParams2& p, const AggTable& t, const uint32_t* s_wp,
+__device__ __forceinline__ void agg_emit(const AggParams2& p, const AggTable& t, const uint32_t* s_wp, const uint16_t* s_row,
                                          unsigned long long base, uint32_t b, uint32_t key_bits, uint32_t shift) {
     const unsigned long long key_mask = (1ULL << key_bits) - 1;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -1017,18 +1024,29 @@ __device__ __forceinline__ void agg_emit(const AggParams2& p, const AggTable& t,
             }
             p.out_keys[o] = (MODE == 5 || (MODE == 3 && p.partial_out)) ? h : kunhash(h);
             if (MODE == 3) {
-                for (uint32_t s = 0; s < p.n_src; ++s) {
-                    const uint32_t e = t.w32[s * t.total + i], nw = p.src_words[s], wo = p.src_woff[s];
-                    const unsigned long long* ent = p.parts + p.src_off[s] + (unsigned long long)(e ? e - 1u : 0u) * (1u + nw);
-                    for (uint32_t w = 0; w < nw; ++w) {
-                        unsigned long long* const row = (wo + w == 0 && p.out_row0) ? p.out_row0 : p.out_words + (unsigned long long)(wo + w) * p.cap;
-                        row[o] = e ? ent[1 + w] : 0ULL;
+                // The words come from the sources' entries (random 16 / 24 / 40-byte reads out of L2).  Eight word rows at a
+                // time -- their (source, word) pairs from s_row, the references, all the loads, then the stores: one
+                // dependent load at a time left the kernel waiting on the scoreboard for a third of its samples
+                // (profiles/r02_merge_*).
+                unsigned long long* const orow = p.out_words + o;
+                for (uint32_t r0 = 0; r0 < p.n_words; r0 += 8) {
+                    unsigned long long v[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        v[q] = 0ULL;
+                        if (r0 + q < p.n_words) {
+                            const uint32_t rw = s_row[r0 + q], sidx = rw >> 10, w = rw & 1023u;
+                            const uint32_t e = t.w32[sidx * t.total + i];
+                            if (e) v[q] = __ldg(p.parts + p.src_off[sidx] + (unsigned long long)(e - 1u) * (1u + p.src_words[sidx]) + 1u + w);
+                        }
                     }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (r0 + q < p.n_words) orow[(unsigned long long)(r0 + q) * p.cap] = v[q];
                 }
             } else {
                 for (uint32_t w = 0; w < p.n_words; ++w) {
-                    unsigned long long* const row = (w == 0 && p.out_row0) ? p.out_row0 : p.out_words + w * p.cap;
-                    row[o] = ((unsigned long long)t.w32[(2 * w + 1) * t.total + i] << 32) | t.w32[2 * w * t.total + i];
+                    p.out_words[w * p.cap + o] = ((unsigned long long)t.w32[(2 * w + 1) * t.total + i] << 32) | t.w32[2 * w * t.total + i];
                 }
             }
         }
@@ -1083,6 +1101,15 @@ k_aggregate_cols(const AggParams2 p) {
     const uint32_t key_bits = 64 - p.bucket_bits;
     const uint32_t n_chunks = (t.total + kAggThreads - 1) / kAggThreads;     // <= kAggMaxChunks (slots <= 16384)
     __shared__ uint32_t s_wc[kAggMaxChunks * (kAggThreads / 32)];
+    // MODE 3: word row r of the result = word (s_row[r] & 1023) of source (s_row[r] >> 10)
+    __shared__ uint16_t s_row[MODE == 3 ? 512 : 1];
+    if (MODE == 3) {
+        for (uint32_t r = threadIdx.x; r < p.n_words && r < 512u; r += kAggThreads) {
+            uint32_t sidx = 0;
+            while (sidx + 1 < p.n_src && r >= p.src_woff[sidx + 1]) ++sidx;
+            s_row[r] = (uint16_t)((sidx << 10) | (r - p.src_woff[sidx]));
+        }
+    }
 
     // A virtual bucket = bucket b restricted to the key sub-range `sub` of 2^sub_bits: the scatter can then use
     // 2^sub_bits fewer buckets (longer runs per tile) than the table size demands.  The CTAs of one bucket's
@@ -1195,7 +1222,7 @@ k_aggregate_cols(const AggParams2 p) {
             }
             agg_fix(t, 64 - key_bits + depth);
             __syncthreads();
-            agg_emit<MODE>(p, t, s_wc, s_base + emitted, b, key_bits, 64 - key_bits + depth);
+            agg_emit<MODE>(p, t, s_wc, s_row, s_base + emitted, b, key_bits, 64 - key_bits + depth);
             emitted += total_kept;
         }
         if (threadIdx.x == 0) {
@@ -1204,20 +1231,6 @@ k_aggregate_cols(const AggParams2 p) {
             atomicAdd(&p.scalars[S_N_DISTINCT], (unsigned long long)bucket_occ);
             if (splits) atomicAdd(&p.scalars[S_N_SPLITS], (unsigned long long)splits);
         }
-    }
-}
-
-// ordered emission: word rows >= 1 from stride cap (the aggregate's output) to the result's stride U, which only the
-// device knows when this is launched (no host round trip between the aggregate and the end of the build)
-__global__ void __launch_bounds__(256)
-k_move_rows(const unsigned long long* __restrict__ src, unsigned long long cap, unsigned long long* __restrict__ dst,
-            const unsigned long long* __restrict__ u_ptr, uint32_t W) {
-    const unsigned long long U = *u_ptr;
-    if (U > cap) return;                                   // the aggregate overflowed its guess: the host repeats it
-    const unsigned long long n = U * (W - 1);
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned long long w = 1 + i / U, j = i - (w - 1) * U;
-        dst[w * U + j] = __ldcs(src + w * cap + j);
     }
 }
 
@@ -1310,7 +1323,7 @@ __global__ void k_kmer_strings(const unsigned long long* __restrict__ kmers, uin
 
 // rows [j0, j0 + n_rows) of the TSV body; row width = k + 2G + 1
 __global__ void k_format_tsv(const unsigned long long* __restrict__ kmers, const unsigned long long* __restrict__ matrix,
-                             uint64_t U, uint32_t G, uint32_t k, uint64_t j0, uint64_t n_bytes, char* __restrict__ dst) {
+                             uint64_t pitch, uint32_t G, uint32_t k, uint64_t j0, uint64_t n_bytes, char* __restrict__ dst) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_bytes) return;
     const uint32_t roww = k + 2 * G + 1;
@@ -1321,7 +1334,7 @@ __global__ void k_format_tsv(const unsigned long long* __restrict__ kmers, const
     else if (((c - k) & 1u) == 0) out = '\t';
     else {
         const uint32_t g = (c - k) >> 1;
-        out = ((matrix[(uint64_t)(g >> 6) * U + j] >> (63 - (g & 63))) & 1ULL) ? '1' : '0';
+        out = ((matrix[(uint64_t)(g >> 6) * pitch + j] >> (63 - (g & 63))) & 1ULL) ? '1' : '0';
     }
     dst[i] = out;
 }

@@ -1,5 +1,5 @@
-// grmkm_result.cuh -- kernels over the finished matrix (kmers[U], matrix[W][U] row-major, genome g at bit
-// 63 - (g & 63) of word row g >> 6, kover/utils.py:144-154) and over Ray Surveyor TSV text.
+// grmkm_result.cuh -- kernels over the finished matrix (kmers[U], matrix[W][U] row-major with a row pitch >= U, genome
+// g at bit 63 - (g & 63) of word row g >> 6, kover/utils.py:144-154) and over Ray Surveyor TSV text.
 //
 //   k_checksum     order-independent digest of the columns (parity checks across GPU counts, bench.py parity_check)
 //   k_sum_rows     KmerRuleClassifications.sum_rows (bin/kover/core/kover/learning/common/rules.py:201-267 with
@@ -17,12 +17,12 @@ constexpr unsigned long long kChkA = 0x9E3779B97F4A7C15ULL, kChkW = 0xC2B2AE3D27
 
 __global__ void __launch_bounds__(256)
 k_checksum(const unsigned long long* __restrict__ kmers, const unsigned long long* __restrict__ matrix, unsigned long long U,
-           uint32_t W, unsigned long long* __restrict__ out /* [2], zeroed */) {
+           unsigned long long pitch, uint32_t W, unsigned long long* __restrict__ out /* [2], zeroed */) {
     unsigned long long s0 = 0, s1 = 0;
     for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < U;
          j += (unsigned long long)gridDim.x * blockDim.x) {
         unsigned long long d = fmix64(kmers[j] + kChkA);
-        for (uint32_t w = 0; w < W; ++w) d = fmix64(d ^ (matrix[(unsigned long long)w * U + j] + (w + 1) * kChkW));
+        for (uint32_t w = 0; w < W; ++w) d = fmix64(d ^ (matrix[(unsigned long long)w * pitch + j] + (w + 1) * kChkW));
         s0 += d;
         s1 += fmix64(d ^ kChkB);
     }
@@ -34,7 +34,7 @@ k_checksum(const unsigned long long* __restrict__ kmers, const unsigned long lon
 
 // out[j] = sum_w popcount(matrix[w][j] & mask[w])  -- the learner's hot loop on the resident matrix
 __global__ void __launch_bounds__(256)
-k_sum_rows(const unsigned long long* __restrict__ matrix, unsigned long long U, uint32_t W,
+k_sum_rows(const unsigned long long* __restrict__ matrix, unsigned long long U, unsigned long long pitch, uint32_t W,
            const unsigned long long* __restrict__ mask, uint32_t* __restrict__ out) {
     __shared__ unsigned long long s_mask[512];
     for (uint32_t w = threadIdx.x; w < W; w += blockDim.x) s_mask[w] = mask[w];
@@ -44,7 +44,7 @@ k_sum_rows(const unsigned long long* __restrict__ matrix, unsigned long long U, 
         uint32_t s = 0;
         for (uint32_t w = 0; w < W; ++w) {
             const unsigned long long m = s_mask[w];
-            if (m) s += (uint32_t)__popcll(__ldcs(matrix + (unsigned long long)w * U + j) & m);
+            if (m) s += (uint32_t)__popcll(__ldcs(matrix + (unsigned long long)w * pitch + j) & m);
         }
         out[j] = s;
     }
@@ -81,7 +81,7 @@ k_tsv_pack(const uint8_t* __restrict__ body, unsigned long long n_rows, uint32_t
 // The column-major words are first turned into per-genome bit rows (64 x 64 bit transposes), then every pair of
 // genomes is a popcount(AND) stream over U / 64 words.
 __global__ void __launch_bounds__(256)
-k_bit_rows(const unsigned long long* __restrict__ matrix, unsigned long long U, uint32_t W, unsigned long long UW /* ceil(U / 64) */,
+k_bit_rows(const unsigned long long* __restrict__ matrix, unsigned long long U, unsigned long long pitch, uint32_t W, unsigned long long UW /* ceil(U / 64) */,
            unsigned long long* __restrict__ rows /* [W * 64][UW] */) {
     // one warp per (word row w, block of 64 columns): lane l holds columns 2l and 2l + 1
     const uint32_t lane = threadIdx.x & 31u;
@@ -91,8 +91,8 @@ k_bit_rows(const unsigned long long* __restrict__ matrix, unsigned long long U, 
         const uint32_t w = (uint32_t)(t / UW);
         const unsigned long long cb = t % UW;
         const unsigned long long j = cb * 64 + 2 * lane;
-        const unsigned long long c0 = j < U ? matrix[(unsigned long long)w * U + j] : 0ULL;
-        const unsigned long long c1 = j + 1 < U ? matrix[(unsigned long long)w * U + j + 1] : 0ULL;
+        const unsigned long long c0 = j < U ? matrix[(unsigned long long)w * pitch + j] : 0ULL;
+        const unsigned long long c1 = j + 1 < U ? matrix[(unsigned long long)w * pitch + j + 1] : 0ULL;
         // genome r of this word row (bit 63 - r of a column word) -> one 64-bit row word: column cb * 64 + q at bit q
         for (uint32_t r = 0; r < 64; ++r) {
             const uint32_t b0 = (uint32_t)(c0 >> (63 - r)) & 1u, b1 = (uint32_t)(c1 >> (63 - r)) & 1u;

@@ -310,9 +310,10 @@ k_units_scatter(const UnitScatterParams p) {
                 if (idx < n_units) {
                     const uint32_t P = s_list[idx];              // tile-local entry where the first k-mer ends
                     const uint32_t gl = P >> 5, e = P & 31u;
-                    const unsigned long long brk = (unsigned long long)s_brk[gl] | ((unsigned long long)s_brk[gl + 1] << 32);
-                    const unsigned long long after = brk >> (e + 1);
-                    const uint32_t dist = after ? (uint32_t)__ffsll((long long)after) : 64u;
+                    // distance to the next break after entry P; only the next lmax <= 32 positions matter, i.e. the low word
+                    // of the 64 break bits shifted down by e + 1 (one funnel shift, one 32-bit find-first-set)
+                    const uint32_t after = __funnelshift_rc(s_brk[gl], s_brk[gl + 1], e + 1u);      // (clamped: a shift of 32 yields the high word)
+                    const uint32_t dist = after ? (uint32_t)__ffs((int)after) : 33u;
                     const uint32_t L = dist < lmax ? dist : lmax;
                     const uint32_t a = P + 32u - (k - 1u);       // first entry of the unit, counted from the group before the tile
                     const uint32_t nb = L + k - 1u;

@@ -6,7 +6,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GRMKM_LIB") or os.path.join(_HERE, "libgrmkm.so")   # GRMKM_LIB: another build of the same library (kernel experiments)
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 OK = 0
 E_INVALID, E_UNSUPPORTED_K, E_NOMEM, E_CUDA, E_IO, E_CAPACITY, E_NO_DEVICE, E_UNSUPPORTED = -1, -2, -3, -4, -5, -6, -7, -8
@@ -91,7 +91,7 @@ def load() -> C.CDLL:
         "grmkm_copy_matrix": (i32, [vp, vp, u64]),
         "grmkm_add_genomes": (i32, [vp, u32, vp, vp, vp, i32]),
         "grmkm_format_tsv": (i32, [vp, C.POINTER(C.c_char_p), vp, u64, C.POINTER(u64)]),
-        "grmkm_device_result": (i32, [vp, C.POINTER(vp), C.POINTER(vp)]),
+        "grmkm_device_result": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]),
         "grmkm_host_result": (i32, [vp, C.POINTER(vp), C.POINTER(vp)]),
         "grmkm_synth_fasta_device": (i32, [vp, vp, u64, vp, u64]),
         "grmkm_build_partial": (i32, [vp, u32, C.POINTER(u64)]),

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GRMKM_ABI_VERSION 8
+#define GRMKM_ABI_VERSION 9
 
 enum {
     GRMKM_OK = 0,
@@ -192,8 +192,10 @@ int grmkm_gram(grmkm_ctx* ctx, uint64_t* dst, uint64_t cap);
 int grmkm_tsv_pack(grmkm_ctx* ctx, const uint8_t* body, uint64_t n_rows, uint32_t row_width, uint32_t k,
                    uint32_t n_tsv_cols, uint32_t n_genomes, const uint32_t* sel, uint64_t* dst, uint64_t cap);
 
-/* Device pointers of the result (kmers[U], matrix[n_words][U]) for callers that stay on the GPU. */
-int grmkm_device_result(const grmkm_ctx* ctx, const uint64_t** d_kmers, const uint64_t** d_matrix);
+/* Device pointers of the result for callers that stay on the GPU: kmers[U] and the matrix, whose word row w starts at
+ * d_matrix + w * pitch_words (pitch_words >= U: the columns are written at their final place while their number is
+ * still unknown, so the rows are spaced by the build's capacity; the host copies above deliver rows U words apart). */
+int grmkm_device_result(const grmkm_ctx* ctx, const uint64_t** d_kmers, const uint64_t** d_matrix, uint64_t* pitch_words);
 
 /*
  * Bench/test utility: materialise the synthetic FASTA of BASELINE.md section 4 /
