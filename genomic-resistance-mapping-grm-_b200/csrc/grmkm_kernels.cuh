@@ -999,7 +999,7 @@ __device__ __forceinline__ void agg_fix(const AggTable& t, uint32_t shift) {
 
 // Pass B2: emission at out[base + rank], rank = kept slots before + correction - own inversions.  s_wp = exclusive scan of s_wc.
 template <int MODE>
-__device__ __forceinline__ void agg_emit(const AggParams2& p, const AggTable& t, const uint32_t* s_wp, const uint16_t* s_row,
+__device__ __forceinline__ void agg_emit(const AggParams2& p, const AggTable& t, const uint32_t* s_wp,
                                          unsigned long long base, uint32_t b, uint32_t key_bits, uint32_t shift) {
     const unsigned long long key_mask = (1ULL << key_bits) - 1;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -1024,25 +1024,43 @@ __device__ __forceinline__ void agg_emit(const AggParams2& p, const AggTable& t,
             }
             p.out_keys[o] = (MODE == 5 || (MODE == 3 && p.partial_out)) ? h : kunhash(h);
             if (MODE == 3) {
-                // The words come from the sources' entries (random 16 / 24 / 40-byte reads out of L2).  Eight word rows at a
-                // time -- their (source, word) pairs from s_row, the references, all the loads, then the stores: one
-                // dependent load at a time left the kernel waiting on the scoreboard for a third of its samples
-                // (profiles/r02_merge_*).
+                // The words come from the sources' entries (random 16 / 24 / 40-byte reads out of L2).  Four sources at a
+                // time: all their references first, then all the loads, then the stores -- one dependent load at a time left
+                // the kernel waiting on the scoreboard for a third of its samples (profiles/r02_merge_*: aggregate 1.05 ->
+                // 0.88 ms at 8 sources x 2 words; a variant that walked the word rows through a (source, word) table in
+                // shared memory, eight at a time, took 1.00 ms).
                 unsigned long long* const orow = p.out_words + o;
-                for (uint32_t r0 = 0; r0 < p.n_words; r0 += 8) {
-                    unsigned long long v[8];
+                for (uint32_t s0 = 0; s0 < p.n_src; s0 += 4) {
+                    uint32_t e[4];
+                    unsigned long long v0[4], v1[4];
+                    const unsigned long long* ent[4];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        v[q] = 0ULL;
-                        if (r0 + q < p.n_words) {
-                            const uint32_t rw = s_row[r0 + q], sidx = rw >> 10, w = rw & 1023u;
-                            const uint32_t e = t.w32[sidx * t.total + i];
-                            if (e) v[q] = __ldg(p.parts + p.src_off[sidx] + (unsigned long long)(e - 1u) * (1u + p.src_words[sidx]) + 1u + w);
+                    for (int q = 0; q < 4; ++q) e[q] = s0 + q < p.n_src ? t.w32[(s0 + q) * t.total + i] : 0u;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        v0[q] = v1[q] = 0ULL;
+                        ent[q] = nullptr;
+                        if (e[q]) {
+                            const uint32_t nw = p.src_words[s0 + q];
+                            ent[q] = p.parts + p.src_off[s0 + q] + (unsigned long long)(e[q] - 1u) * (1u + nw);
+                            if (nw >= 1) v0[q] = __ldg(ent[q] + 1);
+                            if (nw >= 2) v1[q] = __ldg(ent[q] + 2);
                         }
                     }
 #pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        if (r0 + q < p.n_words) orow[(unsigned long long)(r0 + q) * p.cap] = v[q];
+                    for (int q = 0; q < 4; ++q) {
+                        if (s0 + q >= p.n_src) break;
+                        const uint32_t nw = p.src_words[s0 + q], wo = p.src_woff[s0 + q];
+                        if (nw >= 1) orow[(unsigned long long)wo * p.cap] = v0[q];
+                        if (nw >= 2) orow[(unsigned long long)(wo + 1) * p.cap] = v1[q];
+                        for (uint32_t w0 = 2; w0 < nw; w0 += 4) {      // (sources of more than 128 genomes: four more words at a time)
+                            unsigned long long x[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) x[j] = (ent[q] && w0 + j < nw) ? __ldg(ent[q] + 1 + w0 + j) : 0ULL;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) if (w0 + j < nw) orow[(unsigned long long)(wo + w0 + j) * p.cap] = x[j];
+                        }
+                    }
                 }
             } else {
                 for (uint32_t w = 0; w < p.n_words; ++w) {
@@ -1101,15 +1119,6 @@ k_aggregate_cols(const AggParams2 p) {
     const uint32_t key_bits = 64 - p.bucket_bits;
     const uint32_t n_chunks = (t.total + kAggThreads - 1) / kAggThreads;     // <= kAggMaxChunks (slots <= 16384)
     __shared__ uint32_t s_wc[kAggMaxChunks * (kAggThreads / 32)];
-    // MODE 3: word row r of the result = word (s_row[r] & 1023) of source (s_row[r] >> 10)
-    __shared__ uint16_t s_row[MODE == 3 ? 512 : 1];
-    if (MODE == 3) {
-        for (uint32_t r = threadIdx.x; r < p.n_words && r < 512u; r += kAggThreads) {
-            uint32_t sidx = 0;
-            while (sidx + 1 < p.n_src && r >= p.src_woff[sidx + 1]) ++sidx;
-            s_row[r] = (uint16_t)((sidx << 10) | (r - p.src_woff[sidx]));
-        }
-    }
 
     // A virtual bucket = bucket b restricted to the key sub-range `sub` of 2^sub_bits: the scatter can then use
     // 2^sub_bits fewer buckets (longer runs per tile) than the table size demands.  The CTAs of one bucket's
@@ -1222,7 +1231,7 @@ k_aggregate_cols(const AggParams2 p) {
             }
             agg_fix(t, 64 - key_bits + depth);
             __syncthreads();
-            agg_emit<MODE>(p, t, s_wc, s_row, s_base + emitted, b, key_bits, 64 - key_bits + depth);
+            agg_emit<MODE>(p, t, s_wc, s_base + emitted, b, key_bits, 64 - key_bits + depth);
             emitted += total_kept;
         }
         if (threadIdx.x == 0) {

@@ -61,6 +61,8 @@ class CudaEngine:
 
     def __init__(self, builder):
         self.b = builder
+        self.launches = 0
+        self.local_times, self.local_stats, self.merge_times = {}, {}, {}
 
     def plan_bucket_bits(self) -> int:
         v = C.c_uint32()
@@ -91,21 +93,24 @@ class CudaEngine:
         return counts, send[:n]
 
     def build_local(self, world: int):
-        """Local stages only -> counts per owner [world]; the partial columns stay in the context (export_peers)."""
+        """Local stages only -> counts per owner [world]; the partial columns stay in the context (export_peers).
+        The stage times and statistics are read by collect_local(), once the export is under way (the GPU has nothing to
+        do between the local aggregate and the export kernel: no host work belongs there)."""
         counts = (C.c_uint64 * world)()
         self.b._check(self.b._lib.grmkm_build_partial(self.b._ctx, world, counts))
+        return [int(x) for x in counts]
+
+    def collect_local(self):
         st = self.b.stats
         self.launches = st["n_launches"]
         self.local_times = self.b.times
         self.local_stats = st
-        return [int(x) for x in counts]
 
     def export_peers(self, world: int, peer_ptrs: Sequence[int], word_offsets: Sequence[int]):
         """Owner d's slice is stored straight into peer d's receive buffer (asynchronous on the context's stream)."""
         ptrs = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in peer_ptrs])
         offs = (C.c_uint64 * world)(*[int(o) for o in word_offsets])
         self.b._check(self.b._lib.grmkm_export_partials_peers(self.b._ctx, world, ptrs, offs))
-        self.launches += 1
 
     def merge(self, recv, world: int, rank: int, src_counts: Sequence[int], src_words: Sequence[int], n_genomes: int):
         sc = (C.c_uint64 * world)(*src_counts)
@@ -295,6 +300,7 @@ class DistributedBuilder:
         offs = [sum(M[s][d] * width[s] for s in range(r)) for d in range(P)]
         self.engine.export_peers(P, list(self._peer_hdl.buffer_ptrs), offs)
         self._peer_hdl.barrier()                                         # every slice has landed (same stream as the kernel)
+        self.engine.collect_local()                                      # (while the export kernel runs)
         self.exchange_bytes = int(sum(counts) * width[r] * 8)
         ev[1].record()
         src_counts = [M[s][r] for s in range(P)]
