@@ -11,7 +11,8 @@ buckets -> shared-memory aggregation -> ordered columns (kmers[U] + matrix[W][U]
 run the front end in rounds of a few genomes with per-genome counters and end with one presence merge.
   value : whole-job Gbases/s with the text already resident in HBM (CUDA events, max over ranks)
   e2e   : same metric through the public API with HOST (pinned) buffers: H2D of the text and D2H of kmers + matrix
-          inside the timed region
+          inside the timed region, every step.  At N = 1 the steps run through builder.BuildPipeline (two contexts of the
+          GPU alternate: step i+1's text goes in while step i's result comes out); e2e.serial is one build at a time
   parity_check : after the timed loops, the order-independent checksum of every rank's column slice (GPU kernel), summed
           over the ranks, against the same checksum of the oracle's matrix of the same genomes (rank 0, CPU)
 
