@@ -835,7 +835,7 @@ int run_job(grmkm_ctx* c, const Geo& geo, const Job& job, JobOut& out) {
             xp.cap = wcap; xp.k = c->cfg.k; xp.bucket_bits = geo.bucket_bits; xp.wbits = wbits;
             xp.cursors = (unsigned long long*)c->hist.p; xp.records = nullptr;
             xp.overflow = (unsigned long long*)(d_scalars + S_WIDE_OVERFLOW);
-            const uint32_t xgrid = (uint32_t)std::min<uint64_t>((wcap + kStUnits - 1) / kStUnits, (uint64_t)c->sm_count);
+            const uint32_t xgrid = (uint32_t)std::min<uint64_t>((wcap + kStThreads - 1) / kStThreads, (uint64_t)c->sm_count);
             if (!wide_exact) {
                 // over-provisioned bucket regions, no count pass.  Presence: the distinct k-mers are estimated as 1.9 x the
                 // largest genome plus 5 % of all input (what every further genome adds to a species' pan-genome), 1.3

@@ -557,19 +557,18 @@ struct UnitExpandParams {
     unsigned long long* overflow;        // set when a region was too small (the host redoes the expansion with exact offsets)
 };
 
-// k-mers e = 0 .. 15 of one half of a unit's window: rr / yy are the three words of the forward / reverse-complement
-// window that this half's k-mers lie in (the second half is the same code one 32-bit word = 16 entries further on)
-__device__ __forceinline__ void expand_hash_group(const uint32_t (&rr)[3], const uint32_t (&yy)[3], uint32_t have,
+__device__ __forceinline__ void expand_hash_group(const uint32_t (&r)[4], const uint32_t (&y)[4], uint32_t have,
                                                   uint32_t kmask_lo, uint32_t kmask_hi, uint32_t key_bits, uint32_t* s_cnt,
                                                   unsigned long long (&hsh)[kStPerThread]) {
 #pragma unroll
     for (int e = 0; e < kStPerThread; ++e) {
         if ((have >> e) & 1u) {
-            const int fw_s = 2 * (15 - e), rc_s = 2 * e;
-            const uint32_t fw_lo = __funnelshift_r(rr[0], rr[1], fw_s) & kmask_lo;
-            const uint32_t fw_hi = __funnelshift_r(rr[1], rr[2], fw_s) & kmask_hi;
-            const uint32_t rc_lo = __funnelshift_r(yy[0], yy[1], rc_s) & kmask_lo;
-            const uint32_t rc_hi = __funnelshift_r(yy[1], yy[2], rc_s) & kmask_hi;
+            const int fs = 2 * (31 - e), fw_w = fs >> 5, fw_s = fs & 31;
+            const int rs = 2 * e, rc_w = rs >> 5, rc_s = rs & 31;
+            const uint32_t fw_lo = __funnelshift_r(r[fw_w], r[fw_w + 1], fw_s) & kmask_lo;
+            const uint32_t fw_hi = __funnelshift_r(r[fw_w + 1], r[fw_w + 2], fw_s) & kmask_hi;
+            const uint32_t rc_lo = __funnelshift_r(y[rc_w], y[rc_w + 1], rc_s) & kmask_lo;
+            const uint32_t rc_hi = __funnelshift_r(y[rc_w + 1], y[rc_w + 2], rc_s) & kmask_hi;
             const uint64_t fw = ((uint64_t)fw_hi << 32) | fw_lo, rc = ((uint64_t)rc_hi << 32) | rc_lo;
             const uint64_t h = khash(fw < rc ? fw : rc);
             atomicAdd(&s_cnt[(uint32_t)(h >> key_bits)], 1u);
@@ -585,8 +584,8 @@ k_units_expand(const UnitExpandParams p) {
     extern __shared__ unsigned long long s_dyn[];
     __shared__ uint32_t s_total;
     __shared__ uint32_t s_warp[33];
-    __shared__ unsigned long long s_word[WB][kStUnits];
-    __shared__ uint16_t s_blk[kStUnits];
+    __shared__ unsigned long long s_word[WB][kStThreads];
+    __shared__ uint16_t s_blk[kStThreads];
     const uint32_t B = 1u << p.bucket_bits;
     unsigned long long* s_delta = s_dyn;
     unsigned long long* s_rec = s_delta + B;
@@ -595,27 +594,24 @@ k_units_expand(const UnitExpandParams p) {
     uint16_t* s_src = reinterpret_cast<uint16_t*>(s_off + B);
     const unsigned long long n_all = *p.n_ptr;
     const unsigned long long n = n_all < p.cap ? n_all : p.cap;
-    const unsigned long long n_tiles = (n + kStUnits - 1) / kStUnits;
+    const unsigned long long n_tiles = (n + kStThreads - 1) / kStThreads;
     const uint32_t k = p.k;
     const uint32_t kmask_lo = k >= 16 ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
     const uint32_t kmask_hi = k <= 16 ? 0u : (k == 32 ? 0xFFFFFFFFu : ((1u << (2 * k - 32)) - 1u));
     const uint32_t key_bits = 64 - p.bucket_bits;
     const uint32_t tid = threadIdx.x;
-    // Two threads per unit (its k-mers 0..15 and 16..31): 32 warps per SM instead of 16 hide the latencies of a kernel that
-    // ran at 23 % issue with one 512-thread CTA per SM, and 16 hashes per thread fit the 64-register budget.
-    const uint32_t unit = tid >> 1, half = tid & 1u;
     for (uint32_t i = tid; i < B; i += kStThreads) s_cnt[i] = 0;
     __syncthreads();
     for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const unsigned long long i = tile * kStUnits + unit;
+        const unsigned long long i = tile * kStThreads + tid;
         unsigned long long hsh[kStPerThread];
         uint32_t have = 0;
         if (i < n) {
             const unsigned long long lo = p.wu[ES * i], hik = p.wu[ES * i + 1];
-            if (!COUNT && half == 0) {
+            if (!COUNT) {
 #pragma unroll
-                for (int w = 0; w < WB; ++w) s_word[w][unit] = p.wu[ES * i + 2 + w];
-                s_blk[unit] = (uint16_t)(hik >> 48);
+                for (int w = 0; w < WB; ++w) s_word[w][tid] = p.wu[ES * i + 2 + w];
+                s_blk[tid] = (uint16_t)(hik >> 48);
             }
             const uint32_t L = (uint32_t)(lo >> 58) + 1u;
             const unsigned long long Vlo = (lo & kUnitLoMask) | (hik << 58), Vhi = (hik & kUnitHiMask) >> 6;
@@ -628,10 +624,8 @@ k_units_expand(const UnitExpandParams p) {
             const uint32_t y[4] = {(uint32_t)Vlo ^ 0xAAAAAAAAu, (uint32_t)(Vlo >> 32) ^ 0xAAAAAAAAu,
                                    (uint32_t)Vhi ^ 0xAAAAAAAAu, (uint32_t)(Vhi >> 32) ^ 0xAAAAAAAAu};
             const uint32_t r[4] = {rev2_32(x[3]), rev2_32(x[2]), rev2_32(x[1]), rev2_32(x[0])};
-            have = ((L >= 32 ? 0xFFFFFFFFu : ((1u << L) - 1u)) >> (16u * half)) & 0xFFFFu;
-            const uint32_t rr[3] = {half ? r[0] : r[1], half ? r[1] : r[2], half ? r[2] : r[3]};
-            const uint32_t yy[3] = {half ? y[1] : y[0], half ? y[2] : y[1], half ? y[3] : y[2]};
-            expand_hash_group(rr, yy, have, kmask_lo, kmask_hi, key_bits, s_cnt, hsh);
+            have = L >= 32 ? 0xFFFFFFFFu : ((1u << L) - 1u);
+            expand_hash_group(r, y, have, kmask_lo, kmask_hi, key_bits, s_cnt, hsh);
         }
         __syncthreads();
         {
@@ -678,7 +672,7 @@ k_units_expand(const UnitExpandParams p) {
                 if ((have >> e) & 1u) {
                     const uint32_t dst = atomicAdd(&s_off[(uint32_t)(hsh[e] >> key_bits)], 1u);
                     s_rec[dst] = hsh[e];
-                    s_src[dst] = (uint16_t)unit;
+                    s_src[dst] = (uint16_t)tid;
                 }
             }
             __syncthreads();
