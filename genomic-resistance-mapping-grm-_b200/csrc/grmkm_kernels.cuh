@@ -205,6 +205,74 @@ __device__ __noinline__ void tile_lookback(uint64_t tile, uint64_t first, uint64
     }
 }
 
+// FASTA: the same walk with the summaries in their compact form (grmkm_device.cuh, fa_combine) widened to 64 bits --
+// bits 0-29 entries after the first line start, 30-59 sequence bytes before it, 60-61 type of the last line start.  A
+// fold of 32 summaries is then ~70 instructions instead of ~600 with the general four-state transducer, so a tile
+// whose predecessor is not resolved yet folds from an older resolved tile instead of waiting a round trip per hop.
+__device__ __forceinline__ unsigned long long fa64_from_pub(unsigned long long a0) {
+    const uint32_t e = (uint32_t)(a0 >> 48) & 0xFFu, c0 = (uint32_t)(a0 >> 24) & 0xFFFFFFu, c1 = (uint32_t)a0 & 0xFFFFFFu;
+    const unsigned long long t = e == 0xE4u ? 0ULL : (unsigned long long)((e & 3u) + 1u);
+    return (unsigned long long)c0 | ((unsigned long long)(c1 - c0) << 30) | (t << 60);
+}
+__device__ __forceinline__ unsigned long long fa64_combine(unsigned long long A, unsigned long long B) {      // A first, then B
+    constexpr unsigned long long M30 = (1ULL << 30) - 1;
+    const uint32_t ta = (uint32_t)(A >> 60), tb = (uint32_t)(B >> 60);
+    const unsigned long long hb = (B >> 30) & M30;
+    unsigned long long r = (A & ((1ULL << 60) - 1)) + (B & M30);
+    r += ta == 0 ? hb << 30 : 0ULL;
+    r += ta == 2 ? hb : 0ULL;
+    return r | ((unsigned long long)(tb ? tb : ta) << 60);
+}
+__device__ __noinline__ void tile_lookback_fa(uint64_t tile, uint64_t first, uint64_t pos_first, const unsigned long long* a0,
+                                              const unsigned long long* ps, uint32_t& st, uint64_t& pos) {
+    constexpr unsigned long long M30 = (1ULL << 30) - 1;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long ident = kPubValid | (0xE4ULL << 48);
+    unsigned long long acc = 0;                    // fold of the tiles between the resolved one and `tile` (identity: nothing seen)
+    long long hi = (long long)tile - 1;
+    auto finish = [&](unsigned long long r, unsigned long long a) {
+        const uint32_t st0 = (uint32_t)(r >> 61) & 3u, t = (uint32_t)(a >> 60);
+        st = t ? t - 1u : st0;
+        pos = (r & ((1ULL << 61) - 1)) + (a & M30) + (st0 == ST_SEQ ? ((a >> 30) & M30) : 0ULL);
+    };
+    while (true) {
+        unsigned long long w0[kLbWindows], wp[kLbWindows];
+#pragma unroll
+        for (int w = 0; w < kLbWindows; ++w) {
+            const long long j = hi - 32 * w - 31 + lane;
+            w0[w] = ident; wp[w] = kPubValid | pos_first;
+            if (j >= (long long)first) { w0[w] = ld_relaxed_u64(a0 + j); wp[w] = ld_relaxed_u64(ps + j); }
+        }
+        int folded = 0;
+#pragma unroll
+        for (int w = 0; w < kLbWindows; ++w) {
+            const bool rdy_l = (w0[w] & kPubValid) != 0;
+            const uint32_t rdy = __ballot_sync(0xffffffffu, rdy_l);
+            const uint32_t res = __ballot_sync(0xffffffffu, rdy_l && (wp[w] & kPubValid));
+            if (w == 0 && (res >> 31)) {                           // the usual case: the tile right before this one is resolved
+                finish(__shfl_sync(0xffffffffu, wp[0], 31), fa64_combine(fa64_from_pub(__shfl_sync(0xffffffffu, w0[0], 31)), acc));
+                return;
+            }
+            const int top = res ? 31 - __clz(res) : 0;             // nearest resolved tile of the window, if any
+            if ((rdy >> top) != (0xFFFFFFFFu >> top)) break;       // a tile this side of it has not published yet: poll again
+            // ordered fold of lanes top .. 31 (lane 31 = the nearest tile); lanes below top count as the identity
+            unsigned long long v = lane < top ? 0ULL : fa64_from_pub(w0[w]);
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long o = __shfl_down_sync(0xffffffffu, v, d);
+                if (lane + d < 32) v = fa64_combine(v, o);
+            }
+            acc = fa64_combine(__shfl_sync(0xffffffffu, v, 0), acc);
+            folded = w + 1;
+            if (res) {
+                finish(__shfl_sync(0xffffffffu, wp[w], top), acc);
+                return;
+            }
+        }
+        hi -= 32 * folded;
+    }
+}
+
 // Two-pass parse for very long files.  The look-back resolves a file's tiles one after the other in the worst case,
 // and with a handful of files of tens of thousands of tiles each (a 300 MB read set is 19 k tiles) almost every tile
 // waits for its predecessor: 8.5 ms for 620 MB.  Such inputs get a first pass that only publishes the tile summaries
@@ -339,7 +407,8 @@ k_pack(const PackParams p) {
     auto resolve = [&](uint32_t& st_in, uint64_t& tpos) {
         if (threadIdx.x < 32) {
             uint32_t st; uint64_t pos;
-            tile_lookback<KIND>(tile, t.fd.tile_begin, file_stream_start, p.pub_a0, p.pub_a1, p.pub_ps, st, pos);
+            if (KIND == 0) tile_lookback_fa(tile, t.fd.tile_begin, file_stream_start, p.pub_a0, p.pub_ps, st, pos);
+            else tile_lookback<KIND>(tile, t.fd.tile_begin, file_stream_start, p.pub_a0, p.pub_a1, p.pub_ps, st, pos);
             if (threadIdx.x == 0) {
                 st_relaxed_u64(p.pub_ps + tile, kPubValid | ((unsigned long long)st << 61) | pos);
                 s_st = st; s_pos = pos;
