@@ -132,12 +132,13 @@ __device__ __forceinline__ Sum sum_shfl_down(const Sum& a, int d) {
     return r;
 }
 // ordered fold of one Sum per lane (lane 0 first); the result is valid in every lane
+template <bool ROT>
 __device__ __forceinline__ Sum warp_fold_sum(Sum s) {
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const Sum o = sum_shfl_down(s, d);
-        if (lane + d < 32) s = sum_combine(s, o);              // lane i: fold of lanes [i, i + 2d)
+        if (lane + d < 32) s = sum_comb<ROT>(s, o);            // lane i: fold of lanes [i, i + 2d)
     }
     Sum w;
     w.e = __shfl_sync(0xffffffffu, s.e, 0); w.c0 = __shfl_sync(0xffffffffu, s.c0, 0); w.c1 = __shfl_sync(0xffffffffu, s.c1, 0);
@@ -181,7 +182,7 @@ __device__ __noinline__ void tile_lookback(uint64_t tile, uint64_t first, uint64
                 // the usual case: the tile right before this one is resolved (no fold; a fold costs ~600 instructions)
                 const unsigned long long q0 = __shfl_sync(0xffffffffu, w0[0], 31), q1 = __shfl_sync(0xffffffffu, w1[0], 31);
                 const unsigned long long r = __shfl_sync(0xffffffffu, wp[0], 31);
-                const Sum a = sum_combine(pub_sum(q0, q1), acc);
+                const Sum a = sum_comb<KIND == 1>(pub_sum(q0, q1), acc);
                 const uint32_t st0 = (uint32_t)(r >> 61) & 3u;
                 st = sum_end(a, st0);
                 pos = (r & ((1ULL << 61) - 1)) + sum_cnt(a, st0);
@@ -189,7 +190,7 @@ __device__ __noinline__ void tile_lookback(uint64_t tile, uint64_t first, uint64
             }
             const int top = res ? 31 - __clz(res) : 0;             // nearest resolved tile of the window, if any
             if ((rdy >> top) != (0xFFFFFFFFu >> top)) break;       // a tile this side of it has not published yet: poll again
-            acc = sum_combine(warp_fold_sum(lane < top ? sum_identity() : pub_sum(w0[w], w1[w])), acc);
+            acc = sum_comb<KIND == 1>(warp_fold_sum<KIND == 1>(lane < top ? sum_identity() : pub_sum(w0[w], w1[w])), acc);
             folded = w + 1;
             if (res) {
                 const unsigned long long r = __shfl_sync(0xffffffffu, wp[w], top);
@@ -298,7 +299,7 @@ k_scan_tile_chains(const FileDesc* __restrict__ files, uint32_t n_files, const u
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const Sum o = sum_shfl_up(inc, d);
-            if (lane >= d) inc = sum_combine(o, inc);
+            if (lane >= d) inc = sum_comb<KIND == 1>(o, inc);
         }
         Sum excl = sum_shfl_up(inc, 1);
         if (lane == 0) excl = sum_identity();
@@ -369,7 +370,7 @@ template <int KIND, bool SUMMARY_ONLY = false, bool TMA = false>
 __global__ void __launch_bounds__(kParseThreads, 1024 / kParseThreads)
 k_pack(const PackParams p) {
     constexpr int kGroups = kTileBytes / 32 + 2;
-    __shared__ Sum s_w[kParseThreads / 32];
+    __shared__ Sum s_w[2 * (kParseThreads / 32) + 1];
     // the tile's groups, assembled with shared-memory ORs: codes (two words per group) and validity bits in ONE 16-byte
     // aligned block, so that it is cleared with two 128-bit stores per thread
     constexpr int kCodeWords = kGroups * 2 + 4, kValidWords = kGroups + 2;
@@ -475,9 +476,9 @@ k_pack(const PackParams p) {
             } else {
                 sums[c] = chunk_summary<1>(x.ch[c], x.prev[c], pos0, t.fd.len, t.hdr0);
             }
-            mine = sum_combine(mine, sums[c]);
+            mine = sum_combine_rot(mine, sums[c]);
         }
-        block_scan_sum(mine, excl, total, s_w);
+        block_scan_sum<true>(mine, excl, total, s_w);
         publish(total);
         if (SUMMARY_ONLY) return;
         resolve(st_in, tpos);
