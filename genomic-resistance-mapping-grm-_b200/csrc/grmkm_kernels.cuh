@@ -1362,11 +1362,28 @@ k_gather_buckets_peers(const unsigned long long* __restrict__ tmp_keys, const un
         while (d + 1 < ps.n && b >= ps.first[d + 1]) ++d;
         const unsigned long long src = bucket_base[b], d0 = offsets[b] - offsets[ps.first[d]], n = offsets[b + 1] - offsets[b];
         unsigned long long* __restrict__ dst = ps.dst[d] + d0 * (1 + W);
-        const unsigned long long cells = n * (1 + W);
-        for (unsigned long long c = threadIdx.x; c < cells; c += blockDim.x) {
-            const unsigned long long i = c / (1 + W);
-            const uint32_t f = (uint32_t)(c - i * (1 + W));
-            dst[c] = f == 0 ? tmp_keys[src + i] : tmp_words[(unsigned long long)(f - 1) * tmp_cap + src + i];
+        // (a bucket's chunk is far below 2^32 cells: 32-bit index arithmetic, the 64-bit division per cell was most of the
+        // kernel's instructions)
+        const uint32_t width = 1u + W, cells = (uint32_t)n * width;
+        const unsigned long long* __restrict__ keys = tmp_keys + src;
+        const unsigned long long* __restrict__ words = tmp_words + src;
+        // four cells per thread and step, the loads ahead of the stores: with one 8-byte load in flight per thread the kernel
+        // ran at 1.9 TB/s of combined traffic (0.25 ms for 240 MB on two GPUs), bound by latency, not by HBM or NVLink
+        for (uint32_t c0 = threadIdx.x; c0 < cells; c0 += 4 * blockDim.x) {
+            unsigned long long v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t c = c0 + q * blockDim.x;
+                if (c < cells) {
+                    const uint32_t i = c / width, f = c - i * width;
+                    v[q] = f == 0 ? keys[i] : words[(unsigned long long)(f - 1) * tmp_cap + i];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t c = c0 + q * blockDim.x;
+                if (c < cells) dst[c] = v[q];
+            }
         }
     }
 }
@@ -1380,11 +1397,25 @@ k_gather_buckets_aos(const unsigned long long* __restrict__ tmp_keys, const unsi
     for (uint32_t b = blockIdx.x; b < B; b += gridDim.x) {
         const unsigned long long src = bucket_base[b], d0 = offsets[b], n = offsets[b + 1] - d0;
         // one u64 of the AoS output per thread and step: coalesced stores, the loads hit W + 1 runs
-        const unsigned long long cells = n * (1 + W);
-        for (unsigned long long c = threadIdx.x; c < cells; c += blockDim.x) {
-            const unsigned long long i = c / (1 + W);
-            const uint32_t f = (uint32_t)(c - i * (1 + W));
-            dst[d0 * (1 + W) + c] = f == 0 ? tmp_keys[src + i] : tmp_words[(unsigned long long)(f - 1) * tmp_cap + src + i];
+        const uint32_t width = 1u + W, cells = (uint32_t)n * width;      // (32-bit index arithmetic: see k_gather_buckets_peers)
+        const unsigned long long* __restrict__ keys = tmp_keys + src;
+        const unsigned long long* __restrict__ words = tmp_words + src;
+        unsigned long long* __restrict__ out = dst + d0 * width;
+        for (uint32_t c0 = threadIdx.x; c0 < cells; c0 += 4 * blockDim.x) {      // (four loads in flight per thread)
+            unsigned long long v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t c = c0 + q * blockDim.x;
+                if (c < cells) {
+                    const uint32_t i = c / width, f = c - i * width;
+                    v[q] = f == 0 ? keys[i] : words[(unsigned long long)(f - 1) * tmp_cap + i];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t c = c0 + q * blockDim.x;
+                if (c < cells) out[c] = v[q];
+            }
         }
     }
 }

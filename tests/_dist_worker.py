@@ -26,6 +26,13 @@ def main():
         db.add_genome_bytes(i, genomes[g])
     db.build()
     res = db.gather()
+    # the host-side counts exchange of the peer path (distributed.HostCounts), several rounds in both buffer halves
+    from grm_b200.distributed import HostCounts
+    if HostCounts.available(world):
+        hc = HostCounts(dist, world, rank)
+        for rnd in range(1, 6):
+            M = hc.exchange([1000 * rnd + 10 * rank + d for d in range(world)])
+            assert M == [[1000 * rnd + 10 * s + d for d in range(world)] for s in range(world)], M
     if rank == 0:
         np.savez(os.path.join(out_dir, "result.npz"), kmers=res[0], matrix=res[1])
     dist.barrier()
