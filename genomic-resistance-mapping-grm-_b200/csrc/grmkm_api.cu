@@ -721,7 +721,8 @@ int run_job(grmkm_ctx* c, const Geo& geo, const Job& job, JobOut& out) {
             const uint64_t n_utiles = (n_groups_max + kUsTileGroups - 1) / kUsTileGroups;
             ENSURE(c, c->stile_file, n_utiles * 4);
             if (!pipelined && c->ev_ok) cudaEventRecord(c->ev[T_COUNT], st);
-            const uint32_t bgrid = (uint32_t)((n_groups_max + 511) / 512);       // two groups per thread
+            // two groups per thread and step, grid-stride (the next pair's words are fetched ahead): 8 CTAs' worth per SM
+            const uint32_t bgrid = (uint32_t)std::min<uint64_t>((n_groups_max + 511) / 512, (uint64_t)c->sm_count * 8);
 #define GRMKM_BOUNDS(WW)                                                                                        \
     k_unit_bounds<WW><<<bgrid, 256, 0, st>>>((const unsigned long long*)c->codes.p, (const uint32_t*)c->valid.p, d_scalars, \
                                              ug.k, ug.m, (uint2*)c->masks.p)

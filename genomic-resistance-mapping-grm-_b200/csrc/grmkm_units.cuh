@@ -74,28 +74,17 @@ __device__ __forceinline__ uint32_t unit_hash32(uint32_t lo0, uint32_t lo1, uint
 //    with inner = min of the W - 1 m-mers both windows share, that is  min(h[e], h[e + W]) <= inner  -- one
 //    __vibmin_u16x2, whose predicate outputs are the answer for both groups.  It covers every change of the
 //    minimum, reads the same from either strand, and bounds a run by W <= lmax.
+// masks of the groups g and g + 1 from their code / validity words and those of group g - 1
 template <int W>
-__global__ void __launch_bounds__(256)
-k_unit_bounds(const unsigned long long* __restrict__ codes, const uint32_t* __restrict__ valid,
-              const uint64_t* __restrict__ scalars, uint32_t k, uint32_t m, uint2* __restrict__ masks) {
-    const uint64_t n_groups = (scalars[S_STREAM_LEN] + 31) >> 5;
-    const uint64_t g = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 2;          // groups g and g + 1
-    if (g >= n_groups) return;
-    const bool two = g + 1 < n_groups;
-    const unsigned long long c0 = codes[g], c1 = two ? codes[g + 1] : 0ULL;
-    const uint32_t v0 = valid[g], v1 = two ? valid[g + 1] : 0u;
-    unsigned long long cp = 0; uint32_t vp = 0;
-    if (g > 0) { cp = codes[g - 1]; vp = valid[g - 1]; }
+__device__ __forceinline__ void unit_bounds_pair(unsigned long long cp, unsigned long long c0, unsigned long long c1, uint32_t vp, uint32_t v0,
+                                                 uint32_t v1, uint32_t k, uint32_t m, uint2& ma, uint2& mb) {
     // valid k-mers: smear the invalid entries over the k - 1 entries that follow them
     unsigned long long sa = ~((unsigned long long)vp | ((unsigned long long)v0 << 32));
     unsigned long long sb = ~((unsigned long long)v0 | ((unsigned long long)v1 << 32));
     for (uint32_t c = 1; c < k;) { const uint32_t d = c < k - c ? c : k - c; sa |= sa << d; sb |= sb << d; c += d; }
     const uint32_t vka = ~(uint32_t)(sa >> 32), vkb = ~(uint32_t)(sb >> 32);
-    if ((vka | vkb) == 0) {
-        masks[g] = make_uint2(0u, 0u);
-        if (two) masks[g + 1] = make_uint2(0u, 0u);
-        return;
-    }
+    ma = mb = make_uint2(0u, 0u);
+    if ((vka | vkb) == 0) return;
     const uint32_t vka_before = (uint32_t)((sa >> 31) & 1ULL) ^ 1u;             // the k-mer ending at the last entry of group g - 1
     // 96-entry window [group g - 1 | g | g + 1]: entry q at bits 2q of x[]
     const uint32_t x[6] = {(uint32_t)cp, (uint32_t)(cp >> 32), (uint32_t)c0, (uint32_t)(c0 >> 32), (uint32_t)c1, (uint32_t)(c1 >> 32)};
@@ -147,8 +136,41 @@ k_unit_bounds(const unsigned long long* __restrict__ codes, const uint32_t* __re
         }
     }
     const uint32_t before_a = (vka << 1) | vka_before, before_b = (vkb << 1) | (vka >> 31);
-    masks[g] = make_uint2(vka & (~before_a | changed_a), vka);
-    if (two) masks[g + 1] = make_uint2(vkb & (~before_b | changed_b), vkb);
+    ma = make_uint2(vka & (~before_a | changed_a), vka);
+    mb = make_uint2(vkb & (~before_b | changed_b), vkb);
+}
+
+// Grid-stride over the group pairs with the NEXT pair's words fetched before the current pair is worked on: at 91
+// registers only 3 - 4 warps per scheduler are resident, and with one pair per thread a fifth of the kernel's stall
+// samples sat on the first loads (profiles/r02_v8 source page: line of `cp = codes[g - 1]`).
+template <int W>
+__global__ void __launch_bounds__(256)
+k_unit_bounds(const unsigned long long* __restrict__ codes, const uint32_t* __restrict__ valid,
+              const uint64_t* __restrict__ scalars, uint32_t k, uint32_t m, uint2* __restrict__ masks) {
+    const uint64_t n_groups = (scalars[S_STREAM_LEN] + 31) >> 5;
+    const uint64_t stride = (uint64_t)gridDim.x * 512;
+    uint64_t g = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 2;                // groups g and g + 1
+    unsigned long long c0 = 0, c1 = 0, cp = 0;
+    uint32_t v0 = 0, v1 = 0, vp = 0;
+    auto fetch = [&](uint64_t q, unsigned long long& a0, unsigned long long& a1, unsigned long long& ap, uint32_t& b0, uint32_t& b1, uint32_t& bp) {
+        a0 = a1 = ap = 0ULL; b0 = b1 = bp = 0u;
+        if (q < n_groups) {
+            a0 = codes[q]; b0 = valid[q];
+            if (q + 1 < n_groups) { a1 = codes[q + 1]; b1 = valid[q + 1]; }
+            if (q > 0) { ap = codes[q - 1]; bp = valid[q - 1]; }
+        }
+    };
+    fetch(g, c0, c1, cp, v0, v1, vp);
+    while (g < n_groups) {
+        unsigned long long n0, n1, np;
+        uint32_t w0, w1, wp;
+        fetch(g + stride, n0, n1, np, w0, w1, wp);
+        uint2 ma, mb;
+        unit_bounds_pair<W>(cp, c0, c1, vp, v0, v1, k, m, ma, mb);
+        masks[g] = ma;
+        if (g + 1 < n_groups) masks[g + 1] = mb;
+        g += stride; c0 = n0; c1 = n1; cp = np; v0 = w0; v1 = w1; vp = wp;
+    }
 }
 
 // ---- k_units_scatter: units -> content-hash buckets ------------------------------------------
