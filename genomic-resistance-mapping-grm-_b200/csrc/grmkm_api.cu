@@ -6,6 +6,7 @@
 #include "grmkm_result.cuh"
 #include "grmkm_synth.cuh"
 
+#include <nvtx3/nvToolsExt.h>      // header-only; the ranges cost nothing until a tool (nsys, ncu --nvtx) attaches
 #include <zlib.h>
 
 #include <algorithm>
@@ -22,6 +23,14 @@ using namespace grmkm;
 namespace {
 
 thread_local std::string g_create_error;
+
+// NVTX range on the calling host thread: the stages of a build as a profiler sees them enqueued
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 struct DevBuf {
     void* p = nullptr;
@@ -672,6 +681,7 @@ int run_job(grmkm_ctx* c, const Geo& geo, const Job& job, JobOut& out) {
         if (pipelined && c->ev_ok)
             for (int e : {T_H2D, T_PARSE, T_PACK, T_COUNT, T_BOUNDS}) cudaEventRecord(c->ev[e], st);   // stages interleave: only "scatter" is timed
         out.h2d = 0;
+        NvtxRange nv_front("grmkm front: stage / pack / unit bounds / unit scatter");
         std::unique_lock<std::mutex> gate;
         cudaEvent_t* gate_ev = nullptr;
         if (any_host && c->device >= 0 && c->device < 64 && !getenv("GRMKM_NO_H2D_GATE")) {
@@ -791,6 +801,7 @@ int run_job(grmkm_ctx* c, const Geo& geo, const Job& job, JobOut& out) {
             c->pre_groups = c->pass_groups; c->pre_pub_bytes = c->pass_pub_bytes;
         }
 
+        NvtxRange nv_back("grmkm back: dedupe / expand / aggregate");
         // Dedupe -> expand -> aggregate run back to back without a host round trip.  The dedupe's entry list and the
         // expansion's bucket regions are sized from estimates; the one synchronisation after the aggregate reads what
         // was really needed, and a guess that was too small repeats the round (entry list: larger; regions: exact
@@ -1265,6 +1276,7 @@ static int build_impl(grmkm_ctx* c, uint32_t mode /*0 final, 1 partial*/, uint32
 // every failure of a build leaves the context quiet: nothing in flight reads borrowed host buffers any more, and no
 // side-stream clear is counted on
 static int build_guarded(grmkm_ctx* c, uint32_t mode, uint32_t n_ranges) {
+    NvtxRange nv(mode == 0 ? "grmkm_build" : "grmkm_build_partial");
     const int r = build_impl(c, mode, n_ranges);
     if (r != GRMKM_OK) {
         const std::string msg = c->err;
@@ -1565,6 +1577,7 @@ int grmkm_host_result(grmkm_ctx* c, const uint64_t** kmers, const uint64_t** mat
         c->host_res_cap = want;
     }
     uint8_t* h = (uint8_t*)c->host_res;
+    NvtxRange nv("grmkm_host_result: device -> host");
     // In pieces of 4 MiB: a single large device->host copy starves the host->device copies of another context that is
     // staging its text at the same time (BuildPipeline); in pieces both directions keep moving
     // (profiles/r02_duplex_pattern.txt).  Rows are c->pitch words apart on the device, U words apart on the host.
@@ -1681,6 +1694,7 @@ int grmkm_export_partials_peers(grmkm_ctx* c, uint32_t n_ranks, void* const* pee
 static int merge_sources(grmkm_ctx* c, const void* dev_parts, uint32_t n_ranks, const uint64_t* src_counts, const uint32_t* src_words,
                          uint32_t total_genomes, uint32_t ob, uint64_t own_lo, uint64_t own_hi, uint32_t owners, bool partial_out,
                          bool inside_build) {
+    NvtxRange nv("grmkm merge of sorted partial-column lists");
     cudaStream_t st = c->stream;
     Launches L;
     AggParams2 ap{};
