@@ -129,6 +129,7 @@ struct grmkm_ctx {
     uint32_t part_buckets = 0;
     uint32_t part_words = 0;
     uint32_t cur_bucket_bits = 0;
+    int32_t xrank = -1;                  // this context's rank in the exchange (grmkm_set_exchange_rank); -1: the device index
 };
 
 namespace {
@@ -1625,6 +1626,13 @@ int grmkm_set_bucket_bits(grmkm_ctx* c, uint32_t bits) {
     return GRMKM_OK;
 }
 
+int grmkm_set_exchange_rank(grmkm_ctx* c, uint32_t rank) {
+    if (check_ctx(c)) return GRMKM_E_INVALID;
+    if (rank >= 16) return fail(c, GRMKM_E_INVALID, "rank out of range (at most 16 ranks)");
+    c->xrank = (int32_t)rank;
+    return GRMKM_OK;
+}
+
 int grmkm_plan_bucket_bits(grmkm_ctx* c, uint32_t* bits) {
     if (check_ctx(c) || !bits) return GRMKM_E_INVALID;
     const InputTable tab = tabulate_inputs(c);
@@ -1673,6 +1681,7 @@ int grmkm_export_partials_peers(grmkm_ctx* c, uint32_t n_ranks, void* const* pee
     const uint32_t sub = ceil_log2(std::max(1u, c->part_buckets >> c->cur_bucket_bits));      // virtual buckets per bucket
     const uint64_t B = 1ULL << c->cur_bucket_bits;
     for (uint32_t d = 0; d <= n_ranks; ++d) ps.first[d] = (uint32_t)((B * d / n_ranks) << sub);
+    ps.rot = ps.first[((uint32_t)(c->xrank >= 0 ? c->xrank : c->device) + 1u) % n_ranks];
     for (uint32_t d = 0; d < n_ranks; ++d) {
         if (c->part_counts[d] && !peer_dst[d]) return fail(c, GRMKM_E_INVALID, "null peer buffer");
         ps.dst[d] = (unsigned long long*)peer_dst[d] + peer_word_off[d];

@@ -1352,12 +1352,19 @@ struct PeerSlices {
     unsigned long long* dst[16];          // peer d's receive buffer + this rank's word offset in it
     uint32_t first[17];                   // first (virtual) bucket of owner d; first[n] = B
     uint32_t n;
+    uint32_t rot;                         // the walk over the buckets starts here (the first bucket of the NEXT rank's range)
 };
 __global__ void __launch_bounds__(256)
 k_gather_buckets_peers(const unsigned long long* __restrict__ tmp_keys, const unsigned long long* __restrict__ tmp_words,
                        unsigned long long tmp_cap, const unsigned long long* __restrict__ bucket_base,
                        const unsigned long long* __restrict__ offsets, uint32_t B, uint32_t W, const PeerSlices ps) {
-    for (uint32_t b = blockIdx.x; b < B; b += gridDim.x) {
+    // Every rank starts with the buckets of the rank after it and ends with its own: at any moment the P exporters store
+    // into P different receivers.  Walked from bucket 0 on every rank, all of them filled owners 0 .. 4 first and 5 .. 7
+    // afterwards -- an all-to-all in which five, then three receivers take everybody's stores (N = 8: 0.57 ms for 214 MB
+    // per rank over NVLink).
+    for (uint32_t i = blockIdx.x; i < B; i += gridDim.x) {
+        uint32_t b = i + ps.rot;
+        if (b >= B) b -= B;
         uint32_t d = 0;
         while (d + 1 < ps.n && b >= ps.first[d + 1]) ++d;
         const unsigned long long src = bucket_base[b], d0 = offsets[b] - offsets[ps.first[d]], n = offsets[b + 1] - offsets[b];

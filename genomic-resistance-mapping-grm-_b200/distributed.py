@@ -204,6 +204,8 @@ class DistributedBuilder:
                 self._stream = stream = torch.cuda.current_stream().cuda_stream      # kernels and collectives on ONE stream
             self.builder = KmerMatrixBuilder(k=k, min_abundance=min_abundance, keep_singletons=keep_singletons,
                                              input_kind=input_kind, device=device, stream=stream)
+            if self.world > 1:
+                self.builder._check(self.builder._lib.grmkm_set_exchange_rank(self.builder._ctx, self.rank))
             engine = CudaEngine(self.builder)
         self.engine = engine
         self._n_kmers = 0

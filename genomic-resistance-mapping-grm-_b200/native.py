@@ -6,7 +6,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GRMKM_LIB") or os.path.join(_HERE, "libgrmkm.so")   # GRMKM_LIB: another build of the same library (kernel experiments)
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 OK = 0
 E_INVALID, E_UNSUPPORTED_K, E_NOMEM, E_CUDA, E_IO, E_CAPACITY, E_NO_DEVICE, E_UNSUPPORTED = -1, -2, -3, -4, -5, -6, -7, -8
@@ -20,7 +20,7 @@ SYMBOLS = [
     "grmkm_build", "grmkm_dims", "grmkm_get_stats", "grmkm_stage_times", "grmkm_copy_kmers_packed",
     "grmkm_copy_kmer_strings", "grmkm_copy_matrix", "grmkm_format_tsv", "grmkm_device_result", "grmkm_host_result",
     "grmkm_synth_fasta_device", "grmkm_build_partial", "grmkm_export_partials", "grmkm_export_partials_peers", "grmkm_merge_partials",
-    "grmkm_plan_bucket_bits", "grmkm_set_bucket_bits",
+    "grmkm_plan_bucket_bits", "grmkm_set_bucket_bits", "grmkm_set_exchange_rank",
     "grmkm_result_checksum", "grmkm_sum_rows", "grmkm_gram", "grmkm_tsv_pack",
 ]
 
@@ -100,6 +100,7 @@ def load() -> C.CDLL:
         "grmkm_merge_partials": (i32, [vp, vp, u32, u32, C.POINTER(u64), C.POINTER(u32), u32]),
         "grmkm_plan_bucket_bits": (i32, [vp, C.POINTER(u32)]),
         "grmkm_set_bucket_bits": (i32, [vp, u32]),
+        "grmkm_set_exchange_rank": (i32, [vp, u32]),
         "grmkm_result_checksum": (i32, [vp, C.POINTER(u64)]),
         "grmkm_sum_rows": (i32, [vp, vp, u32, vp, u64]),
         "grmkm_gram": (i32, [vp, vp, u64]),

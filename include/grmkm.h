@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GRMKM_ABI_VERSION 9
+#define GRMKM_ABI_VERSION 10
 
 enum {
     GRMKM_OK = 0,
@@ -235,6 +235,10 @@ int grmkm_export_partials(grmkm_ctx* ctx, void* dev_dst, uint64_t dst_bytes);
  * peer_word_off[d] -- over NVLink, no send buffer and no NCCL send/recv (Ray's message routing, src/app.py:1310).
  * Asynchronous on the context's stream; the ranks synchronise (barrier) before anybody merges. */
 int grmkm_export_partials_peers(grmkm_ctx* ctx, uint32_t n_ranks, void* const* peer_dst, const uint64_t* peer_word_off);
+/* This context's rank among the exporters (default: its device index).  Only staggers the order in which the export walks
+ * the owners -- rank r starts with owner r + 1 -- so that the P exporters store into P different receivers at any moment
+ * (the hash-routed message rounds of `mpiexec -n 4 Ray`, src/app.py:1310); the result does not depend on it. */
+int grmkm_set_exchange_rank(grmkm_ctx* ctx, uint32_t rank);
 int grmkm_merge_partials(grmkm_ctx* ctx, const void* dev_parts, uint32_t n_ranks, uint32_t rank,
                          const uint64_t* src_counts, const uint32_t* src_words, uint32_t total_genomes);
 
