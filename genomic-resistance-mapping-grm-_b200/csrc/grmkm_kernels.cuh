@@ -155,7 +155,10 @@ __device__ __forceinline__ Sum warp_fold_sum(Sum s) {
 // kLbWindows x 32 tiles are polled per round trip (lane 31 of window 0 = the nearest tile): the resolved front
 // trails the newest published tile by (tiles per microsecond) x (poll latency), and a poll that does not reach it
 // costs a whole extra round trip.
-constexpr int kLbWindows = 2;
+#ifndef GRMKM_LB_WINDOWS
+#define GRMKM_LB_WINDOWS 1          // (2 and 4 windows per poll measured slower once a fold had become cheap: profiles/r02_pack_occupancy_ab.txt)
+#endif
+constexpr int kLbWindows = GRMKM_LB_WINDOWS;
 template <int KIND>
 __device__ __noinline__ void tile_lookback(uint64_t tile, uint64_t first, uint64_t pos_first, const unsigned long long* a0,
                                            const unsigned long long* a1, const unsigned long long* ps, uint32_t& st, uint64_t& pos) {
@@ -367,7 +370,10 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // SUMMARY_ONLY: publish the tile's summary and stop (first pass of the two-pass parse of very long files, see
 // k_scan_tile_chains).
 template <int KIND, bool SUMMARY_ONLY = false, bool TMA = false>
-__global__ void __launch_bounds__(kParseThreads, 1024 / kParseThreads)
+#ifndef GRMKM_PACK_CTAS
+#define GRMKM_PACK_CTAS (1024 / kParseThreads)      // resident CTAs per SM the register budget is cut for (A/B: profiles/r02_pack_occupancy_ab.txt)
+#endif
+__global__ void __launch_bounds__(kParseThreads, GRMKM_PACK_CTAS)
 k_pack(const PackParams p) {
     constexpr int kGroups = kTileBytes / 32 + 2;
     __shared__ Sum s_w[2 * (kParseThreads / 32) + 1];
