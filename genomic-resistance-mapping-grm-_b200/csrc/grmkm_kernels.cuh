@@ -158,7 +158,8 @@ __device__ __forceinline__ Sum warp_fold_sum(Sum s) {
 #ifndef GRMKM_LB_WINDOWS
 #define GRMKM_LB_WINDOWS 1          // (2 and 4 windows per poll measured slower once a fold had become cheap: profiles/r02_pack_occupancy_ab.txt)
 #endif
-constexpr int kLbWindows = GRMKM_LB_WINDOWS;
+constexpr int kLbWindows = GRMKM_LB_WINDOWS;      // FASTA (tile_lookback_fa): many short per-file chains
+constexpr int kLbWindowsFq = 2;                   // FASTQ (tile_lookback): one long chain per read set, the resolved front trails further
 template <int KIND>
 __device__ __noinline__ void tile_lookback(uint64_t tile, uint64_t first, uint64_t pos_first, const unsigned long long* a0,
                                            const unsigned long long* a1, const unsigned long long* ps, uint32_t& st, uint64_t& pos) {
@@ -167,9 +168,9 @@ __device__ __noinline__ void tile_lookback(uint64_t tile, uint64_t first, uint64
     Sum acc = sum_identity();                      // fold of the tiles between the resolved one and `tile`
     long long hi = (long long)tile - 1;            // nearest tile not folded yet
     while (true) {
-        unsigned long long w0[kLbWindows], w1[kLbWindows], wp[kLbWindows];
+        unsigned long long w0[kLbWindowsFq], w1[kLbWindowsFq], wp[kLbWindowsFq];
 #pragma unroll
-        for (int w = 0; w < kLbWindows; ++w) {
+        for (int w = 0; w < kLbWindowsFq; ++w) {
             const long long j = hi - 32 * w - 31 + lane;
             w0[w] = ident; w1[w] = kPubValid; wp[w] = kPubValid | pos_first;
             if (j >= (long long)first) { w0[w] = ld_relaxed_u64(a0 + j); wp[w] = ld_relaxed_u64(ps + j); if (KIND == 1) w1[w] = ld_relaxed_u64(a1 + j); }
@@ -177,7 +178,7 @@ __device__ __noinline__ void tile_lookback(uint64_t tile, uint64_t first, uint64
         bool done = false;
         int folded = 0;                            // windows of this poll that are folded into acc
 #pragma unroll
-        for (int w = 0; w < kLbWindows; ++w) {
+        for (int w = 0; w < kLbWindowsFq; ++w) {
             const bool rdy_l = (w0[w] & w1[w] & kPubValid) != 0;
             const uint32_t rdy = __ballot_sync(0xffffffffu, rdy_l);
             const uint32_t res = __ballot_sync(0xffffffffu, rdy_l && (wp[w] & kPubValid));

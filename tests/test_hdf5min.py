@@ -115,3 +115,28 @@ def test_root_group_capacity_is_enforced(tmp_path):
         h5.create_dataset(f"d{i}", np.arange(2, dtype=np.uint8))
     with pytest.raises(ValueError):
         h5.close()
+
+
+def test_libhdf5_reads_what_hdf5min_writes(tmp_path):
+    """When h5py (i.e. libhdf5, the library Kover's ds.py reads datasets with) is importable, it must read a
+    .kover-shaped file written by hdf5min: attributes, fixed-length strings, a gzip-chunked matrix with an edge chunk.
+    There is no h5py in the build image (the test is skipped there); it runs wherever the package is installed."""
+    h5py = pytest.importorskip("h5py")
+    rng = np.random.default_rng(5)
+    mat = rng.integers(0, 1 << 63, size=(3, 250_001), dtype=np.uint64)
+    seqs = np.array([b"ACGT" * 7 + b"ACG"] * 1000, dtype="S31")
+    p = tmp_path / "d.kover"
+    with hdf5min.H5Writer(str(p)) as h5:
+        h5.attrs["created"] = "now"
+        h5.attrs["compression"] = "gzip (level 4)"
+        h5.create_dataset("genome_identifiers", np.array([b"562.1", b"562.22"], dtype="S6"))
+        h5.create_dataset("kmer_sequences", seqs, chunks=(500,), gzip=4)
+        h5.create_dataset("kmer_matrix", mat, chunks=(1, 100_000), gzip=4)
+        h5.create_dataset("kmer_by_matrix_column", np.arange(250_001, dtype=np.uint32), chunks=(100_000,), gzip=4)
+    with h5py.File(str(p), "r") as f:
+        assert f.attrs["created"] in ("now", b"now")
+        assert [x for x in f["genome_identifiers"][...]] == [b"562.1", b"562.22"]
+        assert np.array_equal(f["kmer_sequences"][...], seqs)
+        assert f["kmer_matrix"].chunks == (1, 100_000) and f["kmer_matrix"].compression == "gzip"
+        assert np.array_equal(f["kmer_matrix"][...], mat)
+        assert np.array_equal(f["kmer_by_matrix_column"][-3:], np.arange(249_998, 250_001))
