@@ -74,17 +74,29 @@ class HostCounts:
         words = world * 2 * (1 + world)
         name = [None]
         if rank == 0:
-            fd, path = tempfile.mkstemp(prefix="grm_counts_", dir="/dev/shm")
-            os.ftruncate(fd, words * 8)
-            os.close(fd)
-            name[0] = path
+            try:
+                fd, path = tempfile.mkstemp(prefix="grm_counts_", dir="/dev/shm")
+                os.ftruncate(fd, words * 8)
+                os.close(fd)
+                name[0] = path
+            except OSError:
+                name[0] = None                                 # no usable /dev/shm: every rank falls back together
         dist.broadcast_object_list(name, src=0)
-        with open(name[0], "r+b") as f:
-            self._mm = mmap.mmap(f.fileno(), words * 8)
-        self.tab = np.frombuffer(self._mm, dtype=np.int64).reshape(world, 2, 1 + world)
-        dist.barrier()
+        if name[0] is None:
+            raise OSError("no shared-memory file for the counts table")
+        ok = 1
+        try:
+            with open(name[0], "r+b") as f:
+                self._mm = mmap.mmap(f.fileno(), words * 8)
+            self.tab = np.frombuffer(self._mm, dtype=np.int64).reshape(world, 2, 1 + world)
+        except OSError:
+            ok = 0                                             # (a rank that does not see rank 0's /dev/shm: another node)
+        flags = [None] * world
+        dist.all_gather_object(flags, ok)
         if rank == 0:
             os.unlink(name[0])                                 # the mapping keeps the memory alive
+        if not all(flags):
+            raise OSError("a rank cannot map the counts table")
 
     @staticmethod
     def available(world: int) -> bool:
@@ -346,7 +358,12 @@ class DistributedBuilder:
         counts = self.engine.build_local(P)
         ev[0].record()
         if self._host_counts is None:
-            self._host_counts = HostCounts(dist, P, r) if HostCounts.available(P) else False
+            self._host_counts = False
+            if HostCounts.available(P):                                  # (the same answer on every rank: environment only)
+                try:
+                    self._host_counts = HostCounts(dist, P, r)           # collective; fails on every rank or on none
+                except OSError:
+                    self._host_counts = False
         if self._host_counts:
             M = self._host_counts.exchange(counts)                       # M[s][d]: columns source s holds for owner d
         else:
