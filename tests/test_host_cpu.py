@@ -222,3 +222,59 @@ def test_cli_from_tsv_and_errors(tmp_path, capsys):
     # missing input -> non-zero exit, message on stderr (reference prints and exits, kover:133-136)
     assert cli.main(["dataset", "create", "from-tsv", "--genomic-data", str(tmp_path / "nope"), "--output", str(out)]) == 1
     assert "Error" in capsys.readouterr().err
+
+
+def test_build_pipeline_slots_and_order(monkeypatch):
+    """BuildPipeline's host logic without a GPU: submissions alternate over the slots, every slot works through its
+    own submissions in order (one worker each), results come back through the futures, close() closes every slot."""
+    import threading
+    import time
+    from grm_b200 import builder as B
+
+    class FakeBuilder:
+        made = []
+
+        def __init__(self, **kw):
+            self.kw, self.log, self.closed = kw, [], False
+            self._n = 0
+            FakeBuilder.made.append(self)
+
+        def reset(self):
+            self.log.append("reset")
+
+        def set_genome_count(self, n):
+            self.log.append(("count", n))
+
+        def add_genomes(self, rows, data, lens, on_device):
+            self.log.append(("add", list(rows), on_device))
+
+        def build(self):
+            time.sleep(0.01)
+            self._n += 1
+
+        def result_host(self):
+            return ("km", self._n, threading.get_ident()), ("mat", self._n)
+
+        @property
+        def stats(self):
+            return {"n": self._n}
+
+        def close(self):
+            self.closed = True
+
+    monkeypatch.setattr(B, "KmerMatrixBuilder", FakeBuilder)
+    with B.BuildPipeline(depth=2, streams=[11, 22], k=31, keep_singletons=True) as pipe:
+        slots = list(pipe.slots)
+        assert [s.kw["stream"] for s in slots] == [11, 22] and all(s.kw["k"] == 31 for s in slots)
+        futs = [pipe.submit([i], [b"x"], n_genomes=i) for i in range(5)]
+        res = [f.result() for f in futs]
+    # submissions 0, 2, 4 went to slot 0 (its 1st, 2nd, 3rd build), 1 and 3 to slot 1
+    assert [r[0][1] for r in res] == [1, 1, 2, 2, 3]
+    assert len({res[0][0][2], res[2][0][2], res[4][0][2]}) == 1 and res[0][0][2] != res[1][0][2]      # one worker thread per slot
+    assert [e for e in slots[0].log if e[0] == "add"] == [("add", [0], False), ("add", [2], False), ("add", [4], False)]
+    assert ("count", 3) in slots[1].log and ("count", 0) not in slots[0].log            # n_genomes = 0 means "not given"
+    assert all(s.closed for s in slots)
+    with pytest.raises(ValueError):
+        B.BuildPipeline(depth=0)
+    with pytest.raises(ValueError):
+        B.BuildPipeline(depth=2, streams=[1])
