@@ -1104,7 +1104,7 @@ __device__ __forceinline__ void agg_emit(const AggParams2& p, const AggTable& t,
             if (MODE == 3) {
                 // The words come from the sources' entries (random 16 / 24 / 40-byte reads out of L2).  Four sources at a
                 // time: all their references first, then all the loads, then the stores -- one dependent load at a time left
-                // the kernel waiting on the scoreboard for a third of its samples (profiles/r02_merge_*: aggregate 1.05 ->
+                // the kernel waiting on the scoreboard for a third of its samples (profiles/r02_merge_emit.txt: aggregate 1.05 ->
                 // 0.88 ms at 8 sources x 2 words; a variant that walked the word rows through a (source, word) table in
                 // shared memory, eight at a time, took 1.00 ms).
                 unsigned long long* const orow = p.out_words + o;
