@@ -27,9 +27,11 @@ thread_local std::string g_create_error;
 // NVTX range on the calling host thread: the stages of a build as a profiler sees them enqueued
 struct NvtxRange {
     explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
-    ~NvtxRange() { nvtxRangePop(); }
+    ~NvtxRange() { end(); }
+    void end() { if (open) { nvtxRangePop(); open = false; } }      // ranges are closed in the order they were opened
     NvtxRange(const NvtxRange&) = delete;
     NvtxRange& operator=(const NvtxRange&) = delete;
+    bool open = true;
 };
 
 struct DevBuf {
@@ -802,6 +804,7 @@ int run_job(grmkm_ctx* c, const Geo& geo, const Job& job, JobOut& out) {
             c->pre_groups = c->pass_groups; c->pre_pub_bytes = c->pass_pub_bytes;
         }
 
+        nv_front.end();
         NvtxRange nv_back("grmkm back: dedupe / expand / aggregate");
         // Dedupe -> expand -> aggregate run back to back without a host round trip.  The dedupe's entry list and the
         // expansion's bucket regions are sized from estimates; the one synchronisation after the aggregate reads what
